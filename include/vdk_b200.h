@@ -1,0 +1,119 @@
+/* vdk_b200.h — C ABI of libvdk_b200.so, the sm_100a implementation of DORAEMON's (wuji3/visiondk)
+ * embedding hot path.  The reference is pure Python and has no FFI of its own; each
+ * entry point below names the reference call site (file:line under /root/reference) whose arithmetic
+ * it replaces.  A maintainer binds these with ctypes (INTEGRATION.md shows the stubs).
+ *
+ * Conventions
+ *   - every pointer is a DEVICE pointer owned by the caller unless the name says `host`;
+ *   - `stream` is a cudaStream_t passed as void*; calls enqueue work and return without synchronising;
+ *   - nothing is allocated behind the caller: scratch comes in as `workspace` (+ a *_workspace_bytes query);
+ *   - return value: VDK_OK (0) or a negative VDK_ERR_*; vdk_last_error_string() explains the last failure
+ *     on the calling thread.  There is no CPU fallback: without a CUDA device every compute call fails.
+ */
+#ifndef VDK_B200_H_
+#define VDK_B200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define VDK_OK 0
+#define VDK_ERR_INVALID (-1)   /* bad argument / unsupported shape */
+#define VDK_ERR_CUDA (-2)      /* a CUDA runtime or driver call failed */
+#define VDK_ERR_WORKSPACE (-3) /* workspace too small */
+#define VDK_ERR_OVERFLOW (-4)  /* a candidate buffer overflowed; caller must take the wide path */
+
+/* ---- library ------------------------------------------------------------------------------- */
+int vdk_version(void);                    /* major*10000 + minor*100 + patch */
+const char* vdk_last_error_string(void);  /* thread-local, never NULL */
+/* 0 when a device of compute capability 10.x is present and usable, else VDK_ERR_CUDA. */
+int vdk_device_check(void);
+
+/* ---- dense contraction: D = epilogue(A . B^T) ---------------------------------------------- */
+/* Replaces the cuBLAS/cuDNN GEMMs inside timm's ConvNeXt/ViT blocks that models/faceX/backbone/
+ * timm_wrapper.py:52 runs (pointwise Linear layers, patchify convs as GEMMs) and the neck Linear
+ * (timm_wrapper.py:36).  A is [M,K] row-major (pitch lda), B is [N,K] row-major (pitch ldb) — the
+ * layout of nn.Linear.weight — both 16-bit (bf16 or fp16); accumulation is fp32 on tcgen05/TMEM. */
+#define VDK_DTYPE_BF16 0
+#define VDK_DTYPE_FP16 1
+#define VDK_DTYPE_FP32 2
+
+#define VDK_EPI_NONE 0           /* D = acc (+ bias[n]) */
+#define VDK_EPI_GELU 1           /* D = gelu_erf(acc + bias[n]) */
+#define VDK_EPI_SCALE_RESIDUAL 2 /* D = residual[m,n] + gamma[n] * (acc + bias[n])  (ConvNeXt layer-scale) */
+
+int vdk_gemm_tn(const void* A, const void* B, void* D, int M, int N, int K, int lda, int ldb, int ldd,
+                int in_dtype,          /* VDK_DTYPE_BF16 | VDK_DTYPE_FP16 */
+                int out_dtype,         /* VDK_DTYPE_BF16 | VDK_DTYPE_FP16 | VDK_DTYPE_FP32 */
+                int epilogue,          /* VDK_EPI_* */
+                const float* bias,     /* [N] or NULL */
+                const float* gamma,    /* [N], VDK_EPI_SCALE_RESIDUAL only */
+                const void* residual,  /* [M,ldr] same dtype as D, VDK_EPI_SCALE_RESIDUAL only */
+                int ldr, void* stream);
+
+/* ---- retrieval: L2-normalise -> inner product -> top-k -------------------------------------- */
+/* Replaces F.normalize at models/faceX/face_model.py:139, faiss index.add at
+ * engine/cbir/evaluation.py:166-168 and faiss index.search at engine/cbir/evaluation.py:193
+ * (cbir_eval.py:95,116).  Semantics: exact inner-product top-k; scores are the canonical fp32 scores
+ * defined in oracle/retrieval.py (fixed-order fp64 accumulation), order = (score desc, id asc),
+ * ids are int64, missing entries are id -1 / score -inf like faiss. */
+
+/* Row preparation.  x: fp32 [n, dim] (pitch dim).  If `normalize`: xn = x / max(||x||, 1e-12) (F.normalize),
+ * else xn = x.  Writes xn (fp32), xh = fp16(xn), row_norm[n] = ||xn||, row_err[n] >= ||xn - xh||.
+ * Any of xn / row_norm may alias NULL to skip that output; xn may alias x (in place). */
+int vdk_rows_prepare(const float* x, int64_t n, int dim, int normalize, float* xn, void* xh, float* row_norm,
+                     float* row_err, void* stream);
+
+typedef struct vdk_topk_plan {
+  int64_t n_query;       /* rows of the query block */
+  int64_t n_gallery;     /* rows of the (local shard of the) gallery */
+  int dim;               /* embedding width, multiple of 64, <= 512 */
+  int k;                 /* neighbours wanted, 1..1024 */
+  int cand_capacity;     /* per-query candidate slots (power of two, >= 2k) */
+  int n_stages;          /* gallery is scanned in n_stages ranges; thresholds tighten between them */
+  int64_t stage_end[8];  /* exclusive end row of each stage (last == n_gallery) */
+} vdk_topk_plan;
+
+/* Fills stage boundaries / capacity for the given problem; returns VDK_OK. */
+int vdk_topk_plan_default(vdk_topk_plan* plan, int64_t n_query, int64_t n_gallery, int dim, int k);
+/* Scratch bytes vdk_ip_topk needs for this plan. */
+size_t vdk_topk_workspace_bytes(const vdk_topk_plan* plan);
+
+/* Exact inner-product top-k of q against g.
+ *   q32/g32  : fp32 rows (what the scores are defined on), qh/gh: their fp16 copies from vdk_rows_prepare
+ *   q_norm/q_err : per-query ||q|| and fp16 rounding-error norm; g_norm_max/g_err_max: device scalars, the
+ *                  maxima over the gallery (vdk_reduce_max) — they bound the tensor-core score error.
+ *   id_offset : added to every returned id (shard offset under multi-GPU sharding).
+ *   out_scores: fp32 [n_query,k], out_ids: int64 [n_query,k].
+ *   status    : device int32[4]: {overflow_rows, max_candidates_seen, rerank_rows_max, reserved}. */
+int vdk_ip_topk(const vdk_topk_plan* plan, const float* q32, const void* qh, const float* q_norm,
+                const float* q_err, const float* g32, const void* gh, const float* g_norm_max,
+                const float* g_err_max, int64_t id_offset, float* out_scores, int64_t* out_ids, int32_t* status,
+                void* workspace, size_t workspace_bytes, void* stream);
+
+/* Measurement hook: launches ONLY the score/filter kernel of vdk_ip_topk for gallery rows [lo, hi), reusing the
+ * thresholds a previous vdk_ip_topk left in `workspace` (dense != 0: the threshold-free first-range variant).
+ * bench.py brackets this call with CUDA events to time the dominant kernel in isolation. */
+int vdk_score_range(const vdk_topk_plan* plan, const void* qh, const void* gh, int64_t lo, int64_t hi, int dense,
+                    void* workspace, size_t workspace_bytes, void* stream);
+
+/* Max over a float vector into a device scalar (gallery-wide error/norm bounds). */
+int vdk_reduce_max(const float* x, int64_t n, float* out, void* stream);
+
+/* Merge `n_lists` per-shard top-k lists (each [n_query,k], already ordered) into the global top-k with
+ * the same (score desc, id asc) rule.  Replaces faiss' IndexShards merge (the reference uses replicas,
+ * engine/cbir/evaluation.py:159-162; sharding is BASELINE config 4). */
+int vdk_topk_merge(const float* scores, const int64_t* ids, int n_lists, int64_t n_query, int k, float* out_scores,
+                   int64_t* out_ids, void* stream);
+
+/* Brute-force canonical scores for verification at full size: out[i] = canonical_score(q[qi[i]], g[gi[i]]). */
+int vdk_ip_exact_pairs(const float* q32, const float* g32, int dim, const int64_t* qi, const int64_t* gi, int64_t n,
+                       float* out, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* VDK_B200_H_ */

@@ -1,0 +1,176 @@
+"""GPU parity of the retrieval path (rows_prepare -> score_filter -> select/re-rank) against oracle/retrieval.py.
+
+Bar: ids AND scores bit-exact (integer/index work; scores are defined canonically in the oracle).
+"""
+import numpy as np
+import pytest
+import torch
+
+from oracle import retrieval as R
+from visiondk_b200 import _lib
+from visiondk_b200.retrieval import FlatIPIndex, PreparedRows, merge_topk, exact_pair_scores
+
+pytestmark = pytest.mark.gpu
+
+
+def unit_rows(n, dim, seed):
+    rng = np.random.default_rng(seed)
+    return R.l2_normalize(rng.standard_normal((n, dim)).astype(np.float32))
+
+
+def assert_same(got_s, got_i, ref_s, ref_i, what):
+    got_s, got_i = np.asarray(got_s), np.asarray(got_i)
+    bad_rows = np.nonzero((got_i != ref_i).any(axis=1))[0]
+    msg = ""
+    if len(bad_rows):
+        r = bad_rows[0]
+        c = np.nonzero(got_i[r] != ref_i[r])[0][:5]
+        msg = (f"{what}: {len(bad_rows)}/{got_i.shape[0]} rows differ; row {r} cols {c.tolist()} got ids "
+               f"{got_i[r, c].tolist()} ref ids {ref_i[r, c].tolist()} got s {got_s[r, c].tolist()} ref s {ref_s[r, c].tolist()}")
+    assert len(bad_rows) == 0, msg
+    assert np.array_equal(got_s.view(np.uint32), ref_s.view(np.uint32)), f"{what}: ids equal but scores differ in bits"
+
+
+def test_rows_prepare_matches_oracle(lib):
+    rng = np.random.default_rng(0)
+    x = (rng.standard_normal((777, 512)) * rng.uniform(0.01, 30, (777, 1))).astype(np.float32)
+    x[5] = 0.0  # zero row: eps clamp
+    p = PreparedRows(torch.from_numpy(x).cuda(), normalize=True)
+    ref = R.l2_normalize(x)
+    got = p.x32.cpu().numpy()
+    assert np.array_equal(got.view(np.uint32), ref.view(np.uint32))
+    xh = p.xh.cpu().numpy()
+    assert np.array_equal(xh.view(np.uint16), ref.astype(np.float16).view(np.uint16))
+    err = np.linalg.norm(ref.astype(np.float64) - xh.astype(np.float64), axis=1)
+    assert (p.err.cpu().numpy() >= err).all() and (p.err.cpu().numpy() <= err * 1.001 + 1e-20).all()
+    nrm = np.linalg.norm(ref.astype(np.float64), axis=1)
+    assert (p.norm.cpu().numpy() >= nrm * 0.999999).all()
+
+
+@pytest.mark.parametrize("nq,ng,dim,k", [(50, 3000, 512, 10), (1, 1, 64, 1), (3, 5, 128, 10), (130, 4096, 256, 100),
+                                         (257, 700, 512, 100), (17, 300, 320, 7)])
+def test_topk_single_range_bit_exact(lib, nq, ng, dim, k):
+    q, g = unit_rows(nq, dim, 10 + nq), unit_rows(ng, dim, 20 + ng)
+    idx = FlatIPIndex(dim, "cuda")
+    idx.train(g)
+    idx.add(g)
+    s, i = idx.search(q, k)
+    info = idx.check_status()
+    ref_s, ref_i = R.flat_ip_search(q, g, k)
+    assert_same(s, i, ref_s, ref_i, f"single-range nq={nq} ng={ng} dim={dim} k={k} {info}")
+
+
+@pytest.mark.parametrize("nq,ng,dim,k", [(300, 40000, 512, 100), (129, 70001, 128, 10), (64, 300000, 64, 1)])
+def test_topk_multi_range_bit_exact(lib, nq, ng, dim, k):
+    q, g = unit_rows(nq, dim, 1), unit_rows(ng, dim, 2)
+    idx = FlatIPIndex(dim, "cuda")
+    idx.add(g)
+    s, i = idx.search(q, k)
+    info = idx.check_status()
+    ref_s, ref_i = R.flat_ip_search_candidates(q, g, k)
+    assert_same(s, i, ref_s, ref_i, f"multi-range nq={nq} ng={ng} dim={dim} k={k} {info}")
+
+
+def test_topk_planted_identities_and_normalize(lib):
+    g, q, labels = R.synthetic_gallery(n_ids=300, per_id=100, dim=512, seed=2)
+    # feed UN-normalised rows and let the index normalise (F.normalize fused in)
+    rng = np.random.default_rng(9)
+    g_raw = g * rng.uniform(0.5, 4.0, (g.shape[0], 1)).astype(np.float32)
+    q_raw = q * rng.uniform(0.5, 4.0, (q.shape[0], 1)).astype(np.float32)
+    idx = FlatIPIndex(512, "cuda", normalize=True)
+    idx.add(g_raw)
+    s, i = idx.search(q_raw, 100)
+    idx.check_status()
+    ref_s, ref_i = R.flat_ip_search_candidates(R.l2_normalize(q_raw), R.l2_normalize(g_raw), 100)
+    assert_same(s, i, ref_s, ref_i, "planted identities")
+    recall = np.mean([(labels[i[r]] == r).mean() for r in range(q.shape[0])])
+    assert recall > 0.99, f"planted positives not retrieved: recall@100={recall}"
+
+
+def test_topk_tie_rule_and_padding(lib):
+    base = unit_rows(40, 128, 3)
+    g = np.concatenate([base, base, base[:7]], axis=0)  # exact duplicates -> exact score ties
+    q = unit_rows(9, 128, 4)
+    idx = FlatIPIndex(128, "cuda")
+    idx.add(g)
+    s, i = idx.search(q, 100)  # k > ntotal: padded with (-FLT_MAX, -1)
+    idx.check_status()
+    ref_s, ref_i = R.flat_ip_search(q, g, 100)
+    assert_same(s, i, ref_s, ref_i, "ties + padding")
+    assert (i[:, 87:] == -1).all() and (s[:, 87:] == np.float32(-3.4028234663852886e38)).all()
+
+
+def test_topk_empty_inputs(lib):
+    idx = FlatIPIndex(64, "cuda")
+    s, i = idx.search(unit_rows(3, 64, 1), 5)  # empty gallery
+    assert (i == -1).all() and s.shape == (3, 5)
+    idx.add(unit_rows(10, 64, 2))
+    s, i = idx.search(np.zeros((0, 64), np.float32), 5)  # empty query block
+    assert s.shape == (0, 5) and i.shape == (0, 5)
+
+
+def test_topk_sharded_merge_equals_unsharded(lib):
+    nq, ng, dim, k = 200, 50000, 512, 100
+    q, g = unit_rows(nq, dim, 5), unit_rows(ng, dim, 6)
+    whole = FlatIPIndex(dim, "cuda")
+    whole.add(g)
+    ws, wi = whole.search_device(torch.from_numpy(q).cuda(), k)
+    whole.check_status()
+    bounds = [0, 11000, 11001, 30000, ng]
+    ss, ii = [], []
+    for a, b in zip(bounds[:-1], bounds[1:]):
+        shard = FlatIPIndex(dim, "cuda", id_offset=a)
+        shard.add(g[a:b])
+        s_, i_ = shard.search_device(torch.from_numpy(q).cuda(), k)
+        shard.check_status()
+        ss.append(s_)
+        ii.append(i_)
+    ms, mi = merge_topk(torch.stack(ss), torch.stack(ii), k)
+    assert torch.equal(mi, wi) and torch.equal(ms.view(torch.int32), ws.view(torch.int32))
+    ref_s, ref_i = R.merge_topk([s_.cpu().numpy() for s_ in ss], [i_.cpu().numpy() for i_ in ii], k)
+    assert np.array_equal(mi.cpu().numpy(), ref_i)
+
+
+def test_tensor_core_error_within_bound(lib):
+    """The admission slack 2*eps relies on |fp16 tensor-core score - canonical score| <= eps; measure it."""
+    nq, ng, dim = 256, 8192, 512
+    q, g = unit_rows(nq, dim, 7), unit_rows(ng, dim, 8)
+    qp = PreparedRows(torch.from_numpy(q).cuda(), False)
+    gp = PreparedRows(torch.from_numpy(g).cuda(), False)
+    approx = torch.empty((nq, ng), dtype=torch.float32, device="cuda")
+    rc = lib.vdk_gemm_tn(qp.xh.data_ptr(), gp.xh.data_ptr(), approx.data_ptr(), nq, ng, dim, dim, dim, ng,
+                         _lib.DTYPE_FP16, _lib.DTYPE_FP32, _lib.EPI_NONE, 0, 0, 0, 0, _lib.stream_ptr())
+    _lib.check(rc, "vdk_gemm_tn")
+    exact = (torch.from_numpy(q).cuda().double() @ torch.from_numpy(g).cuda().double().t())
+    err = (approx.double() - exact).abs().max().item()
+    gn, ge = gp.maxima()
+    eps = (qp.err * gn + (qp.norm + qp.err) * ge + 2.0 ** -13 * (qp.norm + qp.err) * (gn + ge)).min().item()
+    assert err <= eps, f"measured tensor-core score error {err:.3e} exceeds the bound {eps:.3e}"
+    assert err >= 1e-6  # sanity: fp16 rounding really is in play
+
+
+@pytest.mark.slow
+def test_topk_full_size_properties(lib):
+    """BASELINE config 4 at full size (10k x 1M x 512, k=100): size-independent properties + sampled brute force."""
+    nq, ng, dim, k = 10000, 1000000, 512, 100
+    gen = torch.Generator(device="cuda").manual_seed(5)
+    g = torch.nn.functional.normalize(torch.randn(ng, dim, device="cuda", generator=gen))
+    q = torch.nn.functional.normalize(torch.randn(nq, dim, device="cuda", generator=gen))
+    idx = FlatIPIndex(dim, "cuda")
+    idx.add(g)
+    s, i = idx.search_device(q, k)
+    info = idx.check_status()
+    # sortedness under (score desc, id asc)
+    ds = s[:, 1:] - s[:, :-1]
+    assert (ds <= 0).all()
+    assert ((ds < 0) | (i[:, 1:] > i[:, :-1])).all()
+    assert (i >= 0).all() and (i < ng).all()
+    # every returned score is the canonical score of its pair
+    qi = torch.arange(nq, device="cuda").repeat_interleave(k)
+    assert torch.equal(exact_pair_scores(q, g, qi, i.reshape(-1)).view(torch.int32), s.reshape(-1).view(torch.int32))
+    # sampled brute force in fp64
+    rows = torch.arange(0, nq, 499, device="cuda")
+    full = q[rows].double() @ g.double().t()
+    top = full.topk(k, dim=1).indices
+    agree = (top == i[rows]).float().mean().item()
+    assert agree > 0.999, f"sampled brute-force agreement {agree} ({info})"

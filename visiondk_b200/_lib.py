@@ -1,0 +1,95 @@
+"""ctypes binding of libvdk_b200.so — the only way Python reaches the CUDA kernels.
+
+There is no CPU fallback anywhere in this package: if the library is missing it must be built
+(`python -m visiondk_b200.build`), and every compute entry point raises RuntimeError when the C ABI
+returns a non-zero status (e.g. no sm_100 device).
+"""
+from __future__ import annotations
+
+import ctypes as C
+from pathlib import Path
+
+_LIB_PATH = Path(__file__).resolve().parent / "lib" / "libvdk_b200.so"
+
+VDK_OK = 0
+VDK_ERR_INVALID, VDK_ERR_CUDA, VDK_ERR_WORKSPACE, VDK_ERR_OVERFLOW = -1, -2, -3, -4
+DTYPE_BF16, DTYPE_FP16, DTYPE_FP32 = 0, 1, 2
+EPI_NONE, EPI_GELU, EPI_SCALE_RESIDUAL = 0, 1, 2
+
+
+class TopkPlan(C.Structure):
+    _fields_ = [
+        ("n_query", C.c_int64),
+        ("n_gallery", C.c_int64),
+        ("dim", C.c_int),
+        ("k", C.c_int),
+        ("cand_capacity", C.c_int),
+        ("n_stages", C.c_int),
+        ("stage_end", C.c_int64 * 8),
+    ]
+
+
+_p, _i, _i64, _sz = C.c_void_p, C.c_int, C.c_int64, C.c_size_t
+
+# name -> (restype, argtypes); must list every symbol include/vdk_b200.h declares (tests check this).
+SIGNATURES = {
+    "vdk_version": (_i, []),
+    "vdk_last_error_string": (C.c_char_p, []),
+    "vdk_device_check": (_i, []),
+    "vdk_gemm_tn": (_i, [_p, _p, _p, _i, _i, _i, _i, _i, _i, _i, _i, _i, _p, _p, _p, _i, _p]),
+    "vdk_rows_prepare": (_i, [_p, _i64, _i, _i, _p, _p, _p, _p, _p]),
+    "vdk_topk_plan_default": (_i, [C.POINTER(TopkPlan), _i64, _i64, _i, _i]),
+    "vdk_topk_workspace_bytes": (_sz, [C.POINTER(TopkPlan)]),
+    "vdk_ip_topk": (_i, [C.POINTER(TopkPlan), _p, _p, _p, _p, _p, _p, _p, _p, _i64, _p, _p, _p, _p, _sz, _p]),
+    "vdk_score_range": (_i, [C.POINTER(TopkPlan), _p, _p, _i64, _i64, _i, _p, _sz, _p]),
+    "vdk_reduce_max": (_i, [_p, _i64, _p, _p]),
+    "vdk_topk_merge": (_i, [_p, _p, _i, _i64, _i, _p, _p, _p]),
+    "vdk_ip_exact_pairs": (_i, [_p, _p, _i, _p, _p, _i64, _p, _p]),
+}
+
+_lib = None
+
+
+def lib_path() -> Path:
+    return _LIB_PATH
+
+
+def load() -> C.CDLL:
+    """Loads libvdk_b200.so and types its symbols.  Raises if it has not been built."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not _LIB_PATH.exists():
+        raise RuntimeError(
+            f"{_LIB_PATH} is missing: build it with `python -m visiondk_b200.build` "
+            "(there is no CPU fallback for the hot path)")
+    lib = C.CDLL(str(_LIB_PATH))
+    for name, (res, args) in SIGNATURES.items():
+        fn = getattr(lib, name)
+        fn.restype = res
+        fn.argtypes = args
+    _lib = lib
+    return lib
+
+
+def last_error() -> str:
+    return load().vdk_last_error_string().decode("utf-8", "replace")
+
+
+def check(rc: int, what: str) -> None:
+    if rc != VDK_OK:
+        raise RuntimeError(f"{what} failed (status {rc}): {last_error()}")
+
+
+def require_device() -> None:
+    check(load().vdk_device_check(), "vdk_device_check")
+
+
+def ptr(t) -> int:
+    """Device pointer of a torch tensor (None -> NULL)."""
+    return 0 if t is None else t.data_ptr()
+
+
+def stream_ptr() -> int:
+    import torch
+    return torch.cuda.current_stream().cuda_stream

@@ -1,0 +1,313 @@
+// gemm.cu — D = epilogue(A . B^T) on tcgen05 tensor cores, operands staged by TMA, accumulators in TMEM.
+//
+// Replaces the library GEMMs behind timm's ConvNeXt/ViT Linear layers and patchify convolutions that
+// models/faceX/backbone/timm_wrapper.py:52 runs, and the neck Linear of timm_wrapper.py:36.
+//
+// One persistent CTA per SM, 192 threads:
+//   warp 0      : TMA producer   (A tile 128x64, B tile BNx64 per stage, 128-byte swizzle)
+//   warp 1      : TMEM allocator + single-thread tcgen05.mma issuer (UMMA 128 x BN x 16, fp32 accumulate)
+//   warps 2..5  : epilogue       (tcgen05.ld -> bias / GELU / layer-scale+residual -> 16-byte global stores)
+// Two accumulator stages in TMEM (2 x BN columns) let the epilogue of tile i overlap the MMAs of tile i+1.
+#include "vdk_host.h"
+#include "vdk_ptx.cuh"
+
+namespace vdk {
+
+constexpr int kBM = 128;
+constexpr int kBK = 64;  // 64 x 16-bit = one 128-byte swizzle row
+constexpr int kGemmThreads = 192;
+
+struct GemmParams {
+  int M, N, K;
+  void* D;
+  int ldd;
+  const float* bias;
+  const float* gamma;
+  const void* residual;
+  int ldr;
+  int out_dtype;
+  int epilogue;
+};
+
+template <int BN>
+struct GemmCfg {
+  static constexpr int kStageA = kBM * kBK * 2;
+  static constexpr int kStageB = BN * kBK * 2;
+  static constexpr int kStageBytes = kStageA + kStageB;
+  static constexpr int kStages = (BN == 256) ? 4 : 6;
+  static constexpr int kTmemCols = 2 * BN;
+  // stages + barriers (full, empty: kStages each; tmem_full, tmem_empty: 2 each) + tmem ptr + 1 KB align slack
+  static constexpr int kSmemBytes = kStages * kStageBytes + (2 * kStages + 4) * 8 + 16 + 1024;
+};
+
+__device__ __forceinline__ float gelu_erf(float x) { return 0.5f * x * (1.0f + erff(x * 0.70710678118654752440f)); }
+
+__device__ __forceinline__ uint32_t pack2(float a, float b, int out_dtype) {
+  if (out_dtype == VDK_DTYPE_BF16) {
+    __nv_bfloat162 h = __floats2bfloat162_rn(a, b);
+    return *reinterpret_cast<uint32_t*>(&h);
+  } else {
+    __half2 h = __floats2half2_rn(a, b);
+    return *reinterpret_cast<uint32_t*>(&h);
+  }
+}
+__device__ __forceinline__ float2 unpack2(uint32_t u, int dtype) {
+  if (dtype == VDK_DTYPE_BF16) {
+    __nv_bfloat162 h = *reinterpret_cast<__nv_bfloat162*>(&u);
+    return __bfloat1622float2(h);
+  } else {
+    __half2 h = *reinterpret_cast<__half2*>(&u);
+    return __half22float2(h);
+  }
+}
+
+template <int BN, bool kBf16>
+__global__ void __launch_bounds__(kGemmThreads, 1)
+gemm_tn_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b,
+               const GemmParams p) {
+  using Cfg = GemmCfg<BN>;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + Cfg::kStages * Cfg::kStageBytes);
+  uint64_t* empty_bar = full_bar + Cfg::kStages;
+  uint64_t* tmem_full = empty_bar + Cfg::kStages;
+  uint64_t* tmem_empty = tmem_full + 2;
+  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(tmem_empty + 2);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+
+  const int num_m = (p.M + kBM - 1) / kBM;
+  const int num_n = (p.N + BN - 1) / BN;
+  const int num_tiles = num_m * num_n;
+  const int num_kb = (p.K + kBK - 1) / kBK;
+
+  if (warp == 0 && lane == 0) {
+    prefetch_tensormap(&map_a);
+    prefetch_tensormap(&map_b);
+    for (int i = 0; i < Cfg::kStages; ++i) {
+      mbar_init(&full_bar[i], 1);
+      mbar_init(&empty_bar[i], 1);
+    }
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(&tmem_full[i], 1);
+      mbar_init(&tmem_empty[i], 128);
+    }
+    fence_mbar_init();
+  }
+  if (warp == 1) tmem_alloc<Cfg::kTmemCols>(tmem_ptr);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_ptr;
+
+  if (warp == 0) {
+    // ===================== TMA producer =====================
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+        const int m0 = (tile / num_n) * kBM;
+        const int n0 = (tile % num_n) * BN;
+        for (int kb = 0; kb < num_kb; ++kb) {
+          mbar_wait(&empty_bar[stage], phase ^ 1);
+          uint8_t* sa = smem + stage * Cfg::kStageBytes;
+          uint8_t* sb = sa + Cfg::kStageA;
+          mbar_arrive_expect_tx(&full_bar[stage], Cfg::kStageBytes);
+          tma_load_2d(sa, &map_a, &full_bar[stage], kb * kBK, m0, kEvictNormal);
+          tma_load_2d(sb, &map_b, &full_bar[stage], kb * kBK, n0, kEvictLast);
+          if (++stage == Cfg::kStages) {
+            stage = 0;
+            phase ^= 1;
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ===================== MMA issuer =====================
+    if (lane == 0) {
+      constexpr uint32_t idesc = umma_idesc_f16<kBf16>(kBM, BN);
+      int stage = 0;
+      uint32_t phase = 0;
+      int it = 0;
+      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
+        const int acc = it & 1;
+        const uint32_t acc_phase = (it >> 1) & 1;
+        mbar_wait(&tmem_empty[acc], acc_phase ^ 1);
+        tc_fence_after();
+        const uint32_t tmem_d = tmem_base + acc * BN;
+        for (int kb = 0; kb < num_kb; ++kb) {
+          mbar_wait(&full_bar[stage], phase);
+          tc_fence_after();
+          const uint32_t sa = smem_u32(smem + stage * Cfg::kStageBytes);
+          const uint32_t sb = sa + Cfg::kStageA;
+          const uint64_t da = umma_desc_k_sw128(sa);
+          const uint64_t db = umma_desc_k_sw128(sb);
+#pragma unroll
+          for (int k = 0; k < kBK / 16; ++k) {
+            // advance 16 elements (32 bytes) along K inside the 128-byte swizzle row: +2 in 16-byte units
+            umma_f16_ss(tmem_d, da + 2 * k, db + 2 * k, idesc, (kb | k) != 0 ? 1u : 0u);
+          }
+          umma_commit(&empty_bar[stage]);  // smem slot reusable once these MMAs retire
+          if (++stage == Cfg::kStages) {
+            stage = 0;
+            phase ^= 1;
+          }
+        }
+        umma_commit(&tmem_full[acc]);  // accumulator complete -> epilogue
+      }
+    }
+  } else {
+    // ===================== epilogue =====================
+    const int lane_base = (warp & 3) * 32;  // TMEM lanes this warp may touch
+    int it = 0;
+    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
+      const int acc = it & 1;
+      const uint32_t acc_phase = (it >> 1) & 1;
+      const int m0 = (tile / num_n) * kBM;
+      const int n0 = (tile % num_n) * BN;
+      const int row = m0 + lane_base + lane;
+      mbar_wait(&tmem_full[acc], acc_phase);
+      tc_fence_after();
+#pragma unroll 1
+      for (int c = 0; c < BN / 32; ++c) {
+        uint32_t r[32];
+        tmem_ld_32x32b_x32(tmem_base + (static_cast<uint32_t>(lane_base) << 16) + acc * BN + c * 32, r);
+        tmem_ld_wait();
+        const int col0 = n0 + c * 32;
+        if (row < p.M && col0 < p.N) {
+          float v[32];
+#pragma unroll
+          for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]);
+          const int ncols = min(32, p.N - col0);  // multiple of 8 (N % 8 == 0 is required)
+          if (p.bias != nullptr) {
+#pragma unroll
+            for (int j = 0; j < 32; j += 4) {
+              if (j < ncols) {
+                const float4 b = __ldg(reinterpret_cast<const float4*>(p.bias + col0 + j));
+                v[j] += b.x; v[j + 1] += b.y; v[j + 2] += b.z; v[j + 3] += b.w;
+              }
+            }
+          }
+          if (p.epilogue == VDK_EPI_GELU) {
+#pragma unroll
+            for (int j = 0; j < 32; ++j) v[j] = gelu_erf(v[j]);
+          } else if (p.epilogue == VDK_EPI_SCALE_RESIDUAL) {
+#pragma unroll
+            for (int j = 0; j < 32; j += 4) {
+              if (j < ncols) {
+                const float4 g = __ldg(reinterpret_cast<const float4*>(p.gamma + col0 + j));
+                v[j] *= g.x; v[j + 1] *= g.y; v[j + 2] *= g.z; v[j + 3] *= g.w;
+              }
+            }
+            if (p.out_dtype == VDK_DTYPE_FP32) {
+              const float* res = reinterpret_cast<const float*>(p.residual) + static_cast<size_t>(row) * p.ldr + col0;
+#pragma unroll
+              for (int j = 0; j < 32; j += 4) {
+                if (j < ncols) {
+                  const float4 t = *reinterpret_cast<const float4*>(res + j);
+                  v[j] += t.x; v[j + 1] += t.y; v[j + 2] += t.z; v[j + 3] += t.w;
+                }
+              }
+            } else {
+              const uint16_t* res = reinterpret_cast<const uint16_t*>(p.residual) + static_cast<size_t>(row) * p.ldr + col0;
+#pragma unroll
+              for (int j = 0; j < 32; j += 8) {
+                if (j < ncols) {
+                  const uint4 t = *reinterpret_cast<const uint4*>(res + j);
+                  const float2 a0 = unpack2(t.x, p.out_dtype), a1 = unpack2(t.y, p.out_dtype);
+                  const float2 a2 = unpack2(t.z, p.out_dtype), a3 = unpack2(t.w, p.out_dtype);
+                  v[j] += a0.x; v[j + 1] += a0.y; v[j + 2] += a1.x; v[j + 3] += a1.y;
+                  v[j + 4] += a2.x; v[j + 5] += a2.y; v[j + 6] += a3.x; v[j + 7] += a3.y;
+                }
+              }
+            }
+          }
+          if (p.out_dtype == VDK_DTYPE_FP32) {
+            float* out = reinterpret_cast<float*>(p.D) + static_cast<size_t>(row) * p.ldd + col0;
+#pragma unroll
+            for (int j = 0; j < 32; j += 4)
+              if (j < ncols) *reinterpret_cast<float4*>(out + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
+          } else {
+            uint16_t* out = reinterpret_cast<uint16_t*>(p.D) + static_cast<size_t>(row) * p.ldd + col0;
+#pragma unroll
+            for (int j = 0; j < 32; j += 8) {
+              if (j < ncols) {
+                uint4 t;
+                t.x = pack2(v[j], v[j + 1], p.out_dtype);
+                t.y = pack2(v[j + 2], v[j + 3], p.out_dtype);
+                t.z = pack2(v[j + 4], v[j + 5], p.out_dtype);
+                t.w = pack2(v[j + 6], v[j + 7], p.out_dtype);
+                *reinterpret_cast<uint4*>(out + j) = t;
+              }
+            }
+          }
+        }
+      }
+      tc_fence_before();
+      mbar_arrive(&tmem_empty[acc]);
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc<Cfg::kTmemCols>(tmem_base);
+  }
+}
+
+template <int BN, bool kBf16>
+static int launch_gemm(const CUtensorMap& ma, const CUtensorMap& mb, const GemmParams& p, cudaStream_t stream) {
+  using Cfg = GemmCfg<BN>;
+  auto kern = gemm_tn_kernel<BN, kBf16>;
+  static bool attr_set = false;  // per (BN, dtype) instantiation
+  if (!attr_set) {
+    VDK_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes));
+    attr_set = true;
+  }
+  const int num_tiles = ((p.M + kBM - 1) / kBM) * ((p.N + BN - 1) / BN);
+  const int grid = num_tiles < sm_count() ? num_tiles : sm_count();
+  kern<<<grid, kGemmThreads, Cfg::kSmemBytes, stream>>>(ma, mb, p);
+  VDK_CUDA_OK(cudaGetLastError());
+  return VDK_OK;
+}
+
+}  // namespace vdk
+
+extern "C" int vdk_gemm_tn(const void* A, const void* B, void* D, int M, int N, int K, int lda, int ldb, int ldd,
+                           int in_dtype, int out_dtype, int epilogue, const float* bias, const float* gamma,
+                           const void* residual, int ldr, void* stream) {
+  using namespace vdk;
+  VDK_REQUIRE(A && B && D, "vdk_gemm_tn: null operand");
+  VDK_REQUIRE(M > 0 && N > 0 && K > 0, "vdk_gemm_tn: empty problem M=%d N=%d K=%d", M, N, K);
+  VDK_REQUIRE(in_dtype == VDK_DTYPE_BF16 || in_dtype == VDK_DTYPE_FP16, "vdk_gemm_tn: in_dtype must be bf16/fp16");
+  VDK_REQUIRE(out_dtype >= VDK_DTYPE_BF16 && out_dtype <= VDK_DTYPE_FP32, "vdk_gemm_tn: bad out_dtype");
+  VDK_REQUIRE(N % 8 == 0 && K % 8 == 0, "vdk_gemm_tn: N and K must be multiples of 8 (N=%d K=%d)", N, K);
+  VDK_REQUIRE(lda >= K && ldb >= K && ldd >= N && lda % 8 == 0 && ldb % 8 == 0, "vdk_gemm_tn: bad pitches");
+  VDK_REQUIRE(ldd % (out_dtype == VDK_DTYPE_FP32 ? 4 : 8) == 0, "vdk_gemm_tn: ldd must keep rows 16-byte aligned");
+  VDK_REQUIRE((reinterpret_cast<uintptr_t>(D) & 15) == 0, "vdk_gemm_tn: D must be 16-byte aligned");
+  VDK_REQUIRE(epilogue >= VDK_EPI_NONE && epilogue <= VDK_EPI_SCALE_RESIDUAL, "vdk_gemm_tn: bad epilogue");
+  if (epilogue == VDK_EPI_SCALE_RESIDUAL) {
+    VDK_REQUIRE(gamma && residual, "vdk_gemm_tn: SCALE_RESIDUAL needs gamma and residual");
+    VDK_REQUIRE(ldr >= N && ldr % (out_dtype == VDK_DTYPE_FP32 ? 4 : 8) == 0 &&
+                    (reinterpret_cast<uintptr_t>(residual) & 15) == 0,
+                "vdk_gemm_tn: residual must be 16-byte aligned rows");
+  }
+  if (bias) VDK_REQUIRE((reinterpret_cast<uintptr_t>(bias) & 15) == 0, "vdk_gemm_tn: bias must be 16-byte aligned");
+  if (gamma) VDK_REQUIRE((reinterpret_cast<uintptr_t>(gamma) & 15) == 0, "vdk_gemm_tn: gamma must be 16-byte aligned");
+
+  // Narrow outputs use 128-column tiles (more tiles to balance over 148 SMs); wide ones 256.
+  const bool wide = (N % 256 == 0) || N > 512;
+  const int BN = wide ? 256 : 128;
+  CUtensorMap ma, mb;
+  int rc = make_tma_2d_16bit(&ma, A, (uint64_t)M, (uint64_t)K, (uint64_t)lda, kBM, kBK);
+  if (rc != VDK_OK) return rc;
+  rc = make_tma_2d_16bit(&mb, B, (uint64_t)N, (uint64_t)K, (uint64_t)ldb, BN, kBK);
+  if (rc != VDK_OK) return rc;
+  GemmParams p{M, N, K, D, ldd, bias, gamma, residual, ldr, out_dtype, epilogue};
+  cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
+  const bool bf = in_dtype == VDK_DTYPE_BF16;
+  if (wide) return bf ? launch_gemm<256, true>(ma, mb, p, s) : launch_gemm<256, false>(ma, mb, p, s);
+  return bf ? launch_gemm<128, true>(ma, mb, p, s) : launch_gemm<128, false>(ma, mb, p, s);
+}

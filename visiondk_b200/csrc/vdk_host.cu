@@ -1,0 +1,95 @@
+// vdk_host.cu — library-level C-ABI entry points and host helpers (error text, TMA descriptors).
+#include "vdk_host.h"
+
+#include <cstring>
+#include <mutex>
+
+namespace vdk {
+
+static thread_local char t_error[1024] = "";
+
+void set_error(const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(t_error, sizeof(t_error), fmt, ap);
+  va_end(ap);
+}
+
+int fail(int code, const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(t_error, sizeof(t_error), fmt, ap);
+  va_end(ap);
+  return code;
+}
+
+// cuTensorMapEncodeTiled is a driver API; it is resolved at run time through the runtime so the library
+// carries no link-time dependency on libcuda (it must load — not compute — on a machine without a driver).
+using EncodeTiledFn = CUresult (*)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                   const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                   CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static EncodeTiledFn encode_tiled_fn() {
+  static EncodeTiledFn fn = nullptr;
+  static std::once_flag once;
+  std::call_once(once, [] {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess &&
+        q == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<EncodeTiledFn>(p);
+  });
+  return fn;
+}
+
+int make_tma_2d_16bit(CUtensorMap* map, const void* base, uint64_t rows, uint64_t cols, uint64_t ld,
+                      uint32_t box_rows, uint32_t box_cols) {
+  EncodeTiledFn fn = encode_tiled_fn();
+  if (!fn) return fail(VDK_ERR_CUDA, "cuTensorMapEncodeTiled entry point unavailable (no CUDA driver?)");
+  if ((reinterpret_cast<uintptr_t>(base) & 15) != 0 || (ld * 2) % 16 != 0)
+    return fail(VDK_ERR_INVALID, "TMA operand must be 16-byte aligned with a 16-byte-multiple pitch (ld=%llu)",
+                (unsigned long long)ld);
+  if (box_cols * 2 != 128 || box_rows > 256)
+    return fail(VDK_ERR_INVALID, "TMA box must be 128 bytes wide and <= 256 rows");
+  cuuint64_t gdim[2] = {cols, rows};
+  cuuint64_t gstride[1] = {ld * 2};
+  cuuint32_t box[2] = {box_cols, box_rows};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_UINT16, 2, const_cast<void*>(base), gdim, gstride, box, estr,
+                  CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) return fail(VDK_ERR_CUDA, "cuTensorMapEncodeTiled failed with CUresult %d", (int)r);
+  return VDK_OK;
+}
+
+int sm_count() {
+  static int n = 0;
+  if (n == 0) {
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess) return 148;
+    if (cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n <= 0) n = 148;
+  }
+  return n;
+}
+
+}  // namespace vdk
+
+extern "C" {
+
+int vdk_version(void) { return 100; }  // 0.1.0
+
+const char* vdk_last_error_string(void) { return vdk::t_error; }
+
+int vdk_device_check(void) {
+  int n = 0;
+  cudaError_t e = cudaGetDeviceCount(&n);
+  if (e != cudaSuccess || n == 0)
+    return vdk::fail(VDK_ERR_CUDA, "no CUDA device: %s", e == cudaSuccess ? "device count is 0" : cudaGetErrorString(e));
+  int dev = 0, major = 0;
+  VDK_CUDA_OK(cudaGetDevice(&dev));
+  VDK_CUDA_OK(cudaDeviceGetAttribute(&major, cudaDevAttrComputeCapabilityMajor, dev));
+  if (major != 10) return vdk::fail(VDK_ERR_CUDA, "device compute capability %d.x; this library is sm_100a only", major);
+  return VDK_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,39 @@
+// vdk_host.h — host-side helpers shared by the translation units of libvdk_b200.so:
+// error reporting (vdk_last_error_string), TMA descriptor encoding, device properties.
+#pragma once
+#include <cuda.h>
+#include <cuda_runtime.h>
+#include <cstdint>
+#include <cstdio>
+#include <cstdarg>
+
+#include "../../include/vdk_b200.h"
+
+namespace vdk {
+
+// Thread-local last error text; every C-ABI entry point returns a VDK_* code and records why.
+void set_error(const char* fmt, ...);
+int fail(int code, const char* fmt, ...);
+
+// Checks a CUDA runtime call inside a C-ABI entry point.
+#define VDK_CUDA_OK(expr)                                                                          \
+  do {                                                                                             \
+    cudaError_t _e = (expr);                                                                       \
+    if (_e != cudaSuccess)                                                                         \
+      return ::vdk::fail(VDK_ERR_CUDA, "%s failed: %s (%s:%d)", #expr, cudaGetErrorString(_e), __FILE__, __LINE__); \
+  } while (0)
+
+#define VDK_REQUIRE(cond, ...)                                       \
+  do {                                                               \
+    if (!(cond)) return ::vdk::fail(VDK_ERR_INVALID, __VA_ARGS__);   \
+  } while (0)
+
+// Encodes a 2-D row-major tensor map for 16-bit elements: `rows` x `cols`, row pitch `ld` elements,
+// box = box_rows x box_cols, 128-byte swizzle (box_cols * 2 bytes must be 128).
+// Returns VDK_OK or an error code (driver entry point missing, bad alignment...).
+int make_tma_2d_16bit(CUtensorMap* map, const void* base, uint64_t rows, uint64_t cols, uint64_t ld,
+                      uint32_t box_rows, uint32_t box_cols);
+
+int sm_count();
+
+}  // namespace vdk

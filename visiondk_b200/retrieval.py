@@ -1,0 +1,198 @@
+"""Flat inner-product index on B200: the drop-in for the faiss objects of the reference's CBIR path.
+
+Seam (Seam 6): engine/cbir/evaluation.py:155-168 builds
+`faiss.index_factory(dim, "Flat", faiss.METRIC_INNER_PRODUCT)`, clones it to the GPUs, then calls
+`.train(x)`, `.add(x)` and (evaluation.py:193) `.search(x, k) -> (scores float32 [n,k] desc, ids int64 [n,k])`.
+FlatIPIndex answers exactly those calls with numpy in / numpy out, and adds `search_device` for callers that
+keep embeddings on the GPU (what extract -> search should do on a B200; the reference's per-batch
+`.cpu().numpy()` at face_model.py:140 is a host round trip the hot path does not need).
+
+Results are EXACT inner-product top-k under the canonical score / tie rule of oracle/retrieval.py
+(score desc, id asc), independent of how the gallery is sharded.  The fp16 tensor-core pass only nominates
+candidates; every returned score is re-computed from the fp32 rows.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from typing import Optional, Tuple
+
+import numpy as np
+import torch
+
+from . import _lib
+
+FLT_LOWEST = -3.4028234663852886e38
+
+
+def _dev(device) -> torch.device:
+    d = torch.device(device if device is not None else "cuda")
+    if d.type != "cuda":
+        raise RuntimeError("visiondk_b200 runs on CUDA (sm_100a) devices only; there is no CPU path")
+    return d
+
+
+class PreparedRows:
+    """fp32 rows + fp16 copy + norm / rounding-error bounds, all resident in HBM."""
+
+    def __init__(self, x: torch.Tensor, normalize: bool):
+        lib = _lib.load()
+        if x.dim() != 2:
+            raise ValueError(f"expected [n, dim] rows, got shape {tuple(x.shape)}")
+        x = x.contiguous().float()
+        n, dim = x.shape
+        self.n, self.dim = n, dim
+        self.x32 = x if not normalize else torch.empty_like(x)
+        self.xh = torch.empty((n, dim), dtype=torch.float16, device=x.device)
+        self.norm = torch.empty((n,), dtype=torch.float32, device=x.device)
+        self.err = torch.empty((n,), dtype=torch.float32, device=x.device)
+        with torch.cuda.device(x.device):
+            _lib.check(lib.vdk_rows_prepare(_lib.ptr(x), n, dim, int(normalize), _lib.ptr(self.x32), _lib.ptr(self.xh),
+                                            _lib.ptr(self.norm), _lib.ptr(self.err), _lib.stream_ptr()),
+                       "vdk_rows_prepare")
+
+    def maxima(self) -> Tuple[torch.Tensor, torch.Tensor]:
+        lib = _lib.load()
+        out = torch.zeros((2,), dtype=torch.float32, device=self.x32.device)
+        with torch.cuda.device(self.x32.device):
+            _lib.check(lib.vdk_reduce_max(_lib.ptr(self.norm), self.n, out.data_ptr(), _lib.stream_ptr()),
+                       "vdk_reduce_max")
+            _lib.check(lib.vdk_reduce_max(_lib.ptr(self.err), self.n, out.data_ptr() + 4, _lib.stream_ptr()),
+                       "vdk_reduce_max")
+        return out[0:1], out[1:2]
+
+
+class FlatIPIndex:
+    """Exact inner-product index (faiss "Flat", METRIC_INNER_PRODUCT) with the gallery resident on one GPU.
+
+    normalize=True fuses F.normalize (face_model.py:139) into add()/search(), i.e. cosine similarity.
+    id_offset shifts returned ids (a shard's first global row under multi-GPU sharding).
+    """
+
+    def __init__(self, dim: int, device=None, normalize: bool = False, id_offset: int = 0):
+        _lib.load()
+        self.d = int(dim)
+        self.device = _dev(device)
+        self.normalize = bool(normalize)
+        self.id_offset = int(id_offset)
+        self.is_trained = True
+        self._chunks = []
+        self._rows: Optional[PreparedRows] = None
+        self._gmax = None
+        self._ws = None
+        self.last_status = None
+
+    # ---- faiss-shaped surface -------------------------------------------------------------------
+    @property
+    def ntotal(self) -> int:
+        return sum(c.shape[0] for c in self._chunks) + (self._rows.n if self._rows is not None else 0)
+
+    def train(self, x) -> None:  # Flat indexes need no training (evaluation.py:167)
+        return None
+
+    def add(self, x) -> None:
+        t = self._to_device(x)
+        if t.shape[1] != self.d:
+            raise ValueError(f"index dimension is {self.d}, got rows of width {t.shape[1]}")
+        if self._rows is not None:  # re-open: keep the fp32 rows, re-prepare on next search
+            self._chunks.insert(0, self._rows.x32)
+            self._rows = None
+        self._chunks.append(t)
+
+    def reset(self) -> None:
+        self._chunks, self._rows, self._gmax = [], None, None
+
+    def search(self, x, k: int):
+        """numpy float32 [n, d] -> (scores float32 [n, k], ids int64 [n, k]); the faiss call of evaluation.py:193."""
+        s, i = self.search_device(self._to_device(x), k)
+        return s.cpu().numpy(), i.cpu().numpy()
+
+    # ---- device-resident path ----------------------------------------------------------------------
+    def search_device(self, q: torch.Tensor, k: int):
+        lib = _lib.load()
+        _lib.require_device()
+        self._finalize()
+        k = int(k)
+        if not (1 <= k <= 1024):
+            raise ValueError("k must be in [1, 1024]")
+        q = self._to_device(q)
+        if q.shape[1] != self.d:
+            raise ValueError(f"index dimension is {self.d}, got queries of width {q.shape[1]}")
+        nq = q.shape[0]
+        out_s = torch.empty((nq, k), dtype=torch.float32, device=self.device)
+        out_i = torch.empty((nq, k), dtype=torch.int64, device=self.device)
+        status = torch.zeros((4,), dtype=torch.int32, device=self.device)
+        if nq == 0:
+            return out_s, out_i
+        qp = PreparedRows(q, self.normalize)
+        ng = self._rows.n if self._rows is not None else 0
+        plan = _lib.TopkPlan()
+        _lib.check(lib.vdk_topk_plan_default(C.byref(plan), nq, ng, self.d, k), "vdk_topk_plan_default")
+        need = lib.vdk_topk_workspace_bytes(C.byref(plan))
+        if self._ws is None or self._ws.numel() < need:
+            self._ws = torch.empty((need,), dtype=torch.uint8, device=self.device)
+        g = self._rows
+        gn, ge = self._gmax if self._gmax is not None else (None, None)
+        with torch.cuda.device(self.device):
+            rc = lib.vdk_ip_topk(C.byref(plan), _lib.ptr(qp.x32), _lib.ptr(qp.xh), _lib.ptr(qp.norm), _lib.ptr(qp.err),
+                                 _lib.ptr(g.x32) if g else 0, _lib.ptr(g.xh) if g else 0, _lib.ptr(gn), _lib.ptr(ge),
+                                 self.id_offset, out_s.data_ptr(), out_i.data_ptr(), status.data_ptr(),
+                                 self._ws.data_ptr(), self._ws.numel(), _lib.stream_ptr())
+        _lib.check(rc, "vdk_ip_topk")
+        self.last_status = status
+        return out_s, out_i
+
+    def check_status(self) -> dict:
+        """Synchronises and raises if any query overflowed its candidate list (results would be incomplete)."""
+        st = self.last_status.cpu().tolist()
+        info = {"overflow_rows": st[0], "max_candidates": st[1], "max_survivors": st[2]}
+        if st[0] != 0:
+            raise RuntimeError(f"vdk_ip_topk: {st[0]} query rows overflowed their candidate lists {info}; "
+                               "the gallery has more near-ties than the plan's capacity")
+        return info
+
+    # ---- internals -----------------------------------------------------------------------------
+    def _to_device(self, x) -> torch.Tensor:
+        if isinstance(x, np.ndarray):
+            x = torch.from_numpy(np.ascontiguousarray(x, dtype=np.float32))
+        if not isinstance(x, torch.Tensor):
+            raise TypeError("expected a numpy array or torch tensor")
+        if x.dim() != 2:
+            raise ValueError(f"expected [n, dim], got shape {tuple(x.shape)}")
+        return x.to(self.device, torch.float32, non_blocking=True).contiguous()
+
+    def _finalize(self) -> None:
+        if not self._chunks:
+            return
+        rows = self._chunks[0] if len(self._chunks) == 1 else torch.cat(self._chunks, dim=0)
+        self._chunks = []
+        if rows.shape[0] == 0:
+            self._rows, self._gmax = None, None
+            return
+        self._rows = PreparedRows(rows, self.normalize)
+        self._gmax = self._rows.maxima()
+
+
+def merge_topk(scores: torch.Tensor, ids: torch.Tensor, k: int):
+    """Merge per-shard lists [n_lists, n_query, k] -> global [n_query, k] (score desc, id asc)."""
+    lib = _lib.load()
+    n_lists, nq, kk = scores.shape
+    assert kk == k and ids.shape == scores.shape
+    scores = scores.contiguous().float()
+    ids = ids.contiguous().long()
+    out_s = torch.empty((nq, k), dtype=torch.float32, device=scores.device)
+    out_i = torch.empty((nq, k), dtype=torch.int64, device=scores.device)
+    with torch.cuda.device(scores.device):
+        _lib.check(lib.vdk_topk_merge(scores.data_ptr(), ids.data_ptr(), n_lists, nq, k, out_s.data_ptr(),
+                                      out_i.data_ptr(), _lib.stream_ptr()), "vdk_topk_merge")
+    return out_s, out_i
+
+
+def exact_pair_scores(q32: torch.Tensor, g32: torch.Tensor, qi: torch.Tensor, gi: torch.Tensor) -> torch.Tensor:
+    """Canonical scores of explicit (query, gallery) pairs — the verification kernel used by tests/bench."""
+    lib = _lib.load()
+    out = torch.empty((qi.numel(),), dtype=torch.float32, device=q32.device)
+    with torch.cuda.device(q32.device):
+        _lib.check(lib.vdk_ip_exact_pairs(q32.data_ptr(), g32.data_ptr(), q32.shape[1], qi.contiguous().data_ptr(),
+                                          gi.contiguous().data_ptr(), qi.numel(), out.data_ptr(), _lib.stream_ptr()),
+                   "vdk_ip_exact_pairs")
+    return out
