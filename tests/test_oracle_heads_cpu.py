@@ -1,0 +1,47 @@
+"""Pins oracle/heads.py to golden vectors produced by the REFERENCE's own head / loss modules
+(oracle/make_golden.py, run in the authoring container where /root/reference is mounted)."""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import heads as H
+
+GOLD = os.path.join(os.path.dirname(__file__), "golden")
+
+KINDS = {
+    "arcface": ("arcface", dict(margin_arc=0.35, margin_am=0.0, scale=32)),
+    "arcface_am": ("arcface", dict(margin_arc=0.5, margin_am=0.2, scale=64)),
+    "circleloss": ("circleloss", dict(margin=0.25, gamma=256)),
+}
+
+
+@pytest.mark.parametrize("case", ["small", "cfg"])
+@pytest.mark.parametrize("kind", list(KINDS))
+def test_heads_match_reference_golden(case, kind):
+    z = np.load(os.path.join(GOLD, f"heads_{case}.npz"))
+    feats = torch.from_numpy(z["feats"]).requires_grad_(True)
+    labels = torch.from_numpy(z["labels"])
+    w = torch.from_numpy(z[f"{kind}_weight"]).requires_grad_(True)
+    fn, kw = KINDS[kind]
+    loss, logits = H.head_loss(fn, feats, w, labels, label_smooth=float(z["label_smooth"]), **kw)
+    loss.backward()
+    assert np.array_equal(logits.detach().numpy(), z[f"{kind}_logits"])
+    assert np.array_equal(loss.detach().numpy(), z[f"{kind}_loss"])
+    np.testing.assert_allclose(feats.grad.numpy(), z[f"{kind}_dfeats"], rtol=1e-6, atol=1e-9)
+    np.testing.assert_allclose(w.grad.numpy(), z[f"{kind}_dweight"], rtol=1e-6, atol=1e-9)
+
+
+def test_fallback_branch_is_exercised():
+    z = np.load(os.path.join(GOLD, "heads_small.npz"))
+    cos = H.cos_theta(torch.from_numpy(z["feats"]), torch.from_numpy(z["arcface_am_weight"]))
+    lab = torch.from_numpy(z["labels"])
+    target = cos[torch.arange(len(lab)), lab]
+    import math
+    assert (target <= math.cos(math.pi - 0.5)).any()
+
+
+def test_init_head_weight_has_unit_columns():
+    w = H.init_head_weight(64, 10, torch.Generator().manual_seed(0))
+    np.testing.assert_allclose(w.norm(dim=0).numpy(), 1.0, rtol=1e-5)
