@@ -45,6 +45,26 @@ int vdk_device_check(void);
 #define VDK_EPI_GELU 1           /* D = gelu_erf(acc + bias[n]) */
 #define VDK_EPI_SCALE_RESIDUAL 2 /* D = residual[m,n] + gamma[n] * (acc + bias[n])  (ConvNeXt layer-scale) */
 
+#define VDK_EPI_LAYERNORM 3      /* D = LayerNorm_N(acc + bias) * gamma + beta; the tile must span the row (N <= 256) */
+
+typedef struct vdk_gemm_desc {
+  const void* A; /* [M,K] 16-bit, pitch lda */
+  const void* B; /* [N,K] 16-bit, pitch ldb (nn.Linear.weight layout) */
+  void* D;       /* [M,N] out_dtype, pitch ldd */
+  int M, N, K, lda, ldb, ldd;
+  int in_dtype, out_dtype, epilogue;
+  const float* bias;    /* [N] or NULL */
+  const float* gamma;   /* [N]: layer-scale (SCALE_RESIDUAL) or LayerNorm weight (LAYERNORM) */
+  const float* beta;    /* [N]: LayerNorm bias */
+  const void* residual; /* [M,ldr], dtype of D (SCALE_RESIDUAL) */
+  int ldr;
+  float ln_eps;
+  int split_k; /* > 1: K is split over split_k CTAs per tile whose fp32 partials are atomically added into a
+                  ZEROED fp32 D (skinny-M neck GEMM, timm_wrapper.py:36); epilogue NONE, no bias */
+} vdk_gemm_desc;
+int vdk_gemm(const vdk_gemm_desc* desc, void* stream);
+
+/* Positional convenience form of vdk_gemm (split_k = 1, no LayerNorm). */
 int vdk_gemm_tn(const void* A, const void* B, void* D, int M, int N, int K, int lda, int ldb, int ldd,
                 int in_dtype,          /* VDK_DTYPE_BF16 | VDK_DTYPE_FP16 */
                 int out_dtype,         /* VDK_DTYPE_BF16 | VDK_DTYPE_FP16 | VDK_DTYPE_FP32 */
@@ -53,6 +73,64 @@ int vdk_gemm_tn(const void* A, const void* B, void* D, int M, int N, int K, int 
                 const float* gamma,    /* [N], VDK_EPI_SCALE_RESIDUAL only */
                 const void* residual,  /* [M,ldr] same dtype as D, VDK_EPI_SCALE_RESIDUAL only */
                 int ldr, void* stream);
+
+/* ---- ConvNeXt embedding forward (eval) ------------------------------------------------------ */
+/* Replaces TimmWrapper.forward (models/faceX/backbone/timm_wrapper.py:51-54: timm ConvNeXt features with
+ * num_classes=0, global_pool='' -> BatchNorm2d -> Flatten -> Linear -> BatchNorm1d, :30-38) followed by
+ * F.normalize (models/faceX/face_model.py:139).  All pointers are device pointers to weights the caller packed
+ * (visiondk_b200/backbone.py: layouts below); activations are NHWC bf16 in `workspace`. */
+#define VDK_CONVNEXT_MAX_BLOCKS 64
+
+typedef struct vdk_convnext_block {
+  const float* dw_w;  /* depthwise 7x7 taps, [49][C] fp32 (tap-major, channel contiguous) */
+  const float* dw_b;  /* [C] */
+  const float* ln_w;  /* [C] LayerNorm(eps 1e-6) */
+  const float* ln_b;  /* [C] */
+  const void* fc1_w;  /* [4C, C] bf16 (nn.Linear.weight) */
+  const float* fc1_b; /* [4C] */
+  const void* fc2_w;  /* [C, 4C] bf16 */
+  const float* fc2_b; /* [C] */
+  const float* gamma; /* [C] layer scale */
+} vdk_convnext_block;
+
+typedef struct vdk_convnext_down {
+  const float* ln_w;   /* [Cin] LayerNorm2d(eps 1e-6) */
+  const float* ln_b;   /* [Cin] */
+  const void* conv_w;  /* [Cout, 4*Cin] bf16, K order (kh, kw, cin) */
+  const float* conv_b; /* [Cout] */
+} vdk_convnext_down;
+
+typedef struct vdk_convnext_net {
+  int image_size; /* square input side, multiple of 32 */
+  int feat_dim;   /* embedding width (neck Linear out_features) */
+  int depths[4];
+  int dims[4];
+  const void* stem_w;     /* [dims[0], 48] bf16, K order (c, kh, kw) = Conv2d(3,C0,4,4).weight flattened */
+  const float* stem_b;    /* [dims[0]] */
+  const float* stem_ln_w; /* [dims[0]] */
+  const float* stem_ln_b;
+  vdk_convnext_down down[4]; /* down[0] unused */
+  vdk_convnext_block blocks[VDK_CONVNEXT_MAX_BLOCKS]; /* stage-major */
+  const float* head_ln_w; /* [dims[3]] model.head.norm */
+  const float* head_ln_b;
+  const void* neck_w;  /* [feat_dim, h*w*dims[3]] bf16, K order (h, w, c), BN2d/BN1d eval statistics folded in */
+  const float* neck_b; /* [feat_dim] folded bias */
+} vdk_convnext_net;
+
+/* Building blocks of the forward, exported for unit parity tests (NHWC bf16 activations):
+ *   vdk_dwconv7_ln        y = LayerNorm_C(depthwise7x7(x, pad 3) + bias)         timm ConvNeXtBlock.conv_dw + .norm
+ *   vdk_layernorm_patchify out = LayerNorm_C(x), patch == 2: regrouped as 2x2/stride-2 patch rows [B*H/2*W/2, 4C]
+ *                          in (kh, kw, c) order (timm downsample LayerNorm2d + the im2col of its Conv2d(k2,s2)) */
+int vdk_dwconv7_ln(const void* x, int batch, int H, int W, int C, const float* w49, const float* bias,
+                   const float* ln_w, const float* ln_b, float eps, void* y, void* stream);
+int vdk_layernorm_patchify(const void* x, int batch, int H, int W, int C, const float* ln_w, const float* ln_b,
+                           float eps, int patch, void* out, void* stream);
+
+size_t vdk_convnext_workspace_bytes(const vdk_convnext_net* net, int batch);
+/* images: fp32 NCHW [batch,3,S,S] (what the reference's DataLoader yields); embeddings: fp32 [batch, feat_dim],
+ * L2-normalised when l2_normalize != 0 (extract_cbir semantics). */
+int vdk_convnext_forward(const vdk_convnext_net* net, const float* images, int batch, int l2_normalize,
+                         float* embeddings, void* workspace, size_t workspace_bytes, void* stream);
 
 /* ---- retrieval: L2-normalise -> inner product -> top-k -------------------------------------- */
 /* Replaces F.normalize at models/faceX/face_model.py:139, faiss index.add at

@@ -14,7 +14,7 @@ _LIB_PATH = Path(__file__).resolve().parent / "lib" / "libvdk_b200.so"
 VDK_OK = 0
 VDK_ERR_INVALID, VDK_ERR_CUDA, VDK_ERR_WORKSPACE, VDK_ERR_OVERFLOW = -1, -2, -3, -4
 DTYPE_BF16, DTYPE_FP16, DTYPE_FP32 = 0, 1, 2
-EPI_NONE, EPI_GELU, EPI_SCALE_RESIDUAL = 0, 1, 2
+EPI_NONE, EPI_GELU, EPI_SCALE_RESIDUAL, EPI_LAYERNORM = 0, 1, 2, 3
 
 
 class TopkPlan(C.Structure):
@@ -31,11 +31,27 @@ class TopkPlan(C.Structure):
 
 _p, _i, _i64, _sz = C.c_void_p, C.c_int, C.c_int64, C.c_size_t
 
+
+class GemmDesc(C.Structure):
+    _fields_ = [
+        ("A", C.c_void_p), ("B", C.c_void_p), ("D", C.c_void_p),
+        ("M", C.c_int), ("N", C.c_int), ("K", C.c_int), ("lda", C.c_int), ("ldb", C.c_int), ("ldd", C.c_int),
+        ("in_dtype", C.c_int), ("out_dtype", C.c_int), ("epilogue", C.c_int),
+        ("bias", C.c_void_p), ("gamma", C.c_void_p), ("beta", C.c_void_p), ("residual", C.c_void_p),
+        ("ldr", C.c_int), ("ln_eps", C.c_float), ("split_k", C.c_int),
+    ]
+
+
 # name -> (restype, argtypes); must list every symbol include/vdk_b200.h declares (tests check this).
 SIGNATURES = {
     "vdk_version": (_i, []),
     "vdk_last_error_string": (C.c_char_p, []),
     "vdk_device_check": (_i, []),
+    "vdk_gemm": (_i, [_p, _p]),
+    "vdk_dwconv7_ln": (_i, [_p, _i, _i, _i, _i, _p, _p, _p, _p, C.c_float, _p, _p]),
+    "vdk_layernorm_patchify": (_i, [_p, _i, _i, _i, _i, _p, _p, C.c_float, _i, _p, _p]),
+    "vdk_convnext_workspace_bytes": (_sz, [_p, _i]),
+    "vdk_convnext_forward": (_i, [_p, _p, _i, _i, _p, _p, _sz, _p]),
     "vdk_gemm_tn": (_i, [_p, _p, _p, _i, _i, _i, _i, _i, _i, _i, _i, _i, _p, _p, _p, _i, _p]),
     "vdk_rows_prepare": (_i, [_p, _i64, _i, _i, _p, _p, _p, _p, _p]),
     "vdk_topk_plan_default": (_i, [C.POINTER(TopkPlan), _i64, _i64, _i, _i]),

@@ -1,0 +1,248 @@
+"""Backbone seam of the faceX / CBIR path on B200 (Seam 1).
+
+The reference builds `TimmWrapper(model_name, feat_dim, image_size, pretrained)` in
+models/faceX/backbone/backbone_def.py:16-26 (config key `timm-<name>`), i.e. a timm backbone created with
+num_classes=0 / global_pool='' plus the neck BatchNorm2d -> Flatten -> Linear -> BatchNorm1d
+(models/faceX/backbone/timm_wrapper.py:16-49), `forward(x[B,3,S,S]) -> [B, feat_dim]` (:51-54) and
+state_dict prefixes `model.` / `output_layer.`.
+
+This module keeps exactly that surface (constructor arguments, parameter names and shapes — timm 0.9.16
+ConvNeXt checkpoints and the reference's Epoch_N.pt `state_dict` / `ema` entries load with strict=True) but the
+arithmetic is the hand-written sm_100a path: vdk_convnext_forward in csrc/convnext.cu (tcgen05 GEMMs with fused
+LayerNorm / GELU / layer-scale+residual epilogues, NHWC bf16 activations).  The nn.Module children below are
+parameter containers only; their own forward() is never used on the hot path, and there is no CPU fallback.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+import warnings
+from typing import Dict, Optional
+
+import torch
+import torch.nn as nn
+
+from . import _lib
+
+CONVNEXT_ARCHS = {
+    "convnext_atto": ((2, 2, 6, 2), (40, 80, 160, 320)),
+    "convnext_femto": ((2, 2, 6, 2), (48, 96, 192, 384)),
+    "convnext_pico": ((2, 2, 6, 2), (64, 128, 256, 512)),
+    "convnext_nano": ((2, 2, 8, 2), (80, 160, 320, 640)),
+    "convnext_tiny": ((3, 3, 9, 3), (96, 192, 384, 768)),
+    "convnext_small": ((3, 3, 27, 3), (96, 192, 384, 768)),
+    "convnext_base": ((3, 3, 27, 3), (128, 256, 512, 1024)),
+    "convnext_large": ((3, 3, 27, 3), (192, 384, 768, 1536)),
+}
+
+
+class _LayerNorm2d(nn.LayerNorm):
+    """Parameter container named like timm.layers.LayerNorm2d (weight, bias over channels)."""
+
+
+class _Mlp(nn.Module):
+    def __init__(self, dim: int):
+        super().__init__()
+        self.fc1 = nn.Linear(dim, 4 * dim)
+        self.fc2 = nn.Linear(4 * dim, dim)
+
+
+class _Block(nn.Module):
+    def __init__(self, dim: int, ls_init_value: float = 1e-6):
+        super().__init__()
+        self.conv_dw = nn.Conv2d(dim, dim, kernel_size=7, padding=3, groups=dim)
+        self.norm = nn.LayerNorm(dim, eps=1e-6)
+        self.mlp = _Mlp(dim)
+        self.gamma = nn.Parameter(ls_init_value * torch.ones(dim))
+
+
+class _Stage(nn.Module):
+    def __init__(self, in_chs: int, out_chs: int, depth: int, downsample: bool):
+        super().__init__()
+        if downsample:
+            self.downsample = nn.Sequential(_LayerNorm2d(in_chs, eps=1e-6), nn.Conv2d(in_chs, out_chs, kernel_size=2, stride=2))
+        else:
+            self.downsample = nn.Identity()
+        self.blocks = nn.Sequential(*[_Block(out_chs) for _ in range(depth)])
+
+
+class _Head(nn.Module):
+    def __init__(self, dim: int):
+        super().__init__()
+        self.norm = _LayerNorm2d(dim, eps=1e-6)
+
+
+class ConvNeXtParams(nn.Module):
+    """timm 0.9.16 `ConvNeXt(num_classes=0, global_pool='')` parameter tree (timm/models/convnext.py)."""
+
+    def __init__(self, depths, dims):
+        super().__init__()
+        self.depths, self.dims = tuple(depths), tuple(dims)
+        self.stem = nn.Sequential(nn.Conv2d(3, dims[0], kernel_size=4, stride=4), _LayerNorm2d(dims[0], eps=1e-6))
+        stages, prev = [], dims[0]
+        for i, (d, c) in enumerate(zip(depths, dims)):
+            stages.append(_Stage(prev, c, d, downsample=i > 0))
+            prev = c
+        self.stages = nn.Sequential(*stages)
+        self.head = _Head(prev)
+        # timm's init: trunc_normal(std .02) weights, zero biases (convnext.py _init_weights)
+        for m in self.modules():
+            if isinstance(m, (nn.Conv2d, nn.Linear)):
+                nn.init.trunc_normal_(m.weight, std=0.02)
+                nn.init.zeros_(m.bias)
+
+
+class _BlockC(C.Structure):
+    _fields_ = [(n, C.c_void_p) for n in ("dw_w", "dw_b", "ln_w", "ln_b", "fc1_w", "fc1_b", "fc2_w", "fc2_b", "gamma")]
+
+
+class _DownC(C.Structure):
+    _fields_ = [(n, C.c_void_p) for n in ("ln_w", "ln_b", "conv_w", "conv_b")]
+
+
+class ConvNeXtNetC(C.Structure):
+    _fields_ = [
+        ("image_size", C.c_int), ("feat_dim", C.c_int), ("depths", C.c_int * 4), ("dims", C.c_int * 4),
+        ("stem_w", C.c_void_p), ("stem_b", C.c_void_p), ("stem_ln_w", C.c_void_p), ("stem_ln_b", C.c_void_p),
+        ("down", _DownC * 4), ("blocks", _BlockC * 64),
+        ("head_ln_w", C.c_void_p), ("head_ln_b", C.c_void_p), ("neck_w", C.c_void_p), ("neck_b", C.c_void_p),
+    ]
+
+
+class TimmWrapper(nn.Module):
+    """Drop-in for models/faceX/backbone/timm_wrapper.py::TimmWrapper (ConvNeXt family)."""
+
+    def __init__(self, model_name: str, feat_dim: int, image_size: int, pretrained: bool = True, depths=None, dims=None,
+                 **kwargs):
+        super().__init__()
+        if depths is None:
+            if model_name not in CONVNEXT_ARCHS:
+                raise ValueError(f"backbone '{model_name}' is not built for B200 yet; available: {sorted(CONVNEXT_ARCHS)}")
+            depths, dims = CONVNEXT_ARCHS[model_name]
+        if image_size % 32 != 0:
+            raise ValueError("image_size must be a multiple of 32")
+        self.model_name, self.feat_dim, self.image_size = model_name, int(feat_dim), int(image_size)
+        self.model = ConvNeXtParams(depths, dims)
+        hw = image_size // 32
+        self.output_layer = nn.Sequential(nn.BatchNorm2d(dims[-1]), nn.Flatten(1),
+                                          nn.Linear(dims[-1] * hw * hw, feat_dim), nn.BatchNorm1d(feat_dim))
+        self._packed: Optional[Dict] = None
+        self._packed_key = None
+        self._ws = None
+        if pretrained:
+            self._load_pretrained(model_name)
+
+    # ---- reference surface ---------------------------------------------------------------------
+    def forward(self, x: torch.Tensor) -> torch.Tensor:
+        if self.training:
+            raise RuntimeError("visiondk_b200.TimmWrapper: the training forward/backward kernels are not built yet; "
+                               "call .eval() for the embedding-extraction path")
+        return self.embed(x, l2_normalize=False)
+
+    # ---- B200 path -------------------------------------------------------------------------------
+    @torch.no_grad()
+    def embed(self, x: torch.Tensor, l2_normalize: bool = False) -> torch.Tensor:
+        """[B,3,S,S] fp32 (NCHW, already normalised like the reference's transforms) -> fp32 [B, feat_dim]."""
+        lib = _lib.load()
+        if x.device.type != "cuda":
+            raise RuntimeError("visiondk_b200.TimmWrapper runs on CUDA (sm_100a) only; there is no CPU fallback")
+        if x.dim() != 4 or x.shape[1] != 3 or x.shape[2] != self.image_size or x.shape[3] != self.image_size:
+            raise ValueError(f"expected [B,3,{self.image_size},{self.image_size}], got {tuple(x.shape)}")
+        x = x.contiguous().float()
+        net = self._pack(x.device)
+        B = x.shape[0]
+        out = torch.empty((B, self.feat_dim), dtype=torch.float32, device=x.device)
+        need = lib.vdk_convnext_workspace_bytes(C.byref(net), B)
+        if self._ws is None or self._ws.numel() < need or self._ws.device != x.device:
+            self._ws = torch.empty((need,), dtype=torch.uint8, device=x.device)
+        with torch.cuda.device(x.device):
+            _lib.check(lib.vdk_convnext_forward(C.byref(net), x.data_ptr(), B, int(l2_normalize), out.data_ptr(),
+                                                self._ws.data_ptr(), self._ws.numel(), _lib.stream_ptr()),
+                       "vdk_convnext_forward")
+        return out
+
+    # ---- weight packing --------------------------------------------------------------------------
+    def _version_key(self, device):
+        return (str(device),) + tuple(int(t._version) for t in list(self.parameters()) + list(self.buffers()))
+
+    def _pack(self, device) -> ConvNeXtNetC:
+        """Kernel-side layouts (include/vdk_b200.h): bf16 GEMM weights, fp32 vectors, depthwise taps [49][C],
+        downsample conv K order (kh,kw,cin), neck with BN2d/BN1d eval statistics folded and K order (h,w,c)."""
+        key = self._version_key(device)
+        if self._packed is not None and self._packed_key == key:
+            return self._packed["net"]
+        keep = []
+
+        def f32(t):
+            t = t.detach().to(device, torch.float32).contiguous()
+            keep.append(t)
+            return t.data_ptr()
+
+        def bf16(t):
+            t = t.detach().to(device, torch.float32).contiguous().to(torch.bfloat16)
+            keep.append(t)
+            return t.data_ptr()
+
+        m, net = self.model, ConvNeXtNetC()
+        net.image_size, net.feat_dim = self.image_size, self.feat_dim
+        for i in range(4):
+            net.depths[i], net.dims[i] = m.depths[i], m.dims[i]
+        net.stem_w = bf16(m.stem[0].weight.reshape(m.dims[0], 48))
+        net.stem_b, net.stem_ln_w, net.stem_ln_b = f32(m.stem[0].bias), f32(m.stem[1].weight), f32(m.stem[1].bias)
+        bi = 0
+        for si, stage in enumerate(m.stages):
+            if si > 0:
+                ln, conv = stage.downsample[0], stage.downsample[1]
+                net.down[si].ln_w, net.down[si].ln_b = f32(ln.weight), f32(ln.bias)
+                net.down[si].conv_w = bf16(conv.weight.permute(0, 2, 3, 1).reshape(conv.weight.shape[0], -1))
+                net.down[si].conv_b = f32(conv.bias)
+            for blk in stage.blocks:
+                b = net.blocks[bi]
+                c = blk.conv_dw.weight.shape[0]
+                b.dw_w = f32(blk.conv_dw.weight.reshape(c, 49).t())
+                b.dw_b, b.ln_w, b.ln_b = f32(blk.conv_dw.bias), f32(blk.norm.weight), f32(blk.norm.bias)
+                b.fc1_w, b.fc1_b = bf16(blk.mlp.fc1.weight), f32(blk.mlp.fc1.bias)
+                b.fc2_w, b.fc2_b = bf16(blk.mlp.fc2.weight), f32(blk.mlp.fc2.bias)
+                b.gamma = f32(blk.gamma)
+                bi += 1
+        net.head_ln_w, net.head_ln_b = f32(m.head.norm.weight), f32(m.head.norm.bias)
+        bn2, lin, bn1 = self.output_layer[0], self.output_layer[2], self.output_layer[3]
+        c_last, hw = m.dims[-1], self.image_size // 32
+        with torch.no_grad():
+            s2 = (bn2.weight.double() / torch.sqrt(bn2.running_var.double() + bn2.eps)).to(device)
+            t2 = (bn2.bias.double().to(device) - bn2.running_mean.double().to(device) * s2)
+            s1 = (bn1.weight.double() / torch.sqrt(bn1.running_var.double() + bn1.eps)).to(device)
+            w = lin.weight.detach().double().to(device).reshape(self.feat_dim, c_last, hw, hw)
+            bias = lin.bias.detach().double().to(device) + (w * t2.view(1, -1, 1, 1)).sum(dim=(1, 2, 3))
+            bias = s1 * (bias - bn1.running_mean.double().to(device)) + bn1.bias.double().to(device)
+            w = w * s2.view(1, -1, 1, 1) * s1.view(-1, 1, 1, 1)
+            w = w.permute(0, 2, 3, 1).reshape(self.feat_dim, hw * hw * c_last)
+        net.neck_w, net.neck_b = bf16(w), f32(bias)
+        self._packed, self._packed_key = {"net": net, "keep": keep}, key
+        return net
+
+    def _load_pretrained(self, model_name: str) -> None:
+        """The reference downloads timm weights (timm_wrapper.py:16-21); this box has no network, so weights come
+        from $VDK_PRETRAINED_DIR/<model_name>.pth (a timm state_dict) when present."""
+        root = os.environ.get("VDK_PRETRAINED_DIR")
+        path = os.path.join(root, f"{model_name}.pth") if root else None
+        if path and os.path.exists(path):
+            sd = torch.load(path, map_location="cpu")
+            sd = {k: v for k, v in sd.items() if not k.startswith("head.fc")}
+            self.model.load_state_dict(sd, strict=True)
+        else:
+            warnings.warn(f"pretrained weights for '{model_name}' not found (set VDK_PRETRAINED_DIR); using random init")
+
+
+class BackboneFactory:
+    """models/faceX/backbone/backbone_def.py:5-26: `{'timm-<name>': {pretrained, image_size, feat_dim}}`."""
+
+    def __init__(self, backbone_config: dict):
+        for k, v in backbone_config.items():
+            self.backbone_type, self.backbone_param = k, v
+
+    def get_backbone(self) -> nn.Module:
+        if not self.backbone_type.startswith("timm-"):
+            raise ValueError(f"Unsupported backbone type: {self.backbone_type}. Only timm models are supported.")
+        model_name = self.backbone_type[5:]
+        return TimmWrapper(model_name=model_name, **self.backbone_param)

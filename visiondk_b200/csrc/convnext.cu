@@ -1,0 +1,447 @@
+// convnext.cu — ConvNeXt (timm 0.9.16 layout) embedding forward for the faceX/CBIR extract path, NHWC bf16.
+//
+// Replaces timm's ConvNeXt forward + the reference neck + F.normalize:
+//   models/faceX/backbone/timm_wrapper.py:51-54 (TimmWrapper.forward), :30-38 (output_layer),
+//   models/faceX/face_model.py:137-139 (extract_cbir: model(x) then F.normalize).
+//
+// Dense contractions run on the tcgen05 GEMM (gemm.cu) with fused epilogues; everything around them is an
+// HBM-bound kernel written here:
+//   stem_patchify     NCHW fp32 image -> 4x4 patch rows [B*H/4*W/4, 48] bf16          (then GEMM + bias + LayerNorm)
+//   dwconv7_ln        depthwise 7x7 (pad 3) + bias + LayerNorm over C, NHWC bf16      (then GEMM+GELU, GEMM+gamma+res)
+//   ln_patchify       LayerNorm over C [+ 2x2/s2 patch gather]                        (downsample conv / head norm)
+//   neck_finalize     split-K partials + folded BN bias [+ L2 normalise] -> fp32 embeddings
+#include "vdk_host.h"
+#include "vdk_ptx.cuh"
+
+namespace vdk {
+
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+  for (int off = 16; off > 0; off >>= 1) v += __shfl_xor_sync(0xffffffffu, v, off);
+  return v;
+}
+
+// ------------------------------------------------------------------------------------------------
+// stem: 4x4 stride-4 patches of an NCHW fp32 image -> rows of 48 (c, kh, kw) in bf16
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) stem_patchify_kernel(const float* __restrict__ x, int B, int H, int W,
+                                                            __nv_bfloat16* __restrict__ out) {
+  // one thread per (patch, c, kh): reads 4 contiguous pixels, writes 4 contiguous bf16
+  const int PH = H / 4, PW = W / 4;
+  const int64_t total = static_cast<int64_t>(B) * PH * PW * 12;
+  for (int64_t t = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x; t < total;
+       t += static_cast<int64_t>(gridDim.x) * blockDim.x) {
+    const int ck = static_cast<int>(t % 12);
+    const int64_t patch = t / 12;
+    const int c = ck >> 2, kh = ck & 3;
+    const int pw = static_cast<int>(patch % PW);
+    const int ph = static_cast<int>((patch / PW) % PH);
+    const int b = static_cast<int>(patch / (static_cast<int64_t>(PW) * PH));
+    const float4 v = *reinterpret_cast<const float4*>(x + ((static_cast<int64_t>(b) * 3 + c) * H + (ph * 4 + kh)) * W + pw * 4);
+    __nv_bfloat162 lo = __floats2bfloat162_rn(v.x, v.y), hi = __floats2bfloat162_rn(v.z, v.w);
+    uint2 o;
+    o.x = *reinterpret_cast<uint32_t*>(&lo);
+    o.y = *reinterpret_cast<uint32_t*>(&hi);
+    *reinterpret_cast<uint2*>(out + patch * 48 + ck * 4) = o;
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// depthwise 7x7 + bias + LayerNorm(C): one CTA = TW output pixels of one image row x all channels
+// ------------------------------------------------------------------------------------------------
+constexpr int kDwTW = 4;  // output pixels per CTA along W
+
+template <int CPT>  // channels per thread (2 or 4), contiguous -> coalesced NHWC access
+__global__ void __launch_bounds__(512)
+dwconv7_ln_kernel(const __nv_bfloat16* __restrict__ x, int B, int H, int W, int C,
+                  const float* __restrict__ w49,  // [49][C]
+                  const float* __restrict__ bias, const float* __restrict__ ln_w, const float* __restrict__ ln_b,
+                  float eps, __nv_bfloat16* __restrict__ y) {
+  __shared__ float red[kDwTW][16];
+  __shared__ float stat[kDwTW];
+  const int tiles_w = (W + kDwTW - 1) / kDwTW;
+  const int tw = blockIdx.x % tiles_w;
+  const int oy = (blockIdx.x / tiles_w) % H;
+  const int b = blockIdx.x / (tiles_w * H);
+  const int ox0 = tw * kDwTW;
+  const int c0 = threadIdx.x * CPT;
+  const bool active = c0 < C;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarps = (blockDim.x + 31) >> 5;
+
+  float acc[kDwTW][CPT];
+#pragma unroll
+  for (int p = 0; p < kDwTW; ++p)
+#pragma unroll
+    for (int c = 0; c < CPT; ++c) acc[p][c] = 0.f;
+
+  if (active) {
+    const __nv_bfloat16* xb = x + static_cast<int64_t>(b) * H * W * C;
+#pragma unroll 1
+    for (int dy = 0; dy < 7; ++dy) {
+      const int iy = oy + dy - 3;
+      if (iy < 0 || iy >= H) continue;
+      float wrow[7][CPT];
+#pragma unroll
+      for (int dx = 0; dx < 7; ++dx) {
+        if (CPT == 4) {
+          const float4 t = __ldg(reinterpret_cast<const float4*>(w49 + (dy * 7 + dx) * C + c0));
+          wrow[dx][0] = t.x; wrow[dx][1] = t.y; wrow[dx][CPT - 2] = t.z; wrow[dx][CPT - 1] = t.w;
+        } else {
+          const float2 t = __ldg(reinterpret_cast<const float2*>(w49 + (dy * 7 + dx) * C + c0));
+          wrow[dx][0] = t.x; wrow[dx][1] = t.y;
+        }
+      }
+#pragma unroll
+      for (int ix = 0; ix < kDwTW + 6; ++ix) {
+        const int gx = ox0 + ix - 3;
+        if (gx < 0 || gx >= W) continue;
+        float v[CPT];
+        const __nv_bfloat16* src = xb + (static_cast<int64_t>(iy) * W + gx) * C + c0;
+        if (CPT == 4) {
+          const uint2 t = *reinterpret_cast<const uint2*>(src);
+          const float2 a = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&t.x));
+          const float2 c = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&t.y));
+          v[0] = a.x; v[1] = a.y; v[CPT - 2] = c.x; v[CPT - 1] = c.y;
+        } else {
+          const float2 a = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(src));
+          v[0] = a.x; v[1] = a.y;
+        }
+#pragma unroll
+        for (int p = 0; p < kDwTW; ++p) {
+          const int dx = ix - p;  // input column ix feeds output pixel p through tap dx
+          if (dx >= 0 && dx < 7) {
+#pragma unroll
+            for (int c = 0; c < CPT; ++c) acc[p][c] = fmaf(v[c], wrow[dx][c], acc[p][c]);
+          }
+        }
+      }
+    }
+#pragma unroll
+    for (int c = 0; c < CPT; ++c) {
+      const float bc = __ldg(bias + c0 + c);
+#pragma unroll
+      for (int p = 0; p < kDwTW; ++p) acc[p][c] += bc;
+    }
+  }
+
+  // LayerNorm over C for each of the kDwTW pixels: block reduction of the mean, then of the centred squares
+  float mean[kDwTW], rstd[kDwTW];
+#pragma unroll
+  for (int pass = 0; pass < 2; ++pass) {
+#pragma unroll
+    for (int p = 0; p < kDwTW; ++p) {
+      float s = 0.f;
+      if (active) {
+#pragma unroll
+        for (int c = 0; c < CPT; ++c) {
+          const float d = pass == 0 ? acc[p][c] : acc[p][c] - mean[p];
+          s += pass == 0 ? d : d * d;
+        }
+      }
+      s = warp_sum(s);
+      if (lane == 0) red[p][warp] = s;
+    }
+    __syncthreads();
+    if (warp == 0) {
+#pragma unroll
+      for (int p = 0; p < kDwTW; ++p) {
+        float s = lane < nwarps ? red[p][lane] : 0.f;
+        s = warp_sum(s);
+        if (lane == 0) stat[p] = s / static_cast<float>(C);
+      }
+    }
+    __syncthreads();
+#pragma unroll
+    for (int p = 0; p < kDwTW; ++p) {
+      if (pass == 0) mean[p] = stat[p];
+      else rstd[p] = rsqrtf(stat[p] + eps);
+    }
+    __syncthreads();
+  }
+
+  if (active) {
+    float g[CPT], bb[CPT];
+#pragma unroll
+    for (int c = 0; c < CPT; ++c) {
+      g[c] = __ldg(ln_w + c0 + c);
+      bb[c] = __ldg(ln_b + c0 + c);
+    }
+#pragma unroll
+    for (int p = 0; p < kDwTW; ++p) {
+      const int ox = ox0 + p;
+      if (ox >= W) continue;
+      __nv_bfloat16* dst = y + ((static_cast<int64_t>(b) * H + oy) * W + ox) * C + c0;
+      float o[CPT];
+#pragma unroll
+      for (int c = 0; c < CPT; ++c) o[c] = (acc[p][c] - mean[p]) * rstd[p] * g[c] + bb[c];
+      if (CPT == 4) {
+        __nv_bfloat162 lo = __floats2bfloat162_rn(o[0], o[1]), hi = __floats2bfloat162_rn(o[CPT - 2], o[CPT - 1]);
+        uint2 t;
+        t.x = *reinterpret_cast<uint32_t*>(&lo);
+        t.y = *reinterpret_cast<uint32_t*>(&hi);
+        *reinterpret_cast<uint2*>(dst) = t;
+      } else {
+        *reinterpret_cast<__nv_bfloat162*>(dst) = __floats2bfloat162_rn(o[0], o[1]);
+      }
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// LayerNorm over C of NHWC rows, optionally scattered into 2x2/stride-2 patch rows (kh, kw, c)
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+ln_patchify_kernel(const __nv_bfloat16* __restrict__ x, int B, int H, int W, int C, const float* __restrict__ ln_w,
+                   const float* __restrict__ ln_b, float eps, int patch /*1 or 2*/, __nv_bfloat16* __restrict__ out) {
+  // one warp per input pixel; lane handles channel pairs lane*2 + 64*i
+  const int lane = threadIdx.x & 31;
+  const int64_t pix = (static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x) >> 5;
+  const int64_t npix = static_cast<int64_t>(B) * H * W;
+  if (pix >= npix) return;
+  const __nv_bfloat16* src = x + pix * C;
+  constexpr int kMaxIter = 16;  // C <= 2048
+  float2 v[kMaxIter];
+  const int iters = (C + 63) / 64;
+  float s = 0.f;
+#pragma unroll
+  for (int i = 0; i < kMaxIter; ++i) {
+    if (i < iters) {
+      const int c = i * 64 + lane * 2;
+      v[i] = c < C ? __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(src + c)) : make_float2(0.f, 0.f);
+      s += v[i].x + v[i].y;
+    }
+  }
+  const float mean = warp_sum(s) / static_cast<float>(C);
+  float q = 0.f;
+#pragma unroll
+  for (int i = 0; i < kMaxIter; ++i) {
+    if (i < iters) {
+      const int c = i * 64 + lane * 2;
+      if (c < C) {
+        const float a = v[i].x - mean, b = v[i].y - mean;
+        q += a * a + b * b;
+      }
+    }
+  }
+  const float rstd = rsqrtf(warp_sum(q) / static_cast<float>(C) + eps);
+  int64_t orow;
+  int ocol0;
+  if (patch == 2) {
+    const int xw = static_cast<int>(pix % W);
+    const int yh = static_cast<int>((pix / W) % H);
+    const int b = static_cast<int>(pix / (static_cast<int64_t>(W) * H));
+    orow = (static_cast<int64_t>(b) * (H / 2) + (yh >> 1)) * (W / 2) + (xw >> 1);
+    ocol0 = ((yh & 1) * 2 + (xw & 1)) * C;
+  } else {
+    orow = pix;
+    ocol0 = 0;
+  }
+  __nv_bfloat16* dst = out + orow * (static_cast<int64_t>(C) * patch * patch) + ocol0;
+#pragma unroll
+  for (int i = 0; i < kMaxIter; ++i) {
+    if (i < iters) {
+      const int c = i * 64 + lane * 2;
+      if (c < C) {
+        const float2 g = *reinterpret_cast<const float2*>(ln_w + c);
+        const float2 bb = *reinterpret_cast<const float2*>(ln_b + c);
+        *reinterpret_cast<__nv_bfloat162*>(dst + c) =
+            __floats2bfloat162_rn((v[i].x - mean) * rstd * g.x + bb.x, (v[i].y - mean) * rstd * g.y + bb.y);
+      }
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// neck finalize: split-K partial sums + folded bias -> embedding rows (optionally L2-normalised)
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+neck_finalize_kernel(const float* __restrict__ acc, int B, int F, const float* __restrict__ bias, int l2norm,
+                     float* __restrict__ out) {
+  const int lane = threadIdx.x & 31;
+  const int row = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  if (row >= B) return;
+  double ss = 0.0;
+  // the canonical F.normalize of retrieval.cu: fixed-order fp64 sum of squares (lane-strided, xor butterfly)
+  for (int i = lane; i < F; i += 32) {
+    const float v = acc[static_cast<size_t>(row) * F + i] + bias[i];
+    ss = fma(static_cast<double>(v), static_cast<double>(v), ss);
+  }
+#pragma unroll
+  for (int off = 16; off > 0; off >>= 1) ss += __shfl_xor_sync(0xffffffffu, ss, off);
+  const float denom = l2norm ? fmaxf(static_cast<float>(sqrt(ss)), 1e-12f) : 1.0f;
+  for (int i = lane; i < F; i += 32) {
+    const float v = acc[static_cast<size_t>(row) * F + i] + bias[i];
+    out[static_cast<size_t>(row) * F + i] = l2norm ? __fdiv_rn(v, denom) : v;
+  }
+}
+
+static size_t up256(size_t v) { return (v + 255) & ~static_cast<size_t>(255); }
+
+static int check_net(const vdk_convnext_net* n) {
+  VDK_REQUIRE(n, "vdk_convnext: null network");
+  VDK_REQUIRE(n->image_size > 0 && n->image_size % 32 == 0, "vdk_convnext: image_size must be a multiple of 32");
+  VDK_REQUIRE(n->feat_dim > 0 && n->feat_dim % 8 == 0, "vdk_convnext: feat_dim must be a multiple of 8");
+  int nb = 0;
+  for (int s = 0; s < 4; ++s) {
+    VDK_REQUIRE(n->dims[s] > 0 && n->dims[s] % 8 == 0 && n->dims[s] <= 2048, "vdk_convnext: dims must be multiples of 8, <= 2048");
+    VDK_REQUIRE(n->depths[s] >= 0, "vdk_convnext: bad depth");
+    nb += n->depths[s];
+  }
+  VDK_REQUIRE(nb <= VDK_CONVNEXT_MAX_BLOCKS, "vdk_convnext: too many blocks (%d)", nb);
+  VDK_REQUIRE(n->dims[0] <= 256, "vdk_convnext: stem width must be <= 256 (LayerNorm epilogue tile)");
+  return VDK_OK;
+}
+
+}  // namespace vdk
+
+using namespace vdk;
+
+static int launch_dwconv7_ln(const __nv_bfloat16* x, int batch, int H, int W, int C, const float* w49, const float* bias,
+                             const float* ln_w, const float* ln_b, float eps, __nv_bfloat16* y, cudaStream_t s) {
+  const int tiles_w = (W + kDwTW - 1) / kDwTW;
+  const unsigned grid = static_cast<unsigned>(batch) * H * tiles_w;
+  if (C % 4 == 0 && C / 4 >= 32) {
+    const int threads = ((C / 4) + 31) / 32 * 32;
+    VDK_REQUIRE(threads <= 512, "dwconv7_ln: C too large (%d)", C);
+    dwconv7_ln_kernel<4><<<grid, threads, 0, s>>>(x, batch, H, W, C, w49, bias, ln_w, ln_b, eps, y);
+  } else {
+    VDK_REQUIRE(C % 2 == 0 && C / 2 <= 512, "dwconv7_ln: unsupported C (%d)", C);
+    const int threads = ((C / 2) + 31) / 32 * 32;
+    dwconv7_ln_kernel<2><<<grid, threads, 0, s>>>(x, batch, H, W, C, w49, bias, ln_w, ln_b, eps, y);
+  }
+  VDK_CUDA_OK(cudaGetLastError());
+  return VDK_OK;
+}
+
+extern "C" int vdk_dwconv7_ln(const void* x, int batch, int H, int W, int C, const float* w49, const float* bias,
+                              const float* ln_w, const float* ln_b, float eps, void* y, void* stream) {
+  VDK_REQUIRE(x && y && w49 && bias && ln_w && ln_b, "vdk_dwconv7_ln: null operand");
+  VDK_REQUIRE(batch > 0 && H > 0 && W > 0 && C > 0 && C % 8 == 0, "vdk_dwconv7_ln: bad shape");
+  return launch_dwconv7_ln(reinterpret_cast<const __nv_bfloat16*>(x), batch, H, W, C, w49, bias, ln_w, ln_b, eps,
+                           reinterpret_cast<__nv_bfloat16*>(y), reinterpret_cast<cudaStream_t>(stream));
+}
+
+extern "C" int vdk_layernorm_patchify(const void* x, int batch, int H, int W, int C, const float* ln_w,
+                                      const float* ln_b, float eps, int patch, void* out, void* stream) {
+  VDK_REQUIRE(x && out && ln_w && ln_b, "vdk_layernorm_patchify: null operand");
+  VDK_REQUIRE(batch > 0 && H > 0 && W > 0 && C > 0 && C % 2 == 0 && C <= 2048, "vdk_layernorm_patchify: bad shape");
+  VDK_REQUIRE(patch == 1 || (patch == 2 && H % 2 == 0 && W % 2 == 0), "vdk_layernorm_patchify: patch must be 1 or 2");
+  const int64_t npix = static_cast<int64_t>(batch) * H * W;
+  ln_patchify_kernel<<<static_cast<unsigned>((npix * 32 + 255) / 256), 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
+      reinterpret_cast<const __nv_bfloat16*>(x), batch, H, W, C, ln_w, ln_b, eps, patch,
+      reinterpret_cast<__nv_bfloat16*>(out));
+  VDK_CUDA_OK(cudaGetLastError());
+  return VDK_OK;
+}
+
+extern "C" size_t vdk_convnext_workspace_bytes(const vdk_convnext_net* net, int batch) {
+  if (!net || batch <= 0) return 0;
+  const size_t hw0 = static_cast<size_t>(net->image_size / 4) * (net->image_size / 4);
+  size_t max_mc = 0, max_m4c = 0;
+  size_t hw = hw0;
+  for (int s = 0; s < 4; ++s) {
+    if (s > 0) hw /= 4;
+    const size_t m = static_cast<size_t>(batch) * hw;
+    max_mc = std::max(max_mc, m * net->dims[s]);
+    max_m4c = std::max(max_m4c, m * net->dims[s] * 4);
+  }
+  const size_t patches = static_cast<size_t>(batch) * hw0 * 48;
+  // x (residual stream), y (dwconv+LN / patch rows), h (hidden 4C or stem patches), neck accumulators
+  return up256(max_mc * 2) * 2 + up256(std::max(max_m4c, patches) * 2) + up256(static_cast<size_t>(batch) * net->feat_dim * 4) + 1024;
+}
+
+extern "C" int vdk_convnext_forward(const vdk_convnext_net* net, const float* images, int batch, int l2_normalize,
+                                    float* embeddings, void* workspace, size_t workspace_bytes, void* stream) {
+  int rc = check_net(net);
+  if (rc != VDK_OK) return rc;
+  VDK_REQUIRE(images && embeddings && batch > 0, "vdk_convnext_forward: null image/embedding buffer");
+  VDK_REQUIRE(workspace && workspace_bytes >= vdk_convnext_workspace_bytes(net, batch),
+              "vdk_convnext_forward: workspace too small");
+  VDK_REQUIRE((reinterpret_cast<uintptr_t>(workspace) & 255) == 0 && (reinterpret_cast<uintptr_t>(images) & 15) == 0,
+              "vdk_convnext_forward: workspace must be 256-byte and images 16-byte aligned");
+  cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
+  const int S = net->image_size;
+  const size_t hw0 = static_cast<size_t>(S / 4) * (S / 4);
+  size_t max_mc = 0, max_m4c = 0, hwt = hw0;
+  for (int st = 0; st < 4; ++st) {
+    if (st > 0) hwt /= 4;
+    max_mc = std::max(max_mc, static_cast<size_t>(batch) * hwt * net->dims[st]);
+    max_m4c = std::max(max_m4c, static_cast<size_t>(batch) * hwt * net->dims[st] * 4);
+  }
+  uint8_t* ws = reinterpret_cast<uint8_t*>(workspace);
+  __nv_bfloat16* xbuf = reinterpret_cast<__nv_bfloat16*>(ws);
+  ws += up256(max_mc * 2);
+  __nv_bfloat16* ybuf = reinterpret_cast<__nv_bfloat16*>(ws);
+  ws += up256(max_mc * 2);
+  __nv_bfloat16* hbuf = reinterpret_cast<__nv_bfloat16*>(ws);
+  ws += up256(std::max(max_m4c, static_cast<size_t>(batch) * hw0 * 48) * 2);
+  float* nacc = reinterpret_cast<float*>(ws);
+
+  auto gemm = [&](const void* A, const void* Bw, void* D, int M, int N, int K, int epi, const float* bias,
+                  const float* gamma, const float* beta, const void* res, int out_dtype, int split) -> int {
+    vdk_gemm_desc g{};
+    g.A = A; g.B = Bw; g.D = D;
+    g.M = M; g.N = N; g.K = K; g.lda = K; g.ldb = K; g.ldd = N;
+    g.in_dtype = VDK_DTYPE_BF16; g.out_dtype = out_dtype; g.epilogue = epi;
+    g.bias = bias; g.gamma = gamma; g.beta = beta; g.residual = res; g.ldr = N;
+    g.ln_eps = 1e-6f; g.split_k = split;
+    return gemm_run(g, s);
+  };
+
+  // ---- stem: conv4x4/s4 as a GEMM over patch rows, + bias + LayerNorm2d in the epilogue ----
+  int H = S / 4, W = S / 4, C = net->dims[0];
+  int M = batch * H * W;
+  {
+    const int64_t total = static_cast<int64_t>(M) * 12;
+    const int blocks = static_cast<int>(std::min<int64_t>((total + 255) / 256, 148 * 16));
+    stem_patchify_kernel<<<blocks, 256, 0, s>>>(images, batch, S, S, hbuf);
+    VDK_CUDA_OK(cudaGetLastError());
+    rc = gemm(hbuf, net->stem_w, xbuf, M, C, 48, VDK_EPI_LAYERNORM, net->stem_b, net->stem_ln_w, net->stem_ln_b, nullptr,
+              VDK_DTYPE_BF16, 1);
+    if (rc != VDK_OK) return rc;
+  }
+  int blk = 0;
+  for (int st = 0; st < 4; ++st) {
+    if (st > 0) {
+      // ---- downsample: LayerNorm2d then conv2x2/s2 as a GEMM over (kh, kw, c) patch rows ----
+      const vdk_convnext_down* d = &net->down[st];
+      const int Cin = C;
+      const int64_t npix = static_cast<int64_t>(batch) * H * W;
+      ln_patchify_kernel<<<static_cast<unsigned>((npix * 32 + 255) / 256), 256, 0, s>>>(xbuf, batch, H, W, Cin, d->ln_w,
+                                                                                         d->ln_b, 1e-6f, 2, ybuf);
+      VDK_CUDA_OK(cudaGetLastError());
+      H /= 2; W /= 2; C = net->dims[st];
+      M = batch * H * W;
+      rc = gemm(ybuf, d->conv_w, xbuf, M, C, 4 * Cin, VDK_EPI_NONE, d->conv_b, nullptr, nullptr, nullptr, VDK_DTYPE_BF16, 1);
+      if (rc != VDK_OK) return rc;
+    }
+    for (int j = 0; j < net->depths[st]; ++j, ++blk) {
+      const vdk_convnext_block* b = &net->blocks[blk];
+      rc = launch_dwconv7_ln(xbuf, batch, H, W, C, b->dw_w, b->dw_b, b->ln_w, b->ln_b, 1e-6f, ybuf, s);
+      if (rc != VDK_OK) return rc;
+      rc = gemm(ybuf, b->fc1_w, hbuf, M, 4 * C, C, VDK_EPI_GELU, b->fc1_b, nullptr, nullptr, nullptr, VDK_DTYPE_BF16, 1);
+      if (rc != VDK_OK) return rc;
+      rc = gemm(hbuf, b->fc2_w, xbuf, M, C, 4 * C, VDK_EPI_SCALE_RESIDUAL, b->fc2_b, b->gamma, nullptr, xbuf, VDK_DTYPE_BF16, 1);
+      if (rc != VDK_OK) return rc;
+    }
+  }
+  // ---- head LayerNorm2d (applied by timm even with global_pool='') ----
+  {
+    const int64_t npix = static_cast<int64_t>(batch) * H * W;
+    ln_patchify_kernel<<<static_cast<unsigned>((npix * 32 + 255) / 256), 256, 0, s>>>(xbuf, batch, H, W, C, net->head_ln_w,
+                                                                                       net->head_ln_b, 1e-6f, 1, ybuf);
+    VDK_CUDA_OK(cudaGetLastError());
+  }
+  // ---- neck: BN2d -> Flatten -> Linear -> BN1d, all folded into one skinny GEMM (eval statistics) ----
+  {
+    const int Kn = H * W * C, F = net->feat_dim;
+    VDK_CUDA_OK(cudaMemsetAsync(nacc, 0, static_cast<size_t>(batch) * F * sizeof(float), s));
+    const int tiles = ((batch + 127) / 128) * ((F + 127) / 128);
+    int split = std::max(1, (2 * sm_count()) / std::max(1, tiles));
+    rc = gemm(ybuf, net->neck_w, nacc, batch, F, Kn, VDK_EPI_NONE, nullptr, nullptr, nullptr, nullptr, VDK_DTYPE_FP32, split);
+    if (rc != VDK_OK) return rc;
+    neck_finalize_kernel<<<(batch * 32 + 255) / 256, 256, 0, s>>>(nacc, batch, F, net->neck_b, l2_normalize, embeddings);
+    VDK_CUDA_OK(cudaGetLastError());
+  }
+  return VDK_OK;
+}

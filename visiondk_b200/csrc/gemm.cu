@@ -22,11 +22,14 @@ struct GemmParams {
   void* D;
   int ldd;
   const float* bias;
-  const float* gamma;
+  const float* gamma;  // layer-scale (SCALE_RESIDUAL) or LayerNorm weight (LAYERNORM)
+  const float* beta;   // LayerNorm bias
   const void* residual;
   int ldr;
   int out_dtype;
   int epilogue;
+  float ln_eps;
+  int split_k;  // > 1: each tile's K range is split over split_k work items, fp32 partials are atomically added
 };
 
 template <int BN>
@@ -79,8 +82,10 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
 
   const int num_m = (p.M + kBM - 1) / kBM;
   const int num_n = (p.N + BN - 1) / BN;
-  const int num_tiles = num_m * num_n;
-  const int num_kb = (p.K + kBK - 1) / kBK;
+  const int num_kb_total = (p.K + kBK - 1) / kBK;
+  const int kb_per_split = (num_kb_total + p.split_k - 1) / p.split_k;
+  const int num_tiles = num_m * num_n * p.split_k;  // work items; split index is the slowest dimension
+  (void)num_m;
 
   if (warp == 0 && lane == 0) {
     prefetch_tensormap(&map_a);
@@ -107,9 +112,12 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
       int stage = 0;
       uint32_t phase = 0;
       for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
-        const int m0 = (tile / num_n) * kBM;
-        const int n0 = (tile % num_n) * BN;
-        for (int kb = 0; kb < num_kb; ++kb) {
+        const int mn = tile % (num_m * num_n), split = tile / (num_m * num_n);
+        const int m0 = (mn / num_n) * kBM;
+        const int n0 = (mn % num_n) * BN;
+        const int kb0 = split * kb_per_split;
+        const int kb1 = min(kb0 + kb_per_split, num_kb_total);
+        for (int kb = kb0; kb < kb1; ++kb) {
           mbar_wait(&empty_bar[stage], phase ^ 1);
           uint8_t* sa = smem + stage * Cfg::kStageBytes;
           uint8_t* sb = sa + Cfg::kStageA;
@@ -136,7 +144,10 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
         mbar_wait(&tmem_empty[acc], acc_phase ^ 1);
         tc_fence_after();
         const uint32_t tmem_d = tmem_base + acc * BN;
-        for (int kb = 0; kb < num_kb; ++kb) {
+        const int split = tile / (num_m * num_n);
+        const int kb0 = split * kb_per_split;
+        const int kb1 = min(kb0 + kb_per_split, num_kb_total);
+        for (int kb = kb0; kb < kb1; ++kb) {
           mbar_wait(&full_bar[stage], phase);
           tc_fence_after();
           const uint32_t sa = smem_u32(smem + stage * Cfg::kStageBytes);
@@ -146,7 +157,7 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
 #pragma unroll
           for (int k = 0; k < kBK / 16; ++k) {
             // advance 16 elements (32 bytes) along K inside the 128-byte swizzle row: +2 in 16-byte units
-            umma_f16_ss(tmem_d, da + 2 * k, db + 2 * k, idesc, (kb | k) != 0 ? 1u : 0u);
+            umma_f16_ss(tmem_d, da + 2 * k, db + 2 * k, idesc, (kb > kb0 || k > 0) ? 1u : 0u);
           }
           umma_commit(&empty_bar[stage]);  // smem slot reusable once these MMAs retire
           if (++stage == Cfg::kStages) {
@@ -164,18 +175,62 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
     for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
       const int acc = it & 1;
       const uint32_t acc_phase = (it >> 1) & 1;
-      const int m0 = (tile / num_n) * kBM;
-      const int n0 = (tile % num_n) * BN;
+      const int mn = tile % (num_m * num_n);
+      const int m0 = (mn / num_n) * kBM;
+      const int n0 = (mn % num_n) * BN;
       const int row = m0 + lane_base + lane;
       mbar_wait(&tmem_full[acc], acc_phase);
       tc_fence_after();
+      const uint32_t tacc = tmem_base + (static_cast<uint32_t>(lane_base) << 16) + acc * BN;
+      float ln_mean = 0.f, ln_rstd = 1.f;
+      if (p.epilogue == VDK_EPI_LAYERNORM) {
+        // the tile spans the whole row (N <= BN): this thread owns every channel of its row in TMEM.
+        // pass 1: mean, pass 2: centred variance; the write pass below re-reads TMEM (cheap) instead of
+        // holding BN values in registers.
+        float sum = 0.f;
+#pragma unroll 1
+        for (int c = 0; c < BN / 32; ++c) {
+          uint32_t r[32];
+          tmem_ld_32x32b_x32(tacc + c * 32, r);
+          tmem_ld_wait();
+#pragma unroll
+          for (int j = 0; j < 32; ++j) {
+            const int col = c * 32 + j;
+            if (col < p.N) sum += __uint_as_float(r[j]) + (p.bias ? __ldg(p.bias + col) : 0.f);
+          }
+        }
+        ln_mean = sum / static_cast<float>(p.N);
+        float sq = 0.f;
+#pragma unroll 1
+        for (int c = 0; c < BN / 32; ++c) {
+          uint32_t r[32];
+          tmem_ld_32x32b_x32(tacc + c * 32, r);
+          tmem_ld_wait();
+#pragma unroll
+          for (int j = 0; j < 32; ++j) {
+            const int col = c * 32 + j;
+            if (col < p.N) {
+              const float d = __uint_as_float(r[j]) + (p.bias ? __ldg(p.bias + col) : 0.f) - ln_mean;
+              sq = fmaf(d, d, sq);
+            }
+          }
+        }
+        ln_rstd = rsqrtf(sq / static_cast<float>(p.N) + p.ln_eps);
+      }
 #pragma unroll 1
       for (int c = 0; c < BN / 32; ++c) {
         uint32_t r[32];
-        tmem_ld_32x32b_x32(tmem_base + (static_cast<uint32_t>(lane_base) << 16) + acc * BN + c * 32, r);
+        tmem_ld_32x32b_x32(tacc + c * 32, r);
         tmem_ld_wait();
         const int col0 = n0 + c * 32;
-        if (row < p.M && col0 < p.N) {
+        if (row < p.M && col0 < p.N && p.split_k > 1) {
+          // split-K: raw fp32 partial sums, combined in HBM (D was zeroed by the caller)
+          float* out = reinterpret_cast<float*>(p.D) + static_cast<size_t>(row) * p.ldd + col0;
+          const int ncols = min(32, p.N - col0);
+#pragma unroll
+          for (int j = 0; j < 32; ++j)
+            if (j < ncols) atomicAdd(out + j, __uint_as_float(r[j]));
+        } else if (row < p.M && col0 < p.N) {
           float v[32];
 #pragma unroll
           for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]);
@@ -192,6 +247,18 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
           if (p.epilogue == VDK_EPI_GELU) {
 #pragma unroll
             for (int j = 0; j < 32; ++j) v[j] = gelu_erf(v[j]);
+          } else if (p.epilogue == VDK_EPI_LAYERNORM) {
+#pragma unroll
+            for (int j = 0; j < 32; j += 4) {
+              if (j < ncols) {
+                const float4 g = __ldg(reinterpret_cast<const float4*>(p.gamma + col0 + j));
+                const float4 b = __ldg(reinterpret_cast<const float4*>(p.beta + col0 + j));
+                v[j] = (v[j] - ln_mean) * ln_rstd * g.x + b.x;
+                v[j + 1] = (v[j + 1] - ln_mean) * ln_rstd * g.y + b.y;
+                v[j + 2] = (v[j + 2] - ln_mean) * ln_rstd * g.z + b.z;
+                v[j + 3] = (v[j + 3] - ln_mean) * ln_rstd * g.w + b.w;
+              }
+            }
           } else if (p.epilogue == VDK_EPI_SCALE_RESIDUAL) {
 #pragma unroll
             for (int j = 0; j < 32; j += 4) {
@@ -266,7 +333,7 @@ static int launch_gemm(const CUtensorMap& ma, const CUtensorMap& mb, const GemmP
     VDK_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes));
     attr_set = true;
   }
-  const int num_tiles = ((p.M + kBM - 1) / kBM) * ((p.N + BN - 1) / BN);
+  const int num_tiles = ((p.M + kBM - 1) / kBM) * ((p.N + BN - 1) / BN) * p.split_k;
   const int grid = num_tiles < sm_count() ? num_tiles : sm_count();
   kern<<<grid, kGemmThreads, Cfg::kSmemBytes, stream>>>(ma, mb, p);
   VDK_CUDA_OK(cudaGetLastError());
@@ -275,39 +342,75 @@ static int launch_gemm(const CUtensorMap& ma, const CUtensorMap& mb, const GemmP
 
 }  // namespace vdk
 
+namespace vdk {
+
+int gemm_run(const vdk_gemm_desc& g, cudaStream_t s) {
+  VDK_REQUIRE(g.A && g.B && g.D, "vdk_gemm: null operand");
+  VDK_REQUIRE(g.M > 0 && g.N > 0 && g.K > 0, "vdk_gemm: empty problem M=%d N=%d K=%d", g.M, g.N, g.K);
+  VDK_REQUIRE(g.in_dtype == VDK_DTYPE_BF16 || g.in_dtype == VDK_DTYPE_FP16, "vdk_gemm: in_dtype must be bf16/fp16");
+  VDK_REQUIRE(g.out_dtype >= VDK_DTYPE_BF16 && g.out_dtype <= VDK_DTYPE_FP32, "vdk_gemm: bad out_dtype");
+  VDK_REQUIRE(g.N % 8 == 0 && g.K % 8 == 0, "vdk_gemm: N and K must be multiples of 8 (N=%d K=%d)", g.N, g.K);
+  VDK_REQUIRE(g.lda >= g.K && g.ldb >= g.K && g.ldd >= g.N && g.lda % 8 == 0 && g.ldb % 8 == 0, "vdk_gemm: bad pitches");
+  const int dalign = g.out_dtype == VDK_DTYPE_FP32 ? 4 : 8;
+  VDK_REQUIRE(g.ldd % dalign == 0, "vdk_gemm: ldd must keep rows 16-byte aligned");
+  VDK_REQUIRE((reinterpret_cast<uintptr_t>(g.D) & 15) == 0, "vdk_gemm: D must be 16-byte aligned");
+  VDK_REQUIRE(g.epilogue >= VDK_EPI_NONE && g.epilogue <= VDK_EPI_LAYERNORM, "vdk_gemm: bad epilogue");
+  if (g.epilogue == VDK_EPI_SCALE_RESIDUAL) {
+    VDK_REQUIRE(g.gamma && g.residual, "vdk_gemm: SCALE_RESIDUAL needs gamma and residual");
+    VDK_REQUIRE(g.ldr >= g.N && g.ldr % dalign == 0 && (reinterpret_cast<uintptr_t>(g.residual) & 15) == 0,
+                "vdk_gemm: residual must be 16-byte aligned rows");
+  }
+  if (g.epilogue == VDK_EPI_LAYERNORM) {
+    VDK_REQUIRE(g.gamma && g.beta, "vdk_gemm: LAYERNORM needs gamma (weight) and beta (bias)");
+    VDK_REQUIRE(g.N <= 256, "vdk_gemm: LAYERNORM epilogue needs the whole row in one tile (N <= 256, got %d)", g.N);
+    VDK_REQUIRE((reinterpret_cast<uintptr_t>(g.beta) & 15) == 0, "vdk_gemm: beta must be 16-byte aligned");
+  }
+  if (g.bias) VDK_REQUIRE((reinterpret_cast<uintptr_t>(g.bias) & 15) == 0, "vdk_gemm: bias must be 16-byte aligned");
+  if (g.gamma) VDK_REQUIRE((reinterpret_cast<uintptr_t>(g.gamma) & 15) == 0, "vdk_gemm: gamma must be 16-byte aligned");
+  int split = g.split_k < 1 ? 1 : g.split_k;
+  {
+    // every split must own at least one 64-wide K block (an empty split would publish an unwritten accumulator)
+    const int kbt = (g.K + kBK - 1) / kBK;
+    if (split > kbt) split = kbt;
+    const int per = (kbt + split - 1) / split;
+    split = (kbt + per - 1) / per;
+  }
+  if (split > 1)
+    VDK_REQUIRE(g.out_dtype == VDK_DTYPE_FP32 && g.epilogue == VDK_EPI_NONE && !g.bias,
+                "vdk_gemm: split_k > 1 needs fp32 output, no bias and no epilogue (partials are atomically added)");
+
+  // LayerNorm needs the whole row in one tile; otherwise narrow outputs use 128-column tiles (more tiles to
+  // balance over 148 SMs) and wide ones 256.
+  bool wide = (g.N % 256 == 0) || g.N > 512;
+  if (g.epilogue == VDK_EPI_LAYERNORM) wide = g.N > 128;
+  const int BN = wide ? 256 : 128;
+  CUtensorMap ma, mb;
+  int rc = make_tma_2d_16bit(&ma, g.A, (uint64_t)g.M, (uint64_t)g.K, (uint64_t)g.lda, kBM, kBK);
+  if (rc != VDK_OK) return rc;
+  rc = make_tma_2d_16bit(&mb, g.B, (uint64_t)g.N, (uint64_t)g.K, (uint64_t)g.ldb, BN, kBK);
+  if (rc != VDK_OK) return rc;
+  GemmParams p{g.M, g.N, g.K, g.D, g.ldd, g.bias, g.gamma, g.beta, g.residual, g.ldr, g.out_dtype, g.epilogue,
+               g.ln_eps, split};
+  const bool bf = g.in_dtype == VDK_DTYPE_BF16;
+  if (wide) return bf ? launch_gemm<256, true>(ma, mb, p, s) : launch_gemm<256, false>(ma, mb, p, s);
+  return bf ? launch_gemm<128, true>(ma, mb, p, s) : launch_gemm<128, false>(ma, mb, p, s);
+}
+
+}  // namespace vdk
+
+extern "C" int vdk_gemm(const vdk_gemm_desc* desc, void* stream) {
+  VDK_REQUIRE(desc, "vdk_gemm: null descriptor");
+  return vdk::gemm_run(*desc, reinterpret_cast<cudaStream_t>(stream));
+}
+
 extern "C" int vdk_gemm_tn(const void* A, const void* B, void* D, int M, int N, int K, int lda, int ldb, int ldd,
                            int in_dtype, int out_dtype, int epilogue, const float* bias, const float* gamma,
                            const void* residual, int ldr, void* stream) {
-  using namespace vdk;
-  VDK_REQUIRE(A && B && D, "vdk_gemm_tn: null operand");
-  VDK_REQUIRE(M > 0 && N > 0 && K > 0, "vdk_gemm_tn: empty problem M=%d N=%d K=%d", M, N, K);
-  VDK_REQUIRE(in_dtype == VDK_DTYPE_BF16 || in_dtype == VDK_DTYPE_FP16, "vdk_gemm_tn: in_dtype must be bf16/fp16");
-  VDK_REQUIRE(out_dtype >= VDK_DTYPE_BF16 && out_dtype <= VDK_DTYPE_FP32, "vdk_gemm_tn: bad out_dtype");
-  VDK_REQUIRE(N % 8 == 0 && K % 8 == 0, "vdk_gemm_tn: N and K must be multiples of 8 (N=%d K=%d)", N, K);
-  VDK_REQUIRE(lda >= K && ldb >= K && ldd >= N && lda % 8 == 0 && ldb % 8 == 0, "vdk_gemm_tn: bad pitches");
-  VDK_REQUIRE(ldd % (out_dtype == VDK_DTYPE_FP32 ? 4 : 8) == 0, "vdk_gemm_tn: ldd must keep rows 16-byte aligned");
-  VDK_REQUIRE((reinterpret_cast<uintptr_t>(D) & 15) == 0, "vdk_gemm_tn: D must be 16-byte aligned");
-  VDK_REQUIRE(epilogue >= VDK_EPI_NONE && epilogue <= VDK_EPI_SCALE_RESIDUAL, "vdk_gemm_tn: bad epilogue");
-  if (epilogue == VDK_EPI_SCALE_RESIDUAL) {
-    VDK_REQUIRE(gamma && residual, "vdk_gemm_tn: SCALE_RESIDUAL needs gamma and residual");
-    VDK_REQUIRE(ldr >= N && ldr % (out_dtype == VDK_DTYPE_FP32 ? 4 : 8) == 0 &&
-                    (reinterpret_cast<uintptr_t>(residual) & 15) == 0,
-                "vdk_gemm_tn: residual must be 16-byte aligned rows");
-  }
-  if (bias) VDK_REQUIRE((reinterpret_cast<uintptr_t>(bias) & 15) == 0, "vdk_gemm_tn: bias must be 16-byte aligned");
-  if (gamma) VDK_REQUIRE((reinterpret_cast<uintptr_t>(gamma) & 15) == 0, "vdk_gemm_tn: gamma must be 16-byte aligned");
-
-  // Narrow outputs use 128-column tiles (more tiles to balance over 148 SMs); wide ones 256.
-  const bool wide = (N % 256 == 0) || N > 512;
-  const int BN = wide ? 256 : 128;
-  CUtensorMap ma, mb;
-  int rc = make_tma_2d_16bit(&ma, A, (uint64_t)M, (uint64_t)K, (uint64_t)lda, kBM, kBK);
-  if (rc != VDK_OK) return rc;
-  rc = make_tma_2d_16bit(&mb, B, (uint64_t)N, (uint64_t)K, (uint64_t)ldb, BN, kBK);
-  if (rc != VDK_OK) return rc;
-  GemmParams p{M, N, K, D, ldd, bias, gamma, residual, ldr, out_dtype, epilogue};
-  cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
-  const bool bf = in_dtype == VDK_DTYPE_BF16;
-  if (wide) return bf ? launch_gemm<256, true>(ma, mb, p, s) : launch_gemm<256, false>(ma, mb, p, s);
-  return bf ? launch_gemm<128, true>(ma, mb, p, s) : launch_gemm<128, false>(ma, mb, p, s);
+  vdk_gemm_desc g{};
+  g.A = A; g.B = B; g.D = D;
+  g.M = M; g.N = N; g.K = K; g.lda = lda; g.ldb = ldb; g.ldd = ldd;
+  g.in_dtype = in_dtype; g.out_dtype = out_dtype; g.epilogue = epilogue;
+  g.bias = bias; g.gamma = gamma; g.residual = residual; g.ldr = ldr;
+  g.split_k = 1;
+  return vdk::gemm_run(g, reinterpret_cast<cudaStream_t>(stream));
 }

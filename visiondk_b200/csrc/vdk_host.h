@@ -37,3 +37,8 @@ int make_tma_2d_16bit(CUtensorMap* map, const void* base, uint64_t rows, uint64_
 int sm_count();
 
 }  // namespace vdk
+
+namespace vdk {
+// Internal form of vdk_gemm used by the composite entry points (convnext forward, heads).
+int gemm_run(const vdk_gemm_desc& g, cudaStream_t stream);
+}  // namespace vdk
