@@ -150,7 +150,8 @@ typedef struct vdk_topk_plan {
   int64_t n_gallery;     /* rows of the (local shard of the) gallery */
   int dim;               /* embedding width, multiple of 64, <= 512 */
   int k;                 /* neighbours wanted, 1..1024 */
-  int cand_capacity;     /* per-query candidate slots (power of two, >= 2k) */
+  int cand_capacity;     /* per-query slots for one range's admitted candidates (multiple of 32, >= 2k) */
+  int carry_capacity;    /* per-query slots for survivors carried between ranges (in [2k, 4096]) */
   int n_stages;          /* gallery is scanned in n_stages ranges; thresholds tighten between them */
   int64_t stage_end[8];  /* exclusive end row of each stage (last == n_gallery) */
 } vdk_topk_plan;

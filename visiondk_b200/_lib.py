@@ -24,6 +24,7 @@ class TopkPlan(C.Structure):
         ("dim", C.c_int),
         ("k", C.c_int),
         ("cand_capacity", C.c_int),
+        ("carry_capacity", C.c_int),
         ("n_stages", C.c_int),
         ("stage_end", C.c_int64 * 8),
     ]

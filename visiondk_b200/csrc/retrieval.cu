@@ -7,11 +7,13 @@
 //   rows_prepare   fp32 rows -> canonical unit rows (fp32) + fp16 copy + per-row rounding-error norm
 //   score_filter   fp16 tcgen05 GEMM of a 128-query tile (resident in smem) against streamed gallery tiles;
 //                  the epilogue never writes the score matrix: each thread owns one query row in TMEM and
-//                  appends only scores >= tau[row] to that row's candidate list
+//                  appends only scores >= tau[row] to a segment of that row's candidate list that this CTA
+//                  owns exclusively (plain stores, a register counter — no atomics on the scan path)
 //   select         per query: k-th largest approximate score A_k (radix select), keep a >= A_k - 2*eps
-//                  (eps bounds |approx - canonical|, so the true top-k survive), tighten tau for the next
-//                  gallery range; on the last range re-score survivors canonically (fp64, fixed order) and
-//                  sort by (score desc, id asc)
+//                  (eps bounds |approx - canonical|, so the true top-k survive) as the row's carry list and
+//                  tighten tau for the next gallery range
+//   rerank         after the last range: canonical re-score of the carry list (fp64, fixed order), sort by
+//                  (score desc, id asc), emit k
 // The gallery is scanned in geometrically growing ranges so that tau is tight when most of it streams by.
 #include "vdk_host.h"
 #include "vdk_ptx.cuh"
@@ -104,26 +106,22 @@ constexpr int kGStageBytes = kGN * kSBK * 2;   // 32 KB
 constexpr int kGStages = 3;
 constexpr int kScoreThreads = 192;
 constexpr int kMaxKB = 8;         // dim <= 512
+constexpr int kMaxSeg = 32;       // gallery splits per range = candidate segments per query
 
 struct ScoreParams {
   int n_query;
   int num_kb;  // dim / 64
   int64_t g_lo, g_hi;
   int n_qtiles, n_splits, tiles_per_split, n_tiles;
-  const float* tau;  // per-query admission threshold (sparse mode)
-  uint2* cand;       // [n_query][cap] {score bits, gallery row}
-  int cap;
-  unsigned* counts;  // [n_query]
+  const float* tau;   // per-query admission threshold (sparse mode)
+  uint2* seg;         // [n_query][seg_stride] {score bits, gallery row}; split s owns [s*seg_cap, (s+1)*seg_cap)
+  int seg_stride;     // entries per query
+  int seg_cap;        // entries per (query, split)
+  unsigned* seg_cnt;  // [n_query][kMaxSeg] admitted count per (query, split) — may exceed seg_cap (overflow)
 };
 
 static int score_smem_bytes(int num_kb) {
   return num_kb * kQBlockBytes + kGStages * kGStageBytes + (2 * kGStages + 6) * 8 + 16 + 1024;
-}
-
-__device__ __noinline__ void cand_append(uint2* cand, unsigned* counts, int cap, int row, float a, uint32_t gidx) {
-  const unsigned pos = atomicAdd(&counts[row], 1u);
-  if (pos < static_cast<unsigned>(cap))
-    cand[static_cast<size_t>(row) * cap + pos] = make_uint2(__float_as_uint(a), gidx);
 }
 
 template <bool kDense>
@@ -248,6 +246,9 @@ score_filter_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_cons
       const bool row_ok = row < p.n_query;
       float tau = INFINITY;
       if (!kDense && row_ok) tau = p.tau[row];
+      // this thread is the only writer of segment (row, sp): a register counter and plain stores suffice
+      uint2* seg = p.seg + static_cast<size_t>(row_ok ? row : 0) * p.seg_stride + (kDense ? 0 : sp * p.seg_cap);
+      unsigned cnt = 0;
       for (int t = t0; t < t1; ++t, ++it) {
         const int acc = it & 1;
         mbar_wait(&tmem_full[acc], (it >> 1) & 1);
@@ -261,7 +262,7 @@ score_filter_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_cons
           const int64_t g0 = gbase + c * 32;
           if (kDense) {
             if (row_ok && g0 < p.g_hi) {
-              uint2* dst = p.cand + static_cast<size_t>(row) * p.cap + (g0 - p.g_lo);
+              uint2* dst = seg + (g0 - p.g_lo);
               const int64_t rem = p.g_hi - g0;
               const int nv = rem < 32 ? static_cast<int>(rem) : 32;
               if (nv == 32) {
@@ -276,15 +277,27 @@ score_filter_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_cons
               }
             }
           } else {
-            float m = __uint_as_float(r[0]);
+            // two-level test: group maxima first, so the common case costs ~1 instruction per score
+            float gm[4];
 #pragma unroll
-            for (int j = 1; j < 32; ++j) m = fmaxf(m, __uint_as_float(r[j]));
-            if (m >= tau) {  // rare once tau is tight; rows beyond n_query carry tau = +inf
+            for (int q = 0; q < 4; ++q) {
+              float m = __uint_as_float(r[q * 8]);
 #pragma unroll
-              for (int j = 0; j < 32; ++j) {
-                const float a = __uint_as_float(r[j]);
-                if (a >= tau && g0 + j < p.g_hi)
-                  cand_append(p.cand, p.counts, p.cap, row, a, static_cast<uint32_t>(g0 + j));
+              for (int j = 1; j < 8; ++j) m = fmaxf(m, __uint_as_float(r[q * 8 + j]));
+              gm[q] = m;
+            }
+            if (fmaxf(fmaxf(gm[0], gm[1]), fmaxf(gm[2], gm[3])) >= tau) {  // rows beyond n_query carry tau = +inf
+#pragma unroll
+              for (int q = 0; q < 4; ++q) {
+                if (gm[q] >= tau) {
+#pragma unroll
+                  for (int j = q * 8; j < q * 8 + 8; ++j) {
+                    if (__uint_as_float(r[j]) >= tau && g0 + j < p.g_hi) {
+                      if (cnt < static_cast<unsigned>(p.seg_cap)) seg[cnt] = make_uint2(r[j], static_cast<uint32_t>(g0 + j));
+                      ++cnt;
+                    }
+                  }
+                }
               }
             }
           }
@@ -292,6 +305,7 @@ score_filter_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_cons
         tc_fence_before();
         mbar_arrive(&tmem_empty[acc]);
       }
+      if (!kDense && row_ok) p.seg_cnt[static_cast<size_t>(row) * kMaxSeg + sp] = cnt;
     }
   }
 
@@ -304,146 +318,184 @@ score_filter_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_cons
 }
 
 // ------------------------------------------------------------------------------------------------
-// select: one CTA per query
+// select: one CTA per query — k-th largest approximate score, admission bound, compaction of survivors
 // ------------------------------------------------------------------------------------------------
-constexpr int kSelThreads = 256;
-constexpr int kSortMax = 2048;  // survivors the final sort can hold
+constexpr int kSelThreads = 128;
 
 struct SelectParams {
-  int n_query, dim, k, cap;
-  uint2* cand;
-  unsigned* counts;
+  int n_query, k;
+  const uint2* carry_in;  // [n_query][carry_cap] survivors of earlier ranges
+  uint2* carry_out;       // [n_query][carry_cap]
+  unsigned* carry_cnt;    // [n_query] in: entries in carry_in; out: entries in carry_out
+  int carry_cap;
+  const uint2* seg;       // this range's admitted candidates
+  int seg_stride, seg_cap, n_seg;
+  const unsigned* seg_cnt;
+  int dense_n;            // > 0: the range was scored densely: seg holds dense_n entries per row
   float* tau;
-  const float* eps;  // per-query bound on |approx - canonical|
-  int dense_n;       // > 0: counts[] are implied (dense stage wrote dense_n entries per row)
-  int final_stage;
+  const float* eps;       // per-query bound on |approx - canonical|
+  int32_t* status;        // {overflow_rows, max_candidates, max_survivors, reserved}
+};
+
+__global__ void __launch_bounds__(kSelThreads) select_kernel(const SelectParams p) {
+  __shared__ unsigned hist[256];
+  __shared__ unsigned s_cnt[kMaxSeg + 1];
+  __shared__ unsigned s_bin, s_krem, s_m, s_over;
+  const int row = blockIdx.x;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+
+  // entry lists of this row: list 0 = carry, lists 1.. = segments (or one dense list)
+  const int n_lists = 1 + (p.dense_n > 0 ? 1 : p.n_seg);
+  if (tid == 0) {
+    s_over = 0;
+    s_m = 0;
+    s_cnt[0] = min(p.carry_cnt[row], static_cast<unsigned>(p.carry_cap));
+  }
+  if (tid >= 1 && tid < n_lists) {
+    if (p.dense_n > 0) {
+      s_cnt[1] = static_cast<unsigned>(p.dense_n);
+    } else {
+      const unsigned c = p.seg_cnt[static_cast<size_t>(row) * kMaxSeg + (tid - 1)];
+      if (c > static_cast<unsigned>(p.seg_cap)) atomicOr(&s_over, 1u);
+      s_cnt[tid] = min(c, static_cast<unsigned>(p.seg_cap));
+    }
+  }
+  __syncthreads();
+  auto list_ptr = [&](int l) -> const uint2* {
+    if (l == 0) return p.carry_in + static_cast<size_t>(row) * p.carry_cap;
+    return p.seg + static_cast<size_t>(row) * p.seg_stride + static_cast<size_t>(l - 1) * (p.dense_n > 0 ? 0 : p.seg_cap);
+  };
+  unsigned n = 0;
+  for (int l = 0; l < n_lists; ++l) n += s_cnt[l];
+
+  // ---- radix select of the k-th largest key over all lists (4 x 8 bits, MSB first) ----
+  float tau_use = -INFINITY;
+  if (n >= static_cast<unsigned>(p.k)) {
+    uint32_t prefix = 0, mask = 0;
+    unsigned k_rem = static_cast<unsigned>(p.k);
+    for (int shift = 24; shift >= 0; shift -= 8) {
+      for (int i = tid; i < 256; i += kSelThreads) hist[i] = 0;
+      __syncthreads();
+      for (int l = 0; l < n_lists; ++l) {
+        const uint2* e = list_ptr(l);
+        const unsigned c = s_cnt[l];
+        for (unsigned i = tid; i < c; i += kSelThreads) {
+          const uint32_t key = ord_u32(__uint_as_float(e[i].x));
+          if ((key & mask) == prefix) atomicAdd(&hist[(key >> shift) & 255u], 1u);
+        }
+      }
+      __syncthreads();
+      if (warp == 0) {
+        // lane l owns bins 255-8l .. 248-8l (descending); find the bin where the running count reaches k_rem
+        unsigned part = 0;
+#pragma unroll
+        for (int j = 0; j < 8; ++j) part += hist[255 - 8 * lane - j];
+        unsigned incl = part;
+#pragma unroll
+        for (int off = 1; off < 32; off <<= 1) {
+          const unsigned o = __shfl_up_sync(0xffffffffu, incl, off);
+          if (lane >= off) incl += o;
+        }
+        const unsigned excl = incl - part;
+        if (excl < k_rem && incl >= k_rem) {  // exactly one lane
+          unsigned acc = excl;
+          int b = 255 - 8 * lane;
+          for (int j = 0; j < 8; ++j, --b) {
+            if (acc + hist[b] >= k_rem) break;
+            acc += hist[b];
+          }
+          s_bin = static_cast<unsigned>(b);
+          s_krem = k_rem - acc;
+        }
+      }
+      __syncthreads();
+      prefix |= s_bin << shift;
+      mask |= 255u << shift;
+      k_rem = s_krem;
+      __syncthreads();
+    }
+    // admission bound: everything within 2*eps below the k-th largest approximate score may be a true top-k member
+    tau_use = unord_u32(prefix) - 2.0f * p.eps[row];
+  }
+
+  // ---- compaction of the survivors into the other carry buffer ----
+  uint2* out = p.carry_out + static_cast<size_t>(row) * p.carry_cap;
+  for (int l = 0; l < n_lists; ++l) {
+    const uint2* e = list_ptr(l);
+    const unsigned c = s_cnt[l];
+    for (unsigned i = tid; i < c; i += kSelThreads) {
+      const uint2 v = e[i];
+      if (__uint_as_float(v.x) >= tau_use) {
+        const unsigned pos = atomicAdd(&s_m, 1u);
+        if (pos < static_cast<unsigned>(p.carry_cap)) out[pos] = v;
+      }
+    }
+  }
+  __syncthreads();
+  if (tid == 0) {
+    const unsigned m = s_m;
+    p.carry_cnt[row] = min(m, static_cast<unsigned>(p.carry_cap));
+    p.tau[row] = tau_use;
+    if (s_over || m > static_cast<unsigned>(p.carry_cap)) atomicAdd(&p.status[0], 1);
+    atomicMax(&p.status[1], static_cast<int>(min(n, 0x7fffffffu)));
+    atomicMax(&p.status[2], static_cast<int>(min(m, 0x7fffffffu)));
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// rerank: canonical re-score of a row's carry list, sort by (score desc, id asc), emit k
+// ------------------------------------------------------------------------------------------------
+constexpr int kRerankThreads = 256;
+
+struct RerankParams {
+  int n_query, dim, k;
+  const uint2* carry;
+  const unsigned* carry_cnt;
+  int carry_cap;
   const float* q32;
   const float* g32;
   int64_t id_offset;
   float* out_scores;
   int64_t* out_ids;
-  int32_t* status;  // {overflow_rows, max_candidates, max_survivors, reserved}
 };
 
-// k-th largest of keys[0..n) (order-preserving uint32), n >= k >= 1.  All threads must call.
-__device__ uint32_t block_kth_largest(const uint32_t* keys, int n, int k, unsigned* hist /*[256]*/,
-                                      unsigned* bcast /*[2]*/) {
-  uint32_t prefix = 0, mask = 0;
-  int k_rem = k;
-  for (int shift = 24; shift >= 0; shift -= 8) {
-    for (int i = threadIdx.x; i < 256; i += blockDim.x) hist[i] = 0;
-    __syncthreads();
-    for (int i = threadIdx.x; i < n; i += blockDim.x) {
-      const uint32_t key = keys[i];
-      if ((key & mask) == prefix) atomicAdd(&hist[(key >> shift) & 255u], 1u);
-    }
-    __syncthreads();
-    if (threadIdx.x == 0) {
-      int acc = 0, b = 255;
-      for (; b > 0; --b) {
-        if (acc + static_cast<int>(hist[b]) >= k_rem) break;
-        acc += hist[b];
-      }
-      bcast[0] = static_cast<unsigned>(b);
-      bcast[1] = static_cast<unsigned>(k_rem - acc);
-    }
-    __syncthreads();
-    prefix |= bcast[0] << shift;
-    mask |= 255u << shift;
-    k_rem = static_cast<int>(bcast[1]);
-    __syncthreads();
-  }
-  return prefix;
-}
-
-__global__ void __launch_bounds__(kSelThreads) select_kernel(const SelectParams p) {
-  extern __shared__ uint8_t sel_smem[];
-  uint32_t* s_key = reinterpret_cast<uint32_t*>(sel_smem);          // [cap]
-  uint32_t* s_idx = s_key + p.cap;                                   // [cap]
-  unsigned long long* s_sort = reinterpret_cast<unsigned long long*>(s_idx + p.cap);  // [kSortMax] (final only)
-  __shared__ unsigned hist[256];
-  __shared__ unsigned bcast[2];
-  __shared__ unsigned s_m;
-
+__global__ void __launch_bounds__(kRerankThreads) rerank_kernel(const RerankParams p) {
+  extern __shared__ unsigned long long s_sort[];  // [pow2 >= m]
   const int row = blockIdx.x;
-  const int tid = threadIdx.x;
-  const unsigned cnt = p.dense_n > 0 ? static_cast<unsigned>(p.dense_n) : p.counts[row];
-  const int n = static_cast<int>(min(cnt, static_cast<unsigned>(p.cap)));
-  uint2* rc = p.cand + static_cast<size_t>(row) * p.cap;
-  if (tid == 0) {
-    if (cnt > static_cast<unsigned>(p.cap)) atomicAdd(&p.status[0], 1);
-    atomicMax(&p.status[1], static_cast<int>(min(cnt, 0x7fffffffu)));
-    s_m = 0;
-  }
-  for (int i = tid; i < n; i += blockDim.x) {
-    const uint2 e = rc[i];
-    s_key[i] = ord_u32(__uint_as_float(e.x));
-    s_idx[i] = e.y;
-  }
-  __syncthreads();
-
-  // admission bound: everything within 2*eps below the k-th largest approximate score may be a true top-k member
-  float tau_use = -INFINITY;
-  if (n >= p.k) {
-    const uint32_t kth = block_kth_largest(s_key, n, p.k, hist, bcast);
-    tau_use = unord_u32(kth) - 2.0f * p.eps[row];
-  }
-  const uint32_t tau_key = ord_u32(tau_use);
-
-  if (!p.final_stage) {
-    // compact survivors to the front of the row's list; later ranges append behind them
-    for (int i = tid; i < n; i += blockDim.x) {
-      if (s_key[i] >= tau_key) {
-        const unsigned pos = atomicAdd(&s_m, 1u);
-        rc[pos] = make_uint2(__float_as_uint(unord_u32(s_key[i])), s_idx[i]);
-      }
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  constexpr int nwarps = kRerankThreads / 32;
+  const int m = static_cast<int>(min(p.carry_cnt[row], static_cast<unsigned>(p.carry_cap)));
+  const uint2* e = p.carry + static_cast<size_t>(row) * p.carry_cap;
+  const float* q = p.q32 + static_cast<size_t>(row) * p.dim;
+  // two candidates per warp iteration: their row loads are independent, which hides the gather latency
+  for (int c = warp * 2; c < m; c += nwarps * 2) {
+    const uint32_t gi0 = e[c].y;
+    const bool has1 = c + 1 < m;
+    const uint32_t gi1 = has1 ? e[c + 1].y : gi0;
+    const float* g0 = p.g32 + static_cast<size_t>(gi0) * p.dim;
+    const float* g1 = p.g32 + static_cast<size_t>(gi1) * p.dim;
+    double a0 = 0.0, a1 = 0.0;
+    for (int i = lane; i < p.dim; i += 32) {
+      const double qv = static_cast<double>(q[i]);
+      a0 = fma(qv, static_cast<double>(g0[i]), a0);
+      a1 = fma(qv, static_cast<double>(g1[i]), a1);
     }
-    __syncthreads();
-    if (tid == 0) {
-      p.counts[row] = s_m;
-      p.tau[row] = tau_use;
-    }
-    return;
-  }
-
-  // ---- final range: canonical re-score of the survivors, then sort by (score desc, id asc) ----
-  // survivors are gathered into s_sort as (idx) first, then overwritten with sortable 64-bit keys
-  for (int i = tid; i < n; i += blockDim.x) {
-    if (s_key[i] >= tau_key) {
-      const unsigned pos = atomicAdd(&s_m, 1u);
-      if (pos < kSortMax) s_sort[pos] = s_idx[i];
-    }
-  }
-  __syncthreads();
-  const unsigned m_all = s_m;
-  const int m = static_cast<int>(min(m_all, static_cast<unsigned>(kSortMax)));
-  if (tid == 0) {
-    if (m_all > kSortMax) atomicAdd(&p.status[0], 1);
-    atomicMax(&p.status[2], static_cast<int>(m_all));
-  }
-  {
-    const int warp = tid >> 5, lane = tid & 31, nwarps = blockDim.x >> 5;
-    const float* q = p.q32 + static_cast<size_t>(row) * p.dim;
-    for (int c = warp; c < m; c += nwarps) {
-      const uint32_t gi = static_cast<uint32_t>(s_sort[c]);
-      const float* g = p.g32 + static_cast<size_t>(gi) * p.dim;
-      double acc = 0.0;
-      for (int i = lane; i < p.dim; i += 32) acc = fma(static_cast<double>(q[i]), static_cast<double>(g[i]), acc);
-      acc = warp_sum_f64(acc);
-      __syncwarp();
-      if (lane == 0)
-        s_sort[c] = (static_cast<unsigned long long>(ord_u32(static_cast<float>(acc))) << 32) |
-                    static_cast<unsigned long long>(~gi);
+    a0 = warp_sum_f64(a0);
+    a1 = warp_sum_f64(a1);
+    if (lane == 0) {
+      s_sort[c] = (static_cast<unsigned long long>(ord_u32(static_cast<float>(a0))) << 32) | static_cast<unsigned long long>(~gi0);
+      if (has1)
+        s_sort[c + 1] = (static_cast<unsigned long long>(ord_u32(static_cast<float>(a1))) << 32) | static_cast<unsigned long long>(~gi1);
     }
   }
   int m2 = 1;
   while (m2 < m) m2 <<= 1;
-  for (int i = m + tid; i < m2; i += blockDim.x) s_sort[i] = 0ull;  // below every real key
+  for (int i = m + tid; i < m2; i += kRerankThreads) s_sort[i] = 0ull;  // below every real key
   __syncthreads();
-  // bitonic sort, descending
+  // bitonic sort, descending: key = (ordered score, ~id) so equal scores order by ascending id
   for (int size = 2; size <= m2; size <<= 1) {
     for (int stride = size >> 1; stride > 0; stride >>= 1) {
-      for (int i = tid; i < (m2 >> 1); i += blockDim.x) {
+      for (int i = tid; i < (m2 >> 1); i += kRerankThreads) {
         const int lo = 2 * i - (i & (stride - 1));
         const int hi = lo + stride;
         const bool desc = ((lo & size) == 0);
@@ -456,7 +508,7 @@ __global__ void __launch_bounds__(kSelThreads) select_kernel(const SelectParams 
       __syncthreads();
     }
   }
-  for (int j = tid; j < p.k; j += blockDim.x) {
+  for (int j = tid; j < p.k; j += kRerankThreads) {
     float sc = -FLT_MAX;  // faiss pads inner-product results with lowest() and id -1
     int64_t id = -1;
     if (j < m) {
@@ -471,16 +523,16 @@ __global__ void __launch_bounds__(kSelThreads) select_kernel(const SelectParams 
 
 __global__ void eps_kernel(const float* __restrict__ q_norm, const float* __restrict__ q_err,
                            const float* __restrict__ g_norm_max, const float* __restrict__ g_err_max, int n,
-                           float* __restrict__ eps, float* __restrict__ tau, unsigned* __restrict__ counts) {
+                           float* __restrict__ eps, float* __restrict__ tau, unsigned* __restrict__ carry_cnt) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
-  const float gn = *g_norm_max, ge = *g_err_max;
+  const float gn = g_norm_max ? *g_norm_max : 0.f, ge = g_err_max ? *g_err_max : 0.f;
   const float qn = q_norm[i] + q_err[i];
   // |approx - canonical| <= |dq.g| + |qh.dg| + tensor-core accumulation error ("error bound")
   const float e = q_err[i] * gn + qn * ge + 1.220703125e-4f /*2^-13*/ * qn * (gn + ge);
   eps[i] = e * 1.0001f + 1e-30f;
   tau[i] = -INFINITY;
-  counts[i] = 0;
+  carry_cnt[i] = 0;
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -551,9 +603,47 @@ static int pow2_ceil(int v) {
   return p;
 }
 
+struct TopkWorkspace {
+  uint2* seg;
+  uint2* carry[2];
+  unsigned* seg_cnt;
+  unsigned* carry_cnt;
+  float* tau;
+  float* eps;
+};
+static size_t align256(size_t v) { return (v + 255) & ~static_cast<size_t>(255); }
+static size_t workspace_bytes(int64_t nq, int seg_stride, int carry_cap) {
+  const size_t n = static_cast<size_t>(nq);
+  return align256(n * seg_stride * sizeof(uint2)) + 2 * align256(n * carry_cap * sizeof(uint2)) +
+         align256(n * kMaxSeg * sizeof(unsigned)) + 3 * align256(n * sizeof(float)) + 256;
+}
+static TopkWorkspace carve_workspace(void* workspace, int64_t nq, int seg_stride, int carry_cap) {
+  const size_t n = static_cast<size_t>(nq);
+  uint8_t* ws = reinterpret_cast<uint8_t*>(workspace);
+  TopkWorkspace w;
+  w.seg = reinterpret_cast<uint2*>(ws);
+  ws += align256(n * seg_stride * sizeof(uint2));
+  for (int i = 0; i < 2; ++i) {
+    w.carry[i] = reinterpret_cast<uint2*>(ws);
+    ws += align256(n * carry_cap * sizeof(uint2));
+  }
+  w.seg_cnt = reinterpret_cast<unsigned*>(ws);
+  ws += align256(n * kMaxSeg * sizeof(unsigned));
+  w.carry_cnt = reinterpret_cast<unsigned*>(ws);
+  ws += align256(n * sizeof(float));
+  w.tau = reinterpret_cast<float*>(ws);
+  ws += align256(n * sizeof(float));
+  w.eps = reinterpret_cast<float*>(ws);
+  return w;
+}
+
+struct RangeLaunch {
+  int n_splits, seg_cap;
+};
+
 // One gallery range [lo, hi) of the scan: the launch both vdk_ip_topk and vdk_score_range use.
 static int launch_score_range(const CUtensorMap& mq, const CUtensorMap& mg, int nq, int dim, int64_t lo, int64_t hi,
-                              bool dense, const float* tau, uint2* cand, int cap, unsigned* counts, cudaStream_t s) {
+                              bool dense, const TopkWorkspace& w, int seg_stride, RangeLaunch* info, cudaStream_t s) {
   static bool score_attr = false;
   if (!score_attr) {
     VDK_CUDA_OK(cudaFuncSetAttribute(score_filter_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
@@ -563,7 +653,7 @@ static int launch_score_range(const CUtensorMap& mq, const CUtensorMap& mg, int 
     score_attr = true;
   }
   VDK_REQUIRE(lo % kGN == 0, "score range must start on a multiple of %d", kGN);
-  if (dense) VDK_REQUIRE(hi - lo <= cap, "dense first range exceeds candidate capacity");
+  if (dense) VDK_REQUIRE(hi - lo <= seg_stride, "dense first range exceeds candidate capacity");
   const int sms = sm_count();
   ScoreParams p{};
   p.n_query = nq;
@@ -572,14 +662,21 @@ static int launch_score_range(const CUtensorMap& mq, const CUtensorMap& mg, int 
   p.g_hi = hi;
   p.n_qtiles = (nq + kQM - 1) / kQM;
   p.n_tiles = static_cast<int>((hi - lo + kGN - 1) / kGN);
+  // enough (query tile, gallery split) units to fill the SMs ~4x over, at most kMaxSeg splits (one candidate
+  // segment per split and query)
   int splits = (4 * sms + p.n_qtiles - 1) / p.n_qtiles;
-  splits = std::max(1, std::min(splits, p.n_tiles));
+  splits = std::max(1, std::min(std::min(splits, kMaxSeg), p.n_tiles));
   p.tiles_per_split = (p.n_tiles + splits - 1) / splits;
   p.n_splits = (p.n_tiles + p.tiles_per_split - 1) / p.tiles_per_split;
-  p.tau = tau;
-  p.cand = cand;
-  p.cap = cap;
-  p.counts = counts;
+  p.tau = w.tau;
+  p.seg = w.seg;
+  p.seg_stride = seg_stride;
+  p.seg_cap = seg_stride / p.n_splits;
+  p.seg_cnt = w.seg_cnt;
+  if (info) {
+    info->n_splits = p.n_splits;
+    info->seg_cap = p.seg_cap;
+  }
   const int units = p.n_qtiles * p.n_splits;
   const int grid = std::min(units, sms);
   const int smem = score_smem_bytes(p.num_kb);
@@ -589,26 +686,6 @@ static int launch_score_range(const CUtensorMap& mq, const CUtensorMap& mg, int 
     score_filter_kernel<false><<<grid, kScoreThreads, smem, s>>>(mq, mg, p);
   VDK_CUDA_OK(cudaGetLastError());
   return VDK_OK;
-}
-
-struct TopkWorkspace {
-  uint2* cand;
-  unsigned* counts;
-  float* tau;
-  float* eps;
-};
-static size_t align256(size_t v) { return (v + 255) & ~static_cast<size_t>(255); }
-static TopkWorkspace carve_workspace(void* workspace, int64_t nq, int cap) {
-  uint8_t* ws = reinterpret_cast<uint8_t*>(workspace);
-  TopkWorkspace w;
-  w.cand = reinterpret_cast<uint2*>(ws);
-  ws += align256(static_cast<size_t>(nq) * cap * sizeof(uint2));
-  w.counts = reinterpret_cast<unsigned*>(ws);
-  ws += align256(static_cast<size_t>(nq) * sizeof(float));
-  w.tau = reinterpret_cast<float*>(ws);
-  ws += align256(static_cast<size_t>(nq) * sizeof(float));
-  w.eps = reinterpret_cast<float*>(ws);
-  return w;
 }
 
 }  // namespace vdk
@@ -649,7 +726,8 @@ extern "C" int vdk_topk_plan_default(vdk_topk_plan* plan, int64_t n_query, int64
   plan->n_gallery = n_gallery;
   plan->dim = dim;
   plan->k = k;
-  plan->cand_capacity = pow2_ceil(std::max(8192, 16 * k));
+  plan->cand_capacity = pow2_ceil(std::max(8192, 8 * k));   // per-range admitted candidates per query
+  plan->carry_capacity = pow2_ceil(std::max(2048, 4 * k));  // survivors carried between ranges
   // first range is scored densely (no threshold yet); each later range is 8x the prefix before it, so the
   // expected number of admitted candidates per range stays near 7k.
   int64_t end = std::min<int64_t>(n_gallery, std::max(4096, 4 * k));
@@ -672,98 +750,97 @@ extern "C" int vdk_topk_plan_default(vdk_topk_plan* plan, int64_t n_query, int64
 
 extern "C" size_t vdk_topk_workspace_bytes(const vdk_topk_plan* plan) {
   if (!plan) return 0;
-  const size_t nq = static_cast<size_t>(plan->n_query);
-  return align256(nq * plan->cand_capacity * sizeof(uint2)) + 3 * align256(nq * sizeof(float)) + 256;
+  return workspace_bytes(plan->n_query, plan->cand_capacity, plan->carry_capacity);
+}
+
+static int check_plan(const vdk_topk_plan* plan) {
+  VDK_REQUIRE(plan, "null plan");
+  const int dim = plan->dim, k = plan->k;
+  VDK_REQUIRE(dim > 0 && dim % 64 == 0 && dim <= 64 * kMaxKB, "unsupported dim %d", dim);
+  VDK_REQUIRE(k >= 1 && k <= 1024, "k must be in [1,1024]");
+  VDK_REQUIRE(plan->cand_capacity >= 2 * k && plan->cand_capacity % kMaxSeg == 0, "bad cand_capacity");
+  VDK_REQUIRE(plan->carry_capacity >= 2 * k && plan->carry_capacity <= 4096, "carry_capacity must be in [2k, 4096]");
+  VDK_REQUIRE(plan->n_stages >= 1 && plan->n_stages <= 8 && plan->stage_end[plan->n_stages - 1] == plan->n_gallery,
+              "stage table must end at n_gallery");
+  VDK_REQUIRE(plan->n_query < (1ll << 31) - kQM && plan->n_gallery < (1ll << 31), "sizes exceed 32-bit tiling");
+  return VDK_OK;
 }
 
 extern "C" int vdk_ip_topk(const vdk_topk_plan* plan, const float* q32, const void* qh, const float* q_norm,
                            const float* q_err, const float* g32, const void* gh, const float* g_norm_max,
                            const float* g_err_max, int64_t id_offset, float* out_scores, int64_t* out_ids,
                            int32_t* status, void* workspace, size_t workspace_bytes, void* stream) {
-  VDK_REQUIRE(plan && out_scores && out_ids && status, "vdk_ip_topk: null plan/output");
+  int rc = check_plan(plan);
+  if (rc != VDK_OK) return rc;
+  VDK_REQUIRE(out_scores && out_ids && status, "vdk_ip_topk: null output");
   const int64_t nq = plan->n_query, ng = plan->n_gallery;
-  const int dim = plan->dim, k = plan->k, cap = plan->cand_capacity;
-  VDK_REQUIRE(dim > 0 && dim % 64 == 0 && dim <= 64 * kMaxKB, "vdk_ip_topk: unsupported dim %d", dim);
-  VDK_REQUIRE(k >= 1 && k <= 1024 && cap >= 2 * k && (cap & (cap - 1)) == 0, "vdk_ip_topk: bad k/capacity");
-  VDK_REQUIRE(plan->n_stages >= 1 && plan->n_stages <= 8 && plan->stage_end[plan->n_stages - 1] == ng,
-              "vdk_ip_topk: stage table must end at n_gallery");
-  VDK_REQUIRE(nq < (1ll << 31) / kQM * kQM && ng < (1ll << 31), "vdk_ip_topk: sizes exceed 32-bit tiling");
+  const int dim = plan->dim, k = plan->k, seg_stride = plan->cand_capacity, carry_cap = plan->carry_capacity;
   cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
   VDK_CUDA_OK(cudaMemsetAsync(status, 0, 4 * sizeof(int32_t), s));
   if (nq == 0) return VDK_OK;
   VDK_REQUIRE(q32 && qh && q_norm && q_err, "vdk_ip_topk: null query operand");
   VDK_REQUIRE(workspace && workspace_bytes >= vdk_topk_workspace_bytes(plan), "vdk_ip_topk: workspace too small");
   VDK_REQUIRE((reinterpret_cast<uintptr_t>(workspace) & 255) == 0, "vdk_ip_topk: workspace must be 256-byte aligned");
+  if (ng > 0) VDK_REQUIRE(g32 && gh && g_norm_max && g_err_max, "vdk_ip_topk: null gallery operand");
 
-  const TopkWorkspace w = carve_workspace(workspace, nq, cap);
-  uint2* cand = w.cand;
-  unsigned* counts = w.counts;
-  float* tau = w.tau;
-  float* eps = w.eps;
-
-  SelectParams sp{};
-  sp.n_query = static_cast<int>(nq);
-  sp.dim = dim;
-  sp.k = k;
-  sp.cap = cap;
-  sp.cand = cand;
-  sp.counts = counts;
-  sp.tau = tau;
-  sp.eps = eps;
-  sp.q32 = q32;
-  sp.g32 = g32;
-  sp.id_offset = id_offset;
-  sp.out_scores = out_scores;
-  sp.out_ids = out_ids;
-  sp.status = status;
-  const int sel_smem = cap * 8 + kSortMax * 8;
-  static bool sel_attr = false;
-  if (!sel_attr) {
-    VDK_CUDA_OK(cudaFuncSetAttribute(select_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
-    sel_attr = true;
-  }
-  VDK_REQUIRE(sel_smem <= 200 * 1024, "vdk_ip_topk: candidate capacity too large for the select kernel");
-
-  if (ng == 0) {  // empty gallery: all results are padding
-    VDK_CUDA_OK(cudaMemsetAsync(counts, 0, nq * sizeof(unsigned), s));
-    sp.dense_n = 0;
-    sp.final_stage = 1;
-    static const float zero = 0.f;
-    (void)zero;
-    eps_kernel<<<(static_cast<int>(nq) + 255) / 256, 256, 0, s>>>(q_norm, q_err, q_err, q_err, static_cast<int>(nq),
-                                                                   eps, tau, counts);
-    select_kernel<<<static_cast<unsigned>(nq), kSelThreads, sel_smem, s>>>(sp);
-    VDK_CUDA_OK(cudaGetLastError());
-    return VDK_OK;
-  }
-  VDK_REQUIRE(g32 && gh && g_norm_max && g_err_max, "vdk_ip_topk: null gallery operand");
-
-  eps_kernel<<<(static_cast<int>(nq) + 255) / 256, 256, 0, s>>>(q_norm, q_err, g_norm_max, g_err_max,
-                                                                 static_cast<int>(nq), eps, tau, counts);
+  const TopkWorkspace w = carve_workspace(workspace, nq, seg_stride, carry_cap);
+  eps_kernel<<<(static_cast<int>(nq) + 255) / 256, 256, 0, s>>>(q_norm, q_err, ng > 0 ? g_norm_max : nullptr,
+                                                                 ng > 0 ? g_err_max : nullptr, static_cast<int>(nq),
+                                                                 w.eps, w.tau, w.carry_cnt);
   VDK_CUDA_OK(cudaGetLastError());
 
-  CUtensorMap mq, mg;
-  int rc = make_tma_2d_16bit(&mq, qh, static_cast<uint64_t>(nq), dim, dim, kQM, kSBK);
-  if (rc != VDK_OK) return rc;
-  rc = make_tma_2d_16bit(&mg, gh, static_cast<uint64_t>(ng), dim, dim, kGN, kSBK);
-  if (rc != VDK_OK) return rc;
-
-  int64_t lo = 0;
-  for (int st = 0; st < plan->n_stages; ++st) {
-    const int64_t hi = plan->stage_end[st];
-    VDK_REQUIRE(hi > lo || (hi == lo && st > 0), "vdk_ip_topk: stage table must be increasing");
-    const bool dense = (st == 0);
-    const bool last = (st == plan->n_stages - 1);
-    if (hi > lo) {
-      rc = launch_score_range(mq, mg, static_cast<int>(nq), dim, lo, hi, dense, tau, cand, cap, counts, s);
+  int cur = 0;  // carry buffer holding the current survivors
+  if (ng > 0) {
+    CUtensorMap mq, mg;
+    rc = make_tma_2d_16bit(&mq, qh, static_cast<uint64_t>(nq), dim, dim, kQM, kSBK);
+    if (rc != VDK_OK) return rc;
+    rc = make_tma_2d_16bit(&mg, gh, static_cast<uint64_t>(ng), dim, dim, kGN, kSBK);
+    if (rc != VDK_OK) return rc;
+    int64_t lo = 0;
+    for (int st = 0; st < plan->n_stages; ++st) {
+      const int64_t hi = plan->stage_end[st];
+      VDK_REQUIRE(hi > lo || (hi == lo && st > 0), "vdk_ip_topk: stage table must be increasing");
+      if (hi == lo) continue;
+      const bool dense = (st == 0);
+      RangeLaunch info{};
+      rc = launch_score_range(mq, mg, static_cast<int>(nq), dim, lo, hi, dense, w, seg_stride, &info, s);
       if (rc != VDK_OK) return rc;
+      SelectParams sp{};
+      sp.n_query = static_cast<int>(nq);
+      sp.k = k;
+      sp.carry_in = w.carry[cur];
+      sp.carry_out = w.carry[cur ^ 1];
+      sp.carry_cnt = w.carry_cnt;
+      sp.carry_cap = carry_cap;
+      sp.seg = w.seg;
+      sp.seg_stride = seg_stride;
+      sp.seg_cap = info.seg_cap;
+      sp.n_seg = info.n_splits;
+      sp.seg_cnt = w.seg_cnt;
+      sp.dense_n = dense ? static_cast<int>(hi - lo) : 0;
+      sp.tau = w.tau;
+      sp.eps = w.eps;
+      sp.status = status;
+      select_kernel<<<static_cast<unsigned>(nq), kSelThreads, 0, s>>>(sp);
+      VDK_CUDA_OK(cudaGetLastError());
+      cur ^= 1;
+      lo = hi;
     }
-    sp.dense_n = dense ? static_cast<int>(hi - lo) : 0;
-    sp.final_stage = last ? 1 : 0;
-    select_kernel<<<static_cast<unsigned>(nq), kSelThreads, sel_smem, s>>>(sp);
-    VDK_CUDA_OK(cudaGetLastError());
-    lo = hi;
   }
+  RerankParams rp{};
+  rp.n_query = static_cast<int>(nq);
+  rp.dim = dim;
+  rp.k = k;
+  rp.carry = w.carry[cur];
+  rp.carry_cnt = w.carry_cnt;
+  rp.carry_cap = carry_cap;
+  rp.q32 = q32;
+  rp.g32 = g32;
+  rp.id_offset = id_offset;
+  rp.out_scores = out_scores;
+  rp.out_ids = out_ids;
+  rerank_kernel<<<static_cast<unsigned>(nq), kRerankThreads, carry_cap * sizeof(unsigned long long), s>>>(rp);
+  VDK_CUDA_OK(cudaGetLastError());
   return VDK_OK;
 }
 
@@ -792,15 +869,17 @@ extern "C" int vdk_ip_exact_pairs(const float* q32, const float* g32, int dim, c
 
 extern "C" int vdk_score_range(const vdk_topk_plan* plan, const void* qh, const void* gh, int64_t lo, int64_t hi,
                                int dense, void* workspace, size_t workspace_bytes, void* stream) {
-  VDK_REQUIRE(plan && qh && gh && workspace, "vdk_score_range: null operand");
+  int rc = check_plan(plan);
+  if (rc != VDK_OK) return rc;
+  VDK_REQUIRE(qh && gh && workspace, "vdk_score_range: null operand");
   VDK_REQUIRE(workspace_bytes >= vdk_topk_workspace_bytes(plan), "vdk_score_range: workspace too small");
   VDK_REQUIRE(lo >= 0 && hi > lo && hi <= plan->n_gallery, "vdk_score_range: bad range");
-  const TopkWorkspace w = carve_workspace(workspace, plan->n_query, plan->cand_capacity);
+  const TopkWorkspace w = carve_workspace(workspace, plan->n_query, plan->cand_capacity, plan->carry_capacity);
   CUtensorMap mq, mg;
-  int rc = make_tma_2d_16bit(&mq, qh, static_cast<uint64_t>(plan->n_query), plan->dim, plan->dim, kQM, kSBK);
+  rc = make_tma_2d_16bit(&mq, qh, static_cast<uint64_t>(plan->n_query), plan->dim, plan->dim, kQM, kSBK);
   if (rc != VDK_OK) return rc;
   rc = make_tma_2d_16bit(&mg, gh, static_cast<uint64_t>(plan->n_gallery), plan->dim, plan->dim, kGN, kSBK);
   if (rc != VDK_OK) return rc;
-  return launch_score_range(mq, mg, static_cast<int>(plan->n_query), plan->dim, lo, hi, dense != 0, w.tau, w.cand,
-                            plan->cand_capacity, w.counts, reinterpret_cast<cudaStream_t>(stream));
+  return launch_score_range(mq, mg, static_cast<int>(plan->n_query), plan->dim, lo, hi, dense != 0, w,
+                            plan->cand_capacity, nullptr, reinterpret_cast<cudaStream_t>(stream));
 }
