@@ -132,6 +132,51 @@ size_t vdk_convnext_workspace_bytes(const vdk_convnext_net* net, int batch);
 int vdk_convnext_forward(const vdk_convnext_net* net, const float* images, int batch, int l2_normalize,
                          float* embeddings, void* workspace, size_t workspace_bytes, void* stream);
 
+/* ---- margin-softmax heads + cross-entropy --------------------------------------------------- */
+/* Replaces ArcFace.forward (models/faceX/head/arcface.py:20-36), CircleLoss.forward (models/faceX/head/
+ * circleloss.py:21-43), nn.CrossEntropyLoss(label_smoothing) (models/losses/loss.py:71-73) and their autograd
+ * backward, as called at engine/procedure/train.py:196.  fp32 in / fp32 out like the reference (no autocast on the
+ * face path); the three contractions run on tcgen05 with a 3-way bf16 operand split (fp32-grade accuracy). */
+#define VDK_HEAD_ARCFACE 0
+#define VDK_HEAD_CIRCLELOSS 1
+
+typedef struct vdk_head_desc {
+  int kind;                 /* VDK_HEAD_* */
+  int batch, feat_dim, num_class;
+  float margin_arc, margin_am, scale; /* ArcFace(margin_arc, margin_am, scale) */
+  float margin, gamma;                /* CircleLoss(margin, gamma) */
+  float label_smooth;                 /* CrossEntropyLoss(label_smoothing) */
+} vdk_head_desc;
+
+size_t vdk_head_workspace_bytes(const vdk_head_desc* d);
+/* feats fp32 [B,D]; weight fp32 [D,C] (the head Parameter); labels int64 [B].
+ * logits: fp32 [B,C] or NULL; loss: device scalar (mean CE); row_lse: fp32 [B] saved for the backward;
+ * cos_saved: fp32 [B,C] clamped cos(theta) or NULL. */
+int vdk_head_forward(const vdk_head_desc* d, const float* feats, const float* weight, const int64_t* labels,
+                     float* logits, float* loss, float* row_lse, float* cos_saved, void* workspace,
+                     size_t workspace_bytes, void* stream);
+/* Fused backward of mean-CE(head(feats)) (dlogits == NULL; grad_loss: device scalar or NULL for 1), or the head-only
+ * backward for a caller-supplied dlogits fp32 [B,C] (row_lse / grad_loss ignored).  dfeats [B,D], dweight [D,C]. */
+int vdk_head_backward(const vdk_head_desc* d, const float* feats, const float* weight, const int64_t* labels,
+                      const float* row_lse, const float* grad_loss, const float* dlogits, float* dfeats,
+                      float* dweight, void* workspace, size_t workspace_bytes, void* stream);
+
+/* ---- optimizer step -------------------------------------------------------------------------- */
+/* Replaces Trainer.update's clip_grad_norm_(max_norm=10) -> SGD step -> zero_grad -> ModelEMA.update
+ * (engine/procedure/train.py:203-215, engine/optimizer.py:119-121, models/ema.py:28-37) on FLAT fp32 buffers
+ * (parameters, gradients, momentum and EMA of one param group laid out contiguously by the caller). */
+size_t vdk_grad_sumsq_workspace_bytes(void);
+/* total_sumsq (device double) = [accumulate ? previous : 0] + sum(grads^2); deterministic summation order. */
+int vdk_grad_sumsq(const float* grads, int64_t n, double* total_sumsq, int accumulate, void* workspace,
+                   size_t workspace_bytes, void* stream);
+/* One param group: g *= min(1, max_norm / (sqrt(total_sumsq) + 1e-6)); g += wd * p; buf = first_step ? g : mom*buf + g;
+ * p -= lr * buf; ema = ema*d + (1-d)*p (ema may be NULL); g = 0 if zero_grad. */
+int vdk_sgd_clip_ema_step(float* params, float* grads, float* momentum_buf, float* ema, int64_t n,
+                          const double* total_sumsq, float max_norm, float lr, float momentum, float weight_decay,
+                          int first_step, float ema_decay, float ema_one_minus_decay, int zero_grad, void* stream);
+/* EMA of non-parameter float state (BatchNorm running statistics): ema = ema*d + (1-d)*src. */
+int vdk_ema_update(float* ema, const float* src, int64_t n, float decay, float one_minus_decay, void* stream);
+
 /* ---- retrieval: L2-normalise -> inner product -> top-k -------------------------------------- */
 /* Replaces F.normalize at models/faceX/face_model.py:139, faiss index.add at
  * engine/cbir/evaluation.py:166-168 and faiss index.search at engine/cbir/evaluation.py:193

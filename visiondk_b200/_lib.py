@@ -17,6 +17,12 @@ DTYPE_BF16, DTYPE_FP16, DTYPE_FP32 = 0, 1, 2
 EPI_NONE, EPI_GELU, EPI_SCALE_RESIDUAL, EPI_LAYERNORM = 0, 1, 2, 3
 
 
+class HeadDesc(C.Structure):
+    _fields_ = [("kind", C.c_int), ("batch", C.c_int), ("feat_dim", C.c_int), ("num_class", C.c_int),
+                ("margin_arc", C.c_float), ("margin_am", C.c_float), ("scale", C.c_float),
+                ("margin", C.c_float), ("gamma", C.c_float), ("label_smooth", C.c_float)]
+
+
 class TopkPlan(C.Structure):
     _fields_ = [
         ("n_query", C.c_int64),
@@ -53,6 +59,14 @@ SIGNATURES = {
     "vdk_layernorm_patchify": (_i, [_p, _i, _i, _i, _i, _p, _p, C.c_float, _i, _p, _p]),
     "vdk_convnext_workspace_bytes": (_sz, [_p, _i]),
     "vdk_convnext_forward": (_i, [_p, _p, _i, _i, _p, _p, _sz, _p]),
+    "vdk_head_workspace_bytes": (_sz, [_p]),
+    "vdk_head_forward": (_i, [_p, _p, _p, _p, _p, _p, _p, _p, _p, _sz, _p]),
+    "vdk_head_backward": (_i, [_p, _p, _p, _p, _p, _p, _p, _p, _p, _p, _sz, _p]),
+    "vdk_grad_sumsq_workspace_bytes": (_sz, []),
+    "vdk_grad_sumsq": (_i, [_p, _i64, _p, _i, _p, _sz, _p]),
+    "vdk_sgd_clip_ema_step": (_i, [_p, _p, _p, _p, _i64, _p, C.c_float, C.c_float, C.c_float, C.c_float, _i, C.c_float,
+                                   C.c_float, _i, _p]),
+    "vdk_ema_update": (_i, [_p, _p, _i64, C.c_float, C.c_float, _p]),
     "vdk_gemm_tn": (_i, [_p, _p, _p, _i, _i, _i, _i, _i, _i, _i, _i, _i, _p, _p, _p, _i, _p]),
     "vdk_rows_prepare": (_i, [_p, _i64, _i, _i, _p, _p, _p, _p, _p]),
     "vdk_topk_plan_default": (_i, [C.POINTER(TopkPlan), _i64, _i64, _i, _i]),
