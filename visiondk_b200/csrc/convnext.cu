@@ -47,32 +47,41 @@ __global__ void __launch_bounds__(256) stem_patchify_kernel(const float* __restr
 }
 
 // ------------------------------------------------------------------------------------------------
-// depthwise 7x7 + bias + LayerNorm(C): one CTA = TW output pixels of one image row x all channels
+// depthwise 7x7 + bias + LayerNorm(C)
 // ------------------------------------------------------------------------------------------------
-constexpr int kDwTW = 4;  // output pixels per CTA along W
+// A "group" of C/4 threads (4 contiguous channels each -> 8-byte coalesced NHWC loads) produces a strip of
+// kDwTW output pixels of one image row; a CTA holds G groups working on G consecutive rows, so the 7-row
+// input halo is shared through L1.  The 49 taps of a thread's 4 channels are read 7 at a time (one filter row),
+// accumulators stay in registers, and LayerNorm over C is a reduction inside the group (pure warp shuffles when
+// the group is a single warp).  FMA-bound: 49 FMAs per output against ~4 bytes of HBM traffic.
+constexpr int kDwTW = 8;  // output pixels per strip along W
 
-template <int CPT>  // channels per thread (2 or 4), contiguous -> coalesced NHWC access
-__global__ void __launch_bounds__(512)
-dwconv7_ln_kernel(const __nv_bfloat16* __restrict__ x, int B, int H, int W, int C,
+__global__ void __launch_bounds__(256)
+dwconv7_ln_kernel(const __nv_bfloat16* __restrict__ x, int B, int H, int W, int C, int tpg /*threads per group, x32*/,
                   const float* __restrict__ w49,  // [49][C]
                   const float* __restrict__ bias, const float* __restrict__ ln_w, const float* __restrict__ ln_b,
                   float eps, __nv_bfloat16* __restrict__ y) {
-  __shared__ float red[kDwTW][16];
-  __shared__ float stat[kDwTW];
+  __shared__ float red[8][kDwTW][8];  // [group][pixel][warp in group]
+  const int groups = blockDim.x / tpg;
+  const int grp = threadIdx.x / tpg;
+  const int tig = threadIdx.x - grp * tpg;  // thread in group
   const int tiles_w = (W + kDwTW - 1) / kDwTW;
+  const int tiles_h = (H + groups - 1) / groups;
   const int tw = blockIdx.x % tiles_w;
-  const int oy = (blockIdx.x / tiles_w) % H;
-  const int b = blockIdx.x / (tiles_w * H);
+  const int th = (blockIdx.x / tiles_w) % tiles_h;
+  const int b = blockIdx.x / (tiles_w * tiles_h);
+  const int oy = th * groups + grp;
   const int ox0 = tw * kDwTW;
-  const int c0 = threadIdx.x * CPT;
-  const bool active = c0 < C;
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarps = (blockDim.x + 31) >> 5;
+  const int c0 = tig * 4;
+  const bool active = c0 < C && oy < H;
+  const int lane = threadIdx.x & 31;
+  const int wig = tig >> 5, nwig = tpg >> 5;  // warp in group, warps per group
 
-  float acc[kDwTW][CPT];
+  float acc[kDwTW][4];
 #pragma unroll
   for (int p = 0; p < kDwTW; ++p)
 #pragma unroll
-    for (int c = 0; c < CPT; ++c) acc[p][c] = 0.f;
+    for (int c = 0; c < 4; ++c) acc[p][c] = 0.f;
 
   if (active) {
     const __nv_bfloat16* xb = x + static_cast<int64_t>(b) * H * W * C;
@@ -80,109 +89,89 @@ dwconv7_ln_kernel(const __nv_bfloat16* __restrict__ x, int B, int H, int W, int 
     for (int dy = 0; dy < 7; ++dy) {
       const int iy = oy + dy - 3;
       if (iy < 0 || iy >= H) continue;
-      float wrow[7][CPT];
+      float4 wrow[7];
 #pragma unroll
-      for (int dx = 0; dx < 7; ++dx) {
-        if (CPT == 4) {
-          const float4 t = __ldg(reinterpret_cast<const float4*>(w49 + (dy * 7 + dx) * C + c0));
-          wrow[dx][0] = t.x; wrow[dx][1] = t.y; wrow[dx][CPT - 2] = t.z; wrow[dx][CPT - 1] = t.w;
-        } else {
-          const float2 t = __ldg(reinterpret_cast<const float2*>(w49 + (dy * 7 + dx) * C + c0));
-          wrow[dx][0] = t.x; wrow[dx][1] = t.y;
-        }
-      }
+      for (int dx = 0; dx < 7; ++dx) wrow[dx] = __ldg(reinterpret_cast<const float4*>(w49 + (dy * 7 + dx) * C + c0));
+      const __nv_bfloat16* xrow = xb + static_cast<int64_t>(iy) * W * C + c0;
 #pragma unroll
       for (int ix = 0; ix < kDwTW + 6; ++ix) {
         const int gx = ox0 + ix - 3;
         if (gx < 0 || gx >= W) continue;
-        float v[CPT];
-        const __nv_bfloat16* src = xb + (static_cast<int64_t>(iy) * W + gx) * C + c0;
-        if (CPT == 4) {
-          const uint2 t = *reinterpret_cast<const uint2*>(src);
-          const float2 a = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&t.x));
-          const float2 c = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&t.y));
-          v[0] = a.x; v[1] = a.y; v[CPT - 2] = c.x; v[CPT - 1] = c.y;
-        } else {
-          const float2 a = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(src));
-          v[0] = a.x; v[1] = a.y;
-        }
+        const uint2 t = *reinterpret_cast<const uint2*>(xrow + static_cast<int64_t>(gx) * C);
+        const float2 a = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&t.x));
+        const float2 c = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&t.y));
 #pragma unroll
         for (int p = 0; p < kDwTW; ++p) {
           const int dx = ix - p;  // input column ix feeds output pixel p through tap dx
           if (dx >= 0 && dx < 7) {
-#pragma unroll
-            for (int c = 0; c < CPT; ++c) acc[p][c] = fmaf(v[c], wrow[dx][c], acc[p][c]);
+            acc[p][0] = fmaf(a.x, wrow[dx].x, acc[p][0]);
+            acc[p][1] = fmaf(a.y, wrow[dx].y, acc[p][1]);
+            acc[p][2] = fmaf(c.x, wrow[dx].z, acc[p][2]);
+            acc[p][3] = fmaf(c.y, wrow[dx].w, acc[p][3]);
           }
         }
       }
     }
+    const float4 bc = __ldg(reinterpret_cast<const float4*>(bias + c0));
 #pragma unroll
-    for (int c = 0; c < CPT; ++c) {
-      const float bc = __ldg(bias + c0 + c);
-#pragma unroll
-      for (int p = 0; p < kDwTW; ++p) acc[p][c] += bc;
+    for (int p = 0; p < kDwTW; ++p) {
+      acc[p][0] += bc.x; acc[p][1] += bc.y; acc[p][2] += bc.z; acc[p][3] += bc.w;
     }
   }
 
-  // LayerNorm over C for each of the kDwTW pixels: block reduction of the mean, then of the centred squares
+  // LayerNorm over C per pixel: reduce inside the group (mean, then centred second moment)
   float mean[kDwTW], rstd[kDwTW];
+  const float inv_c = 1.0f / static_cast<float>(C);
 #pragma unroll
   for (int pass = 0; pass < 2; ++pass) {
+    float s[kDwTW];
 #pragma unroll
     for (int p = 0; p < kDwTW; ++p) {
-      float s = 0.f;
+      float v = 0.f;
       if (active) {
 #pragma unroll
-        for (int c = 0; c < CPT; ++c) {
+        for (int c = 0; c < 4; ++c) {
           const float d = pass == 0 ? acc[p][c] : acc[p][c] - mean[p];
-          s += pass == 0 ? d : d * d;
+          v += pass == 0 ? d : d * d;
         }
       }
-      s = warp_sum(s);
-      if (lane == 0) red[p][warp] = s;
+      s[p] = warp_sum(v);
     }
-    __syncthreads();
-    if (warp == 0) {
+    if (nwig > 1) {  // uniform across the CTA (tpg is a launch parameter)
+      if (lane == 0) {
+#pragma unroll
+        for (int p = 0; p < kDwTW; ++p) red[grp][p][wig] = s[p];
+      }
+      __syncthreads();
 #pragma unroll
       for (int p = 0; p < kDwTW; ++p) {
-        float s = lane < nwarps ? red[p][lane] : 0.f;
-        s = warp_sum(s);
-        if (lane == 0) stat[p] = s / static_cast<float>(C);
+        float t = 0.f;
+        for (int w = 0; w < nwig; ++w) t += red[grp][p][w];
+        s[p] = t;
       }
+      __syncthreads();
     }
-    __syncthreads();
 #pragma unroll
     for (int p = 0; p < kDwTW; ++p) {
-      if (pass == 0) mean[p] = stat[p];
-      else rstd[p] = rsqrtf(stat[p] + eps);
+      if (pass == 0) mean[p] = s[p] * inv_c;
+      else rstd[p] = rsqrtf(s[p] * inv_c + eps);
     }
-    __syncthreads();
   }
 
   if (active) {
-    float g[CPT], bb[CPT];
-#pragma unroll
-    for (int c = 0; c < CPT; ++c) {
-      g[c] = __ldg(ln_w + c0 + c);
-      bb[c] = __ldg(ln_b + c0 + c);
-    }
+    const float4 g = __ldg(reinterpret_cast<const float4*>(ln_w + c0));
+    const float4 bb = __ldg(reinterpret_cast<const float4*>(ln_b + c0));
 #pragma unroll
     for (int p = 0; p < kDwTW; ++p) {
       const int ox = ox0 + p;
       if (ox >= W) continue;
       __nv_bfloat16* dst = y + ((static_cast<int64_t>(b) * H + oy) * W + ox) * C + c0;
-      float o[CPT];
-#pragma unroll
-      for (int c = 0; c < CPT; ++c) o[c] = (acc[p][c] - mean[p]) * rstd[p] * g[c] + bb[c];
-      if (CPT == 4) {
-        __nv_bfloat162 lo = __floats2bfloat162_rn(o[0], o[1]), hi = __floats2bfloat162_rn(o[CPT - 2], o[CPT - 1]);
-        uint2 t;
-        t.x = *reinterpret_cast<uint32_t*>(&lo);
-        t.y = *reinterpret_cast<uint32_t*>(&hi);
-        *reinterpret_cast<uint2*>(dst) = t;
-      } else {
-        *reinterpret_cast<__nv_bfloat162*>(dst) = __floats2bfloat162_rn(o[0], o[1]);
-      }
+      __nv_bfloat162 lo = __floats2bfloat162_rn((acc[p][0] - mean[p]) * rstd[p] * g.x + bb.x, (acc[p][1] - mean[p]) * rstd[p] * g.y + bb.y);
+      __nv_bfloat162 hi = __floats2bfloat162_rn((acc[p][2] - mean[p]) * rstd[p] * g.z + bb.z, (acc[p][3] - mean[p]) * rstd[p] * g.w + bb.w);
+      uint2 t;
+      t.x = *reinterpret_cast<uint32_t*>(&lo);
+      t.y = *reinterpret_cast<uint32_t*>(&hi);
+      *reinterpret_cast<uint2*>(dst) = t;
     }
   }
 }
@@ -298,17 +287,12 @@ using namespace vdk;
 
 static int launch_dwconv7_ln(const __nv_bfloat16* x, int batch, int H, int W, int C, const float* w49, const float* bias,
                              const float* ln_w, const float* ln_b, float eps, __nv_bfloat16* y, cudaStream_t s) {
-  const int tiles_w = (W + kDwTW - 1) / kDwTW;
-  const unsigned grid = static_cast<unsigned>(batch) * H * tiles_w;
-  if (C % 4 == 0 && C / 4 >= 32) {
-    const int threads = ((C / 4) + 31) / 32 * 32;
-    VDK_REQUIRE(threads <= 512, "dwconv7_ln: C too large (%d)", C);
-    dwconv7_ln_kernel<4><<<grid, threads, 0, s>>>(x, batch, H, W, C, w49, bias, ln_w, ln_b, eps, y);
-  } else {
-    VDK_REQUIRE(C % 2 == 0 && C / 2 <= 512, "dwconv7_ln: unsupported C (%d)", C);
-    const int threads = ((C / 2) + 31) / 32 * 32;
-    dwconv7_ln_kernel<2><<<grid, threads, 0, s>>>(x, batch, H, W, C, w49, bias, ln_w, ln_b, eps, y);
-  }
+  VDK_REQUIRE(C % 4 == 0 && C <= 1024, "dwconv7_ln: C must be a multiple of 4, <= 1024 (got %d)", C);
+  const int tpg = ((C / 4) + 31) / 32 * 32;     // threads per group, whole warps
+  const int groups = std::max(1, 256 / tpg);    // strips (consecutive rows) per CTA
+  const int tiles_w = (W + kDwTW - 1) / kDwTW, tiles_h = (H + groups - 1) / groups;
+  const unsigned grid = static_cast<unsigned>(batch) * tiles_h * tiles_w;
+  dwconv7_ln_kernel<<<grid, groups * tpg, 0, s>>>(x, batch, H, W, C, tpg, w49, bias, ln_w, ln_b, eps, y);
   VDK_CUDA_OK(cudaGetLastError());
   return VDK_OK;
 }
@@ -316,7 +300,7 @@ static int launch_dwconv7_ln(const __nv_bfloat16* x, int batch, int H, int W, in
 extern "C" int vdk_dwconv7_ln(const void* x, int batch, int H, int W, int C, const float* w49, const float* bias,
                               const float* ln_w, const float* ln_b, float eps, void* y, void* stream) {
   VDK_REQUIRE(x && y && w49 && bias && ln_w && ln_b, "vdk_dwconv7_ln: null operand");
-  VDK_REQUIRE(batch > 0 && H > 0 && W > 0 && C > 0 && C % 8 == 0, "vdk_dwconv7_ln: bad shape");
+  VDK_REQUIRE(batch > 0 && H > 0 && W > 0 && C > 0 && C % 8 == 0, "vdk_dwconv7_ln: bad shape (C must be a multiple of 8)");
   return launch_dwconv7_ln(reinterpret_cast<const __nv_bfloat16*>(x), batch, H, W, C, w49, bias, ln_w, ln_b, eps,
                            reinterpret_cast<__nv_bfloat16*>(y), reinterpret_cast<cudaStream_t>(stream));
 }

@@ -6,7 +6,8 @@
 // One persistent CTA per SM, 192 threads:
 //   warp 0      : TMA producer   (A tile 128x64, B tile BNx64 per stage, 128-byte swizzle)
 //   warp 1      : TMEM allocator + single-thread tcgen05.mma issuer (UMMA 128 x BN x 16, fp32 accumulate)
-//   warps 2..5  : epilogue       (tcgen05.ld -> bias / GELU / layer-scale+residual -> 16-byte global stores)
+//   warps 2..9  : epilogue       (tcgen05.ld -> bias / GELU / layer-scale+residual / LayerNorm -> 16-byte global
+//                 stores); two warps share each TMEM lane quarter and take alternate 32-column chunks
 // Two accumulator stages in TMEM (2 x BN columns) let the epilogue of tile i overlap the MMAs of tile i+1.
 #include "vdk_host.h"
 #include "vdk_ptx.cuh"
@@ -15,7 +16,7 @@ namespace vdk {
 
 constexpr int kBM = 128;
 constexpr int kBK = 64;  // 64 x 16-bit = one 128-byte swizzle row
-constexpr int kGemmThreads = 192;
+constexpr int kGemmThreads = 320;  // TMA warp, MMA warp, 8 epilogue warps
 
 struct GemmParams {
   int M, N, K;
@@ -43,7 +44,31 @@ struct GemmCfg {
   static constexpr int kSmemBytes = kStages * kStageBytes + (2 * kStages + 4) * 8 + 16 + 1024;
 };
 
-__device__ __forceinline__ float gelu_erf(float x) { return 0.5f * x * (1.0f + erff(x * 0.70710678118654752440f)); }
+// GELU(x) = 0.5 x (1 + erf(x / sqrt 2)), erf by Abramowitz-Stegun 7.1.26 (|abs err| < 1.5e-7) on the SFU
+// (rcp.approx / ex2.approx): branch-free, ~16 instructions per element instead of erff()'s two-branch polynomial.
+__device__ __forceinline__ float rcp_approx(float x) {
+  float y;
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+__device__ __forceinline__ float ex2_approx(float x) {
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+__device__ __forceinline__ float gelu_erf(float x) {
+  const float z = fabsf(x) * 0.70710678118654752440f;
+  const float t = rcp_approx(fmaf(0.3275911f, z, 1.0f));
+  float p = fmaf(1.061405429f, t, -1.453152027f);
+  p = fmaf(p, t, 1.421413741f);
+  p = fmaf(p, t, -0.284496736f);
+  p = fmaf(p, t, 0.254829592f);
+  p *= t;
+  const float e = ex2_approx(-1.4426950408889634f * z * z);  // exp(-z^2)
+  const float erf_abs = fmaf(-p, e, 1.0f);
+  const float erf_v = copysignf(erf_abs, x);
+  return 0.5f * x * (1.0f + erf_v);
+}
 
 __device__ __forceinline__ uint32_t pack2(float a, float b, int out_dtype) {
   if (out_dtype == VDK_DTYPE_BF16) {
@@ -96,7 +121,7 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
     }
     for (int i = 0; i < 2; ++i) {
       mbar_init(&tmem_full[i], 1);
-      mbar_init(&tmem_empty[i], 128);
+      mbar_init(&tmem_empty[i], 256);
     }
     fence_mbar_init();
   }
@@ -171,6 +196,7 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
   } else {
     // ===================== epilogue =====================
     const int lane_base = (warp & 3) * 32;  // TMEM lanes this warp may touch
+    const int half = (warp - 2) >> 2;       // which of the two warps sharing this lane quarter
     int it = 0;
     for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
       const int acc = it & 1;
@@ -218,7 +244,7 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
         ln_rstd = rsqrtf(sq / static_cast<float>(p.N) + p.ln_eps);
       }
 #pragma unroll 1
-      for (int c = 0; c < BN / 32; ++c) {
+      for (int c = half; c < BN / 32; c += 2) {
         uint32_t r[32];
         tmem_ld_32x32b_x32(tacc + c * 32, r);
         tmem_ld_wait();
