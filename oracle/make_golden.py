@@ -43,9 +43,12 @@ def heads():
             head = mod(D, Cn, **kwargs)
             if kind == "arcface_am":
                 # make a few rows hit the theta+m > pi fallback branch (cos <= cos(pi - m))
+                # (not exactly cos = -1: the reference's sqrt(1 - cos^2) has a NaN gradient there)
                 with torch.no_grad():
+                    gen = torch.Generator().manual_seed(5)
                     for r in range(0, B, 3):
-                        head.weight[:, labels[r]] = -feats[r]
+                        noise = torch.randn(D, generator=gen) * feats[r].norm() / D ** 0.5
+                        head.weight[:, labels[r]] = -feats[r] + 0.3 * noise
             f = feats.clone().requires_grad_(True)
             logits = head(f, labels)
             crit = loss.create_Lossfn("ce")(label_smooth=smooth)
@@ -74,6 +77,7 @@ def ema_sgd_sched():
     for step in range(12):
         x = torch.randn(16, 6)
         y = torch.randint(0, 3, (16,))
+        lrs.append([g["lr"] for g in opt.param_groups])  # learning rates in effect during this step
         loss = torch.nn.functional.cross_entropy(model(x) * 30, y)
         loss.backward()
         gn = torch.nn.utils.clip_grad_norm_(model.parameters(), max_norm=10.0)  # train.py:209
@@ -82,7 +86,6 @@ def ema_sgd_sched():
         ema.update(model)  # train.py:214-215
         sc.step()          # train.py:230 (per batch)
         xs.append(x.numpy()); ys.append(y.numpy()); gnorms.append(float(gn))
-        lrs.append([g["lr"] for g in opt.param_groups])
         params.append(np.concatenate([p.detach().numpy().ravel() for p in model.state_dict().values()]))
         emas.append(np.concatenate([p.detach().numpy().ravel().astype(np.float32) for p in ema.ema.state_dict().values()]))
     np.savez_compressed(os.path.join(OUT, "step_sgd_ema.npz"), init=rec["init"], x=np.stack(xs), y=np.stack(ys),

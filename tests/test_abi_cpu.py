@@ -53,13 +53,13 @@ def test_topk_plan_default(lib):
     plan = _lib.TopkPlan()
     assert lib.vdk_topk_plan_default(C.byref(plan), 10000, 1000000, 512, 100) == 0
     ends = list(plan.stage_end)[:plan.n_stages]
-    assert ends == [4096, 32768, 262144, 1000000] and plan.cand_capacity == 8192 and plan.carry_capacity == 2048
+    assert ends == [4096, 32768, 262144, 1000000] and plan.cand_capacity == 16384 and plan.carry_capacity == 2048
     assert all(e % 256 == 0 for e in ends[:-1])
-    assert lib.vdk_topk_workspace_bytes(C.byref(plan)) >= 10000 * (8192 + 2 * 2048) * 8
+    assert lib.vdk_topk_workspace_bytes(C.byref(plan)) >= 10000 * (16384 + 2 * 2048) * 8
     assert lib.vdk_topk_plan_default(C.byref(plan), 5, 100, 64, 10) == 0
     assert plan.n_stages == 1 and plan.stage_end[0] == 100
     assert lib.vdk_topk_plan_default(C.byref(plan), 5, 100, 64, 1024) == 0
-    assert plan.cand_capacity == 8192 and plan.carry_capacity == 4096
+    assert plan.cand_capacity == 16384 and plan.carry_capacity == 4096
     assert lib.vdk_topk_plan_default(C.byref(plan), 5, 100, 100, 10) == _lib.VDK_ERR_INVALID
     assert "multiple of 64" in _lib.last_error()
     assert lib.vdk_topk_plan_default(C.byref(plan), 5, 100, 64, 0) == _lib.VDK_ERR_INVALID

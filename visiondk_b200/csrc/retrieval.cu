@@ -104,9 +104,9 @@ constexpr int kSBK = 64;          // K per smem block (128-byte swizzle row of f
 constexpr int kQBlockBytes = kQM * kSBK * 2;   // 16 KB
 constexpr int kGStageBytes = kGN * kSBK * 2;   // 32 KB
 constexpr int kGStages = 3;
-constexpr int kScoreThreads = 192;
+constexpr int kScoreThreads = 320;  // TMA warp, MMA warp, 8 epilogue warps
 constexpr int kMaxKB = 8;         // dim <= 512
-constexpr int kMaxSeg = 32;       // gallery splits per range = candidate segments per query
+constexpr int kMaxSeg = 32;       // candidate segments per query = 2 x gallery splits per range (two epilogue warps per row)
 
 struct ScoreParams {
   int n_query;
@@ -114,7 +114,7 @@ struct ScoreParams {
   int64_t g_lo, g_hi;
   int n_qtiles, n_splits, tiles_per_split, n_tiles;
   const float* tau;   // per-query admission threshold (sparse mode)
-  uint2* seg;         // [n_query][seg_stride] {score bits, gallery row}; split s owns [s*seg_cap, (s+1)*seg_cap)
+  uint2* seg;         // [n_query][seg_stride] {score bits, gallery row}; writer (split s, half h) owns segment 2s+h
   int seg_stride;     // entries per query
   int seg_cap;        // entries per (query, split)
   unsigned* seg_cnt;  // [n_query][kMaxSeg] admitted count per (query, split) — may exceed seg_cap (overflow)
@@ -153,7 +153,7 @@ score_filter_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_cons
     }
     for (int i = 0; i < 2; ++i) {
       mbar_init(&tmem_full[i], 1);
-      mbar_init(&tmem_empty[i], 128);
+      mbar_init(&tmem_empty[i], 256);
     }
     mbar_init(q_full, 1);
     mbar_init(q_empty, 1);
@@ -234,8 +234,11 @@ score_filter_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_cons
       }
     }
   } else {
-    // ===================== epilogue: one thread = one query row =====================
+    // ===================== epilogue: one query row per TMEM lane =====================
+    // Eight warps: two per TMEM lane quarter, taking alternate 32-column chunks (two warps per scheduler hide
+    // each other's TMEM-load and ALU latency).  Each (row, split, half) has exactly one writer thread.
     const int lane_base = (warp & 3) * 32;
+    const int half = (warp - 2) >> 2;
     int it = 0;
     for (int u = blockIdx.x; u < n_units; u += gridDim.x) {
       const int qt = u % p.n_qtiles, sp = u / p.n_qtiles;
@@ -246,19 +249,21 @@ score_filter_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_cons
       const bool row_ok = row < p.n_query;
       float tau = INFINITY;
       if (!kDense && row_ok) tau = p.tau[row];
-      // this thread is the only writer of segment (row, sp): a register counter and plain stores suffice
-      uint2* seg = p.seg + static_cast<size_t>(row_ok ? row : 0) * p.seg_stride + (kDense ? 0 : sp * p.seg_cap);
+      uint2* seg = p.seg + static_cast<size_t>(row_ok ? row : 0) * p.seg_stride + (kDense ? 0 : (sp * 2 + half) * p.seg_cap);
       unsigned cnt = 0;
       for (int t = t0; t < t1; ++t, ++it) {
         const int acc = it & 1;
         mbar_wait(&tmem_full[acc], (it >> 1) & 1);
         tc_fence_after();
         const int64_t gbase = p.g_lo + static_cast<int64_t>(t) * kGN;
+        const uint32_t tacc = tmem_base + (static_cast<uint32_t>(lane_base) << 16) + acc * kGN;
+        uint32_t r[32], rn[32];
+        tmem_ld_32x32b_x32(tacc + half * 32, r);
 #pragma unroll 1
-        for (int c = 0; c < kGN / 32; ++c) {
-          uint32_t r[32];
-          tmem_ld_32x32b_x32(tmem_base + (static_cast<uint32_t>(lane_base) << 16) + acc * kGN + c * 32, r);
+        for (int c = half; c < kGN / 32; c += 2) {
           tmem_ld_wait();
+          // prefetch this warp's next chunk while the current one is examined
+          if (c + 2 < kGN / 32) tmem_ld_32x32b_x32(tacc + (c + 2) * 32, rn);
           const int64_t g0 = gbase + c * 32;
           if (kDense) {
             if (row_ok && g0 < p.g_hi) {
@@ -287,13 +292,16 @@ score_filter_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_cons
               gm[q] = m;
             }
             if (fmaxf(fmaxf(gm[0], gm[1]), fmaxf(gm[2], gm[3])) >= tau) {  // rows beyond n_query carry tau = +inf
+              const uint32_t gcol = static_cast<uint32_t>(g0);
+              const int64_t remv = p.g_hi - g0;
+              const uint32_t nvalid = remv < 32 ? static_cast<uint32_t>(remv > 0 ? remv : 0) : 32u;
 #pragma unroll
               for (int q = 0; q < 4; ++q) {
                 if (gm[q] >= tau) {
 #pragma unroll
                   for (int j = q * 8; j < q * 8 + 8; ++j) {
-                    if (__uint_as_float(r[j]) >= tau && g0 + j < p.g_hi) {
-                      if (cnt < static_cast<unsigned>(p.seg_cap)) seg[cnt] = make_uint2(r[j], static_cast<uint32_t>(g0 + j));
+                    if (__uint_as_float(r[j]) >= tau && static_cast<uint32_t>(j) < nvalid) {
+                      if (cnt < static_cast<unsigned>(p.seg_cap)) seg[cnt] = make_uint2(r[j], gcol + j);
                       ++cnt;
                     }
                   }
@@ -301,11 +309,13 @@ score_filter_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_cons
               }
             }
           }
+#pragma unroll
+          for (int j = 0; j < 32; ++j) r[j] = rn[j];
         }
         tc_fence_before();
         mbar_arrive(&tmem_empty[acc]);
       }
-      if (!kDense && row_ok) p.seg_cnt[static_cast<size_t>(row) * kMaxSeg + sp] = cnt;
+      if (!kDense && row_ok) p.seg_cnt[static_cast<size_t>(row) * kMaxSeg + sp * 2 + half] = cnt;
     }
   }
 
@@ -662,16 +672,29 @@ static int launch_score_range(const CUtensorMap& mq, const CUtensorMap& mg, int 
   p.g_hi = hi;
   p.n_qtiles = (nq + kQM - 1) / kQM;
   p.n_tiles = static_cast<int>((hi - lo + kGN - 1) / kGN);
-  // enough (query tile, gallery split) units to fill the SMs ~4x over, at most kMaxSeg splits (one candidate
-  // segment per split and query)
-  int splits = (4 * sms + p.n_qtiles - 1) / p.n_qtiles;
-  splits = std::max(1, std::min(std::min(splits, kMaxSeg), p.n_tiles));
-  p.tiles_per_split = (p.n_tiles + splits - 1) / splits;
+  // (query tile, gallery split) units are statically dealt to the persistent CTAs: pick the split count (at most
+  // kMaxSeg/2, one candidate segment per split, query and epilogue half) whose unit count fills whole waves best
+  const int max_splits = std::max(1, std::min(kMaxSeg / 2, p.n_tiles));
+  int best = 1;
+  double best_eff = -1.0;
+  for (int sp = 1; sp <= max_splits; ++sp) {
+    const int tps = (p.n_tiles + sp - 1) / sp;
+    const int nsp = (p.n_tiles + tps - 1) / tps;
+    const long long units = static_cast<long long>(p.n_qtiles) * nsp;
+    const long long waves = (units + sms - 1) / sms;
+    // work is quantised in tiles per unit: the busiest CTA runs `waves` units of `tps` tiles
+    const double eff = static_cast<double>(p.n_qtiles) * p.n_tiles / (static_cast<double>(waves) * sms * tps);
+    if (eff > best_eff + 1e-9 || (eff > best_eff - 1e-9 && nsp > best)) {
+      best_eff = eff;
+      best = nsp;
+    }
+  }
+  p.tiles_per_split = (p.n_tiles + best - 1) / best;
   p.n_splits = (p.n_tiles + p.tiles_per_split - 1) / p.tiles_per_split;
   p.tau = w.tau;
   p.seg = w.seg;
   p.seg_stride = seg_stride;
-  p.seg_cap = seg_stride / p.n_splits;
+  p.seg_cap = seg_stride / (2 * p.n_splits);
   p.seg_cnt = w.seg_cnt;
   if (info) {
     info->n_splits = p.n_splits;
@@ -726,7 +749,7 @@ extern "C" int vdk_topk_plan_default(vdk_topk_plan* plan, int64_t n_query, int64
   plan->n_gallery = n_gallery;
   plan->dim = dim;
   plan->k = k;
-  plan->cand_capacity = pow2_ceil(std::max(8192, 8 * k));   // per-range admitted candidates per query
+  plan->cand_capacity = pow2_ceil(std::max(16384, 16 * k));  // per-range admitted candidates per query
   plan->carry_capacity = pow2_ceil(std::max(2048, 4 * k));  // survivors carried between ranges
   // first range is scored densely (no threshold yet); each later range is 8x the prefix before it, so the
   // expected number of admitted candidates per range stays near 7k.
@@ -815,7 +838,7 @@ extern "C" int vdk_ip_topk(const vdk_topk_plan* plan, const float* q32, const vo
       sp.seg = w.seg;
       sp.seg_stride = seg_stride;
       sp.seg_cap = info.seg_cap;
-      sp.n_seg = info.n_splits;
+      sp.n_seg = 2 * info.n_splits;
       sp.seg_cnt = w.seg_cnt;
       sp.dense_n = dense ? static_cast<int>(hi - lo) : 0;
       sp.tau = w.tau;

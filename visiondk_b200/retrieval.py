@@ -80,6 +80,7 @@ class FlatIPIndex:
         self._gmax = None
         self._ws = None
         self.last_status = None
+        self.stage_ends = None  # optional override of the gallery range schedule (tuning / tests)
 
     # ---- faiss-shaped surface -------------------------------------------------------------------
     @property
@@ -127,6 +128,11 @@ class FlatIPIndex:
         ng = self._rows.n if self._rows is not None else 0
         plan = _lib.TopkPlan()
         _lib.check(lib.vdk_topk_plan_default(C.byref(plan), nq, ng, self.d, k), "vdk_topk_plan_default")
+        if self.stage_ends is not None and ng > 0:
+            ends = [min(int(e), ng) for e in self.stage_ends if int(e) < ng] + [ng]
+            plan.n_stages = len(ends)
+            for j in range(8):
+                plan.stage_end[j] = ends[min(j, len(ends) - 1)]
         need = lib.vdk_topk_workspace_bytes(C.byref(plan))
         if self._ws is None or self._ws.numel() < need:
             self._ws = torch.empty((need,), dtype=torch.uint8, device=self.device)
