@@ -1,22 +1,24 @@
 #!/usr/bin/env python
-"""bench.py — the hot-path benchmark (driver contract: one JSON line on rank 0).
+"""bench.py — the hot-path benchmark (driver contract: ONE JSON line on rank 0).
 
     python bench.py --gpus N --steps K --warmup W [--impl reference]
     python -m torch.distributed.run --nnodes=1 --nproc-per-node N ... bench.py --gpus N --steps K --warmup W
 
-Workload (BASELINE.json configs[3], the CBIR eval half of the metric): 10 000 queries x 1 000 000 gallery
-rows, 512-d, cosine top-100.  A "step" is one full search pass: L2-normalise + fp16 copy of the query block,
-score/filter over the whole (local shard of the) gallery on tcgen05, select + canonical re-rank.  Under N>1
-the gallery is sharded by rows (strong scaling: the 1M gallery is fixed), queries are all-gathered, every rank
-searches its shard, and the per-shard top-k lists are all-gathered and merged (NCCL over NVLink only for those
-two small exchanges).
+BASELINE.json's metric has two halves, "embeddings/sec and query x gallery pairs/sec, ConvNeXt-B 224^2"; both are
+the CBIR eval path (configs[3]: ConvNeXt-B 512-d, 1M gallery x 10k queries, cosine top-100).  The line's
+`metric`/`value` is the first half and the `retrieval` object carries the second with the same fields.
 
-`value`  : pairs/s with the query block and the index already resident in HBM.
-`e2e`    : the same through the reference-facing call FlatIPIndex.search(numpy float32) — host query buffer in,
-           host (scores, ids) out, both copies inside the timed region.
-`roofline`: the dominant kernel (score_filter over the last gallery range) timed alone with CUDA events.
-`cpu_baseline`: the oracle's reference formulation (256-query slices: q @ g.T + top-k, engine/cbir/evaluation.py
-           :190-195 with faiss replaced by its published brute-force algorithm) on the host cores.
+  embeddings/sec  step = one batch of 256 synthetic 224^2 images per GPU through TimmWrapper.embed(l2_normalize=True)
+                  (= FeatureExtractor.extract_cbir's model(x) + F.normalize, face_model.py:137-139), bf16 activations.
+                  N GPUs: images are independent units, no collective -> weak scaling.
+  pairs/sec       step = one full search: 10 000 queries x 1 000 000 gallery rows, 512-d, top-100
+                  (rows_prepare -> tcgen05 score/filter over the gallery ranges -> select -> canonical re-rank).
+                  N GPUs: gallery rows sharded, all-gather of queries and of per-shard lists + merge -> strong scaling.
+
+`value` is measured with inputs resident in HBM; `e2e` goes through the reference-facing call with HOST buffers
+(pinned): images H2D + embeddings D2H per step for extraction, FlatIPIndex.search-style query H2D + (scores, ids)
+D2H for retrieval.  `roofline` times the dominant kernel alone with CUDA events (tensor bound, measured peak from
+MEASURED_PEAKS.json).  `cpu_baseline` is the oracle's port of the reference CPU formulation on the host cores.
 """
 from __future__ import annotations
 
@@ -32,63 +34,76 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
 NQ, NG, DIM, K = 10000, 1000000, 512, 100
+MODEL, IMG, FEAT, BATCH = "convnext_base", 224, 512, 256
+GFLOP_PER_EMBEDDING = 30.76
 
 
 def parse():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--batch", type=int, default=BATCH)
     ap.add_argument("--nq", type=int, default=NQ)
     ap.add_argument("--ng", type=int, default=NG)
-    ap.add_argument("--dim", type=int, default=DIM)
     ap.add_argument("--k", type=int, default=K)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--only", default="both", choices=["both", "extract", "retrieval"])
     return ap.parse_args()
 
 
 # ------------------------------------------------------------------------------------------------------
-# clocks sampler (nvidia-smi during the timed region)
+# clocks during the timed region: one persistent nvidia-smi -lms process, parsed afterwards
 # ------------------------------------------------------------------------------------------------------
 class ClockSampler:
     FIELDS = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
               "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
 
     def __init__(self, index: int):
-        self.index, self.samples, self.stop_flag, self.thread = index, [], False, None
-
-    def _run(self):
-        while not self.stop_flag:
-            try:
-                out = subprocess.run(["nvidia-smi", f"--query-gpu={self.FIELDS}", "--format=csv,noheader,nounits",
-                                      "-i", str(self.index)], capture_output=True, text=True, timeout=5).stdout.strip()
-                if out:
-                    self.samples.append([c.strip() for c in out.split(",")])
-            except Exception:
-                pass
-            time.sleep(0.1)
+        self.index, self.proc, self.lines = index, None, []
 
     def start(self):
-        self.thread = threading.Thread(target=self._run, daemon=True)
-        self.thread.start()
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.FIELDS}", "--format=csv,noheader,nounits",
+                                          "-i", str(self.index), "-lms", "100"], stdout=subprocess.PIPE, text=True)
+            self.thread = threading.Thread(target=self._read, daemon=True)
+            self.thread.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.lines.append(line)
 
     def stop(self):
-        self.stop_flag = True
-        if self.thread:
-            self.thread.join(timeout=6)
-        sm = sorted(int(s[0]) for s in self.samples if s and s[0].isdigit())
-        mx = [int(s[1]) for s in self.samples if len(s) > 1 and s[1].isdigit()]
+        if self.proc is None:
+            return None
+        time.sleep(0.15)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except Exception:
+            self.proc.kill()
+        rows = [[c.strip() for c in l.split(",")] for l in self.lines if l.strip()]
+        sm = sorted(int(r[0]) for r in rows if r and r[0].isdigit())
+        mx = [int(r[1]) for r in rows if len(r) > 1 and r[1].isdigit()]
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        reasons = sorted({names[j] for s in self.samples for j in range(4) if len(s) > 2 + j and s[2 + j] == "Active"})
+        reasons = sorted({names[j] for r in rows for j in range(4) if len(r) > 2 + j and r[2 + j] == "Active"})
         return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(mx) if mx else None,
                 "reasons": reasons, "samples": len(sm)}
 
 
 # ------------------------------------------------------------------------------------------------------
-# CPU reference arm: the reference formulation on the host cores
+# CPU legs (oracle port of the reference formulation; the only place bench.py executes oracle/)
 # ------------------------------------------------------------------------------------------------------
-def cpu_reference_pass(q, g, k, slice_rows=256):
+def cpu_embeddings_pass(model, x):
+    import torch
+    with torch.no_grad():
+        return torch.nn.functional.normalize(model(x))  # face_model.py:137-139
+
+
+def cpu_retrieval_pass(q, g, k, slice_rows=256):
     """engine/cbir/evaluation.py:190-195: 256-query slices against the whole index, top-k per slice."""
     import torch
     outs = []
@@ -98,213 +113,277 @@ def cpu_reference_pass(q, g, k, slice_rows=256):
     return outs
 
 
-def cpu_baseline(ng, dim, k, target_s=12.0):
+def cpu_baselines(args, want_retrieval=True, target_s=10.0):
     import torch
+    from oracle.convnext import TimmWrapperOracle
     cores = os.cpu_count() or 1
     torch.set_num_threads(cores)
-    gen = torch.Generator().manual_seed(5)
-    g = torch.nn.functional.normalize(torch.randn(ng, dim, generator=gen))
-    q = torch.nn.functional.normalize(torch.randn(256, dim, generator=gen))
-    cpu_reference_pass(q[:64], g, k)  # warm-up
+    out = {}
+    model = TimmWrapperOracle(MODEL, FEAT, IMG).eval()
+    x = torch.randn(64, 3, IMG, IMG)
+    cpu_embeddings_pass(model, x[:8])
     t0 = time.perf_counter()
-    cpu_reference_pass(q, g, k)
-    t1 = time.perf_counter() - t0
-    reps = max(1, min(40, int(target_s / max(t1, 1e-3))))
-    t0 = time.perf_counter()
-    for _ in range(reps):
-        cpu_reference_pass(q, g, k)
+    n = 0
+    while True:
+        cpu_embeddings_pass(model, x)
+        n += 64
+        if time.perf_counter() - t0 > target_s or n >= 512:
+            break
     dt = time.perf_counter() - t0
-    pairs = reps * 256 * ng
-    return {"value": pairs / dt, "unit": "pairs/s", "cores": cores, "kind": "port",
-            "sample": f"{reps} x (256 queries x {ng} gallery x {dim}-d fp32, q@g.T + top-{k}), {dt:.1f} s"}, (q, g)
+    out["embeddings"] = {"value": n / dt, "unit": "embeddings/s", "cores": cores, "kind": "port",
+                         "sample": f"{n} images (bs 64, fp32 oracle ConvNeXt-B 224 + F.normalize), {dt:.1f} s"}
+    if want_retrieval:
+        gen = torch.Generator().manual_seed(5)
+        g = torch.nn.functional.normalize(torch.randn(args.ng, DIM, generator=gen))
+        q = torch.nn.functional.normalize(torch.randn(256, DIM, generator=gen))
+        cpu_retrieval_pass(q[:64], g, args.k)
+        t0 = time.perf_counter()
+        reps = 0
+        while True:
+            cpu_retrieval_pass(q, g, args.k)
+            reps += 1
+            if time.perf_counter() - t0 > target_s or reps >= 40:
+                break
+        dt = time.perf_counter() - t0
+        out["retrieval"] = {"value": reps * 256 * args.ng / dt, "unit": "pairs/s", "cores": cores, "kind": "port",
+                            "sample": f"{reps} x (256 queries x {args.ng} gallery x {DIM}-d fp32, q@g.T + top-{args.k}), {dt:.1f} s"}
+    return out
 
 
 def run_reference(args):
-    """--impl reference: the reference's own CPU formulation (oracle port; faiss is not installable here)."""
+    """--impl reference: the reference's own CPU formulation on the host cores (oracle port; timm/faiss cannot be
+    installed here).  One step = a bounded sample: one bs-64 batch of embeddings."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
     import torch
+    from oracle.convnext import TimmWrapperOracle
     cores = os.cpu_count() or 1
     torch.set_num_threads(cores)
-    ng, dim, k = args.ng, args.dim, args.k
-    gen = torch.Generator().manual_seed(5)
-    g = torch.nn.functional.normalize(torch.randn(ng, dim, generator=gen))
-    q = torch.nn.functional.normalize(torch.randn(256, dim, generator=gen))
-    # one step = a bounded sample of the workload: one 256-query slice against the full gallery
-    for _ in range(max(1, args.warmup)):
-        cpu_reference_pass(q, g, k)
+    model = TimmWrapperOracle(MODEL, FEAT, IMG).eval()
+    x = torch.randn(64, 3, IMG, IMG)
+    for _ in range(max(1, min(args.warmup, 2))):
+        cpu_embeddings_pass(model, x)
     t0 = time.perf_counter()
     for _ in range(args.steps):
-        cpu_reference_pass(q, g, k)
+        cpu_embeddings_pass(model, x)
     dt = time.perf_counter() - t0
-    value = args.steps * 256 * ng / dt
+    value = args.steps * 64 / dt
+    gen = torch.Generator().manual_seed(5)
+    g = torch.nn.functional.normalize(torch.randn(args.ng, DIM, generator=gen))
+    q = torch.nn.functional.normalize(torch.randn(256, DIM, generator=gen))
+    cpu_retrieval_pass(q, g, args.k)
+    t0 = time.perf_counter()
+    reps = max(1, min(args.steps, 5))
+    for _ in range(reps):
+        cpu_retrieval_pass(q, g, args.k)
+    rdt = time.perf_counter() - t0
+    rvalue = reps * 256 * args.ng / rdt
     line = {
-        "impl": "reference", "metric": "query x gallery pairs/sec (cosine top-100, 512-d)", "value": value,
-        "unit": "pairs/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
-        "ms_per_step": dt / args.steps * 1e3, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
+        "impl": "reference", "metric": "embeddings/sec (ConvNeXt-B 224^2, CBIR extract)", "value": value,
+        "unit": "embeddings/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": dt / args.steps * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "f32", "data": "synthetic",
-        "config": {"workload": f"CBIR eval: {args.nq} queries x {ng} gallery x {dim}-d, cosine top-{k}",
-                   "reference_formulation": "256-query slices, q @ g.T + top-k (faiss IndexFlatIP restated)"},
-        "cpu_baseline": {"value": value, "unit": "pairs/s", "cores": cores, "kind": "port",
-                         "sample": f"each step = 256 queries x {ng} gallery (1/{max(1, args.nq // 256)} of the query block)"},
-        "e2e": {"value": value, "unit": "pairs/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "config": {"workload": "CBIR eval extract: ConvNeXt-B 224^2 -> 512-d, L2-normalised",
+                   "note": "reference CPU path restated (oracle); each step = one bs-64 batch"},
+        "cpu_baseline": {"value": value, "unit": "embeddings/s", "cores": cores, "kind": "port",
+                         "sample": "each step = 64 images (bs 64) through the fp32 oracle ConvNeXt-B + F.normalize"},
+        "e2e": {"value": value, "unit": "embeddings/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
+        "retrieval": {"metric": "query x gallery pairs/sec (cosine top-100, 512-d)", "value": rvalue, "unit": "pairs/s",
+                      "cpu_baseline": {"value": rvalue, "unit": "pairs/s", "cores": cores, "kind": "port",
+                                       "sample": f"{reps} x (256 queries x {args.ng} gallery, q@g.T + top-{args.k})"},
+                      "e2e": {"value": rvalue, "unit": "pairs/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}},
     }
     print(json.dumps(line), flush=True)
 
 
 # ------------------------------------------------------------------------------------------------------
-# our arm
+# GPU legs
 # ------------------------------------------------------------------------------------------------------
-def main():
-    args = parse()
-    if args.impl == "reference":
-        return run_reference(args)
+class Ctx:
+    pass
 
-    import ctypes as C
+
+def timed(ctx, fn, steps, warmup):
+    """W warm-up calls, then K calls bracketed by barrier + synchronize; CUDA events; max over ranks."""
     import torch
     import torch.distributed as dist
-    from visiondk_b200 import _lib, build
+    for _ in range(max(3, warmup)):
+        fn()
+    ctx.barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(steps):
+        fn()
+    e1.record()
+    ctx.barrier()
+    ms = e0.elapsed_time(e1)
+    if ctx.world > 1:
+        t = torch.tensor([ms], device=ctx.dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms = float(t.item())
+    return ms / steps
+
+
+def peak_tflops():
+    try:
+        p = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+        return float(p["bf16_tflops"]), "MEASURED_PEAKS.json bf16_tflops (burst: kernel timed alone)"
+    except Exception:
+        return 1590.0, "fallback 1590 TFLOP/s (B200_PROFILING.md)"
+
+
+def bench_extract(ctx, args):
+    import ctypes as C
+    import torch
+    from visiondk_b200 import _lib
+    from visiondk_b200.backbone import TimmWrapper
+    lib = _lib.load()
+    B = args.batch
+    torch.manual_seed(0)
+    model = TimmWrapper(MODEL, FEAT, IMG, pretrained=False).to(ctx.dev).eval()
+    # random-init weights of the named architecture; visible layer scale so every block contributes
+    with torch.no_grad():
+        for n, p in model.named_parameters():
+            if n.endswith("gamma"):
+                p.fill_(0.1)
+    gen = torch.Generator(device=ctx.dev).manual_seed(ctx.rank)
+    pool = [torch.randn(B, 3, IMG, IMG, device=ctx.dev, generator=gen) for _ in range(2)]  # 2 x 154 MB > 126 MB L2
+    state = {"i": 0}
+
+    def step_dev():
+        x = pool[state["i"] & 1]
+        state["i"] += 1
+        return model.embed(x, l2_normalize=True)
+
+    ms = timed(ctx, step_dev, args.steps, args.warmup)
+    value = ctx.world * B / (ms * 1e-3)
+
+    host_x = [torch.randn(B, 3, IMG, IMG).pin_memory() for _ in range(2)]
+    host_out = torch.empty(B, FEAT).pin_memory()
+
+    def step_e2e():
+        x = host_x[state["i"] & 1].to(ctx.dev, non_blocking=True)
+        state["i"] += 1
+        e = model.embed(x, l2_normalize=True)
+        host_out.copy_(e, non_blocking=True)
+        torch.cuda.synchronize()
+
+    e2e_ms = timed(ctx, step_e2e, args.steps, args.warmup)
+
+    roof = None
+    if ctx.rank == 0:
+        # the dominant kernel: gemm_tn_kernel<256, bf16> at the shapes the network launches it with
+        depths, dims = model.model.depths, model.model.dims
+        shapes = []
+        hw = (IMG // 4) ** 2
+        for s, (d, c) in enumerate(zip(depths, dims)):
+            if s > 0:
+                hw //= 4
+                shapes.append((1, B * hw, c, 4 * dims[s - 1], _lib.EPI_NONE))
+            M = B * hw
+            shapes.append((d, M, 4 * c, c, _lib.EPI_GELU))
+            if c % 256 == 0:
+                shapes.append((d, M, c, 4 * c, _lib.EPI_SCALE_RESIDUAL))
+        tot_flops, tot_ms, n_launch = 0.0, 0.0, 0
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        for cnt, M, N, Kd, epi in shapes:
+            a = torch.randn(M, Kd, device=ctx.dev).to(torch.bfloat16)
+            w = torch.randn(N, Kd, device=ctx.dev).to(torch.bfloat16)
+            d_ = torch.empty(M, N, device=ctx.dev, dtype=torch.bfloat16)
+            bias = torch.zeros(N, device=ctx.dev)
+            gamma = torch.ones(N, device=ctx.dev)
+            res = torch.zeros(M, N, device=ctx.dev, dtype=torch.bfloat16) if epi == _lib.EPI_SCALE_RESIDUAL else None
+            g = _lib.GemmDesc(A=a.data_ptr(), B=w.data_ptr(), D=d_.data_ptr(), M=M, N=N, K=Kd, lda=Kd, ldb=Kd, ldd=N,
+                              in_dtype=_lib.DTYPE_BF16, out_dtype=_lib.DTYPE_BF16, epilogue=epi, bias=bias.data_ptr(),
+                              gamma=gamma.data_ptr(), beta=0, residual=_lib.ptr(res), ldr=N, ln_eps=1e-6, split_k=1)
+            for _ in range(2):
+                _lib.check(lib.vdk_gemm(C.byref(g), _lib.stream_ptr()), "vdk_gemm")
+            torch.cuda.synchronize()
+            reps = 5
+            e0.record()
+            for _ in range(reps):
+                _lib.check(lib.vdk_gemm(C.byref(g), _lib.stream_ptr()), "vdk_gemm")
+            e1.record()
+            torch.cuda.synchronize()
+            t = e0.elapsed_time(e1) / reps
+            tot_flops += cnt * 2.0 * M * N * Kd
+            tot_ms += cnt * t
+            n_launch += cnt
+            del a, w, d_, res
+        peak, src = peak_tflops()
+        ach = tot_flops / (tot_ms * 1e-3) / 1e12
+        roof = {"bound": "tensor", "kernel": "gemm_tn_kernel<256,bf16> (MLP / downsample shapes of one forward)",
+                "achieved": ach, "peak": peak, "unit": "TFLOP/s", "frac": ach / peak, "traffic": None, "peak_source": src,
+                "launches": n_launch, "launch_ms": tot_ms / n_launch, "algorithmic_flops_per_launch": tot_flops / n_launch,
+                "share_of_step": tot_ms / ms,
+                "whole_step": {"achieved": B * GFLOP_PER_EMBEDDING / ms, "frac": B * GFLOP_PER_EMBEDDING / ms / peak,
+                               "note": "30.76 GFLOP per embedding over the whole forward"}}
+    n_blocks = sum(model.model.depths)
+    return {"value": value, "ms": ms, "e2e_ms": e2e_ms, "roofline": roof,
+            "launches_per_step": 2 + 3 * n_blocks + 6 + 1 + 2,
+            "h2d": B * 3 * IMG * IMG * 4, "d2h": B * FEAT * 4, "batch": B}
+
+
+def bench_retrieval(ctx, args):
+    import ctypes as C
+    import torch
+    from visiondk_b200 import _lib, sharding
     from visiondk_b200.retrieval import FlatIPIndex, PreparedRows, merge_topk
-
-    world = int(os.environ.get("WORLD_SIZE", "1"))
-    rank = int(os.environ.get("RANK", "0"))
-    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
-    if not torch.cuda.is_available():
-        raise SystemExit("bench.py needs a B200: there is no CPU fallback for the hot path")
-    torch.cuda.set_device(local_rank)
-    dev = torch.device("cuda", local_rank)
-    if world > 1:
-        dist.init_process_group("nccl", device_id=dev)
-    build.build()
-    _lib.load()
-    _lib.require_device()
-
-    nq, ng, dim, k = args.nq, args.ng, args.dim, args.k
-    # synthetic data (seeded; the same rows on every rank, each rank keeps its shard)
-    lo = ng * rank // world
-    hi = ng * (rank + 1) // world
-    gen = torch.Generator(device=dev).manual_seed(5)
-    g_all_rows = None
+    lib = _lib.load()
+    nq, ng, dim, k = args.nq, args.ng, DIM, args.k
+    lo, hi = sharding.shard_bounds(ng, ctx.world, ctx.rank)
+    gen = torch.Generator(device=ctx.dev).manual_seed(5)
     chunks = []
-    # generate the full gallery in chunks with one generator so that shards are slices of the same 1M rows
-    step_rows = 125000
-    for a in range(0, ng, step_rows):
-        b = min(ng, a + step_rows)
-        blk = torch.nn.functional.normalize(torch.randn(b - a, dim, device=dev, generator=gen))
+    for a in range(0, ng, 125000):  # one generator stream so that shards are slices of the same 1M rows
+        b = min(ng, a + 125000)
+        blk = torch.nn.functional.normalize(torch.randn(b - a, dim, device=ctx.dev, generator=gen))
         s0, s1 = max(a, lo), min(b, hi)
         if s1 > s0:
             chunks.append(blk[s0 - a:s1 - a].clone())
         del blk
-    q_full = torch.nn.functional.normalize(torch.randn(nq, dim, device=dev, generator=gen))
-    index = FlatIPIndex(dim, dev, normalize=True, id_offset=lo)
+    q_full = torch.nn.functional.normalize(torch.randn(nq, dim, device=ctx.dev, generator=gen))
+    index = FlatIPIndex(dim, ctx.dev, normalize=True, id_offset=lo)
     for c in chunks:
         index.add(c)
     del chunks
     index._finalize()
-    q_lo, q_hi = nq * rank // world, nq * (rank + 1) // world
+    q_lo, q_hi = sharding.shard_bounds(nq, ctx.world, ctx.rank)
+    q_sizes = sharding.shard_sizes(nq, ctx.world)
     q_local = q_full[q_lo:q_hi].contiguous()
-    q_sizes = [nq * (r + 1) // world - nq * r // world for r in range(world)]
 
-    def step_device():
-        if world > 1:
-            # exchange 1: all-gather of the query embeddings (each rank extracted nq/world of them)
-            parts = [torch.empty((n, dim), dtype=torch.float32, device=dev) for n in q_sizes]
-            dist.all_gather(parts, q_local)
-            q = torch.cat(parts, 0)
-        else:
-            q = q_local
-        s, i = index.search_device(q, k)
-        if world > 1:
-            # exchange 2: all-gather of per-shard top-k, merged with the canonical tie rule
-            ss = torch.empty((world,) + tuple(s.shape), dtype=s.dtype, device=dev)
-            ii = torch.empty((world,) + tuple(i.shape), dtype=i.dtype, device=dev)
-            dist.all_gather_into_tensor(ss, s)
-            dist.all_gather_into_tensor(ii, i)
-            s, i = merge_topk(ss, ii, k)
-        return s, i
+    def step_dev():
+        return sharding.sharded_search(q_local, q_sizes, index.search_device, merge_topk, k)
 
-    def barrier():
-        if world > 1:
-            dist.barrier()
-        torch.cuda.synchronize()
-
-    for _ in range(max(3, args.warmup)):
-        out = step_device()
+    ms = timed(ctx, step_dev, args.steps, args.warmup)
     index.check_status()
-    barrier()
+    value = nq * ng / (ms * 1e-3)
 
-    sampler = ClockSampler(local_rank) if rank == 0 else None
-    if sampler:
-        sampler.start()
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    barrier()
-    e0.record()
-    for _ in range(args.steps):
-        out = step_device()
-    e1.record()
-    barrier()
-    ms_total = e0.elapsed_time(e1)
-    if world > 1:
-        t = torch.tensor([ms_total], device=dev)
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        ms_total = float(t.item())
-    ms_step = ms_total / args.steps
-    value = nq * ng / (ms_step * 1e-3)
-
-    # ---- e2e: host query buffer -> (scores, ids) on the host, through the faiss-shaped call ----
     q_host = torch.empty((nq, dim), dtype=torch.float32).pin_memory()
     q_host.copy_(q_full.cpu())
     s_host = torch.empty((nq, k), dtype=torch.float32).pin_memory()
     i_host = torch.empty((nq, k), dtype=torch.int64).pin_memory()
 
     def step_e2e():
-        qd = q_host[q_lo:q_hi].to(dev, non_blocking=True) if world > 1 else q_host.to(dev, non_blocking=True)
-        if world > 1:
-            parts = [torch.empty((n, dim), dtype=torch.float32, device=dev) for n in q_sizes]
-            dist.all_gather(parts, qd)
-            qd = torch.cat(parts, 0)
-        s, i = index.search_device(qd, k)
-        if world > 1:
-            ss = torch.empty((world,) + tuple(s.shape), dtype=s.dtype, device=dev)
-            ii = torch.empty((world,) + tuple(i.shape), dtype=i.dtype, device=dev)
-            dist.all_gather_into_tensor(ss, s)
-            dist.all_gather_into_tensor(ii, i)
-            s, i = merge_topk(ss, ii, k)
-        if rank == 0:
+        qd = q_host[q_lo:q_hi].to(ctx.dev, non_blocking=True)
+        s, i = sharding.sharded_search(qd, q_sizes, index.search_device, merge_topk, k)
+        if ctx.rank == 0:
             s_host.copy_(s, non_blocking=True)
             i_host.copy_(i, non_blocking=True)
         torch.cuda.synchronize()
 
-    for _ in range(3):
-        step_e2e()
-    barrier()
-    t0 = time.perf_counter()
-    e0.record()
-    for _ in range(args.steps):
-        step_e2e()
-    e1.record()
-    barrier()
-    e2e_ms = e0.elapsed_time(e1) / args.steps
-    if world > 1:
-        t = torch.tensor([e2e_ms], device=dev)
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        e2e_ms = float(t.item())
-    clocks = sampler.stop() if sampler else None
+    e2e_ms = timed(ctx, step_e2e, args.steps, args.warmup)
 
-    # ---- roofline: the dominant kernel alone (score/filter over the last gallery range) ----
-    lib = _lib.load()
     roof = None
-    if rank == 0:
-        ngl = hi - lo
-        plan = _lib.TopkPlan()
-        _lib.check(lib.vdk_topk_plan_default(C.byref(plan), nq, ngl, dim, k), "plan")
+    ngl = hi - lo
+    plan = _lib.TopkPlan()
+    _lib.check(lib.vdk_topk_plan_default(C.byref(plan), nq, ngl, dim, k), "plan")
+    if ctx.rank == 0:
         qp = PreparedRows(q_full, True)
         r_lo = plan.stage_end[plan.n_stages - 2] if plan.n_stages > 1 else 0
         dense = 1 if plan.n_stages == 1 else 0
         ws = index._ws  # thresholds of the last search are still in the workspace
-        reps = 5
 
         def score_only():
             _lib.check(lib.vdk_score_range(C.byref(plan), qp.xh.data_ptr(), index._rows.xh.data_ptr(), r_lo, ngl, dense,
@@ -312,6 +391,8 @@ def main():
 
         score_only()
         torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        reps = 5
         e0.record()
         for _ in range(reps):
             score_only()
@@ -319,44 +400,98 @@ def main():
         torch.cuda.synchronize()
         k_ms = e0.elapsed_time(e1) / reps
         flops = 2.0 * dim * nq * (ngl - r_lo)
-        peaks = {}
-        try:
-            peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
-        except Exception:
-            pass
-        peak = float(peaks.get("bf16_tflops", 1590.0))
+        peak, src = peak_tflops()
         ach = flops / (k_ms * 1e-3) / 1e12
-        roof = {"bound": "tensor", "kernel": "score_filter_kernel<false>", "achieved": ach, "peak": peak,
-                "unit": "TFLOP/s", "frac": ach / peak, "traffic": None,
-                "peak_source": "MEASURED_PEAKS.json bf16_tflops (burst; fp16 runs at the same tensor rate)" if peaks
-                else "fallback 1590 TFLOP/s (B200_PROFILING.md)",
-                "launch_ms": k_ms, "algorithmic_flops_per_launch": flops,
-                "share_of_step": k_ms / ms_step}
+        roof = {"bound": "tensor", "kernel": "score_filter_kernel<sparse> over the last gallery range", "achieved": ach,
+                "peak": peak, "unit": "TFLOP/s", "frac": ach / peak, "traffic": None, "peak_source": src, "launch_ms": k_ms,
+                "algorithmic_flops_per_launch": flops, "share_of_step": k_ms / ms,
+                "whole_step": {"achieved": 2.0 * dim * nq * ngl / (ms * 1e-3) / 1e12,
+                               "frac": 2.0 * dim * nq * ngl / (ms * 1e-3) / 1e12 / peak,
+                               "note": "2*D FLOP per pair over the whole search (all ranges, select, re-rank)"}}
+    launches = 2 + 2 * plan.n_stages + 1 + (1 if ctx.world > 1 else 0)
+    return {"value": value, "ms": ms, "e2e_ms": e2e_ms, "roofline": roof, "launches_per_step": launches,
+            "h2d": nq * dim * 4, "d2h": nq * k * 12}
 
-    cpu = None
-    if rank == 0 and world == 1 and not args.no_cpu_baseline:
-        cpu, _ = cpu_baseline(ng, dim, k)
 
-    if rank == 0:
-        n_stages = 4 if (hi - lo) > 262144 else (3 if (hi - lo) > 32768 else (2 if (hi - lo) > 4096 else 1))
-        launches_per_step = 1 + 1 + 2 * n_stages + (1 if world > 1 else 0)
-        line = {
-            "metric": "query x gallery pairs/sec (cosine top-100, 512-d)", "value": value, "unit": "pairs/s",
-            "n_gpus": world, "steps": args.steps, "warmup": max(3, args.warmup), "ms_per_step": ms_step,
-            "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f16 (candidates) + f64 re-rank",
-            "data": "synthetic",
-            "config": {"workload": f"CBIR eval: {nq} queries x {ng} gallery x {dim}-d, cosine top-{k}, gallery sharded by rows over {world} GPU(s)",
-                       "l2": "gallery (fp16 1.0 GB + fp32 2.0 GB per 1M rows) exceeds the 126 MB L2; no flush needed",
-                       "exactness": "ids and scores bit-exact vs oracle/retrieval.py (canonical fp64 re-rank)"},
-            "e2e": {"value": nq * ng / (e2e_ms * 1e-3), "unit": "pairs/s", "ms_per_step": e2e_ms,
-                    "h2d_bytes_per_step": nq * dim * 4, "d2h_bytes_per_step": nq * k * 12},
-            "gpu_launches": launches_per_step * args.steps,
-            "clocks": clocks,
-            "roofline": roof,
-            "cpu_baseline": cpu,
-        }
+def main():
+    args = parse()
+    if args.impl == "reference":
+        return run_reference(args)
+
+    import torch
+    import torch.distributed as dist
+    from visiondk_b200 import _lib, build
+
+    ctx = Ctx()
+    ctx.world = int(os.environ.get("WORLD_SIZE", "1"))
+    ctx.rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a B200: there is no CPU fallback for the hot path")
+    torch.cuda.set_device(local_rank)
+    ctx.dev = torch.device("cuda", local_rank)
+    if ctx.world > 1:
+        dist.init_process_group("nccl", device_id=ctx.dev)
+    build.build()
+    _lib.load()
+    _lib.require_device()
+
+    def barrier():
+        if ctx.world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    ctx.barrier = barrier
+
+    sampler = ClockSampler(local_rank) if ctx.rank == 0 else None
+    if sampler:
+        sampler.start()
+    ex = bench_extract(ctx, args) if args.only in ("both", "extract") else None
+    torch.cuda.empty_cache()
+    rt = bench_retrieval(ctx, args) if args.only in ("both", "retrieval") else None
+    clocks = sampler.stop() if sampler else None
+
+    cpu = {}
+    if ctx.rank == 0 and ctx.world == 1 and not args.no_cpu_baseline:
+        cpu = cpu_baselines(args, want_retrieval=rt is not None)
+
+    if ctx.rank == 0:
+        W = max(3, args.warmup)
+        retrieval = None
+        if rt is not None:
+            retrieval = {
+                "metric": "query x gallery pairs/sec (cosine top-100, 512-d)", "value": rt["value"], "unit": "pairs/s",
+                "ms_per_step": rt["ms"], "scaling": "strong", "dtype": "f16 candidates + f64 canonical re-rank",
+                "config": {"workload": f"{args.nq} queries x {args.ng} gallery x {DIM}-d, cosine top-{args.k}, gallery "
+                                       f"sharded by rows over {ctx.world} GPU(s)",
+                           "l2": "gallery (fp16 1.0 GB + fp32 2.0 GB per 1M rows) exceeds the 126 MB L2; no flush needed",
+                           "exactness": "ids and scores bit-exact vs oracle/retrieval.py"},
+                "e2e": {"value": args.nq * args.ng / (rt["e2e_ms"] * 1e-3), "unit": "pairs/s", "ms_per_step": rt["e2e_ms"],
+                        "h2d_bytes_per_step": rt["h2d"], "d2h_bytes_per_step": rt["d2h"]},
+                "gpu_launches": rt["launches_per_step"] * args.steps,
+                "roofline": rt["roofline"], "cpu_baseline": cpu.get("retrieval"),
+            }
+        if ex is not None:
+            line = {
+                "metric": "embeddings/sec (ConvNeXt-B 224^2, CBIR extract)", "value": ex["value"], "unit": "embeddings/s",
+                "n_gpus": ctx.world, "steps": args.steps, "warmup": W, "ms_per_step": ex["ms"], "higher_is_better": True,
+                "scaling": "weak", "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
+                "config": {"workload": f"CBIR eval extract: ConvNeXt-B {IMG}^2 -> {FEAT}-d L2-normalised embeddings, "
+                                       f"batch {ex['batch']} per GPU, random-init weights",
+                           "l2": "two alternating input batches (2 x 154 MB) exceed the 126 MB L2; activations stream through HBM",
+                           "second_metric": "see `retrieval` (pairs/sec, same CBIR eval path)"},
+                "e2e": {"value": ctx.world * ex["batch"] / (ex["e2e_ms"] * 1e-3), "unit": "embeddings/s",
+                        "ms_per_step": ex["e2e_ms"], "h2d_bytes_per_step": ex["h2d"], "d2h_bytes_per_step": ex["d2h"]},
+                "gpu_launches": ex["launches_per_step"] * args.steps,
+                "clocks": clocks, "roofline": ex["roofline"], "cpu_baseline": cpu.get("embeddings"),
+                "retrieval": retrieval,
+            }
+        else:
+            line = dict(retrieval)
+            line.update({"n_gpus": ctx.world, "steps": args.steps, "warmup": W, "higher_is_better": True,
+                         "vs_baseline": None, "data": "synthetic", "clocks": clocks})
         print(json.dumps(line), flush=True)
-    if world > 1:
+    if ctx.world > 1:
         dist.destroy_process_group()
 
 

@@ -31,6 +31,7 @@ struct GemmParams {
   int epilogue;
   float ln_eps;
   int split_k;  // > 1: each tile's K range is split over split_k work items, fp32 partials are atomically added
+  int tma_store;  // 16-bit outputs: stage 128x64 sub-tiles in smem and write them with TMA (full-line stores)
 };
 
 template <int BN>
@@ -41,7 +42,8 @@ struct GemmCfg {
   static constexpr int kStages = (BN == 256) ? 4 : 6;
   static constexpr int kTmemCols = 2 * BN;
   // stages + barriers (full, empty: kStages each; tmem_full, tmem_empty: 2 each) + tmem ptr + 1 KB align slack
-  static constexpr int kSmemBytes = kStages * kStageBytes + (2 * kStages + 4) * 8 + 16 + 1024;
+  static constexpr int kStoreStageBytes = kBM * 64 * 2;  // one 128 x 64 16-bit sub-tile per epilogue half
+  static constexpr int kSmemBytes = kStages * kStageBytes + 2 * kStoreStageBytes + (2 * kStages + 4) * 8 + 16 + 1024;
 };
 
 // GELU(x) = 0.5 x (1 + erf(x / sqrt 2)), erf by Abramowitz-Stegun 7.1.26 (|abs err| < 1.5e-7) on the SFU
@@ -89,14 +91,77 @@ __device__ __forceinline__ float2 unpack2(uint32_t u, int dtype) {
   }
 }
 
+// Per-chunk epilogue arithmetic on this thread's 32 consecutive columns [col0, col0 + ncols) of row `row`.
+__device__ __forceinline__ void epi_math(const GemmParams& p, float (&v)[32], int row, int col0, int ncols, float ln_mean,
+                                         float ln_rstd) {
+  if (p.bias != nullptr) {
+#pragma unroll
+    for (int j = 0; j < 32; j += 4) {
+      if (j < ncols) {
+        const float4 b = __ldg(reinterpret_cast<const float4*>(p.bias + col0 + j));
+        v[j] += b.x; v[j + 1] += b.y; v[j + 2] += b.z; v[j + 3] += b.w;
+      }
+    }
+  }
+  if (p.epilogue == VDK_EPI_GELU) {
+#pragma unroll
+    for (int j = 0; j < 32; ++j) v[j] = gelu_erf(v[j]);
+  } else if (p.epilogue == VDK_EPI_LAYERNORM) {
+#pragma unroll
+    for (int j = 0; j < 32; j += 4) {
+      if (j < ncols) {
+        const float4 g = __ldg(reinterpret_cast<const float4*>(p.gamma + col0 + j));
+        const float4 b = __ldg(reinterpret_cast<const float4*>(p.beta + col0 + j));
+        v[j] = (v[j] - ln_mean) * ln_rstd * g.x + b.x;
+        v[j + 1] = (v[j + 1] - ln_mean) * ln_rstd * g.y + b.y;
+        v[j + 2] = (v[j + 2] - ln_mean) * ln_rstd * g.z + b.z;
+        v[j + 3] = (v[j + 3] - ln_mean) * ln_rstd * g.w + b.w;
+      }
+    }
+  } else if (p.epilogue == VDK_EPI_SCALE_RESIDUAL) {
+#pragma unroll
+    for (int j = 0; j < 32; j += 4) {
+      if (j < ncols) {
+        const float4 g = __ldg(reinterpret_cast<const float4*>(p.gamma + col0 + j));
+        v[j] *= g.x; v[j + 1] *= g.y; v[j + 2] *= g.z; v[j + 3] *= g.w;
+      }
+    }
+    if (row < p.M) {
+      if (p.out_dtype == VDK_DTYPE_FP32) {
+        const float* res = reinterpret_cast<const float*>(p.residual) + static_cast<size_t>(row) * p.ldr + col0;
+#pragma unroll
+        for (int j = 0; j < 32; j += 4) {
+          if (j < ncols) {
+            const float4 t = *reinterpret_cast<const float4*>(res + j);
+            v[j] += t.x; v[j + 1] += t.y; v[j + 2] += t.z; v[j + 3] += t.w;
+          }
+        }
+      } else {
+        const uint16_t* res = reinterpret_cast<const uint16_t*>(p.residual) + static_cast<size_t>(row) * p.ldr + col0;
+#pragma unroll
+        for (int j = 0; j < 32; j += 8) {
+          if (j < ncols) {
+            const uint4 t = *reinterpret_cast<const uint4*>(res + j);
+            const float2 a0 = unpack2(t.x, p.out_dtype), a1 = unpack2(t.y, p.out_dtype);
+            const float2 a2 = unpack2(t.z, p.out_dtype), a3 = unpack2(t.w, p.out_dtype);
+            v[j] += a0.x; v[j + 1] += a0.y; v[j + 2] += a1.x; v[j + 3] += a1.y;
+            v[j + 4] += a2.x; v[j + 5] += a2.y; v[j + 6] += a3.x; v[j + 7] += a3.y;
+          }
+        }
+      }
+    }
+  }
+}
+
 template <int BN, bool kBf16>
 __global__ void __launch_bounds__(kGemmThreads, 1)
 gemm_tn_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b,
-               const GemmParams p) {
+               const __grid_constant__ CUtensorMap map_d, const GemmParams p) {
   using Cfg = GemmCfg<BN>;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + Cfg::kStages * Cfg::kStageBytes);
+  uint8_t* smem_store = smem + Cfg::kStages * Cfg::kStageBytes;
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem_store + 2 * Cfg::kStoreStageBytes);
   uint64_t* empty_bar = full_bar + Cfg::kStages;
   uint64_t* tmem_full = empty_bar + Cfg::kStages;
   uint64_t* tmem_empty = tmem_full + 2;
@@ -115,6 +180,7 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
   if (warp == 0 && lane == 0) {
     prefetch_tensormap(&map_a);
     prefetch_tensormap(&map_b);
+    if (p.tma_store) prefetch_tensormap(&map_d);
     for (int i = 0; i < Cfg::kStages; ++i) {
       mbar_init(&full_bar[i], 1);
       mbar_init(&empty_bar[i], 1);
@@ -197,6 +263,7 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
     // ===================== epilogue =====================
     const int lane_base = (warp & 3) * 32;  // TMEM lanes this warp may touch
     const int half = (warp - 2) >> 2;       // which of the two warps sharing this lane quarter
+    bool stores_issued = false;
     int it = 0;
     for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
       const int acc = it & 1;
@@ -243,95 +310,84 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
         }
         ln_rstd = rsqrtf(sq / static_cast<float>(p.N) + p.ln_eps);
       }
+      if (p.tma_store) {
+        // 16-bit outputs: each half stages 128 x 64 sub-tiles (128-byte rows, 128B swizzle) and one thread hands
+        // them to TMA, so global memory sees full-line stores instead of 32 row-strided 16-byte pieces per warp
+        uint8_t* stg = smem_store + half * Cfg::kStoreStageBytes;
+        const bool leader = threadIdx.x == 64 + half * 128;
+        const int rit = lane_base + lane;  // row inside the tile
 #pragma unroll 1
-      for (int c = half; c < BN / 32; c += 2) {
-        uint32_t r[32];
-        tmem_ld_32x32b_x32(tacc + c * 32, r);
-        tmem_ld_wait();
-        const int col0 = n0 + c * 32;
-        if (row < p.M && col0 < p.N && p.split_k > 1) {
-          // split-K: raw fp32 partial sums, combined in HBM (D was zeroed by the caller)
-          float* out = reinterpret_cast<float*>(p.D) + static_cast<size_t>(row) * p.ldd + col0;
-          const int ncols = min(32, p.N - col0);
+        for (int sc = half; sc < BN / 64; sc += 2) {
+          const int colS = n0 + sc * 64;
+          if (colS >= p.N) break;
+          uint32_t packed[32];
 #pragma unroll
-          for (int j = 0; j < 32; ++j)
-            if (j < ncols) atomicAdd(out + j, __uint_as_float(r[j]));
-        } else if (row < p.M && col0 < p.N) {
-          float v[32];
+          for (int hh = 0; hh < 2; ++hh) {
+            uint32_t r[32];
+            tmem_ld_32x32b_x32(tacc + sc * 64 + hh * 32, r);
+            tmem_ld_wait();
+            float v[32];
 #pragma unroll
-          for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]);
-          const int ncols = min(32, p.N - col0);  // multiple of 8 (N % 8 == 0 is required)
-          if (p.bias != nullptr) {
+            for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]);
+            const int col0 = colS + hh * 32;
+            const int ncols = max(0, min(32, p.N - col0));
+            if (ncols > 0) epi_math(p, v, row, col0, ncols, ln_mean, ln_rstd);
 #pragma unroll
-            for (int j = 0; j < 32; j += 4) {
-              if (j < ncols) {
-                const float4 b = __ldg(reinterpret_cast<const float4*>(p.bias + col0 + j));
-                v[j] += b.x; v[j + 1] += b.y; v[j + 2] += b.z; v[j + 3] += b.w;
-              }
-            }
+            for (int j = 0; j < 32; j += 2) packed[hh * 16 + (j >> 1)] = pack2(v[j], v[j + 1], p.out_dtype);
           }
-          if (p.epilogue == VDK_EPI_GELU) {
+          if (stores_issued) {  // the previous sub-tile must have been read out of the staging buffer
+            if (leader) tma_store_wait_read<0>();
+            named_bar_sync(1 + half, 128);
+          }
 #pragma unroll
-            for (int j = 0; j < 32; ++j) v[j] = gelu_erf(v[j]);
-          } else if (p.epilogue == VDK_EPI_LAYERNORM) {
+          for (int q = 0; q < 8; ++q)
+            *reinterpret_cast<uint4*>(stg + rit * 128 + ((q ^ (rit & 7)) << 4)) =
+                make_uint4(packed[4 * q], packed[4 * q + 1], packed[4 * q + 2], packed[4 * q + 3]);
+          fence_proxy_async_smem();
+          named_bar_sync(1 + half, 128);
+          if (leader) {
+            tma_store_2d(&map_d, stg, colS, m0);
+            tma_store_commit();
+          }
+          stores_issued = true;
+        }
+      } else {
+#pragma unroll 1
+        for (int c = half; c < BN / 32; c += 2) {
+          uint32_t r[32];
+          tmem_ld_32x32b_x32(tacc + c * 32, r);
+          tmem_ld_wait();
+          const int col0 = n0 + c * 32;
+          if (row < p.M && col0 < p.N && p.split_k > 1) {
+            // split-K: raw fp32 partial sums, combined in HBM (D was zeroed by the caller)
+            float* out = reinterpret_cast<float*>(p.D) + static_cast<size_t>(row) * p.ldd + col0;
+            const int ncols = min(32, p.N - col0);
 #pragma unroll
-            for (int j = 0; j < 32; j += 4) {
-              if (j < ncols) {
-                const float4 g = __ldg(reinterpret_cast<const float4*>(p.gamma + col0 + j));
-                const float4 b = __ldg(reinterpret_cast<const float4*>(p.beta + col0 + j));
-                v[j] = (v[j] - ln_mean) * ln_rstd * g.x + b.x;
-                v[j + 1] = (v[j + 1] - ln_mean) * ln_rstd * g.y + b.y;
-                v[j + 2] = (v[j + 2] - ln_mean) * ln_rstd * g.z + b.z;
-                v[j + 3] = (v[j + 3] - ln_mean) * ln_rstd * g.w + b.w;
-              }
-            }
-          } else if (p.epilogue == VDK_EPI_SCALE_RESIDUAL) {
+            for (int j = 0; j < 32; ++j)
+              if (j < ncols) atomicAdd(out + j, __uint_as_float(r[j]));
+          } else if (row < p.M && col0 < p.N) {
+            float v[32];
 #pragma unroll
-            for (int j = 0; j < 32; j += 4) {
-              if (j < ncols) {
-                const float4 g = __ldg(reinterpret_cast<const float4*>(p.gamma + col0 + j));
-                v[j] *= g.x; v[j + 1] *= g.y; v[j + 2] *= g.z; v[j + 3] *= g.w;
-              }
-            }
+            for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]);
+            const int ncols = min(32, p.N - col0);  // multiple of 8 (N % 8 == 0 is required)
+            epi_math(p, v, row, col0, ncols, ln_mean, ln_rstd);
             if (p.out_dtype == VDK_DTYPE_FP32) {
-              const float* res = reinterpret_cast<const float*>(p.residual) + static_cast<size_t>(row) * p.ldr + col0;
+              float* out = reinterpret_cast<float*>(p.D) + static_cast<size_t>(row) * p.ldd + col0;
 #pragma unroll
-              for (int j = 0; j < 32; j += 4) {
-                if (j < ncols) {
-                  const float4 t = *reinterpret_cast<const float4*>(res + j);
-                  v[j] += t.x; v[j + 1] += t.y; v[j + 2] += t.z; v[j + 3] += t.w;
-                }
-              }
+              for (int j = 0; j < 32; j += 4)
+                if (j < ncols) *reinterpret_cast<float4*>(out + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
             } else {
-              const uint16_t* res = reinterpret_cast<const uint16_t*>(p.residual) + static_cast<size_t>(row) * p.ldr + col0;
+              uint16_t* out = reinterpret_cast<uint16_t*>(p.D) + static_cast<size_t>(row) * p.ldd + col0;
 #pragma unroll
               for (int j = 0; j < 32; j += 8) {
                 if (j < ncols) {
-                  const uint4 t = *reinterpret_cast<const uint4*>(res + j);
-                  const float2 a0 = unpack2(t.x, p.out_dtype), a1 = unpack2(t.y, p.out_dtype);
-                  const float2 a2 = unpack2(t.z, p.out_dtype), a3 = unpack2(t.w, p.out_dtype);
-                  v[j] += a0.x; v[j + 1] += a0.y; v[j + 2] += a1.x; v[j + 3] += a1.y;
-                  v[j + 4] += a2.x; v[j + 5] += a2.y; v[j + 6] += a3.x; v[j + 7] += a3.y;
+                  uint4 t;
+                  t.x = pack2(v[j], v[j + 1], p.out_dtype);
+                  t.y = pack2(v[j + 2], v[j + 3], p.out_dtype);
+                  t.z = pack2(v[j + 4], v[j + 5], p.out_dtype);
+                  t.w = pack2(v[j + 6], v[j + 7], p.out_dtype);
+                  *reinterpret_cast<uint4*>(out + j) = t;
                 }
-              }
-            }
-          }
-          if (p.out_dtype == VDK_DTYPE_FP32) {
-            float* out = reinterpret_cast<float*>(p.D) + static_cast<size_t>(row) * p.ldd + col0;
-#pragma unroll
-            for (int j = 0; j < 32; j += 4)
-              if (j < ncols) *reinterpret_cast<float4*>(out + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
-          } else {
-            uint16_t* out = reinterpret_cast<uint16_t*>(p.D) + static_cast<size_t>(row) * p.ldd + col0;
-#pragma unroll
-            for (int j = 0; j < 32; j += 8) {
-              if (j < ncols) {
-                uint4 t;
-                t.x = pack2(v[j], v[j + 1], p.out_dtype);
-                t.y = pack2(v[j + 2], v[j + 3], p.out_dtype);
-                t.z = pack2(v[j + 4], v[j + 5], p.out_dtype);
-                t.w = pack2(v[j + 6], v[j + 7], p.out_dtype);
-                *reinterpret_cast<uint4*>(out + j) = t;
               }
             }
           }
@@ -340,6 +396,7 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
       tc_fence_before();
       mbar_arrive(&tmem_empty[acc]);
     }
+    if (p.tma_store && stores_issued && threadIdx.x == 64 + half * 128) tma_store_wait<0>();
   }
 
   tc_fence_before();
@@ -351,7 +408,8 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
 }
 
 template <int BN, bool kBf16>
-static int launch_gemm(const CUtensorMap& ma, const CUtensorMap& mb, const GemmParams& p, cudaStream_t stream) {
+static int launch_gemm(const CUtensorMap& ma, const CUtensorMap& mb, const CUtensorMap& md, const GemmParams& p,
+                       cudaStream_t stream) {
   using Cfg = GemmCfg<BN>;
   auto kern = gemm_tn_kernel<BN, kBf16>;
   static bool attr_set = false;  // per (BN, dtype) instantiation
@@ -361,7 +419,7 @@ static int launch_gemm(const CUtensorMap& ma, const CUtensorMap& mb, const GemmP
   }
   const int num_tiles = ((p.M + kBM - 1) / kBM) * ((p.N + BN - 1) / BN) * p.split_k;
   const int grid = num_tiles < sm_count() ? num_tiles : sm_count();
-  kern<<<grid, kGemmThreads, Cfg::kSmemBytes, stream>>>(ma, mb, p);
+  kern<<<grid, kGemmThreads, Cfg::kSmemBytes, stream>>>(ma, mb, md, p);
   VDK_CUDA_OK(cudaGetLastError());
   return VDK_OK;
 }
@@ -415,11 +473,17 @@ int gemm_run(const vdk_gemm_desc& g, cudaStream_t s) {
   if (rc != VDK_OK) return rc;
   rc = make_tma_2d_16bit(&mb, g.B, (uint64_t)g.N, (uint64_t)g.K, (uint64_t)g.ldb, BN, kBK);
   if (rc != VDK_OK) return rc;
+  const int tma_store = (g.out_dtype != VDK_DTYPE_FP32 && split == 1) ? 1 : 0;
+  CUtensorMap md = ma;  // placeholder when unused
+  if (tma_store) {
+    rc = make_tma_2d_16bit(&md, g.D, (uint64_t)g.M, (uint64_t)g.N, (uint64_t)g.ldd, kBM, 64);
+    if (rc != VDK_OK) return rc;
+  }
   GemmParams p{g.M, g.N, g.K, g.D, g.ldd, g.bias, g.gamma, g.beta, g.residual, g.ldr, g.out_dtype, g.epilogue,
-               g.ln_eps, split};
+               g.ln_eps, split, tma_store};
   const bool bf = g.in_dtype == VDK_DTYPE_BF16;
-  if (wide) return bf ? launch_gemm<256, true>(ma, mb, p, s) : launch_gemm<256, false>(ma, mb, p, s);
-  return bf ? launch_gemm<128, true>(ma, mb, p, s) : launch_gemm<128, false>(ma, mb, p, s);
+  if (wide) return bf ? launch_gemm<256, true>(ma, mb, md, p, s) : launch_gemm<256, false>(ma, mb, md, p, s);
+  return bf ? launch_gemm<128, true>(ma, mb, md, p, s) : launch_gemm<128, false>(ma, mb, md, p, s);
 }
 
 }  // namespace vdk

@@ -331,6 +331,7 @@ score_filter_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_cons
 // select: one CTA per query — k-th largest approximate score, admission bound, compaction of survivors
 // ------------------------------------------------------------------------------------------------
 constexpr int kSelThreads = 128;
+constexpr unsigned kShortList = 256;  // lists up to this length are swept by a single warp
 
 struct SelectParams {
   int n_query, k;
@@ -386,10 +387,22 @@ __global__ void __launch_bounds__(kSelThreads) select_kernel(const SelectParams 
     for (int shift = 24; shift >= 0; shift -= 8) {
       for (int i = tid; i < 256; i += kSelThreads) hist[i] = 0;
       __syncthreads();
+      // long lists (the dense first range) are swept by the whole CTA, short ones (a segment holds tens of
+      // entries) by one warp each, so that 30+ nearly empty lists do not cost 30+ CTA-wide loop trips
       for (int l = 0; l < n_lists; ++l) {
-        const uint2* e = list_ptr(l);
         const unsigned c = s_cnt[l];
+        if (c <= kShortList) continue;
+        const uint2* e = list_ptr(l);
         for (unsigned i = tid; i < c; i += kSelThreads) {
+          const uint32_t key = ord_u32(__uint_as_float(e[i].x));
+          if ((key & mask) == prefix) atomicAdd(&hist[(key >> shift) & 255u], 1u);
+        }
+      }
+      for (int l = warp; l < n_lists; l += kSelThreads / 32) {
+        const unsigned c = s_cnt[l];
+        if (c > kShortList) continue;
+        const uint2* e = list_ptr(l);
+        for (unsigned i = lane; i < c; i += 32) {
           const uint32_t key = ord_u32(__uint_as_float(e[i].x));
           if ((key & mask) == prefix) atomicAdd(&hist[(key >> shift) & 255u], 1u);
         }
@@ -431,9 +444,22 @@ __global__ void __launch_bounds__(kSelThreads) select_kernel(const SelectParams 
   // ---- compaction of the survivors into the other carry buffer ----
   uint2* out = p.carry_out + static_cast<size_t>(row) * p.carry_cap;
   for (int l = 0; l < n_lists; ++l) {
-    const uint2* e = list_ptr(l);
     const unsigned c = s_cnt[l];
+    if (c <= kShortList) continue;
+    const uint2* e = list_ptr(l);
     for (unsigned i = tid; i < c; i += kSelThreads) {
+      const uint2 v = e[i];
+      if (__uint_as_float(v.x) >= tau_use) {
+        const unsigned pos = atomicAdd(&s_m, 1u);
+        if (pos < static_cast<unsigned>(p.carry_cap)) out[pos] = v;
+      }
+    }
+  }
+  for (int l = warp; l < n_lists; l += kSelThreads / 32) {
+    const unsigned c = s_cnt[l];
+    if (c > kShortList) continue;
+    const uint2* e = list_ptr(l);
+    for (unsigned i = lane; i < c; i += 32) {
       const uint2 v = e[i];
       if (__uint_as_float(v.x) >= tau_use) {
         const unsigned pos = atomicAdd(&s_m, 1u);
