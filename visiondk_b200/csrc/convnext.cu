@@ -49,129 +49,150 @@ __global__ void __launch_bounds__(256) stem_patchify_kernel(const float* __restr
 // ------------------------------------------------------------------------------------------------
 // depthwise 7x7 + bias + LayerNorm(C)
 // ------------------------------------------------------------------------------------------------
-// A "group" of C/4 threads (4 contiguous channels each -> 8-byte coalesced NHWC loads) produces a strip of
-// kDwTW output pixels of one image row; a CTA holds G groups working on G consecutive rows, so the 7-row
-// input halo is shared through L1.  The 49 taps of a thread's 4 channels are read 7 at a time (one filter row),
-// accumulators stay in registers, and LayerNorm over C is a reduction inside the group (pure warp shuffles when
-// the group is a single warp).  FMA-bound: 49 FMAs per output against ~4 bytes of HBM traffic.
-constexpr int kDwTW = 8;  // output pixels per strip along W
-
-__global__ void __launch_bounds__(256)
-dwconv7_ln_kernel(const __nv_bfloat16* __restrict__ x, int B, int H, int W, int C, int tpg /*threads per group, x32*/,
+// One CTA = a TH x TW tile of output pixels x ALL channels (LayerNorm couples the channels of a pixel).  The
+// (TH+6) x (TW+6) x C input halo is brought into shared memory by TMA as a 4-D NHWC box whose out-of-bounds part
+// is zero-filled by the hardware — exactly the convolution's zero padding, so the arithmetic loop has no bounds
+// checks.  A "group" of C/4 threads (4 contiguous channels each: conflict-free 8-byte LDS, coalesced 8-byte STG)
+// owns one output row of the tile at a time; the 49 taps of a thread's 4 channels are read one filter row at a
+// time (L1-resident), accumulators stay in registers, and LayerNorm over C is a reduction inside the group.
+// FMA-bound: 49 FMAs per output against 2 + 2 bytes of HBM traffic.
+template <int TW>
+__global__ void __launch_bounds__(512)
+dwconv7_ln_kernel(const __grid_constant__ CUtensorMap map_x, int B, int H, int W, int C, int TH, int box_c,
+                  int tpg /*threads per group, whole warps*/,
                   const float* __restrict__ w49,  // [49][C]
                   const float* __restrict__ bias, const float* __restrict__ ln_w, const float* __restrict__ ln_b,
                   float eps, __nv_bfloat16* __restrict__ y) {
-  __shared__ float red[8][kDwTW][8];  // [group][pixel][warp in group]
+  extern __shared__ uint8_t dw_smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(dw_smem_raw) + 127) & ~uintptr_t(127));
+  const int box_h = TH + 6, box_w = TW + 6;
+  const int n_chunks = C / box_c;
+  const int chunk_bytes = box_h * box_w * box_c * 2;
+  float* red = reinterpret_cast<float*>(smem + n_chunks * chunk_bytes);  // [group][TW][warps per group <= 16]
+  uint64_t* bar = reinterpret_cast<uint64_t*>(red + 16 * TW * 16);
+
   const int groups = blockDim.x / tpg;
   const int grp = threadIdx.x / tpg;
-  const int tig = threadIdx.x - grp * tpg;  // thread in group
-  const int tiles_w = (W + kDwTW - 1) / kDwTW;
-  const int tiles_h = (H + groups - 1) / groups;
+  const int tig = threadIdx.x - grp * tpg;
+  const int tiles_w = (W + TW - 1) / TW, tiles_h = (H + TH - 1) / TH;
   const int tw = blockIdx.x % tiles_w;
   const int th = (blockIdx.x / tiles_w) % tiles_h;
   const int b = blockIdx.x / (tiles_w * tiles_h);
-  const int oy = th * groups + grp;
-  const int ox0 = tw * kDwTW;
+  const int oy0 = th * TH, ox0 = tw * TW;
   const int c0 = tig * 4;
-  const bool active = c0 < C && oy < H;
+  const bool has_c = c0 < C;
   const int lane = threadIdx.x & 31;
-  const int wig = tig >> 5, nwig = tpg >> 5;  // warp in group, warps per group
+  const int wig = tig >> 5, nwig = tpg >> 5;
 
-  float acc[kDwTW][4];
-#pragma unroll
-  for (int p = 0; p < kDwTW; ++p)
-#pragma unroll
-    for (int c = 0; c < 4; ++c) acc[p][c] = 0.f;
+  if (threadIdx.x == 0) {
+    prefetch_tensormap(&map_x);
+    mbar_init(bar, 1);
+    fence_mbar_init();
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    mbar_arrive_expect_tx(bar, n_chunks * chunk_bytes);
+    for (int ch = 0; ch < n_chunks; ++ch)
+      tma_load_4d(smem + ch * chunk_bytes, &map_x, bar, ch * box_c, ox0 - 3, oy0 - 3, b);
+  }
+  // weights / affine parameters of this thread's channels while the tile is in flight
+  float4 bc = make_float4(0.f, 0.f, 0.f, 0.f), g4 = bc, b4 = bc;
+  if (has_c) {
+    bc = __ldg(reinterpret_cast<const float4*>(bias + c0));
+    g4 = __ldg(reinterpret_cast<const float4*>(ln_w + c0));
+    b4 = __ldg(reinterpret_cast<const float4*>(ln_b + c0));
+  }
+  const int pix_stride = box_c * 2;  // bytes between neighbouring pixels of one chunk
+  const uint8_t* tbase = smem + (has_c ? (c0 / box_c) * chunk_bytes + (c0 % box_c) * 2 : 0);
+  mbar_wait(bar, 0);
 
-  if (active) {
-    const __nv_bfloat16* xb = x + static_cast<int64_t>(b) * H * W * C;
+  const float inv_c = 1.0f / static_cast<float>(C);
+  const int rounds = (TH + groups - 1) / groups;
+  for (int rd = 0; rd < rounds; ++rd) {
+    const int oyl = rd * groups + grp;  // output row inside the tile
+    const bool active = has_c && oyl < TH && oy0 + oyl < H;
+    float acc[TW][4];
+#pragma unroll
+    for (int p = 0; p < TW; ++p) {
+      acc[p][0] = bc.x; acc[p][1] = bc.y; acc[p][2] = bc.z; acc[p][3] = bc.w;
+    }
+    if (active) {
 #pragma unroll 1
-    for (int dy = 0; dy < 7; ++dy) {
-      const int iy = oy + dy - 3;
-      if (iy < 0 || iy >= H) continue;
-      float4 wrow[7];
+      for (int dy = 0; dy < 7; ++dy) {
+        float4 wrow[7];
 #pragma unroll
-      for (int dx = 0; dx < 7; ++dx) wrow[dx] = __ldg(reinterpret_cast<const float4*>(w49 + (dy * 7 + dx) * C + c0));
-      const __nv_bfloat16* xrow = xb + static_cast<int64_t>(iy) * W * C + c0;
+        for (int dx = 0; dx < 7; ++dx) wrow[dx] = __ldg(reinterpret_cast<const float4*>(w49 + (dy * 7 + dx) * C + c0));
+        const uint8_t* rowp = tbase + static_cast<size_t>((oyl + dy) * box_w) * pix_stride;
 #pragma unroll
-      for (int ix = 0; ix < kDwTW + 6; ++ix) {
-        const int gx = ox0 + ix - 3;
-        if (gx < 0 || gx >= W) continue;
-        const uint2 t = *reinterpret_cast<const uint2*>(xrow + static_cast<int64_t>(gx) * C);
-        const float2 a = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&t.x));
-        const float2 c = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&t.y));
+        for (int ix = 0; ix < TW + 6; ++ix) {
+          const uint2 t = *reinterpret_cast<const uint2*>(rowp + ix * pix_stride);
+          const float2 a = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&t.x));
+          const float2 c = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&t.y));
 #pragma unroll
-        for (int p = 0; p < kDwTW; ++p) {
-          const int dx = ix - p;  // input column ix feeds output pixel p through tap dx
-          if (dx >= 0 && dx < 7) {
-            acc[p][0] = fmaf(a.x, wrow[dx].x, acc[p][0]);
-            acc[p][1] = fmaf(a.y, wrow[dx].y, acc[p][1]);
-            acc[p][2] = fmaf(c.x, wrow[dx].z, acc[p][2]);
-            acc[p][3] = fmaf(c.y, wrow[dx].w, acc[p][3]);
+          for (int p = 0; p < TW; ++p) {
+            const int dx = ix - p;  // input column ix feeds output pixel p through tap dx
+            if (dx >= 0 && dx < 7) {
+              acc[p][0] = fmaf(a.x, wrow[dx].x, acc[p][0]);
+              acc[p][1] = fmaf(a.y, wrow[dx].y, acc[p][1]);
+              acc[p][2] = fmaf(c.x, wrow[dx].z, acc[p][2]);
+              acc[p][3] = fmaf(c.y, wrow[dx].w, acc[p][3]);
+            }
           }
         }
       }
     }
-    const float4 bc = __ldg(reinterpret_cast<const float4*>(bias + c0));
+    // LayerNorm over C for the TW pixels of this row: mean, then centred second moment, reduced in the group
+    float mean[TW], rstd[TW];
 #pragma unroll
-    for (int p = 0; p < kDwTW; ++p) {
-      acc[p][0] += bc.x; acc[p][1] += bc.y; acc[p][2] += bc.z; acc[p][3] += bc.w;
-    }
-  }
-
-  // LayerNorm over C per pixel: reduce inside the group (mean, then centred second moment)
-  float mean[kDwTW], rstd[kDwTW];
-  const float inv_c = 1.0f / static_cast<float>(C);
+    for (int pass = 0; pass < 2; ++pass) {
+      float sred[TW];
 #pragma unroll
-  for (int pass = 0; pass < 2; ++pass) {
-    float s[kDwTW];
+      for (int p = 0; p < TW; ++p) {
+        float v = 0.f;
+        if (active) {
 #pragma unroll
-    for (int p = 0; p < kDwTW; ++p) {
-      float v = 0.f;
-      if (active) {
-#pragma unroll
-        for (int c = 0; c < 4; ++c) {
-          const float d = pass == 0 ? acc[p][c] : acc[p][c] - mean[p];
-          v += pass == 0 ? d : d * d;
+          for (int c = 0; c < 4; ++c) {
+            const float d = pass == 0 ? acc[p][c] : acc[p][c] - mean[p];
+            v += pass == 0 ? d : d * d;
+          }
         }
+        sred[p] = warp_sum(v);
       }
-      s[p] = warp_sum(v);
-    }
-    if (nwig > 1) {  // uniform across the CTA (tpg is a launch parameter)
-      if (lane == 0) {
+      if (nwig > 1) {  // uniform across the CTA
+        if (lane == 0) {
 #pragma unroll
-        for (int p = 0; p < kDwTW; ++p) red[grp][p][wig] = s[p];
+          for (int p = 0; p < TW; ++p) red[(grp * TW + p) * 16 + wig] = sred[p];
+        }
+        __syncthreads();
+#pragma unroll
+        for (int p = 0; p < TW; ++p) {
+          float t = 0.f;
+          for (int w = 0; w < nwig; ++w) t += red[(grp * TW + p) * 16 + w];
+          sred[p] = t;
+        }
+        __syncthreads();
       }
-      __syncthreads();
 #pragma unroll
-      for (int p = 0; p < kDwTW; ++p) {
-        float t = 0.f;
-        for (int w = 0; w < nwig; ++w) t += red[grp][p][w];
-        s[p] = t;
+      for (int p = 0; p < TW; ++p) {
+        if (pass == 0) mean[p] = sred[p] * inv_c;
+        else rstd[p] = rsqrtf(sred[p] * inv_c + eps);
       }
-      __syncthreads();
     }
+    if (active) {
 #pragma unroll
-    for (int p = 0; p < kDwTW; ++p) {
-      if (pass == 0) mean[p] = s[p] * inv_c;
-      else rstd[p] = rsqrtf(s[p] * inv_c + eps);
-    }
-  }
-
-  if (active) {
-    const float4 g = __ldg(reinterpret_cast<const float4*>(ln_w + c0));
-    const float4 bb = __ldg(reinterpret_cast<const float4*>(ln_b + c0));
-#pragma unroll
-    for (int p = 0; p < kDwTW; ++p) {
-      const int ox = ox0 + p;
-      if (ox >= W) continue;
-      __nv_bfloat16* dst = y + ((static_cast<int64_t>(b) * H + oy) * W + ox) * C + c0;
-      __nv_bfloat162 lo = __floats2bfloat162_rn((acc[p][0] - mean[p]) * rstd[p] * g.x + bb.x, (acc[p][1] - mean[p]) * rstd[p] * g.y + bb.y);
-      __nv_bfloat162 hi = __floats2bfloat162_rn((acc[p][2] - mean[p]) * rstd[p] * g.z + bb.z, (acc[p][3] - mean[p]) * rstd[p] * g.w + bb.w);
-      uint2 t;
-      t.x = *reinterpret_cast<uint32_t*>(&lo);
-      t.y = *reinterpret_cast<uint32_t*>(&hi);
-      *reinterpret_cast<uint2*>(dst) = t;
+      for (int p = 0; p < TW; ++p) {
+        const int ox = ox0 + p;
+        if (ox >= W) continue;
+        __nv_bfloat16* dst = y + ((static_cast<int64_t>(b) * H + oy0 + oyl) * W + ox) * C + c0;
+        __nv_bfloat162 lo = __floats2bfloat162_rn((acc[p][0] - mean[p]) * rstd[p] * g4.x + b4.x,
+                                                  (acc[p][1] - mean[p]) * rstd[p] * g4.y + b4.y);
+        __nv_bfloat162 hi = __floats2bfloat162_rn((acc[p][2] - mean[p]) * rstd[p] * g4.z + b4.z,
+                                                  (acc[p][3] - mean[p]) * rstd[p] * g4.w + b4.w);
+        uint2 t;
+        t.x = *reinterpret_cast<uint32_t*>(&lo);
+        t.y = *reinterpret_cast<uint32_t*>(&hi);
+        *reinterpret_cast<uint2*>(dst) = t;
+      }
     }
   }
 }
@@ -285,16 +306,39 @@ static int check_net(const vdk_convnext_net* n) {
 
 using namespace vdk;
 
-static int launch_dwconv7_ln(const __nv_bfloat16* x, int batch, int H, int W, int C, const float* w49, const float* bias,
-                             const float* ln_w, const float* ln_b, float eps, __nv_bfloat16* y, cudaStream_t s) {
-  VDK_REQUIRE(C % 4 == 0 && C <= 1024, "dwconv7_ln: C must be a multiple of 4, <= 1024 (got %d)", C);
-  const int tpg = ((C / 4) + 31) / 32 * 32;     // threads per group, whole warps
-  const int groups = std::max(1, 256 / tpg);    // strips (consecutive rows) per CTA
-  const int tiles_w = (W + kDwTW - 1) / kDwTW, tiles_h = (H + groups - 1) / groups;
-  const unsigned grid = static_cast<unsigned>(batch) * tiles_h * tiles_w;
-  dwconv7_ln_kernel<<<grid, groups * tpg, 0, s>>>(x, batch, H, W, C, tpg, w49, bias, ln_w, ln_b, eps, y);
+template <int TW>
+static int launch_dwconv_tw(const CUtensorMap& mx, int batch, int H, int W, int C, int TH, int box_c, const float* w49,
+                            const float* bias, const float* ln_w, const float* ln_b, float eps, __nv_bfloat16* y,
+                            cudaStream_t s) {
+  const int tpg = ((C / 4) + 31) / 32 * 32;
+  const int groups = std::max(1, std::min(512 / tpg, TH));
+  const int n_chunks = C / box_c;
+  const int smem = n_chunks * (TH + 6) * (TW + 6) * box_c * 2 + 16 * TW * 16 * 4 + 16 + 128;
+  auto kern = dwconv7_ln_kernel<TW>;
+  VDK_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+  const unsigned grid = static_cast<unsigned>(batch) * ((H + TH - 1) / TH) * ((W + TW - 1) / TW);
+  kern<<<grid, groups * tpg, smem, s>>>(mx, batch, H, W, C, TH, box_c, tpg, w49, bias, ln_w, ln_b, eps, y);
   VDK_CUDA_OK(cudaGetLastError());
   return VDK_OK;
+}
+
+static int launch_dwconv7_ln(const __nv_bfloat16* x, int batch, int H, int W, int C, const float* w49, const float* bias,
+                             const float* ln_w, const float* ln_b, float eps, __nv_bfloat16* y, cudaStream_t s) {
+  VDK_REQUIRE(C % 8 == 0 && C <= 2048, "dwconv7_ln: C must be a multiple of 8, <= 2048 (got %d)", C);
+  // channel chunk of one TMA box: the largest divisor of C that is <= 256 and a multiple of 8
+  int box_c = std::min(C, 256);
+  while (C % box_c != 0 || box_c % 8 != 0) --box_c;
+  // spatial tile: the largest of 7 / 4 / 2 whose halo (T+6)^2 x C x 2 B fits in ~200 KB of shared memory
+  int T = 7;
+  while (T > 2 && (T + 6) * (T + 6) * C * 2 > 200 * 1024) T = (T == 7) ? 4 : 2;
+  VDK_REQUIRE((T + 6) * (T + 6) * C * 2 <= 200 * 1024, "dwconv7_ln: C too large for the shared-memory halo (%d)", C);
+  const int TH = std::min(T, H);
+  CUtensorMap mx;
+  int rc = make_tma_nhwc_16bit(&mx, x, batch, H, W, C, TH + 6, T + 6, box_c);
+  if (rc != VDK_OK) return rc;
+  if (T == 7) return launch_dwconv_tw<7>(mx, batch, H, W, C, TH, box_c, w49, bias, ln_w, ln_b, eps, y, s);
+  if (T == 4) return launch_dwconv_tw<4>(mx, batch, H, W, C, TH, box_c, w49, bias, ln_w, ln_b, eps, y, s);
+  return launch_dwconv_tw<2>(mx, batch, H, W, C, TH, box_c, w49, bias, ln_w, ln_b, eps, y, s);
 }
 
 extern "C" int vdk_dwconv7_ln(const void* x, int batch, int H, int W, int C, const float* w49, const float* bias,

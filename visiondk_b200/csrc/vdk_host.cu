@@ -62,6 +62,24 @@ int make_tma_2d_16bit(CUtensorMap* map, const void* base, uint64_t rows, uint64_
   return VDK_OK;
 }
 
+int make_tma_nhwc_16bit(CUtensorMap* map, const void* base, int B, int H, int W, int C, int box_h, int box_w,
+                        int box_c) {
+  EncodeTiledFn fn = encode_tiled_fn();
+  if (!fn) return fail(VDK_ERR_CUDA, "cuTensorMapEncodeTiled entry point unavailable (no CUDA driver?)");
+  if ((reinterpret_cast<uintptr_t>(base) & 15) != 0 || (C * 2) % 16 != 0 || (box_c * 2) % 16 != 0)
+    return fail(VDK_ERR_INVALID, "NHWC TMA operand must be 16-byte aligned with C*2 a multiple of 16 (C=%d)", C);
+  if (box_c > 256 || box_w > 256 || box_h > 256) return fail(VDK_ERR_INVALID, "NHWC TMA box dims must be <= 256");
+  cuuint64_t gdim[4] = {(cuuint64_t)C, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)B};
+  cuuint64_t gstride[3] = {(cuuint64_t)C * 2, (cuuint64_t)W * C * 2, (cuuint64_t)H * W * C * 2};
+  cuuint32_t box[4] = {(cuuint32_t)box_c, (cuuint32_t)box_w, (cuuint32_t)box_h, 1};
+  cuuint32_t estr[4] = {1, 1, 1, 1};
+  CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_UINT16, 4, const_cast<void*>(base), gdim, gstride, box, estr,
+                  CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) return fail(VDK_ERR_CUDA, "cuTensorMapEncodeTiled (NHWC) failed with CUresult %d", (int)r);
+  return VDK_OK;
+}
+
 int sm_count() {
   static int n = 0;
   if (n == 0) {

@@ -34,6 +34,10 @@ int fail(int code, const char* fmt, ...);
 int make_tma_2d_16bit(CUtensorMap* map, const void* base, uint64_t rows, uint64_t cols, uint64_t ld,
                       uint32_t box_rows, uint32_t box_cols);
 
+// 4-D tile map over an NHWC 16-bit tensor: box = [1, box_h, box_w, box_c], no swizzle, out-of-bounds reads give 0
+// (which is exactly the zero padding of a convolution).
+int make_tma_nhwc_16bit(CUtensorMap* map, const void* base, int B, int H, int W, int C, int box_h, int box_w, int box_c);
+
 int sm_count();
 
 }  // namespace vdk
