@@ -198,6 +198,8 @@ typedef struct vdk_topk_plan {
   int cand_capacity;     /* per-query slots for one range's admitted candidates (multiple of 32, >= 2k) */
   int carry_capacity;    /* per-query slots for survivors carried between ranges (in [2k, 4096]) */
   int n_stages;          /* gallery is scanned in n_stages ranges; thresholds tighten between them */
+  int dense_mask;        /* bit s set: range s is scored densely (no admission threshold; must fit cand_capacity);
+                            bit 0 is implied.  An all-dense plan cannot overflow a segment (the wide path). */
   int64_t stage_end[8];  /* exclusive end row of each stage (last == n_gallery) */
 } vdk_topk_plan;
 
@@ -217,6 +219,11 @@ int vdk_ip_topk(const vdk_topk_plan* plan, const float* q32, const void* qh, con
                 const float* q_err, const float* g32, const void* gh, const float* g_norm_max,
                 const float* g_err_max, int64_t id_offset, float* out_scores, int64_t* out_ids, int32_t* status,
                 void* workspace, size_t workspace_bytes, void* stream);
+
+/* Device pointer (inside `workspace`) to int32[n_query] flags the last vdk_ip_topk set for rows whose candidate lists
+ * overflowed; status[0] counts them.  Their results are incomplete and must be recomputed with an all-dense plan. */
+int vdk_topk_row_flags(const vdk_topk_plan* plan, const void* workspace, size_t workspace_bytes,
+                       const int32_t** row_flags);
 
 /* Measurement hook: launches ONLY the score/filter kernel of vdk_ip_topk for gallery rows [lo, hi), reusing the
  * thresholds a previous vdk_ip_topk left in `workspace` (dense != 0: the threshold-free first-range variant).

@@ -174,3 +174,34 @@ def test_topk_full_size_properties(lib):
     top = full.topk(k, dim=1).indices
     agree = (top == i[rows]).float().mean().item()
     assert agree > 0.999, f"sampled brute-force agreement {agree} ({info})"
+
+
+def test_adversarially_ordered_gallery_takes_the_wide_path(lib):
+    """Gallery sorted by increasing similarity to the queries: every later range beats the thresholds learnt on the
+    earlier ones, candidate segments overflow, and the flagged queries must be recomputed (all-dense plan) exactly."""
+    rng = np.random.default_rng(11)
+    dim, ng, nq, k = 128, 60000, 40, 50
+    p = rng.standard_normal(dim).astype(np.float32)
+    g = R.l2_normalize(rng.standard_normal((ng, dim)).astype(np.float32) + 0.6 * p)
+    order = np.argsort(g @ (p / np.linalg.norm(p)), kind="stable")
+    g = g[order]
+    q = R.l2_normalize(p[None, :] + 0.3 * rng.standard_normal((nq, dim)).astype(np.float32))
+    idx = FlatIPIndex(dim, "cuda")
+    idx.add(g)
+    s, i = idx.search(q, k)  # numpy API resolves overflow
+    assert idx.wide_path_rows > 0, "this gallery is built to overflow the admission segments"
+    ref_s, ref_i = R.flat_ip_search_candidates(q, g, k)
+    assert_same(s, i, ref_s, ref_i, "wide path")
+    # the un-resolved device call reports the overflow instead of silently returning incomplete lists
+    idx.search_device(torch.from_numpy(q).cuda(), k)
+    with pytest.raises(RuntimeError):
+        idx.check_status()
+
+
+def test_massive_duplicates_fail_loudly(lib):
+    v = unit_rows(1, 64, 1)
+    g = np.repeat(v, 5000, axis=0)  # 5000 exact ties: more than carry_capacity
+    idx = FlatIPIndex(64, "cuda")
+    idx.add(g)
+    with pytest.raises(RuntimeError):
+        idx.search(unit_rows(2, 64, 2), 10)

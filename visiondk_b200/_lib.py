@@ -32,6 +32,7 @@ class TopkPlan(C.Structure):
         ("cand_capacity", C.c_int),
         ("carry_capacity", C.c_int),
         ("n_stages", C.c_int),
+        ("dense_mask", C.c_int),
         ("stage_end", C.c_int64 * 8),
     ]
 
@@ -72,6 +73,7 @@ SIGNATURES = {
     "vdk_topk_plan_default": (_i, [C.POINTER(TopkPlan), _i64, _i64, _i, _i]),
     "vdk_topk_workspace_bytes": (_sz, [C.POINTER(TopkPlan)]),
     "vdk_ip_topk": (_i, [C.POINTER(TopkPlan), _p, _p, _p, _p, _p, _p, _p, _p, _i64, _p, _p, _p, _p, _sz, _p]),
+    "vdk_topk_row_flags": (_i, [C.POINTER(TopkPlan), _p, _sz, C.POINTER(C.c_void_p)]),
     "vdk_score_range": (_i, [C.POINTER(TopkPlan), _p, _p, _i64, _i64, _i, _p, _sz, _p]),
     "vdk_reduce_max": (_i, [_p, _i64, _p, _p]),
     "vdk_topk_merge": (_i, [_p, _p, _i, _i64, _i, _p, _p, _p]),

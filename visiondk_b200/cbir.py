@@ -18,6 +18,41 @@ import torch
 from .retrieval import FlatIPIndex
 
 
+def _prefetch_to_device(dataloader, device):
+    """Yields device batches with the host->device copy of batch i+1 (pinned memory, side stream) overlapping the
+    kernels of batch i — what the reference's DataLoader(pin_memory=True) + .to(device, non_blocking=True)
+    (engine/vision_engine.py:457-468, face_model.py:136) is meant to achieve."""
+    copy_stream = torch.cuda.Stream(device=device)
+    main = torch.cuda.current_stream(device)
+
+    def stage(batch):
+        if isinstance(batch, (list, tuple)):
+            batch = batch[0]
+        if batch.device == device:
+            return batch, None
+        with torch.cuda.stream(copy_stream):
+            dev = batch.to(device, non_blocking=True)
+            ev = torch.cuda.Event()
+            ev.record(copy_stream)
+        return dev, ev
+
+    it = iter(dataloader)
+    try:
+        nxt = stage(next(it))
+    except StopIteration:
+        return
+    while nxt is not None:
+        cur, ev = nxt
+        try:
+            nxt = stage(next(it))
+        except StopIteration:
+            nxt = None
+        if ev is not None:
+            main.wait_event(ev)
+            cur.record_stream(main)
+        yield cur
+
+
 class FeatureExtractor:
     """models/faceX/face_model.py:88-144 (CBIR branch)."""
 
@@ -34,18 +69,32 @@ class FeatureExtractor:
         model.eval()
         model.to(device)
         feats = []
-        for tensors in dataloader:
-            if isinstance(tensors, (list, tuple)):
-                tensors = tensors[0]
-            tensors = tensors.to(device, non_blocking=True)
+        for tensors in _prefetch_to_device(dataloader, device):
             feats.append(model.embed(tensors, l2_normalize=True))
         if not feats:
             return torch.empty((0, model.feat_dim), dtype=torch.float32, device=device)
         return torch.cat(feats, dim=0)
 
+    @torch.no_grad()
     def extract_cbir(self, dataloader, device) -> np.ndarray:
-        """Reference signature: numpy float32 [N, feat_dim] (one device->host copy at the end, not one per batch)."""
-        return self.extract_cbir_device(dataloader, device).cpu().numpy()
+        """Reference signature: numpy float32 [N, feat_dim].  Every batch's embeddings are copied to pinned host
+        memory asynchronously (the reference blocks on `.cpu().numpy()` per batch, face_model.py:140)."""
+        device = torch.device(device)
+        if device.type != "cuda":
+            raise RuntimeError("visiondk_b200 extraction runs on CUDA (sm_100a) only; there is no CPU fallback")
+        model = self.model
+        model.eval()
+        model.to(device)
+        host_chunks = []
+        for tensors in _prefetch_to_device(dataloader, device):
+            emb = model.embed(tensors, l2_normalize=True)
+            host = torch.empty(emb.shape, dtype=torch.float32, pin_memory=True)
+            host.copy_(emb, non_blocking=True)
+            host_chunks.append(host)
+        torch.cuda.current_stream(device).synchronize()
+        if not host_chunks:
+            return np.zeros((0, model.feat_dim), np.float32)
+        return np.concatenate([h.numpy() for h in host_chunks], axis=0)
 
 
 def index(extractor: FeatureExtractor, gallery_dataloader, device, logger=None, index_factory: str = "Flat",
@@ -84,6 +133,5 @@ def search(extractor: FeatureExtractor, query_dataloader, faiss_index: FlatIPInd
     q = extractor.extract_cbir_device(query_dataloader, device)
     if logger is not None:
         logger.console("Searching ...")
-    scores, ids = faiss_index.search_device(q, k)
-    faiss_index.check_status()
+    scores, ids = faiss_index.search_device(q, k, resolve_overflow=True)
     return scores.cpu().numpy(), ids.cpu().numpy()

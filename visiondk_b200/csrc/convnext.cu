@@ -200,40 +200,56 @@ dwconv7_ln_kernel(const __grid_constant__ CUtensorMap map_x, int B, int H, int W
 // ------------------------------------------------------------------------------------------------
 // LayerNorm over C of NHWC rows, optionally scattered into 2x2/stride-2 patch rows (kh, kw, c)
 // ------------------------------------------------------------------------------------------------
+template <int LPP>  // lanes per pixel (8, 16 or 32); each lane owns 8-channel (16-byte) vectors c = (sub + i*LPP)*8
 __global__ void __launch_bounds__(256)
 ln_patchify_kernel(const __nv_bfloat16* __restrict__ x, int B, int H, int W, int C, const float* __restrict__ ln_w,
                    const float* __restrict__ ln_b, float eps, int patch /*1 or 2*/, __nv_bfloat16* __restrict__ out) {
-  // one warp per input pixel; lane handles channel pairs lane*2 + 64*i
+  constexpr int kPPW = 32 / LPP;  // pixels per warp
+  constexpr int kMaxIter = 8;     // C <= LPP * 8 * kMaxIter
   const int lane = threadIdx.x & 31;
-  const int64_t pix = (static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x) >> 5;
+  const int sub = lane % LPP;
+  const int64_t warp_id = (static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x) >> 5;
+  const int64_t pix = warp_id * kPPW + lane / LPP;
   const int64_t npix = static_cast<int64_t>(B) * H * W;
-  if (pix >= npix) return;
-  const __nv_bfloat16* src = x + pix * C;
-  constexpr int kMaxIter = 16;  // C <= 2048
-  float2 v[kMaxIter];
-  const int iters = (C + 63) / 64;
+  const bool ok = pix < npix;
+  const __nv_bfloat16* src = x + (ok ? pix : 0) * C;
+  const int iters = (C + LPP * 8 - 1) / (LPP * 8);
+  float v[kMaxIter][8];
   float s = 0.f;
 #pragma unroll
   for (int i = 0; i < kMaxIter; ++i) {
     if (i < iters) {
-      const int c = i * 64 + lane * 2;
-      v[i] = c < C ? __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(src + c)) : make_float2(0.f, 0.f);
-      s += v[i].x + v[i].y;
+      const int c = (sub + i * LPP) * 8;
+      uint4 t = make_uint4(0, 0, 0, 0);
+      if (ok && c < C) t = *reinterpret_cast<const uint4*>(src + c);
+      const float2 a0 = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&t.x));
+      const float2 a1 = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&t.y));
+      const float2 a2 = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&t.z));
+      const float2 a3 = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&t.w));
+      v[i][0] = a0.x; v[i][1] = a0.y; v[i][2] = a1.x; v[i][3] = a1.y;
+      v[i][4] = a2.x; v[i][5] = a2.y; v[i][6] = a3.x; v[i][7] = a3.y;
+#pragma unroll
+      for (int j = 0; j < 8; ++j) s += v[i][j];
     }
   }
-  const float mean = warp_sum(s) / static_cast<float>(C);
+#pragma unroll
+  for (int off = LPP / 2; off > 0; off >>= 1) s += __shfl_xor_sync(0xffffffffu, s, off);
+  const float mean = s / static_cast<float>(C);
   float q = 0.f;
 #pragma unroll
   for (int i = 0; i < kMaxIter; ++i) {
-    if (i < iters) {
-      const int c = i * 64 + lane * 2;
-      if (c < C) {
-        const float a = v[i].x - mean, b = v[i].y - mean;
-        q += a * a + b * b;
+    if (i < iters && (sub + i * LPP) * 8 < C) {
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        const float d = v[i][j] - mean;
+        q = fmaf(d, d, q);
       }
     }
   }
-  const float rstd = rsqrtf(warp_sum(q) / static_cast<float>(C) + eps);
+#pragma unroll
+  for (int off = LPP / 2; off > 0; off >>= 1) q += __shfl_xor_sync(0xffffffffu, q, off);
+  const float rstd = rsqrtf(q / static_cast<float>(C) + eps);
+  if (!ok) return;
   int64_t orow;
   int ocol0;
   if (patch == 2) {
@@ -249,16 +265,38 @@ ln_patchify_kernel(const __nv_bfloat16* __restrict__ x, int B, int H, int W, int
   __nv_bfloat16* dst = out + orow * (static_cast<int64_t>(C) * patch * patch) + ocol0;
 #pragma unroll
   for (int i = 0; i < kMaxIter; ++i) {
-    if (i < iters) {
-      const int c = i * 64 + lane * 2;
-      if (c < C) {
-        const float2 g = *reinterpret_cast<const float2*>(ln_w + c);
-        const float2 bb = *reinterpret_cast<const float2*>(ln_b + c);
-        *reinterpret_cast<__nv_bfloat162*>(dst + c) =
-            __floats2bfloat162_rn((v[i].x - mean) * rstd * g.x + bb.x, (v[i].y - mean) * rstd * g.y + bb.y);
-      }
+    const int c = (sub + i * LPP) * 8;
+    if (i < iters && c < C) {
+      const float4 g0 = __ldg(reinterpret_cast<const float4*>(ln_w + c)), g1 = __ldg(reinterpret_cast<const float4*>(ln_w + c + 4));
+      const float4 b0 = __ldg(reinterpret_cast<const float4*>(ln_b + c)), b1 = __ldg(reinterpret_cast<const float4*>(ln_b + c + 4));
+      __nv_bfloat162 o0 = __floats2bfloat162_rn((v[i][0] - mean) * rstd * g0.x + b0.x, (v[i][1] - mean) * rstd * g0.y + b0.y);
+      __nv_bfloat162 o1 = __floats2bfloat162_rn((v[i][2] - mean) * rstd * g0.z + b0.z, (v[i][3] - mean) * rstd * g0.w + b0.w);
+      __nv_bfloat162 o2 = __floats2bfloat162_rn((v[i][4] - mean) * rstd * g1.x + b1.x, (v[i][5] - mean) * rstd * g1.y + b1.y);
+      __nv_bfloat162 o3 = __floats2bfloat162_rn((v[i][6] - mean) * rstd * g1.z + b1.z, (v[i][7] - mean) * rstd * g1.w + b1.w);
+      uint4 t;
+      t.x = *reinterpret_cast<uint32_t*>(&o0); t.y = *reinterpret_cast<uint32_t*>(&o1);
+      t.z = *reinterpret_cast<uint32_t*>(&o2); t.w = *reinterpret_cast<uint32_t*>(&o3);
+      *reinterpret_cast<uint4*>(dst + c) = t;
     }
   }
+}
+
+static int launch_ln_patchify(const __nv_bfloat16* x, int B, int H, int W, int C, const float* ln_w, const float* ln_b, float eps,
+                              int patch, __nv_bfloat16* out, cudaStream_t s) {
+  VDK_REQUIRE(C % 8 == 0 && C <= 2048, "layernorm_patchify: C must be a multiple of 8, <= 2048 (got %d)", C);
+  const int64_t npix = static_cast<int64_t>(B) * H * W;
+  const int vecs = C / 8;
+  if (vecs <= 8) {
+    const int64_t warps = (npix + 3) / 4;
+    ln_patchify_kernel<8><<<static_cast<unsigned>((warps * 32 + 255) / 256), 256, 0, s>>>(x, B, H, W, C, ln_w, ln_b, eps, patch, out);
+  } else if (vecs <= 16) {
+    const int64_t warps = (npix + 1) / 2;
+    ln_patchify_kernel<16><<<static_cast<unsigned>((warps * 32 + 255) / 256), 256, 0, s>>>(x, B, H, W, C, ln_w, ln_b, eps, patch, out);
+  } else {
+    ln_patchify_kernel<32><<<static_cast<unsigned>((npix * 32 + 255) / 256), 256, 0, s>>>(x, B, H, W, C, ln_w, ln_b, eps, patch, out);
+  }
+  VDK_CUDA_OK(cudaGetLastError());
+  return VDK_OK;
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -352,14 +390,10 @@ extern "C" int vdk_dwconv7_ln(const void* x, int batch, int H, int W, int C, con
 extern "C" int vdk_layernorm_patchify(const void* x, int batch, int H, int W, int C, const float* ln_w,
                                       const float* ln_b, float eps, int patch, void* out, void* stream) {
   VDK_REQUIRE(x && out && ln_w && ln_b, "vdk_layernorm_patchify: null operand");
-  VDK_REQUIRE(batch > 0 && H > 0 && W > 0 && C > 0 && C % 2 == 0 && C <= 2048, "vdk_layernorm_patchify: bad shape");
+  VDK_REQUIRE(batch > 0 && H > 0 && W > 0 && C > 0 && C % 8 == 0 && C <= 2048, "vdk_layernorm_patchify: bad shape");
   VDK_REQUIRE(patch == 1 || (patch == 2 && H % 2 == 0 && W % 2 == 0), "vdk_layernorm_patchify: patch must be 1 or 2");
-  const int64_t npix = static_cast<int64_t>(batch) * H * W;
-  ln_patchify_kernel<<<static_cast<unsigned>((npix * 32 + 255) / 256), 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
-      reinterpret_cast<const __nv_bfloat16*>(x), batch, H, W, C, ln_w, ln_b, eps, patch,
-      reinterpret_cast<__nv_bfloat16*>(out));
-  VDK_CUDA_OK(cudaGetLastError());
-  return VDK_OK;
+  return launch_ln_patchify(reinterpret_cast<const __nv_bfloat16*>(x), batch, H, W, C, ln_w, ln_b, eps, patch,
+                            reinterpret_cast<__nv_bfloat16*>(out), reinterpret_cast<cudaStream_t>(stream));
 }
 
 extern "C" size_t vdk_convnext_workspace_bytes(const vdk_convnext_net* net, int batch) {
@@ -434,10 +468,8 @@ extern "C" int vdk_convnext_forward(const vdk_convnext_net* net, const float* im
       // ---- downsample: LayerNorm2d then conv2x2/s2 as a GEMM over (kh, kw, c) patch rows ----
       const vdk_convnext_down* d = &net->down[st];
       const int Cin = C;
-      const int64_t npix = static_cast<int64_t>(batch) * H * W;
-      ln_patchify_kernel<<<static_cast<unsigned>((npix * 32 + 255) / 256), 256, 0, s>>>(xbuf, batch, H, W, Cin, d->ln_w,
-                                                                                         d->ln_b, 1e-6f, 2, ybuf);
-      VDK_CUDA_OK(cudaGetLastError());
+      rc = launch_ln_patchify(xbuf, batch, H, W, Cin, d->ln_w, d->ln_b, 1e-6f, 2, ybuf, s);
+      if (rc != VDK_OK) return rc;
       H /= 2; W /= 2; C = net->dims[st];
       M = batch * H * W;
       rc = gemm(ybuf, d->conv_w, xbuf, M, C, 4 * Cin, VDK_EPI_NONE, d->conv_b, nullptr, nullptr, nullptr, VDK_DTYPE_BF16, 1);
@@ -455,10 +487,8 @@ extern "C" int vdk_convnext_forward(const vdk_convnext_net* net, const float* im
   }
   // ---- head LayerNorm2d (applied by timm even with global_pool='') ----
   {
-    const int64_t npix = static_cast<int64_t>(batch) * H * W;
-    ln_patchify_kernel<<<static_cast<unsigned>((npix * 32 + 255) / 256), 256, 0, s>>>(xbuf, batch, H, W, C, net->head_ln_w,
-                                                                                       net->head_ln_b, 1e-6f, 1, ybuf);
-    VDK_CUDA_OK(cudaGetLastError());
+    rc = launch_ln_patchify(xbuf, batch, H, W, C, net->head_ln_w, net->head_ln_b, 1e-6f, 1, ybuf, s);
+    if (rc != VDK_OK) return rc;
   }
   // ---- neck: BN2d -> Flatten -> Linear -> BN1d, all folded into one skinny GEMM (eval statistics) ----
   {

@@ -43,11 +43,9 @@ struct GemmCfg {
   static constexpr int kTmemCols = 2 * BN;
   // stages + barriers (full, empty: kStages each; tmem_full, tmem_empty: 2 each) + tmem ptr + 1 KB align slack
   static constexpr int kStoreStageBytes = kBM * 64 * 2;  // one 128 x 64 16-bit sub-tile per epilogue half
-  static constexpr int kSmemBytes = kStages * kStageBytes + 2 * kStoreStageBytes + (2 * kStages + 4) * 8 + 16 + 1024;
+  static constexpr int kSmemBytes = kStages * kStageBytes + 2 * kStoreStageBytes + (2 * kStages + 6) * 8 + 16 + 1024;
 };
 
-// GELU(x) = 0.5 x (1 + erf(x / sqrt 2)), erf by Abramowitz-Stegun 7.1.26 (|abs err| < 1.5e-7) on the SFU
-// (rcp.approx / ex2.approx): branch-free, ~16 instructions per element instead of erff()'s two-branch polynomial.
 __device__ __forceinline__ float rcp_approx(float x) {
   float y;
   asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
@@ -58,18 +56,16 @@ __device__ __forceinline__ float ex2_approx(float x) {
   asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
   return y;
 }
+// erf-GELU(x) = x * Phi(x) evaluated as x * sigmoid(2u), u = x (a + b x^2 + c x^4) a least-squares fit of
+// atanh(erf(x / sqrt 2)) (|x| clamped to 8 where the sigmoid is saturated): max |deviation| from the exact erf form
+// is 3.0e-5, below one bf16 ulp of the result for |y| > 0.008, and the multiplicative form keeps relative accuracy in
+// the negative tail.  10 instructions (2 on the SFU) instead of erff()'s ~25, which matters because the fc1 epilogue
+// is ALU-bound: 4C x tokens GELUs per block against 4096 tensor-core cycles per 128 x 256 tile.
 __device__ __forceinline__ float gelu_erf(float x) {
-  const float z = fabsf(x) * 0.70710678118654752440f;
-  const float t = rcp_approx(fmaf(0.3275911f, z, 1.0f));
-  float p = fmaf(1.061405429f, t, -1.453152027f);
-  p = fmaf(p, t, 1.421413741f);
-  p = fmaf(p, t, -0.284496736f);
-  p = fmaf(p, t, 0.254829592f);
-  p *= t;
-  const float e = ex2_approx(-1.4426950408889634f * z * z);  // exp(-z^2)
-  const float erf_abs = fmaf(-p, e, 1.0f);
-  const float erf_v = copysignf(erf_abs, x);
-  return 0.5f * x * (1.0f + erf_v);
+  const float xc = fminf(fmaxf(x, -8.0f), 8.0f);
+  const float t = xc * xc;
+  const float k = xc * fmaf(t, fmaf(t, 0.0010350829f, -0.1069047f), -2.3009787f);  // -2 u(x) log2(e)
+  return x * rcp_approx(1.0f + ex2_approx(k));
 }
 
 __device__ __forceinline__ uint32_t pack2(float a, float b, int out_dtype) {
@@ -93,7 +89,7 @@ __device__ __forceinline__ float2 unpack2(uint32_t u, int dtype) {
 
 // Per-chunk epilogue arithmetic on this thread's 32 consecutive columns [col0, col0 + ncols) of row `row`.
 __device__ __forceinline__ void epi_math(const GemmParams& p, float (&v)[32], int row, int col0, int ncols, float ln_mean,
-                                         float ln_rstd) {
+                                         float ln_rstd, bool residual_from_smem = false) {
   if (p.bias != nullptr) {
 #pragma unroll
     for (int j = 0; j < 32; j += 4) {
@@ -126,7 +122,7 @@ __device__ __forceinline__ void epi_math(const GemmParams& p, float (&v)[32], in
         v[j] *= g.x; v[j + 1] *= g.y; v[j + 2] *= g.z; v[j + 3] *= g.w;
       }
     }
-    if (row < p.M) {
+    if (row < p.M && !residual_from_smem) {
       if (p.out_dtype == VDK_DTYPE_FP32) {
         const float* res = reinterpret_cast<const float*>(p.residual) + static_cast<size_t>(row) * p.ldr + col0;
 #pragma unroll
@@ -156,7 +152,8 @@ __device__ __forceinline__ void epi_math(const GemmParams& p, float (&v)[32], in
 template <int BN, bool kBf16>
 __global__ void __launch_bounds__(kGemmThreads, 1)
 gemm_tn_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b,
-               const __grid_constant__ CUtensorMap map_d, const GemmParams p) {
+               const __grid_constant__ CUtensorMap map_d, const __grid_constant__ CUtensorMap map_r,
+               const GemmParams p) {
   using Cfg = GemmCfg<BN>;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
@@ -165,7 +162,8 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
   uint64_t* empty_bar = full_bar + Cfg::kStages;
   uint64_t* tmem_full = empty_bar + Cfg::kStages;
   uint64_t* tmem_empty = tmem_full + 2;
-  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(tmem_empty + 2);
+  uint64_t* res_bar = tmem_empty + 2;  // residual sub-tile landed in the staging buffer (one per epilogue half)
+  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(res_bar + 2);
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -181,6 +179,7 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
     prefetch_tensormap(&map_a);
     prefetch_tensormap(&map_b);
     if (p.tma_store) prefetch_tensormap(&map_d);
+    if (p.tma_store && p.epilogue == VDK_EPI_SCALE_RESIDUAL) prefetch_tensormap(&map_r);
     for (int i = 0; i < Cfg::kStages; ++i) {
       mbar_init(&full_bar[i], 1);
       mbar_init(&empty_bar[i], 1);
@@ -188,6 +187,7 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
     for (int i = 0; i < 2; ++i) {
       mbar_init(&tmem_full[i], 1);
       mbar_init(&tmem_empty[i], 256);
+      mbar_init(&res_bar[i], 1);
     }
     fence_mbar_init();
   }
@@ -264,6 +264,7 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
     const int lane_base = (warp & 3) * 32;  // TMEM lanes this warp may touch
     const int half = (warp - 2) >> 2;       // which of the two warps sharing this lane quarter
     bool stores_issued = false;
+    uint32_t res_phase = 0;
     int it = 0;
     for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
       const int acc = it & 1;
@@ -321,6 +322,16 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
           const int colS = n0 + sc * 64;
           if (colS >= p.N) break;
           uint32_t packed[32];
+          const bool res_smem = p.epilogue == VDK_EPI_SCALE_RESIDUAL;
+          if (res_smem) {
+            // the residual sub-tile is fetched by TMA into the staging buffer (full-line reads instead of 32
+            // row-strided 16-byte loads per warp), updated in place, and stored back from the same buffer
+            if (leader) {
+              if (stores_issued) tma_store_wait_read<0>();
+              mbar_arrive_expect_tx(&res_bar[half], Cfg::kStoreStageBytes);
+              tma_load_2d(stg, &map_r, &res_bar[half], colS, m0, kEvictFirst);
+            }
+          }
 #pragma unroll
           for (int hh = 0; hh < 2; ++hh) {
             uint32_t r[32];
@@ -331,11 +342,25 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
             for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]);
             const int col0 = colS + hh * 32;
             const int ncols = max(0, min(32, p.N - col0));
-            if (ncols > 0) epi_math(p, v, row, col0, ncols, ln_mean, ln_rstd);
+            if (ncols > 0) epi_math(p, v, row, col0, ncols, ln_mean, ln_rstd, res_smem);
+            if (res_smem) {
+              if (hh == 0) {
+                mbar_wait(&res_bar[half], res_phase);
+                res_phase ^= 1;
+              }
+#pragma unroll
+              for (int q = 0; q < 4; ++q) {
+                const uint4 t = *reinterpret_cast<const uint4*>(stg + rit * 128 + (((hh * 4 + q) ^ (rit & 7)) << 4));
+                const float2 a0 = unpack2(t.x, p.out_dtype), a1 = unpack2(t.y, p.out_dtype);
+                const float2 a2 = unpack2(t.z, p.out_dtype), a3 = unpack2(t.w, p.out_dtype);
+                v[q * 8] += a0.x; v[q * 8 + 1] += a0.y; v[q * 8 + 2] += a1.x; v[q * 8 + 3] += a1.y;
+                v[q * 8 + 4] += a2.x; v[q * 8 + 5] += a2.y; v[q * 8 + 6] += a3.x; v[q * 8 + 7] += a3.y;
+              }
+            }
 #pragma unroll
             for (int j = 0; j < 32; j += 2) packed[hh * 16 + (j >> 1)] = pack2(v[j], v[j + 1], p.out_dtype);
           }
-          if (stores_issued) {  // the previous sub-tile must have been read out of the staging buffer
+          if (stores_issued && !res_smem) {  // the previous sub-tile must have been read out of the staging buffer
             if (leader) tma_store_wait_read<0>();
             named_bar_sync(1 + half, 128);
           }
@@ -408,8 +433,8 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
 }
 
 template <int BN, bool kBf16>
-static int launch_gemm(const CUtensorMap& ma, const CUtensorMap& mb, const CUtensorMap& md, const GemmParams& p,
-                       cudaStream_t stream) {
+static int launch_gemm(const CUtensorMap& ma, const CUtensorMap& mb, const CUtensorMap& md, const CUtensorMap& mr,
+                       const GemmParams& p, cudaStream_t stream) {
   using Cfg = GemmCfg<BN>;
   auto kern = gemm_tn_kernel<BN, kBf16>;
   static bool attr_set = false;  // per (BN, dtype) instantiation
@@ -419,7 +444,7 @@ static int launch_gemm(const CUtensorMap& ma, const CUtensorMap& mb, const CUten
   }
   const int num_tiles = ((p.M + kBM - 1) / kBM) * ((p.N + BN - 1) / BN) * p.split_k;
   const int grid = num_tiles < sm_count() ? num_tiles : sm_count();
-  kern<<<grid, kGemmThreads, Cfg::kSmemBytes, stream>>>(ma, mb, md, p);
+  kern<<<grid, kGemmThreads, Cfg::kSmemBytes, stream>>>(ma, mb, md, mr, p);
   VDK_CUDA_OK(cudaGetLastError());
   return VDK_OK;
 }
@@ -479,11 +504,16 @@ int gemm_run(const vdk_gemm_desc& g, cudaStream_t s) {
     rc = make_tma_2d_16bit(&md, g.D, (uint64_t)g.M, (uint64_t)g.N, (uint64_t)g.ldd, kBM, 64);
     if (rc != VDK_OK) return rc;
   }
+  CUtensorMap mr = md;
+  if (tma_store && g.epilogue == VDK_EPI_SCALE_RESIDUAL) {
+    rc = make_tma_2d_16bit(&mr, g.residual, (uint64_t)g.M, (uint64_t)g.N, (uint64_t)g.ldr, kBM, 64);
+    if (rc != VDK_OK) return rc;
+  }
   GemmParams p{g.M, g.N, g.K, g.D, g.ldd, g.bias, g.gamma, g.beta, g.residual, g.ldr, g.out_dtype, g.epilogue,
                g.ln_eps, split, tma_store};
   const bool bf = g.in_dtype == VDK_DTYPE_BF16;
-  if (wide) return bf ? launch_gemm<256, true>(ma, mb, md, p, s) : launch_gemm<256, false>(ma, mb, md, p, s);
-  return bf ? launch_gemm<128, true>(ma, mb, md, p, s) : launch_gemm<128, false>(ma, mb, md, p, s);
+  if (wide) return bf ? launch_gemm<256, true>(ma, mb, md, mr, p, s) : launch_gemm<256, false>(ma, mb, md, mr, p, s);
+  return bf ? launch_gemm<128, true>(ma, mb, md, mr, p, s) : launch_gemm<128, false>(ma, mb, md, mr, p, s);
 }
 
 }  // namespace vdk

@@ -346,6 +346,7 @@ struct SelectParams {
   float* tau;
   const float* eps;       // per-query bound on |approx - canonical|
   int32_t* status;        // {overflow_rows, max_candidates, max_survivors, reserved}
+  int32_t* row_flag;      // [n_query] set to 1 for rows whose lists overflowed (results incomplete)
 };
 
 __global__ void __launch_bounds__(kSelThreads) select_kernel(const SelectParams p) {
@@ -472,7 +473,9 @@ __global__ void __launch_bounds__(kSelThreads) select_kernel(const SelectParams 
     const unsigned m = s_m;
     p.carry_cnt[row] = min(m, static_cast<unsigned>(p.carry_cap));
     p.tau[row] = tau_use;
-    if (s_over || m > static_cast<unsigned>(p.carry_cap)) atomicAdd(&p.status[0], 1);
+    if (s_over || m > static_cast<unsigned>(p.carry_cap)) {
+      if (atomicExch(&p.row_flag[row], 1) == 0) atomicAdd(&p.status[0], 1);  // count each row once
+    }
     atomicMax(&p.status[1], static_cast<int>(min(n, 0x7fffffffu)));
     atomicMax(&p.status[2], static_cast<int>(min(m, 0x7fffffffu)));
   }
@@ -646,12 +649,13 @@ struct TopkWorkspace {
   unsigned* carry_cnt;
   float* tau;
   float* eps;
+  int32_t* row_flag;
 };
 static size_t align256(size_t v) { return (v + 255) & ~static_cast<size_t>(255); }
 static size_t workspace_bytes(int64_t nq, int seg_stride, int carry_cap) {
   const size_t n = static_cast<size_t>(nq);
   return align256(n * seg_stride * sizeof(uint2)) + 2 * align256(n * carry_cap * sizeof(uint2)) +
-         align256(n * kMaxSeg * sizeof(unsigned)) + 3 * align256(n * sizeof(float)) + 256;
+         align256(n * kMaxSeg * sizeof(unsigned)) + 4 * align256(n * sizeof(float)) + 256;
 }
 static TopkWorkspace carve_workspace(void* workspace, int64_t nq, int seg_stride, int carry_cap) {
   const size_t n = static_cast<size_t>(nq);
@@ -670,6 +674,8 @@ static TopkWorkspace carve_workspace(void* workspace, int64_t nq, int seg_stride
   w.tau = reinterpret_cast<float*>(ws);
   ws += align256(n * sizeof(float));
   w.eps = reinterpret_cast<float*>(ws);
+  ws += align256(n * sizeof(float));
+  w.row_flag = reinterpret_cast<int32_t*>(ws);
   return w;
 }
 
@@ -777,6 +783,7 @@ extern "C" int vdk_topk_plan_default(vdk_topk_plan* plan, int64_t n_query, int64
   plan->k = k;
   plan->cand_capacity = pow2_ceil(std::max(16384, 16 * k));  // per-range admitted candidates per query
   plan->carry_capacity = pow2_ceil(std::max(2048, 4 * k));  // survivors carried between ranges
+  plan->dense_mask = 1;                                     // only the first range is scored densely
   // first range is scored densely (no threshold yet); each later range is 8x the prefix before it, so the
   // expected number of admitted candidates per range stays near 7k.
   int64_t end = std::min<int64_t>(n_gallery, std::max(4096, 4 * k));
@@ -812,6 +819,7 @@ static int check_plan(const vdk_topk_plan* plan) {
   VDK_REQUIRE(plan->n_stages >= 1 && plan->n_stages <= 8 && plan->stage_end[plan->n_stages - 1] == plan->n_gallery,
               "stage table must end at n_gallery");
   VDK_REQUIRE(plan->n_query < (1ll << 31) - kQM && plan->n_gallery < (1ll << 31), "sizes exceed 32-bit tiling");
+  VDK_REQUIRE(plan->dense_mask >= 0 && plan->dense_mask < 256, "bad dense_mask");
   return VDK_OK;
 }
 
@@ -833,6 +841,7 @@ extern "C" int vdk_ip_topk(const vdk_topk_plan* plan, const float* q32, const vo
   if (ng > 0) VDK_REQUIRE(g32 && gh && g_norm_max && g_err_max, "vdk_ip_topk: null gallery operand");
 
   const TopkWorkspace w = carve_workspace(workspace, nq, seg_stride, carry_cap);
+  VDK_CUDA_OK(cudaMemsetAsync(w.row_flag, 0, static_cast<size_t>(nq) * sizeof(int32_t), s));
   eps_kernel<<<(static_cast<int>(nq) + 255) / 256, 256, 0, s>>>(q_norm, q_err, ng > 0 ? g_norm_max : nullptr,
                                                                  ng > 0 ? g_err_max : nullptr, static_cast<int>(nq),
                                                                  w.eps, w.tau, w.carry_cnt);
@@ -850,7 +859,7 @@ extern "C" int vdk_ip_topk(const vdk_topk_plan* plan, const float* q32, const vo
       const int64_t hi = plan->stage_end[st];
       VDK_REQUIRE(hi > lo || (hi == lo && st > 0), "vdk_ip_topk: stage table must be increasing");
       if (hi == lo) continue;
-      const bool dense = (st == 0);
+      const bool dense = (st == 0) || ((plan->dense_mask >> st) & 1);
       RangeLaunch info{};
       rc = launch_score_range(mq, mg, static_cast<int>(nq), dim, lo, hi, dense, w, seg_stride, &info, s);
       if (rc != VDK_OK) return rc;
@@ -870,6 +879,7 @@ extern "C" int vdk_ip_topk(const vdk_topk_plan* plan, const float* q32, const vo
       sp.tau = w.tau;
       sp.eps = w.eps;
       sp.status = status;
+      sp.row_flag = w.row_flag;
       select_kernel<<<static_cast<unsigned>(nq), kSelThreads, 0, s>>>(sp);
       VDK_CUDA_OK(cudaGetLastError());
       cur ^= 1;
@@ -931,4 +941,14 @@ extern "C" int vdk_score_range(const vdk_topk_plan* plan, const void* qh, const 
   if (rc != VDK_OK) return rc;
   return launch_score_range(mq, mg, static_cast<int>(plan->n_query), plan->dim, lo, hi, dense != 0, w,
                             plan->cand_capacity, nullptr, reinterpret_cast<cudaStream_t>(stream));
+}
+
+extern "C" int vdk_topk_row_flags(const vdk_topk_plan* plan, const void* workspace, size_t workspace_bytes,
+                                  const int32_t** row_flags) {
+  int rc = check_plan(plan);
+  if (rc != VDK_OK) return rc;
+  VDK_REQUIRE(workspace && row_flags && workspace_bytes >= vdk_topk_workspace_bytes(plan), "vdk_topk_row_flags: bad arguments");
+  const TopkWorkspace w = carve_workspace(const_cast<void*>(workspace), plan->n_query, plan->cand_capacity, plan->carry_capacity);
+  *row_flags = w.row_flag;
+  return VDK_OK;
 }

@@ -81,6 +81,7 @@ class FlatIPIndex:
         self._ws = None
         self.last_status = None
         self.stage_ends = None  # optional override of the gallery range schedule (tuning / tests)
+        self.wide_path_rows = 0
 
     # ---- faiss-shaped surface -------------------------------------------------------------------
     @property
@@ -104,12 +105,53 @@ class FlatIPIndex:
 
     def search(self, x, k: int):
         """numpy float32 [n, d] -> (scores float32 [n, k], ids int64 [n, k]); the faiss call of evaluation.py:193."""
-        s, i = self.search_device(self._to_device(x), k)
+        s, i = self.search_device(self._to_device(x), k, resolve_overflow=True)
         return s.cpu().numpy(), i.cpu().numpy()
 
     # ---- device-resident path ----------------------------------------------------------------------
-    def search_device(self, q: torch.Tensor, k: int):
+    def _run_topk(self, qp: "PreparedRows", rows, g_lo: int, g_hi: int, k: int, dense_all: bool):
+        """One vdk_ip_topk call: queries `rows` of qp (None = all) against gallery rows [g_lo, g_hi)."""
         lib = _lib.load()
+        g = self._rows
+        q32, qh, qn, qe = qp.x32, qp.xh, qp.norm, qp.err
+        if rows is not None:
+            q32, qh, qn, qe = q32[rows].contiguous(), qh[rows].contiguous(), qn[rows].contiguous(), qe[rows].contiguous()
+        nq, ng = q32.shape[0], g_hi - g_lo
+        out_s = torch.empty((nq, k), dtype=torch.float32, device=self.device)
+        out_i = torch.empty((nq, k), dtype=torch.int64, device=self.device)
+        status = torch.zeros((4,), dtype=torch.int32, device=self.device)
+        plan = _lib.TopkPlan()
+        _lib.check(lib.vdk_topk_plan_default(C.byref(plan), nq, ng, self.d, k), "vdk_topk_plan_default")
+        ends = None
+        if dense_all:  # wide path: every range scored densely -> no admission threshold, no segment can overflow
+            cap = plan.cand_capacity
+            ends = list(range(cap, ng, cap))
+            plan.dense_mask = 0xFF
+        elif self.stage_ends is not None:
+            ends = [int(e) for e in self.stage_ends if int(e) < ng]
+        if ends is not None and ng > 0:
+            ends = ends + [ng]
+            assert len(ends) <= 8
+            plan.n_stages = len(ends)
+            for j in range(8):
+                plan.stage_end[j] = ends[min(j, len(ends) - 1)]
+        need = lib.vdk_topk_workspace_bytes(C.byref(plan))
+        if self._ws is None or self._ws.numel() < need:
+            self._ws = torch.empty((need,), dtype=torch.uint8, device=self.device)
+        gn, ge = self._gmax if self._gmax is not None else (None, None)
+        esz32, esz16 = 4 * self.d, 2 * self.d
+        with torch.cuda.device(self.device):
+            rc = lib.vdk_ip_topk(C.byref(plan), q32.data_ptr(), qh.data_ptr(), qn.data_ptr(), qe.data_ptr(),
+                                 (g.x32.data_ptr() + g_lo * esz32) if g else 0, (g.xh.data_ptr() + g_lo * esz16) if g else 0,
+                                 _lib.ptr(gn), _lib.ptr(ge), self.id_offset + g_lo, out_s.data_ptr(), out_i.data_ptr(),
+                                 status.data_ptr(), self._ws.data_ptr(), self._ws.numel(), _lib.stream_ptr())
+        _lib.check(rc, "vdk_ip_topk")
+        return out_s, out_i, status, plan
+
+    def search_device(self, q: torch.Tensor, k: int, resolve_overflow: bool = False):
+        """Device tensors in/out.  With resolve_overflow=True the call synchronises, and queries whose candidate
+        lists overflowed (massive near-ties, adversarially ordered galleries) are recomputed on the wide path."""
+        _lib.load()
         _lib.require_device()
         self._finalize()
         k = int(k)
@@ -119,42 +161,43 @@ class FlatIPIndex:
         if q.shape[1] != self.d:
             raise ValueError(f"index dimension is {self.d}, got queries of width {q.shape[1]}")
         nq = q.shape[0]
-        out_s = torch.empty((nq, k), dtype=torch.float32, device=self.device)
-        out_i = torch.empty((nq, k), dtype=torch.int64, device=self.device)
-        status = torch.zeros((4,), dtype=torch.int32, device=self.device)
         if nq == 0:
-            return out_s, out_i
+            return (torch.empty((0, k), dtype=torch.float32, device=self.device),
+                    torch.empty((0, k), dtype=torch.int64, device=self.device))
         qp = PreparedRows(q, self.normalize)
         ng = self._rows.n if self._rows is not None else 0
-        plan = _lib.TopkPlan()
-        _lib.check(lib.vdk_topk_plan_default(C.byref(plan), nq, ng, self.d, k), "vdk_topk_plan_default")
-        if self.stage_ends is not None and ng > 0:
-            ends = [min(int(e), ng) for e in self.stage_ends if int(e) < ng] + [ng]
-            plan.n_stages = len(ends)
-            for j in range(8):
-                plan.stage_end[j] = ends[min(j, len(ends) - 1)]
-        need = lib.vdk_topk_workspace_bytes(C.byref(plan))
-        if self._ws is None or self._ws.numel() < need:
-            self._ws = torch.empty((need,), dtype=torch.uint8, device=self.device)
-        g = self._rows
-        gn, ge = self._gmax if self._gmax is not None else (None, None)
-        with torch.cuda.device(self.device):
-            rc = lib.vdk_ip_topk(C.byref(plan), _lib.ptr(qp.x32), _lib.ptr(qp.xh), _lib.ptr(qp.norm), _lib.ptr(qp.err),
-                                 _lib.ptr(g.x32) if g else 0, _lib.ptr(g.xh) if g else 0, _lib.ptr(gn), _lib.ptr(ge),
-                                 self.id_offset, out_s.data_ptr(), out_i.data_ptr(), status.data_ptr(),
-                                 self._ws.data_ptr(), self._ws.numel(), _lib.stream_ptr())
-        _lib.check(rc, "vdk_ip_topk")
+        out_s, out_i, status, plan = self._run_topk(qp, None, 0, ng, k, dense_all=False)
         self.last_status = status
+        if resolve_overflow and int(status[0].item()) > 0:
+            self._wide_path(qp, out_s, out_i, plan, k)
         return out_s, out_i
 
-    def check_status(self) -> dict:
-        """Synchronises and raises if any query overflowed its candidate list (results would be incomplete)."""
-        st = self.last_status.cpu().tolist()
-        info = {"overflow_rows": st[0], "max_candidates": st[1], "max_survivors": st[2]}
-        if st[0] != 0:
-            raise RuntimeError(f"vdk_ip_topk: {st[0]} query rows overflowed their candidate lists {info}; "
-                               "the gallery has more near-ties than the plan's capacity")
-        return info
+    def _wide_path(self, qp: "PreparedRows", out_s: torch.Tensor, out_i: torch.Tensor, plan, k: int) -> None:
+        """Recomputes the flagged queries with all-dense plans over gallery slices, merged like shards."""
+        lib = _lib.load()
+        flags_ptr = C.c_void_p()
+        _lib.check(lib.vdk_topk_row_flags(C.byref(plan), self._ws.data_ptr(), self._ws.numel(), C.byref(flags_ptr)),
+                   "vdk_topk_row_flags")
+        off = flags_ptr.value - self._ws.data_ptr()
+        flags = self._ws[off:off + 4 * plan.n_query].view(torch.int32)
+        rows = torch.nonzero(flags).flatten()
+        ng = self._rows.n
+        slice_rows = 8 * plan.cand_capacity
+        lists_s, lists_i = [], []
+        for a in range(0, ng, slice_rows):
+            s_, i_, st, _ = self._run_topk(qp, rows, a, min(ng, a + slice_rows), k, dense_all=True)
+            if int(st[0].item()) > 0:
+                raise RuntimeError("vdk_ip_topk: more than carry_capacity near-tied candidates for a query even on the "
+                                   "wide path (massively duplicated gallery rows)")
+            lists_s.append(s_)
+            lists_i.append(i_)
+        while len(lists_s) > 1:  # merge up to 32 lists at a time
+            ms, mi = merge_topk(torch.stack(lists_s[:32]), torch.stack(lists_i[:32]), k)
+            lists_s, lists_i = [ms] + lists_s[32:], [mi] + lists_i[32:]
+        out_s[rows] = lists_s[0]
+        out_i[rows] = lists_i[0]
+        self.last_status = torch.zeros_like(self.last_status)
+        self.wide_path_rows = int(rows.numel())
 
     # ---- internals -----------------------------------------------------------------------------
     def _to_device(self, x) -> torch.Tensor:
