@@ -61,8 +61,18 @@ typedef struct vdk_gemm_desc {
   float ln_eps;
   int split_k; /* > 1: K is split over split_k CTAs per tile whose fp32 partials are atomically added into a
                   ZEROED fp32 D (skinny-M neck GEMM, timm_wrapper.py:36); epilogue NONE, no bias */
+  long long split_stride; /* split_k > 1 only.  0: partials are atomically added into a zeroed D.  > 0 (elements):
+                             split s stores its partial into the slab D + s*split_stride; the effective number of
+                             splits is min(split_k, ceil(K/64)) rounded so that every split is non-empty — query it
+                             with vdk_gemm_effective_splits.  Deterministic. */
+  int trans_a; /* 1: A is stored [K,M] row-major (pitch lda >= M): the contraction index is the slow dimension */
+  int trans_b; /* 1: B is stored [K,N] row-major (pitch ldb >= N).  Backward GEMMs use these: dgrad
+                  dX = dY . W (B = W stored [N_out,K_in] = [K,N] of this contraction) and wgrad dW = dY^T . X
+                  (both operands stored with the token index slow) need no transposed copies. */
 } vdk_gemm_desc;
 int vdk_gemm(const vdk_gemm_desc* desc, void* stream);
+/* Number of K splits vdk_gemm will actually use for (K, split_k). */
+int vdk_gemm_effective_splits(int K, int split_k);
 
 /* Positional convenience form of vdk_gemm (split_k = 1, no LayerNorm). */
 int vdk_gemm_tn(const void* A, const void* B, void* D, int M, int N, int K, int lda, int ldb, int ldd,

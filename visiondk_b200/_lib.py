@@ -46,7 +46,7 @@ class GemmDesc(C.Structure):
         ("M", C.c_int), ("N", C.c_int), ("K", C.c_int), ("lda", C.c_int), ("ldb", C.c_int), ("ldd", C.c_int),
         ("in_dtype", C.c_int), ("out_dtype", C.c_int), ("epilogue", C.c_int),
         ("bias", C.c_void_p), ("gamma", C.c_void_p), ("beta", C.c_void_p), ("residual", C.c_void_p),
-        ("ldr", C.c_int), ("ln_eps", C.c_float), ("split_k", C.c_int),
+        ("ldr", C.c_int), ("ln_eps", C.c_float), ("split_k", C.c_int), ("split_stride", C.c_longlong), ("trans_a", C.c_int), ("trans_b", C.c_int),
     ]
 
 
@@ -56,6 +56,7 @@ SIGNATURES = {
     "vdk_last_error_string": (C.c_char_p, []),
     "vdk_device_check": (_i, []),
     "vdk_gemm": (_i, [_p, _p]),
+    "vdk_gemm_effective_splits": (_i, [_i, _i]),
     "vdk_dwconv7_ln": (_i, [_p, _i, _i, _i, _i, _p, _p, _p, _p, C.c_float, _p, _p]),
     "vdk_layernorm_patchify": (_i, [_p, _i, _i, _i, _i, _p, _p, C.c_float, _i, _p, _p]),
     "vdk_convnext_workspace_bytes": (_sz, [_p, _i]),

@@ -56,15 +56,20 @@ __global__ void __launch_bounds__(256) stem_patchify_kernel(const float* __restr
 // owns one output row of the tile at a time; the 49 taps of a thread's 4 channels are read one filter row at a
 // time (L1-resident), accumulators stay in registers, and LayerNorm over C is a reduction inside the group.
 // FMA-bound: 49 FMAs per output against 2 + 2 bytes of HBM traffic.
-template <int TW>
+// MODE 0: y = LayerNorm_C(conv + bias) (forward; optionally saves 1/sigma per pixel for the backward)
+// MODE 1: y = conv (+ addend)           (backward-data: the same correlation with the taps reversed, plus the
+//                                        gradient arriving through the residual connection)
+template <int TW, int MODE>
 __global__ void __launch_bounds__(512)
 dwconv7_ln_kernel(const __grid_constant__ CUtensorMap map_x, int B, int H, int W, int C, int TH, int box_c,
                   int tpg /*threads per group, whole warps*/,
                   const float* __restrict__ w49,  // [49][C]
                   const float* __restrict__ bias, const float* __restrict__ ln_w, const float* __restrict__ ln_b,
-                  float eps, __nv_bfloat16* __restrict__ y) {
+                  float eps, __nv_bfloat16* __restrict__ y, float* __restrict__ rstd_out,
+                  const __nv_bfloat16* __restrict__ addend) {
   extern __shared__ uint8_t dw_smem_raw[];
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(dw_smem_raw) + 127) & ~uintptr_t(127));
+  // aligned without a pointer->integer->pointer round trip, so the tile reads below stay LDS (not generic LD)
+  uint8_t* smem = dw_smem_raw + ((128u - (smem_u32(dw_smem_raw) & 127u)) & 127u);
   const int box_h = TH + 6, box_w = TW + 6;
   const int n_chunks = C / box_c;
   const int chunk_bytes = box_h * box_w * box_c * 2;
@@ -97,7 +102,7 @@ dwconv7_ln_kernel(const __grid_constant__ CUtensorMap map_x, int B, int H, int W
   }
   // weights / affine parameters of this thread's channels while the tile is in flight
   float4 bc = make_float4(0.f, 0.f, 0.f, 0.f), g4 = bc, b4 = bc;
-  if (has_c) {
+  if (has_c && MODE == 0) {
     bc = __ldg(reinterpret_cast<const float4*>(bias + c0));
     g4 = __ldg(reinterpret_cast<const float4*>(ln_w + c0));
     b4 = __ldg(reinterpret_cast<const float4*>(ln_b + c0));
@@ -141,6 +146,29 @@ dwconv7_ln_kernel(const __grid_constant__ CUtensorMap map_x, int B, int H, int W
         }
       }
     }
+    if (MODE == 1) {
+      if (active) {
+#pragma unroll
+        for (int p = 0; p < TW; ++p) {
+          const int ox = ox0 + p;
+          if (ox >= W) continue;
+          const int64_t off = ((static_cast<int64_t>(b) * H + oy0 + oyl) * W + ox) * C + c0;
+          float o0 = acc[p][0], o1 = acc[p][1], o2 = acc[p][2], o3 = acc[p][3];
+          if (addend) {
+            const uint2 t = *reinterpret_cast<const uint2*>(addend + off);
+            const float2 a = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&t.x));
+            const float2 c = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&t.y));
+            o0 += a.x; o1 += a.y; o2 += c.x; o3 += c.y;
+          }
+          __nv_bfloat162 lo = __floats2bfloat162_rn(o0, o1), hi = __floats2bfloat162_rn(o2, o3);
+          uint2 t;
+          t.x = *reinterpret_cast<uint32_t*>(&lo);
+          t.y = *reinterpret_cast<uint32_t*>(&hi);
+          *reinterpret_cast<uint2*>(y + off) = t;
+        }
+      }
+      continue;
+    }
     // LayerNorm over C for the TW pixels of this row: mean, then centred second moment, reduced in the group
     float mean[TW], rstd[TW];
 #pragma unroll
@@ -165,10 +193,11 @@ dwconv7_ln_kernel(const __grid_constant__ CUtensorMap map_x, int B, int H, int W
         }
         __syncthreads();
 #pragma unroll
-        for (int p = 0; p < TW; ++p) {
-          float t = 0.f;
-          for (int w = 0; w < nwig; ++w) t += red[(grp * TW + p) * 16 + w];
-          sred[p] = t;
+        for (int p = 0; p < TW; ++p) sred[p] = 0.f;
+#pragma unroll 1
+        for (int w = 0; w < nwig; ++w) {  // not unrolled: a 16-way predicated unroll costs more than the conv itself
+#pragma unroll
+          for (int p = 0; p < TW; ++p) sred[p] += red[(grp * TW + p) * 16 + w];
         }
         __syncthreads();
       }
@@ -183,7 +212,9 @@ dwconv7_ln_kernel(const __grid_constant__ CUtensorMap map_x, int B, int H, int W
       for (int p = 0; p < TW; ++p) {
         const int ox = ox0 + p;
         if (ox >= W) continue;
-        __nv_bfloat16* dst = y + ((static_cast<int64_t>(b) * H + oy0 + oyl) * W + ox) * C + c0;
+        const int64_t pix = (static_cast<int64_t>(b) * H + oy0 + oyl) * W + ox;
+        if (rstd_out != nullptr && tig == 0) rstd_out[pix] = rstd[p];
+        __nv_bfloat16* dst = y + pix * C + c0;
         __nv_bfloat162 lo = __floats2bfloat162_rn((acc[p][0] - mean[p]) * rstd[p] * g4.x + b4.x,
                                                   (acc[p][1] - mean[p]) * rstd[p] * g4.y + b4.y);
         __nv_bfloat162 hi = __floats2bfloat162_rn((acc[p][2] - mean[p]) * rstd[p] * g4.z + b4.z,
@@ -303,24 +334,25 @@ static int launch_ln_patchify(const __nv_bfloat16* x, int B, int H, int W, int C
 // neck finalize: split-K partial sums + folded bias -> embedding rows (optionally L2-normalised)
 // ------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256)
-neck_finalize_kernel(const float* __restrict__ acc, int B, int F, const float* __restrict__ bias, int l2norm,
-                     float* __restrict__ out) {
+neck_finalize_kernel(const float* __restrict__ acc, int n_slabs, size_t slab_stride, int B, int F,
+                     const float* __restrict__ bias, int l2norm, float* __restrict__ out) {
   const int lane = threadIdx.x & 31;
   const int row = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   if (row >= B) return;
   double ss = 0.0;
   // the canonical F.normalize of retrieval.cu: fixed-order fp64 sum of squares (lane-strided, xor butterfly)
+  // split-K slabs are added in slab order: the embedding is bitwise reproducible run to run
   for (int i = lane; i < F; i += 32) {
-    const float v = acc[static_cast<size_t>(row) * F + i] + bias[i];
+    float v = bias[i];
+    for (int sl = 0; sl < n_slabs; ++sl) v += acc[sl * slab_stride + static_cast<size_t>(row) * F + i];
+    out[static_cast<size_t>(row) * F + i] = v;
     ss = fma(static_cast<double>(v), static_cast<double>(v), ss);
   }
 #pragma unroll
   for (int off = 16; off > 0; off >>= 1) ss += __shfl_xor_sync(0xffffffffu, ss, off);
   const float denom = l2norm ? fmaxf(static_cast<float>(sqrt(ss)), 1e-12f) : 1.0f;
-  for (int i = lane; i < F; i += 32) {
-    const float v = acc[static_cast<size_t>(row) * F + i] + bias[i];
-    out[static_cast<size_t>(row) * F + i] = l2norm ? __fdiv_rn(v, denom) : v;
-  }
+  if (l2norm)
+    for (int i = lane; i < F; i += 32) out[static_cast<size_t>(row) * F + i] = __fdiv_rn(out[static_cast<size_t>(row) * F + i], denom);
 }
 
 static size_t up256(size_t v) { return (v + 255) & ~static_cast<size_t>(255); }
@@ -344,39 +376,50 @@ static int check_net(const vdk_convnext_net* n) {
 
 using namespace vdk;
 
-template <int TW>
+template <int TW, int MODE>
 static int launch_dwconv_tw(const CUtensorMap& mx, int batch, int H, int W, int C, int TH, int box_c, const float* w49,
                             const float* bias, const float* ln_w, const float* ln_b, float eps, __nv_bfloat16* y,
-                            cudaStream_t s) {
+                            float* rstd_out, const __nv_bfloat16* addend, cudaStream_t s) {
   const int tpg = ((C / 4) + 31) / 32 * 32;
   const int groups = std::max(1, std::min(512 / tpg, TH));
   const int n_chunks = C / box_c;
   const int smem = n_chunks * (TH + 6) * (TW + 6) * box_c * 2 + 16 * TW * 16 * 4 + 16 + 128;
-  auto kern = dwconv7_ln_kernel<TW>;
+  auto kern = dwconv7_ln_kernel<TW, MODE>;
   VDK_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
   const unsigned grid = static_cast<unsigned>(batch) * ((H + TH - 1) / TH) * ((W + TW - 1) / TW);
-  kern<<<grid, groups * tpg, smem, s>>>(mx, batch, H, W, C, TH, box_c, tpg, w49, bias, ln_w, ln_b, eps, y);
+  kern<<<grid, groups * tpg, smem, s>>>(mx, batch, H, W, C, TH, box_c, tpg, w49, bias, ln_w, ln_b, eps, y, rstd_out, addend);
   VDK_CUDA_OK(cudaGetLastError());
   return VDK_OK;
 }
 
-static int launch_dwconv7_ln(const __nv_bfloat16* x, int batch, int H, int W, int C, const float* w49, const float* bias,
-                             const float* ln_w, const float* ln_b, float eps, __nv_bfloat16* y, cudaStream_t s) {
-  VDK_REQUIRE(C % 8 == 0 && C <= 2048, "dwconv7_ln: C must be a multiple of 8, <= 2048 (got %d)", C);
+// mode 0: forward conv + bias + LayerNorm (rstd_out optional); mode 1: plain conv with `w49` (+ addend)
+static int launch_dwconv7(int mode, const __nv_bfloat16* x, int batch, int H, int W, int C, const float* w49, const float* bias,
+                          const float* ln_w, const float* ln_b, float eps, __nv_bfloat16* y, float* rstd_out,
+                          const __nv_bfloat16* addend, cudaStream_t s) {
+  VDK_REQUIRE(C % 8 == 0 && C <= 2048, "dwconv7: C must be a multiple of 8, <= 2048 (got %d)", C);
   // channel chunk of one TMA box: the largest divisor of C that is <= 256 and a multiple of 8
   int box_c = std::min(C, 256);
   while (C % box_c != 0 || box_c % 8 != 0) --box_c;
   // spatial tile: the largest of 7 / 4 / 2 whose halo (T+6)^2 x C x 2 B fits in ~200 KB of shared memory
   int T = 7;
   while (T > 2 && (T + 6) * (T + 6) * C * 2 > 200 * 1024) T = (T == 7) ? 4 : 2;
-  VDK_REQUIRE((T + 6) * (T + 6) * C * 2 <= 200 * 1024, "dwconv7_ln: C too large for the shared-memory halo (%d)", C);
+  VDK_REQUIRE((T + 6) * (T + 6) * C * 2 <= 200 * 1024, "dwconv7: C too large for the shared-memory halo (%d)", C);
   const int TH = std::min(T, H);
   CUtensorMap mx;
   int rc = make_tma_nhwc_16bit(&mx, x, batch, H, W, C, TH + 6, T + 6, box_c);
   if (rc != VDK_OK) return rc;
-  if (T == 7) return launch_dwconv_tw<7>(mx, batch, H, W, C, TH, box_c, w49, bias, ln_w, ln_b, eps, y, s);
-  if (T == 4) return launch_dwconv_tw<4>(mx, batch, H, W, C, TH, box_c, w49, bias, ln_w, ln_b, eps, y, s);
-  return launch_dwconv_tw<2>(mx, batch, H, W, C, TH, box_c, w49, bias, ln_w, ln_b, eps, y, s);
+#define VDK_DW(TWV)                                                                                                    \
+  return mode == 0 ? launch_dwconv_tw<TWV, 0>(mx, batch, H, W, C, TH, box_c, w49, bias, ln_w, ln_b, eps, y, rstd_out, addend, s) \
+                   : launch_dwconv_tw<TWV, 1>(mx, batch, H, W, C, TH, box_c, w49, bias, ln_w, ln_b, eps, y, rstd_out, addend, s)
+  if (T == 7) { VDK_DW(7); }
+  if (T == 4) { VDK_DW(4); }
+  VDK_DW(2);
+#undef VDK_DW
+}
+
+static int launch_dwconv7_ln(const __nv_bfloat16* x, int batch, int H, int W, int C, const float* w49, const float* bias,
+                             const float* ln_w, const float* ln_b, float eps, __nv_bfloat16* y, cudaStream_t s) {
+  return launch_dwconv7(0, x, batch, H, W, C, w49, bias, ln_w, ln_b, eps, y, nullptr, nullptr, s);
 }
 
 extern "C" int vdk_dwconv7_ln(const void* x, int batch, int H, int W, int C, const float* w49, const float* bias,
@@ -437,7 +480,7 @@ extern "C" int vdk_convnext_forward(const vdk_convnext_net* net, const float* im
   ws += up256(max_mc * 2);
   __nv_bfloat16* hbuf = reinterpret_cast<__nv_bfloat16*>(ws);
   ws += up256(std::max(max_m4c, static_cast<size_t>(batch) * hw0 * 48) * 2);
-  float* nacc = reinterpret_cast<float*>(ws);
+  (void)ws;
 
   auto gemm = [&](const void* A, const void* Bw, void* D, int M, int N, int K, int epi, const float* bias,
                   const float* gamma, const float* beta, const void* res, int out_dtype, int split) -> int {
@@ -493,12 +536,27 @@ extern "C" int vdk_convnext_forward(const vdk_convnext_net* net, const float* im
   // ---- neck: BN2d -> Flatten -> Linear -> BN1d, all folded into one skinny GEMM (eval statistics) ----
   {
     const int Kn = H * W * C, F = net->feat_dim;
-    VDK_CUDA_OK(cudaMemsetAsync(nacc, 0, static_cast<size_t>(batch) * F * sizeof(float), s));
-    const int tiles = ((batch + 127) / 128) * ((F + 127) / 128);
+    const int tiles = ((batch + 127) / 128) * ((F + 255) / 256);
+    // split-K over ~2 waves of CTAs; every split writes its own fp32 slab into the (now idle) hidden buffer and
+    // neck_finalize adds the slabs in order, so the embedding is bitwise reproducible
+    const size_t slab = static_cast<size_t>(batch) * F;
+    const size_t hbytes = up256(std::max(max_m4c, static_cast<size_t>(batch) * hw0 * 48) * 2);
     int split = std::max(1, (2 * sm_count()) / std::max(1, tiles));
-    rc = gemm(ybuf, net->neck_w, nacc, batch, F, Kn, VDK_EPI_NONE, nullptr, nullptr, nullptr, nullptr, VDK_DTYPE_FP32, split);
-    if (rc != VDK_OK) return rc;
-    neck_finalize_kernel<<<(batch * 32 + 255) / 256, 256, 0, s>>>(nacc, batch, F, net->neck_b, l2_normalize, embeddings);
+    split = static_cast<int>(std::min<size_t>(split, hbytes / (slab * sizeof(float))));
+    split = vdk_gemm_effective_splits(Kn, std::max(1, split));
+    float* slabs = reinterpret_cast<float*>(hbuf);
+    {
+      vdk_gemm_desc g{};
+      g.A = ybuf; g.B = net->neck_w; g.D = slabs;
+      g.M = batch; g.N = F; g.K = Kn; g.lda = Kn; g.ldb = Kn; g.ldd = F;
+      g.in_dtype = VDK_DTYPE_BF16; g.out_dtype = VDK_DTYPE_FP32; g.epilogue = VDK_EPI_NONE;
+      g.split_k = split;
+      g.split_stride = split > 1 ? static_cast<long long>(slab) : 0;
+      rc = gemm_run(g, s);
+      if (rc != VDK_OK) return rc;
+    }
+    neck_finalize_kernel<<<(batch * 32 + 255) / 256, 256, 0, s>>>(slabs, split, slab, batch, F, net->neck_b, l2_normalize,
+                                                                 embeddings);
     VDK_CUDA_OK(cudaGetLastError());
   }
   return VDK_OK;

@@ -32,6 +32,8 @@ struct GemmParams {
   float ln_eps;
   int split_k;  // > 1: each tile's K range is split over split_k work items, fp32 partials are atomically added
   int tma_store;  // 16-bit outputs: stage 128x64 sub-tiles in smem and write them with TMA (full-line stores)
+  int a_mn, b_mn;  // operand stored with the contraction index as the slow dimension ([K,M] / [K,N] row-major)
+  long long split_stride;  // > 0: split s writes its partial tile to D + s*split_stride with plain stores (deterministic)
 };
 
 template <int BN>
@@ -56,16 +58,24 @@ __device__ __forceinline__ float ex2_approx(float x) {
   asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
   return y;
 }
-// erf-GELU(x) = x * Phi(x) evaluated as x * sigmoid(2u), u = x (a + b x^2 + c x^4) a least-squares fit of
-// atanh(erf(x / sqrt 2)) (|x| clamped to 8 where the sigmoid is saturated): max |deviation| from the exact erf form
-// is 3.0e-5, below one bf16 ulp of the result for |y| > 0.008, and the multiplicative form keeps relative accuracy in
-// the negative tail.  10 instructions (2 on the SFU) instead of erff()'s ~25, which matters because the fc1 epilogue
-// is ALU-bound: 4C x tokens GELUs per block against 4096 tensor-core cycles per 128 x 256 tile.
-__device__ __forceinline__ float gelu_erf(float x) {
-  const float xc = fminf(fmaxf(x, -8.0f), 8.0f);
-  const float t = xc * xc;
-  const float k = xc * fmaf(t, fmaf(t, 0.0010350829f, -0.1069047f), -2.3009787f);  // -2 u(x) log2(e)
-  return x * rcp_approx(1.0f + ex2_approx(k));
+// erf-GELU for the forward epilogue.  The fc1 epilogue applies 4C x tokens GELUs per block while the tensor core
+// needs only 4096 cycles per 128 x 256 tile, so the activation has to cost ~5 issue slots and half an SFU op per
+// element or the epilogue, not the MMA, sets the pace (measured: two MUFU per element saturate the 16/cycle SFU).
+// y = 0.5 x (1 + tanh(u)), u = x (c1 + c3 x^2) with (c1, c3) refitted to the erf form (max |dev| 3.1e-4 instead of the
+// textbook tanh-GELU's 4.7e-4); u and tanh are evaluated two elements at a time in fp16x2 (tanh.approx.f16x2,
+// rel. error 2^-11), the final multiply in fp32 so that y -> x exactly for large x.  Absolute error <= 6e-4 |x|:
+// below one bf16 ulp of the typical activation; stated in the tests.
+__device__ __forceinline__ void gelu_pair(float& x0, float& x1) {
+  const __half2 h = __floats2half2_rn(x0, x1);
+  const __half2 t = __hmul2(h, h);
+  const __half2 p = __hfma2(t, __floats2half2_rn(0.03489978f, 0.03489978f), __floats2half2_rn(0.79973199f, 0.79973199f));
+  const __half2 u = __hmul2(h, p);
+  uint32_t ui = *reinterpret_cast<const uint32_t*>(&u), thi;
+  asm("tanh.approx.f16x2 %0, %1;" : "=r"(thi) : "r"(ui));
+  const float2 th = __half22float2(*reinterpret_cast<const __half2*>(&thi));
+  const float hx0 = 0.5f * x0, hx1 = 0.5f * x1;
+  x0 = fmaf(hx0, th.x, hx0);
+  x1 = fmaf(hx1, th.y, hx1);
 }
 
 __device__ __forceinline__ uint32_t pack2(float a, float b, int out_dtype) {
@@ -101,7 +111,7 @@ __device__ __forceinline__ void epi_math(const GemmParams& p, float (&v)[32], in
   }
   if (p.epilogue == VDK_EPI_GELU) {
 #pragma unroll
-    for (int j = 0; j < 32; ++j) v[j] = gelu_erf(v[j]);
+    for (int j = 0; j < 32; j += 2) gelu_pair(v[j], v[j + 1]);
   } else if (p.epilogue == VDK_EPI_LAYERNORM) {
 #pragma unroll
     for (int j = 0; j < 32; j += 4) {
@@ -156,7 +166,9 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
                const GemmParams p) {
   using Cfg = GemmCfg<BN>;
   extern __shared__ uint8_t smem_raw[];
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  // align inside the dynamic smem window without a pointer->integer->pointer round trip (which would demote every
+  // later access to generic LD/ST)
+  uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
   uint8_t* smem_store = smem + Cfg::kStages * Cfg::kStageBytes;
   uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem_store + 2 * Cfg::kStoreStageBytes);
   uint64_t* empty_bar = full_bar + Cfg::kStages;
@@ -213,8 +225,18 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
           uint8_t* sa = smem + stage * Cfg::kStageBytes;
           uint8_t* sb = sa + Cfg::kStageA;
           mbar_arrive_expect_tx(&full_bar[stage], Cfg::kStageBytes);
-          tma_load_2d(sa, &map_a, &full_bar[stage], kb * kBK, m0, kEvictNormal);
-          tma_load_2d(sb, &map_b, &full_bar[stage], kb * kBK, n0, kEvictLast);
+          if (p.a_mn) {  // [K,M] storage: 64-wide M blocks x 64 contraction rows, 8 KB each
+#pragma unroll
+            for (int j = 0; j < kBM / 64; ++j) tma_load_2d(sa + j * 8192, &map_a, &full_bar[stage], m0 + j * 64, kb * kBK, kEvictNormal);
+          } else {
+            tma_load_2d(sa, &map_a, &full_bar[stage], kb * kBK, m0, kEvictNormal);
+          }
+          if (p.b_mn) {
+#pragma unroll
+            for (int j = 0; j < BN / 64; ++j) tma_load_2d(sb + j * 8192, &map_b, &full_bar[stage], n0 + j * 64, kb * kBK, kEvictLast);
+          } else {
+            tma_load_2d(sb, &map_b, &full_bar[stage], kb * kBK, n0, kEvictLast);
+          }
           if (++stage == Cfg::kStages) {
             stage = 0;
             phase ^= 1;
@@ -225,7 +247,7 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
   } else if (warp == 1) {
     // ===================== MMA issuer =====================
     if (lane == 0) {
-      constexpr uint32_t idesc = umma_idesc_f16<kBf16>(kBM, BN);
+      const uint32_t idesc = umma_idesc_f16<kBf16>(kBM, BN, p.a_mn ? 1u : 0u, p.b_mn ? 1u : 0u);
       int stage = 0;
       uint32_t phase = 0;
       int it = 0;
@@ -243,13 +265,14 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
           tc_fence_after();
           const uint32_t sa = smem_u32(smem + stage * Cfg::kStageBytes);
           const uint32_t sb = sa + Cfg::kStageA;
-          const uint64_t da = umma_desc_k_sw128(sa);
-          const uint64_t db = umma_desc_k_sw128(sb);
+          const uint64_t da = p.a_mn ? umma_desc_mn_sw128(sa, 8192) : umma_desc_k_sw128(sa);
+          const uint64_t db = p.b_mn ? umma_desc_mn_sw128(sb, 8192) : umma_desc_k_sw128(sb);
+          // one UMMA consumes 16 contraction elements: K-major = 32 bytes inside the swizzle row (+2 in 16-byte
+          // units); MN-major = two 8-row groups of 1024 bytes (+128)
+          const uint32_t step_a = p.a_mn ? 128u : 2u, step_b = p.b_mn ? 128u : 2u;
 #pragma unroll
-          for (int k = 0; k < kBK / 16; ++k) {
-            // advance 16 elements (32 bytes) along K inside the 128-byte swizzle row: +2 in 16-byte units
-            umma_f16_ss(tmem_d, da + 2 * k, db + 2 * k, idesc, (kb > kb0 || k > 0) ? 1u : 0u);
-          }
+          for (int k = 0; k < kBK / 16; ++k)
+            umma_f16_ss(tmem_d, da + step_a * k, db + step_b * k, idesc, (kb > kb0 || k > 0) ? 1u : 0u);
           umma_commit(&empty_bar[stage]);  // smem slot reusable once these MMAs retire
           if (++stage == Cfg::kStages) {
             stage = 0;
@@ -384,12 +407,24 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
           tmem_ld_wait();
           const int col0 = n0 + c * 32;
           if (row < p.M && col0 < p.N && p.split_k > 1) {
-            // split-K: raw fp32 partial sums, combined in HBM (D was zeroed by the caller)
-            float* out = reinterpret_cast<float*>(p.D) + static_cast<size_t>(row) * p.ldd + col0;
+            // split-K: raw fp32 partial sums.  With a slab stride every split owns its own copy of D (plain stores,
+            // the consumer adds the slabs in a fixed order: deterministic); otherwise they are atomically added
+            // into a D the caller zeroed.
             const int ncols = min(32, p.N - col0);
+            if (p.split_stride > 0) {
+              float* out = reinterpret_cast<float*>(p.D) + static_cast<size_t>(tile / (num_m * num_n)) * p.split_stride +
+                           static_cast<size_t>(row) * p.ldd + col0;
 #pragma unroll
-            for (int j = 0; j < 32; ++j)
-              if (j < ncols) atomicAdd(out + j, __uint_as_float(r[j]));
+              for (int j = 0; j < 32; j += 4)
+                if (j < ncols)
+                  *reinterpret_cast<float4*>(out + j) = make_float4(__uint_as_float(r[j]), __uint_as_float(r[j + 1]),
+                                                                    __uint_as_float(r[j + 2]), __uint_as_float(r[j + 3]));
+            } else {
+              float* out = reinterpret_cast<float*>(p.D) + static_cast<size_t>(row) * p.ldd + col0;
+#pragma unroll
+              for (int j = 0; j < 32; ++j)
+                if (j < ncols) atomicAdd(out + j, __uint_as_float(r[j]));
+            }
           } else if (row < p.M && col0 < p.N) {
             float v[32];
 #pragma unroll
@@ -459,7 +494,10 @@ int gemm_run(const vdk_gemm_desc& g, cudaStream_t s) {
   VDK_REQUIRE(g.in_dtype == VDK_DTYPE_BF16 || g.in_dtype == VDK_DTYPE_FP16, "vdk_gemm: in_dtype must be bf16/fp16");
   VDK_REQUIRE(g.out_dtype >= VDK_DTYPE_BF16 && g.out_dtype <= VDK_DTYPE_FP32, "vdk_gemm: bad out_dtype");
   VDK_REQUIRE(g.N % 8 == 0 && g.K % 8 == 0, "vdk_gemm: N and K must be multiples of 8 (N=%d K=%d)", g.N, g.K);
-  VDK_REQUIRE(g.lda >= g.K && g.ldb >= g.K && g.ldd >= g.N && g.lda % 8 == 0 && g.ldb % 8 == 0, "vdk_gemm: bad pitches");
+  VDK_REQUIRE(g.lda >= (g.trans_a ? g.M : g.K) && g.ldb >= (g.trans_b ? g.N : g.K) && g.ldd >= g.N && g.lda % 8 == 0 &&
+                  g.ldb % 8 == 0,
+              "vdk_gemm: bad pitches");
+  if (g.trans_a) VDK_REQUIRE(g.M % 8 == 0, "vdk_gemm: trans_a needs M to be a multiple of 8");
   const int dalign = g.out_dtype == VDK_DTYPE_FP32 ? 4 : 8;
   VDK_REQUIRE(g.ldd % dalign == 0, "vdk_gemm: ldd must keep rows 16-byte aligned");
   VDK_REQUIRE((reinterpret_cast<uintptr_t>(g.D) & 15) == 0, "vdk_gemm: D must be 16-byte aligned");
@@ -484,6 +522,8 @@ int gemm_run(const vdk_gemm_desc& g, cudaStream_t s) {
     const int per = (kbt + split - 1) / split;
     split = (kbt + per - 1) / per;
   }
+  if (g.split_stride != 0)
+    VDK_REQUIRE(g.split_stride >= (long long)g.M * g.ldd && g.split_stride % 4 == 0, "vdk_gemm: split_stride must cover one [M,ldd] slab");
   if (split > 1)
     VDK_REQUIRE(g.out_dtype == VDK_DTYPE_FP32 && g.epilogue == VDK_EPI_NONE && !g.bias,
                 "vdk_gemm: split_k > 1 needs fp32 output, no bias and no epilogue (partials are atomically added)");
@@ -494,9 +534,13 @@ int gemm_run(const vdk_gemm_desc& g, cudaStream_t s) {
   if (g.epilogue == VDK_EPI_LAYERNORM) wide = g.N > 128;
   const int BN = wide ? 256 : 128;
   CUtensorMap ma, mb;
-  int rc = make_tma_2d_16bit(&ma, g.A, (uint64_t)g.M, (uint64_t)g.K, (uint64_t)g.lda, kBM, kBK);
+  // K-major operand: rows = M (or N), box = tile rows x 64 contraction elements; MN-major: rows = contraction index,
+  // box = 64 contraction rows x 64 M (or N) elements
+  int rc = g.trans_a ? make_tma_2d_16bit(&ma, g.A, (uint64_t)g.K, (uint64_t)g.M, (uint64_t)g.lda, kBK, 64)
+                     : make_tma_2d_16bit(&ma, g.A, (uint64_t)g.M, (uint64_t)g.K, (uint64_t)g.lda, kBM, kBK);
   if (rc != VDK_OK) return rc;
-  rc = make_tma_2d_16bit(&mb, g.B, (uint64_t)g.N, (uint64_t)g.K, (uint64_t)g.ldb, BN, kBK);
+  rc = g.trans_b ? make_tma_2d_16bit(&mb, g.B, (uint64_t)g.K, (uint64_t)g.N, (uint64_t)g.ldb, kBK, 64)
+                 : make_tma_2d_16bit(&mb, g.B, (uint64_t)g.N, (uint64_t)g.K, (uint64_t)g.ldb, BN, kBK);
   if (rc != VDK_OK) return rc;
   const int tma_store = (g.out_dtype != VDK_DTYPE_FP32 && split == 1) ? 1 : 0;
   CUtensorMap md = ma;  // placeholder when unused
@@ -510,13 +554,21 @@ int gemm_run(const vdk_gemm_desc& g, cudaStream_t s) {
     if (rc != VDK_OK) return rc;
   }
   GemmParams p{g.M, g.N, g.K, g.D, g.ldd, g.bias, g.gamma, g.beta, g.residual, g.ldr, g.out_dtype, g.epilogue,
-               g.ln_eps, split, tma_store};
+               g.ln_eps, split, tma_store, g.trans_a ? 1 : 0, g.trans_b ? 1 : 0, split > 1 ? (long long)g.split_stride : 0ll};
   const bool bf = g.in_dtype == VDK_DTYPE_BF16;
   if (wide) return bf ? launch_gemm<256, true>(ma, mb, md, mr, p, s) : launch_gemm<256, false>(ma, mb, md, mr, p, s);
   return bf ? launch_gemm<128, true>(ma, mb, md, mr, p, s) : launch_gemm<128, false>(ma, mb, md, mr, p, s);
 }
 
 }  // namespace vdk
+
+extern "C" int vdk_gemm_effective_splits(int K, int split_k) {
+  int split = split_k < 1 ? 1 : split_k;
+  const int kbt = (K + vdk::kBK - 1) / vdk::kBK;
+  if (split > kbt) split = kbt;
+  const int per = (kbt + split - 1) / split;
+  return (kbt + per - 1) / per;
+}
 
 extern "C" int vdk_gemm(const vdk_gemm_desc* desc, void* stream) {
   VDK_REQUIRE(desc, "vdk_gemm: null descriptor");

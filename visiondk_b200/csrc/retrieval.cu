@@ -129,7 +129,9 @@ __global__ void __launch_bounds__(kScoreThreads, 1)
 score_filter_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ CUtensorMap map_g,
                     const ScoreParams p) {
   extern __shared__ uint8_t smem_raw[];
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  // align inside the dynamic smem window without a pointer->integer->pointer round trip (which would demote every
+  // later access to generic LD/ST)
+  uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
   uint8_t* smem_q = smem;
   uint8_t* smem_g = smem + p.num_kb * kQBlockBytes;
   uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem_g + kGStages * kGStageBytes);

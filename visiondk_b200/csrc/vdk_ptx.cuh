@@ -157,14 +157,28 @@ __device__ __forceinline__ uint64_t umma_desc_k_sw128(uint32_t smem_addr) {
   return d;
 }
 
+// MN-major operand (the contraction index is the SLOW dimension in memory), 128-byte swizzle: the tile is stored as
+// blocks of 64 MN-elements (one 128-byte swizzle row) x kBK contraction rows; inside a block groups of 8 contraction
+// rows are 1024 B apart (stride byte offset), and the next block of 64 MN-elements starts `mn_block_bytes` later
+// (leading byte offset).  One UMMA (K = 16) spans two 8-row groups: advance the start address by 2048 B per step.
+__device__ __forceinline__ uint64_t umma_desc_mn_sw128(uint32_t smem_addr, uint32_t mn_block_bytes) {
+  uint64_t d = 0;
+  d |= static_cast<uint64_t>((smem_addr & 0x3FFFFu) >> 4);
+  d |= static_cast<uint64_t>((mn_block_bytes >> 4) & 0x3FFFu) << 16;  // leading byte offset
+  d |= static_cast<uint64_t>(1024 >> 4) << 32;                        // stride byte offset
+  d |= static_cast<uint64_t>(1) << 46;
+  d |= static_cast<uint64_t>(2) << 61;
+  return d;
+}
+
 // Instruction descriptor for kind::f16 (A/B fp16 or bf16, fp32 accumulate, both operands K-major).
 // Field layout: cute/arch/mma_sm100_desc.hpp (InstrDescriptor).
 template <bool kBf16>
-__host__ __device__ constexpr uint32_t umma_idesc_f16(uint32_t m, uint32_t n) {
+__host__ __device__ constexpr uint32_t umma_idesc_f16(uint32_t m, uint32_t n, uint32_t a_mn = 0, uint32_t b_mn = 0) {
   return (1u << 4)                      // c_format = F32
          | ((kBf16 ? 1u : 0u) << 7)     // a_format
          | ((kBf16 ? 1u : 0u) << 10)    // b_format
-         | (0u << 15) | (0u << 16)      // a_major, b_major = K
+         | (a_mn << 15) | (b_mn << 16)  // a_major, b_major: 0 = K-major, 1 = MN-major
          | ((n >> 3) << 17)             // n_dim
          | ((m >> 4) << 24);            // m_dim
 }

@@ -199,6 +199,16 @@ class FlatIPIndex:
         self.last_status = torch.zeros_like(self.last_status)
         self.wide_path_rows = int(rows.numel())
 
+    def check_status(self) -> dict:
+        """Synchronises and raises if any query overflowed its candidate lists (results would be incomplete; the
+        numpy `search()` resolves such rows on the wide path by itself)."""
+        st = self.last_status.cpu().tolist()
+        info = {"overflow_rows": st[0], "max_candidates": st[1], "max_survivors": st[2]}
+        if st[0] != 0:
+            raise RuntimeError(f"vdk_ip_topk: {st[0]} query rows overflowed their candidate lists {info}; "
+                               "call search_device(..., resolve_overflow=True) or search() to recompute them")
+        return info
+
     # ---- internals -----------------------------------------------------------------------------
     def _to_device(self, x) -> torch.Tensor:
         if isinstance(x, np.ndarray):
