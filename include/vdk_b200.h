@@ -45,6 +45,7 @@ int vdk_device_check(void);
 #define VDK_EPI_GELU 1           /* D = gelu_erf(acc + bias[n]) */
 #define VDK_EPI_SCALE_RESIDUAL 2 /* D = residual[m,n] + gamma[n] * (acc + bias[n])  (ConvNeXt layer-scale) */
 
+#define VDK_EPI_MUL_GELU_GRAD 4  /* D = acc * gelu'(residual[m,n]): dgrad through the MLP's GELU (residual = saved pre-activation) */
 #define VDK_EPI_LAYERNORM 3      /* D = LayerNorm_N(acc + bias) * gamma + beta; the tile must span the row (N <= 256) */
 
 typedef struct vdk_gemm_desc {
@@ -65,6 +66,7 @@ typedef struct vdk_gemm_desc {
                              split s stores its partial into the slab D + s*split_stride; the effective number of
                              splits is min(split_k, ceil(K/64)) rounded so that every split is non-empty — query it
                              with vdk_gemm_effective_splits.  Deterministic. */
+  void* aux_out;  /* VDK_EPI_GELU only, may be NULL: also store the pre-activation acc + bias [M,ldd] (saved for backward) */
   int trans_a; /* 1: A is stored [K,M] row-major (pitch lda >= M): the contraction index is the slow dimension */
   int trans_b; /* 1: B is stored [K,N] row-major (pitch ldb >= N).  Backward GEMMs use these: dgrad
                   dX = dY . W (B = W stored [N_out,K_in] = [K,N] of this contraction) and wgrad dW = dY^T . X

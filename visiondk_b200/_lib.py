@@ -14,7 +14,7 @@ _LIB_PATH = Path(__file__).resolve().parent / "lib" / "libvdk_b200.so"
 VDK_OK = 0
 VDK_ERR_INVALID, VDK_ERR_CUDA, VDK_ERR_WORKSPACE, VDK_ERR_OVERFLOW = -1, -2, -3, -4
 DTYPE_BF16, DTYPE_FP16, DTYPE_FP32 = 0, 1, 2
-EPI_NONE, EPI_GELU, EPI_SCALE_RESIDUAL, EPI_LAYERNORM = 0, 1, 2, 3
+EPI_NONE, EPI_GELU, EPI_SCALE_RESIDUAL, EPI_LAYERNORM, EPI_MUL_GELU_GRAD = 0, 1, 2, 3, 4
 
 
 class HeadDesc(C.Structure):
@@ -46,7 +46,8 @@ class GemmDesc(C.Structure):
         ("M", C.c_int), ("N", C.c_int), ("K", C.c_int), ("lda", C.c_int), ("ldb", C.c_int), ("ldd", C.c_int),
         ("in_dtype", C.c_int), ("out_dtype", C.c_int), ("epilogue", C.c_int),
         ("bias", C.c_void_p), ("gamma", C.c_void_p), ("beta", C.c_void_p), ("residual", C.c_void_p),
-        ("ldr", C.c_int), ("ln_eps", C.c_float), ("split_k", C.c_int), ("split_stride", C.c_longlong), ("trans_a", C.c_int), ("trans_b", C.c_int),
+        ("ldr", C.c_int), ("ln_eps", C.c_float), ("split_k", C.c_int), ("split_stride", C.c_longlong), ("aux_out", C.c_void_p), ("trans_a", C.c_int),
+        ("trans_b", C.c_int),
     ]
 
 

@@ -12,6 +12,7 @@
 //   neck_finalize     split-K partials + folded BN bias [+ L2 normalise] -> fp32 embeddings
 #include "vdk_host.h"
 #include "vdk_ptx.cuh"
+#include "convnext_internal.h"
 
 namespace vdk {
 
@@ -234,7 +235,8 @@ dwconv7_ln_kernel(const __grid_constant__ CUtensorMap map_x, int B, int H, int W
 template <int LPP>  // lanes per pixel (8, 16 or 32); each lane owns 8-channel (16-byte) vectors c = (sub + i*LPP)*8
 __global__ void __launch_bounds__(256)
 ln_patchify_kernel(const __nv_bfloat16* __restrict__ x, int B, int H, int W, int C, const float* __restrict__ ln_w,
-                   const float* __restrict__ ln_b, float eps, int patch /*1 or 2*/, __nv_bfloat16* __restrict__ out) {
+                   const float* __restrict__ ln_b, float eps, int patch /*1 or 2*/, __nv_bfloat16* __restrict__ out,
+                   float* __restrict__ rstd_out) {
   constexpr int kPPW = 32 / LPP;  // pixels per warp
   constexpr int kMaxIter = 8;     // C <= LPP * 8 * kMaxIter
   const int lane = threadIdx.x & 31;
@@ -281,6 +283,7 @@ ln_patchify_kernel(const __nv_bfloat16* __restrict__ x, int B, int H, int W, int
   for (int off = LPP / 2; off > 0; off >>= 1) q += __shfl_xor_sync(0xffffffffu, q, off);
   const float rstd = rsqrtf(q / static_cast<float>(C) + eps);
   if (!ok) return;
+  if (rstd_out != nullptr && sub == 0) rstd_out[pix] = rstd;
   int64_t orow;
   int ocol0;
   if (patch == 2) {
@@ -312,19 +315,19 @@ ln_patchify_kernel(const __nv_bfloat16* __restrict__ x, int B, int H, int W, int
   }
 }
 
-static int launch_ln_patchify(const __nv_bfloat16* x, int B, int H, int W, int C, const float* ln_w, const float* ln_b, float eps,
-                              int patch, __nv_bfloat16* out, cudaStream_t s) {
+int launch_ln_patchify(const __nv_bfloat16* x, int B, int H, int W, int C, const float* ln_w, const float* ln_b, float eps,
+                       int patch, __nv_bfloat16* out, float* rstd_out, cudaStream_t s) {
   VDK_REQUIRE(C % 8 == 0 && C <= 2048, "layernorm_patchify: C must be a multiple of 8, <= 2048 (got %d)", C);
   const int64_t npix = static_cast<int64_t>(B) * H * W;
   const int vecs = C / 8;
   if (vecs <= 8) {
     const int64_t warps = (npix + 3) / 4;
-    ln_patchify_kernel<8><<<static_cast<unsigned>((warps * 32 + 255) / 256), 256, 0, s>>>(x, B, H, W, C, ln_w, ln_b, eps, patch, out);
+    ln_patchify_kernel<8><<<static_cast<unsigned>((warps * 32 + 255) / 256), 256, 0, s>>>(x, B, H, W, C, ln_w, ln_b, eps, patch, out, rstd_out);
   } else if (vecs <= 16) {
     const int64_t warps = (npix + 1) / 2;
-    ln_patchify_kernel<16><<<static_cast<unsigned>((warps * 32 + 255) / 256), 256, 0, s>>>(x, B, H, W, C, ln_w, ln_b, eps, patch, out);
+    ln_patchify_kernel<16><<<static_cast<unsigned>((warps * 32 + 255) / 256), 256, 0, s>>>(x, B, H, W, C, ln_w, ln_b, eps, patch, out, rstd_out);
   } else {
-    ln_patchify_kernel<32><<<static_cast<unsigned>((npix * 32 + 255) / 256), 256, 0, s>>>(x, B, H, W, C, ln_w, ln_b, eps, patch, out);
+    ln_patchify_kernel<32><<<static_cast<unsigned>((npix * 32 + 255) / 256), 256, 0, s>>>(x, B, H, W, C, ln_w, ln_b, eps, patch, out, rstd_out);
   }
   VDK_CUDA_OK(cudaGetLastError());
   return VDK_OK;
@@ -393,7 +396,7 @@ static int launch_dwconv_tw(const CUtensorMap& mx, int batch, int H, int W, int 
 }
 
 // mode 0: forward conv + bias + LayerNorm (rstd_out optional); mode 1: plain conv with `w49` (+ addend)
-static int launch_dwconv7(int mode, const __nv_bfloat16* x, int batch, int H, int W, int C, const float* w49, const float* bias,
+int vdk::launch_dwconv7(int mode, const __nv_bfloat16* x, int batch, int H, int W, int C, const float* w49, const float* bias,
                           const float* ln_w, const float* ln_b, float eps, __nv_bfloat16* y, float* rstd_out,
                           const __nv_bfloat16* addend, cudaStream_t s) {
   VDK_REQUIRE(C % 8 == 0 && C <= 2048, "dwconv7: C must be a multiple of 8, <= 2048 (got %d)", C);
@@ -436,7 +439,7 @@ extern "C" int vdk_layernorm_patchify(const void* x, int batch, int H, int W, in
   VDK_REQUIRE(batch > 0 && H > 0 && W > 0 && C > 0 && C % 8 == 0 && C <= 2048, "vdk_layernorm_patchify: bad shape");
   VDK_REQUIRE(patch == 1 || (patch == 2 && H % 2 == 0 && W % 2 == 0), "vdk_layernorm_patchify: patch must be 1 or 2");
   return launch_ln_patchify(reinterpret_cast<const __nv_bfloat16*>(x), batch, H, W, C, ln_w, ln_b, eps, patch,
-                            reinterpret_cast<__nv_bfloat16*>(out), reinterpret_cast<cudaStream_t>(stream));
+                            reinterpret_cast<__nv_bfloat16*>(out), nullptr, reinterpret_cast<cudaStream_t>(stream));
 }
 
 extern "C" size_t vdk_convnext_workspace_bytes(const vdk_convnext_net* net, int batch) {
@@ -511,7 +514,7 @@ extern "C" int vdk_convnext_forward(const vdk_convnext_net* net, const float* im
       // ---- downsample: LayerNorm2d then conv2x2/s2 as a GEMM over (kh, kw, c) patch rows ----
       const vdk_convnext_down* d = &net->down[st];
       const int Cin = C;
-      rc = launch_ln_patchify(xbuf, batch, H, W, Cin, d->ln_w, d->ln_b, 1e-6f, 2, ybuf, s);
+      rc = launch_ln_patchify(xbuf, batch, H, W, Cin, d->ln_w, d->ln_b, 1e-6f, 2, ybuf, nullptr, s);
       if (rc != VDK_OK) return rc;
       H /= 2; W /= 2; C = net->dims[st];
       M = batch * H * W;
@@ -530,7 +533,7 @@ extern "C" int vdk_convnext_forward(const vdk_convnext_net* net, const float* im
   }
   // ---- head LayerNorm2d (applied by timm even with global_pool='') ----
   {
-    rc = launch_ln_patchify(xbuf, batch, H, W, C, net->head_ln_w, net->head_ln_b, 1e-6f, 1, ybuf, s);
+    rc = launch_ln_patchify(xbuf, batch, H, W, C, net->head_ln_w, net->head_ln_b, 1e-6f, 1, ybuf, nullptr, s);
     if (rc != VDK_OK) return rc;
   }
   // ---- neck: BN2d -> Flatten -> Linear -> BN1d, all folded into one skinny GEMM (eval statistics) ----

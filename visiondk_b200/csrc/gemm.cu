@@ -34,6 +34,7 @@ struct GemmParams {
   int tma_store;  // 16-bit outputs: stage 128x64 sub-tiles in smem and write them with TMA (full-line stores)
   int a_mn, b_mn;  // operand stored with the contraction index as the slow dimension ([K,M] / [K,N] row-major)
   long long split_stride;  // > 0: split s writes its partial tile to D + s*split_stride with plain stores (deterministic)
+  int aux_out;  // GELU only: also store the pre-activation (acc + bias) through map_d2 (saved for the backward)
 };
 
 template <int BN>
@@ -76,6 +77,16 @@ __device__ __forceinline__ void gelu_pair(float& x0, float& x1) {
   const float hx0 = 0.5f * x0, hx1 = 0.5f * x1;
   x0 = fmaf(hx0, th.x, hx0);
   x1 = fmaf(hx1, th.y, hx1);
+}
+
+// d/dx of the forward's GELU form 0.5 x (1 + tanh(u)), u = x (c1 + c3 x^2)  (fp32, one SFU op)
+__device__ __forceinline__ float gelu_grad(float x) {
+  const float t = x * x;
+  const float u = x * fmaf(t, 0.03489978f, 0.79973199f);
+  float th;
+  asm("tanh.approx.f32 %0, %1;" : "=f"(th) : "f"(u));
+  const float du = fmaf(t, 3.0f * 0.03489978f, 0.79973199f);
+  return 0.5f * (1.0f + th) + 0.5f * x * (1.0f - th * th) * du;
 }
 
 __device__ __forceinline__ uint32_t pack2(float a, float b, int out_dtype) {
@@ -163,7 +174,7 @@ template <int BN, bool kBf16>
 __global__ void __launch_bounds__(kGemmThreads, 1)
 gemm_tn_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b,
                const __grid_constant__ CUtensorMap map_d, const __grid_constant__ CUtensorMap map_r,
-               const GemmParams p) {
+               const __grid_constant__ CUtensorMap map_d2, const GemmParams p) {
   using Cfg = GemmCfg<BN>;
   extern __shared__ uint8_t smem_raw[];
   // align inside the dynamic smem window without a pointer->integer->pointer round trip (which would demote every
@@ -191,7 +202,8 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
     prefetch_tensormap(&map_a);
     prefetch_tensormap(&map_b);
     if (p.tma_store) prefetch_tensormap(&map_d);
-    if (p.tma_store && p.epilogue == VDK_EPI_SCALE_RESIDUAL) prefetch_tensormap(&map_r);
+    if (p.tma_store && (p.epilogue == VDK_EPI_SCALE_RESIDUAL || p.epilogue == VDK_EPI_MUL_GELU_GRAD)) prefetch_tensormap(&map_r);
+    if (p.aux_out) prefetch_tensormap(&map_d2);
     for (int i = 0; i < Cfg::kStages; ++i) {
       mbar_init(&full_bar[i], 1);
       mbar_init(&empty_bar[i], 1);
@@ -344,11 +356,11 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
         for (int sc = half; sc < BN / 64; sc += 2) {
           const int colS = n0 + sc * 64;
           if (colS >= p.N) break;
-          uint32_t packed[32];
-          const bool res_smem = p.epilogue == VDK_EPI_SCALE_RESIDUAL;
-          if (res_smem) {
-            // the residual sub-tile is fetched by TMA into the staging buffer (full-line reads instead of 32
-            // row-strided 16-byte loads per warp), updated in place, and stored back from the same buffer
+          uint32_t packed[32], packed_aux[32];
+          // auxiliary INPUT tile (residual to add, or the saved pre-activation whose GELU' scales the gradient): fetched
+          // by TMA into the staging buffer (full-line reads instead of 32 row-strided 16-byte loads per warp)
+          const bool aux_in = p.epilogue == VDK_EPI_SCALE_RESIDUAL || p.epilogue == VDK_EPI_MUL_GELU_GRAD;
+          if (aux_in) {
             if (leader) {
               if (stores_issued) tma_store_wait_read<0>();
               mbar_arrive_expect_tx(&res_bar[half], Cfg::kStoreStageBytes);
@@ -365,8 +377,24 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
             for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]);
             const int col0 = colS + hh * 32;
             const int ncols = max(0, min(32, p.N - col0));
-            if (ncols > 0) epi_math(p, v, row, col0, ncols, ln_mean, ln_rstd, res_smem);
-            if (res_smem) {
+            if (p.aux_out) {  // GELU with a saved pre-activation: bias first, keep a copy, then activate
+              if (ncols > 0 && p.bias != nullptr) {
+#pragma unroll
+                for (int j = 0; j < 32; j += 4) {
+                  if (j < ncols) {
+                    const float4 b = __ldg(reinterpret_cast<const float4*>(p.bias + col0 + j));
+                    v[j] += b.x; v[j + 1] += b.y; v[j + 2] += b.z; v[j + 3] += b.w;
+                  }
+                }
+              }
+#pragma unroll
+              for (int j = 0; j < 32; j += 2) packed_aux[hh * 16 + (j >> 1)] = pack2(v[j], v[j + 1], p.out_dtype);
+#pragma unroll
+              for (int j = 0; j < 32; j += 2) gelu_pair(v[j], v[j + 1]);
+            } else if (ncols > 0) {
+              epi_math(p, v, row, col0, ncols, ln_mean, ln_rstd, aux_in);
+            }
+            if (aux_in) {
               if (hh == 0) {
                 mbar_wait(&res_bar[half], res_phase);
                 res_phase ^= 1;
@@ -376,14 +404,38 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
                 const uint4 t = *reinterpret_cast<const uint4*>(stg + rit * 128 + (((hh * 4 + q) ^ (rit & 7)) << 4));
                 const float2 a0 = unpack2(t.x, p.out_dtype), a1 = unpack2(t.y, p.out_dtype);
                 const float2 a2 = unpack2(t.z, p.out_dtype), a3 = unpack2(t.w, p.out_dtype);
-                v[q * 8] += a0.x; v[q * 8 + 1] += a0.y; v[q * 8 + 2] += a1.x; v[q * 8 + 3] += a1.y;
-                v[q * 8 + 4] += a2.x; v[q * 8 + 5] += a2.y; v[q * 8 + 6] += a3.x; v[q * 8 + 7] += a3.y;
+                if (p.epilogue == VDK_EPI_SCALE_RESIDUAL) {
+                  v[q * 8] += a0.x; v[q * 8 + 1] += a0.y; v[q * 8 + 2] += a1.x; v[q * 8 + 3] += a1.y;
+                  v[q * 8 + 4] += a2.x; v[q * 8 + 5] += a2.y; v[q * 8 + 6] += a3.x; v[q * 8 + 7] += a3.y;
+                } else {
+                  v[q * 8] *= gelu_grad(a0.x); v[q * 8 + 1] *= gelu_grad(a0.y);
+                  v[q * 8 + 2] *= gelu_grad(a1.x); v[q * 8 + 3] *= gelu_grad(a1.y);
+                  v[q * 8 + 4] *= gelu_grad(a2.x); v[q * 8 + 5] *= gelu_grad(a2.y);
+                  v[q * 8 + 6] *= gelu_grad(a3.x); v[q * 8 + 7] *= gelu_grad(a3.y);
+                }
               }
             }
 #pragma unroll
             for (int j = 0; j < 32; j += 2) packed[hh * 16 + (j >> 1)] = pack2(v[j], v[j + 1], p.out_dtype);
           }
-          if (stores_issued && !res_smem) {  // the previous sub-tile must have been read out of the staging buffer
+          if (p.aux_out) {  // first the pre-activation copy, through the same staging buffer
+            if (stores_issued) {
+              if (leader) tma_store_wait_read<0>();
+              named_bar_sync(1 + half, 128);
+            }
+#pragma unroll
+            for (int q = 0; q < 8; ++q)
+              *reinterpret_cast<uint4*>(stg + rit * 128 + ((q ^ (rit & 7)) << 4)) =
+                  make_uint4(packed_aux[4 * q], packed_aux[4 * q + 1], packed_aux[4 * q + 2], packed_aux[4 * q + 3]);
+            fence_proxy_async_smem();
+            named_bar_sync(1 + half, 128);
+            if (leader) {
+              tma_store_2d(&map_d2, stg, colS, m0);
+              tma_store_commit();
+            }
+            stores_issued = true;
+          }
+          if (stores_issued && !aux_in) {  // the previous sub-tile must have been read out of the staging buffer
             if (leader) tma_store_wait_read<0>();
             named_bar_sync(1 + half, 128);
           }
@@ -469,7 +521,7 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
 
 template <int BN, bool kBf16>
 static int launch_gemm(const CUtensorMap& ma, const CUtensorMap& mb, const CUtensorMap& md, const CUtensorMap& mr,
-                       const GemmParams& p, cudaStream_t stream) {
+                       const CUtensorMap& md2, const GemmParams& p, cudaStream_t stream) {
   using Cfg = GemmCfg<BN>;
   auto kern = gemm_tn_kernel<BN, kBf16>;
   static bool attr_set = false;  // per (BN, dtype) instantiation
@@ -479,7 +531,7 @@ static int launch_gemm(const CUtensorMap& ma, const CUtensorMap& mb, const CUten
   }
   const int num_tiles = ((p.M + kBM - 1) / kBM) * ((p.N + BN - 1) / BN) * p.split_k;
   const int grid = num_tiles < sm_count() ? num_tiles : sm_count();
-  kern<<<grid, kGemmThreads, Cfg::kSmemBytes, stream>>>(ma, mb, md, mr, p);
+  kern<<<grid, kGemmThreads, Cfg::kSmemBytes, stream>>>(ma, mb, md, mr, md2, p);
   VDK_CUDA_OK(cudaGetLastError());
   return VDK_OK;
 }
@@ -501,7 +553,13 @@ int gemm_run(const vdk_gemm_desc& g, cudaStream_t s) {
   const int dalign = g.out_dtype == VDK_DTYPE_FP32 ? 4 : 8;
   VDK_REQUIRE(g.ldd % dalign == 0, "vdk_gemm: ldd must keep rows 16-byte aligned");
   VDK_REQUIRE((reinterpret_cast<uintptr_t>(g.D) & 15) == 0, "vdk_gemm: D must be 16-byte aligned");
-  VDK_REQUIRE(g.epilogue >= VDK_EPI_NONE && g.epilogue <= VDK_EPI_LAYERNORM, "vdk_gemm: bad epilogue");
+  VDK_REQUIRE(g.epilogue >= VDK_EPI_NONE && g.epilogue <= VDK_EPI_MUL_GELU_GRAD, "vdk_gemm: bad epilogue");
+  if (g.epilogue == VDK_EPI_MUL_GELU_GRAD) {
+    VDK_REQUIRE(g.residual && g.out_dtype != VDK_DTYPE_FP32 && g.split_k <= 1 && !g.bias,
+                "vdk_gemm: MUL_GELU_GRAD needs the saved pre-activation in `residual`, a 16-bit output and no bias");
+    VDK_REQUIRE(g.ldr >= g.N && g.ldr % 8 == 0 && (reinterpret_cast<uintptr_t>(g.residual) & 15) == 0,
+                "vdk_gemm: pre-activation rows must be 16-byte aligned");
+  }
   if (g.epilogue == VDK_EPI_SCALE_RESIDUAL) {
     VDK_REQUIRE(g.gamma && g.residual, "vdk_gemm: SCALE_RESIDUAL needs gamma and residual");
     VDK_REQUIRE(g.ldr >= g.N && g.ldr % dalign == 0 && (reinterpret_cast<uintptr_t>(g.residual) & 15) == 0,
@@ -548,16 +606,23 @@ int gemm_run(const vdk_gemm_desc& g, cudaStream_t s) {
     rc = make_tma_2d_16bit(&md, g.D, (uint64_t)g.M, (uint64_t)g.N, (uint64_t)g.ldd, kBM, 64);
     if (rc != VDK_OK) return rc;
   }
-  CUtensorMap mr = md;
-  if (tma_store && g.epilogue == VDK_EPI_SCALE_RESIDUAL) {
+  CUtensorMap mr = md, md2 = md;
+  if (tma_store && (g.epilogue == VDK_EPI_SCALE_RESIDUAL || g.epilogue == VDK_EPI_MUL_GELU_GRAD)) {
     rc = make_tma_2d_16bit(&mr, g.residual, (uint64_t)g.M, (uint64_t)g.N, (uint64_t)g.ldr, kBM, 64);
     if (rc != VDK_OK) return rc;
   }
+  const int aux_out = (g.aux_out != nullptr) ? 1 : 0;
+  if (aux_out) {
+    VDK_REQUIRE(tma_store && g.epilogue == VDK_EPI_GELU, "vdk_gemm: aux_out needs the GELU epilogue and a 16-bit output");
+    rc = make_tma_2d_16bit(&md2, g.aux_out, (uint64_t)g.M, (uint64_t)g.N, (uint64_t)g.ldd, kBM, 64);
+    if (rc != VDK_OK) return rc;
+  }
   GemmParams p{g.M, g.N, g.K, g.D, g.ldd, g.bias, g.gamma, g.beta, g.residual, g.ldr, g.out_dtype, g.epilogue,
-               g.ln_eps, split, tma_store, g.trans_a ? 1 : 0, g.trans_b ? 1 : 0, split > 1 ? (long long)g.split_stride : 0ll};
+               g.ln_eps, split, tma_store, g.trans_a ? 1 : 0, g.trans_b ? 1 : 0, split > 1 ? (long long)g.split_stride : 0ll,
+               aux_out};
   const bool bf = g.in_dtype == VDK_DTYPE_BF16;
-  if (wide) return bf ? launch_gemm<256, true>(ma, mb, md, mr, p, s) : launch_gemm<256, false>(ma, mb, md, mr, p, s);
-  return bf ? launch_gemm<128, true>(ma, mb, md, mr, p, s) : launch_gemm<128, false>(ma, mb, md, mr, p, s);
+  if (wide) return bf ? launch_gemm<256, true>(ma, mb, md, mr, md2, p, s) : launch_gemm<256, false>(ma, mb, md, mr, md2, p, s);
+  return bf ? launch_gemm<128, true>(ma, mb, md, mr, md2, p, s) : launch_gemm<128, false>(ma, mb, md, mr, md2, p, s);
 }
 
 }  // namespace vdk

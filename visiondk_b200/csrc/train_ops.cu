@@ -1,0 +1,546 @@
+// train_ops.cu — the HBM-bound kernels of the ConvNeXt training backward (everything that is not a GEMM):
+// column sums (bias gradients), LayerNorm backward (with the 2x2 un-patchify of the downsample layers), depthwise-7x7
+// weight gradient, BatchNorm forward/backward with batch statistics (the neck in train mode), layer-scale gradient
+// finalisation, weight packing (fp32 master -> bf16 kernel layouts) and the inverse permutation for gradients.
+//
+// Replaces the autograd backward of timm's ConvNeXtBlock / downsample / stem and of the reference neck
+// (models/faceX/backbone/timm_wrapper.py:30-38 in train mode: BatchNorm with batch statistics), i.e. what
+// `scaler.scale(loss).backward()` at engine/procedure/train.py:206 runs through ATen/cuDNN.
+#include "vdk_host.h"
+#include "vdk_ptx.cuh"
+#include "convnext_internal.h"
+
+namespace vdk {
+
+__device__ __forceinline__ float wsum(float v) {
+#pragma unroll
+  for (int off = 16; off > 0; off >>= 1) v += __shfl_xor_sync(0xffffffffu, v, off);
+  return v;
+}
+
+__device__ __forceinline__ void unpack8(const uint4& t, float (&v)[8]) {
+  const float2 a0 = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&t.x));
+  const float2 a1 = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&t.y));
+  const float2 a2 = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&t.z));
+  const float2 a3 = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&t.w));
+  v[0] = a0.x; v[1] = a0.y; v[2] = a1.x; v[3] = a1.y; v[4] = a2.x; v[5] = a2.y; v[6] = a3.x; v[7] = a3.y;
+}
+__device__ __forceinline__ uint4 pack8(const float (&v)[8]) {
+  __nv_bfloat162 o0 = __floats2bfloat162_rn(v[0], v[1]), o1 = __floats2bfloat162_rn(v[2], v[3]);
+  __nv_bfloat162 o2 = __floats2bfloat162_rn(v[4], v[5]), o3 = __floats2bfloat162_rn(v[6], v[7]);
+  uint4 t;
+  t.x = *reinterpret_cast<uint32_t*>(&o0); t.y = *reinterpret_cast<uint32_t*>(&o1);
+  t.z = *reinterpret_cast<uint32_t*>(&o2); t.w = *reinterpret_cast<uint32_t*>(&o3);
+  return t;
+}
+
+// ------------------------------------------------------------------------------------------------
+// column sums of a bf16 [M, C] matrix into fp32 out[C] (+=): bias gradients
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+col_sum_bf16_kernel(const __nv_bfloat16* __restrict__ x, int64_t M, int C, int ld, float* __restrict__ out) {
+  // a warp owns 32 x 8 = 256 consecutive columns (16-byte loads); the 8 warps of a block stride over rows
+  __shared__ float red[8][256];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int c0 = blockIdx.x * 256 + lane * 8;
+  float acc[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+  if (c0 < C) {
+    for (int64_t r = static_cast<int64_t>(blockIdx.y) * 8 + warp; r < M; r += static_cast<int64_t>(gridDim.y) * 8) {
+      float v[8];
+      unpack8(*reinterpret_cast<const uint4*>(x + r * ld + c0), v);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) acc[j] += v[j];
+    }
+  }
+#pragma unroll
+  for (int j = 0; j < 8; ++j) red[warp][lane * 8 + j] = acc[j];
+  __syncthreads();
+  const int c = blockIdx.x * 256 + threadIdx.x;
+  if (c < C) {
+    float s = 0.f;
+#pragma unroll
+    for (int w = 0; w < 8; ++w) s += red[w][threadIdx.x];
+    atomicAdd(out + c, s);
+  }
+}
+
+int launch_col_sum(const __nv_bfloat16* x, int64_t M, int C, int ld, float* out, cudaStream_t s) {
+  VDK_REQUIRE(C % 8 == 0 && ld % 8 == 0, "col_sum: C and pitch must be multiples of 8");
+  dim3 grid((C + 255) / 256, static_cast<unsigned>(std::max<int64_t>(1, std::min<int64_t>((M + 63) / 64, 592))));
+  col_sum_bf16_kernel<<<grid, 256, 0, s>>>(x, M, C, ld, out);
+  VDK_CUDA_OK(cudaGetLastError());
+  return VDK_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// LayerNorm backward over C (optionally through the 2x2/s2 patch regrouping of the downsample layers)
+// ------------------------------------------------------------------------------------------------
+// dy, y: [rows, patch*patch*C] (grad of / saved LayerNorm output, patch-row layout), rstd[pixel], dx: NHWC [B,H,W,C].
+//   xh = (y - beta) / gamma;  g = dy * gamma;  dx = rstd * (g - mean_C(g) - xh * mean_C(g * xh)) (+ addend)
+//   dgamma += sum_pixels dy * xh;  dbeta += sum_pixels dy
+template <int LPP>
+__global__ void __launch_bounds__(256)
+ln_bwd_kernel(const __nv_bfloat16* __restrict__ dy, const __nv_bfloat16* __restrict__ y, const float* __restrict__ rstd,
+              int B, int H, int W, int C, const float* __restrict__ ln_w, const float* __restrict__ ln_b, int patch,
+              __nv_bfloat16* __restrict__ dx, const __nv_bfloat16* __restrict__ addend, float* __restrict__ dgamma,
+              float* __restrict__ dbeta) {
+  constexpr int kPPW = 32 / LPP;
+  constexpr int kIt = 4;  // C <= LPP * 8 * 4
+  const int lane = threadIdx.x & 31, sub = lane % LPP;
+  const int64_t npix = static_cast<int64_t>(B) * H * W;
+  const int64_t nwarps = (static_cast<int64_t>(gridDim.x) * blockDim.x) >> 5;
+  const int64_t warp_id = (static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x) >> 5;
+  const int iters = (C + LPP * 8 - 1) / (LPP * 8);
+  float gw[kIt][8], gb[kIt][8], lw[kIt][8], lb[kIt][8];
+#pragma unroll
+  for (int i = 0; i < kIt; ++i) {
+    const int c = (sub + i * LPP) * 8;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      gw[i][j] = 0.f; gb[i][j] = 0.f;
+      const bool okc = i < iters && c < C;
+      float w = okc ? ln_w[c + j] : 1.f;
+      if (fabsf(w) < 1e-12f) w = w < 0.f ? -1e-12f : 1e-12f;
+      lw[i][j] = w;
+      lb[i][j] = okc ? ln_b[c + j] : 0.f;
+    }
+  }
+  const float inv_c = 1.0f / static_cast<float>(C);
+  for (int64_t base = warp_id * kPPW; base < npix; base += nwarps * kPPW) {
+    const int64_t pix = base + lane / LPP;
+    const bool ok = pix < npix;
+    int64_t orow = pix;
+    int ocol0 = 0;
+    if (patch == 2 && ok) {
+      const int xw = static_cast<int>(pix % W);
+      const int yh = static_cast<int>((pix / W) % H);
+      const int b = static_cast<int>(pix / (static_cast<int64_t>(W) * H));
+      orow = (static_cast<int64_t>(b) * (H / 2) + (yh >> 1)) * (W / 2) + (xw >> 1);
+      ocol0 = ((yh & 1) * 2 + (xw & 1)) * C;
+    }
+    const int64_t roff = orow * (static_cast<int64_t>(C) * patch * patch) + ocol0;
+    float g[kIt][8], xh[kIt][8];
+    float s1 = 0.f, s2 = 0.f;
+#pragma unroll
+    for (int i = 0; i < kIt; ++i) {
+      const int c = (sub + i * LPP) * 8;
+      if (i < iters) {
+        const bool okc = ok && c < C;
+        uint4 tdy = make_uint4(0, 0, 0, 0), ty = make_uint4(0, 0, 0, 0);
+        if (okc) {
+          tdy = *reinterpret_cast<const uint4*>(dy + roff + c);
+          ty = *reinterpret_cast<const uint4*>(y + roff + c);
+        }
+        float vdy[8], vy[8];
+        unpack8(tdy, vdy);
+        unpack8(ty, vy);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          const float h = okc ? (vy[j] - lb[i][j]) / lw[i][j] : 0.f;
+          xh[i][j] = h;
+          g[i][j] = vdy[j] * lw[i][j];
+          s1 += g[i][j];
+          s2 = fmaf(g[i][j], h, s2);
+          gw[i][j] = fmaf(vdy[j], h, gw[i][j]);
+          gb[i][j] += vdy[j];
+        }
+      }
+    }
+#pragma unroll
+    for (int off = LPP / 2; off > 0; off >>= 1) {
+      s1 += __shfl_xor_sync(0xffffffffu, s1, off);
+      s2 += __shfl_xor_sync(0xffffffffu, s2, off);
+    }
+    if (ok) {
+      const float rs = rstd[pix];
+      const float m1 = s1 * inv_c, m2 = s2 * inv_c;
+#pragma unroll
+      for (int i = 0; i < kIt; ++i) {
+        const int c = (sub + i * LPP) * 8;
+        if (i < iters && c < C) {
+          float o[8];
+#pragma unroll
+          for (int j = 0; j < 8; ++j) o[j] = rs * (g[i][j] - m1 - xh[i][j] * m2);
+          if (addend) {
+            float a[8];
+            unpack8(*reinterpret_cast<const uint4*>(addend + pix * C + c), a);
+#pragma unroll
+            for (int j = 0; j < 8; ++j) o[j] += a[j];
+          }
+          *reinterpret_cast<uint4*>(dx + pix * C + c) = pack8(o);
+        }
+      }
+    }
+  }
+  // lanes that handled the same channels (kPPW pixel slots per warp) are combined, then one atomic per channel per warp
+#pragma unroll
+  for (int i = 0; i < kIt; ++i) {
+    const int c = (sub + i * LPP) * 8;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      float a = gw[i][j], b2 = gb[i][j];
+#pragma unroll
+      for (int off = LPP; off < 32; off <<= 1) {
+        a += __shfl_xor_sync(0xffffffffu, a, off);
+        b2 += __shfl_xor_sync(0xffffffffu, b2, off);
+      }
+      if (lane < LPP && i < iters && c < C) {
+        atomicAdd(dgamma + c + j, a);
+        atomicAdd(dbeta + c + j, b2);
+      }
+    }
+  }
+}
+
+int launch_ln_bwd(const __nv_bfloat16* dy, const __nv_bfloat16* y, const float* rstd, int B, int H, int W, int C,
+                  const float* ln_w, const float* ln_b, int patch, __nv_bfloat16* dx, const __nv_bfloat16* addend,
+                  float* dgamma, float* dbeta, cudaStream_t s) {
+  VDK_REQUIRE(C % 8 == 0 && C <= 1024, "ln_bwd: C must be a multiple of 8, <= 1024 (got %d)", C);
+  const int64_t npix = static_cast<int64_t>(B) * H * W;
+  const int vecs = C / 8;
+  const int blocks = static_cast<int>(std::min<int64_t>((npix + 7) / 8, 148 * 8));
+  if (vecs <= 8) ln_bwd_kernel<8><<<blocks, 256, 0, s>>>(dy, y, rstd, B, H, W, C, ln_w, ln_b, patch, dx, addend, dgamma, dbeta);
+  else if (vecs <= 16) ln_bwd_kernel<16><<<blocks, 256, 0, s>>>(dy, y, rstd, B, H, W, C, ln_w, ln_b, patch, dx, addend, dgamma, dbeta);
+  else ln_bwd_kernel<32><<<blocks, 256, 0, s>>>(dy, y, rstd, B, H, W, C, ln_w, ln_b, patch, dx, addend, dgamma, dbeta);
+  VDK_CUDA_OK(cudaGetLastError());
+  return VDK_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// depthwise 7x7 weight gradient: dw[tap][c] += sum_{b,y,x} dconv[b,y,x,c] * x[b,y+dy-3,x+dx-3,c]; dbias[c] += sum dconv
+// ------------------------------------------------------------------------------------------------
+// CTA = (image, T x T pixel tile, 64-channel chunk): the x halo and the dconv tile arrive by TMA (zero-filled out of
+// bounds, so no masks); 16 channel-quads x 16 pixel planes of threads; one filter row (7 taps x 4 channels) of
+// accumulators at a time; planes are combined through shared memory and each CTA issues one atomic per (tap, channel).
+constexpr int kWgT = 14;
+constexpr int kWgC = 64;
+
+__global__ void __launch_bounds__(256)
+dwconv7_wgrad_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant__ CUtensorMap map_g, int B, int H,
+                     int W, int C, int T, float* __restrict__ dw49, float* __restrict__ dbias) {
+  extern __shared__ uint8_t wg_raw[];
+  uint8_t* smem = wg_raw + ((128u - (smem_u32(wg_raw) & 127u)) & 127u);
+  const int halo = T + 6;
+  const int x_bytes = halo * halo * kWgC * 2, g_bytes = T * T * kWgC * 2;
+  uint8_t* sx = smem;
+  uint8_t* sg = smem + ((x_bytes + 127) & ~127);
+  float* red = reinterpret_cast<float*>(sg + ((g_bytes + 127) & ~127));  // [16 planes][8 (7 taps + bias)][64]
+  uint64_t* bar = reinterpret_cast<uint64_t*>(red + 16 * 8 * kWgC);
+
+  const int tiles_w = (W + T - 1) / T, tiles_h = (H + T - 1) / T;
+  const int n_cc = C / kWgC;
+  int bid = blockIdx.x;
+  const int cc = bid % n_cc; bid /= n_cc;
+  const int tw = bid % tiles_w; bid /= tiles_w;
+  const int th = bid % tiles_h;
+  const int b = bid / tiles_h;
+  const int oy0 = th * T, ox0 = tw * T;
+
+  if (threadIdx.x == 0) {
+    prefetch_tensormap(&map_x);
+    prefetch_tensormap(&map_g);
+    mbar_init(bar, 1);
+    fence_mbar_init();
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    mbar_arrive_expect_tx(bar, x_bytes + g_bytes);
+    tma_load_4d(sx, &map_x, bar, cc * kWgC, ox0 - 3, oy0 - 3, b);
+    tma_load_4d(sg, &map_g, bar, cc * kWgC, ox0, oy0, b);
+  }
+  mbar_wait(bar, 0);
+
+  const int quad = threadIdx.x & 15, plane = threadIdx.x >> 4;
+  const int npx = T * T;
+  float bsum[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll 1
+  for (int dy = 0; dy < 7; ++dy) {
+    float acc[7][4];
+#pragma unroll
+    for (int dx = 0; dx < 7; ++dx)
+#pragma unroll
+      for (int c = 0; c < 4; ++c) acc[dx][c] = 0.f;
+    for (int p = plane; p < npx; p += 16) {
+      const int py = p / T, px = p - py * T;
+      const uint2 tg = *reinterpret_cast<const uint2*>(sg + (p * kWgC + quad * 4) * 2);
+      const float2 g0 = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&tg.x));
+      const float2 g1 = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&tg.y));
+      if (dy == 0) {
+        bsum[0] += g0.x; bsum[1] += g0.y; bsum[2] += g1.x; bsum[3] += g1.y;
+      }
+      const uint8_t* xr = sx + (((py + dy) * halo + px) * kWgC + quad * 4) * 2;
+#pragma unroll
+      for (int dx = 0; dx < 7; ++dx) {
+        const uint2 tx = *reinterpret_cast<const uint2*>(xr + dx * kWgC * 2);
+        const float2 x0 = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&tx.x));
+        const float2 x1 = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&tx.y));
+        acc[dx][0] = fmaf(g0.x, x0.x, acc[dx][0]);
+        acc[dx][1] = fmaf(g0.y, x0.y, acc[dx][1]);
+        acc[dx][2] = fmaf(g1.x, x1.x, acc[dx][2]);
+        acc[dx][3] = fmaf(g1.y, x1.y, acc[dx][3]);
+      }
+    }
+#pragma unroll
+    for (int dx = 0; dx < 7; ++dx)
+#pragma unroll
+      for (int c = 0; c < 4; ++c) red[(plane * 8 + dx) * kWgC + quad * 4 + c] = acc[dx][c];
+    if (dy == 0) {
+#pragma unroll
+      for (int c = 0; c < 4; ++c) red[(plane * 8 + 7) * kWgC + quad * 4 + c] = bsum[c];
+    }
+    __syncthreads();
+    const int n_out = (dy == 0 ? 8 : 7) * kWgC;
+    for (int o = threadIdx.x; o < n_out; o += 256) {
+      float s = 0.f;
+#pragma unroll
+      for (int pl = 0; pl < 16; ++pl) s += red[pl * 8 * kWgC + o];
+      const int slot = o / kWgC, ch = o - slot * kWgC;
+      if (slot < 7) atomicAdd(dw49 + (dy * 7 + slot) * C + cc * kWgC + ch, s);
+      else atomicAdd(dbias + cc * kWgC + ch, s);
+    }
+    __syncthreads();
+  }
+}
+
+int launch_dwconv7_wgrad(const __nv_bfloat16* x, const __nv_bfloat16* dconv, int B, int H, int W, int C, float* dw49,
+                         float* dbias, cudaStream_t s) {
+  VDK_REQUIRE(C % kWgC == 0, "dwconv7_wgrad: C must be a multiple of %d (got %d)", kWgC, C);
+  const int T = std::min(kWgT, std::max(H, W));
+  CUtensorMap mx, mg;
+  int rc = make_tma_nhwc_16bit(&mx, x, B, H, W, C, T + 6, T + 6, kWgC);
+  if (rc != VDK_OK) return rc;
+  rc = make_tma_nhwc_16bit(&mg, dconv, B, H, W, C, T, T, kWgC);
+  if (rc != VDK_OK) return rc;
+  const int halo = T + 6;
+  const int smem = ((halo * halo * kWgC * 2 + 127) & ~127) + ((T * T * kWgC * 2 + 127) & ~127) + 16 * 8 * kWgC * 4 + 16 + 128;
+  static bool attr = false;
+  if (!attr) {
+    VDK_CUDA_OK(cudaFuncSetAttribute(dwconv7_wgrad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024));
+    attr = true;
+  }
+  const unsigned grid = static_cast<unsigned>(B) * ((H + T - 1) / T) * ((W + T - 1) / T) * (C / kWgC);
+  dwconv7_wgrad_kernel<<<grid, 256, smem, s>>>(mx, mg, B, H, W, C, T, dw49, dbias);
+  VDK_CUDA_OK(cudaGetLastError());
+  return VDK_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// BatchNorm with batch statistics over the rows of an [R, C] matrix (channels last): forward and backward
+// ------------------------------------------------------------------------------------------------
+// one block per 32 channels, 8 warps stride the rows; two passes (mean, then centred variance) in fp32
+template <typename TIn, typename TOut>
+__global__ void __launch_bounds__(256)
+bn_train_fwd_kernel(const TIn* __restrict__ x, int R, int C, const float* __restrict__ weight, const float* __restrict__ bias,
+                    float eps, float momentum, TOut* __restrict__ y, float* __restrict__ save_mean,
+                    float* __restrict__ save_rstd, float* __restrict__ running_mean, float* __restrict__ running_var) {
+  __shared__ float red[8][33];
+  __shared__ float s_mean[32], s_rstd[32];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int c = blockIdx.x * 32 + lane;
+  const bool ok = c < C;
+  float s = 0.f;
+  if (ok) for (int r = warp; r < R; r += 8) s += static_cast<float>(x[static_cast<int64_t>(r) * C + c]);
+  red[warp][lane] = s;
+  __syncthreads();
+  if (warp == 0) {
+    float t = 0.f;
+#pragma unroll
+    for (int w = 0; w < 8; ++w) t += red[w][lane];
+    s_mean[lane] = t / static_cast<float>(R);
+  }
+  __syncthreads();
+  const float mean = s_mean[lane];
+  float q = 0.f;
+  if (ok) for (int r = warp; r < R; r += 8) {
+    const float d = static_cast<float>(x[static_cast<int64_t>(r) * C + c]) - mean;
+    q = fmaf(d, d, q);
+  }
+  red[warp][lane] = q;
+  __syncthreads();
+  if (warp == 0) {
+    float t = 0.f;
+#pragma unroll
+    for (int w = 0; w < 8; ++w) t += red[w][lane];
+    const float var = t / static_cast<float>(R);  // biased: what normalises the batch
+    s_rstd[lane] = rsqrtf(var + eps);
+    if (ok) {
+      save_mean[c] = mean;
+      save_rstd[c] = s_rstd[lane];
+      if (running_mean) {  // nn.BatchNorm: running_var uses the unbiased estimate
+        running_mean[c] = (1.f - momentum) * running_mean[c] + momentum * mean;
+        const float unb = R > 1 ? t / static_cast<float>(R - 1) : var;
+        running_var[c] = (1.f - momentum) * running_var[c] + momentum * unb;
+      }
+    }
+  }
+  __syncthreads();
+  if (ok) {
+    const float rs = s_rstd[lane], w = weight[c], b = bias[c];
+    for (int r = warp; r < R; r += 8) {
+      const float v = (static_cast<float>(x[static_cast<int64_t>(r) * C + c]) - mean) * rs * w + b;
+      y[static_cast<int64_t>(r) * C + c] = static_cast<TOut>(v);
+    }
+  }
+}
+
+// dx = w * rstd * (dy - mean(dy) - xh * mean(dy * xh)), xh = (x - mean) * rstd; dweight = sum dy * xh; dbias = sum dy
+template <typename TIn, typename TGrad>
+__global__ void __launch_bounds__(256)
+bn_train_bwd_kernel(const TGrad* __restrict__ dy, const TIn* __restrict__ x, int R, int C, const float* __restrict__ weight,
+                    const float* __restrict__ save_mean, const float* __restrict__ save_rstd, TGrad* __restrict__ dx,
+                    float* __restrict__ dweight, float* __restrict__ dbias) {
+  __shared__ float red[2][8][33];
+  __shared__ float s_a[32], s_b[32];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int c = blockIdx.x * 32 + lane;
+  const bool ok = c < C;
+  const float mean = ok ? save_mean[c] : 0.f, rs = ok ? save_rstd[c] : 0.f;
+  float s1 = 0.f, s2 = 0.f;
+  if (ok) for (int r = warp; r < R; r += 8) {
+    const float g = static_cast<float>(dy[static_cast<int64_t>(r) * C + c]);
+    const float xh = (static_cast<float>(x[static_cast<int64_t>(r) * C + c]) - mean) * rs;
+    s1 += g;
+    s2 = fmaf(g, xh, s2);
+  }
+  red[0][warp][lane] = s1;
+  red[1][warp][lane] = s2;
+  __syncthreads();
+  if (warp == 0) {
+    float a = 0.f, b = 0.f;
+#pragma unroll
+    for (int w = 0; w < 8; ++w) {
+      a += red[0][w][lane];
+      b += red[1][w][lane];
+    }
+    s_a[lane] = a;
+    s_b[lane] = b;
+    if (ok) {
+      dbias[c] += a;
+      dweight[c] += b;
+    }
+  }
+  __syncthreads();
+  if (ok) {
+    const float w = weight[c], m1 = s_a[lane] / static_cast<float>(R), m2 = s_b[lane] / static_cast<float>(R);
+    for (int r = warp; r < R; r += 8) {
+      const float g = static_cast<float>(dy[static_cast<int64_t>(r) * C + c]);
+      const float xh = (static_cast<float>(x[static_cast<int64_t>(r) * C + c]) - mean) * rs;
+      dx[static_cast<int64_t>(r) * C + c] = static_cast<TGrad>(w * rs * (g - m1 - xh * m2));
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// weight packing: fp32 master -> bf16 kernel layout; permutation [a][b][c] -> [a][c][b]; gradient un-permutation
+// ------------------------------------------------------------------------------------------------
+// out_bf16[a][c][b] = in[a][b][c] * (row_scale ? row_scale[a] : 1)
+__global__ void __launch_bounds__(256)
+permute021_kernel(const float* __restrict__ in, int A, int Bd, int Cd, const float* __restrict__ row_scale,
+                  __nv_bfloat16* __restrict__ out_bf16, float* __restrict__ out_f32, int accumulate) {
+  const int64_t total = static_cast<int64_t>(A) * Bd * Cd;
+  for (int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < total;
+       i += static_cast<int64_t>(gridDim.x) * blockDim.x) {
+    // i indexes the OUTPUT [a][c][b] so that writes are coalesced
+    const int b = static_cast<int>(i % Bd);
+    const int c = static_cast<int>((i / Bd) % Cd);
+    const int a = static_cast<int>(i / (static_cast<int64_t>(Bd) * Cd));
+    float v = in[(static_cast<int64_t>(a) * Bd + b) * Cd + c];
+    if (row_scale) v *= row_scale[a];
+    if (out_bf16) out_bf16[i] = __float2bfloat16_rn(v);
+    if (out_f32) out_f32[i] = accumulate ? out_f32[i] + v : v;
+  }
+}
+
+// layer-scale gradient finalisation for fc2 (out = x + gamma * (h W2^T + b2)):
+//   G[c,k] = sum_m dOut[m,c] h[m,k] (the wgrad GEMM without gamma), sdo[c] = sum_m dOut[m,c]
+//   dW2[c,k] += gamma[c] G[c,k];  dgamma[c] += sum_k G[c,k] W2[c,k] + b2[c] sdo[c];  db2[c] += gamma[c] sdo[c]
+__global__ void __launch_bounds__(256)
+layerscale_finalize_kernel(const float* __restrict__ G, const float* __restrict__ W2, const float* __restrict__ b2,
+                           const float* __restrict__ gamma, const float* __restrict__ sdo, int C, int K4,
+                           float* __restrict__ dW2, float* __restrict__ dgamma, float* __restrict__ db2) {
+  __shared__ float red[8];
+  const int c = blockIdx.x;
+  const float gm = gamma[c];
+  float dot = 0.f;
+  for (int k = threadIdx.x; k < K4; k += 256) {
+    const float g = G[static_cast<int64_t>(c) * K4 + k];
+    dot = fmaf(g, W2[static_cast<int64_t>(c) * K4 + k], dot);
+    dW2[static_cast<int64_t>(c) * K4 + k] += gm * g;
+  }
+  dot = wsum(dot);
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = dot;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    float t = 0.f;
+#pragma unroll
+    for (int w = 0; w < 8; ++w) t += red[w];
+    dgamma[c] += t + b2[c] * sdo[c];
+    db2[c] += gm * sdo[c];
+  }
+}
+
+__global__ void cast_f32_bf16_kernel(const float* __restrict__ in, int64_t n, __nv_bfloat16* __restrict__ out) {
+  for (int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < n;
+       i += static_cast<int64_t>(gridDim.x) * blockDim.x)
+    out[i] = __float2bfloat16_rn(in[i]);
+}
+__global__ void add_f32_kernel(float* __restrict__ dst, const float* __restrict__ src, int64_t n) {
+  for (int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < n;
+       i += static_cast<int64_t>(gridDim.x) * blockDim.x)
+    dst[i] += src[i];
+}
+
+static int blocks_for(int64_t n) { return static_cast<int>(std::max<int64_t>(1, std::min<int64_t>((n + 255) / 256, 148 * 16))); }
+
+int launch_permute021(const float* in, int A, int Bd, int Cd, const float* row_scale, __nv_bfloat16* out_bf16,
+                      float* out_f32, int accumulate, cudaStream_t s) {
+  permute021_kernel<<<blocks_for(static_cast<int64_t>(A) * Bd * Cd), 256, 0, s>>>(in, A, Bd, Cd, row_scale, out_bf16, out_f32,
+                                                                                 accumulate);
+  VDK_CUDA_OK(cudaGetLastError());
+  return VDK_OK;
+}
+int launch_cast_bf16(const float* in, int64_t n, __nv_bfloat16* out, cudaStream_t s) {
+  cast_f32_bf16_kernel<<<blocks_for(n), 256, 0, s>>>(in, n, out);
+  VDK_CUDA_OK(cudaGetLastError());
+  return VDK_OK;
+}
+int launch_layerscale_finalize(const float* G, const float* W2, const float* b2, const float* gamma, const float* sdo, int C,
+                               int K4, float* dW2, float* dgamma, float* db2, cudaStream_t s) {
+  layerscale_finalize_kernel<<<C, 256, 0, s>>>(G, W2, b2, gamma, sdo, C, K4, dW2, dgamma, db2);
+  VDK_CUDA_OK(cudaGetLastError());
+  return VDK_OK;
+}
+int launch_bn_fwd_bf16(const __nv_bfloat16* x, int R, int C, const float* w, const float* b, float eps, float momentum,
+                       __nv_bfloat16* y, float* save_mean, float* save_rstd, float* run_mean, float* run_var, cudaStream_t s) {
+  bn_train_fwd_kernel<__nv_bfloat16, __nv_bfloat16><<<(C + 31) / 32, 256, 0, s>>>(x, R, C, w, b, eps, momentum, y, save_mean,
+                                                                                  save_rstd, run_mean, run_var);
+  VDK_CUDA_OK(cudaGetLastError());
+  return VDK_OK;
+}
+int launch_bn_fwd_f32(const float* x, int R, int C, const float* w, const float* b, float eps, float momentum, float* y,
+                      float* save_mean, float* save_rstd, float* run_mean, float* run_var, cudaStream_t s) {
+  bn_train_fwd_kernel<float, float><<<(C + 31) / 32, 256, 0, s>>>(x, R, C, w, b, eps, momentum, y, save_mean, save_rstd, run_mean,
+                                                                  run_var);
+  VDK_CUDA_OK(cudaGetLastError());
+  return VDK_OK;
+}
+int launch_bn_bwd_bf16(const __nv_bfloat16* dy, const __nv_bfloat16* x, int R, int C, const float* w, const float* save_mean,
+                       const float* save_rstd, __nv_bfloat16* dx, float* dweight, float* dbias, cudaStream_t s) {
+  bn_train_bwd_kernel<__nv_bfloat16, __nv_bfloat16><<<(C + 31) / 32, 256, 0, s>>>(dy, x, R, C, w, save_mean, save_rstd, dx,
+                                                                                  dweight, dbias);
+  VDK_CUDA_OK(cudaGetLastError());
+  return VDK_OK;
+}
+int launch_bn_bwd_f32(const float* dy, const float* x, int R, int C, const float* w, const float* save_mean,
+                      const float* save_rstd, float* dx, float* dweight, float* dbias, cudaStream_t s) {
+  bn_train_bwd_kernel<float, float><<<(C + 31) / 32, 256, 0, s>>>(dy, x, R, C, w, save_mean, save_rstd, dx, dweight, dbias);
+  VDK_CUDA_OK(cudaGetLastError());
+  return VDK_OK;
+}
+int launch_add_f32(float* dst, const float* src, int64_t n, cudaStream_t s) {
+  add_f32_kernel<<<blocks_for(n), 256, 0, s>>>(dst, src, n);
+  VDK_CUDA_OK(cudaGetLastError());
+  return VDK_OK;
+}
+
+}  // namespace vdk
