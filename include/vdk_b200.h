@@ -103,6 +103,9 @@ typedef struct vdk_convnext_block {
   const void* fc2_w;  /* [C, 4C] bf16 */
   const float* fc2_b; /* [C] */
   const float* gamma; /* [C] layer scale */
+  /* training only (may be NULL for inference): */
+  const float* dw_w_flip; /* [49][C] taps in reverse order (backward-data of the depthwise conv) */
+  const void* fc2_wg;     /* [C, 4C] bf16: gamma[c] * fc2.weight[c, :] (dgrad through layer scale) */
 } vdk_convnext_block;
 
 typedef struct vdk_convnext_down {
@@ -137,6 +140,84 @@ int vdk_dwconv7_ln(const void* x, int batch, int H, int W, int C, const float* w
                    const float* ln_w, const float* ln_b, float eps, void* y, void* stream);
 int vdk_layernorm_patchify(const void* x, int batch, int H, int W, int C, const float* ln_w, const float* ln_b,
                            float eps, int patch, void* out, void* stream);
+
+/* ---- ConvNeXt training forward / backward -------------------------------------------------- */
+/* fp32 tensors in timm's own layouts (device pointers): the master parameters, or — same struct — their gradients.
+ * Replaces the train-mode forward of TimmWrapper (timm_wrapper.py:51-54, BatchNorm batch statistics at :34,37) and
+ * its autograd backward, i.e. `scaler.scale(loss).backward()` at engine/procedure/train.py:206. */
+typedef struct vdk_convnext_block_tensors {
+  float* dw_w;  /* conv_dw.weight [C,1,7,7] */
+  float* dw_b;
+  float* ln_w;  /* norm.weight */
+  float* ln_b;
+  float* fc1_w; /* mlp.fc1.weight [4C,C] */
+  float* fc1_b;
+  float* fc2_w; /* mlp.fc2.weight [C,4C] */
+  float* fc2_b;
+  float* gamma;
+} vdk_convnext_block_tensors;
+typedef struct vdk_convnext_down_tensors {
+  float* ln_w;
+  float* ln_b;
+  float* conv_w; /* downsample.1.weight [Cout,Cin,2,2] */
+  float* conv_b;
+} vdk_convnext_down_tensors;
+typedef struct vdk_convnext_tensors {
+  float* stem_w; /* stem.0.weight [C0,3,4,4] */
+  float* stem_b;
+  float* stem_ln_w;
+  float* stem_ln_b;
+  vdk_convnext_down_tensors down[4];
+  vdk_convnext_block_tensors blocks[VDK_CONVNEXT_MAX_BLOCKS];
+  float* head_ln_w;
+  float* head_ln_b;
+  float* bn2_w; /* output_layer.0 (BatchNorm2d) */
+  float* bn2_b;
+  float* bn2_running_mean;
+  float* bn2_running_var;
+  float* lin_w; /* output_layer.2.weight [F, C3*h*w] in timm's (c,h,w) flatten order */
+  float* lin_b;
+  float* bn1_w; /* output_layer.3 (BatchNorm1d) */
+  float* bn1_b;
+  float* bn1_running_mean;
+  float* bn1_running_var;
+} vdk_convnext_tensors;
+
+/* Refreshes the bf16 / permuted kernel-layout weights of `net` (whose pointer fields address caller-allocated
+ * buffers) from the fp32 masters: stem_w, down[].conv_w, blocks[].{dw_w, fc1_w, fc2_w, fc2_wg}, neck_w (un-folded,
+ * (h,w,c) order).  fp32 vectors (biases, norms, gamma) are used in place: point net's fields at the masters.
+ * vdk_convnext_pack_flip then derives blocks[].dw_w_flip. */
+int vdk_convnext_pack(const vdk_convnext_tensors* params, vdk_convnext_net* net, void* stream);
+int vdk_convnext_pack_flip(const vdk_convnext_net* net, void* stream);
+size_t vdk_convnext_train_workspace_bytes(const vdk_convnext_net* net, int batch);
+/* images fp32 NCHW -> out_feats fp32 [batch, feat_dim] (NOT normalised: the head normalises).  Saves activations in
+ * `workspace` for the backward; updates the BatchNorm running statistics in `params` with `bn_momentum`. */
+int vdk_convnext_train_forward(const vdk_convnext_net* net, const vdk_convnext_tensors* params, const float* images,
+                               int batch, float bn_momentum, float* out_feats, void* workspace, size_t workspace_bytes,
+                               void* stream);
+/* d_feats fp32 [batch, feat_dim] -> gradients ACCUMULATED (+=) into `grads` (same struct, timm layouts). */
+int vdk_convnext_train_backward(const vdk_convnext_net* net, const vdk_convnext_tensors* params,
+                                const vdk_convnext_tensors* grads, const float* d_feats, int batch, void* workspace,
+                                size_t workspace_bytes, void* stream);
+
+/* Building blocks of the backward, exported for unit parity tests (NHWC bf16 activations, fp32 parameter grads +=):
+ *   vdk_dwconv7             mode 0: LayerNorm_C(dwconv7(x)+bias) (rstd_out optional); mode 1: dwconv7(x) with `w49` (+addend)
+ *                           — with reversed taps this is the depthwise backward-data pass
+ *   vdk_dwconv7_wgrad       dw49[tap][c] += sum dconv * shifted x; dbias[c] += sum dconv
+ *   vdk_layernorm_bwd       LayerNorm backward from the saved OUTPUT y and 1/sigma (patch = 2: through the 2x2 regrouping)
+ *   vdk_batchnorm_train_*   BatchNorm over the rows of [rows, C] with batch statistics (running stats updated) */
+int vdk_dwconv7(int mode, const void* x, int batch, int H, int W, int C, const float* w49, const float* bias,
+                const float* ln_w, const float* ln_b, float eps, void* y, float* rstd_out, const void* addend, void* stream);
+int vdk_dwconv7_wgrad(const void* x, const void* dconv, int batch, int H, int W, int C, float* dw49, float* dbias,
+                      void* stream);
+int vdk_layernorm_bwd(const void* dy, const void* y, const float* rstd, int batch, int H, int W, int C, const float* ln_w,
+                      const float* ln_b, int patch, void* dx, const void* addend, float* dgamma, float* dbeta, void* stream);
+int vdk_batchnorm_train_fwd(const void* x, int rows, int C, int is_bf16, const float* weight, const float* bias, float eps,
+                            float momentum, void* y, float* save_mean, float* save_rstd, float* running_mean,
+                            float* running_var, void* stream);
+int vdk_batchnorm_train_bwd(const void* dy, const void* x, int rows, int C, int is_bf16, const float* weight,
+                            const float* save_mean, const float* save_rstd, void* dx, float* dweight, float* dbias,
+                            void* stream);
 
 size_t vdk_convnext_workspace_bytes(const vdk_convnext_net* net, int batch);
 /* images: fp32 NCHW [batch,3,S,S] (what the reference's DataLoader yields); embeddings: fp32 [batch, feat_dim],

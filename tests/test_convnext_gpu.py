@@ -119,5 +119,5 @@ def test_backbone_factory_surface(lib):
     with pytest.raises(ValueError):
         BackboneFactory({"resnet": {}}).get_backbone()
     with pytest.raises(RuntimeError):
-        m.train()
-        m(torch.zeros(1, 3, 64, 64, device="cuda"))
+        m.eval()
+        m(torch.zeros(1, 3, 64, 64))  # CPU tensors: there is no CPU fallback

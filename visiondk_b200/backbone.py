@@ -93,7 +93,28 @@ class ConvNeXtParams(nn.Module):
 
 
 class _BlockC(C.Structure):
+    _fields_ = [(n, C.c_void_p) for n in ("dw_w", "dw_b", "ln_w", "ln_b", "fc1_w", "fc1_b", "fc2_w", "fc2_b", "gamma",
+                                          "dw_w_flip", "fc2_wg")]
+
+
+class _BlockTensorsC(C.Structure):
     _fields_ = [(n, C.c_void_p) for n in ("dw_w", "dw_b", "ln_w", "ln_b", "fc1_w", "fc1_b", "fc2_w", "fc2_b", "gamma")]
+
+
+class _DownTensorsC(C.Structure):
+    _fields_ = [(n, C.c_void_p) for n in ("ln_w", "ln_b", "conv_w", "conv_b")]
+
+
+class ConvNeXtTensorsC(C.Structure):
+    """vdk_convnext_tensors: fp32 tensors in timm layouts (parameters, or their gradients)."""
+    _fields_ = [
+        ("stem_w", C.c_void_p), ("stem_b", C.c_void_p), ("stem_ln_w", C.c_void_p), ("stem_ln_b", C.c_void_p),
+        ("down", _DownTensorsC * 4), ("blocks", _BlockTensorsC * 64),
+        ("head_ln_w", C.c_void_p), ("head_ln_b", C.c_void_p),
+        ("bn2_w", C.c_void_p), ("bn2_b", C.c_void_p), ("bn2_running_mean", C.c_void_p), ("bn2_running_var", C.c_void_p),
+        ("lin_w", C.c_void_p), ("lin_b", C.c_void_p),
+        ("bn1_w", C.c_void_p), ("bn1_b", C.c_void_p), ("bn1_running_mean", C.c_void_p), ("bn1_running_var", C.c_void_p),
+    ]
 
 
 class _DownC(C.Structure):
@@ -129,14 +150,14 @@ class TimmWrapper(nn.Module):
         self._packed: Optional[Dict] = None
         self._packed_key = None
         self._ws = None
+        self._train = None
         if pretrained:
             self._load_pretrained(model_name)
 
     # ---- reference surface ---------------------------------------------------------------------
     def forward(self, x: torch.Tensor) -> torch.Tensor:
         if self.training:
-            raise RuntimeError("visiondk_b200.TimmWrapper: the training forward/backward kernels are not built yet; "
-                               "call .eval() for the embedding-extraction path")
+            return _ConvNeXtTrainFn.apply(self, x, *self._ordered_params())
         return self.embed(x, l2_normalize=False)
 
     # ---- B200 path -------------------------------------------------------------------------------
@@ -160,6 +181,133 @@ class TimmWrapper(nn.Module):
                                                 self._ws.data_ptr(), self._ws.numel(), _lib.stream_ptr()),
                        "vdk_convnext_forward")
         return out
+
+    # ---- training path (csrc/convnext_train.cu) ------------------------------------------------------
+    def _ordered_params(self):
+        return [p for _, p in self.named_parameters()]
+
+    def _tensors_struct(self, get) -> ConvNeXtTensorsC:
+        """vdk_convnext_tensors whose pointers are `get(name)` for every parameter / BN buffer name."""
+        t = ConvNeXtTensorsC()
+        t.stem_w, t.stem_b = get("model.stem.0.weight"), get("model.stem.0.bias")
+        t.stem_ln_w, t.stem_ln_b = get("model.stem.1.weight"), get("model.stem.1.bias")
+        bi = 0
+        for si, depth in enumerate(self.model.depths):
+            if si > 0:
+                d = t.down[si]
+                d.ln_w, d.ln_b = get(f"model.stages.{si}.downsample.0.weight"), get(f"model.stages.{si}.downsample.0.bias")
+                d.conv_w, d.conv_b = get(f"model.stages.{si}.downsample.1.weight"), get(f"model.stages.{si}.downsample.1.bias")
+            for j in range(depth):
+                pre, b = f"model.stages.{si}.blocks.{j}", t.blocks[bi]
+                b.dw_w, b.dw_b = get(f"{pre}.conv_dw.weight"), get(f"{pre}.conv_dw.bias")
+                b.ln_w, b.ln_b = get(f"{pre}.norm.weight"), get(f"{pre}.norm.bias")
+                b.fc1_w, b.fc1_b = get(f"{pre}.mlp.fc1.weight"), get(f"{pre}.mlp.fc1.bias")
+                b.fc2_w, b.fc2_b = get(f"{pre}.mlp.fc2.weight"), get(f"{pre}.mlp.fc2.bias")
+                b.gamma = get(f"{pre}.gamma")
+                bi += 1
+        t.head_ln_w, t.head_ln_b = get("model.head.norm.weight"), get("model.head.norm.bias")
+        t.bn2_w, t.bn2_b = get("output_layer.0.weight"), get("output_layer.0.bias")
+        t.bn2_running_mean, t.bn2_running_var = get("output_layer.0.running_mean"), get("output_layer.0.running_var")
+        t.lin_w, t.lin_b = get("output_layer.2.weight"), get("output_layer.2.bias")
+        t.bn1_w, t.bn1_b = get("output_layer.3.weight"), get("output_layer.3.bias")
+        t.bn1_running_mean, t.bn1_running_var = get("output_layer.3.running_mean"), get("output_layer.3.running_var")
+        return t
+
+    def _train_state(self, device):
+        """Packed-weight buffers (allocated once) + the net struct whose fp32 vector fields alias the master params."""
+        st = self._train
+        if st is not None and st["device"] == device:
+            return st
+        m = self.model
+        bf = lambda *shape: torch.empty(shape, dtype=torch.bfloat16, device=device)
+        f32 = lambda *shape: torch.empty(shape, dtype=torch.float32, device=device)
+        hw = self.image_size // 32
+        bufs = {"stem_w": bf(m.dims[0], 48), "neck_w": bf(self.feat_dim, hw * hw * m.dims[-1]), "blocks": [], "down": {}}
+        for si, (d, c) in enumerate(zip(m.depths, m.dims)):
+            if si > 0:
+                bufs["down"][si] = bf(c, 4 * m.dims[si - 1])
+            for _ in range(d):
+                bufs["blocks"].append({"dw_w": f32(49, c), "dw_w_flip": f32(49, c), "fc1_w": bf(4 * c, c), "fc2_w": bf(c, 4 * c),
+                                       "fc2_wg": bf(c, 4 * c)})
+        self._train = {"device": device, "bufs": bufs, "ws": None, "gflat": None}
+        return self._train
+
+    def _train_structs(self, device):
+        st = self._train_state(device)
+        named = dict(self.named_parameters())
+        named.update(dict(self.named_buffers()))
+        for n, t in named.items():
+            if t.is_floating_point() and (t.device != device or t.dtype != torch.float32 or not t.is_contiguous()):
+                raise RuntimeError(f"{n}: training needs contiguous fp32 parameters on {device}")
+        params = self._tensors_struct(lambda n: named[n].data_ptr())
+        bufs, m = st["bufs"], self.model
+        net = ConvNeXtNetC()
+        net.image_size, net.feat_dim = self.image_size, self.feat_dim
+        for i in range(4):
+            net.depths[i], net.dims[i] = m.depths[i], m.dims[i]
+        net.stem_w = bufs["stem_w"].data_ptr()
+        net.stem_b, net.stem_ln_w, net.stem_ln_b = params.stem_b, params.stem_ln_w, params.stem_ln_b
+        bi = 0
+        for si, depth in enumerate(m.depths):
+            if si > 0:
+                net.down[si].ln_w, net.down[si].ln_b = params.down[si].ln_w, params.down[si].ln_b
+                net.down[si].conv_w, net.down[si].conv_b = bufs["down"][si].data_ptr(), params.down[si].conv_b
+            for _ in range(depth):
+                b, pb, bb = net.blocks[bi], params.blocks[bi], bufs["blocks"][bi]
+                b.dw_w, b.dw_w_flip = bb["dw_w"].data_ptr(), bb["dw_w_flip"].data_ptr()
+                b.fc1_w, b.fc2_w, b.fc2_wg = bb["fc1_w"].data_ptr(), bb["fc2_w"].data_ptr(), bb["fc2_wg"].data_ptr()
+                b.dw_b, b.ln_w, b.ln_b, b.fc1_b, b.fc2_b, b.gamma = pb.dw_b, pb.ln_w, pb.ln_b, pb.fc1_b, pb.fc2_b, pb.gamma
+                bi += 1
+        net.head_ln_w, net.head_ln_b = params.head_ln_w, params.head_ln_b
+        net.neck_w, net.neck_b = bufs["neck_w"].data_ptr(), params.lin_b
+        return st, net, params
+
+    def _train_forward(self, x: torch.Tensor) -> torch.Tensor:
+        lib = _lib.load()
+        if x.device.type != "cuda":
+            raise RuntimeError("visiondk_b200.TimmWrapper runs on CUDA (sm_100a) only; there is no CPU fallback")
+        x = x.contiguous().float()
+        B = x.shape[0]
+        st, net, params = self._train_structs(x.device)
+        need = lib.vdk_convnext_train_workspace_bytes(C.byref(net), B)
+        if st["ws"] is None or st["ws"].numel() < need:
+            st["ws"] = torch.empty((need,), dtype=torch.uint8, device=x.device)
+        out = torch.empty((B, self.feat_dim), dtype=torch.float32, device=x.device)
+        bn = self.output_layer[0]
+        with torch.cuda.device(x.device):
+            s = _lib.stream_ptr()
+            _lib.check(lib.vdk_convnext_pack(C.byref(params), C.byref(net), s), "vdk_convnext_pack")
+            _lib.check(lib.vdk_convnext_pack_flip(C.byref(net), s), "vdk_convnext_pack_flip")
+            _lib.check(lib.vdk_convnext_train_forward(C.byref(net), C.byref(params), x.data_ptr(), B, float(bn.momentum),
+                                                      out.data_ptr(), st["ws"].data_ptr(), st["ws"].numel(), s),
+                       "vdk_convnext_train_forward")
+        for m in (self.output_layer[0], self.output_layer[3]):
+            m.num_batches_tracked += 1
+        st["last"] = (net, params, B)
+        return out
+
+    def _train_backward(self, dout: torch.Tensor):
+        lib = _lib.load()
+        st = self._train
+        net, params, B = st["last"]
+        plist = list(self.named_parameters())
+        total = sum(p.numel() for _, p in plist)
+        if st["gflat"] is None or st["gflat"].numel() != total:
+            st["gflat"] = torch.empty((total,), dtype=torch.float32, device=dout.device)
+        gflat = st["gflat"]
+        gflat.zero_()
+        offs, off = {}, 0
+        for n, p in plist:
+            offs[n] = off
+            off += p.numel()
+        base = gflat.data_ptr()
+        grads = self._tensors_struct(lambda n: (base + 4 * offs[n]) if n in offs else 0)
+        dout = dout.contiguous().float()
+        with torch.cuda.device(dout.device):
+            _lib.check(lib.vdk_convnext_train_backward(C.byref(net), C.byref(params), C.byref(grads), dout.data_ptr(), B,
+                                                       st["ws"].data_ptr(), st["ws"].numel(), _lib.stream_ptr()),
+                       "vdk_convnext_train_backward")
+        return [gflat[offs[n]:offs[n] + p.numel()].view_as(p) for n, p in plist]
 
     # ---- weight packing --------------------------------------------------------------------------
     def _version_key(self, device):
@@ -232,6 +380,20 @@ class TimmWrapper(nn.Module):
             self.model.load_state_dict(sd, strict=True)
         else:
             warnings.warn(f"pretrained weights for '{model_name}' not found (set VDK_PRETRAINED_DIR); using random init")
+
+
+class _ConvNeXtTrainFn(torch.autograd.Function):
+    """Train-mode forward/backward of the whole backbone + neck as one autograd node (csrc/convnext_train.cu)."""
+
+    @staticmethod
+    def forward(ctx, module, x, *params):
+        ctx.module = module
+        return module._train_forward(x)
+
+    @staticmethod
+    def backward(ctx, dout):
+        grads = ctx.module._train_backward(dout)
+        return (None, None, *grads)
 
 
 class BackboneFactory:

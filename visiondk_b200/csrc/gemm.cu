@@ -35,6 +35,7 @@ struct GemmParams {
   int a_mn, b_mn;  // operand stored with the contraction index as the slow dimension ([K,M] / [K,N] row-major)
   long long split_stride;  // > 0: split s writes its partial tile to D + s*split_stride with plain stores (deterministic)
   int aux_out;  // GELU only: also store the pre-activation (acc + bias) through map_d2 (saved for the backward)
+  int partial_out;  // the caller asked for split-K: raw fp32 partials are added / slab-stored even if one split remains
 };
 
 template <int BN>
@@ -458,7 +459,7 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
           tmem_ld_32x32b_x32(tacc + c * 32, r);
           tmem_ld_wait();
           const int col0 = n0 + c * 32;
-          if (row < p.M && col0 < p.N && p.split_k > 1) {
+          if (row < p.M && col0 < p.N && p.partial_out) {
             // split-K: raw fp32 partial sums.  With a slab stride every split owns its own copy of D (plain stores,
             // the consumer adds the slabs in a fixed order: deterministic); otherwise they are atomically added
             // into a D the caller zeroed.
@@ -582,7 +583,7 @@ int gemm_run(const vdk_gemm_desc& g, cudaStream_t s) {
   }
   if (g.split_stride != 0)
     VDK_REQUIRE(g.split_stride >= (long long)g.M * g.ldd && g.split_stride % 4 == 0, "vdk_gemm: split_stride must cover one [M,ldd] slab");
-  if (split > 1)
+  if (g.split_k > 1)
     VDK_REQUIRE(g.out_dtype == VDK_DTYPE_FP32 && g.epilogue == VDK_EPI_NONE && !g.bias,
                 "vdk_gemm: split_k > 1 needs fp32 output, no bias and no epilogue (partials are atomically added)");
 
@@ -600,7 +601,7 @@ int gemm_run(const vdk_gemm_desc& g, cudaStream_t s) {
   rc = g.trans_b ? make_tma_2d_16bit(&mb, g.B, (uint64_t)g.K, (uint64_t)g.N, (uint64_t)g.ldb, kBK, 64)
                  : make_tma_2d_16bit(&mb, g.B, (uint64_t)g.N, (uint64_t)g.K, (uint64_t)g.ldb, BN, kBK);
   if (rc != VDK_OK) return rc;
-  const int tma_store = (g.out_dtype != VDK_DTYPE_FP32 && split == 1) ? 1 : 0;
+  const int tma_store = (g.out_dtype != VDK_DTYPE_FP32 && g.split_k <= 1) ? 1 : 0;
   CUtensorMap md = ma;  // placeholder when unused
   if (tma_store) {
     rc = make_tma_2d_16bit(&md, g.D, (uint64_t)g.M, (uint64_t)g.N, (uint64_t)g.ldd, kBM, 64);
@@ -618,8 +619,8 @@ int gemm_run(const vdk_gemm_desc& g, cudaStream_t s) {
     if (rc != VDK_OK) return rc;
   }
   GemmParams p{g.M, g.N, g.K, g.D, g.ldd, g.bias, g.gamma, g.beta, g.residual, g.ldr, g.out_dtype, g.epilogue,
-               g.ln_eps, split, tma_store, g.trans_a ? 1 : 0, g.trans_b ? 1 : 0, split > 1 ? (long long)g.split_stride : 0ll,
-               aux_out};
+               g.ln_eps, split, tma_store, g.trans_a ? 1 : 0, g.trans_b ? 1 : 0, g.split_k > 1 ? (long long)g.split_stride : 0ll,
+               aux_out, (g.split_k > 1) ? 1 : 0};
   const bool bf = g.in_dtype == VDK_DTYPE_BF16;
   if (wide) return bf ? launch_gemm<256, true>(ma, mb, md, mr, md2, p, s) : launch_gemm<256, false>(ma, mb, md, mr, md2, p, s);
   return bf ? launch_gemm<128, true>(ma, mb, md, mr, md2, p, s) : launch_gemm<128, false>(ma, mb, md, mr, md2, p, s);

@@ -544,3 +544,56 @@ int launch_add_f32(float* dst, const float* src, int64_t n, cudaStream_t s) {
 }
 
 }  // namespace vdk
+
+// ---- C-ABI exports of the building blocks (unit parity tests; the product calls them through convnext_train.cu) ----
+using namespace vdk;
+
+extern "C" int vdk_layernorm_bwd(const void* dy, const void* y, const float* rstd, int batch, int H, int W, int C,
+                                 const float* ln_w, const float* ln_b, int patch, void* dx, const void* addend, float* dgamma,
+                                 float* dbeta, void* stream) {
+  VDK_REQUIRE(dy && y && rstd && ln_w && ln_b && dx && dgamma && dbeta, "vdk_layernorm_bwd: null operand");
+  VDK_REQUIRE(patch == 1 || (patch == 2 && H % 2 == 0 && W % 2 == 0), "vdk_layernorm_bwd: patch must be 1 or 2");
+  return launch_ln_bwd(reinterpret_cast<const __nv_bfloat16*>(dy), reinterpret_cast<const __nv_bfloat16*>(y), rstd, batch, H, W, C,
+                       ln_w, ln_b, patch, reinterpret_cast<__nv_bfloat16*>(dx), reinterpret_cast<const __nv_bfloat16*>(addend),
+                       dgamma, dbeta, reinterpret_cast<cudaStream_t>(stream));
+}
+
+extern "C" int vdk_dwconv7(int mode, const void* x, int batch, int H, int W, int C, const float* w49, const float* bias,
+                           const float* ln_w, const float* ln_b, float eps, void* y, float* rstd_out, const void* addend,
+                           void* stream) {
+  VDK_REQUIRE(x && y && w49 && (mode == 1 || (bias && ln_w && ln_b)), "vdk_dwconv7: null operand");
+  return launch_dwconv7(mode, reinterpret_cast<const __nv_bfloat16*>(x), batch, H, W, C, w49, bias, ln_w, ln_b, eps,
+                        reinterpret_cast<__nv_bfloat16*>(y), rstd_out, reinterpret_cast<const __nv_bfloat16*>(addend),
+                        reinterpret_cast<cudaStream_t>(stream));
+}
+
+extern "C" int vdk_dwconv7_wgrad(const void* x, const void* dconv, int batch, int H, int W, int C, float* dw49, float* dbias,
+                                 void* stream) {
+  VDK_REQUIRE(x && dconv && dw49 && dbias, "vdk_dwconv7_wgrad: null operand");
+  return launch_dwconv7_wgrad(reinterpret_cast<const __nv_bfloat16*>(x), reinterpret_cast<const __nv_bfloat16*>(dconv), batch, H, W,
+                              C, dw49, dbias, reinterpret_cast<cudaStream_t>(stream));
+}
+
+extern "C" int vdk_batchnorm_train_fwd(const void* x, int rows, int C, int is_bf16, const float* weight, const float* bias,
+                                       float eps, float momentum, void* y, float* save_mean, float* save_rstd,
+                                       float* running_mean, float* running_var, void* stream) {
+  VDK_REQUIRE(x && y && weight && bias && save_mean && save_rstd && rows > 1, "vdk_batchnorm_train_fwd: bad arguments");
+  cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
+  if (is_bf16)
+    return launch_bn_fwd_bf16(reinterpret_cast<const __nv_bfloat16*>(x), rows, C, weight, bias, eps, momentum,
+                              reinterpret_cast<__nv_bfloat16*>(y), save_mean, save_rstd, running_mean, running_var, s);
+  return launch_bn_fwd_f32(reinterpret_cast<const float*>(x), rows, C, weight, bias, eps, momentum, reinterpret_cast<float*>(y),
+                           save_mean, save_rstd, running_mean, running_var, s);
+}
+
+extern "C" int vdk_batchnorm_train_bwd(const void* dy, const void* x, int rows, int C, int is_bf16, const float* weight,
+                                       const float* save_mean, const float* save_rstd, void* dx, float* dweight, float* dbias,
+                                       void* stream) {
+  VDK_REQUIRE(dy && x && weight && save_mean && save_rstd && dx && dweight && dbias, "vdk_batchnorm_train_bwd: null operand");
+  cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
+  if (is_bf16)
+    return launch_bn_bwd_bf16(reinterpret_cast<const __nv_bfloat16*>(dy), reinterpret_cast<const __nv_bfloat16*>(x), rows, C, weight,
+                              save_mean, save_rstd, reinterpret_cast<__nv_bfloat16*>(dx), dweight, dbias, s);
+  return launch_bn_bwd_f32(reinterpret_cast<const float*>(dy), reinterpret_cast<const float*>(x), rows, C, weight, save_mean,
+                           save_rstd, reinterpret_cast<float*>(dx), dweight, dbias, s);
+}
