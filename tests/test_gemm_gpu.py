@@ -108,7 +108,7 @@ def test_gemm_rejects_bad_arguments(lib):
     a = torch.zeros(8, 8, device="cuda", dtype=torch.bfloat16)
     d = torch.zeros(8, 8, device="cuda")
     rc = lib.vdk_gemm_tn(a.data_ptr(), a.data_ptr(), d.data_ptr(), 8, 7, 8, 8, 8, 8, 0, 2, 0, 0, 0, 0, 0, 0)
-    assert rc == _lib.VDK_ERR_INVALID and "multiples of 8" in _lib.last_error()
+    assert rc == _lib.VDK_ERR_INVALID and "multiple of 8" in _lib.last_error()
 
 
 @pytest.mark.parametrize("ta,tb", [(1, 0), (0, 1), (1, 1)])

@@ -287,26 +287,36 @@ class TimmWrapper(nn.Module):
         return out
 
     def _train_backward(self, dout: torch.Tensor):
+        """Gradients of every parameter.  When the parameters already own fp32 `.grad` buffers (the fused optimizer
+        re-points them into its flat gradient buffer) the kernels accumulate straight into those and autograd receives
+        None; otherwise the gradients are produced in a scratch buffer and returned."""
         lib = _lib.load()
         st = self._train
         net, params, B = st["last"]
         plist = list(self.named_parameters())
-        total = sum(p.numel() for _, p in plist)
-        if st["gflat"] is None or st["gflat"].numel() != total:
-            st["gflat"] = torch.empty((total,), dtype=torch.float32, device=dout.device)
-        gflat = st["gflat"]
-        gflat.zero_()
-        offs, off = {}, 0
-        for n, p in plist:
-            offs[n] = off
-            off += p.numel()
-        base = gflat.data_ptr()
-        grads = self._tensors_struct(lambda n: (base + 4 * offs[n]) if n in offs else 0)
+        direct = all(p.grad is not None and p.grad.dtype == torch.float32 and p.grad.is_contiguous() and
+                     p.grad.device == dout.device for _, p in plist)
+        if direct:
+            ptrs = {n: p.grad.data_ptr() for n, p in plist}
+        else:
+            total = sum(p.numel() for _, p in plist)
+            if st["gflat"] is None or st["gflat"].numel() != total:
+                st["gflat"] = torch.empty((total,), dtype=torch.float32, device=dout.device)
+            gflat = st["gflat"]
+            gflat.zero_()
+            offs, off = {}, 0
+            for n, p in plist:
+                offs[n] = off
+                off += p.numel()
+            ptrs = {n: gflat.data_ptr() + 4 * offs[n] for n, _ in plist}
+        grads = self._tensors_struct(lambda n: ptrs.get(n, 0))
         dout = dout.contiguous().float()
         with torch.cuda.device(dout.device):
             _lib.check(lib.vdk_convnext_train_backward(C.byref(net), C.byref(params), C.byref(grads), dout.data_ptr(), B,
                                                        st["ws"].data_ptr(), st["ws"].numel(), _lib.stream_ptr()),
                        "vdk_convnext_train_backward")
+        if direct:
+            return [None] * len(plist)
         return [gflat[offs[n]:offs[n] + p.numel()].view_as(p) for n, p in plist]
 
     # ---- weight packing --------------------------------------------------------------------------

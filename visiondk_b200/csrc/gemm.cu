@@ -546,7 +546,8 @@ int gemm_run(const vdk_gemm_desc& g, cudaStream_t s) {
   VDK_REQUIRE(g.M > 0 && g.N > 0 && g.K > 0, "vdk_gemm: empty problem M=%d N=%d K=%d", g.M, g.N, g.K);
   VDK_REQUIRE(g.in_dtype == VDK_DTYPE_BF16 || g.in_dtype == VDK_DTYPE_FP16, "vdk_gemm: in_dtype must be bf16/fp16");
   VDK_REQUIRE(g.out_dtype >= VDK_DTYPE_BF16 && g.out_dtype <= VDK_DTYPE_FP32, "vdk_gemm: bad out_dtype");
-  VDK_REQUIRE(g.N % 8 == 0 && g.K % 8 == 0, "vdk_gemm: N and K must be multiples of 8 (N=%d K=%d)", g.N, g.K);
+  // K itself is free: TMA zero-fills the contraction tail; only pitches and the output width need 16-byte granularity
+  VDK_REQUIRE(g.N % 8 == 0, "vdk_gemm: N must be a multiple of 8 (N=%d)", g.N);
   VDK_REQUIRE(g.lda >= (g.trans_a ? g.M : g.K) && g.ldb >= (g.trans_b ? g.N : g.K) && g.ldd >= g.N && g.lda % 8 == 0 &&
                   g.ldb % 8 == 0,
               "vdk_gemm: bad pitches");

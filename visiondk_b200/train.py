@@ -1,0 +1,107 @@
+"""faceX train step on B200: the reference's model container and step, same names.
+
+  FaceTrainingModel      models/faceX/face_model.py:28-54   (trainingwrapper = ModuleDict{'backbone','head'})
+  cosine_with_warm       engine/scheduler.py:47-57          (LinearLR 0.1->1 then CosineAnnealingLR, stepped per batch)
+  SeperateLayerParams    built/layer_optimizer.py:9-29      (backbone lr, head lr x10)
+  FaceTrainer.step       engine/procedure/train.py:196-215,230  (criterion∘model, backward, clip, SGD, zero_grad, EMA, LR)
+  DDP                    engine/vision_engine.py:509-510    -> one NCCL all-reduce(mean) of the flat gradient buffers
+
+All arithmetic is the sm_100a kernels: backbone forward/backward (csrc/convnext_train.cu), fused margin head + CE
+(csrc/heads.cu), fused clip + SGD + EMA (csrc/optim.cu).
+"""
+from __future__ import annotations
+
+import copy
+import math
+from typing import Optional
+
+import torch
+import torch.distributed as dist
+import torch.nn as nn
+
+from .backbone import BackboneFactory
+from .heads import HeadFactory, margin_ce_loss
+from .optim import FusedSGDClipEMA
+
+
+class FaceTrainingModel(nn.Module):
+    """models/faceX/face_model.py:28-54."""
+
+    def __init__(self, model_cfg: dict):
+        super().__init__()
+        backbone = BackboneFactory(model_cfg["backbone"]).get_backbone()
+        head = HeadFactory(model_cfg["head"]).get_head()
+        self.trainingwrapper = nn.ModuleDict({"backbone": backbone, "head": head})
+
+    def forward(self, data, label):
+        feat = self.trainingwrapper["backbone"](data)
+        return self.trainingwrapper["head"](feat, label)
+
+    def loss(self, data, label, label_smooth: float = 0.0):
+        """criterion(self(data, label), label) with criterion = CrossEntropyLoss(label_smoothing), fused
+        (train.py:196: the two are only ever called together)."""
+        feat = self.trainingwrapper["backbone"](data)
+        return margin_ce_loss(self.trainingwrapper["head"], feat, label, label_smooth)
+
+
+def cosine_with_warm_lr(step: int, base_lr: float, lr0: float, warm: int, total: int, lrf_ratio: Optional[float]) -> float:
+    """Learning rate of a param group with base lr `base_lr` after `step` scheduler steps under engine/scheduler.py:47-57:
+    SequentialLR([LinearLR(0.1 -> 1, warm), CosineAnnealingLR(total - warm, eta_min = lrf * lr0)], milestones=[warm]).
+    Note eta_min is lrf * the GLOBAL lr0 for every group (the head group's base lr is 10 * lr0)."""
+    lrf = 0.1 if lrf_ratio is None else lrf_ratio
+    if warm > 0 and step < warm:
+        return base_lr * (0.1 + 0.9 * step / warm)
+    eta_min = lrf * lr0
+    t, T = step - warm, max(1, total - warm)
+    return eta_min + (base_lr - eta_min) * 0.5 * (1 + math.cos(math.pi * t / T))
+
+
+def layer_wise_groups(model: FaceTrainingModel, layer_wise: bool, lr: float):
+    """built/layer_optimizer.py:9-29."""
+    if not layer_wise:
+        return [{"params": list(model.parameters()), "lr": lr}]
+    return [{"params": list(model.trainingwrapper["backbone"].parameters()), "lr": lr},
+            {"params": list(model.trainingwrapper["head"].parameters()), "lr": lr * 10}]
+
+
+class FaceTrainer:
+    """The per-batch body of Trainer.train_one_epoch_face (engine/procedure/train.py:217-233) on B200."""
+
+    def __init__(self, model: FaceTrainingModel, lr0: float, momentum: float, weight_decay: float, label_smooth: float = 0.0,
+                 layer_wise: bool = True, warm_steps: int = 0, total_steps: int = 1, lrf_ratio: Optional[float] = None,
+                 use_ema: bool = True, max_norm: float = 10.0):
+        self.model = model
+        self.label_smooth = label_smooth
+        self.ema = copy.deepcopy(model).eval() if use_ema else None  # models/ema.py:20-26
+        if self.ema is not None:
+            for p in self.ema.parameters():
+                p.requires_grad_(False)
+        groups = layer_wise_groups(model, layer_wise, lr0)
+        self.base_lrs = [g["lr"] for g in groups]
+        self.opt = FusedSGDClipEMA(groups, lr=lr0, momentum=momentum, weight_decay=weight_decay, max_norm=max_norm, model=model,
+                                   ema_model=self.ema)
+        self.lr0, self.warm, self.total, self.lrf = lr0, warm_steps, total_steps, lrf_ratio
+        self.sched_step = 0
+        self._apply_lr()
+
+    def _apply_lr(self):
+        for pg, base in zip(self.opt.param_groups, self.base_lrs):
+            pg["lr"] = cosine_with_warm_lr(self.sched_step, base, self.lr0, self.warm, self.total, self.lrf)
+
+    def set_momentum(self, momentum: float):  # vision_engine.py:545-546 switches warm-up momentum -> momentum
+        for pg in self.opt.param_groups:
+            pg["momentum"] = momentum
+
+    def step(self, images: torch.Tensor, labels: torch.Tensor) -> torch.Tensor:
+        """One batch: returns the (device) loss; does not synchronise (the reference's loss.item() every step,
+        train.py:233, is a forced sync the hot path does not need)."""
+        self.model.train()
+        loss = self.model.loss(images, labels, self.label_smooth)
+        loss.backward()
+        if dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1:
+            for g in self.opt.groups:  # DDP's gradient mean, on the flat buffers (one collective per param group)
+                dist.all_reduce(g.g, op=dist.ReduceOp.AVG)
+        self.opt.step()
+        self.sched_step += 1  # scheduler.step() per batch (train.py:230)
+        self._apply_lr()
+        return loss.detach()
