@@ -49,7 +49,8 @@ def parse():
     ap.add_argument("--ng", type=int, default=NG)
     ap.add_argument("--k", type=int, default=K)
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--only", default="both", choices=["both", "extract", "retrieval"])
+    ap.add_argument("--train-batch", type=int, default=128)
+    ap.add_argument("--only", default="all", choices=["all", "both", "train", "extract", "retrieval"])
     return ap.parse_args()
 
 
@@ -113,7 +114,7 @@ def cpu_retrieval_pass(q, g, k, slice_rows=256):
     return outs
 
 
-def cpu_baselines(args, want_retrieval=True, target_s=10.0):
+def cpu_baselines(args, want_retrieval=True, want_train=False, target_s=10.0):
     import torch
     from oracle.convnext import TimmWrapperOracle
     cores = os.cpu_count() or 1
@@ -132,6 +133,32 @@ def cpu_baselines(args, want_retrieval=True, target_s=10.0):
     dt = time.perf_counter() - t0
     out["embeddings"] = {"value": n / dt, "unit": "embeddings/s", "cores": cores, "kind": "port",
                          "sample": f"{n} images (bs 64, fp32 oracle ConvNeXt-B 224 + F.normalize), {dt:.1f} s"}
+    if want_train:
+        from oracle import heads as H
+        model.train()
+        head_w = torch.nn.Parameter(H.init_head_weight(FEAT, 1000))
+        opt = torch.optim.SGD(list(model.parameters()) + [head_w], lr=0.01, momentum=0.937, weight_decay=5e-4)
+        xt, yt = torch.randn(8, 3, IMG, IMG), torch.randint(0, 1000, (8,))
+
+        def tstep():
+            loss = H.cross_entropy(H.arcface_logits(model(xt), head_w, yt, 0.35, 0.0, 32.0), yt, 0.1)
+            loss.backward()
+            torch.nn.utils.clip_grad_norm_(list(model.parameters()) + [head_w], 10.0)
+            opt.step()
+            opt.zero_grad()
+
+        tstep()
+        t0 = time.perf_counter()
+        reps = 0
+        while True:
+            tstep()
+            reps += 1
+            if time.perf_counter() - t0 > target_s or reps >= 8:
+                break
+        dt = time.perf_counter() - t0
+        out["train"] = {"value": reps * 8 / dt, "unit": "embeddings/s", "cores": cores, "kind": "port",
+                        "sample": f"{reps} train steps of 8 images (fp32 oracle fwd + ArcFace/CE + bwd + clip + SGD), {dt:.1f} s"}
+        model.eval()
     if want_retrieval:
         gen = torch.Generator().manual_seed(5)
         g = torch.nn.functional.normalize(torch.randn(args.ng, DIM, generator=gen))
@@ -152,48 +179,82 @@ def cpu_baselines(args, want_retrieval=True, target_s=10.0):
 
 def run_reference(args):
     """--impl reference: the reference's own CPU formulation on the host cores (oracle port; timm/faiss cannot be
-    installed here).  One step = a bounded sample: one bs-64 batch of embeddings."""
+    installed here).  Primary metric = the faceX train step (fwd + CE + bwd + clip + SGD + EMA of the fp32
+    oracle, engine/procedure/train.py:196-215); one step = a bounded sample of 4 images so that K steps stay within minutes."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
+    import copy
     import torch
     from oracle.convnext import TimmWrapperOracle
+    from oracle import heads as H
     cores = os.cpu_count() or 1
     torch.set_num_threads(cores)
-    model = TimmWrapperOracle(MODEL, FEAT, IMG).eval()
-    x = torch.randn(64, 3, IMG, IMG)
-    for _ in range(max(1, min(args.warmup, 2))):
-        cpu_embeddings_pass(model, x)
+    bs = 4
+    backbone = TimmWrapperOracle(MODEL, FEAT, IMG).train()
+    head_w = torch.nn.Parameter(H.init_head_weight(FEAT, 1000))
+    params = list(backbone.parameters()) + [head_w]
+    opt = torch.optim.SGD([{"params": list(backbone.parameters()), "lr": 0.01}, {"params": [head_w], "lr": 0.1}], lr=0.01,
+                          momentum=0.937, weight_decay=5e-4)
+    ema = copy.deepcopy(backbone).eval()
+    x = torch.randn(bs, 3, IMG, IMG)
+    y = torch.randint(0, 1000, (bs,))
+
+    def step():
+        logits = H.arcface_logits(backbone(x), head_w, y, 0.35, 0.0, 32.0)
+        loss = H.cross_entropy(logits, y, 0.1)
+        loss.backward()
+        torch.nn.utils.clip_grad_norm_(params, 10.0)
+        opt.step()
+        opt.zero_grad()
+        with torch.no_grad():
+            for e, p in zip(ema.state_dict().values(), backbone.state_dict().values()):
+                if e.dtype.is_floating_point:
+                    e.mul_(0.999).add_(p.detach(), alpha=0.001)
+        return float(loss)
+
+    for _ in range(max(1, min(args.warmup, 1))):
+        step()
     t0 = time.perf_counter()
     for _ in range(args.steps):
-        cpu_embeddings_pass(model, x)
+        step()
     dt = time.perf_counter() - t0
-    value = args.steps * 64 / dt
+    value = args.steps * bs / dt
+    # secondary: inference embeddings and retrieval, bounded samples
+    backbone.eval()
+    xe = torch.randn(16, 3, IMG, IMG)
+    cpu_embeddings_pass(backbone, xe[:4])
+    t0 = time.perf_counter()
+    cpu_embeddings_pass(backbone, xe)
+    evalue = 16 / (time.perf_counter() - t0)
     gen = torch.Generator().manual_seed(5)
     g = torch.nn.functional.normalize(torch.randn(args.ng, DIM, generator=gen))
     q = torch.nn.functional.normalize(torch.randn(256, DIM, generator=gen))
     cpu_retrieval_pass(q, g, args.k)
     t0 = time.perf_counter()
-    reps = max(1, min(args.steps, 5))
+    reps = 3
     for _ in range(reps):
         cpu_retrieval_pass(q, g, args.k)
-    rdt = time.perf_counter() - t0
-    rvalue = reps * 256 * args.ng / rdt
+    rvalue = reps * 256 * args.ng / (time.perf_counter() - t0)
+    zero = {"h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
     line = {
-        "impl": "reference", "metric": "embeddings/sec (ConvNeXt-B 224^2, CBIR extract)", "value": value,
+        "impl": "reference", "metric": "embeddings/sec (ConvNeXt-B 224^2 faceX ArcFace train step)", "value": value,
         "unit": "embeddings/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": dt / args.steps * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "f32", "data": "synthetic",
-        "config": {"workload": "CBIR eval extract: ConvNeXt-B 224^2 -> 512-d, L2-normalised",
-                   "note": "reference CPU path restated (oracle); each step = one bs-64 batch"},
+        "config": {"workload": "faceX train step: ConvNeXt-B 224^2 + ArcFace(C=1000) + CE + clip + SGD + EMA",
+                   "note": "reference CPU path restated (fp32 oracle + torch.optim.SGD); each step = a bounded sample of 4 images"},
         "cpu_baseline": {"value": value, "unit": "embeddings/s", "cores": cores, "kind": "port",
-                         "sample": "each step = 64 images (bs 64) through the fp32 oracle ConvNeXt-B + F.normalize"},
-        "e2e": {"value": value, "unit": "embeddings/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
-        "gpu_launches": 0,
+                         "sample": "each step = 4 images through fwd + ArcFace/CE + bwd + clip + SGD + EMA (fp32 oracle)"},
+        "e2e": dict(value=value, unit="embeddings/s", **zero), "gpu_launches": 0,
+        "extract": {"metric": "embeddings/sec (ConvNeXt-B 224^2, CBIR extract, inference)", "value": evalue,
+                    "unit": "embeddings/s", "cpu_baseline": {"value": evalue, "unit": "embeddings/s", "cores": cores,
+                                                             "kind": "port", "sample": "16 images, bs 16, fp32 oracle"},
+                    "e2e": dict(value=evalue, unit="embeddings/s", **zero)},
         "retrieval": {"metric": "query x gallery pairs/sec (cosine top-100, 512-d)", "value": rvalue, "unit": "pairs/s",
                       "cpu_baseline": {"value": rvalue, "unit": "pairs/s", "cores": cores, "kind": "port",
                                        "sample": f"{reps} x (256 queries x {args.ng} gallery, q@g.T + top-{args.k})"},
-                      "e2e": {"value": rvalue, "unit": "pairs/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}},
+                      "e2e": dict(value=rvalue, unit="pairs/s", **zero)},
     }
     print(json.dumps(line), flush=True)
 
@@ -338,6 +399,63 @@ def bench_extract(ctx, args):
             "h2d": B * 3 * IMG * IMG * 4, "d2h": B * FEAT * 4, "batch": B}
 
 
+def bench_train(ctx, args):
+    """BASELINE configs[1]: ConvNeXt-B 224^2 faceX ArcFace (C=1000) train step, bf16 activations / fp32 master weights,
+    per-GPU batch fixed (weak scaling), DDP = one NCCL all-reduce(mean) of the flat gradient buffers per step."""
+    import torch
+    from visiondk_b200.train import FaceTrainingModel, FaceTrainer
+    B = args.train_batch
+    torch.manual_seed(0)
+    cfg = {"backbone": {f"timm-{MODEL}": {"pretrained": False, "image_size": IMG, "feat_dim": FEAT}},
+           "head": {"arcface": {"feat_dim": FEAT, "num_class": 1000, "margin_arc": 0.35, "margin_am": 0.0, "scale": 32}}}
+    model = FaceTrainingModel(cfg).to(ctx.dev)
+    with torch.no_grad():
+        for n, p in model.named_parameters():
+            if n.endswith("gamma"):
+                p.fill_(0.1)
+    trainer = FaceTrainer(model, lr0=0.01, momentum=0.937, weight_decay=5e-4, label_smooth=0.1, layer_wise=True, warm_steps=0,
+                          total_steps=100000, use_ema=(ctx.rank == 0))  # EMA on rank 0 only (vision_engine.py:165)
+    gen = torch.Generator(device=ctx.dev).manual_seed(100 + ctx.rank)
+    pool = [torch.randn(B, 3, IMG, IMG, device=ctx.dev, generator=gen) for _ in range(2)]
+    labels = [torch.randint(0, 1000, (B,), device=ctx.dev, generator=gen) for _ in range(2)]
+    state = {"i": 0}
+
+    def step_dev():
+        i = state["i"] & 1
+        state["i"] += 1
+        return trainer.step(pool[i], labels[i])
+
+    ms = timed(ctx, step_dev, args.steps, args.warmup)
+    value = ctx.world * B / (ms * 1e-3)
+
+    host_x = [torch.randn(B, 3, IMG, IMG).pin_memory() for _ in range(2)]
+    host_y = [torch.randint(0, 1000, (B,)).pin_memory() for _ in range(2)]
+
+    def step_e2e():
+        i = state["i"] & 1
+        state["i"] += 1
+        x = host_x[i].to(ctx.dev, non_blocking=True)  # train.py:225: images.to(device, non_blocking=True)
+        y = host_y[i].to(ctx.dev, non_blocking=True)
+        loss = trainer.step(x, y)
+        return loss.item()  # train.py:233: loss.item() every step (device -> host read of the step's result)
+
+    e2e_ms = timed(ctx, step_e2e, args.steps, args.warmup)
+    peak_s = 1422.7
+    try:
+        peak_s = float(json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))["bf16_tflops_sustained"])
+    except Exception:
+        pass
+    gflop_img = 3 * GFLOP_PER_EMBEDDING  # fwd + dgrad + wgrad (SURVEY.md §8d: 92.3 GFLOP per image)
+    ach = B * gflop_img / ms
+    nb = sum(model.trainingwrapper["backbone"].model.depths)
+    launches = (5 * nb + 6) + (3 * nb + 12) + (14 * nb + 30) + 14 + 8
+    return {"value": value, "ms": ms, "e2e_ms": e2e_ms, "batch": B, "h2d": B * 3 * IMG * IMG * 4 + B * 8, "d2h": 4,
+            "launches_per_step": launches,
+            "whole_step": {"achieved": ach, "unit": "TFLOP/s", "peak": peak_s, "frac": ach / peak_s,
+                           "note": "92.3 GFLOP per image (3 x forward) over the whole step incl. head, clip+SGD+EMA; peak = "
+                                   "MEASURED_PEAKS.json bf16_tflops_sustained (kernel inside a long step)"}}
+
+
 def bench_retrieval(ctx, args):
     import ctypes as C
     import torch
@@ -458,18 +576,21 @@ def main():
     sampler = ClockSampler(local_rank) if ctx.rank == 0 else None
     if sampler:
         sampler.start()
-    ex = bench_extract(ctx, args) if args.only in ("both", "extract") else None
+    want = lambda name: args.only in ("all", name) or (args.only == "both" and name in ("extract", "retrieval"))
+    tr = bench_train(ctx, args) if want("train") else None
     torch.cuda.empty_cache()
-    rt = bench_retrieval(ctx, args) if args.only in ("both", "retrieval") else None
+    ex = bench_extract(ctx, args) if want("extract") else None
+    torch.cuda.empty_cache()
+    rt = bench_retrieval(ctx, args) if want("retrieval") else None
     clocks = sampler.stop() if sampler else None
 
     cpu = {}
-    if ctx.rank == 0 and ctx.world == 1 and not args.no_cpu_baseline:
-        cpu = cpu_baselines(args, want_retrieval=rt is not None)
+    if ctx.rank == 0 and ctx.world == 1 and not args.no_cpu_baseline and (ex is not None or tr is not None):
+        cpu = cpu_baselines(args, want_retrieval=rt is not None, want_train=tr is not None)
 
     if ctx.rank == 0:
         W = max(3, args.warmup)
-        retrieval = None
+        retrieval = extract = None
         if rt is not None:
             retrieval = {
                 "metric": "query x gallery pairs/sec (cosine top-100, 512-d)", "value": rt["value"], "unit": "pairs/s",
@@ -484,24 +605,45 @@ def main():
                 "roofline": rt["roofline"], "cpu_baseline": cpu.get("retrieval"),
             }
         if ex is not None:
-            line = {
-                "metric": "embeddings/sec (ConvNeXt-B 224^2, CBIR extract)", "value": ex["value"], "unit": "embeddings/s",
-                "n_gpus": ctx.world, "steps": args.steps, "warmup": W, "ms_per_step": ex["ms"], "higher_is_better": True,
-                "scaling": "weak", "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
+            extract = {
+                "metric": "embeddings/sec (ConvNeXt-B 224^2, CBIR extract, inference)", "value": ex["value"],
+                "unit": "embeddings/s", "ms_per_step": ex["ms"], "scaling": "weak", "dtype": "bf16",
                 "config": {"workload": f"CBIR eval extract: ConvNeXt-B {IMG}^2 -> {FEAT}-d L2-normalised embeddings, "
                                        f"batch {ex['batch']} per GPU, random-init weights",
-                           "l2": "two alternating input batches (2 x 154 MB) exceed the 126 MB L2; activations stream through HBM",
-                           "second_metric": "see `retrieval` (pairs/sec, same CBIR eval path)"},
+                           "l2": "two alternating input batches (2 x 154 MB) exceed the 126 MB L2"},
                 "e2e": {"value": ctx.world * ex["batch"] / (ex["e2e_ms"] * 1e-3), "unit": "embeddings/s",
                         "ms_per_step": ex["e2e_ms"], "h2d_bytes_per_step": ex["h2d"], "d2h_bytes_per_step": ex["d2h"]},
                 "gpu_launches": ex["launches_per_step"] * args.steps,
-                "clocks": clocks, "roofline": ex["roofline"], "cpu_baseline": cpu.get("embeddings"),
-                "retrieval": retrieval,
+                "roofline": ex["roofline"], "cpu_baseline": cpu.get("embeddings"),
             }
+        common = {"n_gpus": ctx.world, "steps": args.steps, "warmup": W, "higher_is_better": True, "vs_baseline": None,
+                  "data": "synthetic", "clocks": clocks}
+        if tr is not None:
+            roof = dict(ex["roofline"]) if ex is not None and ex["roofline"] else None
+            if roof is not None:
+                roof["whole_step"] = tr["whole_step"]
+                roof["note"] = ("dominant kernel of the step = the tcgen05 GEMM; timed alone at the forward MLP/downsample "
+                                "shapes (the backward launches the same kernel with MN-major operands)")
+            line = {
+                "metric": "embeddings/sec (ConvNeXt-B 224^2 faceX ArcFace train step)", "value": tr["value"],
+                "unit": "embeddings/s", "ms_per_step": tr["ms"], "scaling": "weak", "dtype": "bf16",
+                "config": {"workload": f"faceX train step: ConvNeXt-B {IMG}^2 + ArcFace(C=1000) + CE(label_smooth 0.1) + "
+                                       f"clip + SGD + EMA, batch {tr['batch']} per GPU, DDP all-reduce(mean) over {ctx.world} GPU(s)",
+                           "l2": "two alternating input batches; saved activations (~93 MB/image) stream through HBM",
+                           "other_metrics": "see `extract` (inference embeddings/sec) and `retrieval` (pairs/sec)"},
+                "e2e": {"value": ctx.world * tr["batch"] / (tr["e2e_ms"] * 1e-3), "unit": "embeddings/s",
+                        "ms_per_step": tr["e2e_ms"], "h2d_bytes_per_step": tr["h2d"], "d2h_bytes_per_step": tr["d2h"]},
+                "gpu_launches": tr["launches_per_step"] * args.steps,
+                "roofline": roof if roof is not None else {"bound": "tensor", "whole_step": tr["whole_step"]},
+                "cpu_baseline": cpu.get("train"),
+                "extract": extract, "retrieval": retrieval,
+            }
+        elif ex is not None:
+            line = dict(extract)
+            line["retrieval"] = retrieval
         else:
             line = dict(retrieval)
-            line.update({"n_gpus": ctx.world, "steps": args.steps, "warmup": W, "higher_is_better": True,
-                         "vs_baseline": None, "data": "synthetic", "clocks": clocks})
+        line.update(common)
         print(json.dumps(line), flush=True)
     if ctx.world > 1:
         dist.destroy_process_group()

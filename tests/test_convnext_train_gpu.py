@@ -154,20 +154,29 @@ def test_train_forward_backward_matches_oracle_autograd(lib):
     (out * wout.cuda()).sum().backward()
     assert rel(out.detach().cpu(), out_ref.detach()) <= 3e-2
     ref_grads = dict(oracle.named_parameters())
-    worst = []
+    # LayerNorm right before a batch-statistics BatchNorm: a per-channel scale / shift of the BN input is removed by the
+    # normalisation, so the exact gradient of head.norm.{weight,bias} is 0 and only rounding noise remains on both sides
+    invariant = {"model.head.norm.weight", "model.head.norm.bias"}
+    bn_scale = ref_grads["output_layer.0.weight"].grad.abs().max().item()
+    stats, bad = [], []
     for n, p in ours.named_parameters():
         gr = ref_grads[n].grad
         g = p.grad.detach().cpu()
         assert torch.isfinite(g).all(), n
-        if gr.norm() < 1e-6 * (1 + gr.numel() ** 0.5):
-            assert (g - gr).abs().max().item() <= 1e-3, n
+        if n in invariant or gr.norm() < 1e-6 * (1 + gr.numel() ** 0.5):
+            err = (g - gr).abs().max().item()
+            stats.append((n, "abs", err, 0.0))
+            if err > 5e-2 * bn_scale + 1e-3:
+                bad.append(f"{n}: |err| {err:.3e} (exact gradient ~0)")
             continue
         r = rel(g, gr)
         c = F.cosine_similarity(g.flatten(), gr.flatten(), dim=0).item()
-        worst.append((r, c, n))
-        assert r <= 6e-2 and c >= 0.995, f"{n}: rel {r:.4f} cos {c:.5f}"
-    worst.sort(reverse=True)
-    print("worst gradients:", worst[:5])
+        stats.append((n, "rel", r, c))
+        if not (r <= 6e-2 and c >= 0.995):
+            bad.append(f"{n}: rel {r:.4f} cos {c:.5f} |ref| {gr.norm():.3e}")
+    for n, kind, a, c in sorted(stats, key=lambda t: -t[2])[:12]:
+        print(f"  {kind} {a:.4f} cos {c:.5f} {n}")
+    assert not bad, "\n".join(bad)
     # BatchNorm running statistics follow nn.BatchNorm's update
     for i in (0, 3):
         assert rel(ours.output_layer[i].running_mean.cpu(), oracle.output_layer[i].running_mean) <= 2e-2
