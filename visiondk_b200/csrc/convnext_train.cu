@@ -31,9 +31,21 @@ struct TrainLayout {
   size_t hpre[VDK_CONVNEXT_MAX_BLOCKS], hpost[VDK_CONVNEXT_MAX_BLOCKS];
   size_t patch[4], prstd[4];                                   // downsample: LayerNorm'ed 2x2 patch rows, 1/sigma
   size_t f, frstd, fn, bn2_mean, bn2_rstd, z, zslab, bn1_mean, bn1_rstd;
-  size_t dxa, dxb, dy, dconv, G, sdo, dw49, gwc, gwneck, dz, dzb, dfn;
+  size_t dxa, dxb, dy, dconv, G, sdo, dw49, gwc, gwneck, dz, dzb, dfn, wslab;
   size_t total;
 };
+
+// split count for a weight-gradient GEMM (few output tiles, very long contraction): at least two, so that vdk_gemm
+// takes its raw-partials output mode; every split stores its own fp32 slab, which a reduction kernel then adds in a
+// fixed order (deterministic, and no atomics on the few hot output addresses).
+static int wgrad_splits(int M, int N, size_t K) {
+  const int tiles = ((M + 127) / 128) * ((N + 255) / 256);
+  const int want = std::max(2, (2 * sm_count()) / std::max(1, tiles));
+  return vdk_gemm_effective_splits(static_cast<int>(K), want);
+}
+static size_t wgrad_slab_bytes(int M, int N, size_t K) {
+  return static_cast<size_t>(std::max(2, wgrad_splits(M, N, K))) * M * N * 4;
+}
 
 static void make_layout(const vdk_convnext_net* net, int batch, TrainLayout* L) {
   size_t off = 0;
@@ -92,6 +104,14 @@ static void make_layout(const vdk_convnext_net* net, int batch, TrainLayout* L) 
   L->dz = take(static_cast<size_t>(batch) * F * 4);
   L->dzb = take(static_cast<size_t>(batch) * F * 2);
   L->dfn = take(M3 * C3 * 2);
+  size_t slab = wgrad_slab_bytes(net->dims[0], 48, M0);
+  for (int s = 0; s < 4; ++s) {
+    const int C = L->st[s].C;
+    slab = std::max(slab, wgrad_slab_bytes(C, 4 * C, L->st[s].M));
+    slab = std::max(slab, wgrad_slab_bytes(4 * C, C, L->st[s].M));
+    if (s > 0) slab = std::max(slab, wgrad_slab_bytes(C, 4 * L->st[s - 1].C, L->st[s].M));
+  }
+  L->wslab = take(slab);
   L->total = off + 256;
 }
 
@@ -102,6 +122,39 @@ __global__ void slab_reduce_bias_kernel(const float* __restrict__ slabs, int n_s
   float v = bias ? bias[i % cols] : 0.f;
   for (int s = 0; s < n_slabs; ++s) v += slabs[s * stride + i];
   out[i] = v;
+}
+// dst[i] (+)= sum_s slabs[s * stride + i]: 32 float4 columns x 8 slab groups per block; the groups meet in shared
+// memory and are added in a fixed order
+__global__ void __launch_bounds__(256)
+slab_reduce_kernel(const float* __restrict__ slabs, int n_slabs, size_t stride, int64_t n4, float* __restrict__ dst,
+                   int accumulate) {
+  __shared__ float4 part[8][32];
+  const int col = threadIdx.x & 31, grp = threadIdx.x >> 5;
+  const int64_t i = static_cast<int64_t>(blockIdx.x) * 32 + col;
+  float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+  if (i < n4) {
+#pragma unroll 4
+    for (int s = grp; s < n_slabs; s += 8) {
+      const float4 v = __ldg(reinterpret_cast<const float4*>(slabs + static_cast<size_t>(s) * stride) + i);
+      acc.x += v.x; acc.y += v.y; acc.z += v.z; acc.w += v.w;
+    }
+  }
+  part[grp][col] = acc;
+  __syncthreads();
+  if (grp == 0 && i < n4) {
+    float4 t = part[0][col];
+#pragma unroll
+    for (int g = 1; g < 8; ++g) {
+      const float4 v = part[g][col];
+      t.x += v.x; t.y += v.y; t.z += v.z; t.w += v.w;
+    }
+    float4* o = reinterpret_cast<float4*>(dst) + i;
+    if (accumulate) {
+      const float4 d = *o;
+      t.x += d.x; t.y += d.y; t.z += d.z; t.w += d.w;
+    }
+    *o = t;
+  }
 }
 __global__ void col_sum_f32_small_kernel(const float* __restrict__ x, int rows, int cols, float* __restrict__ out) {
   const int c = blockIdx.x * blockDim.x + threadIdx.x;
@@ -143,12 +196,18 @@ struct Gemm {
     g.ln_eps = 1e-6f; g.split_k = split; g.split_stride = stride; g.trans_a = ta; g.trans_b = tb; g.aux_out = aux_out;
     return gemm_run(g, s);
   }
-  // split count for a weight-gradient GEMM: few output tiles, very long contraction
-  static int wgrad_splits(int M, int N, int K) {
-    const int tiles = ((M + 127) / 128) * ((N + 255) / 256);
-    // at least two splits: a split GEMM ADDS its partials to D, which is what accumulating gradients need
-    (void)K;  // vdk_gemm clamps to the number of 64-wide K blocks itself; asking for >= 2 selects the "+=" output mode
-    return std::max(2, (2 * sm_count()) / std::max(1, tiles));
+  // weight gradient D[M,N] (+)= A^T-major product over a long K: split-K partial slabs + fixed-order reduction
+  int wgrad(const void* A, const void* B, float* D, int M, int N, int K, int lda, int ldb, float* slabs, bool accumulate) const {
+    VDK_REQUIRE((static_cast<size_t>(M) * N) % 4 == 0, "wgrad: M*N must be a multiple of 4");
+    const int split = wgrad_splits(M, N, static_cast<size_t>(K));
+    const size_t stride = static_cast<size_t>(M) * N;
+    int rc = run(A, B, slabs, M, N, K, lda, ldb, N, VDK_EPI_NONE, nullptr, nullptr, nullptr, 0, VDK_DTYPE_FP32, std::max(2, split),
+                 static_cast<long long>(stride), 1, 1);
+    if (rc != VDK_OK) return rc;
+    const int64_t n4 = static_cast<int64_t>(stride / 4);
+    slab_reduce_kernel<<<static_cast<unsigned>((n4 + 31) / 32), 256, 0, s>>>(slabs, split, stride, n4, D, accumulate ? 1 : 0);
+    VDK_CUDA_OK(cudaGetLastError());
+    return VDK_OK;
   }
 };
 
@@ -334,17 +393,14 @@ extern "C" int vdk_convnext_train_backward(const vdk_convnext_net* net, const vd
       // fc2 + layer scale: G = dOut^T . h_post;  dW2 = diag(gamma) G;  dgamma, db2 from G, W2, colsum(dOut)
       VDK_CUDA_OK(cudaMemsetAsync(F32(L.sdo), 0, static_cast<size_t>(C) * 4, s));
       RC(launch_col_sum(B16(dx), M, C, C, F32(L.sdo), s));
-      VDK_CUDA_OK(cudaMemsetAsync(F32(L.G), 0, static_cast<size_t>(C) * 4 * C * 4, s));
-      RC(G.run(B16(dx), B16(L.hpost[k]), F32(L.G), C, 4 * C, M, C, 4 * C, 4 * C, VDK_EPI_NONE, nullptr, nullptr, nullptr, 0,
-               VDK_DTYPE_FP32, Gemm::wgrad_splits(C, 4 * C, M), 0, 1, 1));
+      RC(G.wgrad(B16(dx), B16(L.hpost[k]), F32(L.G), C, 4 * C, M, C, 4 * C, F32(L.wslab), false));
       RC(launch_layerscale_finalize(F32(L.G), pb->fc2_w, pb->fc2_b, pb->gamma, F32(L.sdo), C, 4 * C, gb->fc2_w, gb->gamma, gb->fc2_b, s));
       // dH_pre = (dOut . diag(gamma) W2) * gelu'(h_pre)   -> overwrites the h_post buffer
       RC(G.run(B16(dx), b->fc2_wg, B16(L.hpost[k]), M, 4 * C, C, C, 4 * C, 4 * C, VDK_EPI_MUL_GELU_GRAD, nullptr, nullptr,
                B16(L.hpre[k]), 4 * C, VDK_DTYPE_BF16, 1, 0, 0, 1));
       __nv_bfloat16* dh = B16(L.hpost[k]);
       RC(launch_col_sum(dh, M, 4 * C, 4 * C, gb->fc1_b, s));
-      RC(G.run(dh, B16(L.y[k]), gb->fc1_w, 4 * C, C, M, 4 * C, C, C, VDK_EPI_NONE, nullptr, nullptr, nullptr, 0, VDK_DTYPE_FP32,
-               Gemm::wgrad_splits(4 * C, C, M), 0, 1, 1));
+      RC(G.wgrad(dh, B16(L.y[k]), gb->fc1_w, 4 * C, C, M, 4 * C, C, F32(L.wslab), true));
       RC(G.run(dh, b->fc1_w, B16(L.dy), M, C, 4 * C, 4 * C, C, C, VDK_EPI_NONE, nullptr, nullptr, nullptr, 0, VDK_DTYPE_BF16, 1, 0, 0, 1));
       // LayerNorm backward, depthwise weight gradient, depthwise data gradient (+ the residual branch)
       RC(launch_ln_bwd(B16(L.dy), B16(L.y[k]), F32(L.rstd[k]), batch, H, W, C, b->ln_w, b->ln_b, 1, B16(L.dconv), nullptr, gb->ln_w,
@@ -361,9 +417,7 @@ extern "C" int vdk_convnext_train_backward(const vdk_convnext_net* net, const vd
       const vdk_convnext_down_tensors* gd = &g->down[st];
       const int Cin = L.st[st - 1].C;
       RC(launch_col_sum(B16(dx), M, C, C, gd->conv_b, s));
-      VDK_CUDA_OK(cudaMemsetAsync(F32(L.gwc), 0, static_cast<size_t>(C) * 4 * Cin * 4, s));
-      RC(G.run(B16(dx), B16(L.patch[st]), F32(L.gwc), C, 4 * Cin, M, C, 4 * Cin, 4 * Cin, VDK_EPI_NONE, nullptr, nullptr, nullptr, 0,
-               VDK_DTYPE_FP32, Gemm::wgrad_splits(C, 4 * Cin, M), 0, 1, 1));
+      RC(G.wgrad(B16(dx), B16(L.patch[st]), F32(L.gwc), C, 4 * Cin, M, C, 4 * Cin, F32(L.wslab), false));
       RC(launch_permute021(F32(L.gwc), C, 4, Cin, nullptr, nullptr, gd->conv_w, 1, s));  // [C][4][Cin] -> += [C][Cin][4]
       RC(G.run(B16(dx), d->conv_w, B16(L.dy), M, 4 * Cin, C, C, 4 * Cin, 4 * Cin, VDK_EPI_NONE, nullptr, nullptr, nullptr, 0,
                VDK_DTYPE_BF16, 1, 0, 0, 1));
@@ -378,8 +432,7 @@ extern "C" int vdk_convnext_train_backward(const vdk_convnext_net* net, const vd
     RC(launch_ln_bwd(B16(dx), B16(L.xs[0][0]), F32(L.rstd0), batch, L.st[0].H, L.st[0].W, C0, net->stem_ln_w, net->stem_ln_b, 1,
                      B16(L.dy), nullptr, g->stem_ln_w, g->stem_ln_b, s));
     RC(launch_col_sum(B16(L.dy), M0, C0, C0, g->stem_b, s));
-    RC(G.run(B16(L.dy), B16(L.p0), g->stem_w, C0, 48, M0, C0, 48, 48, VDK_EPI_NONE, nullptr, nullptr, nullptr, 0, VDK_DTYPE_FP32,
-             Gemm::wgrad_splits(C0, 48, M0), 0, 1, 1));
+    RC(G.wgrad(B16(L.dy), B16(L.p0), g->stem_w, C0, 48, M0, C0, 48, F32(L.wslab), true));
   }
   return VDK_OK;
 }

@@ -260,17 +260,27 @@ fgrad_finalize_kernel(const float* __restrict__ dfn, const float* __restrict__ f
   for (int k = lane; k < D; k += 32)
     df[static_cast<int64_t>(r) * D + k] = (dfn[static_cast<int64_t>(r) * D + k] - fn[static_cast<int64_t>(r) * D + k] * dot) * inv[r];
 }
-// dW[:,c] = (dW~[:,c] - W~[:,c] (W~[:,c] . dW~[:,c])) * inv_wnorm[c], thread per column
+// dW[:,c] = (dW~[:,c] - W~[:,c] (W~[:,c] . dW~[:,c])) * inv_wnorm[c]; a block owns 32 columns, its 8 warps stride the
+// D rows (coalesced 128-byte row segments) and meet in shared memory for the per-column dot product
 __global__ void __launch_bounds__(256)
 wgrad_finalize_kernel(const float* __restrict__ dwn, int ldw, const float* __restrict__ w, const float* __restrict__ inv, int D,
                       int Cn, float* __restrict__ dw) {
-  const int c = blockIdx.x * blockDim.x + threadIdx.x;
-  if (c >= Cn) return;
-  const float iv = inv[c];
+  __shared__ float red[8][32];
+  const int lane = threadIdx.x & 31, grp = threadIdx.x >> 5;
+  const int c = blockIdx.x * 32 + lane;
+  const bool ok = c < Cn;
+  const float iv = ok ? inv[c] : 0.f;
   float dot = 0.f;
-  for (int d = 0; d < D; ++d) dot = fmaf(w[static_cast<int64_t>(d) * Cn + c] * iv, dwn[static_cast<int64_t>(d) * ldw + c], dot);
-  for (int d = 0; d < D; ++d)
-    dw[static_cast<int64_t>(d) * Cn + c] = (dwn[static_cast<int64_t>(d) * ldw + c] - w[static_cast<int64_t>(d) * Cn + c] * iv * dot) * iv;
+  if (ok)
+    for (int d = grp; d < D; d += 8) dot = fmaf(w[static_cast<int64_t>(d) * Cn + c] * iv, dwn[static_cast<int64_t>(d) * ldw + c], dot);
+  red[grp][lane] = dot;
+  __syncthreads();
+  dot = 0.f;
+#pragma unroll
+  for (int g = 0; g < 8; ++g) dot += red[g][lane];
+  if (ok)
+    for (int d = grp; d < D; d += 8)
+      dw[static_cast<int64_t>(d) * Cn + c] = (dwn[static_cast<int64_t>(d) * ldw + c] - w[static_cast<int64_t>(d) * Cn + c] * iv * dot) * iv;
 }
 
 static size_t a256(size_t v) { return (v + 255) & ~static_cast<size_t>(255); }
@@ -422,7 +432,7 @@ extern "C" int vdk_head_backward(const vdk_head_desc* d, const float* feats, con
   }
   rc = split_gemm(w.a_split, w.b_split, w.dwn, D, w.Cp, 6 * w.Bp, w.Cp, s);
   if (rc != VDK_OK) return rc;
-  wgrad_finalize_kernel<<<(Cn + 255) / 256, 256, 0, s>>>(w.dwn, w.Cp, weight, w.inv_w, D, Cn, dweight);
+  wgrad_finalize_kernel<<<(Cn + 31) / 32, 256, 0, s>>>(w.dwn, w.Cp, weight, w.inv_w, D, Cn, dweight);
   VDK_CUDA_OK(cudaGetLastError());
   return VDK_OK;
 }
