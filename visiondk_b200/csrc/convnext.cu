@@ -12,6 +12,8 @@
 //   neck_finalize     split-K partials + folded BN bias [+ L2 normalise] -> fp32 embeddings
 #include "vdk_host.h"
 #include "vdk_ptx.cuh"
+
+#include <cstdlib>
 #include "convnext_internal.h"
 
 namespace vdk {
@@ -230,6 +232,191 @@ dwconv7_ln_kernel(const __grid_constant__ CUtensorMap map_x, int B, int H, int W
 }
 
 // ------------------------------------------------------------------------------------------------
+// the same operator, channel-chunked: CTA = (image, TH x 7 pixel tile, <=128-channel chunk), one warp per output row
+// ------------------------------------------------------------------------------------------------
+// The all-channel kernel above holds a (T+6)^2 x C halo per CTA (173 KB at C = 512): one CTA per SM, its TMA load
+// fully exposed.  Here a CTA stages only its chunk (43 KB at 128 channels), three CTAs share an SM and hide each
+// other's loads, and the tile count per SM is large enough that the tail wave no longer matters.  LayerNorm couples the
+// chunks of a pixel: the C / chunk CTAs of a tile form a thread-block CLUSTER, each publishes (mean, centred sum of
+// squares) of its channels per pixel in shared memory, and every CTA combines the partials of its peers through
+// distributed shared memory (Chan's parallel-variance update: same two-pass numerics as the reference LayerNorm,
+// one cluster barrier).  MODE as above.
+__device__ __forceinline__ void cluster_arrive() { asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory"); }
+__device__ __forceinline__ void cluster_wait() { asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory"); }
+__device__ __forceinline__ float2 ld_dsmem_f2(const void* local_smem, uint32_t rank) {
+  uint32_t ra;
+  float2 v;
+  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(ra) : "r"(smem_u32(local_smem)), "r"(rank));
+  asm volatile("ld.shared::cluster.v2.f32 {%0, %1}, [%2];" : "=f"(v.x), "=f"(v.y) : "r"(ra) : "memory");
+  return v;
+}
+
+constexpr int kDwTW = 7;
+
+template <int MODE>
+__global__ void __launch_bounds__(224, 3)
+dwconv7_chunk_kernel(const __grid_constant__ CUtensorMap map_x, int B, int H, int W, int C, int TH, int chunk, int nchunks,
+                     const float* __restrict__ w49, const float* __restrict__ bias, const float* __restrict__ ln_w,
+                     const float* __restrict__ ln_b, float eps, __nv_bfloat16* __restrict__ y, float* __restrict__ rstd_out,
+                     const __nv_bfloat16* __restrict__ addend) {
+  extern __shared__ uint8_t dwc_smem_raw[];
+  uint8_t* smem = dwc_smem_raw + ((128u - (smem_u32(dwc_smem_raw) & 127u)) & 127u);
+  constexpr int box_w = kDwTW + 6;
+  const int tile_bytes = (TH + 6) * box_w * chunk * 2;
+  float2* part = reinterpret_cast<float2*>(smem + ((tile_bytes + 127) & ~127));  // [7 rows][8]: (mean, M2) per pixel
+  uint64_t* bar = reinterpret_cast<uint64_t*>(part + 7 * 8);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  int bid = blockIdx.x;
+  const int ck = bid % nchunks; bid /= nchunks;
+  const int tiles_w = (W + kDwTW - 1) / kDwTW, tiles_h = (H + TH - 1) / TH;
+  const int tw = bid % tiles_w; bid /= tiles_w;
+  const int th = bid % tiles_h;
+  const int b = bid / tiles_h;
+  const int oy0 = th * TH, ox0 = tw * kDwTW;
+  const int cl = lane * 4;
+  const bool has_c = cl < chunk;
+  const int c0 = ck * chunk + cl;
+
+  if (threadIdx.x == 0) {
+    prefetch_tensormap(&map_x);
+    mbar_init(bar, 1);
+    fence_mbar_init();
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    mbar_arrive_expect_tx(bar, tile_bytes);
+    tma_load_4d(smem, &map_x, bar, ck * chunk, ox0 - 3, oy0 - 3, b);
+  }
+  float4 bc = make_float4(0.f, 0.f, 0.f, 0.f), g4 = bc, b4 = bc;
+  if (has_c && MODE == 0) {
+    bc = __ldg(reinterpret_cast<const float4*>(bias + c0));
+    g4 = __ldg(reinterpret_cast<const float4*>(ln_w + c0));
+    b4 = __ldg(reinterpret_cast<const float4*>(ln_b + c0));
+  }
+  const int pix_stride = chunk * 2;
+  const bool active = has_c && warp < TH && oy0 + warp < H;
+  float acc[kDwTW][4];
+#pragma unroll
+  for (int p = 0; p < kDwTW; ++p) {
+    acc[p][0] = bc.x; acc[p][1] = bc.y; acc[p][2] = bc.z; acc[p][3] = bc.w;
+  }
+  mbar_wait(bar, 0);
+  if (active) {
+    const uint8_t* tbase = smem + cl * 2;
+#pragma unroll 1
+    for (int dy = 0; dy < 7; ++dy) {
+      float4 wrow[7];
+#pragma unroll
+      for (int dx = 0; dx < 7; ++dx) wrow[dx] = __ldg(reinterpret_cast<const float4*>(w49 + (dy * 7 + dx) * C + c0));
+      const uint8_t* rowp = tbase + static_cast<size_t>((warp + dy) * box_w) * pix_stride;
+#pragma unroll
+      for (int ix = 0; ix < box_w; ++ix) {
+        const uint2 t = *reinterpret_cast<const uint2*>(rowp + ix * pix_stride);
+        const float2 a = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&t.x));
+        const float2 c = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&t.y));
+#pragma unroll
+        for (int p = 0; p < kDwTW; ++p) {
+          const int dx = ix - p;  // input column ix feeds output pixel p through tap dx
+          if (dx >= 0 && dx < 7) {
+            acc[p][0] = fmaf(a.x, wrow[dx].x, acc[p][0]);
+            acc[p][1] = fmaf(a.y, wrow[dx].y, acc[p][1]);
+            acc[p][2] = fmaf(c.x, wrow[dx].z, acc[p][2]);
+            acc[p][3] = fmaf(c.y, wrow[dx].w, acc[p][3]);
+          }
+        }
+      }
+    }
+  }
+  if (MODE == 1) {
+    if (active) {
+#pragma unroll
+      for (int p = 0; p < kDwTW; ++p) {
+        const int ox = ox0 + p;
+        if (ox >= W) continue;
+        const int64_t off = ((static_cast<int64_t>(b) * H + oy0 + warp) * W + ox) * C + c0;
+        float o0 = acc[p][0], o1 = acc[p][1], o2 = acc[p][2], o3 = acc[p][3];
+        if (addend) {
+          const uint2 t = __ldg(reinterpret_cast<const uint2*>(addend + off));
+          const float2 a = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&t.x));
+          const float2 c = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&t.y));
+          o0 += a.x; o1 += a.y; o2 += c.x; o3 += c.y;
+        }
+        __nv_bfloat162 lo = __floats2bfloat162_rn(o0, o1), hi = __floats2bfloat162_rn(o2, o3);
+        uint2 t;
+        t.x = *reinterpret_cast<uint32_t*>(&lo);
+        t.y = *reinterpret_cast<uint32_t*>(&hi);
+        *reinterpret_cast<uint2*>(y + off) = t;
+      }
+    }
+    return;
+  }
+  // ---- LayerNorm over C: local two-pass statistics of this chunk, then the cluster-wide combination ----
+  float mean[kDwTW], rstd[kDwTW];
+  const float inv_chunk = 1.0f / static_cast<float>(chunk), inv_c = 1.0f / static_cast<float>(C);
+#pragma unroll
+  for (int p = 0; p < kDwTW; ++p) {
+    const float s = warp_sum(active ? (acc[p][0] + acc[p][1]) + (acc[p][2] + acc[p][3]) : 0.f);
+    mean[p] = s * inv_chunk;
+  }
+#pragma unroll
+  for (int p = 0; p < kDwTW; ++p) {
+    float q = 0.f;
+    if (active) {
+#pragma unroll
+      for (int c = 0; c < 4; ++c) {
+        const float d = acc[p][c] - mean[p];
+        q = fmaf(d, d, q);
+      }
+    }
+    rstd[p] = warp_sum(q);  // centred sum of squares of this chunk, for now
+  }
+  if (nchunks == 1) {
+#pragma unroll
+    for (int p = 0; p < kDwTW; ++p) rstd[p] = rsqrtf(rstd[p] * inv_c + eps);
+  } else {
+    float2 mine = make_float2(0.f, 0.f);
+#pragma unroll
+    for (int p = 0; p < kDwTW; ++p)
+      if (lane == p) mine = make_float2(mean[p], rstd[p]);
+    if (lane < kDwTW && warp < 7) part[warp * 8 + lane] = mine;
+    cluster_arrive();
+    cluster_wait();
+    const float inv_n = 1.0f / static_cast<float>(nchunks);
+#pragma unroll
+    for (int p = 0; p < kDwTW; ++p) {
+      float2 r = make_float2(0.f, 0.f);
+      if (lane < nchunks) r = ld_dsmem_f2(part + warp * 8 + p, static_cast<uint32_t>(lane));
+      const float m = warp_sum(r.x) * inv_n;
+      const float d = r.x - m;
+      const float m2 = warp_sum(lane < nchunks ? fmaf(static_cast<float>(chunk) * d, d, r.y) : 0.f);
+      mean[p] = m;
+      rstd[p] = rsqrtf(m2 * inv_c + eps);
+    }
+    cluster_arrive();  // my reads of the peers' partials are done (matched by the wait before exit)
+  }
+  if (active) {
+#pragma unroll
+    for (int p = 0; p < kDwTW; ++p) {
+      const int ox = ox0 + p;
+      if (ox >= W) continue;
+      const int64_t pix = (static_cast<int64_t>(b) * H + oy0 + warp) * W + ox;
+      if (rstd_out != nullptr && lane == 0 && ck == 0) rstd_out[pix] = rstd[p];
+      __nv_bfloat16* dst = y + pix * C + c0;
+      __nv_bfloat162 lo = __floats2bfloat162_rn((acc[p][0] - mean[p]) * rstd[p] * g4.x + b4.x,
+                                                (acc[p][1] - mean[p]) * rstd[p] * g4.y + b4.y);
+      __nv_bfloat162 hi = __floats2bfloat162_rn((acc[p][2] - mean[p]) * rstd[p] * g4.z + b4.z,
+                                                (acc[p][3] - mean[p]) * rstd[p] * g4.w + b4.w);
+      uint2 t;
+      t.x = *reinterpret_cast<uint32_t*>(&lo);
+      t.y = *reinterpret_cast<uint32_t*>(&hi);
+      *reinterpret_cast<uint2*>(dst) = t;
+    }
+  }
+  if (nchunks > 1) cluster_wait();  // no CTA of the cluster leaves while a peer may still read its shared memory
+}
+
+// ------------------------------------------------------------------------------------------------
 // LayerNorm over C of NHWC rows, optionally scattered into 2x2/stride-2 patch rows (kh, kw, c)
 // ------------------------------------------------------------------------------------------------
 template <int LPP>  // lanes per pixel (8, 16 or 32); each lane owns 8-channel (16-byte) vectors c = (sub + i*LPP)*8
@@ -400,6 +587,52 @@ int vdk::launch_dwconv7(int mode, const __nv_bfloat16* x, int batch, int H, int 
                           const float* ln_w, const float* ln_b, float eps, __nv_bfloat16* y, float* rstd_out,
                           const __nv_bfloat16* addend, cudaStream_t s) {
   VDK_REQUIRE(C % 8 == 0 && C <= 2048, "dwconv7: C must be a multiple of 8, <= 2048 (got %d)", C);
+  {
+    // channel-chunked kernel (clustered LayerNorm) whenever C splits into <= 16 chunks of <= 128 channels
+    int chunk = 0;
+    if (C <= 128) chunk = C;
+    else if (C % 128 == 0) chunk = 128;
+    else if (C % 96 == 0) chunk = 96;
+    else if (C % 64 == 0) chunk = 64;
+    static const bool use_chunked = [] {
+      const char* e = getenv("VDK_DWCONV_CHUNKED");
+      return e ? atoi(e) != 0 : true;
+    }();
+    if (use_chunked && chunk > 0 && C / chunk <= 16) {
+      const int nchunks = C / chunk;
+      const int TH = std::min(7, H);
+      CUtensorMap mx;
+      int rc = make_tma_nhwc_16bit(&mx, x, batch, H, W, C, TH + 6, kDwTW + 6, chunk);
+      if (rc != VDK_OK) return rc;
+      const int smem = (((TH + 6) * (kDwTW + 6) * chunk * 2 + 127) & ~127) + 7 * 8 * 8 + 16 + 128;
+      const unsigned grid = static_cast<unsigned>(batch) * ((H + TH - 1) / TH) * ((W + kDwTW - 1) / kDwTW) * nchunks;
+      cudaLaunchConfig_t cfg{};
+      cfg.gridDim = dim3(grid);
+      cfg.blockDim = dim3(32 * TH);
+      cfg.dynamicSmemBytes = smem;
+      cfg.stream = s;
+      cudaLaunchAttribute attr[1];
+      attr[0].id = cudaLaunchAttributeClusterDimension;
+      attr[0].val.clusterDim.x = (mode == 0) ? nchunks : 1;
+      attr[0].val.clusterDim.y = 1;
+      attr[0].val.clusterDim.z = 1;
+      cfg.attrs = attr;
+      cfg.numAttrs = 1;
+      if (mode == 0) {
+        auto kern = dwconv7_chunk_kernel<0>;
+        VDK_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024));
+        if (nchunks > 8) VDK_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeNonPortableClusterSizeAllowed, 1));
+        VDK_CUDA_OK(cudaLaunchKernelEx(&cfg, kern, mx, batch, H, W, C, TH, chunk, nchunks, w49, bias, ln_w, ln_b, eps, y, rstd_out,
+                                       addend));
+      } else {
+        auto kern = dwconv7_chunk_kernel<1>;
+        VDK_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024));
+        VDK_CUDA_OK(cudaLaunchKernelEx(&cfg, kern, mx, batch, H, W, C, TH, chunk, nchunks, w49, bias, ln_w, ln_b, eps, y, rstd_out,
+                                       addend));
+      }
+      return VDK_OK;
+    }
+  }
   // channel chunk of one TMA box: the largest divisor of C that is <= 256 and a multiple of 8
   int box_c = std::min(C, 256);
   while (C % box_c != 0 || box_c % 8 != 0) --box_c;

@@ -12,6 +12,8 @@
 #include "vdk_host.h"
 #include "vdk_ptx.cuh"
 
+#include <cstdlib>
+
 namespace vdk {
 
 constexpr int kBM = 128;
@@ -80,14 +82,24 @@ __device__ __forceinline__ void gelu_pair(float& x0, float& x1) {
   x1 = fmaf(hx1, th.y, hx1);
 }
 
-// d/dx of the forward's GELU form 0.5 x (1 + tanh(u)), u = x (c1 + c3 x^2)  (fp32, one SFU op)
-__device__ __forceinline__ float gelu_grad(float x) {
-  const float t = x * x;
-  const float u = x * fmaf(t, 0.03489978f, 0.79973199f);
-  float th;
-  asm("tanh.approx.f32 %0, %1;" : "=f"(th) : "f"(u));
-  const float du = fmaf(t, 3.0f * 0.03489978f, 0.79973199f);
-  return 0.5f * (1.0f + th) + 0.5f * x * (1.0f - th * th) * du;
+// d/dx of the forward's GELU form 0.5 x (1 + tanh(u)), u = x (c1 + c3 x^2), two elements at a time in fp16x2 like the
+// forward (the fc2 data-gradient epilogue evaluates 4C x tokens of these per block): x is clamped to [-8, 8], where
+// the derivative has reached 1 / 0 to fp16 precision, so that x^2 (1 - tanh^2) cannot overflow into inf * 0.
+// Absolute error <= 2e-3 (fp16 tanh.approx + fp16 arithmetic): below the bf16 rounding of the gradient it scales.
+__device__ __forceinline__ float2 gelu_grad_pair(float x0, float x1) {
+  const __half2 lim = __floats2half2_rn(8.0f, 8.0f);
+  const __half2 h = __hmax2(__hmin2(__floats2half2_rn(x0, x1), lim), __hneg2(lim));
+  const __half2 t = __hmul2(h, h);
+  const __half2 c1 = __floats2half2_rn(0.79973199f, 0.79973199f);
+  const __half2 u = __hmul2(h, __hfma2(t, __floats2half2_rn(0.03489978f, 0.03489978f), c1));
+  uint32_t ui = *reinterpret_cast<const uint32_t*>(&u), thi;
+  asm("tanh.approx.f16x2 %0, %1;" : "=r"(thi) : "r"(ui));
+  const __half2 th = *reinterpret_cast<const __half2*>(&thi);
+  const __half2 half = __floats2half2_rn(0.5f, 0.5f);
+  const __half2 du = __hfma2(t, __floats2half2_rn(3.0f * 0.03489978f, 3.0f * 0.03489978f), c1);
+  const __half2 s = __hfma2(__hneg2(th), th, __floats2half2_rn(1.0f, 1.0f));  // 1 - tanh^2
+  const __half2 a = __hmul2(__hmul2(h, du), s);
+  return __half22float2(__hfma2(a, half, __hfma2(th, half, half)));
 }
 
 __device__ __forceinline__ uint32_t pack2(float a, float b, int out_dtype) {
@@ -171,20 +183,26 @@ __device__ __forceinline__ void epi_math(const GemmParams& p, float (&v)[32], in
   }
 }
 
-template <int BN, bool kBf16>
+// kAux: the epilogue streams a second 16-bit tile per output tile (the residual / saved pre-activation it reads, or the
+// pre-activation copy it writes).  That variant trades one mainloop stage for two more 16 KB staging buffers, so the
+// auxiliary input of the NEXT sub-tile is prefetched by TMA while this one is computed and stored, and the two output
+// streams never wait on each other's staging buffer (these GEMMs have short K loops: the epilogue sets their pace).
+template <int BN, bool kBf16, bool kAux>
 __global__ void __launch_bounds__(kGemmThreads, 1)
 gemm_tn_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b,
                const __grid_constant__ CUtensorMap map_d, const __grid_constant__ CUtensorMap map_r,
                const __grid_constant__ CUtensorMap map_d2, const GemmParams p) {
   using Cfg = GemmCfg<BN>;
+  constexpr int kStages = Cfg::kStages - (kAux ? 1 : 0);
+  constexpr int kStoreBufs = kAux ? 4 : 2;
   extern __shared__ uint8_t smem_raw[];
   // align inside the dynamic smem window without a pointer->integer->pointer round trip (which would demote every
   // later access to generic LD/ST)
   uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
-  uint8_t* smem_store = smem + Cfg::kStages * Cfg::kStageBytes;
-  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem_store + 2 * Cfg::kStoreStageBytes);
-  uint64_t* empty_bar = full_bar + Cfg::kStages;
-  uint64_t* tmem_full = empty_bar + Cfg::kStages;
+  uint8_t* smem_store = smem + kStages * Cfg::kStageBytes;
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem_store + kStoreBufs * Cfg::kStoreStageBytes);
+  uint64_t* empty_bar = full_bar + kStages;
+  uint64_t* tmem_full = empty_bar + kStages;
   uint64_t* tmem_empty = tmem_full + 2;
   uint64_t* res_bar = tmem_empty + 2;  // residual sub-tile landed in the staging buffer (one per epilogue half)
   uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(res_bar + 2);
@@ -205,7 +223,7 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
     if (p.tma_store) prefetch_tensormap(&map_d);
     if (p.tma_store && (p.epilogue == VDK_EPI_SCALE_RESIDUAL || p.epilogue == VDK_EPI_MUL_GELU_GRAD)) prefetch_tensormap(&map_r);
     if (p.aux_out) prefetch_tensormap(&map_d2);
-    for (int i = 0; i < Cfg::kStages; ++i) {
+    for (int i = 0; i < kStages; ++i) {
       mbar_init(&full_bar[i], 1);
       mbar_init(&empty_bar[i], 1);
     }
@@ -250,7 +268,7 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
           } else {
             tma_load_2d(sb, &map_b, &full_bar[stage], kb * kBK, n0, kEvictLast);
           }
-          if (++stage == Cfg::kStages) {
+          if (++stage == kStages) {
             stage = 0;
             phase ^= 1;
           }
@@ -287,7 +305,7 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
           for (int k = 0; k < kBK / 16; ++k)
             umma_f16_ss(tmem_d, da + step_a * k, db + step_b * k, idesc, (kb > kb0 || k > 0) ? 1u : 0u);
           umma_commit(&empty_bar[stage]);  // smem slot reusable once these MMAs retire
-          if (++stage == Cfg::kStages) {
+          if (++stage == kStages) {
             stage = 0;
             phase ^= 1;
           }
@@ -302,6 +320,26 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
     bool stores_issued = false;
     uint32_t res_phase = 0;
     int it = 0;
+    // (tile, 64-column sub-tile) sequence of this epilogue half: sub-tiles half, half + 2 of every tile of this CTA
+    auto next_sub = [&](int& t, int& sub) -> bool {
+      sub += 2;
+      while (t < num_tiles) {
+        if (sub < BN / 64 && ((t % (num_m * num_n)) % num_n) * BN + sub * 64 < p.N) return true;
+        t += gridDim.x;
+        sub = half;
+      }
+      return false;
+    };
+    if (kAux && p.tma_store && (p.epilogue == VDK_EPI_SCALE_RESIDUAL || p.epilogue == VDK_EPI_MUL_GELU_GRAD) &&
+        threadIdx.x == 64 + half * 128) {
+      int nt = blockIdx.x, ns = half - 2;
+      if (next_sub(nt, ns)) {
+        const int nmn = nt % (num_m * num_n);
+        mbar_arrive_expect_tx(&res_bar[half], Cfg::kStoreStageBytes);
+        tma_load_2d(smem_store + (2 + half) * Cfg::kStoreStageBytes, &map_r, &res_bar[half], (nmn % num_n) * BN + ns * 64,
+                    (nmn / num_n) * kBM, kEvictFirst);
+      }
+    }
     for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
       const int acc = it & 1;
       const uint32_t acc_phase = (it >> 1) & 1;
@@ -347,7 +385,127 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
         }
         ln_rstd = rsqrtf(sq / static_cast<float>(p.N) + p.ln_eps);
       }
-      if (p.tma_store) {
+      if (kAux && p.tma_store) {
+        // pipelined variant of the staged epilogue below: `stg` stages the output sub-tile, `stg2` holds the auxiliary
+        // INPUT sub-tile (prefetched: the load of the next one is issued as soon as this one sits in registers) or
+        // stages the auxiliary OUTPUT (the saved pre-activation)
+        uint8_t* stg = smem_store + half * Cfg::kStoreStageBytes;
+        uint8_t* stg2 = smem_store + (2 + half) * Cfg::kStoreStageBytes;
+        const bool leader = threadIdx.x == 64 + half * 128;
+        const int rit = lane_base + lane;  // row inside the tile
+        const bool aux_in = p.epilogue == VDK_EPI_SCALE_RESIDUAL || p.epilogue == VDK_EPI_MUL_GELU_GRAD;
+#pragma unroll 1
+        for (int sc = half; sc < BN / 64; sc += 2) {
+          const int colS = n0 + sc * 64;
+          if (colS >= p.N) break;
+          uint32_t packed[32], ain[32];
+          if (aux_in) {
+            mbar_wait(&res_bar[half], res_phase);
+            res_phase ^= 1;
+#pragma unroll
+            for (int q = 0; q < 8; ++q) {
+              const uint4 t = *reinterpret_cast<const uint4*>(stg2 + rit * 128 + ((q ^ (rit & 7)) << 4));
+              ain[4 * q] = t.x; ain[4 * q + 1] = t.y; ain[4 * q + 2] = t.z; ain[4 * q + 3] = t.w;
+            }
+            named_bar_sync(1 + half, 128);  // every row of the input sub-tile is in registers: stg2 may be refilled
+            if (leader) {
+              int nt = tile, ns = sc;
+              if (next_sub(nt, ns)) {
+                const int nmn = nt % (num_m * num_n);
+                mbar_arrive_expect_tx(&res_bar[half], Cfg::kStoreStageBytes);
+                tma_load_2d(stg2, &map_r, &res_bar[half], (nmn % num_n) * BN + ns * 64, (nmn / num_n) * kBM, kEvictFirst);
+              }
+            }
+          }
+#pragma unroll
+          for (int hh = 0; hh < 2; ++hh) {
+            uint32_t r[32];
+            tmem_ld_32x32b_x32(tacc + sc * 64 + hh * 32, r);
+            tmem_ld_wait();
+            float v[32];
+#pragma unroll
+            for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]);
+            const int col0 = colS + hh * 32;
+            const int ncols = max(0, min(32, p.N - col0));
+            if (p.aux_out) {  // GELU with a saved pre-activation: bias only here; the activation follows the aux store
+              if (ncols > 0 && p.bias != nullptr) {
+#pragma unroll
+                for (int j = 0; j < 32; j += 4) {
+                  if (j < ncols) {
+                    const float4 b = __ldg(reinterpret_cast<const float4*>(p.bias + col0 + j));
+                    v[j] += b.x; v[j + 1] += b.y; v[j + 2] += b.z; v[j + 3] += b.w;
+                  }
+                }
+              }
+            } else if (ncols > 0) {
+              epi_math(p, v, row, col0, ncols, ln_mean, ln_rstd, aux_in);
+            }
+            if (aux_in) {
+#pragma unroll
+              for (int q = 0; q < 4; ++q) {
+                const int w0 = (hh * 4 + q) * 4;
+                const float2 a0 = unpack2(ain[w0], p.out_dtype), a1 = unpack2(ain[w0 + 1], p.out_dtype);
+                const float2 a2 = unpack2(ain[w0 + 2], p.out_dtype), a3 = unpack2(ain[w0 + 3], p.out_dtype);
+                if (p.epilogue == VDK_EPI_SCALE_RESIDUAL) {
+                  v[q * 8] += a0.x; v[q * 8 + 1] += a0.y; v[q * 8 + 2] += a1.x; v[q * 8 + 3] += a1.y;
+                  v[q * 8 + 4] += a2.x; v[q * 8 + 5] += a2.y; v[q * 8 + 6] += a3.x; v[q * 8 + 7] += a3.y;
+                } else {
+                  const float2 g0 = gelu_grad_pair(a0.x, a0.y), g1 = gelu_grad_pair(a1.x, a1.y);
+                  const float2 g2 = gelu_grad_pair(a2.x, a2.y), g3 = gelu_grad_pair(a3.x, a3.y);
+                  v[q * 8] *= g0.x; v[q * 8 + 1] *= g0.y; v[q * 8 + 2] *= g1.x; v[q * 8 + 3] *= g1.y;
+                  v[q * 8 + 4] *= g2.x; v[q * 8 + 5] *= g2.y; v[q * 8 + 6] *= g3.x; v[q * 8 + 7] *= g3.y;
+                }
+              }
+            }
+#pragma unroll
+            for (int j = 0; j < 32; j += 2) packed[hh * 16 + (j >> 1)] = pack2(v[j], v[j + 1], p.out_dtype);
+          }
+          if (p.aux_out) {
+            // bulk groups of the leader alternate aux, main, aux, main ...: "at most one pending" means the previous
+            // store out of the buffer about to be rewritten has been read
+            if (stores_issued) {
+              if (leader) tma_store_wait_read<1>();
+              named_bar_sync(1 + half, 128);
+            }
+#pragma unroll
+            for (int q = 0; q < 8; ++q)
+              *reinterpret_cast<uint4*>(stg2 + rit * 128 + ((q ^ (rit & 7)) << 4)) =
+                  make_uint4(packed[4 * q], packed[4 * q + 1], packed[4 * q + 2], packed[4 * q + 3]);
+            fence_proxy_async_smem();
+            named_bar_sync(1 + half, 128);
+            if (leader) {
+              tma_store_2d(&map_d2, stg2, colS, m0);
+              tma_store_commit();
+            }
+            // the activation is applied to the ROUNDED pre-activation (what the backward will see, and what autocast's
+            // 16-bit Linear output hands to nn.GELU)
+#pragma unroll
+            for (int i = 0; i < 32; ++i) {
+              float2 a = unpack2(packed[i], p.out_dtype);
+              gelu_pair(a.x, a.y);
+              packed[i] = pack2(a.x, a.y, p.out_dtype);
+            }
+          }
+          if (stores_issued) {  // the previous output sub-tile must have been read out of `stg`
+            if (leader) {
+              if (p.aux_out) tma_store_wait_read<1>();
+              else tma_store_wait_read<0>();
+            }
+            named_bar_sync(1 + half, 128);
+          }
+#pragma unroll
+          for (int q = 0; q < 8; ++q)
+            *reinterpret_cast<uint4*>(stg + rit * 128 + ((q ^ (rit & 7)) << 4)) =
+                make_uint4(packed[4 * q], packed[4 * q + 1], packed[4 * q + 2], packed[4 * q + 3]);
+          fence_proxy_async_smem();
+          named_bar_sync(1 + half, 128);
+          if (leader) {
+            tma_store_2d(&map_d, stg, colS, m0);
+            tma_store_commit();
+          }
+          stores_issued = true;
+        }
+      } else if (p.tma_store) {
         // 16-bit outputs: each half stages 128 x 64 sub-tiles (128-byte rows, 128B swizzle) and one thread hands
         // them to TMA, so global memory sees full-line stores instead of 32 row-strided 16-byte pieces per warp
         uint8_t* stg = smem_store + half * Cfg::kStoreStageBytes;
@@ -357,7 +515,7 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
         for (int sc = half; sc < BN / 64; sc += 2) {
           const int colS = n0 + sc * 64;
           if (colS >= p.N) break;
-          uint32_t packed[32], packed_aux[32];
+          uint32_t packed[32];
           // auxiliary INPUT tile (residual to add, or the saved pre-activation whose GELU' scales the gradient): fetched
           // by TMA into the staging buffer (full-line reads instead of 32 row-strided 16-byte loads per warp)
           const bool aux_in = p.epilogue == VDK_EPI_SCALE_RESIDUAL || p.epilogue == VDK_EPI_MUL_GELU_GRAD;
@@ -378,7 +536,7 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
             for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]);
             const int col0 = colS + hh * 32;
             const int ncols = max(0, min(32, p.N - col0));
-            if (p.aux_out) {  // GELU with a saved pre-activation: bias first, keep a copy, then activate
+            if (p.aux_out) {  // GELU with a saved pre-activation: bias only here; the activation follows the aux store
               if (ncols > 0 && p.bias != nullptr) {
 #pragma unroll
                 for (int j = 0; j < 32; j += 4) {
@@ -388,10 +546,6 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
                   }
                 }
               }
-#pragma unroll
-              for (int j = 0; j < 32; j += 2) packed_aux[hh * 16 + (j >> 1)] = pack2(v[j], v[j + 1], p.out_dtype);
-#pragma unroll
-              for (int j = 0; j < 32; j += 2) gelu_pair(v[j], v[j + 1]);
             } else if (ncols > 0) {
               epi_math(p, v, row, col0, ncols, ln_mean, ln_rstd, aux_in);
             }
@@ -409,10 +563,10 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
                   v[q * 8] += a0.x; v[q * 8 + 1] += a0.y; v[q * 8 + 2] += a1.x; v[q * 8 + 3] += a1.y;
                   v[q * 8 + 4] += a2.x; v[q * 8 + 5] += a2.y; v[q * 8 + 6] += a3.x; v[q * 8 + 7] += a3.y;
                 } else {
-                  v[q * 8] *= gelu_grad(a0.x); v[q * 8 + 1] *= gelu_grad(a0.y);
-                  v[q * 8 + 2] *= gelu_grad(a1.x); v[q * 8 + 3] *= gelu_grad(a1.y);
-                  v[q * 8 + 4] *= gelu_grad(a2.x); v[q * 8 + 5] *= gelu_grad(a2.y);
-                  v[q * 8 + 6] *= gelu_grad(a3.x); v[q * 8 + 7] *= gelu_grad(a3.y);
+                  const float2 g0 = gelu_grad_pair(a0.x, a0.y), g1 = gelu_grad_pair(a1.x, a1.y);
+                  const float2 g2 = gelu_grad_pair(a2.x, a2.y), g3 = gelu_grad_pair(a3.x, a3.y);
+                  v[q * 8] *= g0.x; v[q * 8 + 1] *= g0.y; v[q * 8 + 2] *= g1.x; v[q * 8 + 3] *= g1.y;
+                  v[q * 8 + 4] *= g2.x; v[q * 8 + 5] *= g2.y; v[q * 8 + 6] *= g3.x; v[q * 8 + 7] *= g3.y;
                 }
               }
             }
@@ -427,7 +581,7 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
 #pragma unroll
             for (int q = 0; q < 8; ++q)
               *reinterpret_cast<uint4*>(stg + rit * 128 + ((q ^ (rit & 7)) << 4)) =
-                  make_uint4(packed_aux[4 * q], packed_aux[4 * q + 1], packed_aux[4 * q + 2], packed_aux[4 * q + 3]);
+                  make_uint4(packed[4 * q], packed[4 * q + 1], packed[4 * q + 2], packed[4 * q + 3]);
             fence_proxy_async_smem();
             named_bar_sync(1 + half, 128);
             if (leader) {
@@ -435,6 +589,14 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
               tma_store_commit();
             }
             stores_issued = true;
+            // the activation is applied to the ROUNDED pre-activation (what the backward will see, and what autocast's
+            // 16-bit Linear output hands to nn.GELU) while TMA drains the staging buffer
+#pragma unroll
+            for (int i = 0; i < 32; ++i) {
+              float2 a = unpack2(packed[i], p.out_dtype);
+              gelu_pair(a.x, a.y);
+              packed[i] = pack2(a.x, a.y, p.out_dtype);
+            }
           }
           if (stores_issued && !aux_in) {  // the previous sub-tile must have been read out of the staging buffer
             if (leader) tma_store_wait_read<0>();
@@ -520,19 +682,21 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
   }
 }
 
-template <int BN, bool kBf16>
+template <int BN, bool kBf16, bool kAux>
 static int launch_gemm(const CUtensorMap& ma, const CUtensorMap& mb, const CUtensorMap& md, const CUtensorMap& mr,
                        const CUtensorMap& md2, const GemmParams& p, cudaStream_t stream) {
   using Cfg = GemmCfg<BN>;
-  auto kern = gemm_tn_kernel<BN, kBf16>;
-  static bool attr_set = false;  // per (BN, dtype) instantiation
+  constexpr int kSmem = Cfg::kSmemBytes + (kAux ? 2 * Cfg::kStoreStageBytes - Cfg::kStageBytes : 0);
+  static_assert(kSmem <= 227 * 1024, "GEMM shared memory budget");
+  auto kern = gemm_tn_kernel<BN, kBf16, kAux>;
+  static bool attr_set = false;  // per (BN, dtype, variant) instantiation
   if (!attr_set) {
-    VDK_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes));
+    VDK_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmem));
     attr_set = true;
   }
   const int num_tiles = ((p.M + kBM - 1) / kBM) * ((p.N + BN - 1) / BN) * p.split_k;
   const int grid = num_tiles < sm_count() ? num_tiles : sm_count();
-  kern<<<grid, kGemmThreads, Cfg::kSmemBytes, stream>>>(ma, mb, md, mr, md2, p);
+  kern<<<grid, kGemmThreads, kSmem, stream>>>(ma, mb, md, mr, md2, p);
   VDK_CUDA_OK(cudaGetLastError());
   return VDK_OK;
 }
@@ -623,8 +787,22 @@ int gemm_run(const vdk_gemm_desc& g, cudaStream_t s) {
                g.ln_eps, split, tma_store, g.trans_a ? 1 : 0, g.trans_b ? 1 : 0, g.split_k > 1 ? (long long)g.split_stride : 0ll,
                aux_out, (g.split_k > 1) ? 1 : 0};
   const bool bf = g.in_dtype == VDK_DTYPE_BF16;
-  if (wide) return bf ? launch_gemm<256, true>(ma, mb, md, mr, md2, p, s) : launch_gemm<256, false>(ma, mb, md, mr, md2, p, s);
-  return bf ? launch_gemm<128, true>(ma, mb, md, mr, md2, p, s) : launch_gemm<128, false>(ma, mb, md, mr, md2, p, s);
+  // which epilogues take the pipelined auxiliary-tile variant (VDK_GEMM_AUXPIPE: bit 0 aux_out, bit 1 MUL_GELU_GRAD,
+  // bit 2 SCALE_RESIDUAL; a tuning switch.  Measured at ConvNeXt-B
+  // shapes: the GELU' data gradient gains 24 %, the layer-scale + residual GEMM (K = 4C: mainloop-bound) loses 8 % to the
+  // missing stage, so the default is 3)
+  static const int aux_mask = [] {
+    const char* e = getenv("VDK_GEMM_AUXPIPE");
+    return e ? atoi(e) : 3;
+  }();
+  const bool aux = tma_store && ((aux_out && (aux_mask & 1)) || (g.epilogue == VDK_EPI_MUL_GELU_GRAD && (aux_mask & 2)) ||
+                                 (g.epilogue == VDK_EPI_SCALE_RESIDUAL && (aux_mask & 4)));
+  if (aux) {
+    if (wide) return bf ? launch_gemm<256, true, true>(ma, mb, md, mr, md2, p, s) : launch_gemm<256, false, true>(ma, mb, md, mr, md2, p, s);
+    return bf ? launch_gemm<128, true, true>(ma, mb, md, mr, md2, p, s) : launch_gemm<128, false, true>(ma, mb, md, mr, md2, p, s);
+  }
+  if (wide) return bf ? launch_gemm<256, true, false>(ma, mb, md, mr, md2, p, s) : launch_gemm<256, false, false>(ma, mb, md, mr, md2, p, s);
+  return bf ? launch_gemm<128, true, false>(ma, mb, md, mr, md2, p, s) : launch_gemm<128, false, false>(ma, mb, md, mr, md2, p, s);
 }
 
 }  // namespace vdk
