@@ -253,17 +253,19 @@ __device__ __forceinline__ float2 ld_dsmem_f2(const void* local_smem, uint32_t r
 
 constexpr int kDwTW = 7;
 
-template <int MODE>
+template <int MODE, int CHUNK>
 __global__ void __launch_bounds__(224, 3)
-dwconv7_chunk_kernel(const __grid_constant__ CUtensorMap map_x, int B, int H, int W, int C, int TH, int chunk, int nchunks,
+dwconv7_chunk_kernel(const __grid_constant__ CUtensorMap map_x, int B, int H, int W, int C, int TH, int nchunks,
                      const float* __restrict__ w49, const float* __restrict__ bias, const float* __restrict__ ln_w,
                      const float* __restrict__ ln_b, float eps, __nv_bfloat16* __restrict__ y, float* __restrict__ rstd_out,
                      const __nv_bfloat16* __restrict__ addend) {
   extern __shared__ uint8_t dwc_smem_raw[];
   uint8_t* smem = dwc_smem_raw + ((128u - (smem_u32(dwc_smem_raw) & 127u)) & 127u);
   constexpr int box_w = kDwTW + 6;
+  constexpr int chunk = CHUNK;  // compile-time: every shared-memory offset of the tap loop is an immediate
   const int tile_bytes = (TH + 6) * box_w * chunk * 2;
-  float2* part = reinterpret_cast<float2*>(smem + ((tile_bytes + 127) & ~127));  // [7 rows][8]: (mean, M2) per pixel
+  float* wsm = reinterpret_cast<float*>(smem + ((tile_bytes + 127) & ~127));     // [49][chunk] taps of this chunk
+  float2* part = reinterpret_cast<float2*>(wsm + 49 * chunk);                    // [7 rows][8]: (mean, M2) per pixel
   uint64_t* bar = reinterpret_cast<uint64_t*>(part + 7 * 8);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -294,35 +296,46 @@ dwconv7_chunk_kernel(const __grid_constant__ CUtensorMap map_x, int B, int H, in
     g4 = __ldg(reinterpret_cast<const float4*>(ln_w + c0));
     b4 = __ldg(reinterpret_cast<const float4*>(ln_b + c0));
   }
-  const int pix_stride = chunk * 2;
+  // the chunk's 49 x chunk taps: shared memory, while the tile is in flight
+  for (int i = threadIdx.x; i < 49 * (chunk / 4); i += blockDim.x) {
+    const int t = i / (chunk / 4), q = i - t * (chunk / 4);
+    *reinterpret_cast<float4*>(wsm + t * chunk + q * 4) = __ldg(reinterpret_cast<const float4*>(w49 + t * C + ck * chunk + q * 4));
+  }
+  __syncthreads();
+  constexpr int pix_stride = chunk * 2;
   const bool active = has_c && warp < TH && oy0 + warp < H;
-  float acc[kDwTW][4];
+  float2 acc[kDwTW][2];  // channel pairs (c0, c0+1), (c0+2, c0+3): the tap loop runs on FFMA2
 #pragma unroll
   for (int p = 0; p < kDwTW; ++p) {
-    acc[p][0] = bc.x; acc[p][1] = bc.y; acc[p][2] = bc.z; acc[p][3] = bc.w;
+    acc[p][0] = make_float2(bc.x, bc.y);
+    acc[p][1] = make_float2(bc.z, bc.w);
   }
   mbar_wait(bar, 0);
   if (active) {
     const uint8_t* tbase = smem + cl * 2;
 #pragma unroll 1
     for (int dy = 0; dy < 7; ++dy) {
-      float4 wrow[7];
+      float2 wlo[7], whi[7];
+      const float* wrow = wsm + dy * (7 * chunk) + cl;
 #pragma unroll
-      for (int dx = 0; dx < 7; ++dx) wrow[dx] = __ldg(reinterpret_cast<const float4*>(w49 + (dy * 7 + dx) * C + c0));
-      const uint8_t* rowp = tbase + static_cast<size_t>((warp + dy) * box_w) * pix_stride;
+      for (int dx = 0; dx < 7; ++dx) {
+        const float4 t = *reinterpret_cast<const float4*>(wrow + dx * chunk);
+        wlo[dx] = make_float2(t.x, t.y);
+        whi[dx] = make_float2(t.z, t.w);
+      }
+      const uint8_t* rowp = tbase + (warp + dy) * (box_w * pix_stride);
 #pragma unroll
       for (int ix = 0; ix < box_w; ++ix) {
         const uint2 t = *reinterpret_cast<const uint2*>(rowp + ix * pix_stride);
-        const float2 a = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&t.x));
-        const float2 c = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&t.y));
+        // bf16 -> fp32 is a 16-bit shift: one ALU op per value
+        const float2 a = make_float2(__uint_as_float(t.x << 16), __uint_as_float(t.x & 0xffff0000u));
+        const float2 c = make_float2(__uint_as_float(t.y << 16), __uint_as_float(t.y & 0xffff0000u));
 #pragma unroll
         for (int p = 0; p < kDwTW; ++p) {
           const int dx = ix - p;  // input column ix feeds output pixel p through tap dx
           if (dx >= 0 && dx < 7) {
-            acc[p][0] = fmaf(a.x, wrow[dx].x, acc[p][0]);
-            acc[p][1] = fmaf(a.y, wrow[dx].y, acc[p][1]);
-            acc[p][2] = fmaf(c.x, wrow[dx].z, acc[p][2]);
-            acc[p][3] = fmaf(c.y, wrow[dx].w, acc[p][3]);
+            acc[p][0] = ffma2(a, wlo[dx], acc[p][0]);
+            acc[p][1] = ffma2(c, whi[dx], acc[p][1]);
           }
         }
       }
@@ -335,7 +348,7 @@ dwconv7_chunk_kernel(const __grid_constant__ CUtensorMap map_x, int B, int H, in
         const int ox = ox0 + p;
         if (ox >= W) continue;
         const int64_t off = ((static_cast<int64_t>(b) * H + oy0 + warp) * W + ox) * C + c0;
-        float o0 = acc[p][0], o1 = acc[p][1], o2 = acc[p][2], o3 = acc[p][3];
+        float o0 = acc[p][0].x, o1 = acc[p][0].y, o2 = acc[p][1].x, o3 = acc[p][1].y;
         if (addend) {
           const uint2 t = __ldg(reinterpret_cast<const uint2*>(addend + off));
           const float2 a = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&t.x));
@@ -356,18 +369,16 @@ dwconv7_chunk_kernel(const __grid_constant__ CUtensorMap map_x, int B, int H, in
   const float inv_chunk = 1.0f / static_cast<float>(chunk), inv_c = 1.0f / static_cast<float>(C);
 #pragma unroll
   for (int p = 0; p < kDwTW; ++p) {
-    const float s = warp_sum(active ? (acc[p][0] + acc[p][1]) + (acc[p][2] + acc[p][3]) : 0.f);
+    const float s = warp_sum(active ? (acc[p][0].x + acc[p][0].y) + (acc[p][1].x + acc[p][1].y) : 0.f);
     mean[p] = s * inv_chunk;
   }
 #pragma unroll
   for (int p = 0; p < kDwTW; ++p) {
     float q = 0.f;
     if (active) {
-#pragma unroll
-      for (int c = 0; c < 4; ++c) {
-        const float d = acc[p][c] - mean[p];
-        q = fmaf(d, d, q);
-      }
+      const float d0 = acc[p][0].x - mean[p], d1 = acc[p][0].y - mean[p];
+      const float d2 = acc[p][1].x - mean[p], d3 = acc[p][1].y - mean[p];
+      q = fmaf(d0, d0, fmaf(d1, d1, fmaf(d2, d2, d3 * d3)));
     }
     rstd[p] = warp_sum(q);  // centred sum of squares of this chunk, for now
   }
@@ -403,10 +414,10 @@ dwconv7_chunk_kernel(const __grid_constant__ CUtensorMap map_x, int B, int H, in
       const int64_t pix = (static_cast<int64_t>(b) * H + oy0 + warp) * W + ox;
       if (rstd_out != nullptr && lane == 0 && ck == 0) rstd_out[pix] = rstd[p];
       __nv_bfloat16* dst = y + pix * C + c0;
-      __nv_bfloat162 lo = __floats2bfloat162_rn((acc[p][0] - mean[p]) * rstd[p] * g4.x + b4.x,
-                                                (acc[p][1] - mean[p]) * rstd[p] * g4.y + b4.y);
-      __nv_bfloat162 hi = __floats2bfloat162_rn((acc[p][2] - mean[p]) * rstd[p] * g4.z + b4.z,
-                                                (acc[p][3] - mean[p]) * rstd[p] * g4.w + b4.w);
+      __nv_bfloat162 lo = __floats2bfloat162_rn((acc[p][0].x - mean[p]) * rstd[p] * g4.x + b4.x,
+                                                (acc[p][0].y - mean[p]) * rstd[p] * g4.y + b4.y);
+      __nv_bfloat162 hi = __floats2bfloat162_rn((acc[p][1].x - mean[p]) * rstd[p] * g4.z + b4.z,
+                                                (acc[p][1].y - mean[p]) * rstd[p] * g4.w + b4.w);
       uint2 t;
       t.x = *reinterpret_cast<uint32_t*>(&lo);
       t.y = *reinterpret_cast<uint32_t*>(&hi);
@@ -590,8 +601,7 @@ int vdk::launch_dwconv7(int mode, const __nv_bfloat16* x, int batch, int H, int 
   {
     // channel-chunked kernel (clustered LayerNorm) whenever C splits into <= 16 chunks of <= 128 channels
     int chunk = 0;
-    if (C <= 128) chunk = C;
-    else if (C % 128 == 0) chunk = 128;
+    if (C % 128 == 0) chunk = 128;
     else if (C % 96 == 0) chunk = 96;
     else if (C % 64 == 0) chunk = 64;
     static const bool use_chunked = [] {
@@ -604,7 +614,7 @@ int vdk::launch_dwconv7(int mode, const __nv_bfloat16* x, int batch, int H, int 
       CUtensorMap mx;
       int rc = make_tma_nhwc_16bit(&mx, x, batch, H, W, C, TH + 6, kDwTW + 6, chunk);
       if (rc != VDK_OK) return rc;
-      const int smem = (((TH + 6) * (kDwTW + 6) * chunk * 2 + 127) & ~127) + 7 * 8 * 8 + 16 + 128;
+      const int smem = (((TH + 6) * (kDwTW + 6) * chunk * 2 + 127) & ~127) + 49 * chunk * 4 + 7 * 8 * 8 + 16 + 128;
       const unsigned grid = static_cast<unsigned>(batch) * ((H + TH - 1) / TH) * ((W + kDwTW - 1) / kDwTW) * nchunks;
       cudaLaunchConfig_t cfg{};
       cfg.gridDim = dim3(grid);
@@ -618,18 +628,23 @@ int vdk::launch_dwconv7(int mode, const __nv_bfloat16* x, int batch, int H, int 
       attr[0].val.clusterDim.z = 1;
       cfg.attrs = attr;
       cfg.numAttrs = 1;
+#define VDK_DWC(MODEV, CHV)                                                                                              \
+  do {                                                                                                                   \
+    auto kern = dwconv7_chunk_kernel<MODEV, CHV>;                                                                        \
+    VDK_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 80 * 1024));                     \
+    if (MODEV == 0 && nchunks > 8) VDK_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeNonPortableClusterSizeAllowed, 1)); \
+    VDK_CUDA_OK(cudaLaunchKernelEx(&cfg, kern, mx, batch, H, W, C, TH, nchunks, w49, bias, ln_w, ln_b, eps, y, rstd_out, addend)); \
+  } while (0)
       if (mode == 0) {
-        auto kern = dwconv7_chunk_kernel<0>;
-        VDK_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024));
-        if (nchunks > 8) VDK_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeNonPortableClusterSizeAllowed, 1));
-        VDK_CUDA_OK(cudaLaunchKernelEx(&cfg, kern, mx, batch, H, W, C, TH, chunk, nchunks, w49, bias, ln_w, ln_b, eps, y, rstd_out,
-                                       addend));
+        if (chunk == 128) VDK_DWC(0, 128);
+        else if (chunk == 96) VDK_DWC(0, 96);
+        else VDK_DWC(0, 64);
       } else {
-        auto kern = dwconv7_chunk_kernel<1>;
-        VDK_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024));
-        VDK_CUDA_OK(cudaLaunchKernelEx(&cfg, kern, mx, batch, H, W, C, TH, chunk, nchunks, w49, bias, ln_w, ln_b, eps, y, rstd_out,
-                                       addend));
+        if (chunk == 128) VDK_DWC(1, 128);
+        else if (chunk == 96) VDK_DWC(1, 96);
+        else VDK_DWC(1, 64);
       }
+#undef VDK_DWC
       return VDK_OK;
     }
   }

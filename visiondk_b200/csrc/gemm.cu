@@ -187,19 +187,29 @@ __device__ __forceinline__ void epi_math(const GemmParams& p, float (&v)[32], in
 // pre-activation copy it writes).  That variant trades one mainloop stage for two more 16 KB staging buffers, so the
 // auxiliary input of the NEXT sub-tile is prefetched by TMA while this one is computed and stored, and the two output
 // streams never wait on each other's staging buffer (these GEMMs have short K loops: the epilogue sets their pace).
-template <int BN, bool kBf16, bool kAux>
+// kPair: the CTAs of a 2-cluster (one TPC) run ONE UMMA of M = 256 (tcgen05 cta_group::2): each CTA stages its own 128
+// rows of A and HALF of the B tile, the leader's MMA thread reads both shared memories, and each CTA's TMEM receives
+// its 128 accumulator rows.  Per output tile that halves the B bytes every SM pulls through L2 and shrinks a stage to
+// 32 KB, so six stages (instead of four) cover the TMA latency at the same shared-memory budget.
+template <int BN, bool kBf16, bool kAux, bool kPair>
 __global__ void __launch_bounds__(kGemmThreads, 1)
 gemm_tn_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b,
                const __grid_constant__ CUtensorMap map_d, const __grid_constant__ CUtensorMap map_r,
                const __grid_constant__ CUtensorMap map_d2, const GemmParams p) {
   using Cfg = GemmCfg<BN>;
-  constexpr int kStages = Cfg::kStages - (kAux ? 1 : 0);
+  constexpr int kStageB = kPair ? Cfg::kStageB / 2 : Cfg::kStageB;  // B rows staged by this CTA
+  constexpr int kStageBytes = Cfg::kStageA + kStageB;
+  constexpr int kStages = kPair ? (kAux ? 5 : 6) : Cfg::kStages - (kAux ? 1 : 0);
   constexpr int kStoreBufs = kAux ? 4 : 2;
+  constexpr int kTM = kPair ? 2 * kBM : kBM;  // rows of one work item (both CTAs of a pair)
+  const int rank = kPair ? static_cast<int>(cluster_ctarank()) : 0;
+  const int tile0 = kPair ? static_cast<int>(blockIdx.x >> 1) : static_cast<int>(blockIdx.x);
+  const int tile_step = kPair ? static_cast<int>(gridDim.x >> 1) : static_cast<int>(gridDim.x);
   extern __shared__ uint8_t smem_raw[];
   // align inside the dynamic smem window without a pointer->integer->pointer round trip (which would demote every
   // later access to generic LD/ST)
   uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
-  uint8_t* smem_store = smem + kStages * Cfg::kStageBytes;
+  uint8_t* smem_store = smem + kStages * kStageBytes;
   uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem_store + kStoreBufs * Cfg::kStoreStageBytes);
   uint64_t* empty_bar = full_bar + kStages;
   uint64_t* tmem_full = empty_bar + kStages;
@@ -210,7 +220,7 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
 
-  const int num_m = (p.M + kBM - 1) / kBM;
+  const int num_m = (p.M + kTM - 1) / kTM;
   const int num_n = (p.N + BN - 1) / BN;
   const int num_kb_total = (p.K + kBK - 1) / kBK;
   const int kb_per_split = (num_kb_total + p.split_k - 1) / p.split_k;
@@ -229,14 +239,18 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
     }
     for (int i = 0; i < 2; ++i) {
       mbar_init(&tmem_full[i], 1);
-      mbar_init(&tmem_empty[i], 256);
+      mbar_init(&tmem_empty[i], kPair ? 16 : 256);  // pair: one arrival per epilogue warp of both CTAs
       mbar_init(&res_bar[i], 1);
     }
     fence_mbar_init();
   }
-  if (warp == 1) tmem_alloc<Cfg::kTmemCols>(tmem_ptr);
+  if (warp == 1) {
+    if (kPair) tmem_alloc_pair<Cfg::kTmemCols>(tmem_ptr);
+    else tmem_alloc<Cfg::kTmemCols>(tmem_ptr);
+  }
   tc_fence_before();
-  __syncthreads();
+  if (kPair) cluster_sync_all();  // the peer's barriers are initialised before any TMA / commit signals them
+  else __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_ptr;
 
@@ -245,17 +259,35 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
     if (lane == 0) {
       int stage = 0;
       uint32_t phase = 0;
-      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+      for (int tile = tile0; tile < num_tiles; tile += tile_step) {
         const int mn = tile % (num_m * num_n), split = tile / (num_m * num_n);
-        const int m0 = (mn / num_n) * kBM;
-        const int n0 = (mn % num_n) * BN;
+        const int m0 = (mn / num_n) * kTM + rank * kBM;
+        const int n0 = (mn % num_n) * BN + (kPair ? rank * (BN / 2) : 0);  // first B row this CTA stages
         const int kb0 = split * kb_per_split;
         const int kb1 = min(kb0 + kb_per_split, num_kb_total);
         for (int kb = kb0; kb < kb1; ++kb) {
           mbar_wait(&empty_bar[stage], phase ^ 1);
-          uint8_t* sa = smem + stage * Cfg::kStageBytes;
+          uint8_t* sa = smem + stage * kStageBytes;
           uint8_t* sb = sa + Cfg::kStageA;
-          mbar_arrive_expect_tx(&full_bar[stage], Cfg::kStageBytes);
+          if (kPair) {
+            // both CTAs' bytes are credited to the LEADER's full barrier, which its MMA thread waits on
+            if (rank == 0) mbar_arrive_expect_tx(&full_bar[stage], 2 * kStageBytes);
+            if (p.a_mn) {
+#pragma unroll
+              for (int j = 0; j < kBM / 64; ++j)
+                tma_load_2d_pair(sa + j * 8192, &map_a, &full_bar[stage], m0 + j * 64, kb * kBK, kEvictNormal);
+            } else {
+              tma_load_2d_pair(sa, &map_a, &full_bar[stage], kb * kBK, m0, kEvictNormal);
+            }
+            if (p.b_mn) {
+#pragma unroll
+              for (int j = 0; j < BN / 128; ++j)
+                tma_load_2d_pair(sb + j * 8192, &map_b, &full_bar[stage], n0 + j * 64, kb * kBK, kEvictLast);
+            } else {
+              tma_load_2d_pair(sb, &map_b, &full_bar[stage], kb * kBK, n0, kEvictLast);
+            }
+          } else {
+          mbar_arrive_expect_tx(&full_bar[stage], kStageBytes);
           if (p.a_mn) {  // [K,M] storage: 64-wide M blocks x 64 contraction rows, 8 KB each
 #pragma unroll
             for (int j = 0; j < kBM / 64; ++j) tma_load_2d(sa + j * 8192, &map_a, &full_bar[stage], m0 + j * 64, kb * kBK, kEvictNormal);
@@ -268,6 +300,7 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
           } else {
             tma_load_2d(sb, &map_b, &full_bar[stage], kb * kBK, n0, kEvictLast);
           }
+          }
           if (++stage == kStages) {
             stage = 0;
             phase ^= 1;
@@ -277,12 +310,12 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
     }
   } else if (warp == 1) {
     // ===================== MMA issuer =====================
-    if (lane == 0) {
-      const uint32_t idesc = umma_idesc_f16<kBf16>(kBM, BN, p.a_mn ? 1u : 0u, p.b_mn ? 1u : 0u);
+    if (lane == 0 && rank == 0) {  // pair: only the leader CTA issues (for both)
+      const uint32_t idesc = umma_idesc_f16<kBf16>(kTM, BN, p.a_mn ? 1u : 0u, p.b_mn ? 1u : 0u);
       int stage = 0;
       uint32_t phase = 0;
       int it = 0;
-      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
+      for (int tile = tile0; tile < num_tiles; tile += tile_step, ++it) {
         const int acc = it & 1;
         const uint32_t acc_phase = (it >> 1) & 1;
         mbar_wait(&tmem_empty[acc], acc_phase ^ 1);
@@ -294,7 +327,7 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
         for (int kb = kb0; kb < kb1; ++kb) {
           mbar_wait(&full_bar[stage], phase);
           tc_fence_after();
-          const uint32_t sa = smem_u32(smem + stage * Cfg::kStageBytes);
+          const uint32_t sa = smem_u32(smem + stage * kStageBytes);
           const uint32_t sb = sa + Cfg::kStageA;
           const uint64_t da = p.a_mn ? umma_desc_mn_sw128(sa, 8192) : umma_desc_k_sw128(sa);
           const uint64_t db = p.b_mn ? umma_desc_mn_sw128(sb, 8192) : umma_desc_k_sw128(sb);
@@ -302,15 +335,21 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
           // units); MN-major = two 8-row groups of 1024 bytes (+128)
           const uint32_t step_a = p.a_mn ? 128u : 2u, step_b = p.b_mn ? 128u : 2u;
 #pragma unroll
-          for (int k = 0; k < kBK / 16; ++k)
-            umma_f16_ss(tmem_d, da + step_a * k, db + step_b * k, idesc, (kb > kb0 || k > 0) ? 1u : 0u);
-          umma_commit(&empty_bar[stage]);  // smem slot reusable once these MMAs retire
+          for (int k = 0; k < kBK / 16; ++k) {
+            if (kPair) umma_f16_ss_pair(tmem_d, da + step_a * k, db + step_b * k, idesc, (kb > kb0 || k > 0) ? 1u : 0u);
+            else umma_f16_ss(tmem_d, da + step_a * k, db + step_b * k, idesc, (kb > kb0 || k > 0) ? 1u : 0u);
+          }
+          // smem slot reusable once these MMAs retire (pair: in both CTAs)
+          if (kPair) umma_commit_pair(&empty_bar[stage]);
+          else umma_commit(&empty_bar[stage]);
           if (++stage == kStages) {
             stage = 0;
             phase ^= 1;
           }
         }
-        umma_commit(&tmem_full[acc]);  // accumulator complete -> epilogue
+        // accumulator complete -> epilogue (pair: of both CTAs)
+        if (kPair) umma_commit_pair(&tmem_full[acc]);
+        else umma_commit(&tmem_full[acc]);
       }
     }
   } else {
@@ -325,26 +364,26 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
       sub += 2;
       while (t < num_tiles) {
         if (sub < BN / 64 && ((t % (num_m * num_n)) % num_n) * BN + sub * 64 < p.N) return true;
-        t += gridDim.x;
+        t += tile_step;
         sub = half;
       }
       return false;
     };
     if (kAux && p.tma_store && (p.epilogue == VDK_EPI_SCALE_RESIDUAL || p.epilogue == VDK_EPI_MUL_GELU_GRAD) &&
         threadIdx.x == 64 + half * 128) {
-      int nt = blockIdx.x, ns = half - 2;
+      int nt = tile0, ns = half - 2;
       if (next_sub(nt, ns)) {
         const int nmn = nt % (num_m * num_n);
         mbar_arrive_expect_tx(&res_bar[half], Cfg::kStoreStageBytes);
         tma_load_2d(smem_store + (2 + half) * Cfg::kStoreStageBytes, &map_r, &res_bar[half], (nmn % num_n) * BN + ns * 64,
-                    (nmn / num_n) * kBM, kEvictFirst);
+                    (nmn / num_n) * kTM + rank * kBM, kEvictFirst);
       }
     }
-    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
+    for (int tile = tile0; tile < num_tiles; tile += tile_step, ++it) {
       const int acc = it & 1;
       const uint32_t acc_phase = (it >> 1) & 1;
       const int mn = tile % (num_m * num_n);
-      const int m0 = (mn / num_n) * kBM;
+      const int m0 = (mn / num_n) * kTM + rank * kBM;
       const int n0 = (mn % num_n) * BN;
       const int row = m0 + lane_base + lane;
       mbar_wait(&tmem_full[acc], acc_phase);
@@ -413,7 +452,8 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
               if (next_sub(nt, ns)) {
                 const int nmn = nt % (num_m * num_n);
                 mbar_arrive_expect_tx(&res_bar[half], Cfg::kStoreStageBytes);
-                tma_load_2d(stg2, &map_r, &res_bar[half], (nmn % num_n) * BN + ns * 64, (nmn / num_n) * kBM, kEvictFirst);
+                tma_load_2d(stg2, &map_r, &res_bar[half], (nmn % num_n) * BN + ns * 64, (nmn / num_n) * kTM + rank * kBM,
+                            kEvictFirst);
               }
             }
           }
@@ -669,32 +709,59 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
         }
       }
       tc_fence_before();
-      mbar_arrive(&tmem_empty[acc]);
+      if (kPair) {  // one arrival per warp on the LEADER's barrier (its MMA thread owns both CTAs' accumulators)
+        __syncwarp();
+        if (lane == 0) mbar_arrive_leader(&tmem_empty[acc]);
+      } else {
+        mbar_arrive(&tmem_empty[acc]);
+      }
     }
     if (p.tma_store && stores_issued && threadIdx.x == 64 + half * 128) tma_store_wait<0>();
   }
 
   tc_fence_before();
-  __syncthreads();
+  if (kPair) cluster_sync_all();  // neither CTA frees TMEM / exits while the pair's MMAs or remote arrivals are in flight
+  else __syncthreads();
   if (warp == 1) {
     tc_fence_after();
-    tmem_dealloc<Cfg::kTmemCols>(tmem_base);
+    if (kPair) tmem_dealloc_pair<Cfg::kTmemCols>(tmem_base);
+    else tmem_dealloc<Cfg::kTmemCols>(tmem_base);
   }
 }
 
-template <int BN, bool kBf16, bool kAux>
+template <int BN, bool kBf16, bool kAux, bool kPair>
 static int launch_gemm(const CUtensorMap& ma, const CUtensorMap& mb, const CUtensorMap& md, const CUtensorMap& mr,
                        const CUtensorMap& md2, const GemmParams& p, cudaStream_t stream) {
   using Cfg = GemmCfg<BN>;
-  constexpr int kSmem = Cfg::kSmemBytes + (kAux ? 2 * Cfg::kStoreStageBytes - Cfg::kStageBytes : 0);
+  constexpr int kStageBytes = Cfg::kStageA + (kPair ? Cfg::kStageB / 2 : Cfg::kStageB);
+  constexpr int kStages = kPair ? (kAux ? 5 : 6) : Cfg::kStages - (kAux ? 1 : 0);
+  constexpr int kSmem = kStages * kStageBytes + (kAux ? 4 : 2) * Cfg::kStoreStageBytes + (2 * kStages + 6) * 8 + 16 + 1024;
   static_assert(kSmem <= 227 * 1024, "GEMM shared memory budget");
-  auto kern = gemm_tn_kernel<BN, kBf16, kAux>;
+  auto kern = gemm_tn_kernel<BN, kBf16, kAux, kPair>;
   static bool attr_set = false;  // per (BN, dtype, variant) instantiation
   if (!attr_set) {
     VDK_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmem));
     attr_set = true;
   }
-  const int num_tiles = ((p.M + kBM - 1) / kBM) * ((p.N + BN - 1) / BN) * p.split_k;
+  const int tm = kPair ? 2 * kBM : kBM;
+  const int num_tiles = ((p.M + tm - 1) / tm) * ((p.N + BN - 1) / BN) * p.split_k;
+  if (kPair) {
+    const int pairs = std::min(num_tiles, sm_count() / 2);
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = dim3(2 * pairs);
+    cfg.blockDim = dim3(kGemmThreads);
+    cfg.dynamicSmemBytes = kSmem;
+    cfg.stream = stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = 2;
+    attr[0].val.clusterDim.y = 1;
+    attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    VDK_CUDA_OK(cudaLaunchKernelEx(&cfg, kern, ma, mb, md, mr, md2, p));
+    return VDK_OK;
+  }
   const int grid = num_tiles < sm_count() ? num_tiles : sm_count();
   kern<<<grid, kGemmThreads, kSmem, stream>>>(ma, mb, md, mr, md2, p);
   VDK_CUDA_OK(cudaGetLastError());
@@ -763,8 +830,14 @@ int gemm_run(const vdk_gemm_desc& g, cudaStream_t s) {
   int rc = g.trans_a ? make_tma_2d_16bit(&ma, g.A, (uint64_t)g.K, (uint64_t)g.M, (uint64_t)g.lda, kBK, 64)
                      : make_tma_2d_16bit(&ma, g.A, (uint64_t)g.M, (uint64_t)g.K, (uint64_t)g.lda, kBM, kBK);
   if (rc != VDK_OK) return rc;
+  // CTA pairs (one UMMA of M = 256 per 2-cluster) for the wide tile whenever there are at least two row blocks
+  static const int pair_mode = [] {
+    const char* e = getenv("VDK_GEMM_PAIR");
+    return e ? atoi(e) : 1;
+  }();
+  const bool pair = wide && pair_mode != 0 && g.M > kBM;
   rc = g.trans_b ? make_tma_2d_16bit(&mb, g.B, (uint64_t)g.K, (uint64_t)g.N, (uint64_t)g.ldb, kBK, 64)
-                 : make_tma_2d_16bit(&mb, g.B, (uint64_t)g.N, (uint64_t)g.K, (uint64_t)g.ldb, BN, kBK);
+                 : make_tma_2d_16bit(&mb, g.B, (uint64_t)g.N, (uint64_t)g.K, (uint64_t)g.ldb, pair ? BN / 2 : BN, kBK);
   if (rc != VDK_OK) return rc;
   const int tma_store = (g.out_dtype != VDK_DTYPE_FP32 && g.split_k <= 1) ? 1 : 0;
   CUtensorMap md = ma;  // placeholder when unused
@@ -797,12 +870,16 @@ int gemm_run(const vdk_gemm_desc& g, cudaStream_t s) {
   }();
   const bool aux = tma_store && ((aux_out && (aux_mask & 1)) || (g.epilogue == VDK_EPI_MUL_GELU_GRAD && (aux_mask & 2)) ||
                                  (g.epilogue == VDK_EPI_SCALE_RESIDUAL && (aux_mask & 4)));
-  if (aux) {
-    if (wide) return bf ? launch_gemm<256, true, true>(ma, mb, md, mr, md2, p, s) : launch_gemm<256, false, true>(ma, mb, md, mr, md2, p, s);
-    return bf ? launch_gemm<128, true, true>(ma, mb, md, mr, md2, p, s) : launch_gemm<128, false, true>(ma, mb, md, mr, md2, p, s);
+  if (pair) {
+    if (aux) return bf ? launch_gemm<256, true, true, true>(ma, mb, md, mr, md2, p, s) : launch_gemm<256, false, true, true>(ma, mb, md, mr, md2, p, s);
+    return bf ? launch_gemm<256, true, false, true>(ma, mb, md, mr, md2, p, s) : launch_gemm<256, false, false, true>(ma, mb, md, mr, md2, p, s);
   }
-  if (wide) return bf ? launch_gemm<256, true, false>(ma, mb, md, mr, md2, p, s) : launch_gemm<256, false, false>(ma, mb, md, mr, md2, p, s);
-  return bf ? launch_gemm<128, true, false>(ma, mb, md, mr, md2, p, s) : launch_gemm<128, false, false>(ma, mb, md, mr, md2, p, s);
+  if (aux) {
+    if (wide) return bf ? launch_gemm<256, true, true, false>(ma, mb, md, mr, md2, p, s) : launch_gemm<256, false, true, false>(ma, mb, md, mr, md2, p, s);
+    return bf ? launch_gemm<128, true, true, false>(ma, mb, md, mr, md2, p, s) : launch_gemm<128, false, true, false>(ma, mb, md, mr, md2, p, s);
+  }
+  if (wide) return bf ? launch_gemm<256, true, false, false>(ma, mb, md, mr, md2, p, s) : launch_gemm<256, false, false, false>(ma, mb, md, mr, md2, p, s);
+  return bf ? launch_gemm<128, true, false, false>(ma, mb, md, mr, md2, p, s) : launch_gemm<128, false, false, false>(ma, mb, md, mr, md2, p, s);
 }
 
 }  // namespace vdk

@@ -283,11 +283,14 @@ constexpr int kWgT = 14;
 constexpr int kWgC = 64;
 constexpr int kWgR = 7;  // strip length (pixels) = taps per filter row
 
+// TT: compile-time tile edge (14 or 7: every shared-memory offset an immediate, no bounds predicates) or 0 = runtime
+template <int TT>
 __global__ void __launch_bounds__(224)
 dwconv7_wgrad_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant__ CUtensorMap map_g, int B, int H,
-                     int W, int C, int T, int ipc, float* __restrict__ dw49, float* __restrict__ dbias) {
+                     int W, int C, int T_rt, int ipc, float* __restrict__ dw49, float* __restrict__ dbias) {
   extern __shared__ uint8_t wg_raw[];
   uint8_t* smem = wg_raw + ((128u - (smem_u32(wg_raw) & 127u)) & 127u);
+  const int T = TT > 0 ? TT : T_rt;
   const int halo = T + 6;
   const int nh = (T + kWgR - 1) / kWgR;   // strips per tile row
   const int planes = 7 * nh;              // (half, dy) pairs
@@ -321,11 +324,12 @@ dwconv7_wgrad_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_con
   const bool active = plane < planes;
   const int hh = plane / 7, dy = plane - hh * 7;
   const int px0 = hh * kWgR;
-  float acc[7][4];
+  float2 acc[7][2];  // channel pairs: the product loop runs on FFMA2
 #pragma unroll
-  for (int dx = 0; dx < 7; ++dx)
-#pragma unroll
-    for (int c = 0; c < 4; ++c) acc[dx][c] = 0.f;
+  for (int dx = 0; dx < 7; ++dx) {
+    acc[dx][0] = make_float2(0.f, 0.f);
+    acc[dx][1] = make_float2(0.f, 0.f);
+  }
   float bsum[4] = {0.f, 0.f, 0.f, 0.f};
 
   uint32_t phase = 0;
@@ -340,37 +344,36 @@ dwconv7_wgrad_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_con
     if (active) {
 #pragma unroll 1
       for (int py = 0; py < T; ++py) {
-        float g[kWgR][4], x[kWgR + 6][4];
+        float2 g[kWgR][2], x[kWgR + 6][2];
         const uint8_t* gr = sg + ((py * T + px0) * kWgC + quad * 4) * 2;
 #pragma unroll
         for (int r = 0; r < kWgR; ++r) {
           uint2 t = make_uint2(0u, 0u);
-          if (px0 + r < T) t = *reinterpret_cast<const uint2*>(gr + r * kWgC * 2);
-          const float2 lo = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&t.x));
-          const float2 hi = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&t.y));
-          g[r][0] = lo.x; g[r][1] = lo.y; g[r][2] = hi.x; g[r][3] = hi.y;
+          if (TT > 0 || px0 + r < T) t = *reinterpret_cast<const uint2*>(gr + r * kWgC * 2);
+          g[r][0] = make_float2(__uint_as_float(t.x << 16), __uint_as_float(t.x & 0xffff0000u));  // bf16 -> fp32
+          g[r][1] = make_float2(__uint_as_float(t.y << 16), __uint_as_float(t.y & 0xffff0000u));
         }
         const uint8_t* xr = sx + (((py + dy) * halo + px0) * kWgC + quad * 4) * 2;
 #pragma unroll
         for (int i = 0; i < kWgR + 6; ++i) {
           uint2 t = make_uint2(0u, 0u);
-          if (px0 + i < halo) t = *reinterpret_cast<const uint2*>(xr + i * kWgC * 2);
-          const float2 lo = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&t.x));
-          const float2 hi = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&t.y));
-          x[i][0] = lo.x; x[i][1] = lo.y; x[i][2] = hi.x; x[i][3] = hi.y;
+          if (TT > 0 || px0 + i < halo) t = *reinterpret_cast<const uint2*>(xr + i * kWgC * 2);
+          x[i][0] = make_float2(__uint_as_float(t.x << 16), __uint_as_float(t.x & 0xffff0000u));
+          x[i][1] = make_float2(__uint_as_float(t.y << 16), __uint_as_float(t.y & 0xffff0000u));
         }
         if (dy == 0) {
 #pragma unroll
-          for (int r = 0; r < kWgR; ++r)
-#pragma unroll
-            for (int c = 0; c < 4; ++c) bsum[c] += g[r][c];
+          for (int r = 0; r < kWgR; ++r) {
+            bsum[0] += g[r][0].x; bsum[1] += g[r][0].y; bsum[2] += g[r][1].x; bsum[3] += g[r][1].y;
+          }
         }
 #pragma unroll
         for (int r = 0; r < kWgR; ++r)
 #pragma unroll
-          for (int dx = 0; dx < 7; ++dx)
-#pragma unroll
-            for (int c = 0; c < 4; ++c) acc[dx][c] = fmaf(g[r][c], x[r + dx][c], acc[dx][c]);
+          for (int dx = 0; dx < 7; ++dx) {
+            acc[dx][0] = ffma2(g[r][0], x[r + dx][0], acc[dx][0]);
+            acc[dx][1] = ffma2(g[r][1], x[r + dx][1], acc[dx][1]);
+          }
       }
     }
     __syncthreads();  // every read of this image's tiles is done before the next TMA (or the reduction) overwrites them
@@ -379,8 +382,8 @@ dwconv7_wgrad_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_con
   if (active) {
 #pragma unroll
     for (int dx = 0; dx < 7; ++dx)
-#pragma unroll
-      for (int c = 0; c < 4; ++c) red[(plane * 7 + dx) * kWgC + quad * 4 + c] = acc[dx][c];
+      *reinterpret_cast<float4*>(red + (plane * 7 + dx) * kWgC + quad * 4) =
+          make_float4(acc[dx][0].x, acc[dx][0].y, acc[dx][1].x, acc[dx][1].y);
     if (dy == 0) {
 #pragma unroll
       for (int c = 0; c < 4; ++c) red[(planes * 7 + hh) * kWgC + quad * 4 + c] = bsum[c];
@@ -413,17 +416,17 @@ int launch_dwconv7_wgrad(const __nv_bfloat16* x, const __nv_bfloat16* dconv, int
   const int halo = T + 6, nh = (T + kWgR - 1) / kWgR, planes = 7 * nh;
   const int x_bytes = halo * halo * kWgC * 2, red_bytes = (planes * 7 + nh) * kWgC * 4;
   const int smem = ((std::max(x_bytes, red_bytes) + 127) & ~127) + ((T * T * kWgC * 2 + 127) & ~127) + 16 + 128;
-  static bool attr = false;
-  if (!attr) {
-    VDK_CUDA_OK(cudaFuncSetAttribute(dwconv7_wgrad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024));
-    attr = true;
-  }
+  VDK_CUDA_OK(cudaFuncSetAttribute(dwconv7_wgrad_kernel<14>, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024));
+  VDK_CUDA_OK(cudaFuncSetAttribute(dwconv7_wgrad_kernel<7>, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024));
+  VDK_CUDA_OK(cudaFuncSetAttribute(dwconv7_wgrad_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024));
   // images per CTA: keep >= ~4 CTAs per SM, and amortise the final atomics over as many images as that allows
   const int64_t per_image = static_cast<int64_t>((H + T - 1) / T) * ((W + T - 1) / T) * (C / kWgC);
   const int ipc = static_cast<int>(std::max<int64_t>(1, std::min<int64_t>(16, (per_image * B) / (sm_count() * 4))));
   const unsigned grid = static_cast<unsigned>(((B + ipc - 1) / ipc) * per_image);
   const int threads = ((16 * planes + 31) / 32) * 32;
-  dwconv7_wgrad_kernel<<<grid, threads, smem, s>>>(mx, mg, B, H, W, C, T, ipc, dw49, dbias);
+  if (T == 14) dwconv7_wgrad_kernel<14><<<grid, threads, smem, s>>>(mx, mg, B, H, W, C, T, ipc, dw49, dbias);
+  else if (T == 7) dwconv7_wgrad_kernel<7><<<grid, threads, smem, s>>>(mx, mg, B, H, W, C, T, ipc, dw49, dbias);
+  else dwconv7_wgrad_kernel<0><<<grid, threads, smem, s>>>(mx, mg, B, H, W, C, T, ipc, dw49, dbias);
   VDK_CUDA_OK(cudaGetLastError());
   return VDK_OK;
 }
