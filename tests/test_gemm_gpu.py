@@ -171,3 +171,21 @@ def test_gemm_split_k_slabs_are_deterministic(lib):
     assert torch.equal(outs[0], outs[1])
     ref = a.float() @ w.float().t()
     assert (outs[0] - ref).abs().max().item() <= 2e-3 * K ** 0.5 * 0.05 + 1e-3
+
+
+@pytest.mark.parametrize("env", [{"VDK_GEMM_PAIR": "2"}, {"VDK_GEMM_PAIR": "0", "VDK_GEMM_AUXPIPE": "7"},
+                                 {"VDK_GEMM_PAIR": "0", "VDK_GEMM_AUXPIPE": "0"}])
+def test_gemm_kernel_variants_in_subprocess(env):
+    """The variant switches are read once per process (the defaults pick per shape): re-run the epilogue / layout tests of
+    this file and the training-GEMM forms with the CTA-pair kernel forced on, and with the pipelined auxiliary epilogue
+    forced on / off, so every instantiation is parity-checked wherever the default policy happens to route a shape."""
+    import os
+    import subprocess
+    import sys
+    here = os.path.dirname(os.path.abspath(__file__))
+    e = dict(os.environ)
+    e.update(env)
+    cmd = [sys.executable, "-m", "pytest", "-x", "-q", "-p", "no:cacheprovider", os.path.join(here, "test_gemm_gpu.py"),
+           os.path.join(here, "test_convnext_train_gpu.py"), "-k", "not subprocess and (gemm or split or trans)"]
+    r = subprocess.run(cmd, env=e, capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-2000:]

@@ -78,6 +78,10 @@ kernels = {
                                                            aux=hpre.data_ptr()), 8.0 * M * Cn * Cn, 2.0 * M * Cn * 9),
     "fc1 fwd (GELU only)": (lambda: gemm(xf, w1, hpost, M, 4 * Cn, Cn, Cn, Cn, 4 * Cn, _lib.EPI_GELU, b1.data_ptr()),
                             8.0 * M * Cn * Cn, 2.0 * M * Cn * 5),
+    "fc1 fwd (bias only)": (lambda: gemm(xf, w1, hpost, M, 4 * Cn, Cn, Cn, Cn, 4 * Cn, _lib.EPI_NONE, b1.data_ptr()),
+                            8.0 * M * Cn * Cn, 2.0 * M * Cn * 5),
+    "fc1 fwd (no epilogue math)": (lambda: gemm(xf, w1, hpost, M, 4 * Cn, Cn, Cn, Cn, 4 * Cn, _lib.EPI_NONE),
+                                   8.0 * M * Cn * Cn, 2.0 * M * Cn * 5),
     "fc2 fwd (layer scale + residual)": (lambda: gemm(hpost, w2, out, M, Cn, 4 * Cn, 4 * Cn, 4 * Cn, Cn, _lib.EPI_SCALE_RESIDUAL,
                                                       bias.data_ptr(), gam.data_ptr(), xf.data_ptr(), Cn), 8.0 * M * Cn * Cn, 2.0 * M * Cn * 6),
     "fc2 dgrad (x gelu')": (lambda: gemm(dxf, w2, hpost, M, 4 * Cn, Cn, Cn, 4 * Cn, 4 * Cn, _lib.EPI_MUL_GELU_GRAD, residual=hpre.data_ptr(),

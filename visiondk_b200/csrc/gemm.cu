@@ -122,17 +122,18 @@ __device__ __forceinline__ float2 unpack2(uint32_t u, int dtype) {
 }
 
 // Per-chunk epilogue arithmetic on this thread's 32 consecutive columns [col0, col0 + ncols) of row `row`.
-__device__ __forceinline__ void epi_math(const GemmParams& p, float (&v)[32], int row, int col0, int ncols, float ln_mean,
-                                         float ln_rstd, bool residual_from_smem = false) {
-  if (p.bias != nullptr) {
+// `bsm`: this tile's bias values for columns [col0, col0 + 32) in shared memory (zero beyond N): staged once per tile so
+// that the epilogue's critical path holds no global loads.
+__device__ __forceinline__ void add_bias32(float (&v)[32], const float* bsm) {
 #pragma unroll
-    for (int j = 0; j < 32; j += 4) {
-      if (j < ncols) {
-        const float4 b = __ldg(reinterpret_cast<const float4*>(p.bias + col0 + j));
-        v[j] += b.x; v[j + 1] += b.y; v[j + 2] += b.z; v[j + 3] += b.w;
-      }
-    }
+  for (int j = 0; j < 32; j += 4) {
+    const float4 b = *reinterpret_cast<const float4*>(bsm + j);
+    v[j] += b.x; v[j + 1] += b.y; v[j + 2] += b.z; v[j + 3] += b.w;
   }
+}
+__device__ __forceinline__ void epi_math(const GemmParams& p, float (&v)[32], int row, int col0, int ncols, float ln_mean,
+                                         float ln_rstd, const float* bsm, bool residual_from_smem = false) {
+  if (p.bias != nullptr) add_bias32(v, bsm);
   if (p.epilogue == VDK_EPI_GELU) {
 #pragma unroll
     for (int j = 0; j < 32; j += 2) gelu_pair(v[j], v[j + 1]);
@@ -216,6 +217,7 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
   uint64_t* tmem_empty = tmem_full + 2;
   uint64_t* res_bar = tmem_empty + 2;  // residual sub-tile landed in the staging buffer (one per epilogue half)
   uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(res_bar + 2);
+  float* bias_sm = reinterpret_cast<float*>(tmem_ptr + 4);  // [BN] bias of the tile being finished (16-byte aligned)
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -266,7 +268,7 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
         const int kb0 = split * kb_per_split;
         const int kb1 = min(kb0 + kb_per_split, num_kb_total);
         for (int kb = kb0; kb < kb1; ++kb) {
-          mbar_wait(&empty_bar[stage], phase ^ 1);
+          mbar_wait_relaxed(&empty_bar[stage], phase ^ 1);
           uint8_t* sa = smem + stage * kStageBytes;
           uint8_t* sb = sa + Cfg::kStageA;
           if (kPair) {
@@ -318,7 +320,7 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
       for (int tile = tile0; tile < num_tiles; tile += tile_step, ++it) {
         const int acc = it & 1;
         const uint32_t acc_phase = (it >> 1) & 1;
-        mbar_wait(&tmem_empty[acc], acc_phase ^ 1);
+        mbar_wait_relaxed(&tmem_empty[acc], acc_phase ^ 1);
         tc_fence_after();
         const uint32_t tmem_d = tmem_base + acc * BN;
         const int split = tile / (num_m * num_n);
@@ -386,7 +388,13 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
       const int m0 = (mn / num_n) * kTM + rank * kBM;
       const int n0 = (mn % num_n) * BN;
       const int row = m0 + lane_base + lane;
-      mbar_wait(&tmem_full[acc], acc_phase);
+      if (p.bias != nullptr) {  // while the accumulator is still being produced
+        const int te = static_cast<int>(threadIdx.x) - 64;
+        named_bar_sync(3, 256);  // the previous tile's bias has been consumed by both halves
+        if (te < BN) bias_sm[te] = (n0 + te < p.N) ? __ldg(p.bias + n0 + te) : 0.f;
+        named_bar_sync(3, 256);
+      }
+      mbar_wait_relaxed(&tmem_full[acc], acc_phase);
       tc_fence_after();
       const uint32_t tacc = tmem_base + (static_cast<uint32_t>(lane_base) << 16) + acc * BN;
       float ln_mean = 0.f, ln_rstd = 1.f;
@@ -468,17 +476,9 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
             const int col0 = colS + hh * 32;
             const int ncols = max(0, min(32, p.N - col0));
             if (p.aux_out) {  // GELU with a saved pre-activation: bias only here; the activation follows the aux store
-              if (ncols > 0 && p.bias != nullptr) {
-#pragma unroll
-                for (int j = 0; j < 32; j += 4) {
-                  if (j < ncols) {
-                    const float4 b = __ldg(reinterpret_cast<const float4*>(p.bias + col0 + j));
-                    v[j] += b.x; v[j + 1] += b.y; v[j + 2] += b.z; v[j + 3] += b.w;
-                  }
-                }
-              }
+              if (p.bias != nullptr) add_bias32(v, bias_sm + (col0 - n0));
             } else if (ncols > 0) {
-              epi_math(p, v, row, col0, ncols, ln_mean, ln_rstd, aux_in);
+              epi_math(p, v, row, col0, ncols, ln_mean, ln_rstd, bias_sm + (col0 - n0), aux_in);
             }
             if (aux_in) {
 #pragma unroll
@@ -577,17 +577,9 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
             const int col0 = colS + hh * 32;
             const int ncols = max(0, min(32, p.N - col0));
             if (p.aux_out) {  // GELU with a saved pre-activation: bias only here; the activation follows the aux store
-              if (ncols > 0 && p.bias != nullptr) {
-#pragma unroll
-                for (int j = 0; j < 32; j += 4) {
-                  if (j < ncols) {
-                    const float4 b = __ldg(reinterpret_cast<const float4*>(p.bias + col0 + j));
-                    v[j] += b.x; v[j + 1] += b.y; v[j + 2] += b.z; v[j + 3] += b.w;
-                  }
-                }
-              }
+              if (p.bias != nullptr) add_bias32(v, bias_sm + (col0 - n0));
             } else if (ncols > 0) {
-              epi_math(p, v, row, col0, ncols, ln_mean, ln_rstd, aux_in);
+              epi_math(p, v, row, col0, ncols, ln_mean, ln_rstd, bias_sm + (col0 - n0), aux_in);
             }
             if (aux_in) {
               if (hh == 0) {
@@ -685,7 +677,7 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
 #pragma unroll
             for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]);
             const int ncols = min(32, p.N - col0);  // multiple of 8 (N % 8 == 0 is required)
-            epi_math(p, v, row, col0, ncols, ln_mean, ln_rstd);
+            epi_math(p, v, row, col0, ncols, ln_mean, ln_rstd, bias_sm + (col0 - n0));
             if (p.out_dtype == VDK_DTYPE_FP32) {
               float* out = reinterpret_cast<float*>(p.D) + static_cast<size_t>(row) * p.ldd + col0;
 #pragma unroll
@@ -735,7 +727,7 @@ static int launch_gemm(const CUtensorMap& ma, const CUtensorMap& mb, const CUten
   using Cfg = GemmCfg<BN>;
   constexpr int kStageBytes = Cfg::kStageA + (kPair ? Cfg::kStageB / 2 : Cfg::kStageB);
   constexpr int kStages = kPair ? (kAux ? 5 : 6) : Cfg::kStages - (kAux ? 1 : 0);
-  constexpr int kSmem = kStages * kStageBytes + (kAux ? 4 : 2) * Cfg::kStoreStageBytes + (2 * kStages + 6) * 8 + 16 + 1024;
+  constexpr int kSmem = kStages * kStageBytes + (kAux ? 4 : 2) * Cfg::kStoreStageBytes + (2 * kStages + 6) * 8 + 16 + BN * 4 + 1024;
   static_assert(kSmem <= 227 * 1024, "GEMM shared memory budget");
   auto kern = gemm_tn_kernel<BN, kBf16, kAux, kPair>;
   static bool attr_set = false;  // per (BN, dtype, variant) instantiation
@@ -835,7 +827,9 @@ int gemm_run(const vdk_gemm_desc& g, cudaStream_t s) {
     const char* e = getenv("VDK_GEMM_PAIR");
     return e ? atoi(e) : 1;
   }();
-  const bool pair = wide && pair_mode != 0 && g.M > kBM;
+  // VDK_GEMM_PAIR: 0 never, 2 whenever possible, 1 (default) where it measured faster at ConvNeXt-B shapes: long K loops
+  // over many row blocks (+4..5 %); short-K GEMMs are paced by their epilogue and lose 2..5 % to the pair's barriers
+  const bool pair = wide && g.M > kBM && (pair_mode == 2 || (pair_mode == 1 && g.K >= 1024 && g.M >= 16384));
   rc = g.trans_b ? make_tma_2d_16bit(&mb, g.B, (uint64_t)g.K, (uint64_t)g.N, (uint64_t)g.ldb, kBK, 64)
                  : make_tma_2d_16bit(&mb, g.B, (uint64_t)g.N, (uint64_t)g.K, (uint64_t)g.ldb, pair ? BN / 2 : BN, kBK);
   if (rc != VDK_OK) return rc;

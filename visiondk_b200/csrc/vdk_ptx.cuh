@@ -79,6 +79,22 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
   }
 }
 
+// The same wait for threads that are expected to wait LONG (a producer out of free slots, an epilogue waiting for the
+// next accumulator): after a few polls the warp sleeps between polls, so that its spin loop stops competing for issue
+// slots with the warps that share its scheduler.
+__device__ __forceinline__ void mbar_wait_relaxed(uint64_t* bar, uint32_t parity) {
+  if (mbar_try_wait(bar, parity)) return;
+  const long long t0 = clock64();
+  int polls = 0;
+  while (!mbar_try_wait(bar, parity)) {
+    if (++polls > 4) __nanosleep(64);
+    if (clock64() - t0 > 4000000000LL) {
+      printf("vdk: mbarrier wait timed out (block %d, thread %d, parity %u)\n", (int)blockIdx.x, (int)threadIdx.x, parity);
+      __trap();
+    }
+  }
+}
+
 // ----------------------------------------------------------------------------------------------
 // TMA
 // ----------------------------------------------------------------------------------------------
