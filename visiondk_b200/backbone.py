@@ -276,8 +276,8 @@ class TimmWrapper(nn.Module):
         bn = self.output_layer[0]
         with torch.cuda.device(x.device):
             s = _lib.stream_ptr()
+            # fp32 masters -> kernel layouts (bf16 weights, [49][C] taps and their reversal, gamma-scaled fc2): batched per stage
             _lib.check(lib.vdk_convnext_pack(C.byref(params), C.byref(net), s), "vdk_convnext_pack")
-            _lib.check(lib.vdk_convnext_pack_flip(C.byref(net), s), "vdk_convnext_pack_flip")
             _lib.check(lib.vdk_convnext_train_forward(C.byref(net), C.byref(params), x.data_ptr(), B, float(bn.momentum),
                                                       out.data_ptr(), st["ws"].data_ptr(), st["ws"].numel(), s),
                        "vdk_convnext_train_forward")

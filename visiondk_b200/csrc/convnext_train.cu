@@ -97,8 +97,9 @@ static void make_layout(const vdk_convnext_net* net, int batch, TrainLayout* L) 
   L->dy = take(max_mc * 2);
   L->dconv = take(max_mc * 2);
   L->G = take(max_cc4 * 4);
-  L->sdo = take(4096 * 4);
-  L->dw49 = take(49 * 2048 * 4);
+  // per-block scratch (zeroed once per backward): column sums of dOut, tap gradients in [49][C] layout
+  L->sdo = take(static_cast<size_t>(L->n_blocks) * 2048 * 4);
+  L->dw49 = take(static_cast<size_t>(L->n_blocks) * 49 * 2048 * 4);
   L->gwc = take(max_cc4 * 4);
   L->gwneck = take(F * Kn * 4);
   L->dz = take(static_cast<size_t>(batch) * F * 4);
@@ -228,30 +229,117 @@ extern "C" size_t vdk_convnext_train_workspace_bytes(const vdk_convnext_net* net
   return L.total;
 }
 
+// ---- weight packing, batched: the blocks of a stage have identical shapes, so ONE launch per (stage, kind) walks a table
+// of per-block pointers passed by value (the per-tensor kernels were launch-bound: ~190 launches of 3-5 us per step) ----
+constexpr int kPackTab = 32;
+struct PackTab {
+  const float* src[kPackTab];
+  void* dst[kPackTab];
+  void* dst2[kPackTab];
+  const float* scale[kPackTab];
+};
+
+// dst[i] = bf16(src[i] * (scale ? scale[i / cols] : 1)) for tensor blockIdx.y;  dst2 (optional): the same without the scale
+__global__ void __launch_bounds__(256)
+pack_cast_kernel(PackTab t, int64_t n, int cols) {
+  const float* __restrict__ src = t.src[blockIdx.y];
+  __nv_bfloat16* __restrict__ dst = reinterpret_cast<__nv_bfloat16*>(t.dst[blockIdx.y]);
+  __nv_bfloat16* __restrict__ dst2 = reinterpret_cast<__nv_bfloat16*>(t.dst2[blockIdx.y]);
+  const float* __restrict__ sc = t.scale[blockIdx.y];
+  for (int64_t i = (static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x) * 4; i < n;
+       i += static_cast<int64_t>(gridDim.x) * blockDim.x * 4) {
+    const float4 v = __ldg(reinterpret_cast<const float4*>(src + i));  // n and cols are multiples of 4
+    if (dst2 != nullptr) {
+      __nv_bfloat162 lo = __floats2bfloat162_rn(v.x, v.y), hi = __floats2bfloat162_rn(v.z, v.w);
+      uint2 o;
+      o.x = *reinterpret_cast<uint32_t*>(&lo);
+      o.y = *reinterpret_cast<uint32_t*>(&hi);
+      *reinterpret_cast<uint2*>(dst2 + i) = o;
+    }
+    const float m = sc ? sc[i / cols] : 1.f;
+    __nv_bfloat162 lo = __floats2bfloat162_rn(v.x * m, v.y * m), hi = __floats2bfloat162_rn(v.z * m, v.w * m);
+    uint2 o;
+    o.x = *reinterpret_cast<uint32_t*>(&lo);
+    o.y = *reinterpret_cast<uint32_t*>(&hi);
+    *reinterpret_cast<uint2*>(dst + i) = o;
+  }
+}
+// conv_dw.weight [C][49] -> taps [49][C] (dst) and the reversed taps [48 - t][C] for the backward-data pass (dst2, optional)
+__global__ void __launch_bounds__(256)
+pack_taps_kernel(PackTab t, int C) {
+  const float* __restrict__ src = t.src[blockIdx.y];
+  float* __restrict__ dst = reinterpret_cast<float*>(t.dst[blockIdx.y]);
+  float* __restrict__ dst2 = reinterpret_cast<float*>(t.dst2[blockIdx.y]);
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;  // output index [tap][c]
+  if (i >= 49 * C) return;
+  const int tap = i / C, c = i - tap * C;
+  const float v = src[c * 49 + tap];
+  if (dst != nullptr) dst[i] = v;
+  if (dst2 != nullptr) dst2[(48 - tap) * C + c] = v;
+}
+
+// gradient of the taps back to timm's layout: dst[c][t] += src[t][c] for tensor blockIdx.y
+__global__ void __launch_bounds__(256)
+unpack_taps_grad_kernel(PackTab t, int C) {
+  const float* __restrict__ src = t.src[blockIdx.y];
+  float* __restrict__ dst = reinterpret_cast<float*>(t.dst[blockIdx.y]);
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;  // input index [tap][c]
+  if (i >= 49 * C) return;
+  const int tap = i / C, c = i - tap * C;
+  dst[c * 49 + tap] += src[i];
+}
+
+static int pack_impl(const vdk_convnext_tensors* p, const vdk_convnext_net* net, bool taps_and_weights, bool flip, cudaStream_t s) {
+  auto bf = [](const void* q) { return const_cast<void*>(q); };
+  int k0 = 0;
+  for (int st = 0; st < 4; ++st) {
+    const int C = net->dims[st], depth = net->depths[st];
+    for (int j0 = 0; j0 < depth; j0 += kPackTab) {
+      const int nb = std::min(kPackTab, depth - j0);
+      PackTab fc1{}, fc2{}, taps{};
+      bool any_flip = false;
+      for (int j = 0; j < nb; ++j) {
+        const vdk_convnext_block_tensors* b = &p->blocks[k0 + j0 + j];
+        const vdk_convnext_block* o = &net->blocks[k0 + j0 + j];
+        fc1.src[j] = b->fc1_w; fc1.dst[j] = bf(o->fc1_w);
+        // fc2: plain cast (dst2) + gamma[c] * W2[c,:] (dst) in one pass when the layer-scaled copy is wanted
+        fc2.src[j] = b->fc2_w;
+        if (o->fc2_wg) { fc2.dst[j] = bf(o->fc2_wg); fc2.dst2[j] = bf(o->fc2_w); fc2.scale[j] = b->gamma; }
+        else { fc2.dst[j] = bf(o->fc2_w); }
+        taps.src[j] = b->dw_w;
+        taps.dst[j] = taps_and_weights ? bf(o->dw_w) : nullptr;
+        taps.dst2[j] = (flip && o->dw_w_flip) ? bf(o->dw_w_flip) : nullptr;
+        any_flip = any_flip || taps.dst2[j] != nullptr;
+      }
+      const int64_t n = static_cast<int64_t>(4) * C * C;
+      const unsigned gx = static_cast<unsigned>(std::max<int64_t>(1, std::min<int64_t>((n / 4 + 255) / 256, 256)));
+      if (taps_and_weights) {
+        pack_cast_kernel<<<dim3(gx, nb), 256, 0, s>>>(fc1, n, 4 * C);  // no scale
+        pack_cast_kernel<<<dim3(gx, nb), 256, 0, s>>>(fc2, n, 4 * C);
+      }
+      if (taps_and_weights || any_flip) pack_taps_kernel<<<dim3((49 * C + 255) / 256, nb), 256, 0, s>>>(taps, C);
+    }
+    k0 += depth;
+  }
+  VDK_CUDA_OK(cudaGetLastError());
+  return VDK_OK;
+}
+
 extern "C" int vdk_convnext_pack(const vdk_convnext_tensors* p, vdk_convnext_net* net, void* stream) {
   VDK_REQUIRE(p && net, "vdk_convnext_pack: null argument");
   cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
   const int C0 = net->dims[0];
   auto bf = [](const void* q) { return reinterpret_cast<__nv_bfloat16*>(const_cast<void*>(q)); };
+  for (int st = 0; st < 4; ++st)
+    VDK_REQUIRE(net->dims[st] % 4 == 0, "vdk_convnext_pack: channel counts must be multiples of 4");
   RC(launch_cast_bf16(p->stem_w, static_cast<int64_t>(C0) * 48, bf(net->stem_w), s));
-  int k = 0;
-  for (int st = 0; st < 4; ++st) {
-    const int C = net->dims[st];
-    if (st > 0) {
-      const int Cin = net->dims[st - 1];
-      // Conv2d(Cin,C,2,2).weight [C][Cin][4] -> [C][4][Cin]
-      RC(launch_permute021(p->down[st].conv_w, C, Cin, 4, nullptr, bf(net->down[st].conv_w), nullptr, 0, s));
-    }
-    for (int j = 0; j < net->depths[st]; ++j, ++k) {
-      const vdk_convnext_block_tensors* b = &p->blocks[k];
-      vdk_convnext_block* o = &net->blocks[k];
-      // conv_dw.weight [C][49] -> taps [49][C] (fp32), and the reversed taps for the backward-data pass
-      RC(launch_permute021(b->dw_w, 1, C, 49, nullptr, nullptr, const_cast<float*>(o->dw_w), 0, s));
-      RC(launch_cast_bf16(b->fc1_w, static_cast<int64_t>(4) * C * C, bf(o->fc1_w), s));
-      RC(launch_cast_bf16(b->fc2_w, static_cast<int64_t>(4) * C * C, bf(o->fc2_w), s));
-      if (o->fc2_wg) RC(launch_permute021(b->fc2_w, C, 1, 4 * C, b->gamma, bf(o->fc2_wg), nullptr, 0, s));  // gamma[c] * W2[c,:]
-    }
+  for (int st = 1; st < 4; ++st) {
+    // Conv2d(Cin,C,2,2).weight [C][Cin][4] -> [C][4][Cin]
+    RC(launch_permute021(p->down[st].conv_w, net->dims[st], net->dims[st - 1], 4, nullptr, bf(net->down[st].conv_w), nullptr, 0, s));
   }
+  // per block: conv_dw.weight [C][49] -> taps [49][C] (fp32, + the reversed taps when the net carries them), fc1 / fc2
+  // casts, gamma[c] * W2[c,:]
+  RC(pack_impl(p, net, true, true, s));
   const int C3 = net->dims[3], hw = (net->image_size / 32) * (net->image_size / 32);
   // Linear weight [F][C3][hw] -> [F][hw][C3]
   RC(launch_permute021(p->lin_w, net->feat_dim, C3, hw, nullptr, bf(net->neck_w), nullptr, 0, s));
@@ -265,6 +353,8 @@ __global__ void flip_taps_kernel(const float* __restrict__ w49, int C, float* __
   out[(48 - t) * C + c] = w49[i];
 }
 
+// Reversed taps from the PACKED taps of `net` (kept for callers that pack by other means; vdk_convnext_pack already
+// writes them when the net carries dw_w_flip buffers).
 extern "C" int vdk_convnext_pack_flip(const vdk_convnext_net* net, void* stream) {
   VDK_REQUIRE(net, "vdk_convnext_pack_flip: null net");
   cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
@@ -363,6 +453,8 @@ extern "C" int vdk_convnext_train_backward(const vdk_convnext_net* net, const vd
   const Gemm G{s};
   const int F = net->feat_dim;
 
+  VDK_CUDA_OK(cudaMemsetAsync(F32(L.sdo), 0, static_cast<size_t>(L.n_blocks) * 2048 * 4, s));
+  VDK_CUDA_OK(cudaMemsetAsync(F32(L.dw49), 0, static_cast<size_t>(L.n_blocks) * 49 * 2048 * 4, s));
   // ---- neck ----
   const int H3 = L.st[3].H, W3 = L.st[3].W, C3 = L.st[3].C, M3 = static_cast<int>(L.st[3].M), Kn = H3 * W3 * C3;
   {
@@ -370,7 +462,6 @@ extern "C" int vdk_convnext_train_backward(const vdk_convnext_net* net, const vd
     col_sum_f32_small_kernel<<<(F + 255) / 256, 256, 0, s>>>(F32(L.dz), batch, F, g->lin_b);
     RC(launch_cast_bf16(F32(L.dz), static_cast<int64_t>(batch) * F, B16(L.dzb), s));
     // dW[F, (h,w,c)] = dZ^T . FN  (both stored with the batch index slow), then un-permute into timm's (c, h, w) order
-    VDK_CUDA_OK(cudaMemsetAsync(F32(L.gwneck), 0, static_cast<size_t>(F) * Kn * 4, s));
     RC(G.run(B16(L.dzb), B16(L.fn), F32(L.gwneck), F, Kn, batch, F, Kn, Kn, VDK_EPI_NONE, nullptr, nullptr, nullptr, 0,
              VDK_DTYPE_FP32, 1, 0, 1, 1));
     RC(launch_permute021(F32(L.gwneck), F, H3 * W3, C3, nullptr, nullptr, g->lin_w, 1, s));
@@ -391,10 +482,10 @@ extern "C" int vdk_convnext_train_backward(const vdk_convnext_net* net, const vd
       const vdk_convnext_block_tensors* pb = &p->blocks[k];
       const vdk_convnext_block_tensors* gb = &g->blocks[k];
       // fc2 + layer scale: G = dOut^T . h_post;  dW2 = diag(gamma) G;  dgamma, db2 from G, W2, colsum(dOut)
-      VDK_CUDA_OK(cudaMemsetAsync(F32(L.sdo), 0, static_cast<size_t>(C) * 4, s));
-      RC(launch_col_sum(B16(dx), M, C, C, F32(L.sdo), s));
+      float* sdo = F32(L.sdo) + static_cast<size_t>(k) * 2048;
+      RC(launch_col_sum(B16(dx), M, C, C, sdo, s));
       RC(G.wgrad(B16(dx), B16(L.hpost[k]), F32(L.G), C, 4 * C, M, C, 4 * C, F32(L.wslab), false));
-      RC(launch_layerscale_finalize(F32(L.G), pb->fc2_w, pb->fc2_b, pb->gamma, F32(L.sdo), C, 4 * C, gb->fc2_w, gb->gamma, gb->fc2_b, s));
+      RC(launch_layerscale_finalize(F32(L.G), pb->fc2_w, pb->fc2_b, pb->gamma, sdo, C, 4 * C, gb->fc2_w, gb->gamma, gb->fc2_b, s));
       // dH_pre = (dOut . diag(gamma) W2) * gelu'(h_pre)   -> overwrites the h_post buffer
       RC(G.run(B16(dx), b->fc2_wg, B16(L.hpost[k]), M, 4 * C, C, C, 4 * C, 4 * C, VDK_EPI_MUL_GELU_GRAD, nullptr, nullptr,
                B16(L.hpre[k]), 4 * C, VDK_DTYPE_BF16, 1, 0, 0, 1));
@@ -405,13 +496,23 @@ extern "C" int vdk_convnext_train_backward(const vdk_convnext_net* net, const vd
       // LayerNorm backward, depthwise weight gradient, depthwise data gradient (+ the residual branch)
       RC(launch_ln_bwd(B16(L.dy), B16(L.y[k]), F32(L.rstd[k]), batch, H, W, C, b->ln_w, b->ln_b, 1, B16(L.dconv), nullptr, gb->ln_w,
                        gb->ln_b, s));
-      VDK_CUDA_OK(cudaMemsetAsync(F32(L.dw49), 0, static_cast<size_t>(49) * C * 4, s));
-      RC(launch_dwconv7_wgrad(B16(L.xs[st][j]), B16(L.dconv), batch, H, W, C, F32(L.dw49), gb->dw_b, s));
-      RC(launch_permute021(F32(L.dw49), 1, 49, C, nullptr, nullptr, gb->dw_w, 1, s));  // [49][C] -> += [C][49]
+      // tap gradients stay in the kernel's [49][C] layout in this block's scratch; un-permuted per stage below
+      RC(launch_dwconv7_wgrad(B16(L.xs[st][j]), B16(L.dconv), batch, H, W, C, F32(L.dw49) + static_cast<size_t>(k) * 49 * 2048, gb->dw_b, s));
       RC(launch_dwconv7(1, B16(L.dconv), batch, H, W, C, b->dw_w_flip, nullptr, nullptr, nullptr, 0.f, B16(dx_other), nullptr,
                         B16(dx), s));
       std::swap(dx, dx_other);
     }
+    // tap gradients of this stage's blocks: [49][C] scratch -> += timm's [C][1][7][7], one launch per <= 32 blocks
+    for (int j0 = 0; j0 < L.depth[st]; j0 += kPackTab) {
+      const int nb = std::min(kPackTab, L.depth[st] - j0);
+      PackTab tab{};
+      for (int j = 0; j < nb; ++j) {
+        tab.src[j] = F32(L.dw49) + static_cast<size_t>(k + j0 + j) * 49 * 2048;
+        tab.dst[j] = g->blocks[k + j0 + j].dw_w;
+      }
+      unpack_taps_grad_kernel<<<dim3((49 * C + 255) / 256, nb), 256, 0, s>>>(tab, C);
+    }
+    VDK_CUDA_OK(cudaGetLastError());
     if (st > 0) {
       const vdk_convnext_down* d = &net->down[st];
       const vdk_convnext_down_tensors* gd = &g->down[st];
