@@ -461,13 +461,16 @@ def bench_train(ctx, args):
     host_x = [torch.randn(B, 3, IMG, IMG).pin_memory() for _ in range(2)]
     host_y = [torch.randint(0, 1000, (B,)).pin_memory() for _ in range(2)]
 
+    # end to end: every step's batch comes from pinned host memory (train.py:225) through the library's prefetcher (copy of
+    # batch i+1 on a side stream under step i) and every step's loss is read back (train.py:233: loss.item())
+    from visiondk_b200.train import DevicePrefetcher
+    n_e2e = max(3, args.warmup) + args.steps
+    feed = DevicePrefetcher(((host_x[j & 1], host_y[j & 1]) for j in range(n_e2e + 1)), ctx.dev)
+
     def step_e2e():
-        i = state["i"] & 1
-        state["i"] += 1
-        x = host_x[i].to(ctx.dev, non_blocking=True)  # train.py:225: images.to(device, non_blocking=True)
-        y = host_y[i].to(ctx.dev, non_blocking=True)
+        x, y = next(feed)
         loss = trainer.step(x, y)
-        return loss.item()  # train.py:233: loss.item() every step (device -> host read of the step's result)
+        return loss.item()
 
     e2e_ms = timed(ctx, step_e2e, args.steps, args.warmup)
     peak_s = 1422.7

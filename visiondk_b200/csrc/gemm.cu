@@ -465,14 +465,17 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
               }
             }
           }
+          // both 32-column halves of the sub-tile leave TMEM before the first is touched: one exposed TMEM latency per
+          // 64 columns, and two independent instruction streams for the scheduler
+          uint32_t rr[2][32];
+          tmem_ld_32x32b_x32(tacc + sc * 64, rr[0]);
+          tmem_ld_32x32b_x32(tacc + sc * 64 + 32, rr[1]);
+          tmem_ld_wait();
 #pragma unroll
           for (int hh = 0; hh < 2; ++hh) {
-            uint32_t r[32];
-            tmem_ld_32x32b_x32(tacc + sc * 64 + hh * 32, r);
-            tmem_ld_wait();
             float v[32];
 #pragma unroll
-            for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]);
+            for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(rr[hh][j]);
             const int col0 = colS + hh * 32;
             const int ncols = max(0, min(32, p.N - col0));
             if (p.aux_out) {  // GELU with a saved pre-activation: bias only here; the activation follows the aux store
@@ -566,14 +569,17 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
               tma_load_2d(stg, &map_r, &res_bar[half], colS, m0, kEvictFirst);
             }
           }
+          // both 32-column halves of the sub-tile leave TMEM before the first is touched: one exposed TMEM latency per
+          // 64 columns, and two independent instruction streams for the scheduler
+          uint32_t rr[2][32];
+          tmem_ld_32x32b_x32(tacc + sc * 64, rr[0]);
+          tmem_ld_32x32b_x32(tacc + sc * 64 + 32, rr[1]);
+          tmem_ld_wait();
 #pragma unroll
           for (int hh = 0; hh < 2; ++hh) {
-            uint32_t r[32];
-            tmem_ld_32x32b_x32(tacc + sc * 64 + hh * 32, r);
-            tmem_ld_wait();
             float v[32];
 #pragma unroll
-            for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]);
+            for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(rr[hh][j]);
             const int col0 = colS + hh * 32;
             const int ncols = max(0, min(32, p.N - col0));
             if (p.aux_out) {  // GELU with a saved pre-activation: bias only here; the activation follows the aux store

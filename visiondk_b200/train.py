@@ -105,3 +105,45 @@ class FaceTrainer:
         self.sched_step += 1  # scheduler.step() per batch (train.py:230)
         self._apply_lr()
         return loss.detach()
+
+
+class DevicePrefetcher:
+    """Host -> device staging for the loop `for images, labels in loader:` (engine/procedure/train.py:221-226, where the
+    reference calls `.to(device, non_blocking=True)` on the compute stream, i.e. the copy and the step serialise).
+    Batch i+1 is copied from pinned host memory on a side stream while batch i trains; the consumer stream waits on the
+    copy's event, and a batch's device buffers are only reused once the step that read them has been enqueued."""
+
+    def __init__(self, loader, device):
+        self.loader = iter(loader)
+        self.device = torch.device(device)
+        self.stream = torch.cuda.Stream(device=self.device)
+        self.next = None
+        self._preload()
+
+    def _preload(self):
+        try:
+            images, labels = next(self.loader)
+        except StopIteration:
+            self.next = None
+            return
+        with torch.cuda.stream(self.stream):
+            x = images.to(self.device, non_blocking=True)
+            y = labels.to(self.device, non_blocking=True)
+        ev = torch.cuda.Event()
+        ev.record(self.stream)
+        self.next = (x, y, ev)
+
+    def __iter__(self):
+        return self
+
+    def __next__(self):
+        if self.next is None:
+            raise StopIteration
+        x, y, ev = self.next
+        cur = torch.cuda.current_stream(self.device)
+        cur.wait_event(ev)
+        x.record_stream(cur)  # the caching allocator must not hand these buffers back to the copy stream early
+        y.record_stream(cur)
+        self._preload()
+        return x, y
+
