@@ -199,6 +199,14 @@ int vdk_convnext_train_forward(const vdk_convnext_net* net, const vdk_convnext_t
 int vdk_convnext_train_backward(const vdk_convnext_net* net, const vdk_convnext_tensors* params,
                                 const vdk_convnext_tensors* grads, const float* d_feats, int batch, void* workspace,
                                 size_t workspace_bytes, void* stream);
+/* The same backward in consecutive UNIT ranges (unit 0 = neck + head LayerNorm, then per stage 3..0 one unit per block,
+ * last block first, and one for the stage's downsample layer / the stem): lets the caller start the DDP all-reduce
+ * (engine/vision_engine.py:509-510 wraps the model in DistributedDataParallel, whose buckets overlap the backward) of the
+ * gradients a range completed while the next range computes.  Ranges must be issued in order and cover [0, units). */
+int vdk_convnext_train_backward_units(const vdk_convnext_net* net);
+int vdk_convnext_train_backward_range(const vdk_convnext_net* net, const vdk_convnext_tensors* params,
+                                      const vdk_convnext_tensors* grads, const float* d_feats, int batch, void* workspace,
+                                      size_t workspace_bytes, void* stream, int unit_begin, int unit_end);
 
 /* Building blocks of the backward, exported for unit parity tests (NHWC bf16 activations, fp32 parameter grads +=):
  *   vdk_dwconv7             mode 0: LayerNorm_C(dwconv7(x)+bias) (rstd_out optional); mode 1: dwconv7(x) with `w49` (+addend)

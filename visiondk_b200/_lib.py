@@ -70,6 +70,8 @@ SIGNATURES = {
     "vdk_convnext_train_workspace_bytes": (_sz, [_p, _i]),
     "vdk_convnext_train_forward": (_i, [_p, _p, _p, _i, C.c_float, _p, _p, _sz, _p]),
     "vdk_convnext_train_backward": (_i, [_p, _p, _p, _p, _i, _p, _sz, _p]),
+    "vdk_convnext_train_backward_units": (_i, [_p]),
+    "vdk_convnext_train_backward_range": (_i, [_p, _p, _p, _p, _i, _p, _sz, _p, _i, _i]),
     "vdk_convnext_workspace_bytes": (_sz, [_p, _i]),
     "vdk_convnext_forward": (_i, [_p, _p, _i, _i, _p, _p, _sz, _p]),
     "vdk_head_workspace_bytes": (_sz, [_p]),

@@ -311,13 +311,53 @@ class TimmWrapper(nn.Module):
             ptrs = {n: gflat.data_ptr() + 4 * offs[n] for n, _ in plist}
         grads = self._tensors_struct(lambda n: ptrs.get(n, 0))
         dout = dout.contiguous().float()
+        hook = getattr(self, "grad_section_hook", None)
         with torch.cuda.device(dout.device):
-            _lib.check(lib.vdk_convnext_train_backward(C.byref(net), C.byref(params), C.byref(grads), dout.data_ptr(), B,
-                                                       st["ws"].data_ptr(), st["ws"].numel(), _lib.stream_ptr()),
-                       "vdk_convnext_train_backward")
+            if hook is not None and direct:
+                # DDP overlap: the backward runs in a few unit ranges; after each one the parameters whose gradients are now
+                # final are handed to the hook (FaceTrainer starts their all-reduce while the next range computes)
+                for (u0, u1), names in self.backward_sections():
+                    _lib.check(lib.vdk_convnext_train_backward_range(C.byref(net), C.byref(params), C.byref(grads), dout.data_ptr(),
+                                                                     B, st["ws"].data_ptr(), st["ws"].numel(), _lib.stream_ptr(),
+                                                                     u0, u1), "vdk_convnext_train_backward_range")
+                    hook(names)
+            else:
+                _lib.check(lib.vdk_convnext_train_backward(C.byref(net), C.byref(params), C.byref(grads), dout.data_ptr(), B,
+                                                           st["ws"].data_ptr(), st["ws"].numel(), _lib.stream_ptr()),
+                           "vdk_convnext_train_backward")
         if direct:
             return [None] * len(plist)
         return [gflat[offs[n]:offs[n] + p.numel()].view_as(p) for n, p in plist]
+
+    def backward_sections(self):
+        """[((unit_begin, unit_end), [parameter names whose gradients are final after that range]), ...] in execution order
+        (units: include/vdk_b200.h, vdk_convnext_train_backward_range).  Four ranges: neck + head norm + stage 4; the second
+        half of stage 3's blocks; the rest of stage 3; stages 2, 1 and the stem — each a contiguous run of named_parameters()."""
+        d = self.model.depths
+        names = [n for n, _ in self.named_parameters()]
+
+        def pick(pred):
+            return [n for n in names if pred(n)]
+
+        def block_id(n, stage):
+            pre = f"model.stages.{stage}.blocks."
+            return int(n[len(pre):].split(".")[0]) if n.startswith(pre) else None
+
+        half = d[2] // 2
+        u_a = 1 + d[3] + 1                  # neck, stage-4 blocks, stage-4 downsample
+        u_b = u_a + (d[2] - half)           # blocks d[2]-1 .. half of stage 3
+        u_c = u_a + d[2] + 1                # remaining blocks + stage-3 downsample
+        u_end = 1 + sum(d) + 4
+        sec = [
+            ((0, u_a), pick(lambda n: n.startswith("output_layer.") or n.startswith("model.head.") or n.startswith("model.stages.3."))),
+            ((u_a, u_b), pick(lambda n: (block_id(n, 2) is not None and block_id(n, 2) >= half))),
+            ((u_b, u_c), pick(lambda n: n.startswith("model.stages.2.") and not (block_id(n, 2) is not None and block_id(n, 2) >= half))),
+            ((u_c, u_end), pick(lambda n: n.startswith("model.stem.") or n.startswith("model.stages.0.") or n.startswith("model.stages.1."))),
+        ]
+        covered = sum(len(ns) for _, ns in sec)
+        if covered != len(names):
+            raise RuntimeError(f"backward_sections: {len(names) - covered} parameters not assigned to a section")
+        return [x for x in sec if x[0][0] < x[0][1]]
 
     # ---- weight packing --------------------------------------------------------------------------
     def _version_key(self, device):

@@ -439,10 +439,25 @@ extern "C" int vdk_convnext_train_forward(const vdk_convnext_net* net, const vdk
   return VDK_OK;
 }
 
-extern "C" int vdk_convnext_train_backward(const vdk_convnext_net* net, const vdk_convnext_tensors* p,
-                                           const vdk_convnext_tensors* g, const float* d_feats, int batch, void* workspace,
-                                           size_t workspace_bytes, void* stream) {
+// The backward as a sequence of UNITS in execution order: unit 0 = neck + head LayerNorm; then per stage 3..0 one unit per
+// block (last block first) followed by one unit for the stage's downsample layer (the stem for stage 0).  A caller that
+// overlaps the gradient all-reduce with the backward runs [0, U) in a few consecutive ranges and reduces the gradients a
+// range completed while the next one computes.
+extern "C" int vdk_convnext_train_backward_units(const vdk_convnext_net* net) {
+  if (!net) return 0;
+  int n = 1 + 4;
+  for (int st = 0; st < 4; ++st) n += net->depths[st];
+  return n;
+}
+
+static int backward_range(const vdk_convnext_net* net, const vdk_convnext_tensors* p, const vdk_convnext_tensors* g,
+                          const float* d_feats, int batch, void* workspace, size_t workspace_bytes, void* stream, int u_begin,
+                          int u_end) {
   VDK_REQUIRE(net && p && g && d_feats && batch > 1, "vdk_convnext_train_backward: bad arguments");
+  VDK_REQUIRE(u_begin >= 0 && u_begin < u_end && u_end <= vdk_convnext_train_backward_units(net),
+              "vdk_convnext_train_backward: bad unit range [%d, %d)", u_begin, u_end);
+  int u = 0;  // running unit index
+  auto active = [&](int unit) { return unit >= u_begin && unit < u_end; };
   TrainLayout L;
   make_layout(net, batch, &L);
   VDK_REQUIRE(workspace && workspace_bytes >= L.total, "vdk_convnext_train_backward: workspace too small");
@@ -453,11 +468,11 @@ extern "C" int vdk_convnext_train_backward(const vdk_convnext_net* net, const vd
   const Gemm G{s};
   const int F = net->feat_dim;
 
-  VDK_CUDA_OK(cudaMemsetAsync(F32(L.sdo), 0, static_cast<size_t>(L.n_blocks) * 2048 * 4, s));
-  VDK_CUDA_OK(cudaMemsetAsync(F32(L.dw49), 0, static_cast<size_t>(L.n_blocks) * 49 * 2048 * 4, s));
   // ---- neck ----
   const int H3 = L.st[3].H, W3 = L.st[3].W, C3 = L.st[3].C, M3 = static_cast<int>(L.st[3].M), Kn = H3 * W3 * C3;
-  {
+  if (active(u++)) {
+    VDK_CUDA_OK(cudaMemsetAsync(F32(L.sdo), 0, static_cast<size_t>(L.n_blocks) * 2048 * 4, s));
+    VDK_CUDA_OK(cudaMemsetAsync(F32(L.dw49), 0, static_cast<size_t>(L.n_blocks) * 49 * 2048 * 4, s));
     RC(launch_bn_bwd_f32(d_feats, F32(L.z), batch, F, p->bn1_w, F32(L.bn1_mean), F32(L.bn1_rstd), F32(L.dz), g->bn1_w, g->bn1_b, s));
     col_sum_f32_small_kernel<<<(F + 255) / 256, 256, 0, s>>>(F32(L.dz), batch, F, g->lin_b);
     RC(launch_cast_bf16(F32(L.dz), static_cast<int64_t>(batch) * F, B16(L.dzb), s));
@@ -472,12 +487,20 @@ extern "C" int vdk_convnext_train_backward(const vdk_convnext_net* net, const vd
     RC(launch_ln_bwd(B16(L.dy), B16(L.f), F32(L.frstd), batch, H3, W3, C3, net->head_ln_w, net->head_ln_b, 1, B16(L.dxa), nullptr,
                      g->head_ln_w, g->head_ln_b, s));
   }
+  // the gradient wrt the residual stream ping-pongs between two buffers: every block / downsample unit swaps them once
   size_t dx = L.dxa, dx_other = L.dxb;
   int k = L.n_blocks;
   for (int st = 3; st >= 0; --st) {
     const int H = L.st[st].H, W = L.st[st].W, C = L.st[st].C, M = static_cast<int>(L.st[st].M);
+    int k_done_lo = -1, k_done_hi = -1;  // blocks of this stage executed by this call: [k_done_lo, k_done_hi]
     for (int j = L.depth[st] - 1; j >= 0; --j) {
       --k;
+      if (!active(u++)) {
+        std::swap(dx, dx_other);
+        continue;
+      }
+      if (k_done_hi < 0) k_done_hi = k;
+      k_done_lo = k;
       const vdk_convnext_block* b = &net->blocks[k];
       const vdk_convnext_block_tensors* pb = &p->blocks[k];
       const vdk_convnext_block_tensors* gb = &g->blocks[k];
@@ -502,18 +525,20 @@ extern "C" int vdk_convnext_train_backward(const vdk_convnext_net* net, const vd
                         B16(dx), s));
       std::swap(dx, dx_other);
     }
-    // tap gradients of this stage's blocks: [49][C] scratch -> += timm's [C][1][7][7], one launch per <= 32 blocks
-    for (int j0 = 0; j0 < L.depth[st]; j0 += kPackTab) {
-      const int nb = std::min(kPackTab, L.depth[st] - j0);
+    // tap gradients of the blocks this call executed: [49][C] scratch -> += timm's [C][1][7][7], one launch per <= 32 blocks
+    for (int k0 = k_done_lo; k_done_lo >= 0 && k0 <= k_done_hi; k0 += kPackTab) {
+      const int nb = std::min(kPackTab, k_done_hi - k0 + 1);
       PackTab tab{};
       for (int j = 0; j < nb; ++j) {
-        tab.src[j] = F32(L.dw49) + static_cast<size_t>(k + j0 + j) * 49 * 2048;
-        tab.dst[j] = g->blocks[k + j0 + j].dw_w;
+        tab.src[j] = F32(L.dw49) + static_cast<size_t>(k0 + j) * 49 * 2048;
+        tab.dst[j] = g->blocks[k0 + j].dw_w;
       }
       unpack_taps_grad_kernel<<<dim3((49 * C + 255) / 256, nb), 256, 0, s>>>(tab, C);
     }
     VDK_CUDA_OK(cudaGetLastError());
-    if (st > 0) {
+    if (st > 0 && !active(u++)) {
+      std::swap(dx, dx_other);
+    } else if (st > 0) {
       const vdk_convnext_down* d = &net->down[st];
       const vdk_convnext_down_tensors* gd = &g->down[st];
       const int Cin = L.st[st - 1].C;
@@ -528,7 +553,7 @@ extern "C" int vdk_convnext_train_backward(const vdk_convnext_net* net, const vd
     }
   }
   // ---- stem ----
-  {
+  if (active(u++)) {
     const int M0 = static_cast<int>(L.st[0].M), C0 = L.st[0].C;
     RC(launch_ln_bwd(B16(dx), B16(L.xs[0][0]), F32(L.rstd0), batch, L.st[0].H, L.st[0].W, C0, net->stem_ln_w, net->stem_ln_b, 1,
                      B16(L.dy), nullptr, g->stem_ln_w, g->stem_ln_b, s));
@@ -536,4 +561,18 @@ extern "C" int vdk_convnext_train_backward(const vdk_convnext_net* net, const vd
     RC(G.wgrad(B16(L.dy), B16(L.p0), g->stem_w, C0, 48, M0, C0, 48, F32(L.wslab), true));
   }
   return VDK_OK;
+}
+
+extern "C" int vdk_convnext_train_backward(const vdk_convnext_net* net, const vdk_convnext_tensors* p,
+                                           const vdk_convnext_tensors* g, const float* d_feats, int batch, void* workspace,
+                                           size_t workspace_bytes, void* stream) {
+  VDK_REQUIRE(net, "vdk_convnext_train_backward: null net");
+  return backward_range(net, p, g, d_feats, batch, workspace, workspace_bytes, stream, 0, vdk_convnext_train_backward_units(net));
+}
+
+extern "C" int vdk_convnext_train_backward_range(const vdk_convnext_net* net, const vdk_convnext_tensors* p,
+                                                 const vdk_convnext_tensors* g, const float* d_feats, int batch, void* workspace,
+                                                 size_t workspace_bytes, void* stream, int unit_begin, int unit_end) {
+  VDK_REQUIRE(net, "vdk_convnext_train_backward_range: null net");
+  return backward_range(net, p, g, d_feats, batch, workspace, workspace_bytes, stream, unit_begin, unit_end);
 }

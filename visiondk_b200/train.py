@@ -92,15 +92,58 @@ class FaceTrainer:
         for pg in self.opt.param_groups:
             pg["momentum"] = momentum
 
+    # ---- DDP: gradient mean on the flat buffers, overlapped with the backward (what DistributedDataParallel's buckets do
+    # in the reference, engine/vision_engine.py:509-510) ----
+    def _flat_slice(self, names):
+        """The slice of a flat gradient buffer that holds exactly the gradients of `names` (None if they do not form one
+        contiguous run inside a single group: the caller then reduces whole buffers after the backward)."""
+        params = dict(self.model.trainingwrapper["backbone"].named_parameters())
+        ps = [params[n] for n in names if n in params]
+        if not ps or any(p.grad is None for p in ps):
+            return None
+        for g in self.opt.groups:
+            base, n_el = g.g.data_ptr(), g.g.numel()
+            offs = [(p.grad.data_ptr() - base) // 4 for p in ps]
+            if all(0 <= o < n_el for o in offs):
+                lo = min(offs)
+                hi = max(o + p.numel() for o, p in zip(offs, ps))
+                if hi - lo <= sum(p.numel() for p in ps) + 64 * len(ps):  # contiguous up to alignment padding
+                    return g, lo, hi
+        return None
+
+    def _on_section(self, names):
+        sl = self._flat_slice(names)
+        if sl is None:
+            self._overlap_failed = True
+            return
+        g, lo, hi = sl
+        self._pending.append(dist.all_reduce(g.g[lo:hi], op=dist.ReduceOp.AVG, async_op=True))
+        self._reduced.append((id(g), lo, hi))
+
     def step(self, images: torch.Tensor, labels: torch.Tensor) -> torch.Tensor:
         """One batch: returns the (device) loss; does not synchronise (the reference's loss.item() every step,
         train.py:233, is a forced sync the hot path does not need)."""
         self.model.train()
+        ddp = dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1
+        backbone = self.model.trainingwrapper["backbone"]
+        self._pending, self._reduced, self._overlap_failed = [], [], False
+        if ddp and hasattr(backbone, "backward_sections"):
+            backbone.grad_section_hook = self._on_section
         loss = self.model.loss(images, labels, self.label_smooth)
         loss.backward()
-        if dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1:
-            for g in self.opt.groups:  # DDP's gradient mean, on the flat buffers (one collective per param group)
-                dist.all_reduce(g.g, op=dist.ReduceOp.AVG)
+        if ddp:
+            backbone.grad_section_hook = None
+            for w in self._pending:
+                w.wait()  # the compute stream waits for the collectives (no host block)
+            for g in self.opt.groups:  # whatever the sections did not cover (the head group; gaps; a failed overlap)
+                done = sorted((lo, hi) for gid, lo, hi in self._reduced if gid == id(g)) if not self._overlap_failed else []
+                if self._overlap_failed and self._reduced:
+                    raise RuntimeError("DDP overlap: gradient sections were not contiguous after some were already reduced")
+                pos = 0
+                for lo, hi in done + [(g.g.numel(), g.g.numel())]:
+                    if lo > pos:
+                        dist.all_reduce(g.g[pos:lo], op=dist.ReduceOp.AVG)
+                    pos = max(pos, hi)
         self.opt.step()
         self.sched_step += 1  # scheduler.step() per batch (train.py:230)
         self._apply_lr()
