@@ -225,6 +225,29 @@ def test_convnext_base_224_training_gradients_match_oracle(lib):
     assert not bad, "\n".join(bad[:20])
 
 
+def test_backward_in_unit_ranges_equals_single_call(lib):
+    """vdk_convnext_train_backward_range over the sections the DDP overlap uses == the one-call backward (same kernels in the
+    same order; only atomics' summation order may differ), and the sections hand over every parameter exactly once."""
+    _, ours = build_pair(seed=11)
+    torch.manual_seed(3)
+    x = torch.randn(6, 3, 64, 64, device="cuda")
+    wout = torch.randn(6, 64, device="cuda")
+    for p in ours.parameters():
+        p.grad = torch.zeros_like(p)  # pre-allocated fp32 buffers: the kernels accumulate straight into them
+    (ours(x) * wout).sum().backward()
+    one_call = {n: p.grad.clone() for n, p in ours.named_parameters()}
+    for p in ours.parameters():
+        p.grad.zero_()
+    seen = []
+    ours.grad_section_hook = lambda names: seen.extend(names)
+    (ours(x) * wout).sum().backward()
+    ours.grad_section_hook = None
+    assert sorted(seen) == sorted(n for n, _ in ours.named_parameters())
+    for n, p in ours.named_parameters():
+        a, b = p.grad, one_call[n]
+        assert (a - b).abs().max().item() <= 1e-4 * (b.abs().max().item() + 1e-6) + 1e-6, n
+
+
 def test_train_step_with_head_and_fused_optimizer(lib):
     """One full faceX train step on the B200 kernels: backbone fwd -> ArcFace+CE -> backward -> clip+SGD+EMA."""
     import copy
