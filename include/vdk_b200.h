@@ -233,6 +233,41 @@ size_t vdk_convnext_workspace_bytes(const vdk_convnext_net* net, int batch);
 int vdk_convnext_forward(const vdk_convnext_net* net, const float* images, int batch, int l2_normalize,
                          float* embeddings, void* workspace, size_t workspace_bytes, void* stream);
 
+/* ---- ViT inference forward (Transformer backbones of the CBIR extract path) ------------------- */
+/* Replaces the eval forward of TimmWrapper for `timm-vit_*` backbones (models/faceX/backbone/timm_wrapper.py:16-21,
+ * 39-47, 51-54: timm VisionTransformer with num_classes=0, global_pool='' -> every token after the final LayerNorm,
+ * then LayerNorm -> Flatten -> Linear -> BatchNorm1d) as run by FeatureExtractor.extract_cbir (face_model.py:120-144).
+ * All 16-bit weights are bf16 in nn.Linear layout [out, in]; vectors fp32; everything device memory. */
+#define VDK_VIT_MAX_BLOCKS 48
+typedef struct vdk_vit_block {
+  const float* ln1_w; const float* ln1_b;
+  const void* qkv_w;  const float* qkv_b;   /* [3*dim, dim], [3*dim]: rows ordered (q | k | v) x head x 64 as in timm */
+  const void* proj_w; const float* proj_b;  /* [dim, dim] */
+  const float* ln2_w; const float* ln2_b;
+  const void* fc1_w;  const float* fc1_b;   /* [4*dim, dim] */
+  const void* fc2_w;  const float* fc2_b;   /* [dim, 4*dim] */
+} vdk_vit_block;
+typedef struct vdk_vit_net {
+  int image_size, patch, dim, depth, heads, feat_dim;
+  const void* patch_w;      /* [dim, Kp] bf16, Kp = 3*patch*patch rounded up to 8, (c, kh, kw) order, zero padded */
+  const float* patch_b;     /* [dim] */
+  const float* cls_token;   /* [dim] */
+  const float* pos_embed;   /* [1 + (image_size/patch)^2, dim] */
+  const float* ones;        /* [dim] of 1.0f (layer-scale slot of the residual epilogue: timm's default ViT has none) */
+  vdk_vit_block blocks[VDK_VIT_MAX_BLOCKS];
+  const float* norm_w; const float* norm_b;        /* model.norm, eps 1e-6 */
+  const float* neck_ln_w; const float* neck_ln_b;  /* output_layer.0, eps 1e-5 */
+  const void* neck_w;       /* [feat_dim, tokens*dim] bf16 with BatchNorm1d (eval) folded in */
+  const float* neck_b;      /* [feat_dim] folded */
+} vdk_vit_net;
+size_t vdk_vit_workspace_bytes(const vdk_vit_net* net, int batch);
+/* images: fp32 NCHW [batch,3,S,S]; embeddings: fp32 [batch, feat_dim], L2-normalised when l2_normalize != 0. */
+int vdk_vit_forward(const vdk_vit_net* net, const float* images, int batch, int l2_normalize, float* embeddings,
+                    void* workspace, size_t workspace_bytes, void* stream);
+/* softmax(Q K^T / sqrt(d)) V on the qkv Linear's output as stored: qkv bf16 [batch, tokens, 3, heads, 64] ->
+ * out bf16 [batch, tokens, heads*64]  (timm Attention.forward, scores never written to memory). */
+int vdk_attention_fwd(const void* qkv, int batch, int tokens, int heads, int head_dim, void* out, void* stream);
+
 /* ---- margin-softmax heads + cross-entropy --------------------------------------------------- */
 /* Replaces ArcFace.forward (models/faceX/head/arcface.py:20-36), CircleLoss.forward (models/faceX/head/
  * circleloss.py:21-43), nn.CrossEntropyLoss(label_smoothing) (models/losses/loss.py:71-73) and their autograd
@@ -344,6 +379,10 @@ int vdk_topk_merge(const float* scores, const int64_t* ids, int n_lists, int64_t
 /* Brute-force canonical scores for verification at full size: out[i] = canonical_score(q[qi[i]], g[gi[i]]). */
 int vdk_ip_exact_pairs(const float* q32, const float* g32, int dim, const int64_t* qi, const int64_t* gi, int64_t n,
                        float* out, void* stream);
+
+/* sizeof() of the by-pointer structs, in this order: vdk_gemm_desc, vdk_topk_plan, vdk_head_desc, vdk_convnext_net,
+ * vdk_convnext_tensors, vdk_vit_net.  Writes min(n, count) entries, returns the count: a binding checks its mirrors. */
+int vdk_struct_sizes(size_t* out, int n);
 
 #ifdef __cplusplus
 }

@@ -69,3 +69,18 @@ def test_argument_validation_needs_no_gpu(lib):
     assert lib.vdk_gemm_tn(0, 0, 0, 8, 8, 8, 8, 8, 8, 0, 0, 0, 0, 0, 0, 0, 0) == _lib.VDK_ERR_INVALID
     assert lib.vdk_rows_prepare(0, 4, 64, 1, 0, 0, 0, 0, 0) == _lib.VDK_ERR_INVALID
     assert lib.vdk_topk_merge(0, 0, 2, 4, 4, 0, 0, 0) == _lib.VDK_ERR_INVALID
+
+
+def test_ctypes_mirrors_have_the_c_struct_sizes():
+    """The Python side mirrors the ABI structs by hand (ctypes.Structure): their sizes must equal the compiler's sizeof."""
+    import ctypes as C
+    from visiondk_b200 import _lib
+    from visiondk_b200.backbone import ConvNeXtNetC, ConvNeXtTensorsC
+    from visiondk_b200.vit import VitNetC
+    lib = _lib.load()
+    out = (C.c_size_t * 8)()
+    n = lib.vdk_struct_sizes(out, 8)
+    mirrors = [_lib.GemmDesc, _lib.TopkPlan, _lib.HeadDesc, ConvNeXtNetC, ConvNeXtTensorsC, VitNetC]
+    assert n == len(mirrors)
+    for i, m in enumerate(mirrors):
+        assert C.sizeof(m) == out[i], (m.__name__, C.sizeof(m), out[i])

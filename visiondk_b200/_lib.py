@@ -54,6 +54,7 @@ class GemmDesc(C.Structure):
 # name -> (restype, argtypes); must list every symbol include/vdk_b200.h declares (tests check this).
 SIGNATURES = {
     "vdk_version": (_i, []),
+    "vdk_struct_sizes": (_i, [_p, _i]),
     "vdk_last_error_string": (C.c_char_p, []),
     "vdk_device_check": (_i, []),
     "vdk_gemm": (_i, [_p, _p]),
@@ -72,6 +73,9 @@ SIGNATURES = {
     "vdk_convnext_train_backward": (_i, [_p, _p, _p, _p, _i, _p, _sz, _p]),
     "vdk_convnext_train_backward_units": (_i, [_p]),
     "vdk_convnext_train_backward_range": (_i, [_p, _p, _p, _p, _i, _p, _sz, _p, _i, _i]),
+    "vdk_vit_workspace_bytes": (_sz, [_p, _i]),
+    "vdk_vit_forward": (_i, [_p, _p, _i, _i, _p, _p, _sz, _p]),
+    "vdk_attention_fwd": (_i, [_p, _i, _i, _i, _i, _p, _p]),
     "vdk_convnext_workspace_bytes": (_sz, [_p, _i]),
     "vdk_convnext_forward": (_i, [_p, _p, _i, _i, _p, _p, _sz, _p]),
     "vdk_head_workspace_bytes": (_sz, [_p]),

@@ -457,4 +457,7 @@ class BackboneFactory:
         if not self.backbone_type.startswith("timm-"):
             raise ValueError(f"Unsupported backbone type: {self.backbone_type}. Only timm models are supported.")
         model_name = self.backbone_type[5:]
+        if model_name.startswith("vit_"):  # Transformer backbones: eval / extract path (visiondk_b200/vit.py)
+            from .vit import ViTWrapper
+            return ViTWrapper(model_name=model_name, **self.backbone_param)
         return TimmWrapper(model_name=model_name, **self.backbone_param)

@@ -556,6 +556,13 @@ neck_finalize_kernel(const float* __restrict__ acc, int n_slabs, size_t slab_str
     for (int i = lane; i < F; i += 32) out[static_cast<size_t>(row) * F + i] = __fdiv_rn(out[static_cast<size_t>(row) * F + i], denom);
 }
 
+int launch_neck_finalize(const float* slabs, int n_slabs, size_t slab_stride, int B, int F, const float* bias, int l2norm,
+                         float* out, cudaStream_t s) {
+  neck_finalize_kernel<<<(B * 32 + 255) / 256, 256, 0, s>>>(slabs, n_slabs, slab_stride, B, F, bias, l2norm, out);
+  VDK_CUDA_OK(cudaGetLastError());
+  return VDK_OK;
+}
+
 static size_t up256(size_t v) { return (v + 255) & ~static_cast<size_t>(255); }
 
 static int check_net(const vdk_convnext_net* n) {

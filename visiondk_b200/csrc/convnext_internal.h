@@ -16,6 +16,10 @@ int launch_dwconv7(int mode, const __nv_bfloat16* x, int batch, int H, int W, in
 int launch_ln_patchify(const __nv_bfloat16* x, int B, int H, int W, int C, const float* ln_w, const float* ln_b, float eps,
                        int patch, __nv_bfloat16* out, float* rstd_out, cudaStream_t s);
 
+// embeddings[row] = bias + sum of split-K slabs (fixed order) [, canonically L2-normalised]
+int launch_neck_finalize(const float* slabs, int n_slabs, size_t slab_stride, int B, int F, const float* bias, int l2norm,
+                         float* out, cudaStream_t s);
+
 }  // namespace vdk
 
 namespace vdk {

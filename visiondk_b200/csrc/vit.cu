@@ -1,0 +1,394 @@
+// vit.cu — ViT inference forward (CBIR extract path with a Transformer backbone) on the same tcgen05 GEMM, plus the one
+// kernel the ConvNeXt path does not have: softmax(Q K^T / sqrt(d)) V.
+//
+// Replaces, for `timm-vit_*` backbones, the eval forward of TimmWrapper (models/faceX/backbone/timm_wrapper.py:51-54: timm's
+// VisionTransformer.forward_features + the Transformer neck LayerNorm -> Flatten -> Linear -> BatchNorm1d of :39-47) that
+// FeatureExtractor.extract_cbir (models/faceX/face_model.py:120-144) runs per batch.
+//
+//   patchify (NCHW fp32 -> [B*N, 3*P*P] bf16)  -> GEMM(+bias)          patch embedding (Conv2d(3,C,P,P) as a GEMM)
+//   assemble: x[b,0] = cls + pos[0]; x[b,1+i] = tok[b,i] + pos[1+i]
+//   per block:  y = LN1(x); qkv = GEMM(y)+b; a = attention(qkv); x = x + GEMM(a)+b        (residual in the GEMM epilogue)
+//               y = LN2(x); h = GELU(GEMM(y)+b); x = x + GEMM(h)+b
+//   y = LN_neck(LN_final(x)); embeddings = split-K GEMM over (token, channel) with BatchNorm1d folded [+ L2 normalise]
+//
+// Attention: one CTA = 64 query rows of one (image, head), 4 warps x 16 rows, K/V streamed in 64-row tiles through
+// swizzled shared memory, mma.sync m16n8k16 (bf16 in, fp32 accumulate) with the online-softmax recurrence in registers
+// (scores never leave the SM).  Attention is 4 % of a ViT-B's FLOPs; the tcgen05 version is the next step for it.
+#include "vdk_host.h"
+#include "vdk_ptx.cuh"
+#include "convnext_internal.h"
+
+#include <algorithm>
+
+namespace vdk {
+
+// ------------------------------------------------------------------------------------------------
+// patchify: NCHW fp32 image -> rows of Kp >= 3*P*P bf16 in (c, kh, kw) order (Conv2d weight order), zero padded to Kp
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+vit_patchify_kernel(const float* __restrict__ x, int B, int S, int P, int Kp, __nv_bfloat16* __restrict__ out) {
+  const int G = S / P;  // patches per side
+  const int64_t total = static_cast<int64_t>(B) * G * G * Kp;
+  for (int64_t t = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x; t < total;
+       t += static_cast<int64_t>(gridDim.x) * blockDim.x) {
+    const int kidx = static_cast<int>(t % Kp);
+    const int64_t patch = t / Kp;
+    float v = 0.f;
+    if (kidx < 3 * P * P) {
+      const int c = kidx / (P * P), r = kidx - c * P * P, kh = r / P, kw = r - kh * P;
+      const int pw = static_cast<int>(patch % G), ph = static_cast<int>((patch / G) % G);
+      const int b = static_cast<int>(patch / (static_cast<int64_t>(G) * G));
+      v = x[((static_cast<int64_t>(b) * 3 + c) * S + (ph * P + kh)) * S + pw * P + kw];
+    }
+    out[t] = __float2bfloat16_rn(v);
+  }
+}
+
+// x[b, 0, :] = cls + pos[0];  x[b, 1 + i, :] = tok[b, i, :] + pos[1 + i]
+__global__ void __launch_bounds__(256)
+vit_assemble_kernel(const __nv_bfloat16* __restrict__ tok, const float* __restrict__ cls, const float* __restrict__ pos, int B,
+                    int N, int C, __nv_bfloat16* __restrict__ x) {
+  const int64_t total = static_cast<int64_t>(B) * (N + 1) * (C / 2);
+  for (int64_t t = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x; t < total;
+       t += static_cast<int64_t>(gridDim.x) * blockDim.x) {
+    const int c2 = static_cast<int>(t % (C / 2));
+    const int64_t row = t / (C / 2);
+    const int tk = static_cast<int>(row % (N + 1));
+    const int b = static_cast<int>(row / (N + 1));
+    float2 v;
+    if (tk == 0) {
+      v = make_float2(cls[2 * c2], cls[2 * c2 + 1]);
+    } else {
+      v = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(tok + (static_cast<int64_t>(b) * N + tk - 1) * C + 2 * c2));
+    }
+    const float2 p = *reinterpret_cast<const float2*>(pos + static_cast<int64_t>(tk) * C + 2 * c2);
+    *reinterpret_cast<__nv_bfloat162*>(x + row * C + 2 * c2) = __floats2bfloat162_rn(v.x + p.x, v.y + p.y);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// attention forward, head_dim 64
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ void ldmatrix_x4(uint32_t (&r)[4], uint32_t addr) {
+  asm volatile("ldmatrix.sync.aligned.m8n8.x4.shared.b16 {%0, %1, %2, %3}, [%4];"
+               : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]) : "r"(addr));
+}
+__device__ __forceinline__ void ldmatrix_x4_trans(uint32_t (&r)[4], uint32_t addr) {
+  asm volatile("ldmatrix.sync.aligned.m8n8.x4.trans.shared.b16 {%0, %1, %2, %3}, [%4];"
+               : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]) : "r"(addr));
+}
+__device__ __forceinline__ void mma_bf16_16816(float (&c)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
+  asm volatile("mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0, %1, %2, %3}, {%4, %5, %6, %7}, {%8, %9}, {%0, %1, %2, %3};"
+               : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
+               : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
+}
+__device__ __forceinline__ float fast_exp2(float x) {
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+
+constexpr int kAttD = 64;   // head dim
+constexpr int kAttBM = 64;  // query rows per CTA
+constexpr int kAttBN = 64;  // key/value rows per tile
+
+// 64 x 64 bf16 tile in shared memory: 128-byte rows, 16-byte chunk index XOR (row & 7) (conflict-free ldmatrix)
+__device__ __forceinline__ uint32_t att_tile_addr(uint32_t base, int row, int col /*multiple of 8*/) {
+  return base + row * 128 + (((col >> 3) ^ (row & 7)) << 4);
+}
+
+// rows [row0, row0 + 64) of a [*, ld] bf16 matrix (rows >= n_rows are zero) -> swizzled tile
+__device__ __forceinline__ void att_load_tile(uint8_t* tile, const __nv_bfloat16* __restrict__ src, int64_t ld, int row0, int n_rows) {
+#pragma unroll
+  for (int c = 0; c < 4; ++c) {
+    const int idx = threadIdx.x + c * 128;
+    const int r = idx >> 3, ch = idx & 7;
+    uint4 v = make_uint4(0u, 0u, 0u, 0u);
+    if (row0 + r < n_rows) v = __ldg(reinterpret_cast<const uint4*>(src + static_cast<int64_t>(row0 + r) * ld + ch * 8));
+    *reinterpret_cast<uint4*>(tile + r * 128 + ((ch ^ (r & 7)) << 4)) = v;
+  }
+}
+
+// qkv: [B, N, 3, H, 64] bf16 (the qkv Linear's output as stored);  out: [B, N, H*64] bf16
+__global__ void __launch_bounds__(128)
+attention_fwd_kernel(const __nv_bfloat16* __restrict__ qkv, int B, int N, int H, float scale_log2e, __nv_bfloat16* __restrict__ out) {
+  __shared__ __align__(128) uint8_t sq[kAttBM * 128];
+  __shared__ __align__(128) uint8_t sk[kAttBN * 128];
+  __shared__ __align__(128) uint8_t sv[kAttBN * 128];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int g = lane >> 2, t = lane & 3;
+  const int q0 = blockIdx.x * kAttBM, h = blockIdx.y, b = blockIdx.z;
+  const int64_t ld = static_cast<int64_t>(3) * H * kAttD;
+  const __nv_bfloat16* base = qkv + static_cast<int64_t>(b) * N * ld + h * kAttD;
+  const __nv_bfloat16* qp = base;
+  const __nv_bfloat16* kp = base + static_cast<int64_t>(H) * kAttD;
+  const __nv_bfloat16* vp = base + static_cast<int64_t>(2) * H * kAttD;
+
+  att_load_tile(sq, qp, ld, q0, N);
+  __syncthreads();
+  // this warp's 16 query rows as A fragments for the 4 k-steps over d
+  uint32_t qa[4][4];
+  {
+    const uint32_t sqb = smem_u32(sq);
+    const int i = lane >> 3, r = lane & 7;
+#pragma unroll
+    for (int kk = 0; kk < 4; ++kk)
+      ldmatrix_x4(qa[kk], att_tile_addr(sqb, warp * 16 + (i & 1) * 8 + r, kk * 16 + (i >> 1) * 8));
+  }
+  float o[8][4];
+#pragma unroll
+  for (int j = 0; j < 8; ++j)
+#pragma unroll
+    for (int c = 0; c < 4; ++c) o[j][c] = 0.f;
+  float m_run[2] = {-INFINITY, -INFINITY}, l_run[2] = {0.f, 0.f};  // rows g and g + 8
+
+  const uint32_t skb = smem_u32(sk), svb = smem_u32(sv);
+  for (int kv0 = 0; kv0 < N; kv0 += kAttBN) {
+    __syncthreads();  // the previous tile has been consumed by every warp
+    att_load_tile(sk, kp, ld, kv0, N);
+    att_load_tile(sv, vp, ld, kv0, N);
+    __syncthreads();
+    // S = Q K^T for 16 rows x 64 key columns
+    float sacc[8][4];
+#pragma unroll
+    for (int j = 0; j < 8; ++j)
+#pragma unroll
+      for (int c = 0; c < 4; ++c) sacc[j][c] = 0.f;
+    {
+      const int i = lane >> 3, r = lane & 7;
+#pragma unroll
+      for (int kk = 0; kk < 4; ++kk) {
+#pragma unroll
+        for (int jp = 0; jp < 4; ++jp) {  // pairs of 8-column tiles
+          uint32_t kb[4];
+          ldmatrix_x4(kb, att_tile_addr(skb, jp * 16 + (i >> 1) * 8 + r, kk * 16 + (i & 1) * 8));
+          mma_bf16_16816(sacc[2 * jp], qa[kk], kb[0], kb[1]);
+          mma_bf16_16816(sacc[2 * jp + 1], qa[kk], kb[2], kb[3]);
+        }
+      }
+    }
+    // scale, mask the columns beyond N, online softmax
+    float mx[2] = {-INFINITY, -INFINITY};
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+#pragma unroll
+      for (int c = 0; c < 4; ++c) {
+        const int col = kv0 + j * 8 + 2 * t + (c & 1);
+        const float v = col < N ? sacc[j][c] * scale_log2e : -INFINITY;
+        sacc[j][c] = v;
+        mx[c >> 1] = fmaxf(mx[c >> 1], v);
+      }
+    }
+#pragma unroll
+    for (int rr = 0; rr < 2; ++rr) {
+      mx[rr] = fmaxf(mx[rr], __shfl_xor_sync(0xffffffffu, mx[rr], 1));
+      mx[rr] = fmaxf(mx[rr], __shfl_xor_sync(0xffffffffu, mx[rr], 2));
+    }
+    float corr[2], m_new[2];
+#pragma unroll
+    for (int rr = 0; rr < 2; ++rr) {
+      m_new[rr] = fmaxf(m_run[rr], mx[rr]);  // finite: every tile has at least one valid column
+      corr[rr] = fast_exp2(m_run[rr] - m_new[rr]);
+      m_run[rr] = m_new[rr];
+    }
+    float rs[2] = {0.f, 0.f};
+    uint32_t pa[4][4];  // P as A fragments: k-step kk covers key columns 16 kk .. 16 kk + 15 = score tiles 2kk, 2kk+1
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const float p0 = fast_exp2(sacc[j][0] - m_new[0]), p1 = fast_exp2(sacc[j][1] - m_new[0]);
+      const float p2 = fast_exp2(sacc[j][2] - m_new[1]), p3 = fast_exp2(sacc[j][3] - m_new[1]);
+      rs[0] += p0 + p1;
+      rs[1] += p2 + p3;
+      __nv_bfloat162 lo = __floats2bfloat162_rn(p0, p1), hi = __floats2bfloat162_rn(p2, p3);
+      pa[j >> 1][(j & 1) * 2] = *reinterpret_cast<uint32_t*>(&lo);
+      pa[j >> 1][(j & 1) * 2 + 1] = *reinterpret_cast<uint32_t*>(&hi);
+    }
+#pragma unroll
+    for (int rr = 0; rr < 2; ++rr) {
+      rs[rr] += __shfl_xor_sync(0xffffffffu, rs[rr], 1);
+      rs[rr] += __shfl_xor_sync(0xffffffffu, rs[rr], 2);
+      l_run[rr] = l_run[rr] * corr[rr] + rs[rr];
+    }
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      o[j][0] *= corr[0]; o[j][1] *= corr[0];
+      o[j][2] *= corr[1]; o[j][3] *= corr[1];
+    }
+    // O += P V
+    {
+      const int i = lane >> 3, r = lane & 7;
+#pragma unroll
+      for (int kk = 0; kk < 4; ++kk) {
+#pragma unroll
+        for (int jp = 0; jp < 4; ++jp) {  // pairs of 8-wide d tiles
+          uint32_t vb[4];
+          ldmatrix_x4_trans(vb, att_tile_addr(svb, kk * 16 + (i & 1) * 8 + r, jp * 16 + (i >> 1) * 8));
+          mma_bf16_16816(o[2 * jp], pa[kk], vb[0], vb[1]);
+          mma_bf16_16816(o[2 * jp + 1], pa[kk], vb[2], vb[3]);
+        }
+      }
+    }
+  }
+  // normalise and store: rows q0 + warp*16 + g (+8), columns h*64 + 8j + 2t
+  const float inv0 = 1.0f / l_run[0], inv1 = 1.0f / l_run[1];
+  const int r0 = q0 + warp * 16 + g, r1 = r0 + 8;
+  __nv_bfloat16* ob = out + static_cast<int64_t>(b) * N * H * kAttD + h * kAttD;
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    if (r0 < N)
+      *reinterpret_cast<__nv_bfloat162*>(ob + static_cast<int64_t>(r0) * H * kAttD + j * 8 + 2 * t) =
+          __floats2bfloat162_rn(o[j][0] * inv0, o[j][1] * inv0);
+    if (r1 < N)
+      *reinterpret_cast<__nv_bfloat162*>(ob + static_cast<int64_t>(r1) * H * kAttD + j * 8 + 2 * t) =
+          __floats2bfloat162_rn(o[j][2] * inv1, o[j][3] * inv1);
+  }
+}
+
+static int launch_attention(const __nv_bfloat16* qkv, int B, int N, int H, int head_dim, __nv_bfloat16* out, cudaStream_t s) {
+  VDK_REQUIRE(head_dim == kAttD, "attention: head_dim must be 64 (got %d)", head_dim);
+  VDK_REQUIRE(B > 0 && N > 0 && H > 0 && H <= 65535 && B <= 65535, "attention: bad shape");
+  const float scale_log2e = 1.4426950408889634f / sqrtf(static_cast<float>(head_dim));
+  attention_fwd_kernel<<<dim3((N + kAttBM - 1) / kAttBM, H, B), 128, 0, s>>>(qkv, B, N, H, scale_log2e, out);
+  VDK_CUDA_OK(cudaGetLastError());
+  return VDK_OK;
+}
+
+static size_t up256v(size_t v) { return (v + 255) & ~static_cast<size_t>(255); }
+
+struct VitLayout {
+  int N, T, C, Kp;  // patches, tokens, width, padded patch-row length
+  size_t M;         // batch * tokens
+  size_t x, y, big, total;
+};
+
+static int vit_layout(const vdk_vit_net* n, int batch, VitLayout* L) {
+  VDK_REQUIRE(n, "vdk_vit: null network");
+  VDK_REQUIRE(n->patch > 0 && n->image_size > 0 && n->image_size % n->patch == 0, "vdk_vit: image_size must be a multiple of patch");
+  VDK_REQUIRE(n->dim > 0 && n->heads > 0 && n->dim == n->heads * kAttD, "vdk_vit: dim must be heads * 64");
+  VDK_REQUIRE(n->dim % 256 == 0 || n->dim % 8 == 0, "vdk_vit: dim must be a multiple of 8");
+  VDK_REQUIRE(n->depth > 0 && n->depth <= VDK_VIT_MAX_BLOCKS, "vdk_vit: bad depth");
+  VDK_REQUIRE(n->feat_dim > 0 && n->feat_dim % 8 == 0, "vdk_vit: feat_dim must be a multiple of 8");
+  const int G = n->image_size / n->patch;
+  L->N = G * G;
+  L->T = L->N + 1;
+  L->C = n->dim;
+  L->Kp = (3 * n->patch * n->patch + 7) & ~7;
+  L->M = static_cast<size_t>(batch) * L->T;
+  size_t off = 0;
+  auto take = [&](size_t bytes) { size_t o = off; off += up256v(bytes); return o; };
+  L->x = take(L->M * L->C * 2);
+  L->y = take(L->M * L->C * 2);
+  // qkv / MLP hidden / patch rows + patch tokens / neck split-K slabs share one buffer
+  size_t big = L->M * 4 * static_cast<size_t>(L->C) * 2;
+  big = std::max(big, static_cast<size_t>(batch) * L->N * (static_cast<size_t>(L->Kp) + L->C) * 2 + 256);
+  big = std::max(big, static_cast<size_t>(batch) * n->feat_dim * 4 * 64);
+  L->big = take(big);
+  L->total = off + 256;
+  return VDK_OK;
+}
+
+}  // namespace vdk
+
+using namespace vdk;
+
+extern "C" size_t vdk_vit_workspace_bytes(const vdk_vit_net* net, int batch) {
+  VitLayout L;
+  if (!net || batch <= 0 || vit_layout(net, batch, &L) != VDK_OK) return 0;
+  return L.total;
+}
+
+extern "C" int vdk_attention_fwd(const void* qkv, int batch, int tokens, int heads, int head_dim, void* out, void* stream) {
+  VDK_REQUIRE(qkv && out, "vdk_attention_fwd: null operand");
+  return launch_attention(reinterpret_cast<const __nv_bfloat16*>(qkv), batch, tokens, heads, head_dim,
+                          reinterpret_cast<__nv_bfloat16*>(out), reinterpret_cast<cudaStream_t>(stream));
+}
+
+extern "C" int vdk_vit_forward(const vdk_vit_net* net, const float* images, int batch, int l2_normalize, float* embeddings,
+                               void* workspace, size_t workspace_bytes, void* stream) {
+  VitLayout L;
+  int rc = vit_layout(net, batch, &L);
+  if (rc != VDK_OK) return rc;
+  VDK_REQUIRE(images && embeddings && batch > 0, "vdk_vit_forward: null image/embedding buffer");
+  VDK_REQUIRE(workspace && workspace_bytes >= L.total && (reinterpret_cast<uintptr_t>(workspace) & 255) == 0,
+              "vdk_vit_forward: workspace too small or misaligned");
+  VDK_REQUIRE(net->patch_w && net->patch_b && net->cls_token && net->pos_embed && net->ones && net->norm_w && net->norm_b &&
+                  net->neck_ln_w && net->neck_ln_b && net->neck_w && net->neck_b,
+              "vdk_vit_forward: null parameter");
+  cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
+  uint8_t* ws = reinterpret_cast<uint8_t*>(workspace);
+  __nv_bfloat16* x = reinterpret_cast<__nv_bfloat16*>(ws + L.x);
+  __nv_bfloat16* y = reinterpret_cast<__nv_bfloat16*>(ws + L.y);
+  __nv_bfloat16* big = reinterpret_cast<__nv_bfloat16*>(ws + L.big);
+  const int C = L.C, T = L.T, N = L.N, M = static_cast<int>(L.M);
+
+  auto gemm = [&](const void* A, const void* Bw, void* D, int m, int n, int k, int lda, int epi, const float* bias, const float* gamma,
+                  const void* res) {
+    vdk_gemm_desc g{};
+    g.A = A; g.B = Bw; g.D = D;
+    g.M = m; g.N = n; g.K = k; g.lda = lda; g.ldb = k; g.ldd = n;
+    g.in_dtype = VDK_DTYPE_BF16; g.out_dtype = VDK_DTYPE_BF16; g.epilogue = epi;
+    g.bias = bias; g.gamma = gamma; g.residual = res; g.ldr = n; g.ln_eps = 1e-6f; g.split_k = 1;
+    return gemm_run(g, s);
+  };
+
+  // ---- patch embedding + cls / position ----
+  {
+    __nv_bfloat16* rows = big;                                                        // [B*N, Kp]
+    __nv_bfloat16* tok = big + (static_cast<size_t>(batch) * N * L.Kp + 127) / 128 * 128;  // [B*N, C]
+    const int64_t total = static_cast<int64_t>(batch) * N * L.Kp;
+    vit_patchify_kernel<<<static_cast<int>(std::min<int64_t>((total + 255) / 256, 148 * 32)), 256, 0, s>>>(images, batch, net->image_size,
+                                                                                                         net->patch, L.Kp, rows);
+    VDK_CUDA_OK(cudaGetLastError());
+    rc = gemm(rows, net->patch_w, tok, batch * N, C, L.Kp, L.Kp, VDK_EPI_NONE, net->patch_b, nullptr, nullptr);
+    if (rc != VDK_OK) return rc;
+    const int64_t tot2 = static_cast<int64_t>(M) * (C / 2);
+    vit_assemble_kernel<<<static_cast<int>(std::min<int64_t>((tot2 + 255) / 256, 148 * 32)), 256, 0, s>>>(tok, net->cls_token, net->pos_embed,
+                                                                                                        batch, N, C, x);
+    VDK_CUDA_OK(cudaGetLastError());
+  }
+  // ---- blocks ----
+  for (int i = 0; i < net->depth; ++i) {
+    const vdk_vit_block* b = &net->blocks[i];
+    VDK_REQUIRE(b->ln1_w && b->ln1_b && b->qkv_w && b->qkv_b && b->proj_w && b->proj_b && b->ln2_w && b->ln2_b && b->fc1_w &&
+                    b->fc1_b && b->fc2_w && b->fc2_b,
+                "vdk_vit_forward: null parameter in block %d", i);
+    rc = launch_ln_patchify(x, batch, T, 1, C, b->ln1_w, b->ln1_b, 1e-6f, 1, y, nullptr, s);
+    if (rc != VDK_OK) return rc;
+    rc = gemm(y, b->qkv_w, big, M, 3 * C, C, C, VDK_EPI_NONE, b->qkv_b, nullptr, nullptr);
+    if (rc != VDK_OK) return rc;
+    rc = launch_attention(big, batch, T, net->heads, kAttD, y, s);
+    if (rc != VDK_OK) return rc;
+    rc = gemm(y, b->proj_w, x, M, C, C, C, VDK_EPI_SCALE_RESIDUAL, b->proj_b, net->ones, x);  // x += proj(a), in place per tile
+    if (rc != VDK_OK) return rc;
+    rc = launch_ln_patchify(x, batch, T, 1, C, b->ln2_w, b->ln2_b, 1e-6f, 1, y, nullptr, s);
+    if (rc != VDK_OK) return rc;
+    rc = gemm(y, b->fc1_w, big, M, 4 * C, C, C, VDK_EPI_GELU, b->fc1_b, nullptr, nullptr);
+    if (rc != VDK_OK) return rc;
+    rc = gemm(big, b->fc2_w, x, M, C, 4 * C, 4 * C, VDK_EPI_SCALE_RESIDUAL, b->fc2_b, net->ones, x);
+    if (rc != VDK_OK) return rc;
+  }
+  // ---- final LayerNorm, neck LayerNorm, Linear over (token, channel) with BatchNorm1d folded ----
+  rc = launch_ln_patchify(x, batch, T, 1, C, net->norm_w, net->norm_b, 1e-6f, 1, y, nullptr, s);
+  if (rc != VDK_OK) return rc;
+  rc = launch_ln_patchify(y, batch, T, 1, C, net->neck_ln_w, net->neck_ln_b, 1e-5f, 1, x, nullptr, s);
+  if (rc != VDK_OK) return rc;
+  {
+    const int Kn = T * C, F = net->feat_dim;
+    const int tiles = ((batch + 127) / 128) * ((F + 255) / 256);
+    const size_t slab = static_cast<size_t>(batch) * F;
+    int split = std::max(1, std::min(64, (2 * sm_count()) / std::max(1, tiles)));
+    split = vdk_gemm_effective_splits(Kn, split);
+    float* slabs = reinterpret_cast<float*>(big);
+    vdk_gemm_desc g{};
+    g.A = x; g.B = net->neck_w; g.D = slabs;
+    g.M = batch; g.N = F; g.K = Kn; g.lda = Kn; g.ldb = Kn; g.ldd = F;
+    g.in_dtype = VDK_DTYPE_BF16; g.out_dtype = VDK_DTYPE_FP32; g.epilogue = VDK_EPI_NONE;
+    g.split_k = split;
+    g.split_stride = split > 1 ? static_cast<long long>(slab) : 0;
+    rc = gemm_run(g, s);
+    if (rc != VDK_OK) return rc;
+    rc = launch_neck_finalize(slabs, split, slab, batch, F, net->neck_b, l2_normalize, embeddings, s);
+    if (rc != VDK_OK) return rc;
+  }
+  return VDK_OK;
+}

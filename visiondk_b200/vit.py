@@ -1,0 +1,193 @@
+"""ViT backbones for the CBIR extract path (inference) on the B200 kernels.
+
+Mirrors what `TimmWrapper(model_name='vit_*', feat_dim, image_size)` builds in the reference
+(models/faceX/backbone/timm_wrapper.py:16-21 + the Transformer neck of :39-47): the parameter tree and state_dict keys of
+timm 0.9.16's VisionTransformer (`model.patch_embed.proj`, `model.cls_token`, `model.pos_embed`, `model.blocks.{i}.{norm1,
+attn.qkv, attn.proj, norm2, mlp.fc1, mlp.fc2}`, `model.norm`) and `output_layer.{0: LayerNorm, 2: Linear, 3: BatchNorm1d}`,
+so reference checkpoints load with `strict=True`.  The eval forward runs in `vdk_vit_forward` (csrc/vit.cu).  Training a
+ViT (BASELINE config 3) needs the attention backward, which is not built: `.train()` forward raises.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from typing import Dict, Optional
+
+import torch
+import torch.nn as nn
+
+from . import _lib
+
+VIT_ARCHS = {
+    # timm name -> (patch, embed_dim, depth, heads)
+    "vit_tiny_patch16_224": (16, 192, 12, 3),
+    "vit_small_patch16_224": (16, 384, 12, 6),
+    "vit_base_patch16_224": (16, 768, 12, 12),
+    "vit_large_patch16_224": (16, 1024, 24, 16),
+    "vit_large_patch14_clip_336": (14, 1024, 24, 16),
+}
+MAX_BLOCKS = 48
+
+
+class _Attention(nn.Module):
+    def __init__(self, dim):
+        super().__init__()
+        self.qkv = nn.Linear(dim, 3 * dim, bias=True)
+        self.proj = nn.Linear(dim, dim)
+
+
+class _Mlp(nn.Module):
+    def __init__(self, dim):
+        super().__init__()
+        self.fc1 = nn.Linear(dim, 4 * dim)
+        self.fc2 = nn.Linear(4 * dim, dim)
+
+
+class _Block(nn.Module):
+    def __init__(self, dim):
+        super().__init__()
+        self.norm1 = nn.LayerNorm(dim, eps=1e-6)
+        self.attn = _Attention(dim)
+        self.norm2 = nn.LayerNorm(dim, eps=1e-6)
+        self.mlp = _Mlp(dim)
+
+
+class _PatchEmbed(nn.Module):
+    def __init__(self, patch, dim):
+        super().__init__()
+        self.proj = nn.Conv2d(3, dim, kernel_size=patch, stride=patch)
+
+
+class ViTParams(nn.Module):
+    """timm 0.9.16 `VisionTransformer(num_classes=0, global_pool='')` parameter tree (timm/models/vision_transformer.py)."""
+
+    def __init__(self, image_size, patch, dim, depth, heads):
+        super().__init__()
+        self.image_size, self.patch, self.dim, self.depth, self.heads = image_size, patch, dim, depth, heads
+        n = (image_size // patch) ** 2
+        self.patch_embed = _PatchEmbed(patch, dim)
+        self.cls_token = nn.Parameter(torch.zeros(1, 1, dim))
+        self.pos_embed = nn.Parameter(torch.randn(1, n + 1, dim) * 0.02)
+        self.blocks = nn.Sequential(*[_Block(dim) for _ in range(depth)])
+        self.norm = nn.LayerNorm(dim, eps=1e-6)
+        for m in self.modules():
+            if isinstance(m, nn.Linear):
+                nn.init.trunc_normal_(m.weight, std=0.02)
+                nn.init.zeros_(m.bias)
+        nn.init.normal_(self.cls_token, std=1e-6)
+
+
+class _VitBlockC(C.Structure):
+    _fields_ = [(n, C.c_void_p) for n in ("ln1_w", "ln1_b", "qkv_w", "qkv_b", "proj_w", "proj_b", "ln2_w", "ln2_b", "fc1_w", "fc1_b",
+                                          "fc2_w", "fc2_b")]
+
+
+class VitNetC(C.Structure):
+    """vdk_vit_net (include/vdk_b200.h)."""
+    _fields_ = [("image_size", C.c_int), ("patch", C.c_int), ("dim", C.c_int), ("depth", C.c_int), ("heads", C.c_int),
+                ("feat_dim", C.c_int),
+                ("patch_w", C.c_void_p), ("patch_b", C.c_void_p), ("cls_token", C.c_void_p), ("pos_embed", C.c_void_p),
+                ("ones", C.c_void_p), ("blocks", _VitBlockC * MAX_BLOCKS),
+                ("norm_w", C.c_void_p), ("norm_b", C.c_void_p), ("neck_ln_w", C.c_void_p), ("neck_ln_b", C.c_void_p),
+                ("neck_w", C.c_void_p), ("neck_b", C.c_void_p)]
+
+
+class ViTWrapper(nn.Module):
+    """Drop-in for the reference's TimmWrapper when the timm model is a VisionTransformer (eval / extract path)."""
+
+    def __init__(self, model_name: str, feat_dim: int, image_size: int, pretrained: bool = True, patch=None, dim=None, depth=None,
+                 heads=None, **kwargs):
+        super().__init__()
+        if dim is None:
+            if model_name not in VIT_ARCHS:
+                raise ValueError(f"backbone '{model_name}' is not built for B200 yet; available: {sorted(VIT_ARCHS)}")
+            patch, dim, depth, heads = VIT_ARCHS[model_name]
+        if image_size % patch != 0 or dim != heads * 64 or depth > MAX_BLOCKS:
+            raise ValueError("ViT on B200: image_size must be a multiple of patch, head_dim must be 64, depth <= 48")
+        self.model_name, self.feat_dim, self.image_size = model_name, int(feat_dim), int(image_size)
+        self.model = ViTParams(image_size, patch, dim, depth, heads)
+        tokens = (image_size // patch) ** 2 + 1
+        self.output_layer = nn.Sequential(nn.LayerNorm(dim), nn.Flatten(1), nn.Linear(tokens * dim, feat_dim),
+                                          nn.BatchNorm1d(feat_dim))
+        self._packed: Optional[Dict] = None
+        self._packed_key = None
+        self._ws = None
+        if pretrained:
+            raise RuntimeError("pretrained timm weights cannot be downloaded here (no network): pass pretrained=False and "
+                               "load a checkpoint with load_state_dict (keys are timm's)")
+
+    def forward(self, x: torch.Tensor) -> torch.Tensor:
+        if self.training:
+            raise NotImplementedError("ViT training (attention backward) is not built on B200 yet; use .eval() for the "
+                                      "extract path — there is no fallback")
+        return self.embed(x, l2_normalize=False)
+
+    def _version_key(self, device):
+        return (str(device),) + tuple(int(t._version) for t in list(self.parameters()) + list(self.buffers()))
+
+    def _pack(self, device) -> VitNetC:
+        key = self._version_key(device)
+        if self._packed is not None and self._packed_key == key:
+            return self._packed["net"]
+        keep = []
+
+        def f32(t):
+            t = t.detach().to(device, torch.float32).contiguous()
+            keep.append(t)
+            return t.data_ptr()
+
+        def bf16(t):
+            t = t.detach().to(device, torch.float32).contiguous().to(torch.bfloat16)
+            keep.append(t)
+            return t.data_ptr()
+
+        m, net = self.model, VitNetC()
+        net.image_size, net.patch, net.dim, net.depth, net.heads, net.feat_dim = (m.image_size, m.patch, m.dim, m.depth, m.heads,
+                                                                                 self.feat_dim)
+        k = 3 * m.patch * m.patch
+        kp = (k + 7) // 8 * 8
+        w = m.patch_embed.proj.weight.detach().reshape(m.dim, k)  # (c, kh, kw) order
+        if kp != k:
+            w = torch.cat([w, torch.zeros(m.dim, kp - k, dtype=w.dtype, device=w.device)], dim=1)
+        net.patch_w, net.patch_b = bf16(w), f32(m.patch_embed.proj.bias)
+        net.cls_token, net.pos_embed = f32(m.cls_token.reshape(-1)), f32(m.pos_embed.reshape(-1, m.dim))
+        net.ones = f32(torch.ones(m.dim))
+        for i, blk in enumerate(m.blocks):
+            b = net.blocks[i]
+            b.ln1_w, b.ln1_b = f32(blk.norm1.weight), f32(blk.norm1.bias)
+            b.qkv_w, b.qkv_b = bf16(blk.attn.qkv.weight), f32(blk.attn.qkv.bias)
+            b.proj_w, b.proj_b = bf16(blk.attn.proj.weight), f32(blk.attn.proj.bias)
+            b.ln2_w, b.ln2_b = f32(blk.norm2.weight), f32(blk.norm2.bias)
+            b.fc1_w, b.fc1_b = bf16(blk.mlp.fc1.weight), f32(blk.mlp.fc1.bias)
+            b.fc2_w, b.fc2_b = bf16(blk.mlp.fc2.weight), f32(blk.mlp.fc2.bias)
+        net.norm_w, net.norm_b = f32(m.norm.weight), f32(m.norm.bias)
+        ln, lin, bn = self.output_layer[0], self.output_layer[2], self.output_layer[3]
+        net.neck_ln_w, net.neck_ln_b = f32(ln.weight), f32(ln.bias)
+        # BatchNorm1d (eval statistics) folded into the Linear: y = s * (W x + b - mean) + beta, s = gamma / sqrt(var + eps)
+        s = (bn.weight.detach().double() / torch.sqrt(bn.running_var.detach().double() + bn.eps))
+        wn = lin.weight.detach().double() * s[:, None]
+        bnb = (lin.bias.detach().double() - bn.running_mean.detach().double()) * s + bn.bias.detach().double()
+        net.neck_w, net.neck_b = bf16(wn.float()), f32(bnb.float())
+        self._packed, self._packed_key = {"net": net, "keep": keep}, key
+        return net
+
+    @torch.no_grad()
+    def embed(self, x: torch.Tensor, l2_normalize: bool = False) -> torch.Tensor:
+        """[B,3,S,S] fp32 NCHW -> fp32 [B, feat_dim] (TimmWrapper.forward in eval mode; optionally F.normalize fused)."""
+        lib = _lib.load()
+        if x.device.type != "cuda":
+            raise RuntimeError("visiondk_b200.ViTWrapper runs on CUDA (sm_100a) only; there is no CPU fallback")
+        if x.dim() != 4 or x.shape[1] != 3 or x.shape[2] != self.image_size or x.shape[3] != self.image_size:
+            raise ValueError(f"expected [B,3,{self.image_size},{self.image_size}], got {tuple(x.shape)}")
+        x = x.contiguous().float()
+        net = self._pack(x.device)
+        B = x.shape[0]
+        out = torch.empty((B, self.feat_dim), dtype=torch.float32, device=x.device)
+        need = lib.vdk_vit_workspace_bytes(C.byref(net), B)
+        if need == 0:
+            raise RuntimeError("vdk_vit_workspace_bytes: " + _lib.last_error())
+        if self._ws is None or self._ws.numel() < need or self._ws.device != x.device:
+            self._ws = torch.empty((need,), dtype=torch.uint8, device=x.device)
+        with torch.cuda.device(x.device):
+            _lib.check(lib.vdk_vit_forward(C.byref(net), x.data_ptr(), B, int(l2_normalize), out.data_ptr(), self._ws.data_ptr(),
+                                           self._ws.numel(), _lib.stream_ptr()), "vdk_vit_forward")
+        return out
