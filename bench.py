@@ -429,6 +429,60 @@ def bench_extract(ctx, args):
             "h2d": B * 3 * IMG * IMG * 4, "d2h": B * FEAT * 4, "batch": B}
 
 
+def bench_extract_vit(ctx, args):
+    """Secondary row (BASELINE config 5 family): CBIR extraction with a Transformer backbone, ViT-B/16 224^2, random-init
+    weights, batch = --batch per GPU.  Device-resident and end-to-end (FeatureExtractor.extract_cbir from pinned host batches)."""
+    import torch
+    from visiondk_b200.vit import ViTWrapper, VIT_ARCHS
+    from visiondk_b200.cbir import FeatureExtractor
+    name, B = "vit_base_patch16_224", args.batch
+    torch.manual_seed(0)
+    model = ViTWrapper(name, FEAT, IMG, pretrained=False).to(ctx.dev).eval()
+    gen = torch.Generator(device=ctx.dev).manual_seed(ctx.rank)
+    pool = [torch.randn(B, 3, IMG, IMG, device=ctx.dev, generator=gen) for _ in range(2)]
+    state = {"i": 0}
+
+    def step_dev():
+        x = pool[state["i"] & 1]
+        state["i"] += 1
+        return model.embed(x, l2_normalize=True)
+
+    ms = timed(ctx, step_dev, args.steps, args.warmup)
+    host_x = [torch.randn(B, 3, IMG, IMG).pin_memory() for _ in range(2)]
+    extractor = FeatureExtractor(model)
+
+    def run_e2e(n_steps):
+        return extractor.extract_cbir((host_x[i & 1] for i in range(n_steps)), ctx.dev)
+
+    run_e2e(3)
+    ctx.barrier()
+    t0 = time.perf_counter()
+    out = run_e2e(args.steps)
+    torch.cuda.synchronize()
+    e2e_ms = (time.perf_counter() - t0) * 1e3 / args.steps
+    assert out.shape == (args.steps * B, FEAT)
+    if ctx.world > 1:
+        import torch.distributed as dist
+        t = torch.tensor([e2e_ms], device=ctx.dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        e2e_ms = float(t.item())
+    patch, dim, depth, heads = VIT_ARCHS[name]
+    T = (IMG // patch) ** 2 + 1
+    gflop = (depth * (24.0 * T * dim * dim + 4.0 * T * T * dim) + 2.0 * (T - 1) * 3 * patch * patch * dim + 2.0 * T * dim * FEAT) / 1e9
+    peak, src = peak_tflops()
+    ach = B * gflop / ms
+    return {"metric": "embeddings/sec (ViT-B/16 224^2, CBIR extract, inference)", "value": ctx.world * B / (ms * 1e-3),
+            "unit": "embeddings/s", "ms_per_step": ms, "scaling": "weak", "dtype": "bf16",
+            "config": {"workload": f"CBIR eval extract: ViT-B/16 {IMG}^2 (197 tokens) -> {FEAT}-d L2-normalised embeddings, batch {B} "
+                                   f"per GPU, random-init weights", "l2": "two alternating input batches (2 x 154 MB)"},
+            "e2e": {"value": ctx.world * B / (e2e_ms * 1e-3), "unit": "embeddings/s", "ms_per_step": e2e_ms,
+                    "h2d_bytes_per_step": B * 3 * IMG * IMG * 4, "d2h_bytes_per_step": B * FEAT * 4},
+            "gpu_launches": (3 + 7 * depth + 4) * args.steps,
+            "roofline": {"bound": "tensor", "whole_step": {"achieved": ach, "unit": "TFLOP/s", "peak": peak, "frac": ach / peak,
+                                                            "peak_source": src,
+                                                            "note": f"{gflop:.2f} GFLOP per embedding over the whole forward"}}}
+
+
 def bench_train(ctx, args):
     """BASELINE configs[1]: ConvNeXt-B 224^2 faceX ArcFace (C=1000) train step, bf16 activations / fp32 master weights,
     per-GPU batch fixed (weak scaling), DDP = one NCCL all-reduce(mean) of the flat gradient buffers per step."""
@@ -614,6 +668,8 @@ def main():
     torch.cuda.empty_cache()
     ex = bench_extract(ctx, args) if want("extract") else None
     torch.cuda.empty_cache()
+    exv = bench_extract_vit(ctx, args) if want("extract") else None
+    torch.cuda.empty_cache()
     rt = bench_retrieval(ctx, args) if want("retrieval") else None
     clocks = sampler.stop() if sampler else None
 
@@ -669,10 +725,11 @@ def main():
                 "gpu_launches": tr["launches_per_step"] * args.steps,
                 "roofline": roof if roof is not None else {"bound": "tensor", "whole_step": tr["whole_step"]},
                 "cpu_baseline": cpu.get("train"),
-                "extract": extract, "retrieval": retrieval,
+                "extract": extract, "extract_vit": exv, "retrieval": retrieval,
             }
         elif ex is not None:
             line = dict(extract)
+            line["extract_vit"] = exv
             line["retrieval"] = retrieval
         else:
             line = dict(retrieval)

@@ -275,13 +275,16 @@ int vdk_attention_fwd(const void* qkv, int batch, int tokens, int heads, int hea
  * face path); the three contractions run on tcgen05 with a 3-way bf16 operand split (fp32-grade accuracy). */
 #define VDK_HEAD_ARCFACE 0
 #define VDK_HEAD_CIRCLELOSS 1
+#define VDK_HEAD_MV_SOFTMAX 2 /* MV_Softmax.forward, models/faceX/head/mv_softmax.py:25-44 */
 
 typedef struct vdk_head_desc {
   int kind;                 /* VDK_HEAD_* */
   int batch, feat_dim, num_class;
-  float margin_arc, margin_am, scale; /* ArcFace(margin_arc, margin_am, scale) */
-  float margin, gamma;                /* CircleLoss(margin, gamma) */
+  float margin_arc, margin_am, scale; /* ArcFace(margin_arc, margin_am, scale); scale also MV_Softmax */
+  float margin, gamma;                /* CircleLoss(margin, gamma); margin also MV_Softmax */
   float label_smooth;                 /* CrossEntropyLoss(label_smoothing) */
+  float mv_weight;                    /* MV_Softmax(is_am, margin, mv_weight, scale) */
+  int is_am;
 } vdk_head_desc;
 
 size_t vdk_head_workspace_bytes(const vdk_head_desc* d);

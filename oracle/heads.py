@@ -51,11 +51,32 @@ def circleloss_logits(feats, weight, labels, margin=0.25, gamma=256.0):
     return torch.where(onehot, logit_p, logit_n) * gamma
 
 
+def mv_softmax_logits(feats, weight, labels, is_am=False, margin=0.35, mv_weight=1.12, scale=32.0):
+    """mv_softmax.py:25-44 (MV-Softmax: hard negatives — those scoring above the margin-shifted target — are re-weighted;
+    the comparison carries no gradient; cos is NOT clamped here, exactly like the reference)."""
+    kernel_norm = F.normalize(weight, dim=0)
+    cos = torch.mm(F.normalize(feats), kernel_norm)
+    gt = cos[torch.arange(labels.shape[0]), labels].view(-1, 1)
+    if is_am:
+        mask = cos > gt - margin
+        final_gt = torch.where(gt > margin, gt - margin, gt)
+    else:
+        sin = torch.sqrt(1.0 - torch.pow(gt, 2))
+        cos_m = gt * math.cos(margin) - sin * math.sin(margin)
+        mask = cos > cos_m
+        final_gt = torch.where(gt > 0.0, cos_m, gt)
+    out = torch.where(mask, mv_weight * cos + mv_weight - 1.0, cos)
+    onehot = F.one_hot(labels, cos.shape[1]).bool()
+    out = torch.where(onehot, final_gt.expand_as(out), out)
+    return out * scale
+
+
 def cross_entropy(logits, labels, label_smooth: float = 0.0):
     """loss.py:71-73, called at engine/procedure/train.py:196."""
     return F.cross_entropy(logits, labels, label_smoothing=label_smooth)
 
 
 def head_loss(kind, feats, weight, labels, label_smooth=0.0, **kw):
-    logits = arcface_logits(feats, weight, labels, **kw) if kind == "arcface" else circleloss_logits(feats, weight, labels, **kw)
+    fn = {"arcface": arcface_logits, "circleloss": circleloss_logits, "mv_softmax": mv_softmax_logits}[kind]
+    logits = fn(feats, weight, labels, **kw)
     return cross_entropy(logits, labels, label_smooth), logits

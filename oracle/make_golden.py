@@ -62,6 +62,33 @@ def heads():
         np.savez_compressed(os.path.join(OUT, f"heads_{name}.npz"), **out)
 
 
+def heads_mv():
+    mv = load("models/faceX/head/mv_softmax.py", "ref_mv_softmax")
+    loss = load("models/losses/loss.py", "ref_loss")
+    B, D, Cn, smooth = 16, 64, 40, 0.1
+    torch.manual_seed(17)
+    feats = torch.randn(B, D) * 2.0
+    labels = torch.randint(0, Cn, (B,))
+    out = {"feats": feats.numpy(), "labels": labels.numpy(), "label_smooth": np.float32(smooth)}
+    for kind, kwargs in (("mv_arc", dict(is_am=False, margin=0.35, mv_weight=1.12, scale=32)),
+                         ("mv_am", dict(is_am=True, margin=0.35, mv_weight=1.12, scale=32))):
+        torch.manual_seed(19)
+        head = mv.MV_Softmax(D, Cn, **kwargs)
+        with torch.no_grad():  # pull some class centres towards their samples so that both gt > 0 / gt > margin branches occur
+            for r in range(0, B, 2):
+                head.weight[:, labels[r]] = feats[r] / feats[r].norm() + 0.4 * head.weight[:, labels[r]]
+        f = feats.clone().requires_grad_(True)
+        logits = head(f, labels)
+        l = loss.create_Lossfn("ce")(label_smooth=smooth)(logits, labels)
+        l.backward()
+        out[f"{kind}_weight"] = head.weight.detach().numpy().copy()
+        out[f"{kind}_logits"] = logits.detach().numpy()
+        out[f"{kind}_loss"] = l.detach().numpy()
+        out[f"{kind}_dfeats"] = f.grad.numpy().copy()
+        out[f"{kind}_dweight"] = head.weight.grad.numpy().copy()
+    np.savez_compressed(os.path.join(OUT, "heads_mv.npz"), **out)
+
+
 def ema_sgd_sched():
     ema_mod = load("models/ema.py", "ref_ema")
     sched = load("engine/scheduler.py", "ref_sched")
@@ -97,5 +124,6 @@ if __name__ == "__main__":
         sys.exit("make_golden.py needs /root/reference (authoring container only)")
     os.makedirs(OUT, exist_ok=True)
     heads()
+    heads_mv()
     ema_sgd_sched()
     print("golden vectors written to", OUT)

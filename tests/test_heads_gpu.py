@@ -12,7 +12,7 @@ import pytest
 import torch
 
 from oracle import heads as H
-from visiondk_b200.heads import ArcFace, CircleLoss, HeadFactory, margin_ce_loss
+from visiondk_b200.heads import ArcFace, CircleLoss, HeadFactory, MV_Softmax, margin_ce_loss
 
 pytestmark = pytest.mark.gpu
 GOLD = os.path.join(os.path.dirname(__file__), "golden")
@@ -57,6 +57,64 @@ def test_heads_match_reference_golden(lib, case, kind):
     close(head.weight.grad.cpu(), torch.from_numpy(z[f"{kind}_dweight"]), 2e-3, "dweight (fused)")
 
 
+@pytest.mark.parametrize("kind,is_am", [("mv_arc", False), ("mv_am", True)])
+def test_mv_softmax_matches_reference_golden(lib, kind, is_am):
+    """MV-Softmax (models/faceX/head/mv_softmax.py) against vectors minted from the reference's own module
+    (tests/golden/heads_mv.npz): un-fused logits + torch CE, and the fused criterion∘head."""
+    z = np.load(os.path.join(GOLD, "heads_mv.npz"))
+    feats = torch.from_numpy(z["feats"]).cuda().requires_grad_(True)
+    labels = torch.from_numpy(z["labels"]).cuda()
+    w = torch.from_numpy(z[f"{kind}_weight"])
+    head = MV_Softmax(w.shape[0], w.shape[1], is_am, 0.35, 1.12, 32).cuda()
+    with torch.no_grad():
+        head.weight.copy_(w)
+    smooth = float(z["label_smooth"])
+    logits = head(feats, labels)
+    close(logits.detach().cpu(), torch.from_numpy(z[f"{kind}_logits"]), 2e-4, "logits")
+    torch.nn.functional.cross_entropy(logits, labels, label_smoothing=smooth).backward()
+    close(feats.grad.cpu(), torch.from_numpy(z[f"{kind}_dfeats"]), 2e-3, "dfeats (un-fused)")
+    close(head.weight.grad.cpu(), torch.from_numpy(z[f"{kind}_dweight"]), 2e-3, "dweight (un-fused)")
+    feats.grad, head.weight.grad = None, None
+    loss = margin_ce_loss(head, feats, labels, smooth)
+    assert abs(loss.item() - float(z[f"{kind}_loss"])) <= 1e-4 * abs(float(z[f"{kind}_loss"])) + 1e-5
+    loss.backward()
+    close(feats.grad.cpu(), torch.from_numpy(z[f"{kind}_dfeats"]), 2e-3, "dfeats (fused)")
+    close(head.weight.grad.cpu(), torch.from_numpy(z[f"{kind}_dweight"]), 2e-3, "dweight (fused)")
+
+
+@pytest.mark.parametrize("is_am", [False, True])
+def test_mv_softmax_matches_oracle_on_fresh_inputs(lib, is_am):
+    """Sizes kept moderate: the hard-example test `cos > threshold` is a discontinuity, and an element within rounding of the
+    threshold may legitimately land on the other side (the comparison below skips elements within 1e-5 of it)."""
+    B, D, Cn = 64, 128, 300
+    torch.manual_seed(5 + int(is_am))
+    feats = torch.randn(B, D) * 2
+    labels = torch.randint(0, Cn, (B,))
+    head = MV_Softmax(D, Cn, is_am, 0.35, 1.12, 32)
+    with torch.no_grad():  # some well-aligned classes so that gt > 0 / gt > margin both occur
+        for r in range(0, B, 2):
+            head.weight[:, labels[r]] = feats[r] / feats[r].norm() + 0.3 * head.weight[:, labels[r]]
+    fo = feats.clone().requires_grad_(True)
+    wo = head.weight.detach().clone().requires_grad_(True)
+    ref_loss, ref_logits = H.head_loss("mv_softmax", fo, wo, labels, label_smooth=0.1, is_am=is_am, margin=0.35, mv_weight=1.12,
+                                       scale=32.0)
+    ref_loss.backward()
+    cos = torch.mm(torch.nn.functional.normalize(feats), torch.nn.functional.normalize(wo.detach(), dim=0))
+    gt = cos[torch.arange(B), labels].view(-1, 1)
+    thr = gt - 0.35 if is_am else gt * np.cos(0.35) - torch.sqrt(1 - gt * gt) * np.sin(0.35)
+    safe = (cos - thr).abs() > 1e-5
+    head = head.cuda()
+    fg = feats.clone().cuda().requires_grad_(True)
+    got_logits = head(fg, labels.cuda()).detach().cpu()
+    assert ((got_logits - ref_logits.detach()).abs()[safe]).max().item() <= 2e-4 * ref_logits.abs().max().item()
+    if bool(safe.all()):
+        loss = margin_ce_loss(head, fg, labels.cuda(), 0.1)
+        loss.backward()
+        assert abs(loss.item() - ref_loss.item()) <= 1e-4 * abs(ref_loss.item()) + 1e-5
+        close(fg.grad.cpu(), fo.grad, 2e-3, "mv dfeats")
+        close(head.weight.grad.cpu(), wo.grad, 2e-3, "mv dweight")
+
+
 @pytest.mark.parametrize("B,D,Cn", [(160, 512, 1000), (7, 64, 33), (256, 512, 2051)])
 def test_heads_match_oracle_on_fresh_inputs(lib, B, D, Cn):
     torch.manual_seed(B)
@@ -87,6 +145,8 @@ def test_head_factory_surface(lib):
     np.testing.assert_allclose(h.weight.detach().norm(dim=0).numpy(), 1.0, rtol=1e-5)
     h = HeadFactory({"circleloss": dict(feat_dim=64, num_class=10, margin=0.25, gamma=256)}).get_head()
     assert isinstance(h, CircleLoss)
+    h2 = HeadFactory({"mv-softmax": dict(feat_dim=64, num_class=10, is_am=False, margin=0.35, mv_weight=1.12, scale=32)}).get_head()
+    assert isinstance(h2, MV_Softmax)
     with pytest.raises(NotImplementedError):
         HeadFactory({"magface": {}}).get_head()
     with pytest.raises(RuntimeError):

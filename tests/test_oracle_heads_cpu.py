@@ -45,3 +45,21 @@ def test_fallback_branch_is_exercised():
 def test_init_head_weight_has_unit_columns():
     w = H.init_head_weight(64, 10, torch.Generator().manual_seed(0))
     np.testing.assert_allclose(w.norm(dim=0).numpy(), 1.0, rtol=1e-5)
+
+
+@pytest.mark.parametrize("kind,is_am", [("mv_arc", False), ("mv_am", True)])
+def test_mv_softmax_oracle_reproduces_reference_goldens(kind, is_am):
+    """tests/golden/heads_mv.npz was produced by the reference's own MV_Softmax + CrossEntropyLoss (oracle/make_golden.py:
+    heads_mv); the restatement must reproduce logits and loss bit for bit and the autograd gradients to rounding."""
+    z = np.load(os.path.join(GOLD, "heads_mv.npz"))
+    feats = torch.from_numpy(z["feats"]).clone().requires_grad_(True)
+    w = torch.from_numpy(z[f"{kind}_weight"]).clone().requires_grad_(True)
+    labels = torch.from_numpy(z["labels"])
+    logits = H.mv_softmax_logits(feats, w, labels, is_am=is_am, margin=0.35, mv_weight=1.12, scale=32.0)
+    loss = H.cross_entropy(logits, labels, float(z["label_smooth"]))
+    loss.backward()
+    assert np.array_equal(logits.detach().numpy(), z[f"{kind}_logits"])
+    assert np.array_equal(loss.detach().numpy(), z[f"{kind}_loss"])
+    np.testing.assert_allclose(feats.grad.numpy(), z[f"{kind}_dfeats"], rtol=1e-6, atol=1e-9)
+    np.testing.assert_allclose(w.grad.numpy(), z[f"{kind}_dweight"], rtol=1e-6, atol=1e-9)
+

@@ -20,7 +20,8 @@ EPI_NONE, EPI_GELU, EPI_SCALE_RESIDUAL, EPI_LAYERNORM, EPI_MUL_GELU_GRAD = 0, 1,
 class HeadDesc(C.Structure):
     _fields_ = [("kind", C.c_int), ("batch", C.c_int), ("feat_dim", C.c_int), ("num_class", C.c_int),
                 ("margin_arc", C.c_float), ("margin_am", C.c_float), ("scale", C.c_float),
-                ("margin", C.c_float), ("gamma", C.c_float), ("label_smooth", C.c_float)]
+                ("margin", C.c_float), ("gamma", C.c_float), ("label_smooth", C.c_float),
+                ("mv_weight", C.c_float), ("is_am", C.c_int)]
 
 
 class TopkPlan(C.Structure):

@@ -120,14 +120,53 @@ __global__ void __launch_bounds__(256) col_inv_norm_kernel(const float* __restri
 }
 
 struct HeadCfg {
-  int kind;  // VDK_HEAD_ARCFACE / VDK_HEAD_CIRCLELOSS
-  float cos_m, sin_m, min_cos, margin_am, scale;  // arcface
-  float margin, gamma;                            // circleloss
+  int kind;  // VDK_HEAD_ARCFACE / VDK_HEAD_CIRCLELOSS / VDK_HEAD_MV_SOFTMAX
+  float cos_m, sin_m, min_cos, margin_am, scale;  // arcface (cos_m, sin_m, scale also mv-softmax)
+  float margin, gamma;                            // circleloss (margin also mv-softmax)
+  float mv_weight;                                // mv-softmax
+  int is_am;
   float label_smooth;
 };
 
+// MV-Softmax (mv_softmax.py:25-44) needs the label column's cosine `gt` of the row for every element: elements scoring
+// above the margin-shifted target are "hard" (re-weighted; the comparison carries no gradient).  No clamp on cos there.
+struct MvRow {
+  float thr;       // hard-example threshold: cos(theta_y + m) (arc) or gt - m (am)
+  float final_gt;  // the label column's logit / scale
+  float dfinal;    // d final_gt / d gt
+};
+__device__ __forceinline__ MvRow mv_row(const HeadCfg& h, float gt) {
+  MvRow r;
+  if (h.is_am) {
+    r.thr = gt - h.margin;
+    r.final_gt = gt > h.margin ? gt - h.margin : gt;
+    r.dfinal = 1.f;
+  } else {
+    const float s = sqrtf(1.0f - gt * gt);  // NaN for |gt| > 1, exactly like the reference
+    const float ctm = gt * h.cos_m - s * h.sin_m;
+    r.thr = ctm;
+    r.final_gt = gt > 0.f ? ctm : gt;
+    r.dfinal = gt > 0.f ? h.cos_m + (gt / s) * h.sin_m : 1.f;
+  }
+  return r;
+}
+
 // logit and d(logit)/d(cos) of one element (the reference's expressions, arcface.py:24-35 / circleloss.py:33-42)
-__device__ __forceinline__ void head_logit(const HeadCfg& h, float cos_raw, bool is_label, float& z, float& dz_dcos) {
+__device__ __forceinline__ void head_logit(const HeadCfg& h, const MvRow& mv, float cos_raw, bool is_label, float& z,
+                                           float& dz_dcos) {
+  if (h.kind == VDK_HEAD_MV_SOFTMAX) {
+    if (is_label) {
+      z = mv.final_gt * h.scale;
+      dz_dcos = mv.dfinal * h.scale;
+    } else if (cos_raw > mv.thr) {
+      z = (h.mv_weight * cos_raw + h.mv_weight - 1.0f) * h.scale;
+      dz_dcos = h.mv_weight * h.scale;
+    } else {
+      z = cos_raw * h.scale;
+      dz_dcos = h.scale;
+    }
+    return;
+  }
   const float c = fminf(fmaxf(cos_raw, -1.f), 1.f);
   const float clamp_pass = (cos_raw >= -1.f && cos_raw <= 1.f) ? 1.f : 0.f;  // torch.clamp backward
   if (h.kind == VDK_HEAD_ARCFACE) {
@@ -165,10 +204,12 @@ margin_ce_fwd_kernel(const float* __restrict__ cosm, int ldc, int B, int Cn, con
   const int row = blockIdx.x;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int64_t y = labels[row];
+  MvRow mv{0.f, 0.f, 0.f};
+  if (h.kind == VDK_HEAD_MV_SOFTMAX) mv = mv_row(h, cosm[static_cast<int64_t>(row) * ldc + y]);
   float mx = -FLT_MAX, se = 0.f, sz = 0.f, zy = 0.f;
   for (int c = tid; c < Cn; c += 256) {
     float z, dz;
-    head_logit(h, cosm[static_cast<int64_t>(row) * ldc + c], c == y, z, dz);
+    head_logit(h, mv, cosm[static_cast<int64_t>(row) * ldc + c], c == y, z, dz);
     if (logits) logits[static_cast<int64_t>(row) * Cn + c] = z;
     if (c == y) zy = z;
     sz += z;
@@ -229,11 +270,13 @@ margin_ce_bwd_kernel(const float* __restrict__ cosm, int ldc, int B, int Cn, con
   const float g = (grad_out ? *grad_out : 1.f) / static_cast<float>(B);
   const float lse = row_lse ? row_lse[row] : 0.f;
   const float t_off = h.label_smooth / static_cast<float>(Cn);
+  MvRow mv{0.f, 0.f, 0.f};
+  if (h.kind == VDK_HEAD_MV_SOFTMAX) mv = mv_row(h, cosm[static_cast<int64_t>(row) * ldc + y]);
   for (int c = threadIdx.x; c < ldd; c += 256) {
     float v = 0.f;
     if (c < Cn) {
       float z, dz;
-      head_logit(h, cosm[static_cast<int64_t>(row) * ldc + c], c == y, z, dz);
+      head_logit(h, mv, cosm[static_cast<int64_t>(row) * ldc + c], c == y, z, dz);
       if (dlogits) {  // un-fused path: the caller's criterion produced d(loss)/d(logits)
         v = dlogits[static_cast<int64_t>(row) * Cn + c] * dz;
       } else {
@@ -288,7 +331,8 @@ static int pad8(int v) { return (v + 7) & ~7; }
 
 static int make_cfg(const vdk_head_desc* d, HeadCfg* h) {
   VDK_REQUIRE(d, "null head descriptor");
-  VDK_REQUIRE(d->kind == VDK_HEAD_ARCFACE || d->kind == VDK_HEAD_CIRCLELOSS, "head kind must be arcface or circleloss");
+  VDK_REQUIRE(d->kind == VDK_HEAD_ARCFACE || d->kind == VDK_HEAD_CIRCLELOSS || d->kind == VDK_HEAD_MV_SOFTMAX,
+              "head kind must be arcface, circleloss or mv-softmax");
   VDK_REQUIRE(d->batch > 0 && d->feat_dim > 0 && d->num_class > 1, "bad head shape");
   VDK_REQUIRE(d->label_smooth >= 0.f && d->label_smooth < 1.f, "label_smooth must be in [0,1)");
   h->kind = d->kind;
@@ -299,6 +343,12 @@ static int make_cfg(const vdk_head_desc* d, HeadCfg* h) {
   h->scale = d->scale;
   h->margin = d->margin;
   h->gamma = d->gamma;
+  h->mv_weight = d->mv_weight;
+  h->is_am = d->is_am;
+  if (d->kind == VDK_HEAD_MV_SOFTMAX) {  // MV_Softmax(is_am, margin, mv_weight, scale): cos/sin of ITS margin
+    h->cos_m = cosf(d->margin);
+    h->sin_m = sinf(d->margin);
+  }
   h->label_smooth = d->label_smooth;
   return VDK_OK;
 }

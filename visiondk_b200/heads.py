@@ -18,7 +18,7 @@ import torch.nn as nn
 
 from . import _lib
 
-HEAD_ARCFACE, HEAD_CIRCLELOSS = 0, 1
+HEAD_ARCFACE, HEAD_CIRCLELOSS, HEAD_MV_SOFTMAX = 0, 1, 2
 
 
 def _desc(head, batch: int, label_smooth: float) -> _lib.HeadDesc:
@@ -31,6 +31,8 @@ def _desc(head, batch: int, label_smooth: float) -> _lib.HeadDesc:
     d.margin = float(getattr(head, "margin", 0.0))
     d.gamma = float(getattr(head, "gamma", 1.0))
     d.label_smooth = float(label_smooth)
+    d.mv_weight = float(getattr(head, "mv_weight", 1.0))
+    d.is_am = int(bool(getattr(head, "is_am", False)))
     return d
 
 
@@ -147,13 +149,22 @@ class CircleLoss(_MarginHead):
         self.margin, self.gamma = margin, gamma
 
 
+class MV_Softmax(_MarginHead):
+    """models/faceX/head/mv_softmax.py:9-44 (same constructor; hard negatives re-weighted by mv_weight)."""
+    kind = HEAD_MV_SOFTMAX
+
+    def __init__(self, feat_dim, num_class, is_am, margin=0.35, mv_weight=1.12, scale=32):
+        super().__init__(feat_dim, num_class)
+        self.is_am, self.margin, self.mv_weight, self.scale = bool(is_am), margin, mv_weight, scale
+
+
 def margin_ce_loss(head: _MarginHead, feats: torch.Tensor, labels: torch.Tensor, label_smooth: float = 0.0) -> torch.Tensor:
     """Fused criterion(head(feats, labels), labels) with criterion = CrossEntropyLoss(label_smoothing)."""
     return _HeadCE.apply(feats, head.weight, labels, head, float(label_smooth))
 
 
 class HeadFactory:
-    """models/faceX/head/head_def.py:7-56 (arcface and circleloss are built; magface / mv-softmax are next, §8f)."""
+    """models/faceX/head/head_def.py:7-56 (arcface, circleloss and mv-softmax are built)."""
 
     def __init__(self, head_config: dict):
         for k, v in head_config.items():
@@ -165,4 +176,7 @@ class HeadFactory:
             return ArcFace(p["feat_dim"], p["num_class"], p["margin_arc"], p["margin_am"], p["scale"])
         if self.head_type == "circleloss":
             return CircleLoss(p["feat_dim"], p["num_class"], p["margin"], p["gamma"])
-        raise NotImplementedError(f"head '{self.head_type}': only arcface and circleloss are built for B200 so far")
+        if self.head_type == "mv-softmax":
+            return MV_Softmax(p["feat_dim"], p["num_class"], p["is_am"], p["margin"], p["mv_weight"], p["scale"])
+        raise NotImplementedError(f"head '{self.head_type}': arcface, circleloss and mv-softmax are built for B200; magface returns "
+                                  f"a (logits, loss) tuple the reference's own train loop cannot consume (magface.py:47 vs train.py:196)")
