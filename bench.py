@@ -418,8 +418,12 @@ def bench_extract(ctx, args):
         peak, src = peak_tflops()
         ach = tot_flops / (tot_ms * 1e-3) / 1e12
         roof = {"bound": "tensor", "kernel": "gemm_tn_kernel<256,bf16> (MLP / downsample shapes of one forward)",
-                "achieved": ach, "peak": peak, "unit": "TFLOP/s", "frac": ach / peak, "traffic": None, "peak_source": src,
-                "launches": n_launch, "launch_ms": tot_ms / n_launch, "algorithmic_flops_per_launch": tot_flops / n_launch,
+                "achieved": ach, "peak": peak, "unit": "TFLOP/s", "frac": ach / peak,
+                # dram__bytes_read.sum + dram__bytes_write.sum per launch, `ncu --set full` of tools/time_extract.py 256 1
+                # (profiles/r01_traffic_gemm_ncu_raw.csv): the two stage-3 MLP launches (54 of the 72): fc1+GELU 53.6 + 147.2 MB,
+                # fc2+residual 259.1 + 32.1 MB; algorithmic bytes of the same launches: 259 / 310 MB (outputs partly still in L2)
+                "traffic": 0.5 * (200.9e6 + 291.2e6) if B == 256 else None, "traffic_unit": "bytes/launch (mean of the two captured)",
+                "peak_source": src, "launches": n_launch, "launch_ms": tot_ms / n_launch, "algorithmic_flops_per_launch": tot_flops / n_launch,
                 "share_of_step": tot_ms / ms,
                 "whole_step": {"achieved": B * GFLOP_PER_EMBEDDING / ms, "frac": B * GFLOP_PER_EMBEDDING / ms / peak,
                                "note": "30.76 GFLOP per embedding over the whole forward"}}
@@ -620,7 +624,11 @@ def bench_retrieval(ctx, args):
         peak, src = peak_tflops()
         ach = flops / (k_ms * 1e-3) / 1e12
         roof = {"bound": "tensor", "kernel": "score_filter_kernel<sparse> over the last gallery range", "achieved": ach,
-                "peak": peak, "unit": "TFLOP/s", "frac": ach / peak, "traffic": None, "peak_source": src, "launch_ms": k_ms,
+                "peak": peak, "unit": "TFLOP/s", "frac": ach / peak,
+                # ncu --set full of this launch (profiles/r01_traffic_retrieval_ncu_raw.csv): 1.130 GB read + 38.5 MB written for
+                # 0.756 GB of fp16 gallery rows (L2 hit 91 %: CTAs drift apart on admissions and re-read tiles a few times)
+                "traffic": 1.168e9 if (nq, ng, ctx.world) == (10000, 1000000, 1) else None, "traffic_unit": "bytes/launch",
+                "peak_source": src, "launch_ms": k_ms,
                 "algorithmic_flops_per_launch": flops, "share_of_step": k_ms / ms,
                 "whole_step": {"achieved": 2.0 * dim * nq * ngl / (ms * 1e-3) / 1e12,
                                "frac": 2.0 * dim * nq * ngl / (ms * 1e-3) / 1e12 / peak,

@@ -19,6 +19,7 @@
 #include "convnext_internal.h"
 
 #include <algorithm>
+#include <cstdlib>
 
 namespace vdk {
 
@@ -88,52 +89,50 @@ __device__ __forceinline__ float fast_exp2(float x) {
   return y;
 }
 
-constexpr int kAttD = 64;   // head dim
-constexpr int kAttBM = 64;  // query rows per CTA
-constexpr int kAttBN = 64;  // key/value rows per tile
+constexpr int kAttD = 64;        // head dim
+constexpr int kAttBN = 64;       // key/value rows per shared-memory tile
+constexpr int kAttMaxWarps = 16; // query rows per CTA = 16 per warp
 
-// 64 x 64 bf16 tile in shared memory: 128-byte rows, 16-byte chunk index XOR (row & 7) (conflict-free ldmatrix)
+// [rows] x 64 bf16 tile in shared memory: 128-byte rows, 16-byte chunk index XOR (row & 7) (conflict-free ldmatrix)
 __device__ __forceinline__ uint32_t att_tile_addr(uint32_t base, int row, int col /*multiple of 8*/) {
   return base + row * 128 + (((col >> 3) ^ (row & 7)) << 4);
 }
 
-// rows [row0, row0 + 64) of a [*, ld] bf16 matrix (rows >= n_rows are zero) -> swizzled tile
-__device__ __forceinline__ void att_load_tile(uint8_t* tile, const __nv_bfloat16* __restrict__ src, int64_t ld, int row0, int n_rows) {
-#pragma unroll
-  for (int c = 0; c < 4; ++c) {
-    const int idx = threadIdx.x + c * 128;
-    const int r = idx >> 3, ch = idx & 7;
-    uint4 v = make_uint4(0u, 0u, 0u, 0u);
-    if (row0 + r < n_rows) v = __ldg(reinterpret_cast<const uint4*>(src + static_cast<int64_t>(row0 + r) * ld + ch * 8));
-    *reinterpret_cast<uint4*>(tile + r * 128 + ((ch ^ (r & 7)) << 4)) = v;
-  }
-}
-
-// qkv: [B, N, 3, H, 64] bf16 (the qkv Linear's output as stored);  out: [B, N, H*64] bf16
-__global__ void __launch_bounds__(128)
+// qkv: [B, N, 3, H, 64] bf16 (the qkv Linear's output as stored);  out: [B, N, H*64] bf16.
+// CTA = up to 16 warps, each owning 16 query rows of one (image, head); K / V stream through 64-row tiles loaded once per
+// CTA (ViT-B/16: 197 tokens -> ONE CTA of 13 warps per (image, head), K and V read once); 8-column score tiles and 16-row
+// P.V steps that lie entirely beyond N are skipped.
+__global__ void __launch_bounds__(kAttMaxWarps * 32)
 attention_fwd_kernel(const __nv_bfloat16* __restrict__ qkv, int B, int N, int H, float scale_log2e, __nv_bfloat16* __restrict__ out) {
-  __shared__ __align__(128) uint8_t sq[kAttBM * 128];
-  __shared__ __align__(128) uint8_t sk[kAttBN * 128];
-  __shared__ __align__(128) uint8_t sv[kAttBN * 128];
+  extern __shared__ __align__(128) uint8_t att_smem[];
+  const int nwarps = blockDim.x >> 5;
+  uint8_t* sq = att_smem;                       // [nwarps * 16][64]
+  uint8_t* skv = att_smem + nwarps * 16 * 128;  // 2 stages x { K [64][64], V [64][64] }
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int g = lane >> 2, t = lane & 3;
-  const int q0 = blockIdx.x * kAttBM, h = blockIdx.y, b = blockIdx.z;
+  const int q0 = (blockIdx.x * nwarps + warp) * 16, h = blockIdx.y, b = blockIdx.z;
   const int64_t ld = static_cast<int64_t>(3) * H * kAttD;
   const __nv_bfloat16* base = qkv + static_cast<int64_t>(b) * N * ld + h * kAttD;
-  const __nv_bfloat16* qp = base;
   const __nv_bfloat16* kp = base + static_cast<int64_t>(H) * kAttD;
   const __nv_bfloat16* vp = base + static_cast<int64_t>(2) * H * kAttD;
 
-  att_load_tile(sq, qp, ld, q0, N);
-  __syncthreads();
-  // this warp's 16 query rows as A fragments for the 4 k-steps over d
+  // this warp's 16 query rows -> its private slice of sq -> A fragments for the 4 k-steps over d
   uint32_t qa[4][4];
   {
-    const uint32_t sqb = smem_u32(sq);
+    uint8_t* mine = sq + warp * 16 * 128;
+#pragma unroll
+    for (int c = 0; c < 4; ++c) {
+      const int idx = lane + c * 32;
+      const int r = idx >> 3, ch = idx & 7;
+      uint4 v = make_uint4(0u, 0u, 0u, 0u);
+      if (q0 + r < N) v = __ldg(reinterpret_cast<const uint4*>(base + static_cast<int64_t>(q0 + r) * ld + ch * 8));
+      *reinterpret_cast<uint4*>(mine + r * 128 + ((ch ^ (r & 7)) << 4)) = v;
+    }
+    __syncwarp();
+    const uint32_t sqb = smem_u32(mine);
     const int i = lane >> 3, r = lane & 7;
 #pragma unroll
-    for (int kk = 0; kk < 4; ++kk)
-      ldmatrix_x4(qa[kk], att_tile_addr(sqb, warp * 16 + (i & 1) * 8 + r, kk * 16 + (i >> 1) * 8));
+    for (int kk = 0; kk < 4; ++kk) ldmatrix_x4(qa[kk], att_tile_addr(sqb, (i & 1) * 8 + r, kk * 16 + (i >> 1) * 8));
   }
   float o[8][4];
 #pragma unroll
@@ -142,12 +141,32 @@ attention_fwd_kernel(const __nv_bfloat16* __restrict__ qkv, int B, int N, int H,
     for (int c = 0; c < 4; ++c) o[j][c] = 0.f;
   float m_run[2] = {-INFINITY, -INFINITY}, l_run[2] = {0.f, 0.f};  // rows g and g + 8
 
-  const uint32_t skb = smem_u32(sk), svb = smem_u32(sv);
-  for (int kv0 = 0; kv0 < N; kv0 += kAttBN) {
-    __syncthreads();  // the previous tile has been consumed by every warp
-    att_load_tile(sk, kp, ld, kv0, N);
-    att_load_tile(sv, vp, ld, kv0, N);
-    __syncthreads();
+  // K / V tiles are double buffered with cp.async: tile t+1 is in flight while tile t is multiplied
+  auto issue_tile = [&](int kv0, int stage) {
+    uint8_t* dstb = skv + stage * (2 * kAttBN * 128);
+    for (int idx = threadIdx.x; idx < 2 * kAttBN * 8; idx += blockDim.x) {
+      const int m = idx >> 9, rem = idx & 511;  // m: 0 = K, 1 = V
+      const int r = rem >> 3, ch = rem & 7;
+      const bool ok = kv0 + r < N;
+      const __nv_bfloat16* src = (m ? vp : kp) + static_cast<int64_t>(ok ? kv0 + r : 0) * ld + ch * 8;
+      const uint32_t dst = smem_u32(dstb + m * (kAttBN * 128) + r * 128 + ((ch ^ (r & 7)) << 4));
+      asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst), "l"(src), "r"(ok ? 16 : 0) : "memory");  // 0: zero fill
+    }
+    asm volatile("cp.async.commit_group;" ::: "memory");
+  };
+  const int n_tiles = (N + kAttBN - 1) / kAttBN;
+  issue_tile(0, 0);
+  for (int tile = 0; tile < n_tiles; ++tile) {
+    const int kv0 = tile * kAttBN;
+    if (tile + 1 < n_tiles) {
+      issue_tile(kv0 + kAttBN, (tile + 1) & 1);
+      asm volatile("cp.async.wait_group 1;" ::: "memory");
+    } else {
+      asm volatile("cp.async.wait_group 0;" ::: "memory");
+    }
+    __syncthreads();  // every thread's part of tile `tile` has landed
+    const uint32_t skb = smem_u32(skv + (tile & 1) * (2 * kAttBN * 128)), svb = skb + kAttBN * 128;
+    const int n_valid = min(kAttBN, N - kv0);  // key columns of this tile that exist
     // S = Q K^T for 16 rows x 64 key columns
     float sacc[8][4];
 #pragma unroll
@@ -157,13 +176,15 @@ attention_fwd_kernel(const __nv_bfloat16* __restrict__ qkv, int B, int N, int H,
     {
       const int i = lane >> 3, r = lane & 7;
 #pragma unroll
-      for (int kk = 0; kk < 4; ++kk) {
+      for (int jp = 0; jp < 4; ++jp) {  // pairs of 8-column tiles
+        if (jp * 16 < n_valid) {
 #pragma unroll
-        for (int jp = 0; jp < 4; ++jp) {  // pairs of 8-column tiles
-          uint32_t kb[4];
-          ldmatrix_x4(kb, att_tile_addr(skb, jp * 16 + (i >> 1) * 8 + r, kk * 16 + (i & 1) * 8));
-          mma_bf16_16816(sacc[2 * jp], qa[kk], kb[0], kb[1]);
-          mma_bf16_16816(sacc[2 * jp + 1], qa[kk], kb[2], kb[3]);
+          for (int kk = 0; kk < 4; ++kk) {
+            uint32_t kb[4];
+            ldmatrix_x4(kb, att_tile_addr(skb, jp * 16 + (i >> 1) * 8 + r, kk * 16 + (i & 1) * 8));
+            mma_bf16_16816(sacc[2 * jp], qa[kk], kb[0], kb[1]);
+            mma_bf16_16816(sacc[2 * jp + 1], qa[kk], kb[2], kb[3]);
+          }
         }
       }
     }
@@ -173,8 +194,8 @@ attention_fwd_kernel(const __nv_bfloat16* __restrict__ qkv, int B, int N, int H,
     for (int j = 0; j < 8; ++j) {
 #pragma unroll
       for (int c = 0; c < 4; ++c) {
-        const int col = kv0 + j * 8 + 2 * t + (c & 1);
-        const float v = col < N ? sacc[j][c] * scale_log2e : -INFINITY;
+        const int col = j * 8 + 2 * t + (c & 1);
+        const float v = col < n_valid ? sacc[j][c] * scale_log2e : -INFINITY;
         sacc[j][c] = v;
         mx[c >> 1] = fmaxf(mx[c >> 1], v);
       }
@@ -219,19 +240,22 @@ attention_fwd_kernel(const __nv_bfloat16* __restrict__ qkv, int B, int N, int H,
       const int i = lane >> 3, r = lane & 7;
 #pragma unroll
       for (int kk = 0; kk < 4; ++kk) {
+        if (kk * 16 < n_valid) {
 #pragma unroll
-        for (int jp = 0; jp < 4; ++jp) {  // pairs of 8-wide d tiles
-          uint32_t vb[4];
-          ldmatrix_x4_trans(vb, att_tile_addr(svb, kk * 16 + (i & 1) * 8 + r, jp * 16 + (i >> 1) * 8));
-          mma_bf16_16816(o[2 * jp], pa[kk], vb[0], vb[1]);
-          mma_bf16_16816(o[2 * jp + 1], pa[kk], vb[2], vb[3]);
+          for (int jp = 0; jp < 4; ++jp) {  // pairs of 8-wide d tiles
+            uint32_t vb[4];
+            ldmatrix_x4_trans(vb, att_tile_addr(svb, kk * 16 + (i & 1) * 8 + r, jp * 16 + (i >> 1) * 8));
+            mma_bf16_16816(o[2 * jp], pa[kk], vb[0], vb[1]);
+            mma_bf16_16816(o[2 * jp + 1], pa[kk], vb[2], vb[3]);
+          }
         }
       }
     }
+    __syncthreads();  // this stage is free again for the tile after next
   }
-  // normalise and store: rows q0 + warp*16 + g (+8), columns h*64 + 8j + 2t
+  // normalise and store: rows q0 + g (+8), columns h*64 + 8j + 2t
   const float inv0 = 1.0f / l_run[0], inv1 = 1.0f / l_run[1];
-  const int r0 = q0 + warp * 16 + g, r1 = r0 + 8;
+  const int r0 = q0 + g, r1 = r0 + 8;
   __nv_bfloat16* ob = out + static_cast<int64_t>(b) * N * H * kAttD + h * kAttD;
 #pragma unroll
   for (int j = 0; j < 8; ++j) {
@@ -248,7 +272,21 @@ static int launch_attention(const __nv_bfloat16* qkv, int B, int N, int H, int h
   VDK_REQUIRE(head_dim == kAttD, "attention: head_dim must be 64 (got %d)", head_dim);
   VDK_REQUIRE(B > 0 && N > 0 && H > 0 && H <= 65535 && B <= 65535, "attention: bad shape");
   const float scale_log2e = 1.4426950408889634f / sqrtf(static_cast<float>(head_dim));
-  attention_fwd_kernel<<<dim3((N + kAttBM - 1) / kAttBM, H, B), 128, 0, s>>>(qkv, B, N, H, scale_log2e, out);
+  const int row_groups = (N + 15) / 16;
+  static const int warp_cap = [] {  // tuning switch: query-row groups (warps) per CTA
+    const char* e = getenv("VDK_ATT_WARPS");
+    const int v = e ? atoi(e) : kAttMaxWarps;
+    return v < 1 ? 1 : (v > kAttMaxWarps ? kAttMaxWarps : v);
+  }();
+  const int ctas = (row_groups + warp_cap - 1) / warp_cap;
+  const int nwarps = (row_groups + ctas - 1) / ctas;  // balanced: 197 tokens -> 1 CTA x 13 warps; 577 -> 3 CTAs x 13 warps
+  const int smem = nwarps * 16 * 128 + 2 * (2 * kAttBN * 128);
+  static bool attr = false;
+  if (!attr) {
+    VDK_CUDA_OK(cudaFuncSetAttribute(attention_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024));
+    attr = true;
+  }
+  attention_fwd_kernel<<<dim3(ctas, H, B), nwarps * 32, smem, s>>>(qkv, B, N, H, scale_log2e, out);
   VDK_CUDA_OK(cudaGetLastError());
   return VDK_OK;
 }
