@@ -268,6 +268,39 @@ int vdk_vit_forward(const vdk_vit_net* net, const float* images, int batch, int 
  * out bf16 [batch, tokens, heads*64]  (timm Attention.forward, scores never written to memory). */
 int vdk_attention_fwd(const void* qkv, int batch, int tokens, int heads, int head_dim, void* out, void* stream);
 
+/* ---- ViT training forward / backward (BASELINE config 3: ViT-B/16 + CircleLoss) ----------------------------------- */
+/* fp32 tensors in timm layouts (parameters, or their gradients): what TimmWrapper('vit_*').train() holds. */
+typedef struct vdk_vit_block_tensors {
+  float* ln1_w; float* ln1_b; float* qkv_w; float* qkv_b; float* proj_w; float* proj_b;
+  float* ln2_w; float* ln2_b; float* fc1_w; float* fc1_b; float* fc2_w; float* fc2_b;
+} vdk_vit_block_tensors;
+typedef struct vdk_vit_tensors {
+  float* patch_w;   /* [dim, 3, P, P] */
+  float* patch_b; float* cls_token; float* pos_embed;
+  vdk_vit_block_tensors blocks[VDK_VIT_MAX_BLOCKS];
+  float* norm_w; float* norm_b; float* neck_ln_w; float* neck_ln_b;
+  float* lin_w;     /* output_layer.2.weight [feat_dim, tokens*dim] */
+  float* lin_b;
+  float* bn1_w; float* bn1_b; float* bn1_running_mean; float* bn1_running_var;  /* output_layer.3 */
+} vdk_vit_tensors;
+/* fp32 masters -> the bf16 GEMM weights of `net` (patch_w, qkv/proj/fc1/fc2, neck_w UNfolded: BatchNorm1d runs on batch
+ * statistics in train mode).  Vector pointers of `net` are set by the caller (they may alias the masters). */
+int vdk_vit_pack(const vdk_vit_tensors* params, vdk_vit_net* net, void* stream);
+size_t vdk_vit_train_workspace_bytes(const vdk_vit_net* net, int batch);
+/* Train-mode forward of TimmWrapper('vit_*') (timm_wrapper.py:51-54; neck :42-47 with BatchNorm1d batch statistics,
+ * running stats updated): images fp32 NCHW -> out_feats fp32 [batch, feat_dim]; activations saved in `workspace`.
+ * Needs 3*patch*patch % 8 == 0 and at most 208 tokens (the attention backward keeps one head's P in shared memory). */
+int vdk_vit_train_forward(const vdk_vit_net* net, const vdk_vit_tensors* params, const float* images, int batch, float bn_momentum,
+                          float* out_feats, void* workspace, size_t workspace_bytes, void* stream);
+/* d_feats fp32 [batch, feat_dim] -> gradients ACCUMULATED (+=) into `grads`. */
+int vdk_vit_train_backward(const vdk_vit_net* net, const vdk_vit_tensors* params, const vdk_vit_tensors* grads, const float* d_feats,
+                           int batch, void* workspace, size_t workspace_bytes, void* stream);
+/* unit-test surface of the attention pair: forward that also saves the log2-domain log-sum-exp [batch, heads, tokens], and
+ * the backward dqkv = d(attention)/d(qkv) for d_out (both [batch, tokens, heads*64] bf16). */
+int vdk_attention_fwd_lse(const void* qkv, int batch, int tokens, int heads, int head_dim, void* out, float* lse2, void* stream);
+int vdk_attention_bwd(const void* qkv, const void* out, const void* d_out, const float* lse2, int batch, int tokens, int heads,
+                      int head_dim, void* dqkv, void* stream);
+
 /* ---- margin-softmax heads + cross-entropy --------------------------------------------------- */
 /* Replaces ArcFace.forward (models/faceX/head/arcface.py:20-36), CircleLoss.forward (models/faceX/head/
  * circleloss.py:21-43), nn.CrossEntropyLoss(label_smoothing) (models/losses/loss.py:71-73) and their autograd
@@ -384,7 +417,7 @@ int vdk_ip_exact_pairs(const float* q32, const float* g32, int dim, const int64_
                        float* out, void* stream);
 
 /* sizeof() of the by-pointer structs, in this order: vdk_gemm_desc, vdk_topk_plan, vdk_head_desc, vdk_convnext_net,
- * vdk_convnext_tensors, vdk_vit_net.  Writes min(n, count) entries, returns the count: a binding checks its mirrors. */
+ * vdk_convnext_tensors, vdk_vit_net, vdk_vit_tensors.  Writes min(n, count) entries, returns the count: a binding checks its mirrors. */
 int vdk_struct_sizes(size_t* out, int n);
 
 #ifdef __cplusplus

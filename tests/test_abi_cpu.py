@@ -76,11 +76,11 @@ def test_ctypes_mirrors_have_the_c_struct_sizes():
     import ctypes as C
     from visiondk_b200 import _lib
     from visiondk_b200.backbone import ConvNeXtNetC, ConvNeXtTensorsC
-    from visiondk_b200.vit import VitNetC
+    from visiondk_b200.vit import VitNetC, VitTensorsC
     lib = _lib.load()
     out = (C.c_size_t * 8)()
     n = lib.vdk_struct_sizes(out, 8)
-    mirrors = [_lib.GemmDesc, _lib.TopkPlan, _lib.HeadDesc, ConvNeXtNetC, ConvNeXtTensorsC, VitNetC]
+    mirrors = [_lib.GemmDesc, _lib.TopkPlan, _lib.HeadDesc, ConvNeXtNetC, ConvNeXtTensorsC, VitNetC, VitTensorsC]
     assert n == len(mirrors)
     for i, m in enumerate(mirrors):
         assert C.sizeof(m) == out[i], (m.__name__, C.sizeof(m), out[i])

@@ -99,7 +99,7 @@ int vdk_version(void) { return 100; }  // 0.1.0
 // sizeof() of every by-pointer struct of the ABI, in header order: lets a binding (ctypes mirror) check its layout
 int vdk_struct_sizes(size_t* out, int n) {
   const size_t sizes[] = {sizeof(vdk_gemm_desc),        sizeof(vdk_topk_plan),  sizeof(vdk_head_desc), sizeof(vdk_convnext_net),
-                          sizeof(vdk_convnext_tensors), sizeof(vdk_vit_net)};
+                          sizeof(vdk_convnext_tensors), sizeof(vdk_vit_net),   sizeof(vdk_vit_tensors)};
   const int k = static_cast<int>(sizeof(sizes) / sizeof(sizes[0]));
   for (int i = 0; i < n && i < k; ++i) out[i] = sizes[i];
   return k;

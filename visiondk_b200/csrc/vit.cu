@@ -17,6 +17,7 @@
 #include "vdk_host.h"
 #include "vdk_ptx.cuh"
 #include "convnext_internal.h"
+#include "train_gemm.h"
 
 #include <algorithm>
 #include <cstdlib>
@@ -103,7 +104,8 @@ __device__ __forceinline__ uint32_t att_tile_addr(uint32_t base, int row, int co
 // CTA (ViT-B/16: 197 tokens -> ONE CTA of 13 warps per (image, head), K and V read once); 8-column score tiles and 16-row
 // P.V steps that lie entirely beyond N are skipped.
 __global__ void __launch_bounds__(kAttMaxWarps * 32)
-attention_fwd_kernel(const __nv_bfloat16* __restrict__ qkv, int B, int N, int H, float scale_log2e, __nv_bfloat16* __restrict__ out) {
+attention_fwd_kernel(const __nv_bfloat16* __restrict__ qkv, int B, int N, int H, float scale_log2e, __nv_bfloat16* __restrict__ out,
+                     float* __restrict__ lse2 /*[B,H,N] log2-domain log-sum-exp per row, or null*/) {
   extern __shared__ __align__(128) uint8_t att_smem[];
   const int nwarps = blockDim.x >> 5;
   uint8_t* sq = att_smem;                       // [nwarps * 16][64]
@@ -256,6 +258,11 @@ attention_fwd_kernel(const __nv_bfloat16* __restrict__ qkv, int B, int N, int H,
   // normalise and store: rows q0 + g (+8), columns h*64 + 8j + 2t
   const float inv0 = 1.0f / l_run[0], inv1 = 1.0f / l_run[1];
   const int r0 = q0 + g, r1 = r0 + 8;
+  if (lse2 != nullptr && t == 0) {  // saved for the backward: P = exp2(s * scale_log2e - lse2)
+    float* lp = lse2 + (static_cast<int64_t>(b) * H + h) * N;
+    if (r0 < N) lp[r0] = m_run[0] + log2f(l_run[0]);
+    if (r1 < N) lp[r1] = m_run[1] + log2f(l_run[1]);
+  }
   __nv_bfloat16* ob = out + static_cast<int64_t>(b) * N * H * kAttD + h * kAttD;
 #pragma unroll
   for (int j = 0; j < 8; ++j) {
@@ -268,14 +275,15 @@ attention_fwd_kernel(const __nv_bfloat16* __restrict__ qkv, int B, int N, int H,
   }
 }
 
-static int launch_attention(const __nv_bfloat16* qkv, int B, int N, int H, int head_dim, __nv_bfloat16* out, cudaStream_t s) {
+static int launch_attention(const __nv_bfloat16* qkv, int B, int N, int H, int head_dim, __nv_bfloat16* out, float* lse2,
+                            cudaStream_t s) {
   VDK_REQUIRE(head_dim == kAttD, "attention: head_dim must be 64 (got %d)", head_dim);
   VDK_REQUIRE(B > 0 && N > 0 && H > 0 && H <= 65535 && B <= 65535, "attention: bad shape");
   const float scale_log2e = 1.4426950408889634f / sqrtf(static_cast<float>(head_dim));
   const int row_groups = (N + 15) / 16;
   static const int warp_cap = [] {  // tuning switch: query-row groups (warps) per CTA
     const char* e = getenv("VDK_ATT_WARPS");
-    const int v = e ? atoi(e) : kAttMaxWarps;
+    const int v = e ? atoi(e) : 8;  // measured on ViT-B/16 batch 256: 16 -> 13.06 ms, 8 -> 12.68 ms, 4 -> 12.87 ms per forward
     return v < 1 ? 1 : (v > kAttMaxWarps ? kAttMaxWarps : v);
   }();
   const int ctas = (row_groups + warp_cap - 1) / warp_cap;
@@ -286,7 +294,225 @@ static int launch_attention(const __nv_bfloat16* qkv, int B, int N, int H, int h
     VDK_CUDA_OK(cudaFuncSetAttribute(attention_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024));
     attr = true;
   }
-  attention_fwd_kernel<<<dim3(ctas, H, B), nwarps * 32, smem, s>>>(qkv, B, N, H, scale_log2e, out);
+  attention_fwd_kernel<<<dim3(ctas, H, B), nwarps * 32, smem, s>>>(qkv, B, N, H, scale_log2e, out, lse2);
+  VDK_CUDA_OK(cudaGetLastError());
+  return VDK_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// attention backward for N <= 208 tokens (ViT-*/16 at 224^2: 197): one CTA per (image, head) keeps Q, K, V, dO and the
+// whole probability matrix in shared memory and runs the five products of the backward as in-CTA GEMMs on mma.sync:
+//   P = exp2(scale' Q K^T - lse2)                    (recomputed from the saved log-sum-exp)
+//   dV = P^T dO;  dP = dO V^T;  dS = scale P (dP - D),  D_i = sum_d dO_id O_id;  dQ = dS K;  dK = dS^T Q
+// Warp w owns rows 16w .. 16w+15 of whichever matrix is being produced.
+// ------------------------------------------------------------------------------------------------
+constexpr int kAttBwdMaxRows = 208;
+constexpr int kAttPStride = 432;  // bytes per row of P (208 bf16 = 416, padded so that 8 rows hit 8 distinct 16-byte bank groups)
+
+__device__ __forceinline__ uint32_t att_p_addr(uint32_t base, int row, int col /*multiple of 8*/) {
+  return base + row * kAttPStride + col * 2;
+}
+
+__global__ void __launch_bounds__(13 * 32)
+attention_bwd_kernel(const __nv_bfloat16* __restrict__ qkv, const __nv_bfloat16* __restrict__ o, const __nv_bfloat16* __restrict__ d_o,
+                     const float* __restrict__ lse2, int B, int N, int H, float scale, float scale_log2e,
+                     __nv_bfloat16* __restrict__ dqkv) {
+  extern __shared__ __align__(128) uint8_t att_smem[];
+  const int nwarps = blockDim.x >> 5;  // = ceil(N / 16)
+  const int Np = nwarps * 16;
+  uint8_t* sq = att_smem;
+  uint8_t* sk = sq + Np * 128;
+  uint8_t* sv = sk + Np * 128;
+  uint8_t* sdo = sv + Np * 128;
+  uint8_t* sp = sdo + Np * 128;                                   // [Np][kAttPStride]
+  float* sD = reinterpret_cast<float*>(sp + Np * kAttPStride);    // [Np]
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int g = lane >> 2, t = lane & 3;
+  const int h = blockIdx.x, b = blockIdx.y;
+  const int64_t ld = static_cast<int64_t>(3) * H * kAttD, ldo = static_cast<int64_t>(H) * kAttD;
+  const __nv_bfloat16* qb = qkv + static_cast<int64_t>(b) * N * ld + h * kAttD;
+  const __nv_bfloat16* ob = o + static_cast<int64_t>(b) * N * ldo + h * kAttD;
+  const __nv_bfloat16* dob = d_o + static_cast<int64_t>(b) * N * ldo + h * kAttD;
+  __nv_bfloat16* dqb = dqkv + static_cast<int64_t>(b) * N * ld + h * kAttD;
+
+  // ---- stage Q, K, V, dO (rows >= N zero) ----
+  for (int idx = threadIdx.x; idx < 4 * Np * 8; idx += blockDim.x) {
+    const int m = idx / (Np * 8), rem = idx - m * (Np * 8);
+    const int r = rem >> 3, ch = rem & 7;
+    uint4 v = make_uint4(0u, 0u, 0u, 0u);
+    if (r < N) {
+      const __nv_bfloat16* src = m < 3 ? qb + static_cast<int64_t>(m) * H * kAttD + static_cast<int64_t>(r) * ld
+                                       : dob + static_cast<int64_t>(r) * ldo;
+      v = __ldg(reinterpret_cast<const uint4*>(src + ch * 8));
+    }
+    *reinterpret_cast<uint4*>(sq + m * (Np * 128) + r * 128 + ((ch ^ (r & 7)) << 4)) = v;
+  }
+  // D_i = sum_d dO_id O_id: 2 lanes per row (32 columns each)
+  {
+    const int r = warp * 16 + (lane >> 1), half = lane & 1;
+    float acc = 0.f;
+    if (r < N) {
+#pragma unroll
+      for (int c = 0; c < 4; ++c) {
+        const uint4 a = __ldg(reinterpret_cast<const uint4*>(ob + static_cast<int64_t>(r) * ldo + half * 32 + c * 8));
+        const uint4 d = __ldg(reinterpret_cast<const uint4*>(dob + static_cast<int64_t>(r) * ldo + half * 32 + c * 8));
+        const uint32_t aw[4] = {a.x, a.y, a.z, a.w}, dw[4] = {d.x, d.y, d.z, d.w};
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+          const float2 fa = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&aw[k]));
+          const float2 fd = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&dw[k]));
+          acc = fmaf(fa.x, fd.x, fmaf(fa.y, fd.y, acc));
+        }
+      }
+    }
+    acc += __shfl_xor_sync(0xffffffffu, acc, 1);
+    if (half == 0) sD[r] = acc;
+  }
+  __syncthreads();
+  const uint32_t sqb = smem_u32(sq), skb = smem_u32(sk), svb = smem_u32(sv), sdob = smem_u32(sdo), spb = smem_u32(sp);
+  const int li = lane >> 3, lr = lane & 7;
+  const int row0 = warp * 16;  // this warp's rows
+  const float* lp = lse2 + (static_cast<int64_t>(b) * H + h) * N;
+  const float l0 = row0 + g < N ? lp[row0 + g] : 0.f, l1 = row0 + g + 8 < N ? lp[row0 + g + 8] : 0.f;
+
+  // ---- phase 1: P rows of this warp = exp2(scale' Q K^T - lse2), stored bf16 ----
+  {
+    uint32_t qa[4][4];
+#pragma unroll
+    for (int kk = 0; kk < 4; ++kk) ldmatrix_x4(qa[kk], att_tile_addr(sqb, row0 + (li & 1) * 8 + lr, kk * 16 + (li >> 1) * 8));
+    for (int c0 = 0; c0 < Np; c0 += 16) {  // two 8-column tiles at a time
+      float s0[4] = {0.f, 0.f, 0.f, 0.f}, s1[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+      for (int kk = 0; kk < 4; ++kk) {
+        uint32_t kb[4];
+        ldmatrix_x4(kb, att_tile_addr(skb, c0 + (li >> 1) * 8 + lr, kk * 16 + (li & 1) * 8));
+        mma_bf16_16816(s0, qa[kk], kb[0], kb[1]);
+        mma_bf16_16816(s1, qa[kk], kb[2], kb[3]);
+      }
+#pragma unroll
+      for (int half = 0; half < 2; ++half) {
+        const float* sv4 = half ? s1 : s0;
+        const int col = c0 + half * 8 + 2 * t;
+        const bool ok0 = col < N, ok1 = col + 1 < N;
+        const float p00 = ok0 && row0 + g < N ? fast_exp2(sv4[0] * scale_log2e - l0) : 0.f;
+        const float p01 = ok1 && row0 + g < N ? fast_exp2(sv4[1] * scale_log2e - l0) : 0.f;
+        const float p10 = ok0 && row0 + g + 8 < N ? fast_exp2(sv4[2] * scale_log2e - l1) : 0.f;
+        const float p11 = ok1 && row0 + g + 8 < N ? fast_exp2(sv4[3] * scale_log2e - l1) : 0.f;
+        *reinterpret_cast<__nv_bfloat162*>(sp + (row0 + g) * kAttPStride + col * 2) = __floats2bfloat162_rn(p00, p01);
+        *reinterpret_cast<__nv_bfloat162*>(sp + (row0 + g + 8) * kAttPStride + col * 2) = __floats2bfloat162_rn(p10, p11);
+      }
+    }
+  }
+  __syncthreads();  // the whole P is in shared memory
+
+  // ---- phase 2: dV rows (key index) of this warp = sum_i P[i][kv] dO[i][:] ----
+  {
+    float acc[8][4];
+#pragma unroll
+    for (int j = 0; j < 8; ++j)
+#pragma unroll
+      for (int c = 0; c < 4; ++c) acc[j][c] = 0.f;
+    for (int i0 = 0; i0 < Np; i0 += 16) {
+      uint32_t a[4];  // A = P^T: rows m = kv (this warp), cols k = i
+      ldmatrix_x4_trans(a, att_p_addr(spb, i0 + (li >> 1) * 8 + lr, row0 + (li & 1) * 8));
+#pragma unroll
+      for (int jp = 0; jp < 4; ++jp) {
+        uint32_t bb[4];
+        ldmatrix_x4_trans(bb, att_tile_addr(sdob, i0 + (li & 1) * 8 + lr, jp * 16 + (li >> 1) * 8));
+        mma_bf16_16816(acc[2 * jp], a, bb[0], bb[1]);
+        mma_bf16_16816(acc[2 * jp + 1], a, bb[2], bb[3]);
+      }
+    }
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      if (row0 + g < N)
+        *reinterpret_cast<__nv_bfloat162*>(dqb + static_cast<int64_t>(2) * H * kAttD + static_cast<int64_t>(row0 + g) * ld + j * 8 + 2 * t) =
+            __floats2bfloat162_rn(acc[j][0], acc[j][1]);
+      if (row0 + g + 8 < N)
+        *reinterpret_cast<__nv_bfloat162*>(dqb + static_cast<int64_t>(2) * H * kAttD + static_cast<int64_t>(row0 + g + 8) * ld + j * 8 + 2 * t) =
+            __floats2bfloat162_rn(acc[j][2], acc[j][3]);
+    }
+  }
+  __syncthreads();  // every warp has read P: it may now be overwritten by dS
+
+  // ---- phase 3: dS rows (query index) of this warp = scale * P * (dO V^T - D), in place over P ----
+  {
+    uint32_t da[4][4];
+#pragma unroll
+    for (int kk = 0; kk < 4; ++kk) ldmatrix_x4(da[kk], att_tile_addr(sdob, row0 + (li & 1) * 8 + lr, kk * 16 + (li >> 1) * 8));
+    const float d0 = sD[row0 + g], d1 = sD[row0 + g + 8];
+    for (int c0 = 0; c0 < Np; c0 += 16) {
+      float s0[4] = {0.f, 0.f, 0.f, 0.f}, s1[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+      for (int kk = 0; kk < 4; ++kk) {
+        uint32_t vb[4];
+        ldmatrix_x4(vb, att_tile_addr(svb, c0 + (li >> 1) * 8 + lr, kk * 16 + (li & 1) * 8));
+        mma_bf16_16816(s0, da[kk], vb[0], vb[1]);
+        mma_bf16_16816(s1, da[kk], vb[2], vb[3]);
+      }
+#pragma unroll
+      for (int half = 0; half < 2; ++half) {
+        const float* dp = half ? s1 : s0;
+        const int col = c0 + half * 8 + 2 * t;
+        __nv_bfloat162* p0 = reinterpret_cast<__nv_bfloat162*>(sp + (row0 + g) * kAttPStride + col * 2);
+        __nv_bfloat162* p1 = reinterpret_cast<__nv_bfloat162*>(sp + (row0 + g + 8) * kAttPStride + col * 2);
+        const float2 pa = __bfloat1622float2(*p0), pb = __bfloat1622float2(*p1);
+        *p0 = __floats2bfloat162_rn(scale * pa.x * (dp[0] - d0), scale * pa.y * (dp[1] - d0));
+        *p1 = __floats2bfloat162_rn(scale * pb.x * (dp[2] - d1), scale * pb.y * (dp[3] - d1));
+      }
+    }
+  }
+  __syncthreads();  // the whole dS is in shared memory
+
+  // ---- phase 4: dQ rows of this warp = dS K;  phase 5: dK rows of this warp = dS^T Q ----
+#pragma unroll 1
+  for (int which = 0; which < 2; ++which) {
+    float acc[8][4];
+#pragma unroll
+    for (int j = 0; j < 8; ++j)
+#pragma unroll
+      for (int c = 0; c < 4; ++c) acc[j][c] = 0.f;
+    const uint32_t bmat = which == 0 ? skb : sqb;
+    for (int k0 = 0; k0 < Np; k0 += 16) {
+      uint32_t a[4];
+      if (which == 0) ldmatrix_x4(a, att_p_addr(spb, row0 + (li & 1) * 8 + lr, k0 + (li >> 1) * 8));          // A = dS
+      else ldmatrix_x4_trans(a, att_p_addr(spb, k0 + (li >> 1) * 8 + lr, row0 + (li & 1) * 8));               // A = dS^T
+#pragma unroll
+      for (int jp = 0; jp < 4; ++jp) {
+        uint32_t bb[4];
+        ldmatrix_x4_trans(bb, att_tile_addr(bmat, k0 + (li & 1) * 8 + lr, jp * 16 + (li >> 1) * 8));
+        mma_bf16_16816(acc[2 * jp], a, bb[0], bb[1]);
+        mma_bf16_16816(acc[2 * jp + 1], a, bb[2], bb[3]);
+      }
+    }
+    __nv_bfloat16* dst = dqb + static_cast<int64_t>(which) * H * kAttD;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      if (row0 + g < N)
+        *reinterpret_cast<__nv_bfloat162*>(dst + static_cast<int64_t>(row0 + g) * ld + j * 8 + 2 * t) =
+            __floats2bfloat162_rn(acc[j][0], acc[j][1]);
+      if (row0 + g + 8 < N)
+        *reinterpret_cast<__nv_bfloat162*>(dst + static_cast<int64_t>(row0 + g + 8) * ld + j * 8 + 2 * t) =
+            __floats2bfloat162_rn(acc[j][2], acc[j][3]);
+    }
+  }
+}
+
+static int launch_attention_bwd(const __nv_bfloat16* qkv, const __nv_bfloat16* o, const __nv_bfloat16* d_o, const float* lse2, int B,
+                                int N, int H, int head_dim, __nv_bfloat16* dqkv, cudaStream_t s) {
+  VDK_REQUIRE(head_dim == kAttD, "attention backward: head_dim must be 64 (got %d)", head_dim);
+  VDK_REQUIRE(N > 0 && N <= kAttBwdMaxRows, "attention backward: at most %d tokens (got %d): the probability matrix of one head is kept "
+              "in shared memory", kAttBwdMaxRows, N);
+  VDK_REQUIRE(B > 0 && H > 0 && H <= 65535 && B <= 65535, "attention backward: bad shape");
+  const int nwarps = (N + 15) / 16, Np = nwarps * 16;
+  const int smem = 4 * Np * 128 + Np * kAttPStride + Np * 4;
+  static bool attr = false;
+  if (!attr) {
+    VDK_CUDA_OK(cudaFuncSetAttribute(attention_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024));
+    attr = true;
+  }
+  const float scale = 1.0f / sqrtf(static_cast<float>(head_dim));
+  attention_bwd_kernel<<<dim3(H, B), nwarps * 32, smem, s>>>(qkv, o, d_o, lse2, B, N, H, scale, scale * 1.4426950408889634f, dqkv);
   VDK_CUDA_OK(cudaGetLastError());
   return VDK_OK;
 }
@@ -338,7 +564,22 @@ extern "C" size_t vdk_vit_workspace_bytes(const vdk_vit_net* net, int batch) {
 extern "C" int vdk_attention_fwd(const void* qkv, int batch, int tokens, int heads, int head_dim, void* out, void* stream) {
   VDK_REQUIRE(qkv && out, "vdk_attention_fwd: null operand");
   return launch_attention(reinterpret_cast<const __nv_bfloat16*>(qkv), batch, tokens, heads, head_dim,
-                          reinterpret_cast<__nv_bfloat16*>(out), reinterpret_cast<cudaStream_t>(stream));
+                          reinterpret_cast<__nv_bfloat16*>(out), nullptr, reinterpret_cast<cudaStream_t>(stream));
+}
+
+extern "C" int vdk_attention_fwd_lse(const void* qkv, int batch, int tokens, int heads, int head_dim, void* out, float* lse2,
+                                     void* stream) {
+  VDK_REQUIRE(qkv && out && lse2, "vdk_attention_fwd_lse: null operand");
+  return launch_attention(reinterpret_cast<const __nv_bfloat16*>(qkv), batch, tokens, heads, head_dim,
+                          reinterpret_cast<__nv_bfloat16*>(out), lse2, reinterpret_cast<cudaStream_t>(stream));
+}
+
+extern "C" int vdk_attention_bwd(const void* qkv, const void* out, const void* d_out, const float* lse2, int batch, int tokens,
+                                 int heads, int head_dim, void* dqkv, void* stream) {
+  VDK_REQUIRE(qkv && out && d_out && lse2 && dqkv, "vdk_attention_bwd: null operand");
+  return launch_attention_bwd(reinterpret_cast<const __nv_bfloat16*>(qkv), reinterpret_cast<const __nv_bfloat16*>(out),
+                              reinterpret_cast<const __nv_bfloat16*>(d_out), lse2, batch, tokens, heads, head_dim,
+                              reinterpret_cast<__nv_bfloat16*>(dqkv), reinterpret_cast<cudaStream_t>(stream));
 }
 
 extern "C" int vdk_vit_forward(const vdk_vit_net* net, const float* images, int batch, int l2_normalize, float* embeddings,
@@ -394,7 +635,7 @@ extern "C" int vdk_vit_forward(const vdk_vit_net* net, const float* images, int 
     if (rc != VDK_OK) return rc;
     rc = gemm(y, b->qkv_w, big, M, 3 * C, C, C, VDK_EPI_NONE, b->qkv_b, nullptr, nullptr);
     if (rc != VDK_OK) return rc;
-    rc = launch_attention(big, batch, T, net->heads, kAttD, y, s);
+    rc = launch_attention(big, batch, T, net->heads, kAttD, y, nullptr, s);
     if (rc != VDK_OK) return rc;
     rc = gemm(y, b->proj_w, x, M, C, C, C, VDK_EPI_SCALE_RESIDUAL, b->proj_b, net->ones, x);  // x += proj(a), in place per tile
     if (rc != VDK_OK) return rc;
@@ -430,3 +671,259 @@ extern "C" int vdk_vit_forward(const vdk_vit_net* net, const float* images, int 
   }
   return VDK_OK;
 }
+
+// ================================================================================================================
+// ViT TRAINING: forward with saved activations, full backward (fp32 gradients accumulated in timm layouts)
+// ================================================================================================================
+// Replaces, for `timm-vit_*` backbones in train mode, TimmWrapper.forward (models/faceX/backbone/timm_wrapper.py:51-54; the
+// Transformer neck :42-47 with BatchNorm1d on batch statistics) and its autograd backward inside
+// `scaler.scale(loss).backward()` (engine/procedure/train.py:206).  BASELINE config 3 (ViT-B/16 + CircleLoss).
+namespace vdk {
+
+struct VitTrainLayout {
+  int N, T, C, Kp, depth;
+  size_t M;
+  size_t rows, x0;                                   // patch rows [B*N, Kp], x after patch embed + cls + pos
+  size_t y1[VDK_VIT_MAX_BLOCKS], r1[VDK_VIT_MAX_BLOCKS], qkv[VDK_VIT_MAX_BLOCKS], att[VDK_VIT_MAX_BLOCKS], lse[VDK_VIT_MAX_BLOCKS];
+  size_t xm[VDK_VIT_MAX_BLOCKS], y2[VDK_VIT_MAX_BLOCKS], r2[VDK_VIT_MAX_BLOCKS], hpre[VDK_VIT_MAX_BLOCKS], hpost[VDK_VIT_MAX_BLOCKS];
+  size_t xo[VDK_VIT_MAX_BLOCKS];                     // block outputs (residual stream)
+  size_t f1, rf1, f2, rf2, z, zslab, bn_mean, bn_rstd;
+  size_t dxa, dxb, dy, dbig, dz, dzb, gw, wslab, tok, dtok;
+  size_t total;
+};
+
+static int vit_train_layout(const vdk_vit_net* n, int batch, VitTrainLayout* L) {
+  VitLayout base;
+  int rc = vit_layout(n, batch, &base);
+  if (rc != VDK_OK) return rc;
+  VDK_REQUIRE(base.Kp == 3 * n->patch * n->patch, "vdk_vit_train: 3*patch*patch must be a multiple of 8 (patch %d)", n->patch);
+  VDK_REQUIRE(base.T <= kAttBwdMaxRows, "vdk_vit_train: at most %d tokens (got %d)", kAttBwdMaxRows, base.T);
+  VDK_REQUIRE(batch > 1, "vdk_vit_train: batch must be > 1 (BatchNorm1d batch statistics)");
+  L->N = base.N; L->T = base.T; L->C = base.C; L->Kp = base.Kp; L->M = base.M; L->depth = n->depth;
+  const size_t M = L->M, C = L->C, F = n->feat_dim;
+  size_t off = 0;
+  auto take = [&](size_t bytes) { size_t o = off; off += up256v(bytes); return o; };
+  L->rows = take(static_cast<size_t>(batch) * L->N * L->Kp * 2);
+  L->tok = take(static_cast<size_t>(batch) * L->N * C * 2);
+  L->x0 = take(M * C * 2);
+  for (int i = 0; i < n->depth; ++i) {
+    L->y1[i] = take(M * C * 2);  L->r1[i] = take(M * 4);
+    L->qkv[i] = take(M * 3 * C * 2);
+    L->att[i] = take(M * C * 2); L->lse[i] = take(static_cast<size_t>(batch) * n->heads * L->T * 4);
+    L->xm[i] = take(M * C * 2);
+    L->y2[i] = take(M * C * 2);  L->r2[i] = take(M * 4);
+    L->hpre[i] = take(M * 4 * C * 2);
+    L->hpost[i] = take(M * 4 * C * 2);
+    L->xo[i] = take(M * C * 2);
+  }
+  L->f1 = take(M * C * 2); L->rf1 = take(M * 4);
+  L->f2 = take(M * C * 2); L->rf2 = take(M * 4);
+  L->z = take(static_cast<size_t>(batch) * F * 4);
+  L->zslab = take(static_cast<size_t>(batch) * F * 4 * 64);
+  L->bn_mean = take(F * 4); L->bn_rstd = take(F * 4);
+  // backward scratch
+  L->dxa = take(M * C * 2); L->dxb = take(M * C * 2); L->dy = take(M * C * 2);
+  L->dbig = take(M * 4 * C * 2);
+  L->dz = take(static_cast<size_t>(batch) * F * 4); L->dzb = take(static_cast<size_t>(batch) * F * 2);
+  L->gw = take(F * static_cast<size_t>(L->T) * C * 4);
+  L->dtok = take(static_cast<size_t>(batch) * L->N * C * 2);
+  size_t slab = wgrad_slab_bytes(static_cast<int>(C), L->Kp, static_cast<size_t>(batch) * L->N);
+  slab = std::max(slab, wgrad_slab_bytes(static_cast<int>(3 * C), static_cast<int>(C), M));
+  slab = std::max(slab, wgrad_slab_bytes(static_cast<int>(C), static_cast<int>(C), M));
+  slab = std::max(slab, wgrad_slab_bytes(static_cast<int>(4 * C), static_cast<int>(C), M));
+  slab = std::max(slab, wgrad_slab_bytes(static_cast<int>(C), static_cast<int>(4 * C), M));
+  L->wslab = take(slab);
+  L->total = off + 256;
+  return VDK_OK;
+}
+
+__global__ void vit_slab_bias_kernel(const float* __restrict__ slabs, int n_slabs, size_t stride, const float* __restrict__ bias, int rows,
+                                     int cols, float* __restrict__ out) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= rows * cols) return;
+  float v = bias[i % cols];
+  for (int s = 0; s < n_slabs; ++s) v += slabs[s * stride + i];
+  out[i] = v;
+}
+__global__ void vit_colsum_f32_kernel(const float* __restrict__ x, int rows, int cols, float* __restrict__ out) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= cols) return;
+  float s = 0.f;
+  for (int r = 0; r < rows; ++r) s += x[static_cast<size_t>(r) * cols + c];
+  out[c] += s;
+}
+// backward of vit_assemble: dtok[b, i] = dx[b, 1 + i];  dpos[t] += sum_b dx[b, t];  dcls += sum_b dx[b, 0]
+__global__ void __launch_bounds__(256)
+vit_assemble_bwd_kernel(const __nv_bfloat16* __restrict__ dx, int B, int N, int C, __nv_bfloat16* __restrict__ dtok,
+                        float* __restrict__ dpos, float* __restrict__ dcls) {
+  const int64_t total = static_cast<int64_t>(N + 1) * C;  // one thread per (token, channel), loop over the batch
+  for (int64_t t = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x; t < total;
+       t += static_cast<int64_t>(gridDim.x) * blockDim.x) {
+    const int c = static_cast<int>(t % C), tk = static_cast<int>(t / C);
+    float s = 0.f;
+    for (int b = 0; b < B; ++b) {
+      const __nv_bfloat16 v = dx[(static_cast<int64_t>(b) * (N + 1) + tk) * C + c];
+      s += __bfloat162float(v);
+      if (tk > 0) dtok[(static_cast<int64_t>(b) * N + tk - 1) * C + c] = v;
+    }
+    dpos[t] += s;
+    if (tk == 0) dcls[c] += s;
+  }
+}
+
+}  // namespace vdk
+
+extern "C" int vdk_vit_pack(const vdk_vit_tensors* p, vdk_vit_net* net, void* stream) {
+  VDK_REQUIRE(p && net, "vdk_vit_pack: null argument");
+  cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
+  VitLayout L;
+  RC(vit_layout(net, 2, &L));
+  VDK_REQUIRE(L.Kp == 3 * net->patch * net->patch, "vdk_vit_pack: 3*patch*patch must be a multiple of 8");
+  auto bf = [](const void* q) { return reinterpret_cast<__nv_bfloat16*>(const_cast<void*>(q)); };
+  const int64_t C = net->dim;
+  RC(launch_cast_bf16(p->patch_w, C * L.Kp, bf(net->patch_w), s));
+  for (int i = 0; i < net->depth; ++i) {
+    const vdk_vit_block_tensors* b = &p->blocks[i];
+    const vdk_vit_block* o = &net->blocks[i];
+    RC(launch_cast_bf16(b->qkv_w, 3 * C * C, bf(o->qkv_w), s));
+    RC(launch_cast_bf16(b->proj_w, C * C, bf(o->proj_w), s));
+    RC(launch_cast_bf16(b->fc1_w, 4 * C * C, bf(o->fc1_w), s));
+    RC(launch_cast_bf16(b->fc2_w, 4 * C * C, bf(o->fc2_w), s));
+  }
+  RC(launch_cast_bf16(p->lin_w, static_cast<int64_t>(net->feat_dim) * L.T * C, bf(net->neck_w), s));
+  return VDK_OK;
+}
+
+extern "C" size_t vdk_vit_train_workspace_bytes(const vdk_vit_net* net, int batch) {
+  VitTrainLayout L;
+  if (!net || batch <= 1 || vit_train_layout(net, batch, &L) != VDK_OK) return 0;
+  return L.total;
+}
+
+extern "C" int vdk_vit_train_forward(const vdk_vit_net* net, const vdk_vit_tensors* p, const float* images, int batch,
+                                     float bn_momentum, float* out_feats, void* workspace, size_t workspace_bytes, void* stream) {
+  VDK_REQUIRE(net && p && images && out_feats, "vdk_vit_train_forward: null argument");
+  VitTrainLayout L;
+  RC(vit_train_layout(net, batch, &L));
+  VDK_REQUIRE(workspace && workspace_bytes >= L.total && (reinterpret_cast<uintptr_t>(workspace) & 255) == 0,
+              "vdk_vit_train_forward: workspace too small or misaligned");
+  cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
+  uint8_t* ws = reinterpret_cast<uint8_t*>(workspace);
+  auto B16 = [&](size_t off) { return reinterpret_cast<__nv_bfloat16*>(ws + off); };
+  auto F32 = [&](size_t off) { return reinterpret_cast<float*>(ws + off); };
+  const Gemm G{s};
+  const int C = L.C, T = L.T, N = L.N, M = static_cast<int>(L.M), F = net->feat_dim;
+
+  {
+    const int64_t total = static_cast<int64_t>(batch) * N * L.Kp;
+    vit_patchify_kernel<<<static_cast<int>(std::min<int64_t>((total + 255) / 256, 148 * 32)), 256, 0, s>>>(images, batch, net->image_size,
+                                                                                                         net->patch, L.Kp, B16(L.rows));
+    VDK_CUDA_OK(cudaGetLastError());
+    RC(G.run(B16(L.rows), net->patch_w, B16(L.tok), batch * N, C, L.Kp, L.Kp, L.Kp, C, VDK_EPI_NONE, net->patch_b, nullptr, nullptr, 0,
+             VDK_DTYPE_BF16, 1, 0, 0, 0));
+    const int64_t tot2 = static_cast<int64_t>(M) * (C / 2);
+    vit_assemble_kernel<<<static_cast<int>(std::min<int64_t>((tot2 + 255) / 256, 148 * 32)), 256, 0, s>>>(B16(L.tok), net->cls_token,
+                                                                                                        net->pos_embed, batch, N, C, B16(L.x0));
+    VDK_CUDA_OK(cudaGetLastError());
+  }
+  const __nv_bfloat16* x = B16(L.x0);
+  for (int i = 0; i < net->depth; ++i) {
+    const vdk_vit_block* b = &net->blocks[i];
+    RC(launch_ln_patchify(x, batch, T, 1, C, b->ln1_w, b->ln1_b, 1e-6f, 1, B16(L.y1[i]), F32(L.r1[i]), s));
+    RC(G.run(B16(L.y1[i]), b->qkv_w, B16(L.qkv[i]), M, 3 * C, C, C, C, 3 * C, VDK_EPI_NONE, b->qkv_b, nullptr, nullptr, 0, VDK_DTYPE_BF16,
+             1, 0, 0, 0));
+    RC(launch_attention(B16(L.qkv[i]), batch, T, net->heads, kAttD, B16(L.att[i]), F32(L.lse[i]), s));
+    RC(G.run(B16(L.att[i]), b->proj_w, B16(L.xm[i]), M, C, C, C, C, C, VDK_EPI_SCALE_RESIDUAL, b->proj_b, net->ones, x, C, VDK_DTYPE_BF16,
+             1, 0, 0, 0));
+    RC(launch_ln_patchify(B16(L.xm[i]), batch, T, 1, C, b->ln2_w, b->ln2_b, 1e-6f, 1, B16(L.y2[i]), F32(L.r2[i]), s));
+    RC(G.run(B16(L.y2[i]), b->fc1_w, B16(L.hpost[i]), M, 4 * C, C, C, C, 4 * C, VDK_EPI_GELU, b->fc1_b, nullptr, nullptr, 0, VDK_DTYPE_BF16,
+             1, 0, 0, 0, B16(L.hpre[i])));
+    RC(G.run(B16(L.hpost[i]), b->fc2_w, B16(L.xo[i]), M, C, 4 * C, 4 * C, 4 * C, C, VDK_EPI_SCALE_RESIDUAL, b->fc2_b, net->ones,
+             B16(L.xm[i]), C, VDK_DTYPE_BF16, 1, 0, 0, 0));
+    x = B16(L.xo[i]);
+  }
+  RC(launch_ln_patchify(x, batch, T, 1, C, net->norm_w, net->norm_b, 1e-6f, 1, B16(L.f1), F32(L.rf1), s));
+  RC(launch_ln_patchify(B16(L.f1), batch, T, 1, C, net->neck_ln_w, net->neck_ln_b, 1e-5f, 1, B16(L.f2), F32(L.rf2), s));
+  {
+    const int Kn = T * C;
+    const int tiles = ((batch + 127) / 128) * ((F + 255) / 256);
+    int split = std::max(1, std::min(64, (2 * sm_count()) / std::max(1, tiles)));
+    split = vdk_gemm_effective_splits(Kn, split);
+    const size_t slab = static_cast<size_t>(batch) * F;
+    RC(G.run(B16(L.f2), net->neck_w, F32(L.zslab), batch, F, Kn, Kn, Kn, F, VDK_EPI_NONE, nullptr, nullptr, nullptr, 0, VDK_DTYPE_FP32, split,
+             split > 1 ? static_cast<long long>(slab) : 0, 0, 0));
+    vit_slab_bias_kernel<<<(batch * F + 255) / 256, 256, 0, s>>>(F32(L.zslab), split, slab, p->lin_b, batch, F, F32(L.z));
+    VDK_CUDA_OK(cudaGetLastError());
+    RC(launch_bn_fwd_f32(F32(L.z), batch, F, p->bn1_w, p->bn1_b, 1e-5f, bn_momentum, out_feats, F32(L.bn_mean), F32(L.bn_rstd),
+                         p->bn1_running_mean, p->bn1_running_var, s));
+  }
+  return VDK_OK;
+}
+
+extern "C" int vdk_vit_train_backward(const vdk_vit_net* net, const vdk_vit_tensors* p, const vdk_vit_tensors* g, const float* d_feats,
+                                      int batch, void* workspace, size_t workspace_bytes, void* stream) {
+  VDK_REQUIRE(net && p && g && d_feats, "vdk_vit_train_backward: null argument");
+  VitTrainLayout L;
+  RC(vit_train_layout(net, batch, &L));
+  VDK_REQUIRE(workspace && workspace_bytes >= L.total, "vdk_vit_train_backward: workspace too small");
+  cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
+  uint8_t* ws = reinterpret_cast<uint8_t*>(workspace);
+  auto B16 = [&](size_t off) { return reinterpret_cast<__nv_bfloat16*>(ws + off); };
+  auto F32 = [&](size_t off) { return reinterpret_cast<float*>(ws + off); };
+  const Gemm G{s};
+  const int C = L.C, T = L.T, N = L.N, M = static_cast<int>(L.M), F = net->feat_dim, Kn = T * C;
+  float* slabs = F32(L.wslab);
+
+  // ---- neck: BatchNorm1d (batch statistics) <- Linear <- LayerNorm(neck) <- LayerNorm(final) ----
+  RC(launch_bn_bwd_f32(d_feats, F32(L.z), batch, F, p->bn1_w, F32(L.bn_mean), F32(L.bn_rstd), F32(L.dz), g->bn1_w, g->bn1_b, s));
+  vit_colsum_f32_kernel<<<(F + 255) / 256, 256, 0, s>>>(F32(L.dz), batch, F, g->lin_b);
+  VDK_CUDA_OK(cudaGetLastError());
+  RC(launch_cast_bf16(F32(L.dz), static_cast<int64_t>(batch) * F, B16(L.dzb), s));
+  // dW[F, Kn] = dZ^T . f2 (contraction over the batch): plain stores into scratch, then += into the gradient
+  RC(G.run(B16(L.dzb), B16(L.f2), F32(L.gw), F, Kn, batch, F, Kn, Kn, VDK_EPI_NONE, nullptr, nullptr, nullptr, 0, VDK_DTYPE_FP32, 1, 0, 1, 1));
+  RC(launch_add_f32(g->lin_w, F32(L.gw), static_cast<int64_t>(F) * Kn, s));
+  // df2[B, Kn] = dZ . W
+  RC(G.run(B16(L.dzb), net->neck_w, B16(L.dy), batch, Kn, F, F, Kn, Kn, VDK_EPI_NONE, nullptr, nullptr, nullptr, 0, VDK_DTYPE_BF16, 1, 0, 0, 1));
+  RC(launch_ln_bwd(B16(L.dy), B16(L.f2), F32(L.rf2), batch, T, 1, C, net->neck_ln_w, net->neck_ln_b, 1, B16(L.dxb), nullptr, g->neck_ln_w,
+                   g->neck_ln_b, s));
+  RC(launch_ln_bwd(B16(L.dxb), B16(L.f1), F32(L.rf1), batch, T, 1, C, net->norm_w, net->norm_b, 1, B16(L.dxa), nullptr, g->norm_w, g->norm_b, s));
+  size_t dx = L.dxa, dx_other = L.dxb;
+  // ---- blocks ----
+  for (int i = net->depth - 1; i >= 0; --i) {
+    const vdk_vit_block* b = &net->blocks[i];
+    const vdk_vit_block_tensors* gb = &g->blocks[i];
+    // MLP: x_out = x_mid + fc2(gelu(fc1(LN2(x_mid))))
+    RC(launch_col_sum(B16(dx), M, C, C, gb->fc2_b, s));
+    RC(G.wgrad(B16(dx), B16(L.hpost[i]), gb->fc2_w, C, 4 * C, M, C, 4 * C, slabs, true));
+    RC(G.run(B16(dx), b->fc2_w, B16(L.dbig), M, 4 * C, C, C, 4 * C, 4 * C, VDK_EPI_MUL_GELU_GRAD, nullptr, nullptr, B16(L.hpre[i]), 4 * C,
+             VDK_DTYPE_BF16, 1, 0, 0, 1));
+    RC(launch_col_sum(B16(L.dbig), M, 4 * C, 4 * C, gb->fc1_b, s));
+    RC(G.wgrad(B16(L.dbig), B16(L.y2[i]), gb->fc1_w, 4 * C, C, M, 4 * C, C, slabs, true));
+    RC(G.run(B16(L.dbig), b->fc1_w, B16(L.dy), M, C, 4 * C, 4 * C, C, C, VDK_EPI_NONE, nullptr, nullptr, nullptr, 0, VDK_DTYPE_BF16, 1, 0, 0, 1));
+    RC(launch_ln_bwd(B16(L.dy), B16(L.y2[i]), F32(L.r2[i]), batch, T, 1, C, b->ln2_w, b->ln2_b, 1, B16(dx_other), B16(dx), gb->ln2_w,
+                     gb->ln2_b, s));  // d x_mid = LN2 backward + the residual branch
+    std::swap(dx, dx_other);
+    // attention: x_mid = x_in + proj(attn(qkv(LN1(x_in))))
+    RC(launch_col_sum(B16(dx), M, C, C, gb->proj_b, s));
+    RC(G.wgrad(B16(dx), B16(L.att[i]), gb->proj_w, C, C, M, C, C, slabs, true));
+    RC(G.run(B16(dx), b->proj_w, B16(L.dy), M, C, C, C, C, C, VDK_EPI_NONE, nullptr, nullptr, nullptr, 0, VDK_DTYPE_BF16, 1, 0, 0, 1));
+    RC(launch_attention_bwd(B16(L.qkv[i]), B16(L.att[i]), B16(L.dy), F32(L.lse[i]), batch, T, net->heads, kAttD, B16(L.dbig), s));
+    RC(launch_col_sum(B16(L.dbig), M, 3 * C, 3 * C, gb->qkv_b, s));
+    RC(G.wgrad(B16(L.dbig), B16(L.y1[i]), gb->qkv_w, 3 * C, C, M, 3 * C, C, slabs, true));
+    RC(G.run(B16(L.dbig), b->qkv_w, B16(L.dy), M, C, 3 * C, 3 * C, C, C, VDK_EPI_NONE, nullptr, nullptr, nullptr, 0, VDK_DTYPE_BF16, 1, 0, 0, 1));
+    RC(launch_ln_bwd(B16(L.dy), B16(L.y1[i]), F32(L.r1[i]), batch, T, 1, C, b->ln1_w, b->ln1_b, 1, B16(dx_other), B16(dx), gb->ln1_w,
+                     gb->ln1_b, s));
+    std::swap(dx, dx_other);
+  }
+  // ---- cls / position embeddings, patch embedding ----
+  {
+    const int64_t tot = static_cast<int64_t>(T) * C;
+    vit_assemble_bwd_kernel<<<static_cast<int>(std::min<int64_t>((tot + 255) / 256, 148 * 8)), 256, 0, s>>>(B16(dx), batch, N, C, B16(L.dtok),
+                                                                                                           g->pos_embed, g->cls_token);
+    VDK_CUDA_OK(cudaGetLastError());
+    RC(launch_col_sum(B16(L.dtok), static_cast<int64_t>(batch) * N, C, C, g->patch_b, s));
+    RC(G.wgrad(B16(L.dtok), B16(L.rows), g->patch_w, C, L.Kp, batch * N, C, L.Kp, slabs, true));
+  }
+  return VDK_OK;
+}
+

@@ -4,8 +4,9 @@ Mirrors what `TimmWrapper(model_name='vit_*', feat_dim, image_size)` builds in t
 (models/faceX/backbone/timm_wrapper.py:16-21 + the Transformer neck of :39-47): the parameter tree and state_dict keys of
 timm 0.9.16's VisionTransformer (`model.patch_embed.proj`, `model.cls_token`, `model.pos_embed`, `model.blocks.{i}.{norm1,
 attn.qkv, attn.proj, norm2, mlp.fc1, mlp.fc2}`, `model.norm`) and `output_layer.{0: LayerNorm, 2: Linear, 3: BatchNorm1d}`,
-so reference checkpoints load with `strict=True`.  The eval forward runs in `vdk_vit_forward` (csrc/vit.cu).  Training a
-ViT (BASELINE config 3) needs the attention backward, which is not built: `.train()` forward raises.
+so reference checkpoints load with `strict=True`.  The eval forward runs in `vdk_vit_forward`, the train-mode forward and
+backward (BASELINE config 3) in `vdk_vit_train_forward` / `vdk_vit_train_backward` (csrc/vit.cu) as ONE autograd node;
+training needs 3*patch^2 % 8 == 0 and at most 208 tokens (ViT-*/16 at 224^2).
 """
 from __future__ import annotations
 
@@ -81,6 +82,20 @@ class _VitBlockC(C.Structure):
                                           "fc2_w", "fc2_b")]
 
 
+class _VitBlockTensorsC(C.Structure):
+    _fields_ = [(n, C.c_void_p) for n in ("ln1_w", "ln1_b", "qkv_w", "qkv_b", "proj_w", "proj_b", "ln2_w", "ln2_b", "fc1_w", "fc1_b",
+                                          "fc2_w", "fc2_b")]
+
+
+class VitTensorsC(C.Structure):
+    """vdk_vit_tensors: fp32 tensors in timm layouts (parameters, or their gradients)."""
+    _fields_ = [("patch_w", C.c_void_p), ("patch_b", C.c_void_p), ("cls_token", C.c_void_p), ("pos_embed", C.c_void_p),
+                ("blocks", _VitBlockTensorsC * MAX_BLOCKS),
+                ("norm_w", C.c_void_p), ("norm_b", C.c_void_p), ("neck_ln_w", C.c_void_p), ("neck_ln_b", C.c_void_p),
+                ("lin_w", C.c_void_p), ("lin_b", C.c_void_p),
+                ("bn1_w", C.c_void_p), ("bn1_b", C.c_void_p), ("bn1_running_mean", C.c_void_p), ("bn1_running_var", C.c_void_p)]
+
+
 class VitNetC(C.Structure):
     """vdk_vit_net (include/vdk_b200.h)."""
     _fields_ = [("image_size", C.c_int), ("patch", C.c_int), ("dim", C.c_int), ("depth", C.c_int), ("heads", C.c_int),
@@ -111,15 +126,123 @@ class ViTWrapper(nn.Module):
         self._packed: Optional[Dict] = None
         self._packed_key = None
         self._ws = None
+        self._train = None
         if pretrained:
             raise RuntimeError("pretrained timm weights cannot be downloaded here (no network): pass pretrained=False and "
                                "load a checkpoint with load_state_dict (keys are timm's)")
 
     def forward(self, x: torch.Tensor) -> torch.Tensor:
         if self.training:
-            raise NotImplementedError("ViT training (attention backward) is not built on B200 yet; use .eval() for the "
-                                      "extract path — there is no fallback")
+            return _ViTTrainFn.apply(self, x, *[p for _, p in self.named_parameters()])
         return self.embed(x, l2_normalize=False)
+
+    # ---- training path (csrc/vit.cu: vdk_vit_train_forward / vdk_vit_train_backward) -------------------------------------
+    def _tensors_struct(self, get) -> VitTensorsC:
+        t = VitTensorsC()
+        t.patch_w, t.patch_b = get("model.patch_embed.proj.weight"), get("model.patch_embed.proj.bias")
+        t.cls_token, t.pos_embed = get("model.cls_token"), get("model.pos_embed")
+        for i in range(self.model.depth):
+            b, pre = t.blocks[i], f"model.blocks.{i}."
+            b.ln1_w, b.ln1_b = get(pre + "norm1.weight"), get(pre + "norm1.bias")
+            b.qkv_w, b.qkv_b = get(pre + "attn.qkv.weight"), get(pre + "attn.qkv.bias")
+            b.proj_w, b.proj_b = get(pre + "attn.proj.weight"), get(pre + "attn.proj.bias")
+            b.ln2_w, b.ln2_b = get(pre + "norm2.weight"), get(pre + "norm2.bias")
+            b.fc1_w, b.fc1_b = get(pre + "mlp.fc1.weight"), get(pre + "mlp.fc1.bias")
+            b.fc2_w, b.fc2_b = get(pre + "mlp.fc2.weight"), get(pre + "mlp.fc2.bias")
+        t.norm_w, t.norm_b = get("model.norm.weight"), get("model.norm.bias")
+        t.neck_ln_w, t.neck_ln_b = get("output_layer.0.weight"), get("output_layer.0.bias")
+        t.lin_w, t.lin_b = get("output_layer.2.weight"), get("output_layer.2.bias")
+        t.bn1_w, t.bn1_b = get("output_layer.3.weight"), get("output_layer.3.bias")
+        t.bn1_running_mean, t.bn1_running_var = get("output_layer.3.running_mean"), get("output_layer.3.running_var")
+        return t
+
+    def _train_structs(self, device):
+        m = self.model
+        if self._train is None or self._train["device"] != device:
+            def buf(*shape):
+                return torch.empty(shape, dtype=torch.bfloat16, device=device)
+            tokens = (m.image_size // m.patch) ** 2 + 1
+            self._train = {"device": device, "ws": None, "gflat": None, "last": None,
+                           "patch_w": buf(m.dim, 3 * m.patch * m.patch),
+                           "blocks": [{"qkv_w": buf(3 * m.dim, m.dim), "proj_w": buf(m.dim, m.dim), "fc1_w": buf(4 * m.dim, m.dim),
+                                       "fc2_w": buf(m.dim, 4 * m.dim)} for _ in range(m.depth)],
+                           "neck_w": buf(self.feat_dim, tokens * m.dim),
+                           "ones": torch.ones(m.dim, dtype=torch.float32, device=device)}
+        st = self._train
+        named = dict(self.named_parameters())
+        named.update(dict(self.named_buffers()))
+        for n, t in named.items():
+            if t.is_floating_point() and (t.device != device or t.dtype != torch.float32 or not t.is_contiguous()):
+                raise RuntimeError(f"{n}: training needs contiguous fp32 parameters on {device}")
+        params = self._tensors_struct(lambda n: named[n].data_ptr())
+        net = VitNetC()
+        net.image_size, net.patch, net.dim, net.depth, net.heads, net.feat_dim = (m.image_size, m.patch, m.dim, m.depth, m.heads,
+                                                                                 self.feat_dim)
+        net.patch_w, net.patch_b = st["patch_w"].data_ptr(), params.patch_b
+        net.cls_token, net.pos_embed, net.ones = params.cls_token, params.pos_embed, st["ones"].data_ptr()
+        for i in range(m.depth):
+            b, pb, bb = net.blocks[i], params.blocks[i], st["blocks"][i]
+            b.ln1_w, b.ln1_b, b.qkv_b, b.proj_b = pb.ln1_w, pb.ln1_b, pb.qkv_b, pb.proj_b
+            b.ln2_w, b.ln2_b, b.fc1_b, b.fc2_b = pb.ln2_w, pb.ln2_b, pb.fc1_b, pb.fc2_b
+            b.qkv_w, b.proj_w = bb["qkv_w"].data_ptr(), bb["proj_w"].data_ptr()
+            b.fc1_w, b.fc2_w = bb["fc1_w"].data_ptr(), bb["fc2_w"].data_ptr()
+        net.norm_w, net.norm_b, net.neck_ln_w, net.neck_ln_b = params.norm_w, params.norm_b, params.neck_ln_w, params.neck_ln_b
+        net.neck_w, net.neck_b = st["neck_w"].data_ptr(), params.lin_b
+        return st, net, params
+
+    def _train_forward(self, x: torch.Tensor) -> torch.Tensor:
+        lib = _lib.load()
+        if x.device.type != "cuda":
+            raise RuntimeError("visiondk_b200.ViTWrapper runs on CUDA (sm_100a) only; there is no CPU fallback")
+        x = x.contiguous().float()
+        B = x.shape[0]
+        st, net, params = self._train_structs(x.device)
+        need = lib.vdk_vit_train_workspace_bytes(C.byref(net), B)
+        if need == 0:
+            raise RuntimeError("vdk_vit_train_workspace_bytes: " + _lib.last_error())
+        if st["ws"] is None or st["ws"].numel() < need:
+            st["ws"] = torch.empty((need,), dtype=torch.uint8, device=x.device)
+        out = torch.empty((B, self.feat_dim), dtype=torch.float32, device=x.device)
+        bn = self.output_layer[3]
+        with torch.cuda.device(x.device):
+            s = _lib.stream_ptr()
+            _lib.check(lib.vdk_vit_pack(C.byref(params), C.byref(net), s), "vdk_vit_pack")
+            _lib.check(lib.vdk_vit_train_forward(C.byref(net), C.byref(params), x.data_ptr(), B, float(bn.momentum), out.data_ptr(),
+                                                 st["ws"].data_ptr(), st["ws"].numel(), s), "vdk_vit_train_forward")
+        bn.num_batches_tracked += 1
+        st["last"] = (net, params, B)
+        return out
+
+    def _train_backward(self, dout: torch.Tensor):
+        """Gradients of every parameter: accumulated straight into pre-allocated fp32 `.grad` buffers when every parameter owns
+        one (the fused optimizer's flat buffer), else produced in a scratch buffer and returned to autograd."""
+        lib = _lib.load()
+        st = self._train
+        net, params, B = st["last"]
+        plist = list(self.named_parameters())
+        direct = all(p.grad is not None and p.grad.dtype == torch.float32 and p.grad.is_contiguous() and
+                     p.grad.device == dout.device for _, p in plist)
+        if direct:
+            ptrs = {n: p.grad.data_ptr() for n, p in plist}
+        else:
+            total = sum(p.numel() for _, p in plist)
+            if st["gflat"] is None or st["gflat"].numel() != total:
+                st["gflat"] = torch.empty((total,), dtype=torch.float32, device=dout.device)
+            gflat = st["gflat"]
+            gflat.zero_()
+            offs, off = {}, 0
+            for n, p in plist:
+                offs[n] = off
+                off += p.numel()
+            ptrs = {n: gflat.data_ptr() + 4 * offs[n] for n, _ in plist}
+        grads = self._tensors_struct(lambda n: ptrs.get(n, 0))
+        dout = dout.contiguous().float()
+        with torch.cuda.device(dout.device):
+            _lib.check(lib.vdk_vit_train_backward(C.byref(net), C.byref(params), C.byref(grads), dout.data_ptr(), B, st["ws"].data_ptr(),
+                                                  st["ws"].numel(), _lib.stream_ptr()), "vdk_vit_train_backward")
+        if direct:
+            return [None] * len(plist)
+        return [gflat[offs[n]:offs[n] + p.numel()].view_as(p) for n, p in plist]
 
     def _version_key(self, device):
         return (str(device),) + tuple(int(t._version) for t in list(self.parameters()) + list(self.buffers()))
@@ -191,3 +314,18 @@ class ViTWrapper(nn.Module):
             _lib.check(lib.vdk_vit_forward(C.byref(net), x.data_ptr(), B, int(l2_normalize), out.data_ptr(), self._ws.data_ptr(),
                                            self._ws.numel(), _lib.stream_ptr()), "vdk_vit_forward")
         return out
+
+
+class _ViTTrainFn(torch.autograd.Function):
+    """Train-mode forward/backward of the whole ViT + neck as one autograd node (csrc/vit.cu)."""
+
+    @staticmethod
+    def forward(ctx, module, x, *params):
+        ctx.module = module
+        return module._train_forward(x)
+
+    @staticmethod
+    def backward(ctx, dout):
+        grads = ctx.module._train_backward(dout)
+        return (None, None, *grads)
+
