@@ -547,6 +547,56 @@ def bench_train(ctx, args):
                                    "MEASURED_PEAKS.json bf16_tflops_sustained (kernel inside a long step)"}}
 
 
+def bench_train_vit(ctx, args):
+    """Secondary row, BASELINE config 3: ViT-B/16 224^2 + CircleLoss (C=1000) train step, same contract as bench_train."""
+    import torch
+    from visiondk_b200.train import FaceTrainingModel, FaceTrainer, DevicePrefetcher
+    B = args.train_batch
+    torch.manual_seed(0)
+    cfg = {"backbone": {"timm-vit_base_patch16_224": {"pretrained": False, "image_size": IMG, "feat_dim": FEAT}},
+           "head": {"circleloss": {"feat_dim": FEAT, "num_class": 1000, "margin": 0.25, "gamma": 256}}}
+    model = FaceTrainingModel(cfg).to(ctx.dev)
+    trainer = FaceTrainer(model, lr0=0.01, momentum=0.937, weight_decay=5e-4, label_smooth=0.1, layer_wise=True, warm_steps=0,
+                          total_steps=100000, use_ema=(ctx.rank == 0))
+    gen = torch.Generator(device=ctx.dev).manual_seed(200 + ctx.rank)
+    pool = [torch.randn(B, 3, IMG, IMG, device=ctx.dev, generator=gen) for _ in range(2)]
+    labels = [torch.randint(0, 1000, (B,), device=ctx.dev, generator=gen) for _ in range(2)]
+    state = {"i": 0}
+
+    def step_dev():
+        i = state["i"] & 1
+        state["i"] += 1
+        return trainer.step(pool[i], labels[i])
+
+    ms = timed(ctx, step_dev, args.steps, args.warmup)
+    host_x = [torch.randn(B, 3, IMG, IMG).pin_memory() for _ in range(2)]
+    host_y = [torch.randint(0, 1000, (B,)).pin_memory() for _ in range(2)]
+    n_e2e = max(3, args.warmup) + args.steps
+    feed = DevicePrefetcher(((host_x[j & 1], host_y[j & 1]) for j in range(n_e2e + 1)), ctx.dev)
+
+    def step_e2e():
+        x, y = next(feed)
+        return trainer.step(x, y).item()
+
+    e2e_ms = timed(ctx, step_e2e, args.steps, args.warmup)
+    gflop = 3 * 35.28
+    peak_s = 1422.7
+    try:
+        peak_s = float(json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))["bf16_tflops_sustained"])
+    except Exception:
+        pass
+    ach = B * gflop / ms
+    del trainer, model
+    return {"metric": "embeddings/sec (ViT-B/16 224^2 faceX CircleLoss train step)", "value": ctx.world * B / (ms * 1e-3),
+            "unit": "embeddings/s", "ms_per_step": ms, "scaling": "weak", "dtype": "bf16",
+            "config": {"workload": f"faceX train step: ViT-B/16 {IMG}^2 + CircleLoss(C=1000) + CE(label_smooth 0.1) + clip + SGD + EMA, "
+                                   f"batch {B} per GPU, DDP all-reduce(mean) over {ctx.world} GPU(s)"},
+            "e2e": {"value": ctx.world * B / (e2e_ms * 1e-3), "unit": "embeddings/s", "ms_per_step": e2e_ms,
+                    "h2d_bytes_per_step": B * 3 * IMG * IMG * 4 + B * 8, "d2h_bytes_per_step": 4},
+            "roofline": {"bound": "tensor", "whole_step": {"achieved": ach, "unit": "TFLOP/s", "peak": peak_s, "frac": ach / peak_s,
+                                                            "note": "105.8 GFLOP per image (3 x forward) over the whole step"}}}
+
+
 def bench_retrieval(ctx, args):
     import ctypes as C
     import torch
@@ -674,6 +724,8 @@ def main():
     want = lambda name: args.only in ("all", name) or (args.only == "both" and name in ("extract", "retrieval"))
     tr = bench_train(ctx, args) if want("train") else None
     torch.cuda.empty_cache()
+    trv = bench_train_vit(ctx, args) if want("train") else None
+    torch.cuda.empty_cache()
     ex = bench_extract(ctx, args) if want("extract") else None
     torch.cuda.empty_cache()
     exv = bench_extract_vit(ctx, args) if want("extract") else None
@@ -733,7 +785,7 @@ def main():
                 "gpu_launches": tr["launches_per_step"] * args.steps,
                 "roofline": roof if roof is not None else {"bound": "tensor", "whole_step": tr["whole_step"]},
                 "cpu_baseline": cpu.get("train"),
-                "extract": extract, "extract_vit": exv, "retrieval": retrieval,
+                "train_vit": trv, "extract": extract, "extract_vit": exv, "retrieval": retrieval,
             }
         elif ex is not None:
             line = dict(extract)
