@@ -205,3 +205,28 @@ def test_massive_duplicates_fail_loudly(lib):
     idx.add(g)
     with pytest.raises(RuntimeError):
         idx.search(unit_rows(2, 64, 2), 10)
+
+
+def test_l2_variant_of_the_cosine_index(lib):
+    """north_star names cosine / L2: for L2-normalised rows the squared distance is 2 - 2 cos, so search_l2 returns the same ids
+    as search with ascending distances; checked against a brute-force fp64 L2 ranking of the oracle-normalised rows."""
+    from oracle import retrieval as oret
+    from visiondk_b200.retrieval import FlatIPIndex
+    rng = np.random.default_rng(3)
+    g = rng.standard_normal((5000, 128)).astype(np.float32)
+    q = rng.standard_normal((37, 128)).astype(np.float32)
+    index = FlatIPIndex(128, "cuda", normalize=True)
+    index.add(g)
+    d, i = index.search_l2(q, 10)
+    s, i2 = index.search(q, 10)
+    assert np.array_equal(i, i2) and np.all(np.diff(d, axis=1) >= 0)
+    np.testing.assert_array_equal(d, (2.0 - 2.0 * s).astype(np.float32))
+    qn, gn = oret.l2_normalize(q).astype(np.float64), oret.l2_normalize(g).astype(np.float64)
+    d64 = ((qn[:, None, :] - gn[None, :, :]) ** 2).sum(-1)
+    ref = np.argsort(d64, axis=1, kind="stable")[:, :10]
+    # identical sets per query; order may differ only where fp32 scores tie within rounding
+    assert all(set(a) == set(b) for a, b in zip(i.tolist(), ref.tolist()))
+    np.testing.assert_allclose(d, np.take_along_axis(d64, i, axis=1), atol=5e-6)
+    with pytest.raises(ValueError):
+        FlatIPIndex(128, "cuda", normalize=False).search_l2(q, 3)
+

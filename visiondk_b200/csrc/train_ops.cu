@@ -266,6 +266,7 @@ int launch_ln_bwd(const __nv_bfloat16* dy, const __nv_bfloat16* y, const float* 
   else if (vecs <= 16) ln_bwd_launch<16, 1, 4>(dy, y, rstd, B, H, W, C, ln_w, ln_b, patch, dx, addend, dgamma, dbeta, s);
   else if (vecs <= 32) ln_bwd_launch<32, 1, 4>(dy, y, rstd, B, H, W, C, ln_w, ln_b, patch, dx, addend, dgamma, dbeta, s);
   else if (vecs <= 64) ln_bwd_launch<32, 2, 2>(dy, y, rstd, B, H, W, C, ln_w, ln_b, patch, dx, addend, dgamma, dbeta, s);
+  else if (vecs <= 96) ln_bwd_launch<32, 3, 1>(dy, y, rstd, B, H, W, C, ln_w, ln_b, patch, dx, addend, dgamma, dbeta, s);  // ViT-B: C = 768
   else ln_bwd_launch<32, 4, 1>(dy, y, rstd, B, H, W, C, ln_w, ln_b, patch, dx, addend, dgamma, dbeta, s);
   VDK_CUDA_OK(cudaGetLastError());
   return VDK_OK;

@@ -108,6 +108,16 @@ class FlatIPIndex:
         s, i = self.search_device(self._to_device(x), k, resolve_overflow=True)
         return s.cpu().numpy(), i.cpu().numpy()
 
+    def search_l2(self, x, k: int):
+        """Squared-L2 top-k for a cosine index (`normalize=True`): for unit vectors ||q - g||^2 = 2 - 2 q.g, so the k nearest in
+        L2 are the k largest inner products.  Returns (distances float32 [n, k] ascending = fl(2 - 2 * canonical score), ids int64
+        [n, k], -1 / +inf padded), ordered by the canonical cosine score (ties broken by id like `search`)."""
+        if not self.normalize:
+            raise ValueError("search_l2 needs a cosine index (normalize=True): un-normalised L2 ranks differently from inner product")
+        s, i = self.search_device(self._to_device(x), k, resolve_overflow=True)
+        d = torch.where(i >= 0, 2.0 - 2.0 * s, torch.full_like(s, float("inf")))
+        return d.cpu().numpy(), i.cpu().numpy()
+
     # ---- device-resident path ----------------------------------------------------------------------
     def _run_topk(self, qp: "PreparedRows", rows, g_lo: int, g_hi: int, k: int, dense_all: bool):
         """One vdk_ip_topk call: queries `rows` of qp (None = all) against gallery rows [g_lo, g_hi)."""
