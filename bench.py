@@ -4,21 +4,25 @@
     python bench.py --gpus N --steps K --warmup W [--impl reference]
     python -m torch.distributed.run --nnodes=1 --nproc-per-node N ... bench.py --gpus N --steps K --warmup W
 
-BASELINE.json's metric has two halves, "embeddings/sec and query x gallery pairs/sec, ConvNeXt-B 224^2"; both are
-the CBIR eval path (configs[3]: ConvNeXt-B 512-d, 1M gallery x 10k queries, cosine top-100).  The line's
-`metric`/`value` is the first half and the `retrieval` object carries the second with the same fields.
+BASELINE.json's metric is "embeddings/sec and query x gallery pairs/sec, ConvNeXt-B 224^2".  The line's headline (`metric`,
+`value`, `e2e`, `roofline`, `cpu_baseline`) is the faceX TRAIN STEP of configs[1] (ConvNeXt-B 224^2 + ArcFace C=1000, per-GPU
+batch 128, DDP all-reduce overlapped with the backward); the other legs ride in sub-objects with the same fields:
 
-  embeddings/sec  step = one batch of 256 synthetic 224^2 images per GPU through TimmWrapper.embed(l2_normalize=True)
-                  (= FeatureExtractor.extract_cbir's model(x) + F.normalize, face_model.py:137-139), bf16 activations.
-                  N GPUs: images are independent units, no collective -> weak scaling.
-  pairs/sec       step = one full search: 10 000 queries x 1 000 000 gallery rows, 512-d, top-100
-                  (rows_prepare -> tcgen05 score/filter over the gallery ranges -> select -> canonical re-rank).
-                  N GPUs: gallery rows sharded, all-gather of queries and of per-shard lists + merge -> strong scaling.
+  train_vit       configs[2]: ViT-B/16 224^2 + CircleLoss train step (secondary)
+  extract         embeddings/sec of the CBIR eval path: one batch of 256 synthetic 224^2 images per GPU through
+                  TimmWrapper.embed(l2_normalize=True) (= FeatureExtractor.extract_cbir's model(x) + F.normalize,
+                  face_model.py:137-139), bf16 activations; N GPUs: independent images, no collective -> weak scaling
+  extract_vit     the same with ViT-B/16 (secondary)
+  retrieval       pairs/sec of configs[3]: one full search, 10 000 queries x 1 000 000 gallery rows, 512-d, cosine top-100
+                  (rows_prepare -> tcgen05 score/filter over the gallery ranges -> select -> canonical re-rank); N GPUs:
+                  gallery rows sharded, all-gather of queries and of per-shard lists + merge -> strong scaling
 
-`value` is measured with inputs resident in HBM; `e2e` goes through the reference-facing call with HOST buffers
-(pinned): images H2D + embeddings D2H per step for extraction, FlatIPIndex.search-style query H2D + (scores, ids)
-D2H for retrieval.  `roofline` times the dominant kernel alone with CUDA events (tensor bound, measured peak from
-MEASURED_PEAKS.json).  `cpu_baseline` is the oracle's port of the reference CPU formulation on the host cores.
+`value` is measured with inputs resident in HBM; `e2e` goes through the reference-facing call with HOST buffers (pinned):
+train: every step's batch crosses PCIe through visiondk_b200.train.DevicePrefetcher and every step's loss is read back;
+extraction: images H2D + embeddings D2H per step (FeatureExtractor.extract_cbir); retrieval: query H2D + (scores, ids) D2H.
+`roofline` times the dominant kernel alone with CUDA events (tensor bound, peaks from MEASURED_PEAKS.json; `traffic` = DRAM bytes
+per launch from the ncu captures under profiles/).  `cpu_baseline` is the oracle's port of the reference CPU formulation on the
+host cores (thread count calibrated, samples bounded); `--impl reference` prints the same line for that CPU port alone.
 """
 from __future__ import annotations
 
@@ -362,7 +366,7 @@ def bench_extract(ctx, args):
         loader = (host_x[i & 1] for i in range(n_steps))
         return extractor.extract_cbir(loader, ctx.dev)  # numpy float32 [n_steps*B, FEAT] on the host
 
-    run_e2e(3)
+    run_e2e(max(3, args.steps))  # warm-up of the same length: the extractor's pinned staging pool reaches its steady size
     ctx.barrier()
     t0 = time.perf_counter()
     out = run_e2e(args.steps)
@@ -458,7 +462,7 @@ def bench_extract_vit(ctx, args):
     def run_e2e(n_steps):
         return extractor.extract_cbir((host_x[i & 1] for i in range(n_steps)), ctx.dev)
 
-    run_e2e(3)
+    run_e2e(max(3, args.steps))  # warm-up of the same length: the extractor's pinned staging pool reaches its steady size
     ctx.barrier()
     t0 = time.perf_counter()
     out = run_e2e(args.steps)

@@ -86,9 +86,17 @@ class FeatureExtractor:
         model.eval()
         model.to(device)
         host_chunks = []
-        for tensors in _prefetch_to_device(dataloader, device):
+        pool = self.__dict__.setdefault("_pinned_pool", [])  # pinned staging buffers are reused across calls: allocating
+        for j, tensors in enumerate(_prefetch_to_device(dataloader, device)):  # page-locked memory synchronises with the device
             emb = model.embed(tensors, l2_normalize=True)
-            host = torch.empty(emb.shape, dtype=torch.float32, pin_memory=True)
+            if j < len(pool) and pool[j].shape == emb.shape:
+                host = pool[j]
+            else:
+                host = torch.empty(emb.shape, dtype=torch.float32, pin_memory=True)
+                if j < len(pool):
+                    pool[j] = host
+                elif len(pool) < 4096:
+                    pool.append(host)
             host.copy_(emb, non_blocking=True)
             host_chunks.append(host)
         torch.cuda.current_stream(device).synchronize()

@@ -3,7 +3,7 @@
 // Replaces the library GEMMs behind timm's ConvNeXt/ViT Linear layers and patchify convolutions that
 // models/faceX/backbone/timm_wrapper.py:52 runs, and the neck Linear of timm_wrapper.py:36.
 //
-// One persistent CTA per SM, 192 threads:
+// One persistent CTA per SM, 320 threads:
 //   warp 0      : TMA producer   (A tile 128x64, B tile BNx64 per stage, 128-byte swizzle)
 //   warp 1      : TMEM allocator + single-thread tcgen05.mma issuer (UMMA 128 x BN x 16, fp32 accumulate)
 //   warps 2..9  : epilogue       (tcgen05.ld -> bias / GELU / layer-scale+residual / LayerNorm -> 16-byte global
