@@ -295,6 +295,12 @@ int vdk_vit_train_forward(const vdk_vit_net* net, const vdk_vit_tensors* params,
 /* d_feats fp32 [batch, feat_dim] -> gradients ACCUMULATED (+=) into `grads`. */
 int vdk_vit_train_backward(const vdk_vit_net* net, const vdk_vit_tensors* params, const vdk_vit_tensors* grads, const float* d_feats,
                            int batch, void* workspace, size_t workspace_bytes, void* stream);
+/* The same backward in consecutive unit ranges (0 = neck + final LayerNorm, 1..depth = blocks depth-1..0, depth+1 = cls / position /
+ * patch embedding): the DDP overlap of vdk_convnext_train_backward_range for Transformer backbones. */
+int vdk_vit_train_backward_units(const vdk_vit_net* net);
+int vdk_vit_train_backward_range(const vdk_vit_net* net, const vdk_vit_tensors* params, const vdk_vit_tensors* grads,
+                                 const float* d_feats, int batch, void* workspace, size_t workspace_bytes, void* stream, int unit_begin,
+                                 int unit_end);
 /* unit-test surface of the attention pair: forward that also saves the log2-domain log-sum-exp [batch, heads, tokens], and
  * the backward dqkv = d(attention)/d(qkv) for d_out (both [batch, tokens, heads*64] bf16). */
 int vdk_attention_fwd_lse(const void* qkv, int batch, int tokens, int heads, int head_dim, void* out, float* lse2, void* stream);

@@ -177,3 +177,27 @@ def test_vit_train_step_with_circleloss_and_fused_optimizer(lib):
     y = torch.randint(0, 10, (16,), device="cuda")
     losses = [float(trainer.step(x, y)) for _ in range(8)]
     assert all(l == l for l in losses) and losses[-1] < losses[0], losses
+
+
+def test_vit_backward_in_unit_ranges_equals_single_call(lib):
+    cfg = dict(feat_dim=64, image_size=64, patch=16, dim=128, depth=3, heads=2)
+    _, ours = build(9, **cfg)
+    ours.train()
+    torch.manual_seed(3)
+    x = torch.randn(6, 3, 64, 64, device="cuda")
+    wout = torch.randn(6, 64, device="cuda")
+    for p in ours.parameters():
+        p.grad = torch.zeros_like(p)
+    (ours(x) * wout).sum().backward()
+    one_call = {n: p.grad.clone() for n, p in ours.named_parameters()}
+    for p in ours.parameters():
+        p.grad.zero_()
+    seen = []
+    ours.grad_section_hook = lambda names: seen.extend(names)
+    (ours(x) * wout).sum().backward()
+    ours.grad_section_hook = None
+    assert sorted(seen) == sorted(n for n, _ in ours.named_parameters())
+    for n, p in ours.named_parameters():
+        a, b = p.grad, one_call[n]
+        assert (a - b).abs().max().item() <= 1e-4 * (b.abs().max().item() + 1e-6) + 1e-6, n
+

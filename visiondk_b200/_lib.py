@@ -79,6 +79,8 @@ SIGNATURES = {
     "vdk_vit_train_workspace_bytes": (_sz, [_p, _i]),
     "vdk_vit_train_forward": (_i, [_p, _p, _p, _i, C.c_float, _p, _p, _sz, _p]),
     "vdk_vit_train_backward": (_i, [_p, _p, _p, _p, _i, _p, _sz, _p]),
+    "vdk_vit_train_backward_units": (_i, [_p]),
+    "vdk_vit_train_backward_range": (_i, [_p, _p, _p, _p, _i, _p, _sz, _p, _i, _i]),
     "vdk_attention_fwd_lse": (_i, [_p, _i, _i, _i, _i, _p, _p, _p]),
     "vdk_attention_bwd": (_i, [_p, _p, _p, _p, _i, _i, _i, _i, _p, _p]),
     "vdk_vit_forward": (_i, [_p, _p, _i, _i, _p, _p, _sz, _p]),

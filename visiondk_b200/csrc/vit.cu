@@ -860,9 +860,15 @@ extern "C" int vdk_vit_train_forward(const vdk_vit_net* net, const vdk_vit_tenso
   return VDK_OK;
 }
 
-extern "C" int vdk_vit_train_backward(const vdk_vit_net* net, const vdk_vit_tensors* p, const vdk_vit_tensors* g, const float* d_feats,
-                                      int batch, void* workspace, size_t workspace_bytes, void* stream) {
+// Units of the backward in execution order: 0 = neck + final LayerNorm; 1 .. depth = blocks depth-1 .. 0; depth + 1 = cls / position /
+// patch embedding.  Consecutive ranges let the caller overlap the DDP all-reduce of finished gradients with the rest.
+extern "C" int vdk_vit_train_backward_units(const vdk_vit_net* net) { return net ? net->depth + 2 : 0; }
+
+static int vit_backward_range(const vdk_vit_net* net, const vdk_vit_tensors* p, const vdk_vit_tensors* g, const float* d_feats, int batch,
+                              void* workspace, size_t workspace_bytes, void* stream, int u_begin, int u_end) {
   VDK_REQUIRE(net && p && g && d_feats, "vdk_vit_train_backward: null argument");
+  VDK_REQUIRE(u_begin >= 0 && u_begin < u_end && u_end <= net->depth + 2, "vdk_vit_train_backward: bad unit range [%d, %d)", u_begin, u_end);
+  auto active = [&](int unit) { return unit >= u_begin && unit < u_end; };
   VitTrainLayout L;
   RC(vit_train_layout(net, batch, &L));
   VDK_REQUIRE(workspace && workspace_bytes >= L.total, "vdk_vit_train_backward: workspace too small");
@@ -875,6 +881,7 @@ extern "C" int vdk_vit_train_backward(const vdk_vit_net* net, const vdk_vit_tens
   float* slabs = F32(L.wslab);
 
   // ---- neck: BatchNorm1d (batch statistics) <- Linear <- LayerNorm(neck) <- LayerNorm(final) ----
+  if (active(0)) {
   RC(launch_bn_bwd_f32(d_feats, F32(L.z), batch, F, p->bn1_w, F32(L.bn_mean), F32(L.bn_rstd), F32(L.dz), g->bn1_w, g->bn1_b, s));
   vit_colsum_f32_kernel<<<(F + 255) / 256, 256, 0, s>>>(F32(L.dz), batch, F, g->lin_b);
   VDK_CUDA_OK(cudaGetLastError());
@@ -887,9 +894,13 @@ extern "C" int vdk_vit_train_backward(const vdk_vit_net* net, const vdk_vit_tens
   RC(launch_ln_bwd(B16(L.dy), B16(L.f2), F32(L.rf2), batch, T, 1, C, net->neck_ln_w, net->neck_ln_b, 1, B16(L.dxb), nullptr, g->neck_ln_w,
                    g->neck_ln_b, s));
   RC(launch_ln_bwd(B16(L.dxb), B16(L.f1), F32(L.rf1), batch, T, 1, C, net->norm_w, net->norm_b, 1, B16(L.dxa), nullptr, g->norm_w, g->norm_b, s));
+  }
+  // the residual-stream gradient ping-pongs between two buffers; every block swaps them twice, so it enters and leaves each
+  // block in dxa and skipped units need no bookkeeping
   size_t dx = L.dxa, dx_other = L.dxb;
   // ---- blocks ----
   for (int i = net->depth - 1; i >= 0; --i) {
+    if (!active(1 + (net->depth - 1 - i))) continue;
     const vdk_vit_block* b = &net->blocks[i];
     const vdk_vit_block_tensors* gb = &g->blocks[i];
     // MLP: x_out = x_mid + fc2(gelu(fc1(LN2(x_mid))))
@@ -916,7 +927,7 @@ extern "C" int vdk_vit_train_backward(const vdk_vit_net* net, const vdk_vit_tens
     std::swap(dx, dx_other);
   }
   // ---- cls / position embeddings, patch embedding ----
-  {
+  if (active(net->depth + 1)) {
     const int64_t tot = static_cast<int64_t>(T) * C;
     vit_assemble_bwd_kernel<<<static_cast<int>(std::min<int64_t>((tot + 255) / 256, 148 * 8)), 256, 0, s>>>(B16(dx), batch, N, C, B16(L.dtok),
                                                                                                            g->pos_embed, g->cls_token);
@@ -925,5 +936,18 @@ extern "C" int vdk_vit_train_backward(const vdk_vit_net* net, const vdk_vit_tens
     RC(G.wgrad(B16(L.dtok), B16(L.rows), g->patch_w, C, L.Kp, batch * N, C, L.Kp, slabs, true));
   }
   return VDK_OK;
+}
+
+extern "C" int vdk_vit_train_backward(const vdk_vit_net* net, const vdk_vit_tensors* p, const vdk_vit_tensors* g, const float* d_feats,
+                                      int batch, void* workspace, size_t workspace_bytes, void* stream) {
+  VDK_REQUIRE(net, "vdk_vit_train_backward: null net");
+  return vit_backward_range(net, p, g, d_feats, batch, workspace, workspace_bytes, stream, 0, net->depth + 2);
+}
+
+extern "C" int vdk_vit_train_backward_range(const vdk_vit_net* net, const vdk_vit_tensors* p, const vdk_vit_tensors* g,
+                                            const float* d_feats, int batch, void* workspace, size_t workspace_bytes, void* stream,
+                                            int unit_begin, int unit_end) {
+  VDK_REQUIRE(net, "vdk_vit_train_backward_range: null net");
+  return vit_backward_range(net, p, g, d_feats, batch, workspace, workspace_bytes, stream, unit_begin, unit_end);
 }
 

@@ -156,6 +156,27 @@ class ViTWrapper(nn.Module):
         t.bn1_running_mean, t.bn1_running_var = get("output_layer.3.running_mean"), get("output_layer.3.running_var")
         return t
 
+    def backward_sections(self):
+        """[((unit_begin, unit_end), [parameter names final after that range]), ...]: neck + final norm + the last third of the
+        blocks; the middle third; the first third + patch / cls / position embeddings — each a contiguous run of named_parameters()."""
+        d = self.model.depth
+        names = [n for n, _ in self.named_parameters()]
+
+        def blk(n):
+            return int(n.split(".")[2]) if n.startswith("model.blocks.") else None
+
+        c1, c2 = d - d // 3, d - 2 * (d // 3)  # blocks >= c1 | c2 <= blocks < c1 | blocks < c2
+        sec = [
+            ((0, 1 + (d - c1)), [n for n in names if n.startswith("output_layer.") or n.startswith("model.norm.") or
+                                 (blk(n) is not None and blk(n) >= c1)]),
+            ((1 + (d - c1), 1 + (d - c2)), [n for n in names if blk(n) is not None and c2 <= blk(n) < c1]),
+            ((1 + (d - c2), d + 2), [n for n in names if (blk(n) is not None and blk(n) < c2) or n in ("model.cls_token", "model.pos_embed")
+                                     or n.startswith("model.patch_embed.")]),
+        ]
+        if sum(len(ns) for _, ns in sec) != len(names):
+            raise RuntimeError("backward_sections: parameters not covered exactly once")
+        return [x for x in sec if x[0][0] < x[0][1] and x[1]]
+
     def _train_structs(self, device):
         m = self.model
         if self._train is None or self._train["device"] != device:
@@ -237,9 +258,18 @@ class ViTWrapper(nn.Module):
             ptrs = {n: gflat.data_ptr() + 4 * offs[n] for n, _ in plist}
         grads = self._tensors_struct(lambda n: ptrs.get(n, 0))
         dout = dout.contiguous().float()
+        hook = getattr(self, "grad_section_hook", None)
         with torch.cuda.device(dout.device):
-            _lib.check(lib.vdk_vit_train_backward(C.byref(net), C.byref(params), C.byref(grads), dout.data_ptr(), B, st["ws"].data_ptr(),
-                                                  st["ws"].numel(), _lib.stream_ptr()), "vdk_vit_train_backward")
+            if hook is not None and direct:  # DDP overlap: reduce the gradients a unit range completed while the next one runs
+                for (u0, u1), names in self.backward_sections():
+                    _lib.check(lib.vdk_vit_train_backward_range(C.byref(net), C.byref(params), C.byref(grads), dout.data_ptr(), B,
+                                                                st["ws"].data_ptr(), st["ws"].numel(), _lib.stream_ptr(), u0, u1),
+                               "vdk_vit_train_backward_range")
+                    hook(names)
+            else:
+                _lib.check(lib.vdk_vit_train_backward(C.byref(net), C.byref(params), C.byref(grads), dout.data_ptr(), B,
+                                                      st["ws"].data_ptr(), st["ws"].numel(), _lib.stream_ptr()),
+                           "vdk_vit_train_backward")
         if direct:
             return [None] * len(plist)
         return [gflat[offs[n]:offs[n] + p.numel()].view_as(p) for n, p in plist]
