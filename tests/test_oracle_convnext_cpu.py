@@ -70,3 +70,43 @@ def test_small_wrapper_runs_train_and_eval():
     m.eval()
     with torch.no_grad():
         assert m(x).shape == (4, 64)
+
+
+def test_oracle_matches_hf_convnext_model():
+    """A second independent implementation of the architecture: HF transformers' ConvNextModel (weights mapped across).  Its
+    `last_hidden_state` is the feature map BEFORE the final LayerNorm (HF normalises the pooled vector instead), i.e. the
+    input of timm's head.norm."""
+    import pytest
+    transformers = pytest.importorskip("transformers")
+    depths, dims = (1, 1, 2, 1), (32, 64, 96, 128)
+    ours = randomize_(ConvNeXt(depths, dims), seed=2).eval()
+    cfg = transformers.ConvNextConfig(num_channels=3, patch_size=4, num_stages=4, hidden_sizes=list(dims), depths=list(depths),
+                                      hidden_act="gelu", layer_norm_eps=1e-6, layer_scale_init_value=1e-6, drop_path_rate=0.0,
+                                      image_size=64)
+    hf = transformers.ConvNextModel(cfg).eval()
+    sd = {}
+    o = ours.state_dict()
+    sd["embeddings.patch_embeddings.weight"], sd["embeddings.patch_embeddings.bias"] = o["stem.0.weight"], o["stem.0.bias"]
+    sd["embeddings.layernorm.weight"], sd["embeddings.layernorm.bias"] = o["stem.1.weight"], o["stem.1.bias"]
+    for i, d in enumerate(depths):
+        if i > 0:
+            sd[f"encoder.stages.{i}.downsampling_layer.0.weight"] = o[f"stages.{i}.downsample.0.weight"]
+            sd[f"encoder.stages.{i}.downsampling_layer.0.bias"] = o[f"stages.{i}.downsample.0.bias"]
+            sd[f"encoder.stages.{i}.downsampling_layer.1.weight"] = o[f"stages.{i}.downsample.1.weight"]
+            sd[f"encoder.stages.{i}.downsampling_layer.1.bias"] = o[f"stages.{i}.downsample.1.bias"]
+        for j in range(d):
+            src, dst = f"stages.{i}.blocks.{j}", f"encoder.stages.{i}.layers.{j}"
+            sd[f"{dst}.dwconv.weight"], sd[f"{dst}.dwconv.bias"] = o[f"{src}.conv_dw.weight"], o[f"{src}.conv_dw.bias"]
+            sd[f"{dst}.layernorm.weight"], sd[f"{dst}.layernorm.bias"] = o[f"{src}.norm.weight"], o[f"{src}.norm.bias"]
+            sd[f"{dst}.pwconv1.weight"], sd[f"{dst}.pwconv1.bias"] = o[f"{src}.mlp.fc1.weight"], o[f"{src}.mlp.fc1.bias"]
+            sd[f"{dst}.pwconv2.weight"], sd[f"{dst}.pwconv2.bias"] = o[f"{src}.mlp.fc2.weight"], o[f"{src}.mlp.fc2.bias"]
+            sd[f"{dst}.layer_scale_parameter"] = o[f"{src}.gamma"]
+    missing, unexpected = hf.load_state_dict(sd, strict=False)
+    assert not unexpected and all(k.startswith("layernorm.") for k in missing), (missing, unexpected)
+    torch.manual_seed(0)
+    x = torch.randn(2, 3, 64, 64)
+    with torch.no_grad():
+        ref = hf(pixel_values=x).last_hidden_state
+        got = ours.stages(ours.stem(x))  # before head.norm
+    assert got.shape == ref.shape == (2, dims[-1], 2, 2)
+    assert (got - ref).abs().max().item() <= 2e-5 * ref.abs().max().item() + 1e-5
