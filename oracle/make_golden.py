@@ -89,6 +89,49 @@ def heads_mv():
     np.savez_compressed(os.path.join(OUT, "heads_mv.npz"), **out)
 
 
+def cbir_metrics():
+    """The reference's own CBIRMetrics / compute_metrics (engine/cbir/evaluation.py:14-224), executed from their source text (the
+    module itself cannot be imported: it pulls in faiss / timm / dataset code at import time), on a synthetic retrieval result."""
+    import ast
+    from sklearn.metrics import ndcg_score, roc_auc_score
+    src = open(os.path.join(REF, "engine/cbir/evaluation.py")).read()
+    tree = ast.parse(src)
+    ns = {"np": np, "roc_auc_score": roc_auc_score, "ndcg_score": ndcg_score}
+    for node in tree.body:
+        if (isinstance(node, ast.ClassDef) and node.name == "CBIRMetrics") or \
+           (isinstance(node, ast.FunctionDef) and node.name == "compute_metrics"):
+            exec(compile(ast.Module(body=[node], type_ignores=[]), "evaluation.py", "exec"), ns)
+    rng = np.random.default_rng(23)
+    nq, ng, k = 40, 400, 10
+    gal_label = rng.integers(0, 25, ng)                      # identity of every gallery item
+    q_label = rng.integers(0, 25, nq)
+    for c in range(25):                                      # every identity has at least two gallery items
+        gal_label[2 * c], gal_label[2 * c + 1] = c, c
+    scores = np.sort(rng.random((nq, k)).astype(np.float32), axis=1)[:, ::-1].copy()
+    scores[3, 2] = scores[3, 3] = scores[3, 4]               # tied scores: sklearn's tie-averaged DCG / AUC paths
+    scores[7, 0] = scores[7, 1]
+    ids = np.stack([rng.choice(ng, k, replace=False) for _ in range(nq)]).astype(np.int64)
+    for q in range(0, nq, 3):                                # plant some hits
+        pos = np.flatnonzero(gal_label == q_label[q])
+        ids[q, rng.integers(0, k)] = pos[0]
+        if len(pos) > 1 and pos[1] not in ids[q]:
+            ids[q, rng.integers(0, k)] = pos[1]
+    for q in range(nq):                                      # keep rows duplicate-free
+        seen, row = set(), ids[q]
+        for j in range(k):
+            while row[j] in seen:
+                row[j] = (row[j] + 1) % ng
+            seen.add(row[j])
+    names = np.array([f"gallery/{i:04d}.jpg" for i in range(ng)])
+    preds = [names[row] for row in ids]
+    labels = [list(names[np.flatnonzero(gal_label == q_label[q])]) for q in range(nq)]
+    cutoffs = [1, 3, 10]
+    metrics = ns["compute_metrics"](preds, scores, labels, metrics=["mrr", "precision", "recall", "auc", "ndcg"], cutoffs=cutoffs)
+    np.savez_compressed(os.path.join(OUT, "cbir_metrics.npz"), ids=ids, scores=scores, gal_label=gal_label, q_label=q_label,
+                        cutoffs=np.array(cutoffs), metric_names=np.array(list(metrics.keys())),
+                        metric_values=np.array([float(v) for v in metrics.values()], dtype=np.float64))
+
+
 def ema_sgd_sched():
     ema_mod = load("models/ema.py", "ref_ema")
     sched = load("engine/scheduler.py", "ref_sched")
@@ -125,5 +168,6 @@ if __name__ == "__main__":
     os.makedirs(OUT, exist_ok=True)
     heads()
     heads_mv()
+    cbir_metrics()
     ema_sgd_sched()
     print("golden vectors written to", OUT)
