@@ -132,6 +132,38 @@ def cbir_metrics():
                         metric_values=np.array([float(v) for v in metrics.values()], dtype=np.float64))
 
 
+def face_verification():
+    """The reference's own Evaluator.test_one_model / getThreshold (engine/faceX/evaluation.py:34-113: LFW-style 10-fold threshold
+    sweep over 6000 pairs), executed from its source text on synthetic unit features."""
+    import ast
+    src = open(os.path.join(REF, "engine/faceX/evaluation.py")).read()
+    ns = {"np": np, "os": os}
+    for node in ast.parse(src).body:
+        if isinstance(node, ast.ClassDef) and node.name == "Evaluator":
+            exec(compile(ast.Module(body=[node], type_ignores=[]), "evaluation.py", "exec"), ns)
+    rng = np.random.default_rng(31)
+    n_id, per_id, dim = 200, 4, 32
+    centres = rng.standard_normal((n_id, dim))
+    feats = centres[:, None, :] + 1.1 * rng.standard_normal((n_id, per_id, dim))
+    feats = (feats / np.linalg.norm(feats, axis=-1, keepdims=True)).astype(np.float32).reshape(n_id * per_id, dim)
+    names = [f"id{i // per_id:03d}/img{i % per_id}.jpg" for i in range(n_id * per_id)]
+    pairs = []
+    for fold in range(10):                      # 300 genuine + 300 impostor pairs per fold, as in the LFW protocol
+        for j in range(600):
+            a = int(rng.integers(0, n_id))
+            if j < 300:
+                i1, i2 = rng.choice(per_id, 2, replace=False)
+                pairs.append((a * per_id + i1, a * per_id + i2, 1))
+            else:
+                b = int((a + 1 + rng.integers(0, n_id - 1)) % n_id)
+                pairs.append((a * per_id + int(rng.integers(0, per_id)), b * per_id + int(rng.integers(0, per_id)), 0))
+    pair_list = [[names[a], names[b], str(l)] for a, b, l in pairs]
+    name2feat = {os.path.normpath(n): f for n, f in zip(names, feats)}
+    mean, std = ns["Evaluator"](None).test_one_model(pair_list, name2feat)
+    np.savez_compressed(os.path.join(OUT, "face_verification.npz"), feats=feats, pairs=np.array(pairs, dtype=np.int64),
+                        mean=np.float64(mean), std=np.float64(std))
+
+
 def ema_sgd_sched():
     ema_mod = load("models/ema.py", "ref_ema")
     sched = load("engine/scheduler.py", "ref_sched")
@@ -169,5 +201,6 @@ if __name__ == "__main__":
     heads()
     heads_mv()
     cbir_metrics()
+    face_verification()
     ema_sgd_sched()
     print("golden vectors written to", OUT)

@@ -50,3 +50,16 @@ def test_padding_and_error_cases():
         cbir_metrics(ids, scores, rel, n_pos, [1, 3, 10], metrics=("auc",))
     with pytest.raises(ValueError):
         cbir_metrics(ids, scores, rel, torch.zeros_like(n_pos), [1], metrics=("recall",))
+
+
+def test_face_verification_matches_the_reference_evaluator():
+    """tests/golden/face_verification.npz: mean / std produced by the reference's own Evaluator.test_one_model on 6000 synthetic
+    pairs (oracle/make_golden.py: face_verification)."""
+    from visiondk_b200.metrics import face_verification_accuracy
+    z = np.load(os.path.join(GOLD, "face_verification.npz"))
+    feats, pairs = z["feats"], z["pairs"]
+    scores = np.array([np.dot(feats[a], feats[b]) for a, b, _ in pairs], dtype=np.float32)  # the reference's np.dot per pair
+    mean, std = face_verification_accuracy(torch.from_numpy(scores), torch.from_numpy(pairs[:, 2]))
+    assert abs(mean - float(z["mean"])) <= 1e-12 and abs(std - float(z["std"])) <= 1e-12, (mean, std, float(z["mean"]), float(z["std"]))
+    with pytest.raises(ValueError):
+        face_verification_accuracy(torch.from_numpy(scores[:-1]), torch.from_numpy(pairs[:-1, 2]))

@@ -1,4 +1,5 @@
-"""CBIR metrics on tensors (the step right after top-k): MRR / Precision / Recall @cutoffs, AUC, nDCG.
+"""Evaluation metrics on tensors (the step right after top-k / pair scoring): CBIR MRR / Precision / Recall @cutoffs, AUC, nDCG, and
+the LFW-style face pair-verification accuracy (`face_verification_accuracy`, engine/faceX/evaluation.py:34-113).
 
 Replaces `CBIRMetrics` + `compute_metrics` (engine/cbir/evaluation.py:14-224), which walk Python lists of gallery PATH strings
 per query (`x in label`, `np.intersect1d`, `np.isin`) and call sklearn's `roc_auc_score` / `ndcg_score` on the host.  Here the
@@ -126,3 +127,42 @@ def cbir_metrics(ids: torch.Tensor, scores: torch.Tensor, rel: torch.Tensor, n_p
         else:
             raise ValueError(f"{m} is not supported")
     return out
+
+
+def face_verification_accuracy(scores: torch.Tensor, labels: torch.Tensor, num_thresholds: int = 1000, folds: int = 10):
+    """Evaluator.test_one_model + getThreshold (engine/faceX/evaluation.py:34-113): LFW-style verification accuracy.
+
+    `scores [N]` float32 cosine similarities of the N pairs in protocol order (N a multiple of `folds`; the reference hard-codes 600
+    pairs per fold), `labels [N]` 1 = same identity.  For every fold the threshold is chosen on the other nine — the one of
+    `num_thresholds` evenly spaced values in (min, max] of the TRAINING scores that maximises TPR - FPR (first maximum) — and the
+    held-out fold is scored with it (score > t for genuine, score < t for impostor pairs).  Returns (mean accuracy, standard
+    error of the mean with ddof = 1), computed like the reference: float32 scores, float64 thresholds.
+    All folds are evaluated at once as [folds, thresholds, pairs] comparisons on the device the scores live on."""
+    n = scores.numel()
+    if n % folds != 0:
+        raise ValueError("make sure the number of pairs is a multiple of 10 (check_nps, evaluation.py:110-113)")
+    per = n // folds
+    s32 = scores.reshape(folds, per).to(torch.float32)
+    lab = labels.reshape(folds, per).to(torch.bool)
+    dev = scores.device
+    accs = []
+    steps = torch.arange(1, num_thresholds + 1, dtype=torch.float64, device=dev)
+    for f in range(folds):
+        keep = torch.ones(folds, dtype=torch.bool, device=dev)
+        keep[f] = False
+        tr_s, tr_l = s32[keep].reshape(-1), lab[keep].reshape(-1)
+        smin, smax = tr_s.min(), tr_s.max()
+        step = ((smax - smin) / num_thresholds)                       # float32, like numpy's float32 / int
+        thr = smin.to(torch.float64) + step.to(torch.float64) * steps  # float64 thresholds
+        pos, neg = tr_s[tr_l].to(torch.float64), tr_s[~tr_l].to(torch.float64)
+        tpr = (pos[None, :] > thr[:, None]).sum(dim=1).to(torch.float64) / pos.numel()
+        fpr = (neg[None, :] > thr[:, None]).sum(dim=1).to(torch.float64) / neg.numel()
+        best = thr[torch.argmax(tpr - fpr)]
+        te_s, te_l = s32[f].to(torch.float64), lab[f]
+        correct = (te_s[te_l] > best).sum() + (te_s[~te_l] < best).sum()
+        accs.append(correct.to(torch.float64) / per)
+    acc = torch.stack(accs)
+    mean = acc.mean()
+    std = acc.std(unbiased=True) / (folds ** 0.5)
+    return float(mean.item()), float(std.item())
+
