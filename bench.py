@@ -53,6 +53,7 @@ def parse():
     ap.add_argument("--ng", type=int, default=NG)
     ap.add_argument("--k", type=int, default=K)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-parity", action="store_true", help="skip the oracle parity check of the retrieval leg")
     ap.add_argument("--train-batch", type=int, default=128)
     ap.add_argument("--only", default="all", choices=["all", "both", "train", "extract", "retrieval"])
     return ap.parse_args()
@@ -605,7 +606,7 @@ def bench_retrieval(ctx, args):
     import ctypes as C
     import torch
     from visiondk_b200 import _lib, sharding
-    from visiondk_b200.retrieval import FlatIPIndex, PreparedRows, merge_topk
+    from visiondk_b200.retrieval import FlatIPIndex, PreparedRows, sharded_flat_search
     lib = _lib.load()
     nq, ng, dim, k = args.nq, args.ng, DIM, args.k
     lo, hi = sharding.shard_bounds(ng, ctx.world, ctx.rank)
@@ -629,11 +630,34 @@ def bench_retrieval(ctx, args):
     q_local = q_full[q_lo:q_hi].contiguous()
 
     def step_dev():
-        return sharding.sharded_search(q_local, q_sizes, index.search_device, merge_topk, k)
+        return sharded_flat_search(index, q_local, q_sizes, k)
 
     ms = timed(ctx, step_dev, args.steps, args.warmup)
     index.check_status()
     value = nq * ng / (ms * 1e-3)
+
+    # parity check, outside the timed region: 64 sampled query rows of THIS search (single GPU or sharded) against the
+    # oracle's exact top-k over the whole gallery, ids and canonical scores bit for bit
+    got_s, got_i = step_dev()
+    parity = None
+    if not args.no_parity:
+        sample = torch.arange(0, nq, max(1, nq // 64), device=ctx.dev)[:64]
+        if ctx.rank == 0:
+            import numpy as np
+            from oracle import retrieval as oret  # the checker (never the thing measured)
+            gen2 = torch.Generator(device=ctx.dev).manual_seed(5)
+            g_host = torch.cat([torch.nn.functional.normalize(torch.randn(min(ng, a + 125000) - a, dim, device=ctx.dev, generator=gen2)).cpu()
+                                for a in range(0, ng, 125000)]).numpy()
+            t0 = time.perf_counter()
+            ref_s, ref_i = oret.flat_ip_search_candidates(oret.l2_normalize(q_full[sample].cpu().numpy()), oret.l2_normalize(g_host), k)
+            ids_ok = bool(np.array_equal(got_i[sample].cpu().numpy(), ref_i))
+            sc_ok = bool(np.array_equal(got_s[sample].cpu().numpy().view(np.uint32), ref_s.view(np.uint32)))
+            parity = {"rows_checked": int(sample.numel()), "ids_bit_exact": ids_ok, "scores_bit_exact": sc_ok,
+                      "against": "oracle.retrieval.flat_ip_search_candidates over the full gallery", "path": f"{ctx.world} shard(s)",
+                      "oracle_seconds": round(time.perf_counter() - t0, 1)}
+            del g_host
+            if not (ids_ok and sc_ok):
+                raise SystemExit(f"bench.py: retrieval parity check FAILED {parity}")
 
     q_host = torch.empty((nq, dim), dtype=torch.float32).pin_memory()
     q_host.copy_(q_full.cpu())
@@ -642,7 +666,7 @@ def bench_retrieval(ctx, args):
 
     def step_e2e():
         qd = q_host[q_lo:q_hi].to(ctx.dev, non_blocking=True)
-        s, i = sharding.sharded_search(qd, q_sizes, index.search_device, merge_topk, k)
+        s, i = sharded_flat_search(index, qd, q_sizes, k)
         if ctx.rank == 0:
             s_host.copy_(s, non_blocking=True)
             i_host.copy_(i, non_blocking=True)
@@ -687,8 +711,8 @@ def bench_retrieval(ctx, args):
                 "whole_step": {"achieved": 2.0 * dim * nq * ngl / (ms * 1e-3) / 1e12,
                                "frac": 2.0 * dim * nq * ngl / (ms * 1e-3) / 1e12 / peak,
                                "note": "2*D FLOP per pair over the whole search (all ranges, select, re-rank)"}}
-    launches = 2 + 2 * plan.n_stages + 1 + (1 if ctx.world > 1 else 0)
-    return {"value": value, "ms": ms, "e2e_ms": e2e_ms, "roofline": roof, "launches_per_step": launches,
+    launches = 2 + 2 * plan.n_stages + 1 + (3 if ctx.world > 1 else 0)  # + rows_prepare of gathered queries is in the 2; pack, merge
+    return {"value": value, "ms": ms, "e2e_ms": e2e_ms, "roofline": roof, "launches_per_step": launches, "parity_check": parity,
             "h2d": nq * dim * 4, "d2h": nq * k * 12}
 
 
@@ -751,7 +775,8 @@ def main():
                 "config": {"workload": f"{args.nq} queries x {args.ng} gallery x {DIM}-d, cosine top-{args.k}, gallery "
                                        f"sharded by rows over {ctx.world} GPU(s)",
                            "l2": "gallery (fp16 1.0 GB + fp32 2.0 GB per 1M rows) exceeds the 126 MB L2; no flush needed",
-                           "exactness": "ids and scores bit-exact vs oracle/retrieval.py"},
+                           "exactness": "see parity_check: sampled rows of this very search vs the oracle, bit for bit"},
+                "parity_check": rt["parity_check"],
                 "e2e": {"value": args.nq * args.ng / (rt["e2e_ms"] * 1e-3), "unit": "pairs/s", "ms_per_step": rt["e2e_ms"],
                         "h2d_bytes_per_step": rt["h2d"], "d2h_bytes_per_step": rt["d2h"]},
                 "gpu_launches": rt["launches_per_step"] * args.steps,

@@ -18,6 +18,8 @@ import time
 import torch
 import yaml
 
+from engine.cbir.evaluation import compute_metrics
+from engine.synthetic import SyntheticFaceData, is_synthetic
 from visiondk_b200.backbone import BackboneFactory
 from visiondk_b200.cbir import FeatureExtractor, index, search
 
@@ -35,7 +37,7 @@ class SyntheticImages:
             yield torch.randn(b, 3, self.size, self.size, device=self.device, generator=gen)
 
 
-def main():
+def main(argv=None):
     ap = argparse.ArgumentParser()
     ap.add_argument("--cfgs", default="configs/faceX/cbir_convnext_b200.yaml")
     ap.add_argument("--weight", default=None, help="Epoch_N.pt written by the trainer (keys 'state_dict' / 'ema')")
@@ -44,7 +46,7 @@ def main():
     ap.add_argument("--queries", type=int, default=1000)
     ap.add_argument("--k", type=int, default=10)
     ap.add_argument("--device", default="cuda:0")
-    opt = ap.parse_args()
+    opt = ap.parse_args(argv)
 
     with open(opt.cfgs, errors="ignore") as f:
         cfgs = yaml.safe_load(f)
@@ -57,16 +59,31 @@ def main():
     extractor = FeatureExtractor(model)
     size, bs = model_cfg["image_size"], data_cfg["val"]["bs"]
 
+    root = str(data_cfg["root"])
+    if is_synthetic(root):  # identity-structured synthetic images: the metrics below mean something
+        data = SyntheticFaceData(root, size, bs, device)
+        gallery, queries = data.gallery_batches(opt.gallery), data.query_batches(opt.queries)
+        g_label, q_label = data.gallery_labels(opt.gallery), data.query_labels(opt.queries)
+    else:
+        gallery, queries = SyntheticImages(opt.gallery, bs, size, device, 1), SyntheticImages(opt.queries, bs, size, device, 2)
+        g_label = q_label = None
     t0 = time.perf_counter()
-    faiss_index = index(extractor, SyntheticImages(opt.gallery, bs, size, device, 1), device)
+    faiss_index = index(extractor, gallery, device)
     torch.cuda.synchronize()
     t1 = time.perf_counter()
-    scores, indices = search(extractor, SyntheticImages(opt.queries, bs, size, device, 2), faiss_index, device, k=opt.k)
+    scores, indices = search(extractor, queries, faiss_index, device, k=opt.k)
     t2 = time.perf_counter()
+    n_q = scores.shape[0]
     print(f"indexed {faiss_index.ntotal} gallery images in {t1 - t0:.2f} s "
-          f"({opt.gallery / (t1 - t0):.0f} embeddings/s incl. synthetic image generation)")
-    print(f"searched {opt.queries} queries (k={opt.k}) in {t2 - t1:.3f} s; top-1 scores mean {scores[:, 0].mean():.4f}")
+          f"({faiss_index.ntotal / (t1 - t0):.0f} embeddings/s incl. synthetic image generation)")
+    print(f"searched {n_q} queries (k={opt.k}) in {t2 - t1:.3f} s; top-1 scores mean {scores[:, 0].mean():.4f}")
     print("status", faiss_index.check_status())
+    if g_label is not None:  # cbir_eval.py:124-199 `evaluate`: metrics at the config's cutoffs (capped at k)
+        cutoffs = [c for c in data_cfg["val"]["metrics"]["cutoffs"] if c <= opt.k] or [opt.k]
+        m = compute_metrics(torch.from_numpy(indices).to(device), torch.from_numpy(scores).to(device), q_label, g_label,
+                            metrics=data_cfg["val"]["metrics"]["metrics"], cutoffs=cutoffs)
+        print({k_: round(float(v), 6) for k_, v in m.items()})
+        return m
 
 
 if __name__ == "__main__":

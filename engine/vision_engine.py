@@ -1,8 +1,8 @@
 """Orchestrator of the faceX / CBIR embedding path on B200 — the surface of the reference's
 engine/vision_engine.py (yaml_load :35-38, increment_path :41-57, CenterProcessor.__init__ :67-167,
 run_embedding :438-560) over the visiondk_b200 kernels.  Written from scratch: model / step / eval come from
-visiondk_b200.{train,cbir}; datasets are out of the hot-path scope, so `data.root` must be a synthetic:// URL (device-
-resident random images with labels) or the caller passes its own iterables of (images[B,3,S,S], labels[B]).
+visiondk_b200.{train,cbir} and engine.cbir.evaluation; the dataset layer is out of the hot-path scope, so `data.root`
+is a synthetic:// URL (engine/synthetic.py) or the caller drives FaceTrainer with its own (images, labels) iterables.
 """
 from __future__ import annotations
 
@@ -11,13 +11,14 @@ import os
 import re
 import time
 from pathlib import Path
-from typing import Iterable, Optional
-from urllib.parse import parse_qs, urlparse
+from typing import Optional
 
 import torch
+import torch.distributed as dist
 import yaml
 
-from visiondk_b200.cbir import FeatureExtractor, index, search
+from engine.cbir.evaluation import valuate as valuate_cbir
+from engine.synthetic import SyntheticFaceData, is_synthetic
 from visiondk_b200.train import FaceTrainer, FaceTrainingModel
 
 
@@ -39,28 +40,53 @@ def increment_path(path, exist_ok=False, sep="", mkdir=False):
     return path
 
 
-class SyntheticFaceData:
-    """`synthetic://cbir?ids=1000&per_id=100&queries=1000`: seeded random images generated on the device."""
-
-    def __init__(self, url: str, image_size: int, batch: int, device, rank: int = 0, world: int = 1):
-        q = parse_qs(urlparse(url).query)
-        self.ids, self.per_id = int(q.get("ids", ["1000"])[0]), int(q.get("per_id", ["100"])[0])
-        self.queries = int(q.get("queries", ["1000"])[0])
-        self.size, self.batch, self.device, self.rank, self.world = image_size, batch, device, rank, world
-
-    def __len__(self):  # batches per epoch and rank (DistributedSampler semantics, drop_last)
-        return (self.ids * self.per_id) // (self.batch * self.world)
-
-    def train_batches(self, epoch: int) -> Iterable:
-        gen = torch.Generator(device=self.device).manual_seed(1000 * epoch + self.rank)  # sampler.set_epoch equivalent
-        for _ in range(len(self)):
-            yield (torch.randn(self.batch, 3, self.size, self.size, device=self.device, generator=gen),
-                   torch.randint(0, self.ids, (self.batch,), device=self.device, generator=gen))
-
-    def images(self, n: int, seed: int) -> Iterable:
-        gen = torch.Generator(device=self.device).manual_seed(seed)
-        for a in range(0, n, self.batch):
-            yield torch.randn(min(self.batch, n - a), 3, self.size, self.size, device=self.device, generator=gen)
+def check(task: str, cfgs: dict) -> None:
+    """utils/checks.py:225-229 for the two embedding tasks: the schema the reference's configs/faceX/{face,cbir}.yaml follow
+    (model{task,image_size,load_from,backbone{timm-<name>:{...}},head{<kind>:{feat_dim,num_class,...}}}, data{root,nw,train,val},
+    hyp{...}) and its asserts (:111-143: the head's num_class equals the number of training identities; one backbone, one
+    head; CE loss).  Raises ValueError / AssertionError with the reference's wording."""
+    if task not in ("face", "cbir"):
+        raise ValueError(f"{task} is not supported")
+    for sec in ("model", "data", "hyp"):
+        if sec not in cfgs:
+            raise ValueError(f"Configuration error: missing top-level section '{sec}'")
+    model_cfg, data_cfg, hyp_cfg = cfgs["model"], cfgs["data"], cfgs["hyp"]
+    if model_cfg.get("task") != task:
+        raise ValueError(f"Configuration error: model.task is {model_cfg.get('task')!r}, expected {task!r}")
+    for sec, keys in ((model_cfg, ("image_size", "backbone", "head")), (data_cfg, ("root", "train", "val")),
+                      (hyp_cfg, ("epochs", "lr0", "momentum", "weight_decay", "warmup_momentum", "warm_ep", "optimizer", "scheduler"))):
+        for k in keys:
+            if k not in sec:
+                raise ValueError(f"Configuration error: missing key '{k}'")
+    if len(model_cfg["backbone"]) != 1 or len(model_cfg["head"]) != 1:
+        raise ValueError("Model configuration error: exactly one backbone and one head must be configured")
+    backbone_key = next(iter(model_cfg["backbone"]))
+    if backbone_key.split("-")[0] != "timm":
+        raise ValueError("Model name error: Format should be [timm-ModelName] for timm models")
+    bb = model_cfg["backbone"][backbone_key]
+    head_key = next(iter(model_cfg["head"]))
+    head = model_cfg["head"][head_key]
+    if bb["feat_dim"] != head["feat_dim"]:
+        raise ValueError("Model configuration error: backbone feat_dim and head feat_dim differ")
+    if bb.get("image_size", model_cfg["image_size"]) != model_cfg["image_size"]:
+        raise ValueError("Model configuration error: backbone image_size differs from model.image_size")
+    loss = hyp_cfg.get("loss", {"ce": True})
+    if not loss.get("ce", False):
+        raise ValueError("Loss configuration error: the face / cbir tasks train with CE (hyp.loss.ce: true)")
+    root = str(data_cfg["root"])
+    if is_synthetic(root):
+        num_classes = SyntheticFaceData(root, model_cfg["image_size"], 1, "cpu").num_classes
+    elif os.path.isdir(root):
+        train_dir = Path(root) / "train"
+        if not train_dir.is_dir():
+            raise ValueError(f"Training data error: {train_dir} not found")
+        num_classes = len([x for x in os.listdir(train_dir) if not (x.startswith(".") or x.startswith("_"))])
+    else:
+        raise ValueError(f"Dataset loading error: {root} is neither a synthetic:// URL nor a local directory "
+                         "(HuggingFace hub datasets need a network, which the B200 box does not have)")
+    model_classes = head["num_class"]
+    assert model_classes == num_classes, \
+        f"Model configuration error: Number of classes mismatch. Expected {num_classes} from dataset, but got {model_classes} in model configuration"
 
 
 class CenterProcessor:
@@ -75,11 +101,16 @@ class CenterProcessor:
         self.device = torch.device("cuda", max(rank, 0))
         torch.cuda.set_device(self.device)
         self.world = int(os.environ.get("WORLD_SIZE", "1")) if rank != -1 else 1
+        if getattr(opt, "sync_bn", False) and self.world > 1:
+            # main.py:57-60 -> vision_engine.py:224-225 converts the neck's two BatchNorms to SyncBatchNorm.  The B200 neck
+            # kernels normalise with the LOCAL batch statistics; silently ignoring the flag would train a different model.
+            raise NotImplementedError("--sync_bn with WORLD_SIZE > 1: cross-rank BatchNorm statistics are not built for the "
+                                      "B200 neck kernels (they use per-rank batch statistics); drop the flag")
         self.model = FaceTrainingModel(self.model_cfg).to(self.device)
         root = str(self.data_cfg["root"])
-        if not root.startswith("synthetic://"):
+        if not is_synthetic(root):
             raise NotImplementedError("dataset loading is outside the B200 hot-path scope: use a synthetic:// root or drive "
-                                      "FaceTrainer / visiondk_b200.cbir with your own (images, labels) iterables")
+                                      "FaceTrainer / engine.cbir.evaluation with your own (images, labels) iterables")
         self.data = SyntheticFaceData(root, self.model_cfg["image_size"], self.data_cfg["train"]["bs"], self.device,
                                       max(rank, 0), self.world)
 
@@ -87,21 +118,48 @@ class CenterProcessor:
         if self.rank in (-1, 0):
             print(msg, flush=True)
 
+    # ---- fine-tune / resume (vision_engine.py:444-454, :494-507) -------------------------------------------------------
+    def _load_from(self, path: str):
+        state = torch.load(path, map_location="cpu", weights_only=False)
+        state = state["ema"] if "ema" in state else state["model_state_dict"]
+        missing, unexpected = self.model.trainingwrapper["backbone"].load_state_dict(state, strict=False)
+        self.log(f"load_from: {path}")
+        self.log(f"Missing keys: {missing}")
+        self.log(f"Unexpected keys: {unexpected}")
+
+    def _resume(self, trainer: FaceTrainer, path: str) -> int:
+        """Restores everything the reference's checkpoint carries (:494-507: model, EMA + `updates`, optimizer, scheduler) and
+        what it forgets (the head's class weights are not in its `state_dict` entry): backbone + head weights, EMA copies,
+        momentum buffers, step counters, the position in the LR schedule and the post-warm-up momentum."""
+        ckpt = torch.load(path, map_location="cpu", weights_only=False)
+        wrap = self.model.trainingwrapper
+        wrap["backbone"].load_state_dict(ckpt["state_dict"], strict=True)  # in place: the parameters live in the flat buffers
+        if "head" in ckpt:
+            wrap["head"].load_state_dict(ckpt["head"], strict=True)
+        if trainer.ema is not None:
+            trainer.ema.trainingwrapper["backbone"].load_state_dict(ckpt["ema"], strict=True)
+            if "ema_head" in ckpt:
+                trainer.ema.trainingwrapper["head"].load_state_dict(ckpt["ema_head"], strict=True)
+        trainer.load_state_dict({"optimizer": ckpt["optimizer"], "scheduler": ckpt["scheduler"], "updates": ckpt["updates"]})
+        start_epoch = ckpt["epoch"] + 1
+        if start_epoch > self.hyp_cfg["warm_ep"]:  # the `epoch == warm_ep` switch below has already happened
+            trainer.set_momentum(self.hyp_cfg["momentum"])
+        self.log(f"resume: {path}")
+        return start_epoch
+
     def run_embedding(self, resume: Optional[str] = None):
         hyp = self.hyp_cfg
         steps_per_epoch = len(self.data)
         name, layer_wise = hyp["optimizer"][0], bool(hyp["optimizer"][1])
         if name != "sgd" or hyp["scheduler"] != "cosine_with_warm":
             raise NotImplementedError("the B200 step implements sgd + cosine_with_warm (the faceX / cbir configs)")
+        if self.model_cfg.get("load_from"):
+            self._load_from(self.model_cfg["load_from"])
         trainer = FaceTrainer(self.model, lr0=hyp["lr0"], momentum=hyp["warmup_momentum"], weight_decay=hyp["weight_decay"],
                               label_smooth=hyp.get("label_smooth", 0.0), layer_wise=layer_wise,
                               warm_steps=hyp["warm_ep"] * steps_per_epoch, total_steps=hyp["epochs"] * steps_per_epoch,
                               lrf_ratio=hyp.get("lrf_ratio"), use_ema=self.rank in (-1, 0))
-        start_epoch = 0
-        if resume:
-            ckpt = torch.load(resume, map_location="cpu", weights_only=False)
-            self.model.trainingwrapper["backbone"].load_state_dict(ckpt["state_dict"], strict=True)
-            start_epoch = ckpt["epoch"] + 1
+        start_epoch = self._resume(trainer, resume) if resume else 0
         t0 = time.time()
         save_freq = getattr(self.opt, "save_freq", 1) if self.opt else 1
         print_freq = getattr(self.opt, "print_freq", 50) if self.opt else 50
@@ -120,19 +178,29 @@ class CenterProcessor:
             if self.rank in (-1, 0) and (epoch + 1) % save_freq == 0:
                 self.save_and_eval(trainer, epoch, steps_per_epoch)
         self.log(f"Training complete ({(time.time() - t0) / 3600:.3f} hours)")
+        return trainer
 
     def save_and_eval(self, trainer: FaceTrainer, epoch: int, steps_per_epoch: int):
-        ema_backbone = trainer.ema.trainingwrapper["backbone"] if trainer.ema is not None else self.model.trainingwrapper["backbone"]
-        ext = FeatureExtractor(ema_backbone)
-        k = self.data_cfg["val"]["metrics"]["cutoffs"][-1]
-        idx = index(ext, self.data.images(min(self.data.ids * self.data.per_id, 4096), 11), self.device)
-        scores, ids = search(ext, self.data.images(min(self.data.queries, 256), 12), idx, self.device, k=k)
-        fitness = {"fitness": {"top1_score_mean": float(scores[:, 0].mean())}, "checkpoint": f"Epoch_{epoch + 1}.pt"}
+        """engine/procedure/train.py:244-278: evaluate the EMA backbone (valuate_cbir -> {metric: float}), write Epoch_N.pt with
+        the reference's key set, plus the entries a faithful resume needs ('head', 'ema_head', momentum buffers)."""
+        src = trainer.ema if trainer.ema is not None else self.model
+        ema_backbone = src.trainingwrapper["backbone"]
+        metrics = valuate_cbir(ema_backbone, self.data_cfg, self.device, None, image_size=self.model_cfg["image_size"],
+                               gallery_limit=getattr(self.opt, "eval_gallery", None) or 4096,
+                               query_limit=getattr(self.opt, "eval_queries", None) or 256)
+        fitness = {"fitness": metrics, "checkpoint": f"Epoch_{epoch + 1}.pt"}
         out_dir = Path(self.project or "run/exp")
         out_dir.mkdir(parents=True, exist_ok=True)
+        wrap = self.model.trainingwrapper
+        state = trainer.state_dict()
+
+        def host(sd):  # parameters are views into the optimizer's flat buffers: save compact per-tensor copies
+            return {k: v.detach().cpu().clone() for k, v in sd.items()}
+
         ckpt = {"epoch": epoch, "batch_id": steps_per_epoch - 1, "fitness": fitness,
-                "state_dict": self.model.trainingwrapper["backbone"].state_dict(), "ema": ema_backbone.state_dict(),
-                "updates": trainer.opt.updates, "optimizer": {"steps": trainer.opt.steps, "param_groups": trainer.opt.param_groups},
-                "scheduler": {"step": trainer.sched_step}}
+                "state_dict": host(wrap["backbone"].state_dict()), "ema": host(ema_backbone.state_dict()),
+                "head": host(wrap["head"].state_dict()), "ema_head": host(src.trainingwrapper["head"].state_dict()),
+                "updates": state["updates"], "optimizer": state["optimizer"], "scheduler": state["scheduler"]}
         torch.save(ckpt, out_dir / f"Epoch_{epoch + 1}.pt")
         self.log(str(fitness))
+        return fitness

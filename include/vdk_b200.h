@@ -405,6 +405,16 @@ int vdk_ip_topk(const vdk_topk_plan* plan, const float* q32, const void* qh, con
 int vdk_topk_row_flags(const vdk_topk_plan* plan, const void* workspace, size_t workspace_bytes,
                        const int32_t** row_flags);
 
+/* Exhaustive exact top-k for a FEW queries: canonical scores against every gallery row, exact selection on
+ * (score desc, id asc) keys.  No candidate capacity, so it cannot overflow: the last resort for queries flagged by
+ * vdk_ip_topk even under an all-dense plan (thousands of exact duplicates of a top-k member) — faiss' flat search
+ * (engine/cbir/evaluation.py:193) answers such queries, so this path must too.  q32: fp32 [n_query, dim] (already
+ * normalised if the index is a cosine index).  workspace >= vdk_ip_topk_exhaustive_workspace_bytes(n_gallery). */
+size_t vdk_ip_topk_exhaustive_workspace_bytes(int64_t n_gallery);
+int vdk_ip_topk_exhaustive(const float* q32, int64_t n_query, const float* g32, int64_t n_gallery, int dim, int k,
+                           int64_t id_offset, float* out_scores, int64_t* out_ids, void* workspace, size_t workspace_bytes,
+                           void* stream);
+
 /* Measurement hook: launches ONLY the score/filter kernel of vdk_ip_topk for gallery rows [lo, hi), reusing the
  * thresholds a previous vdk_ip_topk left in `workspace` (dense != 0: the threshold-free first-range variant).
  * bench.py brackets this call with CUDA events to time the dominant kernel in isolation. */
@@ -419,6 +429,14 @@ int vdk_reduce_max(const float* x, int64_t n, float* out, void* stream);
  * engine/cbir/evaluation.py:159-162; sharding is BASELINE config 4). */
 int vdk_topk_merge(const float* scores, const int64_t* ids, int n_lists, int64_t n_query, int k, float* out_scores,
                    int64_t* out_ids, void* stream);
+
+/* The exchange format of the sharded search: one 64-bit word per list entry, (fp32 score bits << 32) | uint32 id
+ * (id -1, the padding, becomes 0xffffffff; global ids must therefore stay below 2^32 - 1), so that the ranks' lists travel in
+ * ONE all-gather.  vdk_topk_pack: (scores, ids)[n] -> packed[n].  vdk_topk_merge_packed: packed [n_lists, n_query, k] ->
+ * global top-k, same rule as vdk_topk_merge. */
+int vdk_topk_pack(const float* scores, const int64_t* ids, int64_t n, void* packed, void* stream);
+int vdk_topk_merge_packed(const void* packed, int n_lists, int64_t n_query, int k, float* out_scores, int64_t* out_ids,
+                          void* stream);
 
 /* Brute-force canonical scores for verification at full size: out[i] = canonical_score(q[qi[i]], g[gi[i]]). */
 int vdk_ip_exact_pairs(const float* q32, const float* g32, int dim, const int64_t* qi, const int64_t* gi, int64_t n,

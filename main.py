@@ -14,7 +14,7 @@ from pathlib import Path
 import torch
 import torch.distributed as dist
 
-from engine.vision_engine import CenterProcessor, increment_path, yaml_load
+from engine.vision_engine import CenterProcessor, check, increment_path, yaml_load
 
 LOCAL_RANK = int(os.getenv("LOCAL_RANK", -1))
 WORLD_SIZE = int(os.getenv("WORLD_SIZE", 1))
@@ -24,7 +24,7 @@ def parse_opt():
     ap = argparse.ArgumentParser()
     ap.add_argument("--cfgs", default="configs/faceX/cbir_convnext_b200.yaml")
     ap.add_argument("--resume", default="")
-    ap.add_argument("--sync_bn", action="store_true", help="accepted for compatibility; the neck BN uses local batch statistics")
+    ap.add_argument("--sync_bn", action="store_true", help="SyncBatchNorm for the neck (vision_engine.py:224-225); a no-op on one rank, refused on several")
     ap.add_argument("--project", default="run")
     ap.add_argument("--name", default="exp")
     ap.add_argument("--local_rank", type=int, default=-1)
@@ -39,6 +39,7 @@ def main(opt):
         assert torch.cuda.device_count() > LOCAL_RANK, "not enough CUDA devices for this rank"
         dist.init_process_group(backend="nccl", world_size=WORLD_SIZE, rank=LOCAL_RANK)
     cfgs = yaml_load(opt.cfgs)
+    check(cfgs["model"]["task"], cfgs)  # utils/checks.py:225-229
     if LOCAL_RANK in (-1, 0):
         save_dir.mkdir(parents=True, exist_ok=True)
         shutil.copy(opt.cfgs, save_dir)

@@ -4,7 +4,7 @@
 
 The reference package cannot be imported as a whole (timm / faiss / torchmetrics are not installed), so the
 torch-only files are loaded by path: models/faceX/head/{arcface,circleloss}.py, models/losses/loss.py,
-models/ema.py, engine/scheduler.py, engine/optimizer.py.  The committed .npz files are what the CPU tests
+models/ema.py, engine/scheduler.py, engine/optimizer.py, and models/faceX/backbone/timm_wrapper.py (the neck) around a stub `timm`.  The committed .npz files are what the CPU tests
 hold oracle/ to; the GPU tests then hold the CUDA kernels to oracle/.
 """
 from __future__ import annotations
@@ -164,6 +164,71 @@ def face_verification():
                         mean=np.float64(mean), std=np.float64(std))
 
 
+def neck():
+    """The reference's OWN models/faceX/backbone/timm_wrapper.py (constructor logic, both neck branches, forward) executed
+    around a stub `timm` module: `timm.create_model(name, pretrained=..., num_classes=0, global_pool='')` hands back the
+    oracle's toy ConvNeXt / ViT body (timm itself is not installed: the body is the unpinned part, the wrapper and its
+    BatchNorm2d/LayerNorm -> Flatten -> Linear -> BatchNorm1d neck are the reference's code, pinned here).  Stored: the
+    wrapper's state_dict keys as the reference names them, the neck's tensors (the body is rebuilt from its seed), a batch, the body's feature map, the embeddings in eval mode, and in
+    train mode the embeddings, the updated BatchNorm running statistics and the gradients of every neck parameter and of
+    the feature map for loss = sum(out * w_out)."""
+    import types
+    sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+    from oracle.convnext import ConvNeXt, randomize_ as rand_cnx
+    from oracle.vit import VisionTransformer, randomize_ as rand_vit
+    calls = []
+
+    def create_model(name, pretrained=False, num_classes=None, global_pool=None, **kw):
+        calls.append((name, pretrained, num_classes, global_pool))
+        assert num_classes == 0 and global_pool == "", "timm_wrapper.py:16-21 asks for the un-pooled, head-less body"
+        if name == "convnext_toy":
+            return ConvNeXt((1, 1, 2, 1), (64, 128, 128, 256))
+        if name == "vit_toy":
+            return VisionTransformer(64, 16, 128, 2, 2)
+        raise ValueError(name)
+
+    stub = types.ModuleType("timm")
+    stub.create_model = create_model
+    sys.modules["timm"] = stub
+    try:
+        ref = load("models/faceX/backbone/timm_wrapper.py", "ref_timm_wrapper")
+    finally:
+        del sys.modules["timm"]
+    out = {}
+    torch.manual_seed(41)
+    x = torch.randn(6, 3, 64, 64)
+    out["x"] = x.numpy()
+    for tag, name, rand, seed in (("cnn", "convnext_toy", rand_cnx, 51), ("vit", "vit_toy", rand_vit, 52)):
+        w = ref.TimmWrapper(name, feat_dim=64, image_size=64, pretrained=False)
+        rand(w, seed=seed)
+        sd = {k: v.detach().clone() for k, v in w.state_dict().items()}
+        out[f"{tag}_keys"] = np.array(list(sd.keys()))
+        out[f"{tag}_seed"] = np.int32(seed)  # the body is rebuilt from oracle.*.randomize_(wrapper, seed): deterministic
+        out[f"{tag}_body_abs_sum"] = np.float64(sum(v.double().abs().sum().item() for k, v in sd.items() if k.startswith("model.")))
+        for k, v in sd.items():
+            if k.startswith("output_layer."):
+                out[f"{tag}_sd/{k}"] = v.numpy()
+        w.eval()
+        with torch.no_grad():
+            out[f"{tag}_feat"] = w.model(x).numpy()
+            out[f"{tag}_eval"] = w(x).numpy()
+        w.train()
+        feat = w.model(x).detach().requires_grad_(True)
+        y = w.output_layer(feat)
+        g = torch.Generator().manual_seed(61)
+        w_out = torch.randn(y.shape, generator=g)
+        (y * w_out).sum().backward()
+        out[f"{tag}_train"] = y.detach().numpy()
+        out[f"{tag}_w_out"] = w_out.numpy()
+        out[f"{tag}_dfeat"] = feat.grad.numpy()
+        for k, p_ in w.output_layer.named_parameters():
+            out[f"{tag}_grad/output_layer.{k}"] = p_.grad.numpy()
+        for k, b in w.output_layer.named_buffers():
+            out[f"{tag}_after/output_layer.{k}"] = b.detach().numpy()
+    assert [c[0] for c in calls] == ["convnext_toy", "vit_toy"]
+    np.savez_compressed(os.path.join(OUT, "neck_ref.npz"), **out)
+
+
 def ema_sgd_sched():
     ema_mod = load("models/ema.py", "ref_ema")
     sched = load("engine/scheduler.py", "ref_sched")
@@ -203,4 +268,5 @@ if __name__ == "__main__":
     cbir_metrics()
     face_verification()
     ema_sgd_sched()
+    neck()
     print("golden vectors written to", OUT)

@@ -174,6 +174,26 @@ def test_topk_full_size_properties(lib):
     top = full.topk(k, dim=1).indices
     agree = (top == i[rows]).float().mean().item()
     assert agree > 0.999, f"sampled brute-force agreement {agree} ({info})"
+    # BIT-EXACT against the oracle on 80 sampled query rows of the same gallery (ids and canonical scores): a dropped
+    # true top-k member anywhere in these rows fails the test
+    sample = np.arange(0, nq, 125)
+    g_host, q_host = g.cpu().numpy(), q[torch.from_numpy(sample).cuda()].cpu().numpy()
+    ref_s, ref_i = R.flat_ip_search_candidates(q_host, g_host, k)
+    assert_same(s[sample].cpu().numpy(), i[sample].cpu().numpy(), ref_s, ref_i, f"full-size sampled rows ({info})")
+    # the sharded path at full size: 8 row shards searched separately and merged (what 8 GPUs do) equals the unsharded
+    # result bit for bit on EVERY row, hence the oracle on the sampled ones
+    ss, ii = [], []
+    for r in range(8):
+        lo, hi = ng * r // 8, ng * (r + 1) // 8
+        shard = FlatIPIndex(dim, "cuda", id_offset=lo)
+        shard.add(g[lo:hi])
+        s_, i_ = shard.search_device(q, k)
+        shard.check_status()
+        ss.append(s_)
+        ii.append(i_)
+        del shard
+    ms, mi = merge_topk(torch.stack(ss), torch.stack(ii), k)
+    assert torch.equal(mi, i) and torch.equal(ms.view(torch.int32), s.view(torch.int32))
 
 
 def test_adversarially_ordered_gallery_takes_the_wide_path(lib):
@@ -198,13 +218,46 @@ def test_adversarially_ordered_gallery_takes_the_wide_path(lib):
         idx.check_status()
 
 
-def test_massive_duplicates_fail_loudly(lib):
+def test_massive_duplicates_take_the_exhaustive_path(lib):
+    """5000 exact copies of one row: more ties than any carry list holds, on the wide path too.  faiss' flat search
+    (engine/cbir/evaluation.py:193) answers such a gallery, so the index must as well: the flagged queries are scored
+    against every row canonically and selected exactly (score desc, id asc) — the oracle's answer, bit for bit."""
+    rng = np.random.default_rng(5)
     v = unit_rows(1, 64, 1)
-    g = np.repeat(v, 5000, axis=0)  # 5000 exact ties: more than carry_capacity
+    g = np.concatenate([unit_rows(700, 64, 3), np.repeat(v, 5000, axis=0), unit_rows(300, 64, 4)], axis=0)
+    g = g[rng.permutation(len(g))]
+    q = np.concatenate([unit_rows(2, 64, 2), v, -v], axis=0)  # the duplicated row itself, and its antipode (all ties LAST)
     idx = FlatIPIndex(64, "cuda")
     idx.add(g)
+    for k in (10, 100, 1024):
+        s, i = idx.search(q, k)
+        ref_s, ref_i = R.flat_ip_search(q, g, k)
+        assert_same(s, i, ref_s, ref_i, f"massive duplicates k={k}")
+    assert idx.exhaustive_rows > 0, "this gallery is built to overflow the carry lists even on the wide path"
+    # device call without resolution still reports instead of returning incomplete lists
+    idx.search_device(torch.from_numpy(q).cuda(), 10)
     with pytest.raises(RuntimeError):
-        idx.search(unit_rows(2, 64, 2), 10)
+        idx.check_status()
+
+
+def test_exhaustive_path_alone_matches_oracle(lib):
+    """vdk_ip_topk_exhaustive on its own (every query forced through it), incl. k > ntotal padding and an id offset."""
+    q, g = unit_rows(19, 128, 31), unit_rows(3001, 128, 32)
+    g[100] = g[7]
+    g[2999] = g[7]
+    idx = FlatIPIndex(128, "cuda", id_offset=1000)
+    idx.add(g)
+    idx._finalize()
+    for k in (1, 10, 100):
+        s, i = idx._exhaustive(torch.from_numpy(q).cuda(), k)
+        ref_s, ref_i = R.flat_ip_search(q, g, k, id_offset=1000)
+        assert_same(s.cpu().numpy(), i.cpu().numpy(), ref_s, ref_i, f"exhaustive k={k}")
+    small = FlatIPIndex(128, "cuda")
+    small.add(g[:5])
+    small._finalize()
+    s, i = small._exhaustive(torch.from_numpy(q).cuda(), 10)
+    ref_s, ref_i = R.flat_ip_search(q, g[:5], 10)
+    assert_same(s.cpu().numpy(), i.cpu().numpy(), ref_s, ref_i, "exhaustive padded")
 
 
 def test_l2_variant_of_the_cosine_index(lib):

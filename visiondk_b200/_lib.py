@@ -104,7 +104,11 @@ SIGNATURES = {
     "vdk_score_range": (_i, [C.POINTER(TopkPlan), _p, _p, _i64, _i64, _i, _p, _sz, _p]),
     "vdk_reduce_max": (_i, [_p, _i64, _p, _p]),
     "vdk_topk_merge": (_i, [_p, _p, _i, _i64, _i, _p, _p, _p]),
+    "vdk_topk_pack": (_i, [_p, _p, _i64, _p, _p]),
+    "vdk_topk_merge_packed": (_i, [_p, _i, _i64, _i, _p, _p, _p]),
     "vdk_ip_exact_pairs": (_i, [_p, _p, _i, _p, _p, _i64, _p, _p]),
+    "vdk_ip_topk_exhaustive_workspace_bytes": (_sz, [_i64]),
+    "vdk_ip_topk_exhaustive": (_i, [_p, _i64, _p, _i64, _i, _i, _i64, _p, _p, _p, _sz, _p]),
 }
 
 _lib = None

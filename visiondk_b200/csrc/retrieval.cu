@@ -579,9 +579,12 @@ __global__ void eps_kernel(const float* __restrict__ q_norm, const float* __rest
 // ------------------------------------------------------------------------------------------------
 // merge of per-shard lists, and brute-force pair scores for verification
 // ------------------------------------------------------------------------------------------------
-__global__ void topk_merge_kernel(const float* __restrict__ scores, const int64_t* __restrict__ ids, int n_lists,
-                                  int64_t n_query, int k, float* __restrict__ out_scores,
-                                  int64_t* __restrict__ out_ids) {
+// Lists arrive either as separate (scores, ids) arrays or PACKED as one 64-bit word per entry (score bits << 32 | uint32 id,
+// id -1 = 0xffffffff): the packed form is what the ranks exchange in ONE all-gather.
+template <bool kPacked>
+__global__ void topk_merge_kernel(const float* __restrict__ scores, const int64_t* __restrict__ ids,
+                                  const unsigned long long* __restrict__ packed, int n_lists, int64_t n_query, int k,
+                                  float* __restrict__ out_scores, int64_t* __restrict__ out_ids) {
   // one warp per query; lists are individually ordered, so a k-step tournament over n_lists heads suffices
   const int lane = threadIdx.x & 31;
   const int64_t row = (static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x) >> 5;
@@ -592,8 +595,15 @@ __global__ void topk_merge_kernel(const float* __restrict__ scores, const int64_
     float sc = -FLT_MAX;
     int64_t id = -1;
     if (lane < n_lists && head < k) {
-      sc = scores[lane * list_stride + row * k + head];
-      id = ids[lane * list_stride + row * k + head];
+      if (kPacked) {
+        const unsigned long long w = packed[lane * list_stride + row * k + head];
+        sc = __uint_as_float(static_cast<uint32_t>(w >> 32));
+        const uint32_t lo = static_cast<uint32_t>(w & 0xffffffffull);
+        id = lo == 0xffffffffu ? -1 : static_cast<int64_t>(lo);
+      } else {
+        sc = scores[lane * list_stride + row * k + head];
+        id = ids[lane * list_stride + row * k + head];
+      }
     }
     // best = max score, then smallest non-negative id
     float bs = sc;
@@ -624,6 +634,15 @@ __global__ void topk_merge_kernel(const float* __restrict__ scores, const int64_
   }
 }
 
+__global__ void topk_pack_kernel(const float* __restrict__ scores, const int64_t* __restrict__ ids, int64_t n,
+                                 unsigned long long* __restrict__ out) {
+  const int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const int64_t id = ids[i];
+  out[i] = (static_cast<unsigned long long>(__float_as_uint(scores[i])) << 32) |
+           static_cast<unsigned long long>(id < 0 ? 0xffffffffu : static_cast<uint32_t>(id));
+}
+
 __global__ void exact_pairs_kernel(const float* __restrict__ q32, const float* __restrict__ g32, int dim,
                                    const int64_t* __restrict__ qi, const int64_t* __restrict__ gi, int64_t n,
                                    float* __restrict__ out) {
@@ -636,6 +655,124 @@ __global__ void exact_pairs_kernel(const float* __restrict__ q32, const float* _
   for (int i = lane; i < dim; i += 32) acc = fma(static_cast<double>(q[i]), static_cast<double>(g[i]), acc);
   acc = warp_sum_f64(acc);
   if (lane == 0) out[w] = static_cast<float>(acc);
+}
+
+// ------------------------------------------------------------------------------------------------
+// exhaustive path: canonical scores of a few queries against EVERY gallery row, exact selection on 64-bit keys.
+// Taken only for rows whose candidate lists overflowed even on the all-dense plan (thousands of exact duplicates of
+// a top-k member): faiss' flat search never fails on such galleries (engine/cbir/evaluation.py:193), so neither may
+// this one.  No approximate pass, no capacity: key = (ordered canonical score, ~row), unique per row, so the k-th
+// largest key is found exactly by an 8 x 8-bit radix select and the k survivors are sorted.
+// ------------------------------------------------------------------------------------------------
+constexpr int kExQ = 8;  // queries scored per pass over the gallery
+
+__global__ void __launch_bounds__(256) exhaustive_scores_kernel(const float* __restrict__ q32, int nq, const float* __restrict__ g32,
+                                                                int64_t ng, int dim, unsigned long long* __restrict__ keys) {
+  extern __shared__ float ex_q[];  // [nq][dim]
+  for (int i = threadIdx.x; i < nq * dim; i += blockDim.x) ex_q[i] = q32[i];
+  __syncthreads();
+  const int lane = threadIdx.x & 31;
+  const int64_t warps = (static_cast<int64_t>(gridDim.x) * blockDim.x) >> 5;
+  for (int64_t row = (static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x) >> 5; row < ng; row += warps) {
+    const float* g = g32 + row * dim;
+    double acc[kExQ];
+#pragma unroll
+    for (int j = 0; j < kExQ; ++j) acc[j] = 0.0;
+    for (int i = lane; i < dim; i += 32) {  // the canonical order: lane l takes l, l+32, ... then the xor butterfly
+      const double gv = static_cast<double>(g[i]);
+#pragma unroll
+      for (int j = 0; j < kExQ; ++j)
+        if (j < nq) acc[j] = fma(static_cast<double>(ex_q[j * dim + i]), gv, acc[j]);
+    }
+#pragma unroll
+    for (int j = 0; j < kExQ; ++j) {
+      if (j < nq) {
+        const double s = warp_sum_f64(acc[j]);
+        if (lane == 0)
+          keys[static_cast<size_t>(j) * ng + row] = (static_cast<unsigned long long>(ord_u32(static_cast<float>(s))) << 32) |
+                                                    static_cast<unsigned long long>(~static_cast<uint32_t>(row));
+      }
+    }
+  }
+}
+
+constexpr int kExThreads = 1024;
+
+__global__ void __launch_bounds__(kExThreads) exhaustive_select_kernel(const unsigned long long* __restrict__ keys, int64_t ng, int k,
+                                                                       int64_t id_offset, float* __restrict__ out_scores,
+                                                                       int64_t* __restrict__ out_ids) {
+  __shared__ unsigned hist[256];
+  __shared__ unsigned long long s_sort[1024];
+  __shared__ unsigned s_bin, s_krem, s_m;
+  const int tid = threadIdx.x;
+  const unsigned long long* e = keys + static_cast<size_t>(blockIdx.x) * ng;
+  const int kk = static_cast<int>(ng < k ? ng : k);
+  unsigned long long prefix = 0ull, mask = 0ull;
+  unsigned k_rem = static_cast<unsigned>(kk);
+  if (kk > 0 && ng > kk) {
+    for (int shift = 56; shift >= 0; shift -= 8) {
+      for (int i = tid; i < 256; i += kExThreads) hist[i] = 0;
+      __syncthreads();
+      for (int64_t i = tid; i < ng; i += kExThreads) {
+        const unsigned long long key = e[i];
+        if ((key & mask) == prefix) atomicAdd(&hist[(key >> shift) & 255ull], 1u);
+      }
+      __syncthreads();
+      if (tid == 0) {
+        unsigned acc = 0;
+        int b = 255;
+        for (; b > 0; --b) {
+          if (acc + hist[b] >= k_rem) break;
+          acc += hist[b];
+        }
+        s_bin = static_cast<unsigned>(b);
+        s_krem = k_rem - acc;
+      }
+      __syncthreads();
+      prefix |= static_cast<unsigned long long>(s_bin) << shift;
+      mask |= 255ull << shift;
+      k_rem = s_krem;
+      __syncthreads();
+    }
+  }
+  // keys are unique: exactly kk keys are >= the k-th largest (prefix); with ng <= k every key survives (prefix = 0)
+  if (tid == 0) s_m = 0;
+  for (int i = tid; i < 1024; i += kExThreads) s_sort[i] = 0ull;
+  __syncthreads();
+  for (int64_t i = tid; i < ng; i += kExThreads) {
+    const unsigned long long key = e[i];
+    if (key >= prefix) {
+      const unsigned pos = atomicAdd(&s_m, 1u);
+      if (pos < 1024u) s_sort[pos] = key;
+    }
+  }
+  __syncthreads();
+  for (int size = 2; size <= 1024; size <<= 1) {
+    for (int stride = size >> 1; stride > 0; stride >>= 1) {
+      for (int i = tid; i < 512; i += kExThreads) {
+        const int lo = 2 * i - (i & (stride - 1));
+        const int hi = lo + stride;
+        const bool desc = ((lo & size) == 0);
+        const unsigned long long a = s_sort[lo], b = s_sort[hi];
+        if ((a < b) == desc) {
+          s_sort[lo] = b;
+          s_sort[hi] = a;
+        }
+      }
+      __syncthreads();
+    }
+  }
+  for (int j = tid; j < k; j += kExThreads) {
+    float sc = -FLT_MAX;
+    int64_t id = -1;
+    if (j < kk) {
+      const unsigned long long key = s_sort[j];
+      sc = unord_u32(static_cast<uint32_t>(key >> 32));
+      id = static_cast<int64_t>(~static_cast<uint32_t>(key & 0xffffffffull)) + id_offset;
+    }
+    out_scores[static_cast<size_t>(blockIdx.x) * k + j] = sc;
+    out_ids[static_cast<size_t>(blockIdx.x) * k + j] = id;
+  }
 }
 
 static int pow2_ceil(int v) {
@@ -911,8 +1048,29 @@ extern "C" int vdk_topk_merge(const float* scores, const int64_t* ids, int n_lis
   VDK_REQUIRE(n_lists >= 1 && n_lists <= 32 && k >= 1 && n_query >= 0, "vdk_topk_merge: n_lists must be in [1,32]");
   if (n_query == 0) return VDK_OK;
   const int64_t blocks = (n_query + 7) / 8;
-  topk_merge_kernel<<<static_cast<unsigned>(blocks), 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
-      scores, ids, n_lists, n_query, k, out_scores, out_ids);
+  topk_merge_kernel<false><<<static_cast<unsigned>(blocks), 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
+      scores, ids, nullptr, n_lists, n_query, k, out_scores, out_ids);
+  VDK_CUDA_OK(cudaGetLastError());
+  return VDK_OK;
+}
+
+extern "C" int vdk_topk_pack(const float* scores, const int64_t* ids, int64_t n, void* packed, void* stream) {
+  VDK_REQUIRE(scores && ids && packed && n >= 0, "vdk_topk_pack: bad arguments");
+  if (n == 0) return VDK_OK;
+  topk_pack_kernel<<<static_cast<unsigned>((n + 255) / 256), 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
+      scores, ids, n, reinterpret_cast<unsigned long long*>(packed));
+  VDK_CUDA_OK(cudaGetLastError());
+  return VDK_OK;
+}
+
+extern "C" int vdk_topk_merge_packed(const void* packed, int n_lists, int64_t n_query, int k, float* out_scores,
+                                     int64_t* out_ids, void* stream) {
+  VDK_REQUIRE(packed && out_scores && out_ids, "vdk_topk_merge_packed: null operand");
+  VDK_REQUIRE(n_lists >= 1 && n_lists <= 32 && k >= 1 && n_query >= 0, "vdk_topk_merge_packed: n_lists must be in [1,32]");
+  if (n_query == 0) return VDK_OK;
+  const int64_t blocks = (n_query + 7) / 8;
+  topk_merge_kernel<true><<<static_cast<unsigned>(blocks), 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
+      nullptr, nullptr, reinterpret_cast<const unsigned long long*>(packed), n_lists, n_query, k, out_scores, out_ids);
   VDK_CUDA_OK(cudaGetLastError());
   return VDK_OK;
 }
@@ -952,5 +1110,41 @@ extern "C" int vdk_topk_row_flags(const vdk_topk_plan* plan, const void* workspa
   VDK_REQUIRE(workspace && row_flags && workspace_bytes >= vdk_topk_workspace_bytes(plan), "vdk_topk_row_flags: bad arguments");
   const TopkWorkspace w = carve_workspace(const_cast<void*>(workspace), plan->n_query, plan->cand_capacity, plan->carry_capacity);
   *row_flags = w.row_flag;
+  return VDK_OK;
+}
+
+extern "C" size_t vdk_ip_topk_exhaustive_workspace_bytes(int64_t n_gallery) {
+  return static_cast<size_t>(kExQ) * static_cast<size_t>(n_gallery > 0 ? n_gallery : 1) * sizeof(unsigned long long);
+}
+
+extern "C" int vdk_ip_topk_exhaustive(const float* q32, int64_t n_query, const float* g32, int64_t n_gallery, int dim, int k,
+                                      int64_t id_offset, float* out_scores, int64_t* out_ids, void* workspace,
+                                      size_t workspace_bytes, void* stream) {
+  VDK_REQUIRE(out_scores && out_ids, "vdk_ip_topk_exhaustive: null output");
+  VDK_REQUIRE(n_query >= 0 && n_gallery >= 0 && n_gallery < (1ll << 32) && dim > 0, "vdk_ip_topk_exhaustive: bad sizes");
+  VDK_REQUIRE(k >= 1 && k <= 1024, "vdk_ip_topk_exhaustive: k must be in [1,1024]");
+  VDK_REQUIRE(static_cast<size_t>(kExQ) * dim * sizeof(float) <= 96 * 1024, "vdk_ip_topk_exhaustive: dim too large (%d)", dim);
+  if (n_query == 0) return VDK_OK;
+  VDK_REQUIRE(q32 && (g32 || n_gallery == 0), "vdk_ip_topk_exhaustive: null operand");
+  VDK_REQUIRE(workspace && workspace_bytes >= vdk_ip_topk_exhaustive_workspace_bytes(n_gallery),
+              "vdk_ip_topk_exhaustive: workspace too small");
+  cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
+  unsigned long long* keys = reinterpret_cast<unsigned long long*>(workspace);
+  static bool attr = false;
+  if (!attr) {
+    VDK_CUDA_OK(cudaFuncSetAttribute(exhaustive_scores_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024));
+    attr = true;
+  }
+  for (int64_t q0 = 0; q0 < n_query; q0 += kExQ) {
+    const int nq = static_cast<int>(std::min<int64_t>(kExQ, n_query - q0));
+    if (n_gallery > 0) {
+      const int blocks = static_cast<int>(std::min<int64_t>((n_gallery + 7) / 8, 8 * sm_count()));
+      exhaustive_scores_kernel<<<blocks, 256, static_cast<size_t>(nq) * dim * sizeof(float), s>>>(
+          q32 + q0 * dim, nq, g32, n_gallery, dim, keys);
+      VDK_CUDA_OK(cudaGetLastError());
+    }
+    exhaustive_select_kernel<<<nq, kExThreads, 0, s>>>(keys, n_gallery, k, id_offset, out_scores + q0 * k, out_ids + q0 * k);
+    VDK_CUDA_OK(cudaGetLastError());
+  }
   return VDK_OK;
 }

@@ -64,6 +64,7 @@ class FusedSGDClipEMA:
         self._sumsq = torch.zeros((), dtype=torch.float64, device=dev)
         self._ws = torch.empty((lib.vdk_grad_sumsq_workspace_bytes(),), dtype=torch.uint8, device=dev)
         self.ema_model, self.ema_decay, self.ema_tau, self.updates = ema_model, ema_decay, ema_tau, 0
+        self.model = model
         self._buffers = []
         if ema_model is not None:
             assert model is not None, "pass the live model so EMA buffers can be paired by name"
@@ -108,6 +109,37 @@ class FusedSGDClipEMA:
         for e, b in self._buffers:
             _lib.check(lib.vdk_ema_update(e.data_ptr(), b.data_ptr(), b.numel(), d, omd, s), "vdk_ema_update")
         self.steps += 1
+        self._invalidate_packed()
+
+    def _invalidate_packed(self) -> None:
+        """The kernels above write parameters, EMA parameters and EMA buffers through raw pointers, which does not bump
+        torch's `_version` counters — the key the backbones' packed inference weights (`TimmWrapper._pack`,
+        `ViTWrapper._pack`) are cached under.  Drop those caches explicitly so that the next `embed()` of the live model or
+        of the EMA copy (the in-training eval, engine/procedure/train.py:244-262) re-packs the CURRENT weights."""
+        for root in (self.model, self.ema_model):
+            if root is None:
+                continue
+            for m in root.modules():
+                if hasattr(m, "_packed_key"):
+                    m._packed_key = None
+
+    def state_dict(self) -> dict:
+        """What torch.optim.SGD.state_dict() carries for the reference's checkpoint (engine/procedure/train.py:273): the
+        per-group hyper-parameters and the momentum buffers (one flat tensor per group), plus the step / EMA counters."""
+        return {"steps": self.steps, "updates": self.updates, "param_groups": [dict(pg) for pg in self.param_groups],
+                "momentum_buffers": [g.mom.detach().cpu().clone() for g in self.groups]}
+
+    def load_state_dict(self, state: dict) -> None:
+        if len(state["momentum_buffers"]) != len(self.groups):
+            raise ValueError("optimizer state has a different number of parameter groups")
+        for g, m in zip(self.groups, state["momentum_buffers"]):
+            if m.numel() != g.n:
+                raise ValueError("optimizer state does not match the parameter groups (different model?)")
+            g.mom.copy_(m.to(g.mom.device))
+        for pg, saved in zip(self.param_groups, state["param_groups"]):
+            pg.update(saved)
+        self.steps, self.updates = int(state["steps"]), int(state["updates"])
+        self._invalidate_packed()
 
     def grad_norm(self) -> float:
         return float(self._sumsq.sqrt().item())

@@ -82,6 +82,7 @@ class FlatIPIndex:
         self.last_status = None
         self.stage_ends = None  # optional override of the gallery range schedule (tuning / tests)
         self.wide_path_rows = 0
+        self.exhaustive_rows = 0
 
     # ---- faiss-shaped surface -------------------------------------------------------------------
     @property
@@ -194,11 +195,15 @@ class FlatIPIndex:
         ng = self._rows.n
         slice_rows = 8 * plan.cand_capacity
         lists_s, lists_i = [], []
+        still = torch.zeros((rows.numel(),), dtype=torch.bool, device=self.device)
         for a in range(0, ng, slice_rows):
-            s_, i_, st, _ = self._run_topk(qp, rows, a, min(ng, a + slice_rows), k, dense_all=True)
-            if int(st[0].item()) > 0:
-                raise RuntimeError("vdk_ip_topk: more than carry_capacity near-tied candidates for a query even on the "
-                                   "wide path (massively duplicated gallery rows)")
+            s_, i_, st, p_ = self._run_topk(qp, rows, a, min(ng, a + slice_rows), k, dense_all=True)
+            if int(st[0].item()) > 0:  # more near-ties than a carry list holds: those rows go to the exhaustive path
+                fp = C.c_void_p()
+                _lib.check(lib.vdk_topk_row_flags(C.byref(p_), self._ws.data_ptr(), self._ws.numel(), C.byref(fp)),
+                           "vdk_topk_row_flags")
+                o = fp.value - self._ws.data_ptr()
+                still |= self._ws[o:o + 4 * p_.n_query].view(torch.int32) != 0
             lists_s.append(s_)
             lists_i.append(i_)
         while len(lists_s) > 1:  # merge up to 32 lists at a time
@@ -206,8 +211,29 @@ class FlatIPIndex:
             lists_s, lists_i = [ms] + lists_s[32:], [mi] + lists_i[32:]
         out_s[rows] = lists_s[0]
         out_i[rows] = lists_i[0]
-        self.last_status = torch.zeros_like(self.last_status)
         self.wide_path_rows = int(rows.numel())
+        self.exhaustive_rows = 0
+        if bool(still.any().item()):
+            ex = rows[still]
+            es, ei = self._exhaustive(qp.x32[ex].contiguous(), k)
+            out_s[ex] = es
+            out_i[ex] = ei
+            self.exhaustive_rows = int(ex.numel())
+        self.last_status = torch.zeros_like(self.last_status)
+
+    def _exhaustive(self, q32: torch.Tensor, k: int):
+        """Canonical scores of the given (already normalised) queries against every gallery row + exact selection
+        (vdk_ip_topk_exhaustive): cannot overflow, whatever the number of duplicates."""
+        lib = _lib.load()
+        nq, ng = q32.shape[0], self._rows.n
+        out_s = torch.empty((nq, k), dtype=torch.float32, device=self.device)
+        out_i = torch.empty((nq, k), dtype=torch.int64, device=self.device)
+        ws = torch.empty((lib.vdk_ip_topk_exhaustive_workspace_bytes(ng),), dtype=torch.uint8, device=self.device)
+        with torch.cuda.device(self.device):
+            _lib.check(lib.vdk_ip_topk_exhaustive(q32.data_ptr(), nq, self._rows.x32.data_ptr(), ng, self.d, k, self.id_offset,
+                                                  out_s.data_ptr(), out_i.data_ptr(), ws.data_ptr(), ws.numel(),
+                                                  _lib.stream_ptr()), "vdk_ip_topk_exhaustive")
+        return out_s, out_i
 
     def check_status(self) -> dict:
         """Synchronises and raises if any query overflowed its candidate lists (results would be incomplete; the
@@ -254,6 +280,44 @@ def merge_topk(scores: torch.Tensor, ids: torch.Tensor, k: int):
         _lib.check(lib.vdk_topk_merge(scores.data_ptr(), ids.data_ptr(), n_lists, nq, k, out_s.data_ptr(),
                                       out_i.data_ptr(), _lib.stream_ptr()), "vdk_topk_merge")
     return out_s, out_i
+
+
+def pack_topk(scores: torch.Tensor, ids: torch.Tensor) -> torch.Tensor:
+    """(scores, ids) [n_query, k] -> int64 words (score bits << 32 | uint32 id): the sharded search's exchange format."""
+    lib = _lib.load()
+    if ids.numel() and int(ids.shape[0]) and scores.shape != ids.shape:
+        raise ValueError("scores and ids must have the same shape")
+    scores = scores.contiguous().float()
+    ids = ids.contiguous().long()
+    out = torch.empty(scores.shape, dtype=torch.int64, device=scores.device)
+    with torch.cuda.device(scores.device):
+        _lib.check(lib.vdk_topk_pack(scores.data_ptr(), ids.data_ptr(), scores.numel(), out.data_ptr(), _lib.stream_ptr()),
+                   "vdk_topk_pack")
+    return out
+
+
+def merge_topk_packed(packed: torch.Tensor, k: int):
+    """Packed per-shard lists [n_lists, n_query, k] (pack_topk words) -> global (scores, ids) [n_query, k]."""
+    lib = _lib.load()
+    n_lists, nq, kk = packed.shape
+    assert kk == k and packed.dtype == torch.int64
+    packed = packed.contiguous()
+    out_s = torch.empty((nq, k), dtype=torch.float32, device=packed.device)
+    out_i = torch.empty((nq, k), dtype=torch.int64, device=packed.device)
+    with torch.cuda.device(packed.device):
+        _lib.check(lib.vdk_topk_merge_packed(packed.data_ptr(), n_lists, nq, k, out_s.data_ptr(), out_i.data_ptr(),
+                                             _lib.stream_ptr()), "vdk_topk_merge_packed")
+    return out_s, out_i
+
+
+def sharded_flat_search(index: "FlatIPIndex", q_local: torch.Tensor, q_sizes, k: int):
+    """The multi-GPU search call (BASELINE config 4): every rank holds one row shard of the gallery in `index` (built with its
+    `id_offset`) and `q_sizes[rank]` query embeddings; returns the GLOBAL top-k of ALL queries on every rank, bit-identical
+    to the unsharded search (scores are canonical, the merge uses the same (score desc, id asc) rule).  Overflowed queries
+    are resolved locally before the exchange, so the merge never sees an incomplete list."""
+    from . import sharding
+    return sharding.sharded_search(q_local, list(q_sizes), lambda q, kk: index.search_device(q, kk, resolve_overflow=True),
+                                   merge_topk, k, pack=pack_topk, merge_packed=merge_topk_packed)
 
 
 def exact_pair_scores(q32: torch.Tensor, g32: torch.Tensor, qi: torch.Tensor, gi: torch.Tensor) -> torch.Tensor:

@@ -1,11 +1,15 @@
 """Host-side plumbing of the sharded CBIR search: one process per GPU, gallery rows sharded
 contiguously, two small exchanges over torch.distributed (NCCL on GPUs; the same code runs over gloo in the CPU
-tests).  The reference only replicates the index (`faiss.index_cpu_to_all_gpus`, engine/cbir/evaluation.py:159-162);
-sharding is BASELINE config 4.  No arithmetic happens here: scoring and merging are the CUDA kernels' job.
+tests and in the single-GPU two-rank parity test).  The reference only replicates the index
+(`faiss.index_cpu_to_all_gpus`, engine/cbir/evaluation.py:159-162); sharding is BASELINE config 4.  No arithmetic
+happens here: scoring, packing and merging are the CUDA kernels' job.
+
+Exchange 1: all-gather of the query embeddings every rank extracted.
+Exchange 2: ONE all-gather of the per-shard top-k lists, each entry packed into a 64-bit word (score bits << 32 | id).
 """
 from __future__ import annotations
 
-from typing import Callable, List, Tuple
+from typing import Callable, List, Optional, Tuple
 
 import torch
 import torch.distributed as dist
@@ -20,9 +24,26 @@ def shard_sizes(n: int, world: int) -> List[int]:
     return [shard_bounds(n, world, r)[1] - shard_bounds(n, world, r)[0] for r in range(world)]
 
 
+def _active() -> bool:
+    return dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1
+
+
+def _all_gather_into(out: torch.Tensor, src: torch.Tensor) -> None:
+    """all_gather_into_tensor; over gloo, device tensors are staged through the host (gloo gathers host memory only —
+    that backend is the test harness, NCCL is the product path)."""
+    world = dist.get_world_size()
+    flat = (world * src.shape[0],) + tuple(src.shape[1:])  # the concatenated form every backend accepts
+    if src.is_cuda and dist.get_backend() != "nccl":
+        host = torch.empty(flat, dtype=out.dtype)
+        dist.all_gather_into_tensor(host, src.cpu())
+        out.view(flat).copy_(host)
+    else:
+        dist.all_gather_into_tensor(out.view(flat), src)
+
+
 def all_gather_rows(local: torch.Tensor, sizes: List[int]) -> torch.Tensor:
     """Exchange 1: every rank extracted `sizes[rank]` query embeddings; returns all of them in rank order."""
-    if not dist.is_initialized() or dist.get_world_size() == 1:
+    if not _active():
         return local
     # ranks may hold one row more or less: pad to the largest shard so every backend sees equal shapes
     m = max(sizes)
@@ -31,29 +52,48 @@ def all_gather_rows(local: torch.Tensor, sizes: List[int]) -> torch.Tensor:
         pad = torch.zeros((m - padded.shape[0],) + tuple(local.shape[1:]), dtype=local.dtype, device=local.device)
         padded = torch.cat([padded, pad], dim=0)
     out = torch.empty((len(sizes) * m,) + tuple(local.shape[1:]), dtype=local.dtype, device=local.device)
-    dist.all_gather_into_tensor(out, padded)
+    _all_gather_into(out, padded)
     if all(n == m for n in sizes):
         return out
     return torch.cat([out[r * m:r * m + n] for r, n in enumerate(sizes)], dim=0)
 
 
+def all_gather_packed(packed: torch.Tensor) -> torch.Tensor:
+    """Exchange 2: per-shard packed top-k lists [nq,k] int64 -> [world, nq, k] on every rank (one collective, 8 MB per rank
+    at 10k x 100)."""
+    if not _active():
+        return packed.unsqueeze(0)
+    world = dist.get_world_size()
+    out = torch.empty((world,) + tuple(packed.shape), dtype=packed.dtype, device=packed.device)
+    _all_gather_into(out, packed.contiguous())
+    return out
+
+
 def all_gather_topk(scores: torch.Tensor, ids: torch.Tensor) -> Tuple[torch.Tensor, torch.Tensor]:
-    """Exchange 2: per-shard top-k lists [nq,k] -> stacked [world, nq, k] on every rank (8 MB per rank at 10k x 100)."""
-    if not dist.is_initialized() or dist.get_world_size() == 1:
+    """Unpacked variant (two collectives): per-shard lists [nq,k] -> stacked [world, nq, k].  Kept for callers whose global
+    ids do not fit the packed format (>= 2^32 - 1 gallery rows)."""
+    if not _active():
         return scores.unsqueeze(0), ids.unsqueeze(0)
     world = dist.get_world_size()
-    ss = [torch.empty_like(scores) for _ in range(world)]
-    ii = [torch.empty_like(ids) for _ in range(world)]
-    dist.all_gather(ss, scores.contiguous())
-    dist.all_gather(ii, ids.contiguous())
-    return torch.stack(ss), torch.stack(ii)
+    ss = torch.empty((world,) + tuple(scores.shape), dtype=scores.dtype, device=scores.device)
+    ii = torch.empty((world,) + tuple(ids.shape), dtype=ids.dtype, device=ids.device)
+    _all_gather_into(ss, scores.contiguous())
+    _all_gather_into(ii, ids.contiguous())
+    return ss, ii
 
 
-def sharded_search(q_local: torch.Tensor, q_sizes: List[int], local_search: Callable, merge: Callable, k: int):
-    """all-gather queries -> local_search(q_all, k) on this rank's shard -> all-gather lists -> merge(ss, ii, k)."""
+def sharded_search(q_local: torch.Tensor, q_sizes: List[int], local_search: Callable, merge: Callable, k: int,
+                   pack: Optional[Callable] = None, merge_packed: Optional[Callable] = None):
+    """all-gather queries -> local_search(q_all, k) on this rank's shard -> all-gather lists -> merge.
+
+    `local_search` must return COMPLETE lists (FlatIPIndex.search_device(..., resolve_overflow=True)): an overflowed query
+    resolved on one rank only would silently lose candidates in the merge.  With `pack` / `merge_packed`
+    (visiondk_b200.retrieval.pack_topk / merge_topk_packed) the lists travel in one collective."""
     q_all = all_gather_rows(q_local, q_sizes)
     s, i = local_search(q_all, k)
-    ss, ii = all_gather_topk(s, i)
-    if ss.shape[0] == 1:
+    if not _active():
         return s, i
+    if pack is not None and merge_packed is not None:
+        return merge_packed(all_gather_packed(pack(s, i)), k)
+    ss, ii = all_gather_topk(s, i)
     return merge(ss, ii, k)

@@ -83,6 +83,31 @@ class FaceTrainer:
         self.lr0, self.warm, self.total, self.lrf = lr0, warm_steps, total_steps, lrf_ratio
         self.sched_step = 0
         self._apply_lr()
+        self._broadcast_initial_state()
+
+    def _broadcast_initial_state(self):
+        """DistributedDataParallel broadcasts rank 0's parameters and buffers when it wraps the model
+        (engine/vision_engine.py:509-510); without it every rank would keep its own random initialisation and only the
+        gradients would be shared.  Same here, on the flat parameter buffers (+ momentum) and every module buffer."""
+        if not (dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1):
+            return
+        for g in self.opt.groups:
+            dist.broadcast(g.p, src=0)
+            dist.broadcast(g.mom, src=0)
+        for b in self.model.buffers():
+            dist.broadcast(b, src=0)
+        self.opt._invalidate_packed()
+
+    def state_dict(self) -> dict:
+        """The trainer-side entries of the reference's checkpoint (engine/procedure/train.py:266-276): 'optimizer',
+        'scheduler' (position in cosine_with_warm) and the EMA's 'updates'."""
+        return {"optimizer": self.opt.state_dict(), "scheduler": {"step": self.sched_step}, "updates": self.opt.updates}
+
+    def load_state_dict(self, state: dict) -> None:
+        self.opt.load_state_dict(state["optimizer"])
+        self.opt.updates = int(state.get("updates", self.opt.updates))
+        self.sched_step = int(state["scheduler"]["step"])
+        self._apply_lr()  # param_groups' lr follow the restored schedule position, not the saved (pre-step) value
 
     def _apply_lr(self):
         for pg, base in zip(self.opt.param_groups, self.base_lrs):
@@ -111,13 +136,25 @@ class FaceTrainer:
                     return g, lo, hi
         return None
 
+    @staticmethod
+    def _all_reduce_mean(t: torch.Tensor, async_op: bool = False):
+        """Gradient mean over the ranks: ReduceOp.AVG on NCCL (the product path); gloo (the test harness: two ranks sharing
+        one GPU, or CPU tensors) has no AVG, so it sums synchronously and divides."""
+        if dist.get_backend() == "nccl":
+            return dist.all_reduce(t, op=dist.ReduceOp.AVG, async_op=async_op)
+        dist.all_reduce(t, op=dist.ReduceOp.SUM)
+        t.div_(dist.get_world_size())
+        return None
+
     def _on_section(self, names):
         sl = self._flat_slice(names)
         if sl is None:
             self._overlap_failed = True
             return
         g, lo, hi = sl
-        self._pending.append(dist.all_reduce(g.g[lo:hi], op=dist.ReduceOp.AVG, async_op=True))
+        work = self._all_reduce_mean(g.g[lo:hi], async_op=True)
+        if work is not None:
+            self._pending.append(work)
         self._reduced.append((id(g), lo, hi))
 
     def step(self, images: torch.Tensor, labels: torch.Tensor) -> torch.Tensor:
@@ -142,7 +179,7 @@ class FaceTrainer:
                 pos = 0
                 for lo, hi in done + [(g.g.numel(), g.g.numel())]:
                     if lo > pos:
-                        dist.all_reduce(g.g[pos:lo], op=dist.ReduceOp.AVG)
+                        self._all_reduce_mean(g.g[pos:lo])
                     pos = max(pos, hi)
         self.opt.step()
         self.sched_step += 1  # scheduler.step() per batch (train.py:230)
