@@ -175,7 +175,7 @@ def cpu_baselines(args, want_retrieval=True, want_train=False, target_s=10.0):
         model.train()
         head_w = torch.nn.Parameter(H.init_head_weight(FEAT, 1000))
         opt = torch.optim.SGD(list(model.parameters()) + [head_w], lr=0.01, momentum=0.937, weight_decay=5e-4)
-        xt, yt = torch.randn(4, 3, IMG, IMG), torch.randint(0, 1000, (4,))
+        xt, yt = torch.randn(16, 3, IMG, IMG), torch.randint(0, 1000, (16,))
 
         def tstep():
             loss = H.cross_entropy(H.arcface_logits(model(xt), head_w, yt, 0.35, 0.0, 32.0), yt, 0.1)
@@ -184,16 +184,20 @@ def cpu_baselines(args, want_retrieval=True, want_train=False, target_s=10.0):
             opt.step()
             opt.zero_grad()
 
+        tstep()  # warm-up (allocator, thread pool)
         t0 = time.perf_counter()
-        reps = 0
-        while True:  # the first step is counted too (no separate warm-up: the sample is bounded in time)
+        reps, per = 0, []
+        while True:
+            t1 = time.perf_counter()
             tstep()
+            per.append(time.perf_counter() - t1)
             reps += 1
-            if time.perf_counter() - t0 > target_s or reps >= 8:
+            if time.perf_counter() - t0 > 2 * target_s or reps >= 8:
                 break
         dt = time.perf_counter() - t0
-        out["train"] = {"value": reps * 4 / dt, "unit": "embeddings/s", "cores": cores, "kind": "port",
-                        "sample": f"{reps} train steps of 4 images (fp32 oracle fwd + ArcFace/CE + bwd + clip + SGD), {dt:.1f} s"}
+        out["train"] = {"value": reps * 16 / dt, "unit": "embeddings/s", "cores": cores, "kind": "port",
+                        "spread": {"min": 16 / max(per), "max": 16 / min(per), "unit": "embeddings/s per step"},
+                        "sample": f"{reps} train steps of 16 images (fp32 oracle fwd + ArcFace/CE + bwd + clip + SGD), {dt:.1f} s"}
         model.eval()
     if want_retrieval:
         gen = torch.Generator().manual_seed(5)
@@ -225,7 +229,7 @@ def run_reference(args):
     from oracle.convnext import TimmWrapperOracle
     from oracle import heads as H
     cores = usable_threads()
-    bs = 2  # the smallest batch BatchNorm's batch statistics allow: K steps stay within minutes on any host
+    bs = 16  # a bounded sample of the 128-image step: ~3 s per step on the box's host cores, K = 20 steps stay within minutes
     backbone = TimmWrapperOracle(MODEL, FEAT, IMG).train()
     head_w = torch.nn.Parameter(H.init_head_weight(FEAT, 1000))
     params = list(backbone.parameters()) + [head_w]
@@ -248,13 +252,18 @@ def run_reference(args):
                     e.mul_(0.999).add_(p.detach(), alpha=0.001)
         return float(loss)
 
-    for _ in range(max(1, min(args.warmup, 1))):
+    for _ in range(max(1, min(args.warmup, 2))):
         step()
+    per_step = []
     t0 = time.perf_counter()
     for _ in range(args.steps):
+        t1 = time.perf_counter()
         step()
+        per_step.append(time.perf_counter() - t1)
     dt = time.perf_counter() - t0
     value = args.steps * bs / dt
+    srt = sorted(per_step)
+    spread = {"min": bs / srt[-1], "median": bs / srt[len(srt) // 2], "max": bs / srt[0], "unit": "embeddings/s per step"}
     # secondary: inference embeddings and retrieval, bounded samples
     backbone.eval()
     xe = torch.randn(8, 3, IMG, IMG)
@@ -278,9 +287,9 @@ def run_reference(args):
         "ms_per_step": dt / args.steps * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "f32", "data": "synthetic",
         "config": {"workload": "faceX train step: ConvNeXt-B 224^2 + ArcFace(C=1000) + CE + clip + SGD + EMA",
-                   "note": "reference CPU path restated (fp32 oracle + torch.optim.SGD); each step = a bounded sample of 2 images"},
-        "cpu_baseline": {"value": value, "unit": "embeddings/s", "cores": cores, "kind": "port",
-                         "sample": "each step = 2 images through fwd + ArcFace/CE + bwd + clip + SGD + EMA (fp32 oracle)"},
+                   "note": f"reference CPU path restated (fp32 oracle + torch.optim.SGD); each step = a bounded sample of {bs} images"},
+        "cpu_baseline": {"value": value, "unit": "embeddings/s", "cores": cores, "kind": "port", "spread": spread,
+                         "sample": f"each step = {bs} images through fwd + ArcFace/CE + bwd + clip + SGD + EMA (fp32 oracle)"},
         "e2e": dict(value=value, unit="embeddings/s", **zero), "gpu_launches": 0,
         "extract": {"metric": "embeddings/sec (ConvNeXt-B 224^2, CBIR extract, inference)", "value": evalue,
                     "unit": "embeddings/s", "cpu_baseline": {"value": evalue, "unit": "embeddings/s", "cores": cores,
@@ -328,6 +337,70 @@ def peak_tflops():
         return float(p["bf16_tflops"]), "MEASURED_PEAKS.json bf16_tflops (burst: kernel timed alone)"
     except Exception:
         return 1590.0, "fallback 1590 TFLOP/s (B200_PROFILING.md)"
+
+
+def measured_peaks():
+    try:
+        return json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    except Exception:
+        return {}
+
+
+def ncu_traffic(key):
+    """DRAM bytes per launch (dram__bytes_read.sum + dram__bytes_write.sum) of a kernel / shape from the committed ncu captures:
+    profiles/r02_traffic.json maps a key to {"bytes_per_launch": ..., "source": "<csv under profiles/>"}; None when not captured."""
+    try:
+        t = json.load(open(os.path.join(ROOT, "profiles", "r02_traffic.json")))
+        return t.get(key)
+    except Exception:
+        return None
+
+
+def live_profile(fn):
+    """One extra, UNTIMED call of `fn` with the library's event profile open (vdk_prof_begin / vdk_prof_end): per kernel
+    category the launches, the summed CUDA-event time on the launching stream and the algorithmic FLOPs / bytes of that call."""
+    import torch
+    from visiondk_b200 import _lib
+    torch.cuda.synchronize()
+    with _lib.profile() as p:
+        fn()
+        torch.cuda.synchronize()
+    return p.totals
+
+
+def step_roofline(totals, step_ms, what, sustained=True, traffic_key=None):
+    """The `roofline` object of a leg from a live profile of ONE of its steps: the dominant kernel class is the tcgen05 GEMM
+    (tensor bound); the depthwise / attention classes ride along as `secondary` with their own bounds."""
+    pk = measured_peaks()
+    if sustained:
+        peak, src = float(pk.get("bf16_tflops_sustained", 1422.7)), "MEASURED_PEAKS.json bf16_tflops_sustained (kernels timed inside a long step)"
+    else:
+        peak, src = float(pk.get("bf16_tflops", 1590.0)), "MEASURED_PEAKS.json bf16_tflops (burst)"
+    hbm = float(pk.get("hbm_gbs", 6485.2))
+    g = totals["gemm"]
+    if g["launches"] == 0:
+        return None
+    ach = g["flops"] / (g["ms"] * 1e-3) / 1e12
+    tr = ncu_traffic(traffic_key) if traffic_key else None
+    roof = {"bound": "tensor", "kernel": f"gemm_tn_kernel: every tcgen05 GEMM launch of one {what} (timed live, CUDA events around each launch)",
+            "achieved": ach, "peak": peak, "unit": "TFLOP/s", "frac": ach / peak, "peak_source": src,
+            "launches": g["launches"], "launch_ms": g["ms"] / g["launches"], "algorithmic_flops_per_launch": g["flops"] / g["launches"],
+            "algorithmic_bytes_per_launch": g["bytes"] / g["launches"], "share_of_step": g["ms"] / step_ms,
+            "traffic": tr["bytes_per_launch"] if tr else None, "traffic_source": tr["source"] if tr else None, "secondary": {}}
+    d = totals["depthwise"]
+    if d["launches"]:
+        roof["secondary"]["depthwise7x7"] = {
+            "bound": "hbm", "kernel": "dwconv7 forward(+LayerNorm) / data-gradient / weight-gradient launches of the step",
+            "achieved": d["bytes"] / (d["ms"] * 1e-3) / 1e9, "peak": hbm, "unit": "GB/s", "frac": d["bytes"] / (d["ms"] * 1e-3) / 1e9 / hbm,
+            "fp32_tflops": d["flops"] / (d["ms"] * 1e-3) / 1e12,
+            "fp32_peak_note": "FFMA2 measured at 118 FMA/clk/SM = 67 TFLOP/s (tools/ubench_fma.cu): 49 FMA per 4 bytes puts this operator at the FP32 pipe and the HBM roofline at the same time",
+            "launches": d["launches"], "share_of_step": d["ms"] / step_ms}
+    a = totals["attention"]
+    if a["launches"]:
+        roof["secondary"]["attention"] = {"bound": "tensor", "achieved": a["flops"] / (a["ms"] * 1e-3) / 1e12, "peak": peak, "unit": "TFLOP/s",
+                                          "frac": a["flops"] / (a["ms"] * 1e-3) / 1e12 / peak, "launches": a["launches"],
+                                          "share_of_step": a["ms"] / step_ms}
+    return roof
 
 
 def bench_extract(ctx, args):
@@ -382,56 +455,11 @@ def bench_extract(ctx, args):
 
     roof = None
     if ctx.rank == 0:
-        # the dominant kernel: gemm_tn_kernel<256, bf16> at the shapes the network launches it with
-        depths, dims = model.model.depths, model.model.dims
-        shapes = []
-        hw = (IMG // 4) ** 2
-        for s, (d, c) in enumerate(zip(depths, dims)):
-            if s > 0:
-                hw //= 4
-                shapes.append((1, B * hw, c, 4 * dims[s - 1], _lib.EPI_NONE))
-            M = B * hw
-            shapes.append((d, M, 4 * c, c, _lib.EPI_GELU))
-            if c % 256 == 0:
-                shapes.append((d, M, c, 4 * c, _lib.EPI_SCALE_RESIDUAL))
-        tot_flops, tot_ms, n_launch = 0.0, 0.0, 0
-        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        for cnt, M, N, Kd, epi in shapes:
-            a = torch.randn(M, Kd, device=ctx.dev).to(torch.bfloat16)
-            w = torch.randn(N, Kd, device=ctx.dev).to(torch.bfloat16)
-            d_ = torch.empty(M, N, device=ctx.dev, dtype=torch.bfloat16)
-            bias = torch.zeros(N, device=ctx.dev)
-            gamma = torch.ones(N, device=ctx.dev)
-            res = torch.zeros(M, N, device=ctx.dev, dtype=torch.bfloat16) if epi == _lib.EPI_SCALE_RESIDUAL else None
-            g = _lib.GemmDesc(A=a.data_ptr(), B=w.data_ptr(), D=d_.data_ptr(), M=M, N=N, K=Kd, lda=Kd, ldb=Kd, ldd=N,
-                              in_dtype=_lib.DTYPE_BF16, out_dtype=_lib.DTYPE_BF16, epilogue=epi, bias=bias.data_ptr(),
-                              gamma=gamma.data_ptr(), beta=0, residual=_lib.ptr(res), ldr=N, ln_eps=1e-6, split_k=1)
-            for _ in range(2):
-                _lib.check(lib.vdk_gemm(C.byref(g), _lib.stream_ptr()), "vdk_gemm")
-            torch.cuda.synchronize()
-            reps = 5
-            e0.record()
-            for _ in range(reps):
-                _lib.check(lib.vdk_gemm(C.byref(g), _lib.stream_ptr()), "vdk_gemm")
-            e1.record()
-            torch.cuda.synchronize()
-            t = e0.elapsed_time(e1) / reps
-            tot_flops += cnt * 2.0 * M * N * Kd
-            tot_ms += cnt * t
-            n_launch += cnt
-            del a, w, d_, res
-        peak, src = peak_tflops()
-        ach = tot_flops / (tot_ms * 1e-3) / 1e12
-        roof = {"bound": "tensor", "kernel": "gemm_tn_kernel<256,bf16> (MLP / downsample shapes of one forward)",
-                "achieved": ach, "peak": peak, "unit": "TFLOP/s", "frac": ach / peak,
-                # dram__bytes_read.sum + dram__bytes_write.sum per launch, `ncu --set full` of tools/time_extract.py 256 1
-                # (profiles/r01_traffic_gemm_ncu_raw.csv): the two stage-3 MLP launches (54 of the 72): fc1+GELU 53.6 + 147.2 MB,
-                # fc2+residual 259.1 + 32.1 MB; algorithmic bytes of the same launches: 259 / 310 MB (outputs partly still in L2)
-                "traffic": 0.5 * (200.9e6 + 291.2e6) if B == 256 else None, "traffic_unit": "bytes/launch (mean of the two captured)",
-                "peak_source": src, "launches": n_launch, "launch_ms": tot_ms / n_launch, "algorithmic_flops_per_launch": tot_flops / n_launch,
-                "share_of_step": tot_ms / ms,
-                "whole_step": {"achieved": B * GFLOP_PER_EMBEDDING / ms, "frac": B * GFLOP_PER_EMBEDDING / ms / peak,
-                               "note": "30.76 GFLOP per embedding over the whole forward"}}
+        roof = step_roofline(live_profile(step_dev), ms, f"extraction forward (batch {B})", sustained=True, traffic_key=f"extract_gemm_b{B}")
+        if roof is not None:
+            peak = roof["peak"]
+            roof["whole_step"] = {"achieved": B * GFLOP_PER_EMBEDDING / ms, "frac": B * GFLOP_PER_EMBEDDING / ms / peak,
+                                  "note": "30.76 GFLOP per embedding over the whole forward"}
     n_blocks = sum(model.model.depths)
     return {"value": value, "ms": ms, "e2e_ms": e2e_ms, "roofline": roof,
             "launches_per_step": 2 + 3 * n_blocks + 6 + 1 + 2,
@@ -478,8 +506,13 @@ def bench_extract_vit(ctx, args):
     patch, dim, depth, heads = VIT_ARCHS[name]
     T = (IMG // patch) ** 2 + 1
     gflop = (depth * (24.0 * T * dim * dim + 4.0 * T * T * dim) + 2.0 * (T - 1) * 3 * patch * patch * dim + 2.0 * T * dim * FEAT) / 1e9
-    peak, src = peak_tflops()
+    peak = float(measured_peaks().get("bf16_tflops_sustained", 1422.7))
     ach = B * gflop / ms
+    roof = step_roofline(live_profile(step_dev), ms, f"ViT-B/16 extraction forward (batch {B})") if ctx.rank == 0 else None
+    if roof is None:
+        roof = {"bound": "tensor"}
+    roof["whole_step"] = {"achieved": ach, "unit": "TFLOP/s", "peak": peak, "frac": ach / peak,
+                          "note": f"{gflop:.2f} GFLOP per embedding over the whole forward"}
     return {"metric": "embeddings/sec (ViT-B/16 224^2, CBIR extract, inference)", "value": ctx.world * B / (ms * 1e-3),
             "unit": "embeddings/s", "ms_per_step": ms, "scaling": "weak", "dtype": "bf16",
             "config": {"workload": f"CBIR eval extract: ViT-B/16 {IMG}^2 (197 tokens) -> {FEAT}-d L2-normalised embeddings, batch {B} "
@@ -487,9 +520,7 @@ def bench_extract_vit(ctx, args):
             "e2e": {"value": ctx.world * B / (e2e_ms * 1e-3), "unit": "embeddings/s", "ms_per_step": e2e_ms,
                     "h2d_bytes_per_step": B * 3 * IMG * IMG * 4, "d2h_bytes_per_step": B * FEAT * 4},
             "gpu_launches": (3 + 7 * depth + 4) * args.steps,
-            "roofline": {"bound": "tensor", "whole_step": {"achieved": ach, "unit": "TFLOP/s", "peak": peak, "frac": ach / peak,
-                                                            "peak_source": src,
-                                                            "note": f"{gflop:.2f} GFLOP per embedding over the whole forward"}}}
+            "roofline": roof}
 
 
 def bench_train(ctx, args):
@@ -545,8 +576,12 @@ def bench_train(ctx, args):
     ach = B * gflop_img / ms
     nb = sum(model.trainingwrapper["backbone"].model.depths)
     launches = (5 * nb + 6) + (3 * nb + 12) + (14 * nb + 30) + 14 + 8
+    roof = None
+    if ctx.world == 1:  # the profile needs a step without collectives in flight; N>1 lines carry the whole-step figure only
+        roof = step_roofline(live_profile(step_dev), ms, f"train step (batch {B}: forward, dgrad x gelu', weight-gradient slabs, neck, head)",
+                             sustained=True, traffic_key=f"train_gemm_b{B}")
     return {"value": value, "ms": ms, "e2e_ms": e2e_ms, "batch": B, "h2d": B * 3 * IMG * IMG * 4 + B * 8, "d2h": 4,
-            "launches_per_step": launches,
+            "launches_per_step": launches, "roofline": roof,
             "whole_step": {"achieved": ach, "unit": "TFLOP/s", "peak": peak_s, "frac": ach / peak_s,
                            "note": "92.3 GFLOP per image (3 x forward) over the whole step incl. head, clip+SGD+EMA; peak = "
                                    "MEASURED_PEAKS.json bf16_tflops_sustained (kernel inside a long step)"}}
@@ -591,6 +626,11 @@ def bench_train_vit(ctx, args):
     except Exception:
         pass
     ach = B * gflop / ms
+    roof = step_roofline(live_profile(step_dev), ms, f"ViT-B/16 train step (batch {B})") if ctx.world == 1 else None
+    if roof is None:
+        roof = {"bound": "tensor"}
+    roof["whole_step"] = {"achieved": ach, "unit": "TFLOP/s", "peak": peak_s, "frac": ach / peak_s,
+                          "note": "105.8 GFLOP per image (3 x forward) over the whole step"}
     del trainer, model
     return {"metric": "embeddings/sec (ViT-B/16 224^2 faceX CircleLoss train step)", "value": ctx.world * B / (ms * 1e-3),
             "unit": "embeddings/s", "ms_per_step": ms, "scaling": "weak", "dtype": "bf16",
@@ -598,8 +638,7 @@ def bench_train_vit(ctx, args):
                                    f"batch {B} per GPU, DDP all-reduce(mean) over {ctx.world} GPU(s)"},
             "e2e": {"value": ctx.world * B / (e2e_ms * 1e-3), "unit": "embeddings/s", "ms_per_step": e2e_ms,
                     "h2d_bytes_per_step": B * 3 * IMG * IMG * 4 + B * 8, "d2h_bytes_per_step": 4},
-            "roofline": {"bound": "tensor", "whole_step": {"achieved": ach, "unit": "TFLOP/s", "peak": peak_s, "frac": ach / peak_s,
-                                                            "note": "105.8 GFLOP per image (3 x forward) over the whole step"}}}
+            "roofline": roof}
 
 
 def bench_retrieval(ctx, args):
@@ -797,11 +836,9 @@ def main():
         common = {"n_gpus": ctx.world, "steps": args.steps, "warmup": W, "higher_is_better": True, "vs_baseline": None,
                   "data": "synthetic", "clocks": clocks}
         if tr is not None:
-            roof = dict(ex["roofline"]) if ex is not None and ex["roofline"] else None
+            roof = tr.get("roofline")
             if roof is not None:
                 roof["whole_step"] = tr["whole_step"]
-                roof["note"] = ("dominant kernel of the step = the tcgen05 GEMM; timed alone at the forward MLP/downsample "
-                                "shapes (the backward launches the same kernel with MN-major operands)")
             line = {
                 "metric": "embeddings/sec (ConvNeXt-B 224^2 faceX ArcFace train step)", "value": tr["value"],
                 "unit": "embeddings/s", "ms_per_step": tr["ms"], "scaling": "weak", "dtype": "bf16",

@@ -22,7 +22,17 @@ def compute_metrics(ids: torch.Tensor, scores: torch.Tensor, query_label: torch.
     """engine/cbir/evaluation.py:202-224 with the retrieval result as tensors: `ids`/`scores` [Nq,k] as `search` returns them
     (-1 padded), identity labels of queries and gallery items.  Keys and values as the reference's metrics dict."""
     rel, n_pos = M.relevance_from_labels(ids, query_label, gallery_label)
-    return M.cbir_metrics(ids, scores, rel, n_pos, cutoffs, metrics)
+    out: Dict[str, float] = {}
+    for m in metrics:
+        try:
+            out.update(M.cbir_metrics(ids, scores, rel, n_pos, cutoffs, [m]))
+        except ValueError as e:
+            # sklearn's roc_auc_score raises when the retrieved pairs are all relevant (or all irrelevant), which would abort the
+            # reference's in-training eval on an easy dataset; report the metric as undefined instead of losing the checkpoint
+            if m != "auc" or "one class" not in str(e):
+                raise
+            out[f"AUC@{list(cutoffs)[-1]}"] = float("nan")
+    return out
 
 
 def valuate(model, data_cfg: dict, device, logger=None, vis: bool = False, image_size: Optional[int] = None,

@@ -400,6 +400,23 @@ int vdk_ip_topk(const vdk_topk_plan* plan, const float* q32, const void* qh, con
                 const float* g_err_max, int64_t id_offset, float* out_scores, int64_t* out_ids, int32_t* status,
                 void* workspace, size_t workspace_bytes, void* stream);
 
+/* The two halves of vdk_ip_topk, for the SHARDED search (gallery rows split over GPUs, BASELINE config 4):
+ *   vdk_ip_topk_filter  scans this shard (thresholds, ranges, selects), leaves every query's candidates in `workspace` and
+ *                       writes kth_lb_out[n_query]: a lower bound of the shard's k-th largest canonical score (-inf if the
+ *                       shard holds fewer than k rows);
+ *   -- the ranks take the element-wise MAX of kth_lb over all shards (one tiny all-reduce): a lower bound of the GLOBAL
+ *      k-th canonical score --
+ *   vdk_ip_topk_rerank  re-scores canonically only the candidates that can still reach the global top-k
+ *                       (approx >= kth_lb_global - eps) and emits this shard's list, padded with (-FLT_MAX, -1).
+ * The merged result (vdk_topk_merge*) is bit-identical to the unsharded search.  kth_lb_global == NULL re-ranks everything
+ * (what vdk_ip_topk does).  Same plan, workspace and stream for both calls. */
+int vdk_ip_topk_filter(const vdk_topk_plan* plan, const void* qh, const float* q_norm, const float* q_err, const void* gh,
+                       const float* g_norm_max, const float* g_err_max, float* kth_lb_out, int32_t* status, void* workspace,
+                       size_t workspace_bytes, void* stream);
+int vdk_ip_topk_rerank(const vdk_topk_plan* plan, const float* q32, const float* g32, int64_t id_offset,
+                       const float* kth_lb_global, float* out_scores, int64_t* out_ids, void* workspace, size_t workspace_bytes,
+                       void* stream);
+
 /* Device pointer (inside `workspace`) to int32[n_query] flags the last vdk_ip_topk set for rows whose candidate lists
  * overflowed; status[0] counts them.  Their results are incomplete and must be recomputed with an all-dense plan. */
 int vdk_topk_row_flags(const vdk_topk_plan* plan, const void* workspace, size_t workspace_bytes,
@@ -441,6 +458,22 @@ int vdk_topk_merge_packed(const void* packed, int n_lists, int64_t n_query, int 
 /* Brute-force canonical scores for verification at full size: out[i] = canonical_score(q[qi[i]], g[gi[i]]). */
 int vdk_ip_exact_pairs(const float* q32, const float* g32, int dim, const int64_t* qi, const int64_t* gi, int64_t n,
                        float* out, void* stream);
+
+/* Live kernel timing inside a real step (bench.py's roofline legs; not part of the reference's surface).  Between
+ * vdk_prof_begin() and vdk_prof_end() every launch of the categories below is bracketed by two CUDA events on the stream it
+ * is launched on; vdk_prof_end synchronises on them and returns, per category, the launch count, the summed event time and
+ * the summed ALGORITHMIC flops / bytes of those launches.  Categories: 0 tcgen05 GEMM (vdk_gemm and every internal GEMM),
+ * 1 depthwise 7x7 (forward+LN, data gradient, weight gradient), 2 attention (forward, backward), 3 retrieval score/filter,
+ * 4 other.  Profiling perturbs the step (two event records per launch): never time a step with a profile open. */
+typedef struct vdk_prof_total {
+  long long launches;
+  double ms;
+  double flops;
+  double bytes;
+} vdk_prof_total;
+#define VDK_PROF_CATEGORIES 5
+int vdk_prof_begin(void);
+int vdk_prof_end(vdk_prof_total* totals, int n_categories);
 
 /* sizeof() of the by-pointer structs, in this order: vdk_gemm_desc, vdk_topk_plan, vdk_head_desc, vdk_convnext_net,
  * vdk_convnext_tensors, vdk_vit_net, vdk_vit_tensors.  Writes min(n, count) entries, returns the count: a binding checks its mirrors. */

@@ -41,6 +41,13 @@ class TopkPlan(C.Structure):
 _p, _i, _i64, _sz = C.c_void_p, C.c_int, C.c_int64, C.c_size_t
 
 
+class ProfTotal(C.Structure):
+    _fields_ = [("launches", C.c_longlong), ("ms", C.c_double), ("flops", C.c_double), ("bytes", C.c_double)]
+
+
+PROF_CATEGORIES = ("gemm", "depthwise", "attention", "score_filter", "other")
+
+
 class GemmDesc(C.Structure):
     _fields_ = [
         ("A", C.c_void_p), ("B", C.c_void_p), ("D", C.c_void_p),
@@ -58,6 +65,8 @@ SIGNATURES = {
     "vdk_struct_sizes": (_i, [_p, _i]),
     "vdk_last_error_string": (C.c_char_p, []),
     "vdk_device_check": (_i, []),
+    "vdk_prof_begin": (_i, []),
+    "vdk_prof_end": (_i, [C.POINTER(ProfTotal), _i]),
     "vdk_gemm": (_i, [_p, _p]),
     "vdk_gemm_effective_splits": (_i, [_i, _i]),
     "vdk_dwconv7_ln": (_i, [_p, _i, _i, _i, _i, _p, _p, _p, _p, C.c_float, _p, _p]),
@@ -100,6 +109,8 @@ SIGNATURES = {
     "vdk_topk_plan_default": (_i, [C.POINTER(TopkPlan), _i64, _i64, _i, _i]),
     "vdk_topk_workspace_bytes": (_sz, [C.POINTER(TopkPlan)]),
     "vdk_ip_topk": (_i, [C.POINTER(TopkPlan), _p, _p, _p, _p, _p, _p, _p, _p, _i64, _p, _p, _p, _p, _sz, _p]),
+    "vdk_ip_topk_filter": (_i, [C.POINTER(TopkPlan), _p, _p, _p, _p, _p, _p, _p, _p, _p, _sz, _p]),
+    "vdk_ip_topk_rerank": (_i, [C.POINTER(TopkPlan), _p, _p, _i64, _p, _p, _p, _p, _sz, _p]),
     "vdk_topk_row_flags": (_i, [C.POINTER(TopkPlan), _p, _sz, C.POINTER(C.c_void_p)]),
     "vdk_score_range": (_i, [C.POINTER(TopkPlan), _p, _p, _i64, _i64, _i, _p, _sz, _p]),
     "vdk_reduce_max": (_i, [_p, _i64, _p, _p]),
@@ -147,6 +158,24 @@ def check(rc: int, what: str) -> None:
 
 def require_device() -> None:
     check(load().vdk_device_check(), "vdk_device_check")
+
+
+class profile:
+    """`with _lib.profile() as p: step()` -> p.totals = {category: {launches, ms, flops, bytes}} (vdk_prof_begin / vdk_prof_end)."""
+
+    def __enter__(self):
+        check(load().vdk_prof_begin(), "vdk_prof_begin")
+        self.totals = None
+        return self
+
+    def __exit__(self, *exc):
+        arr = (ProfTotal * len(PROF_CATEGORIES))()
+        rc = load().vdk_prof_end(arr, len(PROF_CATEGORIES))
+        self.totals = {name: {"launches": int(arr[i].launches), "ms": float(arr[i].ms), "flops": float(arr[i].flops),
+                              "bytes": float(arr[i].bytes)} for i, name in enumerate(PROF_CATEGORIES)}
+        if exc[0] is None:
+            check(rc, "vdk_prof_end")
+        return False
 
 
 def ptr(t) -> int:

@@ -428,6 +428,284 @@ dwconv7_chunk_kernel(const __grid_constant__ CUtensorMap map_x, int B, int H, in
 }
 
 // ------------------------------------------------------------------------------------------------
+// the same operator, PERSISTENT and software-pipelined (the default): latency was the limiter of the kernel above
+// ------------------------------------------------------------------------------------------------
+// Measured on B200 (tools/ubench_fma.cu): FFMA2 sustains 118 FMA/clk/SM at one issue slot per 2.17 clk, i.e. the tap loop's
+// 98 FFMA2 : 83 other instructions per filter row fits the FP32 pipe's shadow — yet the one-tile-per-CTA kernel ran at 25 %
+// of that rate (IPC 0.25 per scheduler): every CTA paid tensormap prefetch + barrier init + a 43 KB TMA load + 25 KB of tap
+// staging + a cluster barrier + remote partial reads, with nothing to overlap them but two sibling CTAs in the same phase.
+// Here a CTA lives for the whole launch and keeps ONE channel chunk: the chunk's taps / bias / LayerNorm affine are staged
+// once, a producer warp streams halo tiles (TH x 7 output pixels) through a two-deep TMA / mbarrier ring, TH compute warps
+// (one output row each) run the tap loop of tile i+1 while the LayerNorm statistics of tile i cross the cluster
+// (split-phase barrier.cluster: arrive after publishing the chunk's (mean, M2), wait only after the next tile's taps).
+// LayerNorm numerics are unchanged: two-pass statistics per chunk, Chan's combination across the chunks of a pixel.
+template <int MODE, int CHUNK, int TH>
+__global__ void __launch_bounds__((TH + 1) * 32, TH == 7 ? 2 : 1)
+dwconv7_pipe_kernel(const __grid_constant__ CUtensorMap map_x, int B, int H, int W, int C, int nchunks, int n_tiles,
+                    const float* __restrict__ w49, const float* __restrict__ bias, const float* __restrict__ ln_w,
+                    const float* __restrict__ ln_b, float eps, __nv_bfloat16* __restrict__ y, float* __restrict__ rstd_out,
+                    const __nv_bfloat16* __restrict__ addend) {
+  extern __shared__ uint8_t dwp_smem_raw[];
+  uint8_t* smem = dwp_smem_raw + ((128u - (smem_u32(dwp_smem_raw) & 127u)) & 127u);
+  constexpr int box_w = kDwTW + 6, box_h = TH + 6;
+  constexpr int tile_bytes = box_h * box_w * CHUNK * 2;
+  constexpr int tile_stride = (tile_bytes + 127) & ~127;
+  float* wsm = reinterpret_cast<float*>(smem + 2 * tile_stride);   // [49][CHUNK] taps of this chunk
+  float2* part = reinterpret_cast<float2*>(wsm + 49 * CHUNK);     // [2 tile parities][TH rows][8]: (mean, M2) per pixel
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(part + 2 * TH * 8);
+  uint64_t* empty_bar = full_bar + 2;
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int ck = blockIdx.x % nchunks;  // == rank inside the cluster (MODE 0, nchunks > 1)
+  const int group = blockIdx.x / nchunks, n_groups = gridDim.x / nchunks;
+  const int tiles_w = (W + kDwTW - 1) / kDwTW, tiles_h = (H + TH - 1) / TH;
+  const int n_my = group < n_tiles ? (n_tiles - group + n_groups - 1) / n_groups : 0;
+  const bool clustered = MODE == 0 && nchunks > 1;
+
+  if (threadIdx.x == 0) {
+    prefetch_tensormap(&map_x);
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(&full_bar[i], 1);
+      mbar_init(&empty_bar[i], TH);
+    }
+    fence_mbar_init();
+  }
+  for (int i = threadIdx.x; i < 49 * (CHUNK / 4); i += blockDim.x) {
+    const int t = i / (CHUNK / 4), q = i - t * (CHUNK / 4);
+    *reinterpret_cast<float4*>(wsm + t * CHUNK + q * 4) = __ldg(reinterpret_cast<const float4*>(w49 + t * C + ck * CHUNK + q * 4));
+  }
+  __syncthreads();
+
+  auto tile_coords = [&](int it, int& b, int& oy0, int& ox0) {
+    int t = group + it * n_groups;
+    const int tw = t % tiles_w;
+    t /= tiles_w;
+    const int th = t % tiles_h;
+    b = t / tiles_h;
+    oy0 = th * TH;
+    ox0 = tw * kDwTW;
+  };
+
+  if (warp == TH) {
+    // ===================== producer: one tile ahead of the compute warps =====================
+    if (lane == 0 && n_my > 0) {
+      int b, oy0, ox0;
+      tile_coords(0, b, oy0, ox0);
+      mbar_arrive_expect_tx(&full_bar[0], tile_bytes);
+      tma_load_4d(smem, &map_x, &full_bar[0], ck * CHUNK, ox0 - 3, oy0 - 3, b);
+    }
+    for (int it = 0; it < n_my; ++it) {
+      if (lane == 0 && it + 1 < n_my) {
+        const int j = it + 1, buf = j & 1;
+        mbar_wait_relaxed(&empty_bar[buf], ((j >> 1) & 1) ^ 1);  // the tap loops of tile j - 2 are done with this buffer
+        int b, oy0, ox0;
+        tile_coords(j, b, oy0, ox0);
+        mbar_arrive_expect_tx(&full_bar[buf], tile_bytes);
+        tma_load_4d(smem + buf * tile_stride, &map_x, &full_bar[buf], ck * CHUNK, ox0 - 3, oy0 - 3, b);
+      }
+      if (clustered) {  // every thread of the cluster takes part in the per-tile barrier
+        __syncwarp();
+        cluster_arrive();
+        cluster_wait();
+      }
+    }
+    if (clustered) {
+      __syncwarp();
+      cluster_arrive();
+      cluster_wait();
+    }
+    return;
+  }
+
+  // ===================== compute warps: warp w owns output row w of every tile =====================
+  const int cl = lane * 4;
+  const bool has_c = cl < CHUNK;
+  const int c0 = ck * CHUNK + cl;
+  float4 bc = make_float4(0.f, 0.f, 0.f, 0.f), g4 = bc, b4 = bc;
+  if (has_c && MODE == 0) {
+    bc = __ldg(reinterpret_cast<const float4*>(bias + c0));
+    g4 = __ldg(reinterpret_cast<const float4*>(ln_w + c0));
+    b4 = __ldg(reinterpret_cast<const float4*>(ln_b + c0));
+  }
+  constexpr int pix_stride = CHUNK * 2;
+  const float inv_chunk = 1.0f / static_cast<float>(CHUNK), inv_c = 1.0f / static_cast<float>(C);
+
+  // tap loop of one tile row: acc[p] = bias + sum over the 7x7 window (FFMA2 over channel pairs)
+  auto conv_row = [&](const uint8_t* tile, float2 (&acc)[kDwTW][2]) {
+#pragma unroll
+    for (int p = 0; p < kDwTW; ++p) {
+      acc[p][0] = make_float2(bc.x, bc.y);
+      acc[p][1] = make_float2(bc.z, bc.w);
+    }
+    const uint8_t* tbase = tile + cl * 2;
+#pragma unroll 1
+    for (int dy = 0; dy < 7; ++dy) {
+      float2 wlo[7], whi[7];
+      const float* wrow = wsm + dy * (7 * CHUNK) + cl;
+#pragma unroll
+      for (int dx = 0; dx < 7; ++dx) {
+        const float4 t = *reinterpret_cast<const float4*>(wrow + dx * CHUNK);
+        wlo[dx] = make_float2(t.x, t.y);
+        whi[dx] = make_float2(t.z, t.w);
+      }
+      const uint8_t* rowp = tbase + (warp + dy) * (box_w * pix_stride);
+#pragma unroll
+      for (int ix = 0; ix < box_w; ++ix) {
+        const uint2 t = *reinterpret_cast<const uint2*>(rowp + ix * pix_stride);
+        const float2 a = make_float2(__uint_as_float(t.x << 16), __uint_as_float(t.x & 0xffff0000u));
+        const float2 c = make_float2(__uint_as_float(t.y << 16), __uint_as_float(t.y & 0xffff0000u));
+#pragma unroll
+        for (int p = 0; p < kDwTW; ++p) {
+          const int dx = ix - p;
+          if (dx >= 0 && dx < 7) {
+            acc[p][0] = ffma2(a, wlo[dx], acc[p][0]);
+            acc[p][1] = ffma2(c, whi[dx], acc[p][1]);
+          }
+        }
+      }
+    }
+  };
+
+  if (MODE == 1) {
+    for (int it = 0; it < n_my; ++it) {
+      const int buf = it & 1;
+      int b, oy0, ox0;
+      tile_coords(it, b, oy0, ox0);
+      const bool active = has_c && oy0 + warp < H;
+      float2 acc[kDwTW][2];
+      mbar_wait(&full_bar[buf], (it >> 1) & 1);
+      if (active) conv_row(smem + buf * tile_stride, acc);
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&empty_bar[buf]);
+      if (active) {
+#pragma unroll
+        for (int p = 0; p < kDwTW; ++p) {
+          const int ox = ox0 + p;
+          if (ox >= W) continue;
+          const int64_t off = ((static_cast<int64_t>(b) * H + oy0 + warp) * W + ox) * C + c0;
+          float o0 = acc[p][0].x, o1 = acc[p][0].y, o2 = acc[p][1].x, o3 = acc[p][1].y;
+          if (addend) {
+            const uint2 t = __ldg(reinterpret_cast<const uint2*>(addend + off));
+            const float2 a = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&t.x));
+            const float2 c = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&t.y));
+            o0 += a.x; o1 += a.y; o2 += c.x; o3 += c.y;
+          }
+          __nv_bfloat162 lo = __floats2bfloat162_rn(o0, o1), hi = __floats2bfloat162_rn(o2, o3);
+          uint2 t;
+          t.x = *reinterpret_cast<uint32_t*>(&lo);
+          t.y = *reinterpret_cast<uint32_t*>(&hi);
+          *reinterpret_cast<uint2*>(y + off) = t;
+        }
+      }
+    }
+    return;
+  }
+
+  // ---- MODE 0: conv + bias + LayerNorm over C, statistics exchanged across the cluster one tile behind the tap loop ----
+  float2 acc[kDwTW][2];     // tile whose LayerNorm is pending
+  float mean[kDwTW], m2[kDwTW];
+  int pb = 0, poy0 = 0, pox0 = 0;
+  bool pactive = false;
+
+  auto local_stats = [&](bool active, int parity) {  // two-pass (mean, centred sum of squares) of this chunk, published for the peers
+#pragma unroll
+    for (int p = 0; p < kDwTW; ++p)
+      mean[p] = warp_sum(active ? (acc[p][0].x + acc[p][0].y) + (acc[p][1].x + acc[p][1].y) : 0.f) * inv_chunk;
+#pragma unroll
+    for (int p = 0; p < kDwTW; ++p) {
+      float q = 0.f;
+      if (active) {
+        const float d0 = acc[p][0].x - mean[p], d1 = acc[p][0].y - mean[p];
+        const float d2 = acc[p][1].x - mean[p], d3 = acc[p][1].y - mean[p];
+        q = fmaf(d0, d0, fmaf(d1, d1, fmaf(d2, d2, d3 * d3)));
+      }
+      m2[p] = warp_sum(q);
+    }
+    if (clustered) {
+      float2 mine = make_float2(0.f, 0.f);
+#pragma unroll
+      for (int p = 0; p < kDwTW; ++p)
+        if (lane == p) mine = make_float2(mean[p], m2[p]);
+      if (lane < kDwTW) part[(parity * TH + warp) * 8 + lane] = mine;
+    }
+  };
+
+  auto finish = [&](int parity) {  // combine the chunks' statistics (Chan), normalise, store the pending tile
+    float rstd[kDwTW];
+    if (clustered) {
+      float2 r[kDwTW];
+#pragma unroll
+      for (int p = 0; p < kDwTW; ++p) {
+        r[p] = make_float2(0.f, 0.f);
+        if (lane < nchunks) r[p] = ld_dsmem_f2(part + (parity * TH + warp) * 8 + p, static_cast<uint32_t>(lane));
+      }
+      const float inv_n = 1.0f / static_cast<float>(nchunks);
+#pragma unroll
+      for (int p = 0; p < kDwTW; ++p) {
+        const float m = warp_sum(r[p].x) * inv_n;
+        const float d = r[p].x - m;
+        const float q = warp_sum(lane < nchunks ? fmaf(static_cast<float>(CHUNK) * d, d, r[p].y) : 0.f);
+        mean[p] = m;
+        rstd[p] = rsqrtf(q * inv_c + eps);
+      }
+    } else {
+#pragma unroll
+      for (int p = 0; p < kDwTW; ++p) rstd[p] = rsqrtf(m2[p] * inv_c + eps);
+    }
+    if (pactive) {
+#pragma unroll
+      for (int p = 0; p < kDwTW; ++p) {
+        const int ox = pox0 + p;
+        if (ox >= W) continue;
+        const int64_t pix = (static_cast<int64_t>(pb) * H + poy0 + warp) * W + ox;
+        if (rstd_out != nullptr && lane == 0 && ck == 0) rstd_out[pix] = rstd[p];
+        __nv_bfloat16* dst = y + pix * C + c0;
+        __nv_bfloat162 lo = __floats2bfloat162_rn((acc[p][0].x - mean[p]) * rstd[p] * g4.x + b4.x,
+                                                  (acc[p][0].y - mean[p]) * rstd[p] * g4.y + b4.y);
+        __nv_bfloat162 hi = __floats2bfloat162_rn((acc[p][1].x - mean[p]) * rstd[p] * g4.z + b4.z,
+                                                  (acc[p][1].y - mean[p]) * rstd[p] * g4.w + b4.w);
+        uint2 t;
+        t.x = *reinterpret_cast<uint32_t*>(&lo);
+        t.y = *reinterpret_cast<uint32_t*>(&hi);
+        *reinterpret_cast<uint2*>(dst) = t;
+      }
+    }
+  };
+
+  for (int it = 0; it < n_my; ++it) {
+    const int buf = it & 1;
+    int b, oy0, ox0;
+    tile_coords(it, b, oy0, ox0);
+    const bool active = has_c && oy0 + warp < H;
+    float2 nxt[kDwTW][2];
+    mbar_wait(&full_bar[buf], (it >> 1) & 1);
+    if (active) conv_row(smem + buf * tile_stride, nxt);
+    __syncwarp();
+    if (lane == 0) mbar_arrive(&empty_bar[buf]);
+    if (it > 0) {  // the previous tile: its statistics have had a whole tap loop to cross the cluster
+      if (clustered) cluster_wait();
+      finish((it - 1) & 1);
+    }
+#pragma unroll
+    for (int p = 0; p < kDwTW; ++p) {
+      acc[p][0] = nxt[p][0];
+      acc[p][1] = nxt[p][1];
+    }
+    pb = b; poy0 = oy0; pox0 = ox0; pactive = active;
+    local_stats(active, buf);
+    if (clustered) cluster_arrive();
+  }
+  if (n_my > 0) {
+    if (clustered) cluster_wait();
+    finish((n_my - 1) & 1);
+  }
+  if (clustered) {  // no CTA of the cluster leaves while a peer may still read its partials
+    cluster_arrive();
+    cluster_wait();
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
 // LayerNorm over C of NHWC rows, optionally scattered into 2x2/stride-2 patch rows (kh, kw, c)
 // ------------------------------------------------------------------------------------------------
 template <int LPP>  // lanes per pixel (8, 16 or 32); each lane owns 8-channel (16-byte) vectors c = (sub + i*LPP)*8
@@ -600,11 +878,85 @@ static int launch_dwconv_tw(const CUtensorMap& mx, int batch, int H, int W, int 
   return VDK_OK;
 }
 
+
+// Persistent launch: one CTA per SM (two for the 7-row tile), grid = co-resident clusters x chunks.
+template <int MODE, int CHUNK, int TH>
+static int launch_dwconv7_pipe_t(const __nv_bfloat16* x, int batch, int H, int W, int C, const float* w49, const float* bias,
+                                 const float* ln_w, const float* ln_b, float eps, __nv_bfloat16* y, float* rstd_out,
+                                 const __nv_bfloat16* addend, cudaStream_t s) {
+  const int nchunks = C / CHUNK;
+  constexpr int tile_stride = ((TH + 6) * (kDwTW + 6) * CHUNK * 2 + 127) & ~127;
+  constexpr int smem = 2 * tile_stride + 49 * CHUNK * 4 + 2 * TH * 8 * 8 + 4 * 8 + 128;
+  static_assert(smem <= 227 * 1024, "dwconv7_pipe shared memory budget");
+  CUtensorMap mx;
+  int rc = make_tma_nhwc_16bit(&mx, x, batch, H, W, C, TH + 6, kDwTW + 6, CHUNK);
+  if (rc != VDK_OK) return rc;
+  auto kern = dwconv7_pipe_kernel<MODE, CHUNK, TH>;
+  const int cluster = (MODE == 0) ? nchunks : 1;
+  struct Fit { int clusters; };
+  static Fit fit[17] = {};  // per cluster size: co-resident clusters of this instantiation (queried once)
+  cudaLaunchConfig_t cfg{};
+  cfg.blockDim = dim3((TH + 1) * 32);
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = s;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = cluster;
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  if (fit[cluster].clusters == 0) {
+    VDK_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    if (cluster > 8) VDK_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeNonPortableClusterSizeAllowed, 1));
+    cfg.gridDim = dim3(cluster * sm_count());
+    int n = 0;
+    if (cudaOccupancyMaxActiveClusters(&n, kern, &cfg) != cudaSuccess || n <= 0) {
+      cudaGetLastError();
+      fit[cluster].clusters = -1;
+    } else {
+      fit[cluster].clusters = n;
+    }
+  }
+  if (fit[cluster].clusters < 0) return VDK_ERR_WORKSPACE;
+  const int n_tiles = batch * ((H + TH - 1) / TH) * ((W + kDwTW - 1) / kDwTW);
+  const int groups = std::min(n_tiles, fit[cluster].clusters);
+  cfg.gridDim = dim3(static_cast<unsigned>(groups) * nchunks);
+  if (MODE == 1) {
+    // no cluster: any CTA is a "group member"; spread tiles x chunks over every SM slot
+    const int slots = fit[cluster].clusters;
+    const int g = std::max(1, std::min(n_tiles, slots / nchunks));
+    cfg.gridDim = dim3(static_cast<unsigned>(g) * nchunks);
+  }
+  VDK_CUDA_OK(cudaLaunchKernelEx(&cfg, kern, mx, batch, H, W, C, nchunks, n_tiles, w49, bias, ln_w, ln_b, eps, y, rstd_out, addend));
+  return VDK_OK;
+}
+
+static int launch_dwconv7_pipe(int mode, const __nv_bfloat16* x, int batch, int H, int W, int C, int chunk, const float* w49,
+                               const float* bias, const float* ln_w, const float* ln_b, float eps, __nv_bfloat16* y, float* rstd_out,
+                               const __nv_bfloat16* addend, cudaStream_t s) {
+  const bool tall = H > 7;  // 14-row tiles (15 warps, one CTA per SM) unless the map is 7 rows high
+#define VDK_DWP(MODEV, CHV)                                                                                                     \
+  return tall ? launch_dwconv7_pipe_t<MODEV, CHV, 14>(x, batch, H, W, C, w49, bias, ln_w, ln_b, eps, y, rstd_out, addend, s)   \
+              : launch_dwconv7_pipe_t<MODEV, CHV, 7>(x, batch, H, W, C, w49, bias, ln_w, ln_b, eps, y, rstd_out, addend, s)
+  if (mode == 0) {
+    if (chunk == 128) { VDK_DWP(0, 128); }
+    if (chunk == 96) { VDK_DWP(0, 96); }
+    VDK_DWP(0, 64);
+  }
+  if (chunk == 128) { VDK_DWP(1, 128); }
+  if (chunk == 96) { VDK_DWP(1, 96); }
+  VDK_DWP(1, 64);
+#undef VDK_DWP
+}
+
 // mode 0: forward conv + bias + LayerNorm (rstd_out optional); mode 1: plain conv with `w49` (+ addend)
 int vdk::launch_dwconv7(int mode, const __nv_bfloat16* x, int batch, int H, int W, int C, const float* w49, const float* bias,
                           const float* ln_w, const float* ln_b, float eps, __nv_bfloat16* y, float* rstd_out,
                           const __nv_bfloat16* addend, cudaStream_t s) {
   VDK_REQUIRE(C % 8 == 0 && C <= 2048, "dwconv7: C must be a multiple of 8, <= 2048 (got %d)", C);
+  const double dw_elems = static_cast<double>(batch) * H * W * C;
+  ProfScope prof(kProfDepthwise, 2.0 * 49.0 * dw_elems, 2.0 * dw_elems * (addend ? 3.0 : 2.0), s);  // read x (+ addend), write y
   {
     // channel-chunked kernel (clustered LayerNorm) whenever C splits into <= 16 chunks of <= 128 channels
     int chunk = 0;
@@ -615,6 +967,14 @@ int vdk::launch_dwconv7(int mode, const __nv_bfloat16* x, int batch, int H, int 
       const char* e = getenv("VDK_DWCONV_CHUNKED");
       return e ? atoi(e) != 0 : true;
     }();
+    static const bool use_pipe = [] {
+      const char* e = getenv("VDK_DWCONV_PIPE");
+      return e ? atoi(e) != 0 : true;
+    }();
+    if (use_pipe && chunk > 0 && C / chunk <= 16) {
+      const int rc = launch_dwconv7_pipe(mode, x, batch, H, W, C, chunk, w49, bias, ln_w, ln_b, eps, y, rstd_out, addend, s);
+      if (rc != VDK_ERR_WORKSPACE) return rc;  // VDK_ERR_WORKSPACE: the persistent grid does not fit this device -> fall through
+    }
     if (use_chunked && chunk > 0 && C / chunk <= 16) {
       const int nchunks = C / chunk;
       const int TH = std::min(7, H);

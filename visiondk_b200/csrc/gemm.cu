@@ -860,6 +860,12 @@ int gemm_run(const vdk_gemm_desc& g, cudaStream_t s) {
                g.ln_eps, split, tma_store, g.trans_a ? 1 : 0, g.trans_b ? 1 : 0, g.split_k > 1 ? (long long)g.split_stride : 0ll,
                aux_out, (g.split_k > 1) ? 1 : 0};
   const bool bf = g.in_dtype == VDK_DTYPE_BF16;
+  // algorithmic bytes: both operands once, the output once (x2 for an auxiliary 16-bit output), a 16-bit residual / saved tile once
+  const double osz = g.out_dtype == VDK_DTYPE_FP32 ? 4.0 : 2.0;
+  ProfScope prof(kProfGemm, 2.0 * g.M * g.N * g.K,
+                 2.0 * (static_cast<double>(g.M) * g.K + static_cast<double>(g.N) * g.K) + osz * g.M * g.N * (g.split_k > 1 ? split : 1) +
+                     (g.aux_out ? 2.0 * g.M * g.N : 0.0) + (g.residual ? osz * g.M * g.N : 0.0),
+                 s);
   // which epilogues take the pipelined auxiliary-tile variant (VDK_GEMM_AUXPIPE: bit 0 aux_out, bit 1 MUL_GELU_GRAD,
   // bit 2 SCALE_RESIDUAL; a tuning switch.  Measured at ConvNeXt-B
   // shapes: the GELU' data gradient gains 24 %, the layer-scale + residual GEMM (K = 4C: mainloop-bound) loses 8 % to the

@@ -349,17 +349,27 @@ struct SelectParams {
   const float* eps;       // per-query bound on |approx - canonical|
   int32_t* status;        // {overflow_rows, max_candidates, max_survivors, reserved}
   int32_t* row_flag;      // [n_query] set to 1 for rows whose lists overflowed (results incomplete)
+  float* kth_lb;          // [n_query] optional: lower bound of the k-th largest canonical score of this shard
+  int stage_cap;          // entries of dynamic shared memory available for staging (<= kSelStage)
 };
 
+// Rows whose lists hold at most kSelStage entries in total (every sparse range in practice: ~110 carried + a few hundred
+// admitted; the dense first range: 4096) are first gathered into ONE contiguous shared-memory array — every global load of the
+// row is issued at once instead of 33 short dependent sweeps per radix pass — and the four radix passes and the compaction
+// then run out of shared memory.  Longer rows keep sweeping the lists in place.
+constexpr int kSelStage = 4096;
+
 __global__ void __launch_bounds__(kSelThreads) select_kernel(const SelectParams p) {
+  extern __shared__ uint2 s_stage[];  // [p.stage_cap]
   __shared__ unsigned hist[256];
   __shared__ unsigned s_cnt[kMaxSeg + 1];
+  __shared__ unsigned s_off[kMaxSeg + 2];
   __shared__ unsigned s_bin, s_krem, s_m, s_over;
   const int row = blockIdx.x;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
 
   // entry lists of this row: list 0 = carry, lists 1.. = segments (or one dense list)
-  const int n_lists = 1 + (p.dense_n > 0 ? 1 : p.n_seg);
+  int n_lists = 1 + (p.dense_n > 0 ? 1 : p.n_seg);
   if (tid == 0) {
     s_over = 0;
     s_m = 0;
@@ -375,23 +385,54 @@ __global__ void __launch_bounds__(kSelThreads) select_kernel(const SelectParams 
     }
   }
   __syncthreads();
-  auto list_ptr = [&](int l) -> const uint2* {
+  if (tid == 0) {
+    unsigned acc = 0;
+    for (int l = 0; l < n_lists; ++l) {
+      s_off[l] = acc;
+      acc += s_cnt[l];
+    }
+    s_off[n_lists] = acc;
+  }
+  __syncthreads();
+  const unsigned n = s_off[n_lists];
+  auto list_ptr_g = [&](int l) -> const uint2* {
     if (l == 0) return p.carry_in + static_cast<size_t>(row) * p.carry_cap;
     return p.seg + static_cast<size_t>(row) * p.seg_stride + static_cast<size_t>(l - 1) * (p.dense_n > 0 ? 0 : p.seg_cap);
   };
-  unsigned n = 0;
-  for (int l = 0; l < n_lists; ++l) n += s_cnt[l];
+  const bool staged = n <= static_cast<unsigned>(p.stage_cap);
+  if (staged) {
+    for (int l = warp; l < n_lists; l += kSelThreads / 32) {
+      const unsigned c = s_cnt[l];
+      if (c > kShortList) continue;
+      const uint2* e = list_ptr_g(l);
+      const unsigned o = s_off[l];
+      for (unsigned i = lane; i < c; i += 32) s_stage[o + i] = e[i];
+    }
+    for (int l = 0; l < n_lists; ++l) {
+      const unsigned c = s_cnt[l];
+      if (c <= kShortList) continue;
+      const uint2* e = list_ptr_g(l);
+      const unsigned o = s_off[l];
+      for (unsigned i = tid; i < c; i += kSelThreads) s_stage[o + i] = e[i];
+    }
+    __syncthreads();
+    if (tid == 0) s_cnt[0] = n;
+    n_lists = 1;
+    __syncthreads();
+  }
+  auto list_ptr = [&](int l) -> const uint2* { return staged ? s_stage : list_ptr_g(l); };
 
   // ---- radix select of the k-th largest key over all lists (4 x 8 bits, MSB first) ----
   float tau_use = -INFINITY;
+  float kth_approx = -INFINITY;
   if (n >= static_cast<unsigned>(p.k)) {
     uint32_t prefix = 0, mask = 0;
     unsigned k_rem = static_cast<unsigned>(p.k);
     for (int shift = 24; shift >= 0; shift -= 8) {
       for (int i = tid; i < 256; i += kSelThreads) hist[i] = 0;
       __syncthreads();
-      // long lists (the dense first range) are swept by the whole CTA, short ones (a segment holds tens of
-      // entries) by one warp each, so that 30+ nearly empty lists do not cost 30+ CTA-wide loop trips
+      // long lists are swept by the whole CTA, short ones (a segment holds tens of entries) by one warp each, so that
+      // 30+ nearly empty lists do not cost 30+ CTA-wide loop trips
       for (int l = 0; l < n_lists; ++l) {
         const unsigned c = s_cnt[l];
         if (c <= kShortList) continue;
@@ -441,7 +482,8 @@ __global__ void __launch_bounds__(kSelThreads) select_kernel(const SelectParams 
       __syncthreads();
     }
     // admission bound: everything within 2*eps below the k-th largest approximate score may be a true top-k member
-    tau_use = unord_u32(prefix) - 2.0f * p.eps[row];
+    kth_approx = unord_u32(prefix);
+    tau_use = kth_approx - 2.0f * p.eps[row];
   }
 
   // ---- compaction of the survivors into the other carry buffer ----
@@ -475,6 +517,9 @@ __global__ void __launch_bounds__(kSelThreads) select_kernel(const SelectParams 
     const unsigned m = s_m;
     p.carry_cnt[row] = min(m, static_cast<unsigned>(p.carry_cap));
     p.tau[row] = tau_use;
+    // a lower bound of this shard's k-th largest CANONICAL score (|approx - canonical| <= eps): what the ranks of a sharded
+    // search exchange (max) to skip re-ranking candidates that cannot reach the global top-k
+    if (p.kth_lb) p.kth_lb[row] = kth_approx - p.eps[row];
     if (s_over || m > static_cast<unsigned>(p.carry_cap)) {
       if (atomicExch(&p.row_flag[row], 1) == 0) atomicAdd(&p.status[0], 1);  // count each row once
     }
@@ -498,21 +543,34 @@ struct RerankParams {
   int64_t id_offset;
   float* out_scores;
   int64_t* out_ids;
+  const float* kth_lb;  // optional [n_query]: lower bound of the GLOBAL k-th canonical score (max over shards)
+  const float* eps;     // per-query bound on |approx - canonical|
 };
 
 __global__ void __launch_bounds__(kRerankThreads) rerank_kernel(const RerankParams p) {
-  extern __shared__ unsigned long long s_sort[];  // [pow2 >= m]
+  extern __shared__ unsigned long long s_sort[];  // [pow2 >= m] sort keys, then [carry_cap] uint32 kept candidate slots
+  __shared__ unsigned s_keep;
   const int row = blockIdx.x;
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   constexpr int nwarps = kRerankThreads / 32;
-  const int m = static_cast<int>(min(p.carry_cnt[row], static_cast<unsigned>(p.carry_cap)));
+  const int m_all = static_cast<int>(min(p.carry_cnt[row], static_cast<unsigned>(p.carry_cap)));
   const uint2* e = p.carry + static_cast<size_t>(row) * p.carry_cap;
   const float* q = p.q32 + static_cast<size_t>(row) * p.dim;
+  uint32_t* keep = reinterpret_cast<uint32_t*>(s_sort + p.carry_cap);
+  // sharded search: a candidate whose approximate score is below (global k-th canonical lower bound) - eps cannot be in the
+  // global top-k (canonical >= bound implies approx >= bound - eps), so its 2 KB row is never fetched
+  const float thr = p.kth_lb ? p.kth_lb[row] - p.eps[row] : -INFINITY;
+  if (tid == 0) s_keep = 0;
+  __syncthreads();
+  for (int c = tid; c < m_all; c += kRerankThreads)
+    if (__uint_as_float(e[c].x) >= thr) keep[atomicAdd(&s_keep, 1u)] = static_cast<uint32_t>(c);
+  __syncthreads();
+  const int m = static_cast<int>(s_keep);
   // two candidates per warp iteration: their row loads are independent, which hides the gather latency
   for (int c = warp * 2; c < m; c += nwarps * 2) {
-    const uint32_t gi0 = e[c].y;
+    const uint32_t gi0 = e[keep[c]].y;
     const bool has1 = c + 1 < m;
-    const uint32_t gi1 = has1 ? e[c + 1].y : gi0;
+    const uint32_t gi1 = has1 ? e[keep[c + 1]].y : gi0;
     const float* g0 = p.g32 + static_cast<size_t>(gi0) * p.dim;
     const float* g1 = p.g32 + static_cast<size_t>(gi1) * p.dim;
     double a0 = 0.0, a1 = 0.0;
@@ -564,7 +622,8 @@ __global__ void __launch_bounds__(kRerankThreads) rerank_kernel(const RerankPara
 
 __global__ void eps_kernel(const float* __restrict__ q_norm, const float* __restrict__ q_err,
                            const float* __restrict__ g_norm_max, const float* __restrict__ g_err_max, int n,
-                           float* __restrict__ eps, float* __restrict__ tau, unsigned* __restrict__ carry_cnt) {
+                           float* __restrict__ eps, float* __restrict__ tau, unsigned* __restrict__ carry_cnt,
+                           float* __restrict__ kth_lb) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
   const float gn = g_norm_max ? *g_norm_max : 0.f, ge = g_err_max ? *g_err_max : 0.f;
@@ -574,6 +633,7 @@ __global__ void eps_kernel(const float* __restrict__ q_norm, const float* __rest
   eps[i] = e * 1.0001f + 1e-30f;
   tau[i] = -INFINITY;
   carry_cnt[i] = 0;
+  kth_lb[i] = -INFINITY;
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -789,12 +849,13 @@ struct TopkWorkspace {
   float* tau;
   float* eps;
   int32_t* row_flag;
+  float* kth_lb;
 };
 static size_t align256(size_t v) { return (v + 255) & ~static_cast<size_t>(255); }
 static size_t workspace_bytes(int64_t nq, int seg_stride, int carry_cap) {
   const size_t n = static_cast<size_t>(nq);
   return align256(n * seg_stride * sizeof(uint2)) + 2 * align256(n * carry_cap * sizeof(uint2)) +
-         align256(n * kMaxSeg * sizeof(unsigned)) + 4 * align256(n * sizeof(float)) + 256;
+         align256(n * kMaxSeg * sizeof(unsigned)) + 5 * align256(n * sizeof(float)) + 256;
 }
 static TopkWorkspace carve_workspace(void* workspace, int64_t nq, int seg_stride, int carry_cap) {
   const size_t n = static_cast<size_t>(nq);
@@ -815,6 +876,8 @@ static TopkWorkspace carve_workspace(void* workspace, int64_t nq, int seg_stride
   w.eps = reinterpret_cast<float*>(ws);
   ws += align256(n * sizeof(float));
   w.row_flag = reinterpret_cast<int32_t*>(ws);
+  ws += align256(n * sizeof(float));
+  w.kth_lb = reinterpret_cast<float*>(ws);
   return w;
 }
 
@@ -874,6 +937,8 @@ static int launch_score_range(const CUtensorMap& mq, const CUtensorMap& mg, int 
   const int units = p.n_qtiles * p.n_splits;
   const int grid = std::min(units, sms);
   const int smem = score_smem_bytes(p.num_kb);
+  ProfScope prof(kProfScoreFilter, 2.0 * dim * static_cast<double>(nq) * static_cast<double>(hi - lo),
+                 2.0 * dim * (static_cast<double>(hi - lo) + static_cast<double>(nq) * p.n_splits), s);
   if (dense)
     score_filter_kernel<true><<<grid, kScoreThreads, smem, s>>>(mq, mg, p);
   else
@@ -962,30 +1027,34 @@ static int check_plan(const vdk_topk_plan* plan) {
   return VDK_OK;
 }
 
-extern "C" int vdk_ip_topk(const vdk_topk_plan* plan, const float* q32, const void* qh, const float* q_norm,
-                           const float* q_err, const float* g32, const void* gh, const float* g_norm_max,
-                           const float* g_err_max, int64_t id_offset, float* out_scores, int64_t* out_ids,
-                           int32_t* status, void* workspace, size_t workspace_bytes, void* stream) {
+// The scan half of vdk_ip_topk: thresholds, gallery ranges, selects.  Leaves every query's surviving candidates in the
+// workspace (carry list) and, if `kth_lb_out` is given, a lower bound of the shard's k-th largest canonical score per query.
+static int topk_filter(const vdk_topk_plan* plan, const void* qh, const float* q_norm, const float* q_err, const void* gh,
+                       const float* g_norm_max, const float* g_err_max, int32_t* status, void* workspace, size_t workspace_bytes,
+                       cudaStream_t s) {
   int rc = check_plan(plan);
   if (rc != VDK_OK) return rc;
-  VDK_REQUIRE(out_scores && out_ids && status, "vdk_ip_topk: null output");
+  VDK_REQUIRE(status, "vdk_ip_topk: null status");
   const int64_t nq = plan->n_query, ng = plan->n_gallery;
   const int dim = plan->dim, k = plan->k, seg_stride = plan->cand_capacity, carry_cap = plan->carry_capacity;
-  cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
   VDK_CUDA_OK(cudaMemsetAsync(status, 0, 4 * sizeof(int32_t), s));
   if (nq == 0) return VDK_OK;
-  VDK_REQUIRE(q32 && qh && q_norm && q_err, "vdk_ip_topk: null query operand");
+  VDK_REQUIRE(qh && q_norm && q_err, "vdk_ip_topk: null query operand");
   VDK_REQUIRE(workspace && workspace_bytes >= vdk_topk_workspace_bytes(plan), "vdk_ip_topk: workspace too small");
   VDK_REQUIRE((reinterpret_cast<uintptr_t>(workspace) & 255) == 0, "vdk_ip_topk: workspace must be 256-byte aligned");
-  if (ng > 0) VDK_REQUIRE(g32 && gh && g_norm_max && g_err_max, "vdk_ip_topk: null gallery operand");
+  if (ng > 0) VDK_REQUIRE(gh && g_norm_max && g_err_max, "vdk_ip_topk: null gallery operand");
 
   const TopkWorkspace w = carve_workspace(workspace, nq, seg_stride, carry_cap);
   VDK_CUDA_OK(cudaMemsetAsync(w.row_flag, 0, static_cast<size_t>(nq) * sizeof(int32_t), s));
   eps_kernel<<<(static_cast<int>(nq) + 255) / 256, 256, 0, s>>>(q_norm, q_err, ng > 0 ? g_norm_max : nullptr,
                                                                  ng > 0 ? g_err_max : nullptr, static_cast<int>(nq),
-                                                                 w.eps, w.tau, w.carry_cnt);
+                                                                 w.eps, w.tau, w.carry_cnt, w.kth_lb);
   VDK_CUDA_OK(cudaGetLastError());
-
+  static bool sel_attr = false;
+  if (!sel_attr) {
+    VDK_CUDA_OK(cudaFuncSetAttribute(select_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSelStage * sizeof(uint2)));
+    sel_attr = true;
+  }
   int cur = 0;  // carry buffer holding the current survivors
   if (ng > 0) {
     CUtensorMap mq, mg;
@@ -1019,17 +1088,48 @@ extern "C" int vdk_ip_topk(const vdk_topk_plan* plan, const float* q32, const vo
       sp.eps = w.eps;
       sp.status = status;
       sp.row_flag = w.row_flag;
-      select_kernel<<<static_cast<unsigned>(nq), kSelThreads, 0, s>>>(sp);
+      sp.kth_lb = w.kth_lb;
+      // staging area: the dense first range needs room for every score of the range, a sparse range for a few hundred
+      sp.stage_cap = dense ? kSelStage : kSelStage / 2;
+      select_kernel<<<static_cast<unsigned>(nq), kSelThreads, sp.stage_cap * sizeof(uint2), s>>>(sp);
       VDK_CUDA_OK(cudaGetLastError());
       cur ^= 1;
       lo = hi;
     }
   }
+  return VDK_OK;
+}
+
+// carry buffer that holds the survivors after topk_filter ran this plan
+static int final_carry(const vdk_topk_plan* plan) {
+  int cur = 0;
+  int64_t lo = 0;
+  if (plan->n_gallery > 0)
+    for (int st = 0; st < plan->n_stages; ++st) {
+      const int64_t hi = plan->stage_end[st];
+      if (hi == lo) continue;
+      cur ^= 1;
+      lo = hi;
+    }
+  return cur;
+}
+
+static int topk_rerank(const vdk_topk_plan* plan, const float* q32, const float* g32, int64_t id_offset, const float* kth_lb_global,
+                       float* out_scores, int64_t* out_ids, void* workspace, size_t workspace_bytes, cudaStream_t s) {
+  int rc = check_plan(plan);
+  if (rc != VDK_OK) return rc;
+  VDK_REQUIRE(out_scores && out_ids, "vdk_ip_topk: null output");
+  const int64_t nq = plan->n_query;
+  if (nq == 0) return VDK_OK;
+  VDK_REQUIRE(q32 && (g32 || plan->n_gallery == 0), "vdk_ip_topk: null fp32 rows");
+  VDK_REQUIRE(workspace && workspace_bytes >= vdk_topk_workspace_bytes(plan), "vdk_ip_topk: workspace too small");
+  const int carry_cap = plan->carry_capacity;
+  const TopkWorkspace w = carve_workspace(workspace, nq, plan->cand_capacity, carry_cap);
   RerankParams rp{};
   rp.n_query = static_cast<int>(nq);
-  rp.dim = dim;
-  rp.k = k;
-  rp.carry = w.carry[cur];
+  rp.dim = plan->dim;
+  rp.k = plan->k;
+  rp.carry = w.carry[final_carry(plan)];
   rp.carry_cnt = w.carry_cnt;
   rp.carry_cap = carry_cap;
   rp.q32 = q32;
@@ -1037,9 +1137,42 @@ extern "C" int vdk_ip_topk(const vdk_topk_plan* plan, const float* q32, const vo
   rp.id_offset = id_offset;
   rp.out_scores = out_scores;
   rp.out_ids = out_ids;
-  rerank_kernel<<<static_cast<unsigned>(nq), kRerankThreads, carry_cap * sizeof(unsigned long long), s>>>(rp);
+  rp.kth_lb = kth_lb_global;
+  rp.eps = w.eps;
+  rerank_kernel<<<static_cast<unsigned>(nq), kRerankThreads, carry_cap * (sizeof(unsigned long long) + sizeof(uint32_t)), s>>>(rp);
   VDK_CUDA_OK(cudaGetLastError());
   return VDK_OK;
+}
+
+extern "C" int vdk_ip_topk(const vdk_topk_plan* plan, const float* q32, const void* qh, const float* q_norm,
+                           const float* q_err, const float* g32, const void* gh, const float* g_norm_max,
+                           const float* g_err_max, int64_t id_offset, float* out_scores, int64_t* out_ids,
+                           int32_t* status, void* workspace, size_t workspace_bytes, void* stream) {
+  cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
+  VDK_REQUIRE(out_scores && out_ids && status, "vdk_ip_topk: null output");
+  int rc = topk_filter(plan, qh, q_norm, q_err, gh, g_norm_max, g_err_max, status, workspace, workspace_bytes, s);
+  if (rc != VDK_OK) return rc;
+  return topk_rerank(plan, q32, g32, id_offset, nullptr, out_scores, out_ids, workspace, workspace_bytes, s);
+}
+
+extern "C" int vdk_ip_topk_filter(const vdk_topk_plan* plan, const void* qh, const float* q_norm, const float* q_err,
+                                  const void* gh, const float* g_norm_max, const float* g_err_max, float* kth_lb_out,
+                                  int32_t* status, void* workspace, size_t workspace_bytes, void* stream) {
+  cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
+  int rc = topk_filter(plan, qh, q_norm, q_err, gh, g_norm_max, g_err_max, status, workspace, workspace_bytes, s);
+  if (rc != VDK_OK) return rc;
+  if (kth_lb_out && plan->n_query > 0) {
+    const TopkWorkspace w = carve_workspace(workspace, plan->n_query, plan->cand_capacity, plan->carry_capacity);
+    VDK_CUDA_OK(cudaMemcpyAsync(kth_lb_out, w.kth_lb, static_cast<size_t>(plan->n_query) * sizeof(float), cudaMemcpyDeviceToDevice, s));
+  }
+  return VDK_OK;
+}
+
+extern "C" int vdk_ip_topk_rerank(const vdk_topk_plan* plan, const float* q32, const float* g32, int64_t id_offset,
+                                  const float* kth_lb_global, float* out_scores, int64_t* out_ids, void* workspace,
+                                  size_t workspace_bytes, void* stream) {
+  return topk_rerank(plan, q32, g32, id_offset, kth_lb_global, out_scores, out_ids, workspace, workspace_bytes,
+                     reinterpret_cast<cudaStream_t>(stream));
 }
 
 extern "C" int vdk_topk_merge(const float* scores, const int64_t* ids, int n_lists, int64_t n_query, int k,

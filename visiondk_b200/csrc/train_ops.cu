@@ -407,6 +407,9 @@ dwconv7_wgrad_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_con
 
 int launch_dwconv7_wgrad(const __nv_bfloat16* x, const __nv_bfloat16* dconv, int B, int H, int W, int C, float* dw49,
                          float* dbias, cudaStream_t s) {
+  const double wg_elems = static_cast<double>(B) * H * W * C;
+  ProfScope prof(kProfDepthwise, 2.0 * 49.0 * wg_elems, 2.0 * 2.0 * wg_elems, s);  // read x and the output gradient
+
   VDK_REQUIRE(C % kWgC == 0, "dwconv7_wgrad: C must be a multiple of %d (got %d)", kWgC, C);
   const int T = std::min(kWgT, std::max(H, W));
   CUtensorMap mx, mg;

@@ -3,6 +3,7 @@
 
 #include <cstring>
 #include <mutex>
+#include <vector>
 
 namespace vdk {
 
@@ -80,6 +81,32 @@ int make_tma_nhwc_16bit(CUtensorMap* map, const void* base, int B, int H, int W,
   return VDK_OK;
 }
 
+// ---- live profile (see vdk_host.h) ----
+struct ProfRecord {
+  int category;
+  double flops, bytes;
+  cudaEvent_t e0, e1;
+};
+static bool g_prof_on = false;
+static std::vector<ProfRecord> g_prof;
+static std::mutex g_prof_mu;
+
+ProfScope::ProfScope(int category, double flops, double bytes, cudaStream_t s) : slot(-1), stream(s) {
+  if (!g_prof_on) return;
+  std::lock_guard<std::mutex> lock(g_prof_mu);
+  ProfRecord r{category, flops, bytes, nullptr, nullptr};
+  if (cudaEventCreate(&r.e0) != cudaSuccess || cudaEventCreate(&r.e1) != cudaSuccess) return;
+  cudaEventRecord(r.e0, s);
+  g_prof.push_back(r);
+  slot = static_cast<int>(g_prof.size()) - 1;
+}
+
+ProfScope::~ProfScope() {
+  if (slot < 0) return;
+  std::lock_guard<std::mutex> lock(g_prof_mu);
+  if (slot < static_cast<int>(g_prof.size())) cudaEventRecord(g_prof[slot].e1, stream);
+}
+
 int sm_count() {
   static int n = 0;
   if (n == 0) {
@@ -106,6 +133,40 @@ int vdk_struct_sizes(size_t* out, int n) {
 }
 
 const char* vdk_last_error_string(void) { return vdk::t_error; }
+
+int vdk_prof_begin(void) {
+  std::lock_guard<std::mutex> lock(vdk::g_prof_mu);
+  for (auto& r : vdk::g_prof) {
+    cudaEventDestroy(r.e0);
+    cudaEventDestroy(r.e1);
+  }
+  vdk::g_prof.clear();
+  vdk::g_prof_on = true;
+  return VDK_OK;
+}
+
+int vdk_prof_end(vdk_prof_total* totals, int n_categories) {
+  VDK_REQUIRE(totals && n_categories >= 1, "vdk_prof_end: bad arguments");
+  std::lock_guard<std::mutex> lock(vdk::g_prof_mu);
+  vdk::g_prof_on = false;
+  for (int c = 0; c < n_categories; ++c) totals[c] = vdk_prof_total{0, 0.0, 0.0, 0.0};
+  int rc = VDK_OK;
+  for (auto& r : vdk::g_prof) {
+    float ms = 0.f;
+    if (cudaEventSynchronize(r.e1) != cudaSuccess || cudaEventElapsedTime(&ms, r.e0, r.e1) != cudaSuccess)
+      rc = vdk::fail(VDK_ERR_CUDA, "vdk_prof_end: event timing failed");
+    if (r.category >= 0 && r.category < n_categories) {
+      totals[r.category].launches += 1;
+      totals[r.category].ms += ms;
+      totals[r.category].flops += r.flops;
+      totals[r.category].bytes += r.bytes;
+    }
+    cudaEventDestroy(r.e0);
+    cudaEventDestroy(r.e1);
+  }
+  vdk::g_prof.clear();
+  return rc;
+}
 
 int vdk_device_check(void) {
   int n = 0;

@@ -40,6 +40,17 @@ int make_tma_nhwc_16bit(CUtensorMap* map, const void* base, int B, int H, int W,
 
 int sm_count();
 
+// Live kernel timing inside a real step (bench.py's roofline): while a profile is open (vdk_prof_begin), every launch wrapped
+// in a ProfScope is bracketed by two CUDA events on its own stream; vdk_prof_end sums launch count, milliseconds and the
+// algorithmic FLOPs / bytes per category.  Closed (the default), a ProfScope costs one predictable branch.
+enum ProfCategory { kProfGemm = 0, kProfDepthwise = 1, kProfAttention = 2, kProfScoreFilter = 3, kProfOther = 4, kProfCategories = 5 };
+struct ProfScope {
+  ProfScope(int category, double flops, double bytes, cudaStream_t stream);
+  ~ProfScope();
+  int slot;
+  cudaStream_t stream;
+};
+
 }  // namespace vdk
 
 namespace vdk {

@@ -277,6 +277,10 @@ attention_fwd_kernel(const __nv_bfloat16* __restrict__ qkv, int B, int N, int H,
 
 static int launch_attention(const __nv_bfloat16* qkv, int B, int N, int H, int head_dim, __nv_bfloat16* out, float* lse2,
                             cudaStream_t s) {
+  // algorithmic work: QK^T and PV = 4 * N^2 * head_dim flops per (image, head); qkv (+ o, do, dqkv) read / written once
+  ProfScope prof(kProfAttention, 4.0 * static_cast<double>(B) * H * N * N * 64.0,
+                 2.0 * static_cast<double>(B) * N * H * 64.0 * 4.0, s);
+
   VDK_REQUIRE(head_dim == kAttD, "attention: head_dim must be 64 (got %d)", head_dim);
   VDK_REQUIRE(B > 0 && N > 0 && H > 0 && H <= 65535 && B <= 65535, "attention: bad shape");
   const float scale_log2e = 1.4426950408889634f / sqrtf(static_cast<float>(head_dim));
@@ -500,6 +504,10 @@ attention_bwd_kernel(const __nv_bfloat16* __restrict__ qkv, const __nv_bfloat16*
 
 static int launch_attention_bwd(const __nv_bfloat16* qkv, const __nv_bfloat16* o, const __nv_bfloat16* d_o, const float* lse2, int B,
                                 int N, int H, int head_dim, __nv_bfloat16* dqkv, cudaStream_t s) {
+  // algorithmic work: S, dP, dV, dQ, dK = 10 * N^2 * head_dim flops per (image, head); qkv (+ o, do, dqkv) read / written once
+  ProfScope prof(kProfAttention, 10.0 * static_cast<double>(B) * H * N * N * 64.0,
+                 2.0 * static_cast<double>(B) * N * H * 64.0 * 8.0, s);
+
   VDK_REQUIRE(head_dim == kAttD, "attention backward: head_dim must be 64 (got %d)", head_dim);
   VDK_REQUIRE(N > 0 && N <= kAttBwdMaxRows, "attention backward: at most %d tokens (got %d): the probability matrix of one head is kept "
               "in shared memory", kAttBwdMaxRows, N);

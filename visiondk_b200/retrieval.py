@@ -120,8 +120,10 @@ class FlatIPIndex:
         return d.cpu().numpy(), i.cpu().numpy()
 
     # ---- device-resident path ----------------------------------------------------------------------
-    def _run_topk(self, qp: "PreparedRows", rows, g_lo: int, g_hi: int, k: int, dense_all: bool):
-        """One vdk_ip_topk call: queries `rows` of qp (None = all) against gallery rows [g_lo, g_hi)."""
+    def _run_topk(self, qp: "PreparedRows", rows, g_lo: int, g_hi: int, k: int, dense_all: bool, exchange=None):
+        """One vdk_ip_topk call: queries `rows` of qp (None = all) against gallery rows [g_lo, g_hi).  With `exchange` (the
+        sharded search) the call is split: vdk_ip_topk_filter -> exchange(kth_lb) (element-wise max over the ranks, in place)
+        -> vdk_ip_topk_rerank of the candidates that can still reach the global top-k."""
         lib = _lib.load()
         g = self._rows
         q32, qh, qn, qe = qp.x32, qp.xh, qp.norm, qp.err
@@ -151,17 +153,33 @@ class FlatIPIndex:
             self._ws = torch.empty((need,), dtype=torch.uint8, device=self.device)
         gn, ge = self._gmax if self._gmax is not None else (None, None)
         esz32, esz16 = 4 * self.d, 2 * self.d
+        g32_ptr = (g.x32.data_ptr() + g_lo * esz32) if g else 0
+        gh_ptr = (g.xh.data_ptr() + g_lo * esz16) if g else 0
         with torch.cuda.device(self.device):
-            rc = lib.vdk_ip_topk(C.byref(plan), q32.data_ptr(), qh.data_ptr(), qn.data_ptr(), qe.data_ptr(),
-                                 (g.x32.data_ptr() + g_lo * esz32) if g else 0, (g.xh.data_ptr() + g_lo * esz16) if g else 0,
-                                 _lib.ptr(gn), _lib.ptr(ge), self.id_offset + g_lo, out_s.data_ptr(), out_i.data_ptr(),
-                                 status.data_ptr(), self._ws.data_ptr(), self._ws.numel(), _lib.stream_ptr())
-        _lib.check(rc, "vdk_ip_topk")
+            if exchange is None:
+                rc = lib.vdk_ip_topk(C.byref(plan), q32.data_ptr(), qh.data_ptr(), qn.data_ptr(), qe.data_ptr(), g32_ptr, gh_ptr,
+                                     _lib.ptr(gn), _lib.ptr(ge), self.id_offset + g_lo, out_s.data_ptr(), out_i.data_ptr(),
+                                     status.data_ptr(), self._ws.data_ptr(), self._ws.numel(), _lib.stream_ptr())
+                _lib.check(rc, "vdk_ip_topk")
+            else:
+                kth_lb = torch.empty((nq,), dtype=torch.float32, device=self.device)
+                rc = lib.vdk_ip_topk_filter(C.byref(plan), qh.data_ptr(), qn.data_ptr(), qe.data_ptr(), gh_ptr, _lib.ptr(gn),
+                                            _lib.ptr(ge), kth_lb.data_ptr(), status.data_ptr(), self._ws.data_ptr(),
+                                            self._ws.numel(), _lib.stream_ptr())
+                _lib.check(rc, "vdk_ip_topk_filter")
+                exchange(kth_lb)
+                rc = lib.vdk_ip_topk_rerank(C.byref(plan), q32.data_ptr(), g32_ptr, self.id_offset + g_lo, kth_lb.data_ptr(),
+                                            out_s.data_ptr(), out_i.data_ptr(), self._ws.data_ptr(), self._ws.numel(),
+                                            _lib.stream_ptr())
+                _lib.check(rc, "vdk_ip_topk_rerank")
         return out_s, out_i, status, plan
 
-    def search_device(self, q: torch.Tensor, k: int, resolve_overflow: bool = False):
+    def search_device(self, q: torch.Tensor, k: int, resolve_overflow: bool = False, exchange=None):
         """Device tensors in/out.  With resolve_overflow=True the call synchronises, and queries whose candidate
-        lists overflowed (massive near-ties, adversarially ordered galleries) are recomputed on the wide path."""
+        lists overflowed (massive near-ties, adversarially ordered galleries) are recomputed on the wide path.
+        `exchange` (sharded search only): callable that replaces a device float32 [n] tensor by its element-wise maximum over
+        all shards, in place; the returned lists are then this shard's contribution to the GLOBAL top-k (entries that cannot
+        reach it are dropped before the canonical re-rank) and must be merged with the other shards' lists."""
         _lib.load()
         _lib.require_device()
         self._finalize()
@@ -177,7 +195,7 @@ class FlatIPIndex:
                     torch.empty((0, k), dtype=torch.int64, device=self.device))
         qp = PreparedRows(q, self.normalize)
         ng = self._rows.n if self._rows is not None else 0
-        out_s, out_i, status, plan = self._run_topk(qp, None, 0, ng, k, dense_all=False)
+        out_s, out_i, status, plan = self._run_topk(qp, None, 0, ng, k, dense_all=False, exchange=exchange)
         self.last_status = status
         if resolve_overflow and int(status[0].item()) > 0:
             self._wide_path(qp, out_s, out_i, plan, k)
@@ -235,10 +253,20 @@ class FlatIPIndex:
                                                   _lib.stream_ptr()), "vdk_ip_topk_exhaustive")
         return out_s, out_i
 
-    def check_status(self) -> dict:
+    def check_status(self, all_ranks: bool = False) -> dict:
         """Synchronises and raises if any query overflowed its candidate lists (results would be incomplete; the
-        numpy `search()` resolves such rows on the wide path by itself)."""
-        st = self.last_status.cpu().tolist()
+        numpy `search()` resolves such rows on the wide path by itself).  all_ranks=True (sharded search): the status is
+        first max-reduced over the process group, so every rank raises when any shard overflowed."""
+        st_t = self.last_status
+        if all_ranks and torch.distributed.is_available() and torch.distributed.is_initialized() and torch.distributed.get_world_size() > 1:
+            st_t = st_t.clone()
+            if torch.distributed.get_backend() != "nccl" and st_t.is_cuda:
+                host = st_t.cpu()
+                torch.distributed.all_reduce(host, op=torch.distributed.ReduceOp.MAX)
+                st_t = host
+            else:
+                torch.distributed.all_reduce(st_t, op=torch.distributed.ReduceOp.MAX)
+        st = st_t.cpu().tolist()
         info = {"overflow_rows": st[0], "max_candidates": st[1], "max_survivors": st[2]}
         if st[0] != 0:
             raise RuntimeError(f"vdk_ip_topk: {st[0]} query rows overflowed their candidate lists {info}; "
@@ -310,13 +338,23 @@ def merge_topk_packed(packed: torch.Tensor, k: int):
     return out_s, out_i
 
 
-def sharded_flat_search(index: "FlatIPIndex", q_local: torch.Tensor, q_sizes, k: int):
+def sharded_flat_search(index: "FlatIPIndex", q_local: torch.Tensor, q_sizes, k: int, defer_check: bool = False):
     """The multi-GPU search call (BASELINE config 4): every rank holds one row shard of the gallery in `index` (built with its
     `id_offset`) and `q_sizes[rank]` query embeddings; returns the GLOBAL top-k of ALL queries on every rank, bit-identical
-    to the unsharded search (scores are canonical, the merge uses the same (score desc, id asc) rule).  Overflowed queries
-    are resolved locally before the exchange, so the merge never sees an incomplete list."""
+    to the unsharded search (scores are canonical, the merge uses the same (score desc, id asc) rule).
+
+    Three exchanges: all-gather of the query embeddings, a max all-reduce of one float per query (each shard's lower bound of
+    its k-th canonical score: shards then re-rank only the candidates that can reach the global top-k), and ONE all-gather of
+    the packed per-shard lists.  Overflowed queries are resolved locally before the last exchange, so the merge never sees an
+    incomplete list (one host synchronisation per search); defer_check=True skips that synchronisation — the caller then MUST
+    call `index.check_status(all_ranks=True)` before trusting the result (it raises if any shard overflowed)."""
     from . import sharding
-    return sharding.sharded_search(q_local, list(q_sizes), lambda q, kk: index.search_device(q, kk, resolve_overflow=True),
+
+    def exchange(t: torch.Tensor) -> None:
+        sharding.all_reduce_max_(t)
+
+    return sharding.sharded_search(q_local, list(q_sizes),
+                                   lambda q, kk: index.search_device(q, kk, resolve_overflow=not defer_check, exchange=exchange),
                                    merge_topk, k, pack=pack_topk, merge_packed=merge_topk_packed)
 
 

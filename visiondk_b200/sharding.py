@@ -41,6 +41,18 @@ def _all_gather_into(out: torch.Tensor, src: torch.Tensor) -> None:
         dist.all_gather_into_tensor(out.view(flat), src)
 
 
+def all_reduce_max_(t: torch.Tensor) -> None:
+    """In-place element-wise maximum over the ranks (the per-query k-th score bounds of the sharded search: 4 bytes / query)."""
+    if not _active():
+        return
+    if t.is_cuda and dist.get_backend() != "nccl":
+        host = t.cpu()
+        dist.all_reduce(host, op=dist.ReduceOp.MAX)
+        t.copy_(host)
+    else:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+
+
 def all_gather_rows(local: torch.Tensor, sizes: List[int]) -> torch.Tensor:
     """Exchange 1: every rank extracted `sizes[rank]` query embeddings; returns all of them in rank order."""
     if not _active():
