@@ -13,6 +13,8 @@ batch 128, DDP all-reduce overlapped with the backward); the other legs ride in 
                   TimmWrapper.embed(l2_normalize=True) (= FeatureExtractor.extract_cbir's model(x) + F.normalize,
                   face_model.py:137-139), bf16 activations; N GPUs: independent images, no collective -> weak scaling
   extract_vit     the same with ViT-B/16 (secondary)
+  extract_vitl    configs[4]: the same with the CLIP ViT-L/14 tower at 336^2 (timm vit_large_patch14_clip_336), batch 64 per GPU;
+                  its retrieval half is the `retrieval` leg (512-d embeddings, gallery sharded over the GPUs)
   retrieval       pairs/sec of configs[3]: one full search, 10 000 queries x 1 000 000 gallery rows, 512-d, cosine top-100
                   (rows_prepare -> tcgen05 score/filter over the gallery ranges -> select -> canonical re-rank); N GPUs:
                   gallery rows sharded, all-gather of queries and of per-shard lists + merge -> strong scaling
@@ -466,17 +468,18 @@ def bench_extract(ctx, args):
             "h2d": B * 3 * IMG * IMG * 4, "d2h": B * FEAT * 4, "batch": B}
 
 
-def bench_extract_vit(ctx, args):
+def bench_extract_vit(ctx, args, name="vit_base_patch16_224", img=IMG, batch=None, title="ViT-B/16"):
     """Secondary row (BASELINE config 5 family): CBIR extraction with a Transformer backbone, ViT-B/16 224^2, random-init
     weights, batch = --batch per GPU.  Device-resident and end-to-end (FeatureExtractor.extract_cbir from pinned host batches)."""
     import torch
     from visiondk_b200.vit import ViTWrapper, VIT_ARCHS
     from visiondk_b200.cbir import FeatureExtractor
-    name, B = "vit_base_patch16_224", args.batch
+    B = batch or args.batch
+    IMG_ = img
     torch.manual_seed(0)
-    model = ViTWrapper(name, FEAT, IMG, pretrained=False).to(ctx.dev).eval()
+    model = ViTWrapper(name, FEAT, IMG_, pretrained=False).to(ctx.dev).eval()
     gen = torch.Generator(device=ctx.dev).manual_seed(ctx.rank)
-    pool = [torch.randn(B, 3, IMG, IMG, device=ctx.dev, generator=gen) for _ in range(2)]
+    pool = [torch.randn(B, 3, IMG_, IMG_, device=ctx.dev, generator=gen) for _ in range(2)]
     state = {"i": 0}
 
     def step_dev():
@@ -485,7 +488,7 @@ def bench_extract_vit(ctx, args):
         return model.embed(x, l2_normalize=True)
 
     ms = timed(ctx, step_dev, args.steps, args.warmup)
-    host_x = [torch.randn(B, 3, IMG, IMG).pin_memory() for _ in range(2)]
+    host_x = [torch.randn(B, 3, IMG_, IMG_).pin_memory() for _ in range(2)]
     extractor = FeatureExtractor(model)
 
     def run_e2e(n_steps):
@@ -504,21 +507,21 @@ def bench_extract_vit(ctx, args):
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         e2e_ms = float(t.item())
     patch, dim, depth, heads = VIT_ARCHS[name]
-    T = (IMG // patch) ** 2 + 1
+    T = (IMG_ // patch) ** 2 + 1
     gflop = (depth * (24.0 * T * dim * dim + 4.0 * T * T * dim) + 2.0 * (T - 1) * 3 * patch * patch * dim + 2.0 * T * dim * FEAT) / 1e9
     peak = float(measured_peaks().get("bf16_tflops_sustained", 1422.7))
     ach = B * gflop / ms
-    roof = step_roofline(live_profile(step_dev), ms, f"ViT-B/16 extraction forward (batch {B})") if ctx.rank == 0 else None
+    roof = step_roofline(live_profile(step_dev), ms, f"{title} extraction forward (batch {B})") if ctx.rank == 0 else None
     if roof is None:
         roof = {"bound": "tensor"}
     roof["whole_step"] = {"achieved": ach, "unit": "TFLOP/s", "peak": peak, "frac": ach / peak,
                           "note": f"{gflop:.2f} GFLOP per embedding over the whole forward"}
-    return {"metric": "embeddings/sec (ViT-B/16 224^2, CBIR extract, inference)", "value": ctx.world * B / (ms * 1e-3),
+    return {"metric": f"embeddings/sec ({title} {IMG_}^2, CBIR extract, inference)", "value": ctx.world * B / (ms * 1e-3),
             "unit": "embeddings/s", "ms_per_step": ms, "scaling": "weak", "dtype": "bf16",
-            "config": {"workload": f"CBIR eval extract: ViT-B/16 {IMG}^2 (197 tokens) -> {FEAT}-d L2-normalised embeddings, batch {B} "
-                                   f"per GPU, random-init weights", "l2": "two alternating input batches (2 x 154 MB)"},
+            "config": {"workload": f"CBIR eval extract: {title} {IMG_}^2 ({T} tokens, timm {name}) -> {FEAT}-d L2-normalised embeddings, batch {B} "
+                                   f"per GPU, random-init weights", "l2": "two alternating input batches, together larger than the 126 MB L2"},
             "e2e": {"value": ctx.world * B / (e2e_ms * 1e-3), "unit": "embeddings/s", "ms_per_step": e2e_ms,
-                    "h2d_bytes_per_step": B * 3 * IMG * IMG * 4, "d2h_bytes_per_step": B * FEAT * 4},
+                    "h2d_bytes_per_step": B * 3 * IMG_ * IMG_ * 4, "d2h_bytes_per_step": B * FEAT * 4},
             "gpu_launches": (3 + 7 * depth + 4) * args.steps,
             "roofline": roof}
 
@@ -797,6 +800,10 @@ def main():
     torch.cuda.empty_cache()
     exv = bench_extract_vit(ctx, args) if want("extract") else None
     torch.cuda.empty_cache()
+    # BASELINE configs[4]: the CLIP ViT-L/14 tower at 336^2 (timm vit_large_patch14_clip_336: 577 tokens, width 1024, 24 blocks)
+    exl = bench_extract_vit(ctx, args, name="vit_large_patch14_clip_336", img=336, batch=max(8, args.batch // 4),
+                            title="ViT-L/14 (CLIP tower)") if want("extract") else None
+    torch.cuda.empty_cache()
     rt = bench_retrieval(ctx, args) if want("retrieval") else None
     clocks = sampler.stop() if sampler else None
 
@@ -851,11 +858,12 @@ def main():
                 "gpu_launches": tr["launches_per_step"] * args.steps,
                 "roofline": roof if roof is not None else {"bound": "tensor", "whole_step": tr["whole_step"]},
                 "cpu_baseline": cpu.get("train"),
-                "train_vit": trv, "extract": extract, "extract_vit": exv, "retrieval": retrieval,
+                "train_vit": trv, "extract": extract, "extract_vit": exv, "extract_vitl": exl, "retrieval": retrieval,
             }
         elif ex is not None:
             line = dict(extract)
             line["extract_vit"] = exv
+            line["extract_vitl"] = exl
             line["retrieval"] = retrieval
         else:
             line = dict(retrieval)

@@ -261,6 +261,11 @@ typedef struct vdk_vit_net {
   const float* neck_ln_w; const float* neck_ln_b;  /* output_layer.0, eps 1e-5 */
   const void* neck_w;       /* [feat_dim, tokens*dim] bf16 with BatchNorm1d (eval) folded in */
   const float* neck_b;      /* [feat_dim] folded */
+  /* timm's `pre_norm=True` variants (vit_*_clip_*: CLIP towers): a LayerNorm right after cls / position (model.norm_pre),
+   * a bias-free patch embedding (patch_b == NULL) and LayerNorm eps 1e-5.  NULL / 0 = the plain ViT above (eps 1e-6).
+   * Inference only: vdk_vit_train_* refuse a net with norm_pre_w set. */
+  const float* norm_pre_w; const float* norm_pre_b;
+  float ln_eps;             /* eps of norm_pre, the block norms and model.norm; 0 selects 1e-6 */
 } vdk_vit_net;
 size_t vdk_vit_workspace_bytes(const vdk_vit_net* net, int batch);
 /* images: fp32 NCHW [batch,3,S,S]; embeddings: fp32 [batch, feat_dim], L2-normalised when l2_normalize != 0. */

@@ -17,6 +17,12 @@ PyTorch fp32 with the SAME state_dict keys:
 
 Independent cross-check available in this container: HF transformers' ViTModel is architecture-identical
 (tests/test_oracle_vit_cpu.py maps the weights across and compares the token outputs).
+
+pre_norm=True restates timm 0.9.16's `vit_*_clip_*` entries (the CLIP image towers, BASELINE config 5's ViT-L/14 at 336^2:
+`VisionTransformer(pre_norm=True, norm_layer=nn.LayerNorm)`): `model.norm_pre` LayerNorm after cls / position embedding,
+`patch_embed.proj` WITHOUT bias, every LayerNorm at eps 1e-5, standard GELU.  Cross-check: HF transformers' CLIPVisionModel
+with hidden_act="gelu" has the same tower (tests/test_oracle_vit_cpu.py maps the weights across; HF applies its
+post_layernorm to the pooled token only, so the comparison is on the tokens before the final norm).
 """
 from __future__ import annotations
 
@@ -32,8 +38,11 @@ VIT_ARCHS = {
     "vit_small_patch16_224": (16, 384, 12, 6),
     "vit_base_patch16_224": (16, 768, 12, 12),
     "vit_large_patch16_224": (16, 1024, 24, 16),
+    "vit_base_patch16_clip_224": (16, 768, 12, 12),
+    "vit_large_patch14_clip_224": (14, 1024, 24, 16),
     "vit_large_patch14_clip_336": (14, 1024, 24, 16),
 }
+VIT_PRE_NORM = {"vit_base_patch16_clip_224", "vit_large_patch14_clip_224", "vit_large_patch14_clip_336"}
 
 
 class Attention(nn.Module):
@@ -67,11 +76,11 @@ class Mlp(nn.Module):
 
 
 class Block(nn.Module):
-    def __init__(self, dim, heads):
+    def __init__(self, dim, heads, eps=1e-6):
         super().__init__()
-        self.norm1 = nn.LayerNorm(dim, eps=1e-6)
+        self.norm1 = nn.LayerNorm(dim, eps=eps)
         self.attn = Attention(dim, heads)
-        self.norm2 = nn.LayerNorm(dim, eps=1e-6)
+        self.norm2 = nn.LayerNorm(dim, eps=eps)
         self.mlp = Mlp(dim)
 
     def forward(self, x):
@@ -80,39 +89,47 @@ class Block(nn.Module):
 
 
 class PatchEmbed(nn.Module):
-    def __init__(self, patch, dim):
+    def __init__(self, patch, dim, bias=True):
         super().__init__()
-        self.proj = nn.Conv2d(3, dim, kernel_size=patch, stride=patch)
+        self.proj = nn.Conv2d(3, dim, kernel_size=patch, stride=patch, bias=bias)
 
     def forward(self, x):
         return self.proj(x).flatten(2).transpose(1, 2)  # [B, N, C], row-major over (h, w)
 
 
 class VisionTransformer(nn.Module):
-    def __init__(self, image_size, patch, dim, depth, heads):
+    def __init__(self, image_size, patch, dim, depth, heads, pre_norm=False):
         super().__init__()
         n = (image_size // patch) ** 2
-        self.patch_embed = PatchEmbed(patch, dim)
+        eps = 1e-5 if pre_norm else 1e-6  # timm: norm_layer=nn.LayerNorm for the clip entries, partial(LayerNorm, eps=1e-6) otherwise
+        self.patch_embed = PatchEmbed(patch, dim, bias=not pre_norm)
         self.cls_token = nn.Parameter(torch.zeros(1, 1, dim))
         self.pos_embed = nn.Parameter(torch.randn(1, n + 1, dim) * 0.02)
-        self.blocks = nn.Sequential(*[Block(dim, heads) for _ in range(depth)])
-        self.norm = nn.LayerNorm(dim, eps=1e-6)
+        self.norm_pre = nn.LayerNorm(dim, eps=eps) if pre_norm else nn.Identity()
+        self.blocks = nn.Sequential(*[Block(dim, heads, eps) for _ in range(depth)])
+        self.norm = nn.LayerNorm(dim, eps=eps)
 
-    def forward(self, x):
+    def forward_tokens(self, x):
+        """Tokens after the last block, BEFORE the final LayerNorm (what HF's `last_hidden_state` of a CLIP tower holds)."""
         x = self.patch_embed(x)
         x = torch.cat([self.cls_token.expand(x.shape[0], -1, -1), x], dim=1) + self.pos_embed
-        return self.norm(self.blocks(x))
+        return self.blocks(self.norm_pre(x))
+
+    def forward(self, x):
+        return self.norm(self.forward_tokens(x))
 
 
 class ViTWrapperOracle(nn.Module):
     """timm_wrapper.py TimmWrapper for a Transformer backbone: `model` + the `[B,N,C]` neck."""
 
-    def __init__(self, model_name, feat_dim, image_size, patch=None, dim=None, depth=None, heads=None):
+    def __init__(self, model_name, feat_dim, image_size, patch=None, dim=None, depth=None, heads=None, pre_norm=None):
         super().__init__()
         if dim is None:
             patch, dim, depth, heads = VIT_ARCHS[model_name]
+        if pre_norm is None:
+            pre_norm = model_name in VIT_PRE_NORM
         assert image_size % patch == 0 and dim % heads == 0
-        self.model = VisionTransformer(image_size, patch, dim, depth, heads)
+        self.model = VisionTransformer(image_size, patch, dim, depth, heads, pre_norm=pre_norm)
         tokens = (image_size // patch) ** 2 + 1
         self.output_layer = nn.Sequential(nn.LayerNorm(dim), nn.Flatten(1), nn.Linear(tokens * dim, feat_dim),
                                           nn.BatchNorm1d(feat_dim))

@@ -34,13 +34,15 @@ def test_attention_forward_matches_torch(lib, B, N, H):
 def build(seed, **kw):
     oracle = randomize_(ViTWrapperOracle("x", **kw), seed=seed).eval()
     ours = ViTWrapper("x", kw["feat_dim"], kw["image_size"], pretrained=False, patch=kw["patch"], dim=kw["dim"], depth=kw["depth"],
-                      heads=kw["heads"])
+                      heads=kw["heads"], pre_norm=kw.get("pre_norm", False))
     ours.load_state_dict(oracle.state_dict(), strict=True)
     return oracle, ours.cuda().eval()
 
 
 @pytest.mark.parametrize("cfg", [dict(feat_dim=64, image_size=64, patch=16, dim=128, depth=2, heads=2),
-                                 dict(feat_dim=128, image_size=112, patch=14, dim=192, depth=3, heads=3)])
+                                 dict(feat_dim=128, image_size=112, patch=14, dim=192, depth=3, heads=3),
+                                 # timm's pre_norm CLIP tower: norm_pre, bias-free patch embedding, eps 1e-5 (config 5 family)
+                                 dict(feat_dim=64, image_size=56, patch=14, dim=128, depth=2, heads=2, pre_norm=True)])
 def test_vit_toy_embeddings_match_oracle(lib, cfg):
     oracle, ours = build(3, **cfg)
     torch.manual_seed(1)
@@ -71,6 +73,30 @@ def test_vit_base_patch16_224_embeddings_match_oracle(lib):
     cos = (got * ref).sum(dim=1)
     assert rel(got, ref) <= 3e-2, rel(got, ref)
     assert cos.min().item() >= 0.999
+
+
+def test_vit_large_patch14_clip_336_embeddings_match_oracle(lib):
+    """BASELINE config 5 at full size: timm's vit_large_patch14_clip_336 (CLIP ViT-L/14 tower: pre_norm, 577 tokens, width 1024,
+    24 blocks, 16 heads) + the reference's Transformer neck Linear(590 848 -> 512), against the fp32 oracle (cross-checked vs HF
+    CLIPVisionModel in tests/test_oracle_vit_cpu.py).  Tolerance as for the other full-size backbones: bf16 activations through
+    24 blocks -> relative L2 <= 3e-2, cosine >= 0.999 per embedding.  Training of this variant is refused, not faked."""
+    torch.set_num_threads(min(16, torch.get_num_threads()))
+    name = "vit_large_patch14_clip_336"
+    oracle = randomize_(ViTWrapperOracle(name, 512, 336), seed=7).eval()
+    ours = BackboneFactory({f"timm-{name}.openai_ft_in12k_in1k": {"pretrained": False, "image_size": 336, "feat_dim": 512}}).get_backbone()
+    assert ours.model.pre_norm and ours.model.patch_embed.proj.bias is None
+    ours.load_state_dict(oracle.state_dict(), strict=True)  # the key set of timm's pre_norm tower (norm_pre.*, no patch bias)
+    ours = ours.cuda().eval()
+    torch.manual_seed(4)
+    x = torch.randn(2, 3, 336, 336)
+    with torch.no_grad():
+        ref = torch.nn.functional.normalize(oracle(x))
+    got = ours.embed(x.cuda(), l2_normalize=True).cpu()
+    cos = (got * ref).sum(dim=1)
+    assert rel(got, ref) <= 3e-2, rel(got, ref)
+    assert cos.min().item() >= 0.999
+    with pytest.raises(NotImplementedError):
+        ours.train()(x.cuda())
 
 
 @pytest.mark.parametrize("B,N,H", [(2, 197, 3), (1, 208, 2), (3, 50, 2), (2, 17, 1)])

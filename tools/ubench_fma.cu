@@ -60,6 +60,46 @@ __global__ void __launch_bounds__(1024) fma_kernel(float* out, float seed, long 
       t ^= sh[i];
     }
     if (s == 0x1234567ull && t == 77u) out[threadIdx.x] = 1.f;
+  } else if (MODE == 5 || MODE == 6) {
+    // the depthwise tap loop's operand pattern: 14 accumulators, each FFMA2 (5) / FFMA pair (6) reads a DIFFERENT input pair and
+    // tap pair (no operand shared with its neighbours except the input of one column): is the 64-bit operand fetch the limit?
+    float2 acc[14], in[13], w[7];
+#pragma unroll
+    for (int i = 0; i < 14; ++i) acc[i] = make_float2(seed + i, seed - i);
+#pragma unroll
+    for (int i = 0; i < 13; ++i) in[i] = make_float2(seed * (i + 1), seed * 0.5f * (i + 2));
+#pragma unroll
+    for (int i = 0; i < 7; ++i) w[i] = make_float2(seed * 0.25f * (i + 1), seed * 0.125f * (i + 3));
+    for (int it = 0; it < kIters / 8; ++it) {
+#pragma unroll
+      for (int ix = 0; ix < 13; ++ix) {
+#pragma unroll
+        for (int pp = 0; pp < 7; ++pp) {
+          const int dx = ix - pp;
+          if (dx >= 0 && dx < 7) {
+            if (MODE == 5) {
+              unsigned long long ra = *reinterpret_cast<unsigned long long*>(&in[ix]), rb = *reinterpret_cast<unsigned long long*>(&w[dx]);
+              unsigned long long rc = *reinterpret_cast<unsigned long long*>(&acc[pp]);
+              rc = ffma2(ra, rb, rc);
+              acc[pp] = *reinterpret_cast<float2*>(&rc);
+              ra = *reinterpret_cast<unsigned long long*>(&in[(ix + 1) % 13]);
+              rc = *reinterpret_cast<unsigned long long*>(&acc[7 + pp]);
+              rc = ffma2(ra, rb, rc);
+              acc[7 + pp] = *reinterpret_cast<float2*>(&rc);
+            } else {
+              asm volatile("fma.rn.f32 %0, %1, %2, %0;" : "+f"(acc[pp].x) : "f"(in[ix].x), "f"(w[dx].x));
+              asm volatile("fma.rn.f32 %0, %1, %2, %0;" : "+f"(acc[pp].y) : "f"(in[ix].y), "f"(w[dx].y));
+              asm volatile("fma.rn.f32 %0, %1, %2, %0;" : "+f"(acc[7 + pp].x) : "f"(in[(ix + 1) % 13].x), "f"(w[dx].x));
+              asm volatile("fma.rn.f32 %0, %1, %2, %0;" : "+f"(acc[7 + pp].y) : "f"(in[(ix + 1) % 13].y), "f"(w[dx].y));
+            }
+          }
+        }
+      }
+    }
+    float sacc = 0.f;
+#pragma unroll
+    for (int i = 0; i < 14; ++i) sacc += acc[i].x + acc[i].y;
+    if (sacc == 123.456f) out[threadIdx.x] = sacc;
   } else {  // HFMA2 fp16 (2) / bf16 (3)
     unsigned acc[kChains];
     const unsigned a = 0x3c003c00u, b = 0x38003800u;
@@ -82,7 +122,7 @@ __global__ void __launch_bounds__(1024) fma_kernel(float* out, float seed, long 
 }
 
 template <int MODE>
-static void run(const char* name, int fma_per_instr, int sms, float* out, long long* cyc) {
+static void run(const char* name, int fma_per_instr, int sms, float* out, long long* cyc, double instr_scale = 1.0) {
   const int blocks = sms;  // one 1024-thread CTA per SM: 8 warps per scheduler
   fma_kernel<MODE><<<blocks, 1024>>>(out, 1.0001f, cyc);
   cudaDeviceSynchronize();
@@ -100,10 +140,10 @@ static void run(const char* name, int fma_per_instr, int sms, float* out, long l
   double mean = 0;
   for (int i = 0; i < blocks; ++i) mean += double(h[i]);
   mean /= blocks;
-  const double instr_per_sm = double(kIters) * kChains * 32.0;  // warp instructions per SM (32 warps)
+  const double instr_per_sm = double(kIters) * kChains * 32.0 * instr_scale;  // warp instructions per SM (32 warps)
   const double fma_per_clk_sm = instr_per_sm * 32.0 * fma_per_instr / mean;
   printf("%-28s %8.3f ms  %10.0f cycles/CTA  %6.1f FMA/clk/SM  issue interval per scheduler %.2f clk  (%.1f TFLOP/s at this clock x %d SMs)\n",
-         name, ms, mean, fma_per_clk_sm, mean / (double(kIters) * kChains * 8.0),
+         name, ms, mean, fma_per_clk_sm, mean / (double(kIters) * kChains * 8.0 * instr_scale),
          fma_per_clk_sm * 2.0 * sms * (mean / (ms * 1e-3)) * 1e-12, sms);
 }
 
@@ -117,8 +157,10 @@ int main() {
   printf("device %s, %d SMs\n", p.name, p.multiProcessorCount);
   run<0>("FFMA (3-register)", 1, p.multiProcessorCount, out, cyc);
   run<1>("FFMA2 (fma.rn.f32x2)", 2, p.multiProcessorCount, out, cyc);
-  run<4>("FFMA2 + 1 SHL per FFMA2", 2, p.multiProcessorCount, out, cyc);
   run<2>("HFMA2 (fp16x2)", 2, p.multiProcessorCount, out, cyc);
   run<3>("HFMA2.BF16 (bf16x2)", 2, p.multiProcessorCount, out, cyc);
+  // tap-loop pattern: (kIters / 8) iterations x 98 instruction pairs; normalise to the kIters x kChains instruction count above
+  run<5>("FFMA2, tap-loop operands", 2, p.multiProcessorCount, out, cyc, (kIters / 8) * 98.0 / (double(kIters) * kChains));
+  run<6>("FFMA, tap-loop operands", 1, p.multiProcessorCount, out, cyc, (kIters / 8) * 196.0 / (double(kIters) * kChains));
   return 0;
 }

@@ -456,7 +456,7 @@ class BackboneFactory:
     def get_backbone(self) -> nn.Module:
         if not self.backbone_type.startswith("timm-"):
             raise ValueError(f"Unsupported backbone type: {self.backbone_type}. Only timm models are supported.")
-        model_name = self.backbone_type[5:]
+        model_name = self.backbone_type[5:].split(".")[0]  # timm's "<architecture>.<pretrained tag>": the tag names weights only
         if model_name.startswith("vit_"):  # Transformer backbones: eval / extract path (visiondk_b200/vit.py)
             from .vit import ViTWrapper
             return ViTWrapper(model_name=model_name, **self.backbone_param)

@@ -1139,6 +1139,12 @@ static int topk_rerank(const vdk_topk_plan* plan, const float* q32, const float*
   rp.out_ids = out_ids;
   rp.kth_lb = kth_lb_global;
   rp.eps = w.eps;
+  static bool rr_attr = false;
+  if (!rr_attr) {  // carry_capacity up to 4096: 48 KB of sort keys + kept slots, above the default dynamic limit
+    VDK_CUDA_OK(cudaFuncSetAttribute(rerank_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                     4096 * static_cast<int>(sizeof(unsigned long long) + sizeof(uint32_t))));
+    rr_attr = true;
+  }
   rerank_kernel<<<static_cast<unsigned>(nq), kRerankThreads, carry_cap * (sizeof(unsigned long long) + sizeof(uint32_t)), s>>>(rp);
   VDK_CUDA_OK(cudaGetLastError());
   return VDK_OK;

@@ -81,6 +81,24 @@ int make_tma_nhwc_16bit(CUtensorMap* map, const void* base, int B, int H, int W,
   return VDK_OK;
 }
 
+int make_tma_3d_16bit(CUtensorMap* map, const void* base, uint64_t d0, uint64_t d1, uint64_t d2, uint64_t pitch1, uint64_t pitch2,
+                      uint32_t box_rows) {
+  EncodeTiledFn fn = encode_tiled_fn();
+  if (!fn) return fail(VDK_ERR_CUDA, "cuTensorMapEncodeTiled entry point unavailable (no CUDA driver?)");
+  if ((reinterpret_cast<uintptr_t>(base) & 15) != 0 || (pitch1 * 2) % 16 != 0 || (pitch2 * 2) % 16 != 0)
+    return fail(VDK_ERR_INVALID, "3-D TMA operand must be 16-byte aligned with 16-byte-multiple pitches");
+  if (box_rows > 256) return fail(VDK_ERR_INVALID, "TMA box must be <= 256 rows");
+  cuuint64_t gdim[3] = {d0, d1, d2};
+  cuuint64_t gstride[2] = {pitch1 * 2, pitch2 * 2};
+  cuuint32_t box[3] = {64, box_rows, 1};
+  cuuint32_t estr[3] = {1, 1, 1};
+  CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_UINT16, 3, const_cast<void*>(base), gdim, gstride, box, estr,
+                  CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) return fail(VDK_ERR_CUDA, "cuTensorMapEncodeTiled (3-D) failed with CUresult %d", (int)r);
+  return VDK_OK;
+}
+
 // ---- live profile (see vdk_host.h) ----
 struct ProfRecord {
   int category;

@@ -38,6 +38,11 @@ int make_tma_2d_16bit(CUtensorMap* map, const void* base, uint64_t rows, uint64_
 // (which is exactly the zero padding of a convolution).
 int make_tma_nhwc_16bit(CUtensorMap* map, const void* base, int B, int H, int W, int C, int box_h, int box_w, int box_c);
 
+// 3-D map over a 16-bit tensor [d2][d1][d0] (d0 contiguous; pitches in elements): box = [1][box_rows][64 elements], 128-byte
+// swizzle, out-of-bounds rows read as zero.  The attention kernel's view of the qkv buffer: [batch][tokens][3*heads*64].
+int make_tma_3d_16bit(CUtensorMap* map, const void* base, uint64_t d0, uint64_t d1, uint64_t d2, uint64_t pitch1, uint64_t pitch2,
+                      uint32_t box_rows);
+
 int sm_count();
 
 // Live kernel timing inside a real step (bench.py's roofline): while a profile is open (vdk_prof_begin), every launch wrapped

@@ -127,6 +127,15 @@ __device__ __forceinline__ void tma_load_4d(void* smem_dst, const CUtensorMap* m
       : "memory");
 }
 
+__device__ __forceinline__ void tma_load_3d(void* smem_dst, const CUtensorMap* map, uint64_t* bar, int c0, int c1, int c2) {
+  asm volatile(
+      "cp.async.bulk.tensor.3d.shared::cluster.global.tile.mbarrier::complete_tx::bytes"
+      " [%0], [%1, {%3, %4, %5}], [%2];"
+      ::"r"(smem_u32(smem_dst)),
+      "l"(reinterpret_cast<uint64_t>(map)), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2)
+      : "memory");
+}
+
 __device__ __forceinline__ void tma_store_2d(const CUtensorMap* map, const void* smem_src, int c0, int c1) {
   asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.tile.bulk_group [%0, {%2, %3}], [%1];" ::"l"(
                    reinterpret_cast<uint64_t>(map)),
@@ -233,6 +242,20 @@ __device__ __forceinline__ void tmem_ld_32x32b_x32(uint32_t taddr, uint32_t (&r)
 }
 __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 
+// registers -> TMEM: this thread's lane (row), 32 consecutive 32-bit columns (the accumulator rescale of the attention kernel)
+__device__ __forceinline__ void tmem_st_32x32b_x32(uint32_t taddr, const uint32_t (&r)[32]) {
+  asm volatile(
+      "tcgen05.st.sync.aligned.32x32b.x32.b32 [%0], "
+      "{%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16, "
+      "%17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31, %32};"
+      ::"r"(taddr), "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]), "r"(r[8]), "r"(r[9]),
+      "r"(r[10]), "r"(r[11]), "r"(r[12]), "r"(r[13]), "r"(r[14]), "r"(r[15]), "r"(r[16]), "r"(r[17]), "r"(r[18]), "r"(r[19]),
+      "r"(r[20]), "r"(r[21]), "r"(r[22]), "r"(r[23]), "r"(r[24]), "r"(r[25]), "r"(r[26]), "r"(r[27]), "r"(r[28]), "r"(r[29]),
+      "r"(r[30]), "r"(r[31])
+      : "memory");
+}
+__device__ __forceinline__ void tmem_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
+
 // ----------------------------------------------------------------------------------------------
 // CTA pairs (cta_group::2): two CTAs of a 2-cluster share one UMMA (M = 256); forms as in cute/arch/copy_sm100_tma.hpp
 // and cutlass/arch/barrier.h
@@ -298,8 +321,9 @@ __device__ __forceinline__ void umma_commit_pair(uint64_t* bar) {
 }
 
 // ----------------------------------------------------------------------------------------------
-// packed fp32 pairs: sm_100 issues a register-form FFMA every second cycle per scheduler, but FFMA2 (two fp32 FMAs
-// on 64-bit register pairs) at the same rate, so FMA-bound CUDA-core loops have to be written in pairs
+// packed fp32 pairs.  Measured on B200 (tools/ubench_fma.cu): FFMA issues every 1.01 clk per scheduler (126 FMA/clk/SM), FFMA2
+// every 2.17 clk (118 FMA/clk/SM): the same FP32 rate at half the issue slots, which leaves every other slot to the loads /
+// conversions of an FMA-bound CUDA-core loop
 // ----------------------------------------------------------------------------------------------
 __device__ __forceinline__ float2 ffma2(float2 a, float2 b, float2 c) {
   unsigned long long ra = *reinterpret_cast<unsigned long long*>(&a), rb = *reinterpret_cast<unsigned long long*>(&b),

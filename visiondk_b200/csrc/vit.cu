@@ -275,8 +275,27 @@ attention_fwd_kernel(const __nv_bfloat16* __restrict__ qkv, int B, int N, int H,
   }
 }
 
+int launch_attention_tc(const __nv_bfloat16* qkv, int B, int N, int H, __nv_bfloat16* out, float* lse2, cudaStream_t s);  // attention_tc.cu
+
+static int launch_attention_mma_sync(const __nv_bfloat16* qkv, int B, int N, int H, int head_dim, __nv_bfloat16* out, float* lse2,
+                                     cudaStream_t s);
+
+// Forward attention: the tcgen05 kernel (attention_tc.cu) by default; VDK_ATT_TC=0 selects the earlier mma.sync kernel (kept as
+// the comparison baseline of profiles/ and for A/B parity tests).
 static int launch_attention(const __nv_bfloat16* qkv, int B, int N, int H, int head_dim, __nv_bfloat16* out, float* lse2,
                             cudaStream_t s) {
+  static const bool use_tc = [] {
+    const char* e = getenv("VDK_ATT_TC");
+    return e ? atoi(e) != 0 : true;
+  }();
+  if (!use_tc) return launch_attention_mma_sync(qkv, B, N, H, head_dim, out, lse2, s);
+  VDK_REQUIRE(head_dim == kAttD, "attention: head_dim must be 64 (got %d)", head_dim);
+  ProfScope prof(kProfAttention, 4.0 * static_cast<double>(B) * H * N * N * 64.0, 2.0 * static_cast<double>(B) * N * H * 64.0 * 4.0, s);
+  return launch_attention_tc(qkv, B, N, H, out, lse2, s);
+}
+
+static int launch_attention_mma_sync(const __nv_bfloat16* qkv, int B, int N, int H, int head_dim, __nv_bfloat16* out, float* lse2,
+                                     cudaStream_t s) {
   // algorithmic work: QK^T and PV = 4 * N^2 * head_dim flops per (image, head); qkv (+ o, do, dqkv) read / written once
   ProfScope prof(kProfAttention, 4.0 * static_cast<double>(B) * H * N * N * 64.0,
                  2.0 * static_cast<double>(B) * N * H * 64.0 * 4.0, s);
@@ -598,7 +617,7 @@ extern "C" int vdk_vit_forward(const vdk_vit_net* net, const float* images, int 
   VDK_REQUIRE(images && embeddings && batch > 0, "vdk_vit_forward: null image/embedding buffer");
   VDK_REQUIRE(workspace && workspace_bytes >= L.total && (reinterpret_cast<uintptr_t>(workspace) & 255) == 0,
               "vdk_vit_forward: workspace too small or misaligned");
-  VDK_REQUIRE(net->patch_w && net->patch_b && net->cls_token && net->pos_embed && net->ones && net->norm_w && net->norm_b &&
+  VDK_REQUIRE(net->patch_w && net->cls_token && net->pos_embed && net->ones && net->norm_w && net->norm_b &&
                   net->neck_ln_w && net->neck_ln_b && net->neck_w && net->neck_b,
               "vdk_vit_forward: null parameter");
   cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
@@ -607,6 +626,8 @@ extern "C" int vdk_vit_forward(const vdk_vit_net* net, const float* images, int 
   __nv_bfloat16* y = reinterpret_cast<__nv_bfloat16*>(ws + L.y);
   __nv_bfloat16* big = reinterpret_cast<__nv_bfloat16*>(ws + L.big);
   const int C = L.C, T = L.T, N = L.N, M = static_cast<int>(L.M);
+  const float eps = net->ln_eps > 0.f ? net->ln_eps : 1e-6f;
+  VDK_REQUIRE((net->norm_pre_w == nullptr) == (net->norm_pre_b == nullptr), "vdk_vit_forward: norm_pre needs weight and bias");
 
   auto gemm = [&](const void* A, const void* Bw, void* D, int m, int n, int k, int lda, int epi, const float* bias, const float* gamma,
                   const void* res) {
@@ -632,6 +653,11 @@ extern "C" int vdk_vit_forward(const vdk_vit_net* net, const float* images, int 
     vit_assemble_kernel<<<static_cast<int>(std::min<int64_t>((tot2 + 255) / 256, 148 * 32)), 256, 0, s>>>(tok, net->cls_token, net->pos_embed,
                                                                                                         batch, N, C, x);
     VDK_CUDA_OK(cudaGetLastError());
+    if (net->norm_pre_w) {  // timm pre_norm=True (CLIP towers): LayerNorm over every token before the first block
+      rc = launch_ln_patchify(x, batch, T, 1, C, net->norm_pre_w, net->norm_pre_b, eps, 1, y, nullptr, s);
+      if (rc != VDK_OK) return rc;
+      std::swap(x, y);
+    }
   }
   // ---- blocks ----
   for (int i = 0; i < net->depth; ++i) {
@@ -639,7 +665,7 @@ extern "C" int vdk_vit_forward(const vdk_vit_net* net, const float* images, int 
     VDK_REQUIRE(b->ln1_w && b->ln1_b && b->qkv_w && b->qkv_b && b->proj_w && b->proj_b && b->ln2_w && b->ln2_b && b->fc1_w &&
                     b->fc1_b && b->fc2_w && b->fc2_b,
                 "vdk_vit_forward: null parameter in block %d", i);
-    rc = launch_ln_patchify(x, batch, T, 1, C, b->ln1_w, b->ln1_b, 1e-6f, 1, y, nullptr, s);
+    rc = launch_ln_patchify(x, batch, T, 1, C, b->ln1_w, b->ln1_b, eps, 1, y, nullptr, s);
     if (rc != VDK_OK) return rc;
     rc = gemm(y, b->qkv_w, big, M, 3 * C, C, C, VDK_EPI_NONE, b->qkv_b, nullptr, nullptr);
     if (rc != VDK_OK) return rc;
@@ -647,7 +673,7 @@ extern "C" int vdk_vit_forward(const vdk_vit_net* net, const float* images, int 
     if (rc != VDK_OK) return rc;
     rc = gemm(y, b->proj_w, x, M, C, C, C, VDK_EPI_SCALE_RESIDUAL, b->proj_b, net->ones, x);  // x += proj(a), in place per tile
     if (rc != VDK_OK) return rc;
-    rc = launch_ln_patchify(x, batch, T, 1, C, b->ln2_w, b->ln2_b, 1e-6f, 1, y, nullptr, s);
+    rc = launch_ln_patchify(x, batch, T, 1, C, b->ln2_w, b->ln2_b, eps, 1, y, nullptr, s);
     if (rc != VDK_OK) return rc;
     rc = gemm(y, b->fc1_w, big, M, 4 * C, C, C, VDK_EPI_GELU, b->fc1_b, nullptr, nullptr);
     if (rc != VDK_OK) return rc;
@@ -655,7 +681,7 @@ extern "C" int vdk_vit_forward(const vdk_vit_net* net, const float* images, int 
     if (rc != VDK_OK) return rc;
   }
   // ---- final LayerNorm, neck LayerNorm, Linear over (token, channel) with BatchNorm1d folded ----
-  rc = launch_ln_patchify(x, batch, T, 1, C, net->norm_w, net->norm_b, 1e-6f, 1, y, nullptr, s);
+  rc = launch_ln_patchify(x, batch, T, 1, C, net->norm_w, net->norm_b, eps, 1, y, nullptr, s);
   if (rc != VDK_OK) return rc;
   rc = launch_ln_patchify(y, batch, T, 1, C, net->neck_ln_w, net->neck_ln_b, 1e-5f, 1, x, nullptr, s);
   if (rc != VDK_OK) return rc;
@@ -808,9 +834,16 @@ extern "C" size_t vdk_vit_train_workspace_bytes(const vdk_vit_net* net, int batc
   return L.total;
 }
 
+static int refuse_pre_norm(const vdk_vit_net* net) {
+  VDK_REQUIRE(net && net->norm_pre_w == nullptr && !(net->ln_eps > 0.f && net->ln_eps != 1e-6f),
+              "vdk_vit_train: pre_norm / non-default LayerNorm eps variants (CLIP towers) are built for inference only");
+  return VDK_OK;
+}
+
 extern "C" int vdk_vit_train_forward(const vdk_vit_net* net, const vdk_vit_tensors* p, const float* images, int batch,
                                      float bn_momentum, float* out_feats, void* workspace, size_t workspace_bytes, void* stream) {
   VDK_REQUIRE(net && p && images && out_feats, "vdk_vit_train_forward: null argument");
+  RC(refuse_pre_norm(net));
   VitTrainLayout L;
   RC(vit_train_layout(net, batch, &L));
   VDK_REQUIRE(workspace && workspace_bytes >= L.total && (reinterpret_cast<uintptr_t>(workspace) & 255) == 0,

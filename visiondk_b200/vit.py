@@ -24,8 +24,14 @@ VIT_ARCHS = {
     "vit_small_patch16_224": (16, 384, 12, 6),
     "vit_base_patch16_224": (16, 768, 12, 12),
     "vit_large_patch16_224": (16, 1024, 24, 16),
+    "vit_base_patch16_clip_224": (16, 768, 12, 12),
+    "vit_large_patch14_clip_224": (14, 1024, 24, 16),
     "vit_large_patch14_clip_336": (14, 1024, 24, 16),
 }
+# timm 0.9.16 `vit_*_clip_*` (the CLIP image towers; BASELINE config 5's ViT-L/14 at 336^2): VisionTransformer(pre_norm=True,
+# norm_layer=nn.LayerNorm): a `norm_pre` LayerNorm after cls / position, NO bias in patch_embed.proj, LayerNorm eps 1e-5,
+# standard GELU (the `*_clip_quickgelu_*` architectures are separate timm entries and are not built).
+VIT_PRE_NORM = {"vit_base_patch16_clip_224", "vit_large_patch14_clip_224", "vit_large_patch14_clip_336"}
 MAX_BLOCKS = 48
 
 
@@ -44,32 +50,36 @@ class _Mlp(nn.Module):
 
 
 class _Block(nn.Module):
-    def __init__(self, dim):
+    def __init__(self, dim, eps=1e-6):
         super().__init__()
-        self.norm1 = nn.LayerNorm(dim, eps=1e-6)
+        self.norm1 = nn.LayerNorm(dim, eps=eps)
         self.attn = _Attention(dim)
-        self.norm2 = nn.LayerNorm(dim, eps=1e-6)
+        self.norm2 = nn.LayerNorm(dim, eps=eps)
         self.mlp = _Mlp(dim)
 
 
 class _PatchEmbed(nn.Module):
-    def __init__(self, patch, dim):
+    def __init__(self, patch, dim, bias=True):
         super().__init__()
-        self.proj = nn.Conv2d(3, dim, kernel_size=patch, stride=patch)
+        self.proj = nn.Conv2d(3, dim, kernel_size=patch, stride=patch, bias=bias)
 
 
 class ViTParams(nn.Module):
     """timm 0.9.16 `VisionTransformer(num_classes=0, global_pool='')` parameter tree (timm/models/vision_transformer.py)."""
 
-    def __init__(self, image_size, patch, dim, depth, heads):
+    def __init__(self, image_size, patch, dim, depth, heads, pre_norm=False):
         super().__init__()
         self.image_size, self.patch, self.dim, self.depth, self.heads = image_size, patch, dim, depth, heads
+        self.pre_norm = bool(pre_norm)
+        self.ln_eps = 1e-5 if pre_norm else 1e-6
         n = (image_size // patch) ** 2
-        self.patch_embed = _PatchEmbed(patch, dim)
+        self.patch_embed = _PatchEmbed(patch, dim, bias=not pre_norm)
         self.cls_token = nn.Parameter(torch.zeros(1, 1, dim))
         self.pos_embed = nn.Parameter(torch.randn(1, n + 1, dim) * 0.02)
-        self.blocks = nn.Sequential(*[_Block(dim) for _ in range(depth)])
-        self.norm = nn.LayerNorm(dim, eps=1e-6)
+        if pre_norm:
+            self.norm_pre = nn.LayerNorm(dim, eps=self.ln_eps)
+        self.blocks = nn.Sequential(*[_Block(dim, self.ln_eps) for _ in range(depth)])
+        self.norm = nn.LayerNorm(dim, eps=self.ln_eps)
         for m in self.modules():
             if isinstance(m, nn.Linear):
                 nn.init.trunc_normal_(m.weight, std=0.02)
@@ -103,23 +113,26 @@ class VitNetC(C.Structure):
                 ("patch_w", C.c_void_p), ("patch_b", C.c_void_p), ("cls_token", C.c_void_p), ("pos_embed", C.c_void_p),
                 ("ones", C.c_void_p), ("blocks", _VitBlockC * MAX_BLOCKS),
                 ("norm_w", C.c_void_p), ("norm_b", C.c_void_p), ("neck_ln_w", C.c_void_p), ("neck_ln_b", C.c_void_p),
-                ("neck_w", C.c_void_p), ("neck_b", C.c_void_p)]
+                ("neck_w", C.c_void_p), ("neck_b", C.c_void_p),
+                ("norm_pre_w", C.c_void_p), ("norm_pre_b", C.c_void_p), ("ln_eps", C.c_float)]
 
 
 class ViTWrapper(nn.Module):
     """Drop-in for the reference's TimmWrapper when the timm model is a VisionTransformer (eval / extract path)."""
 
     def __init__(self, model_name: str, feat_dim: int, image_size: int, pretrained: bool = True, patch=None, dim=None, depth=None,
-                 heads=None, **kwargs):
+                 heads=None, pre_norm=None, **kwargs):
         super().__init__()
         if dim is None:
             if model_name not in VIT_ARCHS:
                 raise ValueError(f"backbone '{model_name}' is not built for B200 yet; available: {sorted(VIT_ARCHS)}")
             patch, dim, depth, heads = VIT_ARCHS[model_name]
+        if pre_norm is None:
+            pre_norm = model_name in VIT_PRE_NORM
         if image_size % patch != 0 or dim != heads * 64 or depth > MAX_BLOCKS:
             raise ValueError("ViT on B200: image_size must be a multiple of patch, head_dim must be 64, depth <= 48")
         self.model_name, self.feat_dim, self.image_size = model_name, int(feat_dim), int(image_size)
-        self.model = ViTParams(image_size, patch, dim, depth, heads)
+        self.model = ViTParams(image_size, patch, dim, depth, heads, pre_norm=pre_norm)
         tokens = (image_size // patch) ** 2 + 1
         self.output_layer = nn.Sequential(nn.LayerNorm(dim), nn.Flatten(1), nn.Linear(tokens * dim, feat_dim),
                                           nn.BatchNorm1d(feat_dim))
@@ -132,6 +145,8 @@ class ViTWrapper(nn.Module):
                                "load a checkpoint with load_state_dict (keys are timm's)")
 
     def forward(self, x: torch.Tensor) -> torch.Tensor:
+        if self.training and self.model.pre_norm:
+            raise NotImplementedError("pre_norm ViT variants (CLIP towers) are built for inference / extraction only")
         if self.training:
             return _ViTTrainFn.apply(self, x, *[p for _, p in self.named_parameters()])
         return self.embed(x, l2_normalize=False)
@@ -301,7 +316,11 @@ class ViTWrapper(nn.Module):
         w = m.patch_embed.proj.weight.detach().reshape(m.dim, k)  # (c, kh, kw) order
         if kp != k:
             w = torch.cat([w, torch.zeros(m.dim, kp - k, dtype=w.dtype, device=w.device)], dim=1)
-        net.patch_w, net.patch_b = bf16(w), f32(m.patch_embed.proj.bias)
+        net.patch_w = bf16(w)
+        net.patch_b = f32(m.patch_embed.proj.bias) if m.patch_embed.proj.bias is not None else 0
+        if m.pre_norm:
+            net.norm_pre_w, net.norm_pre_b = f32(m.norm_pre.weight), f32(m.norm_pre.bias)
+        net.ln_eps = float(m.ln_eps)
         net.cls_token, net.pos_embed = f32(m.cls_token.reshape(-1)), f32(m.pos_embed.reshape(-1, m.dim))
         net.ones = f32(torch.ones(m.dim))
         for i, blk in enumerate(m.blocks):
