@@ -464,6 +464,24 @@ int vdk_topk_merge_packed(const void* packed, int n_lists, int64_t n_query, int 
 int vdk_ip_exact_pairs(const float* q32, const float* g32, int dim, const int64_t* qi, const int64_t* gi, int64_t n,
                        float* out, void* stream);
 
+/* ---- eval-time image preprocessing (the GPU input pipeline) ------------------------------------------ */
+/* Replaces, for a BATCH of decoded RGB images of different sizes, the `val.augment` list of configs/faceX/{face,cbir}.yaml:
+ * ResizeAndPadding2Square(size, training=False) (dataset/transforms.py:325-365: PIL Image.resize(BILINEAR) of the longer side
+ * to `size`, centred on a black square), T.ToTensor (:466-468) and T.Normalize(mean, std) (:474-477).  Bit-exact with
+ * Pillow's 8-bit resampling + torch's fp32 arithmetic (oracle/preprocess.py, pinned against the installed Pillow / torchvision).
+ *   packed : DEVICE uint8, every image as [height][width][3] (RGB) at images[i].offset
+ *   images : HOST array of n descriptors
+ *   out    : DEVICE fp32 [n, 3, size, size]
+ * The call computes the resampling coefficients on the host (double precision, like Pillow), uploads them and synchronises
+ * the stream once before launching (JPEG decoding itself stays on the host: out of scope). */
+typedef struct vdk_image_desc {
+  int64_t offset;   /* bytes from `packed` to the image's first pixel */
+  int width, height;
+} vdk_image_desc;
+size_t vdk_preprocess_workspace_bytes(const vdk_image_desc* images, int n, int size);
+int vdk_preprocess_resize_pad_normalize(const uint8_t* packed, const vdk_image_desc* images, int n, int size, const float* mean,
+                                        const float* std_, float* out, void* workspace, size_t workspace_bytes, void* stream);
+
 /* Live kernel timing inside a real step (bench.py's roofline legs; not part of the reference's surface).  Between
  * vdk_prof_begin() and vdk_prof_end() every launch of the categories below is bracketed by two CUDA events on the stream it
  * is launched on; vdk_prof_end synchronises on them and returns, per category, the launch count, the summed event time and

@@ -151,3 +151,30 @@ def test_head_factory_surface(lib):
         HeadFactory({"magface": {}}).get_head()
     with pytest.raises(RuntimeError):
         h(torch.zeros(2, 64), torch.zeros(2, dtype=torch.long))
+
+
+def test_arcface_at_the_reference_face_config_scale(lib):
+    """configs/faceX/face.yaml:28-37,42: feat_dim 128, num_class 58 671 (not a multiple of 8), per-GPU batch 160, ArcFace(0.35, 32) —
+    the fused criterion∘head and its backward against the oracle's fp32 autograd at exactly that size."""
+    from oracle import heads as H
+    D, Cn, B = 128, 58671, 160
+    g = torch.Generator().manual_seed(5)
+    feats = torch.randn(B, D, generator=g) * 2.0
+    labels = torch.randint(0, Cn, (B,), generator=g)
+    w = H.init_head_weight(D, Cn)
+    with torch.no_grad():  # some class centres near their samples so that the margin branch matters
+        for r in range(0, B, 4):
+            w[:, labels[r]] = feats[r] / feats[r].norm() + 0.3 * w[:, labels[r]]
+    f_ref = feats.clone().requires_grad_(True)
+    w_ref = w.clone().requires_grad_(True)
+    ref_loss = H.cross_entropy(H.arcface_logits(f_ref, w_ref, labels, 0.35, 0.0, 32.0), labels, 0.1)
+    ref_loss.backward()
+    head = ArcFace(D, Cn, 0.35, 0.0, 32).cuda()
+    with torch.no_grad():
+        head.weight.copy_(w)
+    f = feats.cuda().requires_grad_(True)
+    loss = margin_ce_loss(head, f, labels.cuda(), 0.1)
+    loss.backward()
+    assert abs(loss.item() - ref_loss.item()) <= 1e-4 * abs(ref_loss.item()) + 1e-5
+    close(f.grad.cpu(), f_ref.grad, 2e-3, "dfeats at C=58671")
+    close(head.weight.grad.cpu(), w_ref.grad, 2e-3, "dweight at C=58671")

@@ -41,6 +41,10 @@ class TopkPlan(C.Structure):
 _p, _i, _i64, _sz = C.c_void_p, C.c_int, C.c_int64, C.c_size_t
 
 
+class ImageDesc(C.Structure):
+    _fields_ = [("offset", C.c_int64), ("width", C.c_int), ("height", C.c_int)]
+
+
 class ProfTotal(C.Structure):
     _fields_ = [("launches", C.c_longlong), ("ms", C.c_double), ("flops", C.c_double), ("bytes", C.c_double)]
 
@@ -65,6 +69,9 @@ SIGNATURES = {
     "vdk_struct_sizes": (_i, [_p, _i]),
     "vdk_last_error_string": (C.c_char_p, []),
     "vdk_device_check": (_i, []),
+    "vdk_preprocess_workspace_bytes": (_sz, [C.POINTER(ImageDesc), _i, _i]),
+    "vdk_preprocess_resize_pad_normalize": (_i, [_p, C.POINTER(ImageDesc), _i, _i, C.POINTER(C.c_float), C.POINTER(C.c_float), _p, _p,
+                                                 _sz, _p]),
     "vdk_prof_begin": (_i, []),
     "vdk_prof_end": (_i, [C.POINTER(ProfTotal), _i]),
     "vdk_gemm": (_i, [_p, _p]),

@@ -7,7 +7,10 @@ normalisations, the cos(theta) contraction on tcgen05, the margin, and (in the f
 cross-entropy with label smoothing and the whole backward — is csrc/heads.cu.
 
 `margin_ce_loss(head, feats, labels, label_smooth)` is criterion∘head fused: the two are only ever called
-together (engine/procedure/train.py:196), so the [B,C] logits never have to exist.
+together (engine/procedure/train.py:196), so the caller never holds a [B,C] logits tensor or its autograd graph.  Inside the
+kernels the cosines and the two gradient factors still live in a caller-owned fp32 workspace of 3 x B x C floats (113 MB at the
+reference's face config, B = 160, C = 58 671, configs/faceX/face.yaml:34,42 — tested at that size in tests/test_heads_gpu.py);
+a class-sharded / streaming-softmax head for million-class problems is not built.
 """
 from __future__ import annotations
 
