@@ -671,11 +671,11 @@ def bench_retrieval(ctx, args):
     q_sizes = sharding.shard_sizes(nq, ctx.world)
     q_local = q_full[q_lo:q_hi].contiguous()
 
-    def step_dev():
-        return sharded_flat_search(index, q_local, q_sizes, k)
+    def step_dev():  # device-resident: no host synchronisation inside a search; overflow is checked once after the timed loop
+        return sharded_flat_search(index, q_local, q_sizes, k, defer_check=True)
 
     ms = timed(ctx, step_dev, args.steps, args.warmup)
-    index.check_status()
+    index.check_status(all_ranks=True)  # raises on every rank if any shard overflowed its candidate lists during the loop
     value = nq * ng / (ms * 1e-3)
 
     # parity check, outside the timed region: 64 sampled query rows of THIS search (single GPU or sharded) against the

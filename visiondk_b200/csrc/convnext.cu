@@ -439,7 +439,7 @@ dwconv7_chunk_kernel(const __grid_constant__ CUtensorMap map_x, int B, int H, in
 // (one output row each) run the tap loop of tile i+1 while the LayerNorm statistics of tile i cross the cluster
 // (split-phase barrier.cluster: arrive after publishing the chunk's (mean, M2), wait only after the next tile's taps).
 // LayerNorm numerics are unchanged: two-pass statistics per chunk, Chan's combination across the chunks of a pixel.
-template <int MODE, int CHUNK, int TH>
+template <int MODE, int CHUNK, int TH, bool F2>
 __global__ void __launch_bounds__((TH + 1) * 32, TH == 7 ? 2 : 1)
 dwconv7_pipe_kernel(const __grid_constant__ CUtensorMap map_x, int B, int H, int W, int C, int nchunks, int n_tiles,
                     const float* __restrict__ w49, const float* __restrict__ bias, const float* __restrict__ ln_w,
@@ -558,8 +558,15 @@ dwconv7_pipe_kernel(const __grid_constant__ CUtensorMap map_x, int B, int H, int
         for (int p = 0; p < kDwTW; ++p) {
           const int dx = ix - p;
           if (dx >= 0 && dx < 7) {
-            acc[p][0] = ffma2(a, wlo[dx], acc[p][0]);
-            acc[p][1] = ffma2(c, whi[dx], acc[p][1]);
+            if (F2) {
+              acc[p][0] = ffma2(a, wlo[dx], acc[p][0]);
+              acc[p][1] = ffma2(c, whi[dx], acc[p][1]);
+            } else {  // scalar FFMA form of the same arithmetic (tools/ubench_fma.cu: which form sustains more with these operands)
+              acc[p][0].x = fmaf(a.x, wlo[dx].x, acc[p][0].x);
+              acc[p][0].y = fmaf(a.y, wlo[dx].y, acc[p][0].y);
+              acc[p][1].x = fmaf(c.x, whi[dx].x, acc[p][1].x);
+              acc[p][1].y = fmaf(c.y, whi[dx].y, acc[p][1].y);
+            }
           }
         }
       }
@@ -880,7 +887,7 @@ static int launch_dwconv_tw(const CUtensorMap& mx, int batch, int H, int W, int 
 
 
 // Persistent launch: one CTA per SM (two for the 7-row tile), grid = co-resident clusters x chunks.
-template <int MODE, int CHUNK, int TH>
+template <int MODE, int CHUNK, int TH, bool F2>
 static int launch_dwconv7_pipe_t(const __nv_bfloat16* x, int batch, int H, int W, int C, const float* w49, const float* bias,
                                  const float* ln_w, const float* ln_b, float eps, __nv_bfloat16* y, float* rstd_out,
                                  const __nv_bfloat16* addend, cudaStream_t s) {
@@ -891,7 +898,7 @@ static int launch_dwconv7_pipe_t(const __nv_bfloat16* x, int batch, int H, int W
   CUtensorMap mx;
   int rc = make_tma_nhwc_16bit(&mx, x, batch, H, W, C, TH + 6, kDwTW + 6, CHUNK);
   if (rc != VDK_OK) return rc;
-  auto kern = dwconv7_pipe_kernel<MODE, CHUNK, TH>;
+  auto kern = dwconv7_pipe_kernel<MODE, CHUNK, TH, F2>;
   const int cluster = (MODE == 0) ? nchunks : 1;
   struct Fit { int clusters; };
   static Fit fit[17] = {};  // per cluster size: co-resident clusters of this instantiation (queried once)
@@ -936,9 +943,16 @@ static int launch_dwconv7_pipe(int mode, const __nv_bfloat16* x, int batch, int 
                                const float* bias, const float* ln_w, const float* ln_b, float eps, __nv_bfloat16* y, float* rstd_out,
                                const __nv_bfloat16* addend, cudaStream_t s) {
   const bool tall = H > 7;  // 14-row tiles (15 warps, one CTA per SM) unless the map is 7 rows high
-#define VDK_DWP(MODEV, CHV)                                                                                                     \
-  return tall ? launch_dwconv7_pipe_t<MODEV, CHV, 14>(x, batch, H, W, C, w49, bias, ln_w, ln_b, eps, y, rstd_out, addend, s)   \
-              : launch_dwconv7_pipe_t<MODEV, CHV, 7>(x, batch, H, W, C, w49, bias, ln_w, ln_b, eps, y, rstd_out, addend, s)
+  static const bool f2 = [] {
+    const char* e = getenv("VDK_DWCONV_FFMA2");
+    return e ? atoi(e) != 0 : true;
+  }();
+#define VDK_DWP(MODEV, CHV)                                                                                                           \
+  if (f2)                                                                                                                             \
+    return tall ? launch_dwconv7_pipe_t<MODEV, CHV, 14, true>(x, batch, H, W, C, w49, bias, ln_w, ln_b, eps, y, rstd_out, addend, s)  \
+                : launch_dwconv7_pipe_t<MODEV, CHV, 7, true>(x, batch, H, W, C, w49, bias, ln_w, ln_b, eps, y, rstd_out, addend, s);  \
+  return tall ? launch_dwconv7_pipe_t<MODEV, CHV, 14, false>(x, batch, H, W, C, w49, bias, ln_w, ln_b, eps, y, rstd_out, addend, s)   \
+              : launch_dwconv7_pipe_t<MODEV, CHV, 7, false>(x, batch, H, W, C, w49, bias, ln_w, ln_b, eps, y, rstd_out, addend, s)
   if (mode == 0) {
     if (chunk == 128) { VDK_DWP(0, 128); }
     if (chunk == 96) { VDK_DWP(0, 96); }
