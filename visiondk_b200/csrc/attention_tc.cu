@@ -5,18 +5,19 @@
 // written to memory.  Input is the qkv Linear's output as stored, bf16 [B, N, 3, H, 64]; output bf16 [B, N, H*64]
 // (+ optionally the log2-domain log-sum-exp per row, which the training backward consumes).
 //
-// One CTA = one (image, head) x TWO 128-query tiles (ViT-B/16's 197 tokens are exactly two), 320 threads:
+// CTAs are PERSISTENT (one per SM); an item = one (image, head) x TWO 128-query tiles (ViT-B/16's 197 tokens are exactly two),
+// items strided over the grid.  320 threads:
 //   warps 0-3   softmax group of query tile 0 (TMEM lane = query row: one thread owns one row, no shuffles)
 //   warps 4-7   softmax group of query tile 1
-//   warp  8     TMA producer: Q tiles once, then K/V tiles (128 keys) through a three-deep mbarrier ring
-//   warp  9     tcgen05.mma issuer: S_t = Q_t K_j^T (128x128x64, both operands K-major) into TMEM, O_t += P_t V_j (128x64x128:
+//   warp  8     TMA producer: Q tile pair once per item, K/V tiles (64 keys) through a six-deep mbarrier ring, one item ahead
+//   warp  9     tcgen05.mma issuer: S_t = Q_t K_j^T (128x64x64, both operands K-major) into TMEM, O_t += P_t V_j (128x64x64:
 //               P from shared memory, written by the softmax group in the swizzle-128B K-major layout; V as stored =
 //               MN-major operand)
-// TMEM: S_0, S_1 (128 fp32 columns each), O_0, O_1 (64 each) = 384 of 512 columns.  The two groups ping-pong: while one
-// exponentiates tile j, the tensor core computes the other group's P V and next S.  CTAs are PERSISTENT (one per SM, items
-// strided over the grid): TMEM is allocated once, barrier phases run across items, and the producer loads the next item's Q
-// and K/V while the current one is still in its softmax — the first version (one CTA per item) spent 3/4 of every CTA's life
-// in allocation, barrier set-up and the first TMA round trip (152 TFLOP/s at 197 tokens).
+// TMEM: S_0, S_1, O_0, O_1, 64 fp32 columns each.  A group pulls its 64 scores per row into registers with two
+// `tcgen05.ld.32x32b.x32`, hands S_t back at once (s_free) — so the tensor core computes S_t of the NEXT key tile while the
+// group exponentiates this one — and double-buffers P_t, so P V of tile j runs under the softmax of tile j+1.  History
+// (`profiles/r02_attention.md`): one CTA per item 152 TFLOP/s; persistent 198; 128-key tiles with S read twice 210; this 64-key
+// pipeline removes the S -> softmax -> P V -> S round trip from every tile's critical path.
 // Softmax is the online recurrence in the log2 domain with a LAZY rescale: the running reference maximum only moves (and
 // O / l are only rescaled, TMEM -> registers -> TMEM) when a row's maximum grows by more than 2^8; P = exp2(s - m_ref) then
 // stays below 256, exact in bf16's range, and the final O / l cancels the stale reference.
@@ -30,12 +31,14 @@ namespace vdk {
 
 constexpr int kAtD = 64;          // head dim
 constexpr int kAtQM = 128;        // query rows per tile (TMEM lanes)
-constexpr int kAtKV = 128;        // keys per tile
-constexpr int kAtStages = 3;
+constexpr int kAtKV = 64;         // keys per tile
+constexpr int kAtStages = 6;      // K/V ring (16 KB per stage)
 constexpr int kAtThreads = 320;
-constexpr int kAtTile = kAtQM * kAtD * 2;  // 16 KB: a 128 x 64 bf16 tile
-constexpr int kAtSmem = 2 * kAtTile + kAtStages * 2 * kAtTile + 2 * 2 * kAtTile + 16 * 8 + 16 + 1024;
+constexpr int kAtQTile = kAtQM * kAtD * 2;   // 16 KB: a 128 x 64 bf16 tile (Q, P)
+constexpr int kAtKTile = kAtKV * kAtD * 2;   // 8 KB: a 64 x 64 bf16 tile (K, V)
+constexpr int kAtSmem = 2 * kAtQTile + kAtStages * 2 * kAtKTile + 2 * 2 * kAtQTile + 32 * 8 + 16 + 1024;
 static_assert(kAtSmem <= 227 * 1024, "attention shared memory budget");
+constexpr uint32_t kAtTmemCols = 256;  // S_0, S_1 (64 fp32 columns each), O_0, O_1 (64 each)
 
 struct AttParams {
   int B, N, H;
@@ -50,6 +53,16 @@ __device__ __forceinline__ float ex2_approx(float x) {
   asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
   return y;
 }
+__device__ __forceinline__ float fmax3(float a, float b, float c) {  // 3-input FMNMX3 (sm_100)
+  float d;
+  asm("max.f32 %0, %1, %2, %3;" : "=f"(d) : "f"(a), "f"(b), "f"(c));
+  return d;
+}
+__device__ __forceinline__ float2 fadd2(float2 a, float2 b) {  // add.rn.f32x2: two row-sum accumulations per instruction
+  unsigned long long ra = *reinterpret_cast<unsigned long long*>(&a), rb = *reinterpret_cast<unsigned long long*>(&b), rd;
+  asm("add.rn.f32x2 %0, %1, %2;" : "=l"(rd) : "l"(ra), "l"(rb));
+  return *reinterpret_cast<float2*>(&rd);
+}
 __device__ __forceinline__ uint32_t pack_bf16x2(float lo, float hi) {
   uint32_t r;
   asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(hi), "f"(lo));
@@ -57,20 +70,21 @@ __device__ __forceinline__ uint32_t pack_bf16x2(float lo, float hi) {
 }
 
 __global__ void __launch_bounds__(kAtThreads, 1)
-attention_fwd_tc_kernel(const __grid_constant__ CUtensorMap map_qkv, const AttParams p) {
+attention_fwd_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ CUtensorMap map_kv, const AttParams p) {
   extern __shared__ uint8_t att_smem_raw[];
   uint8_t* smem = att_smem_raw + ((1024u - (smem_u32(att_smem_raw) & 1023u)) & 1023u);
-  uint8_t* smem_q = smem;                                   // [2][16 KB]
-  uint8_t* smem_kv = smem + 2 * kAtTile;                    // [stages][K 16 KB | V 16 KB]
-  uint8_t* smem_p = smem_kv + kAtStages * 2 * kAtTile;      // [2 groups][2 K-blocks of 16 KB]
-  uint64_t* q_full = reinterpret_cast<uint64_t*>(smem_p + 2 * 2 * kAtTile);
+  uint8_t* smem_q = smem;                                     // [2 tiles][16 KB]
+  uint8_t* smem_kv = smem + 2 * kAtQTile;                     // [stages][K 8 KB | V 8 KB]
+  uint8_t* smem_p = smem_kv + kAtStages * 2 * kAtKTile;       // [2 groups][2 buffers][16 KB]
+  uint64_t* q_full = reinterpret_cast<uint64_t*>(smem_p + 2 * 2 * kAtQTile);
   uint64_t* q_empty = q_full + 1;
-  uint64_t* kv_full = q_empty + 1;
-  uint64_t* kv_empty = kv_full + kAtStages;
-  uint64_t* s_full = kv_empty + kAtStages;   // [2]
-  uint64_t* p_full = s_full + 2;             // [2]
-  uint64_t* p_empty = p_full + 2;            // [2]
-  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(p_empty + 2);
+  uint64_t* kv_full = q_empty + 1;           // [stages]
+  uint64_t* kv_empty = kv_full + kAtStages;  // [stages]
+  uint64_t* s_full = kv_empty + kAtStages;   // [2]      S_t is in TMEM
+  uint64_t* s_free = s_full + 2;             // [2]      the group holds S_t in registers: TMEM may be overwritten
+  uint64_t* p_full = s_free + 2;             // [2][2]   P_t[buffer] is in shared memory
+  uint64_t* p_empty = p_full + 4;            // [2][2]   the P V that read P_t[buffer] has retired
+  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(p_empty + 4);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int J = p.n_kvtiles;
@@ -78,7 +92,8 @@ attention_fwd_tc_kernel(const __grid_constant__ CUtensorMap map_qkv, const AttPa
   const int n_items = n_pairs * p.H * p.B;  // persistent: this CTA takes items blockIdx.x, + gridDim.x, ...
 
   if (threadIdx.x == 0) {
-    prefetch_tensormap(&map_qkv);
+    prefetch_tensormap(&map_q);
+    prefetch_tensormap(&map_kv);
     mbar_init(q_full, 1);
     mbar_init(q_empty, 1);
     for (int i = 0; i < kAtStages; ++i) {
@@ -87,12 +102,15 @@ attention_fwd_tc_kernel(const __grid_constant__ CUtensorMap map_qkv, const AttPa
     }
     for (int i = 0; i < 2; ++i) {
       mbar_init(&s_full[i], 1);
-      mbar_init(&p_full[i], 4);   // one arrival per warp of the group
+      mbar_init(&s_free[i], 4);  // one arrival per warp of the group
+    }
+    for (int i = 0; i < 4; ++i) {
+      mbar_init(&p_full[i], 4);
       mbar_init(&p_empty[i], 1);
     }
     fence_mbar_init();
   }
-  if (warp == 9) tmem_alloc<512>(tmem_ptr);
+  if (warp == 9) tmem_alloc<kAtTmemCols>(tmem_ptr);
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
@@ -114,14 +132,14 @@ attention_fwd_tc_kernel(const __grid_constant__ CUtensorMap map_qkv, const AttPa
         decode(item, pair, h, b);
         const int qt0 = pair * 2, n_t = min(2, p.n_qtiles - qt0);
         if (qc > 0) mbar_wait_relaxed(q_empty, (qc - 1) & 1);  // every S = Q K^T of the previous item has retired
-        mbar_arrive_expect_tx(q_full, n_t * kAtTile);
-        for (int t = 0; t < n_t; ++t) tma_load_3d(smem_q + t * kAtTile, &map_qkv, q_full, h * kAtD, (qt0 + t) * kAtQM, b);
+        mbar_arrive_expect_tx(q_full, n_t * kAtQTile);
+        for (int t = 0; t < n_t; ++t) tma_load_3d(smem_q + t * kAtQTile, &map_q, q_full, h * kAtD, (qt0 + t) * kAtQM, b);
         for (int j = 0; j < J; ++j, ++kvc) {
           const int st = kvc % kAtStages;
           if (kvc >= kAtStages) mbar_wait_relaxed(&kv_empty[st], ((kvc / kAtStages) - 1) & 1);
-          mbar_arrive_expect_tx(&kv_full[st], 2 * kAtTile);
-          tma_load_3d(smem_kv + st * 2 * kAtTile, &map_qkv, &kv_full[st], (p.H + h) * kAtD, j * kAtKV, b);
-          tma_load_3d(smem_kv + st * 2 * kAtTile + kAtTile, &map_qkv, &kv_full[st], (2 * p.H + h) * kAtD, j * kAtKV, b);
+          mbar_arrive_expect_tx(&kv_full[st], 2 * kAtKTile);
+          tma_load_3d(smem_kv + st * 2 * kAtKTile, &map_kv, &kv_full[st], (p.H + h) * kAtD, j * kAtKV, b);
+          tma_load_3d(smem_kv + st * 2 * kAtKTile + kAtKTile, &map_kv, &kv_full[st], (2 * p.H + h) * kAtD, j * kAtKV, b);
         }
       }
     }
@@ -131,27 +149,26 @@ attention_fwd_tc_kernel(const __grid_constant__ CUtensorMap map_qkv, const AttPa
       constexpr uint32_t idesc_s = umma_idesc_f16<true>(kAtQM, kAtKV);        // Q, K both K-major
       constexpr uint32_t idesc_o = umma_idesc_f16<true>(kAtQM, kAtD, 0u, 1u);  // P K-major, V MN-major (d contiguous)
       int qc = 0, kvc = 0;
-      int gt[2] = {0, 0};  // tiles of group t handed to the softmax warps so far (phases of s_full / p_full / p_empty)
+      int sg[2] = {0, 0};  // S tiles issued per group (phases of s_full / s_free)
+      int pg[2] = {0, 0};  // P V issued per group (buffer = pg & 1, phase = pg >> 1)
       auto issue_s = [&](int t, int stage) {
-        const uint64_t da = umma_desc_k_sw128(smem_u32(smem_q + t * kAtTile));
-        const uint64_t db = umma_desc_k_sw128(smem_u32(smem_kv + stage * 2 * kAtTile));
+        const uint64_t da = umma_desc_k_sw128(smem_u32(smem_q + t * kAtQTile));
+        const uint64_t db = umma_desc_k_sw128(smem_u32(smem_kv + stage * 2 * kAtKTile));
         const uint32_t d = tmem_base + t * kAtKV;
 #pragma unroll
         for (int k = 0; k < kAtD / 16; ++k) umma_f16_ss(d, da + 2 * k, db + 2 * k, idesc_s, k > 0 ? 1u : 0u);
         umma_commit(&s_full[t]);
+        ++sg[t];
       };
       auto issue_pv = [&](int t, int stage, bool first) {
-        const uint32_t pa = smem_u32(smem_p + t * 2 * kAtTile);
-        const uint64_t db = umma_desc_mn_sw128(smem_u32(smem_kv + stage * 2 * kAtTile + kAtTile), 8192);
+        const int buf = pg[t] & 1;
+        const uint64_t da = umma_desc_k_sw128(smem_u32(smem_p + (t * 2 + buf) * kAtQTile));
+        const uint64_t db = umma_desc_mn_sw128(smem_u32(smem_kv + stage * 2 * kAtKTile + kAtKTile), 8192);
         const uint32_t d = tmem_base + 2 * kAtKV + t * kAtD;
 #pragma unroll
-        for (int kb = 0; kb < 2; ++kb) {
-          const uint64_t da = umma_desc_k_sw128(pa + kb * kAtTile);
-#pragma unroll
-          for (int k = 0; k < 4; ++k)
-            umma_f16_ss(d, da + 2 * k, db + 128u * (kb * 4 + k), idesc_o, (!first || kb > 0 || k > 0) ? 1u : 0u);
-        }
-        umma_commit(&p_empty[t]);
+        for (int k = 0; k < kAtKV / 16; ++k) umma_f16_ss(d, da + 2 * k, db + 128u * k, idesc_o, (!first || k > 0) ? 1u : 0u);
+        umma_commit(&p_empty[t * 2 + buf]);
+        ++pg[t];
       };
       for (int item = blockIdx.x; item < n_items; item += gridDim.x, ++qc) {
         int pair, h, b;
@@ -160,25 +177,29 @@ attention_fwd_tc_kernel(const __grid_constant__ CUtensorMap map_qkv, const AttPa
         mbar_wait(q_full, qc & 1);
         mbar_wait(&kv_full[kvc % kAtStages], (kvc / kAtStages) & 1);
         tc_fence_after();
-        // S of the item's first key tile.  The previous item's last P of group t was consumed before its p_full arrival, which
-        // the loop below waited for, so S_t may be overwritten.
-        for (int t = 0; t < n_t; ++t) issue_s(t, kvc % kAtStages);
+        for (int t = 0; t < n_t; ++t) {
+          if (sg[t] > 0) {  // the group has pulled its previous S tile into registers
+            mbar_wait(&s_free[t], (sg[t] - 1) & 1);
+            tc_fence_after();
+          }
+          issue_s(t, kvc % kAtStages);
+        }
         if (J == 1) umma_commit(q_empty);
         for (int j = 0; j < J; ++j, ++kvc) {
           const int st = kvc % kAtStages;
+          if (j + 1 < J) {  // next S of both groups as soon as their registers hold the current one: runs under the softmax
+            mbar_wait(&kv_full[(kvc + 1) % kAtStages], ((kvc + 1) / kAtStages) & 1);
+            for (int t = 0; t < n_t; ++t) {
+              mbar_wait(&s_free[t], (sg[t] - 1) & 1);
+              tc_fence_after();
+              issue_s(t, (kvc + 1) % kAtStages);
+            }
+            if (j + 2 == J) umma_commit(q_empty);  // the item's last S MMAs are in flight: Q is free once they retire
+          }
           for (int t = 0; t < n_t; ++t) {
-            mbar_wait(&p_full[t], gt[t] & 1);  // P_t of this tile is in shared memory; S_t has been consumed as well
+            mbar_wait(&p_full[t * 2 + (pg[t] & 1)], (pg[t] >> 1) & 1);
             tc_fence_after();
             issue_pv(t, st, j == 0);
-            ++gt[t];
-            if (j + 1 < J) {
-              if (t == 0) {
-                mbar_wait(&kv_full[(kvc + 1) % kAtStages], ((kvc + 1) / kAtStages) & 1);
-                tc_fence_after();
-              }
-              issue_s(t, (kvc + 1) % kAtStages);
-              if (j + 2 == J && t == n_t - 1) umma_commit(q_empty);  // the item's last S MMAs are in flight: Q is free once they retire
-            }
           }
           umma_commit(&kv_empty[st]);  // K_j / V_j free once every MMA issued so far has retired
         }
@@ -191,7 +212,6 @@ attention_fwd_tc_kernel(const __grid_constant__ CUtensorMap map_qkv, const AttPa
     const int r = lane_base + lane;                // row inside the tile
     const uint32_t s_addr = tmem_base + (static_cast<uint32_t>(lane_base) << 16) + t * kAtKV;
     const uint32_t o_addr = tmem_base + (static_cast<uint32_t>(lane_base) << 16) + 2 * kAtKV + t * kAtD;
-    uint8_t* prow = smem_p + t * 2 * kAtTile + r * 128;
     const int rsw = r & 7;
     int gt = 0;  // tiles this group has processed (phases)
     for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
@@ -200,94 +220,104 @@ attention_fwd_tc_kernel(const __grid_constant__ CUtensorMap map_qkv, const AttPa
       const int qt0 = pair * 2;
       if (t >= min(2, p.n_qtiles - qt0)) continue;   // odd tile count: the pair's second group idles for this item
       const int row = (qt0 + t) * kAtQM + r;         // token index of this query
+      const bool warp_rows_valid = (qt0 + t) * kAtQM + lane_base < p.N;  // warp-uniform
       float m_ref = -INFINITY, l = 0.f;
       for (int j = 0; j < J; ++j, ++gt) {
+        const int buf = gt & 1;
+        uint8_t* prow = smem_p + (t * 2 + buf) * kAtQTile + r * 128;
         mbar_wait(&s_full[t], gt & 1);
         tc_fence_after();
         const int valid = min(kAtKV, p.N - j * kAtKV);  // keys of this tile that exist
-        // ---- pass A over TMEM: row maximum ----
-        float mx = -INFINITY;
-#pragma unroll 1
-        for (int c = 0; c < kAtKV / 32; ++c) {
-          if (c * 32 >= valid) break;
-          uint32_t v[32];
-          tmem_ld_32x32b_x32(s_addr + c * 32, v);
+        // ---- the tile row of S: TMEM -> registers, then TMEM is handed back at once (the next S = Q K^T runs under this softmax) ----
+        uint32_t v[2][32];
+        if (warp_rows_valid) {
+          tmem_ld_32x32b_x32(s_addr, v[0]);
+          tmem_ld_32x32b_x32(s_addr + 32, v[1]);
           tmem_ld_wait();
-          if (c * 32 + 32 <= valid) {
-#pragma unroll
-            for (int i = 0; i < 32; ++i) mx = fmaxf(mx, __uint_as_float(v[i]));
-          } else {
-#pragma unroll
-            for (int i = 0; i < 32; ++i)
-              if (c * 32 + i < valid) mx = fmaxf(mx, __uint_as_float(v[i]));
-          }
         }
-        mx *= p.scale_log2e;
-        if (j == 0) {
-          m_ref = mx;
-        } else {
-          const float m_new = fmaxf(m_ref, mx);
-          if (__any_sync(0xffffffffu, m_new - m_ref > 8.0f)) {
-            // rescale O and l of the rows of this warp (alpha = 1 for rows whose maximum did not move)
-            const float alpha = ex2_approx(m_ref - m_new);
-            m_ref = m_new;
-            l *= alpha;
-            mbar_wait(&p_empty[t], (gt - 1) & 1);  // P V of the previous tile has retired: O is stable
-            tc_fence_after();
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&s_free[t]);
+        if (warp_rows_valid) {  // warps whose 32 query rows all lie beyond N skip the arithmetic (their O rows are never stored)
+          float mx = -INFINITY;
+          if (valid == kAtKV) {
 #pragma unroll
-            for (int hc = 0; hc < kAtD / 32; ++hc) {
-              uint32_t o[32];
-              tmem_ld_32x32b_x32(o_addr + hc * 32, o);
-              tmem_ld_wait();
-#pragma unroll
-              for (int i = 0; i < 32; ++i) o[i] = __float_as_uint(__uint_as_float(o[i]) * alpha);
-              tmem_st_32x32b_x32(o_addr + hc * 32, o);
+            for (int i = 0; i < 32; i += 2) {
+              mx = fmax3(mx, __uint_as_float(v[0][i]), __uint_as_float(v[0][i + 1]));
+              mx = fmax3(mx, __uint_as_float(v[1][i]), __uint_as_float(v[1][i + 1]));
             }
-            tmem_st_wait();
-          }
-        }
-        if (gt > 0) mbar_wait(&p_empty[t], (gt - 1) & 1);  // the P buffer is free (already passed if the rescale / epilogue waited)
-        // ---- pass B: P = exp2(s * c - m_ref) -> bf16 -> shared memory (K-major, 128-byte swizzle), row sum in fp32 ----
-        const float nm = -m_ref;
-#pragma unroll 1
-        for (int c = 0; c < kAtKV / 32; ++c) {
-          uint32_t pk[16];
-          if (c * 32 < valid) {
-            uint32_t v[32];
-            tmem_ld_32x32b_x32(s_addr + c * 32, v);
-            tmem_ld_wait();
-            float e[32];
+          } else {
 #pragma unroll
             for (int i = 0; i < 32; ++i) {
-              e[i] = ex2_approx(fmaf(__uint_as_float(v[i]), p.scale_log2e, nm));
-              if (c * 32 + 32 > valid && c * 32 + i >= valid) e[i] = 0.f;
+              if (i < valid) mx = fmaxf(mx, __uint_as_float(v[0][i]));
+              if (32 + i < valid) mx = fmaxf(mx, __uint_as_float(v[1][i]));
             }
-            float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
-#pragma unroll
-            for (int i = 0; i < 32; i += 4) {
-              s0 += e[i]; s1 += e[i + 1]; s2 += e[i + 2]; s3 += e[i + 3];
-            }
-            l += (s0 + s1) + (s2 + s3);
-#pragma unroll
-            for (int i = 0; i < 16; ++i) pk[i] = pack_bf16x2(e[2 * i], e[2 * i + 1]);
+          }
+          mx *= p.scale_log2e;
+          if (j == 0) {
+            m_ref = mx;
           } else {
+            const float m_new = fmaxf(m_ref, mx);
+            if (__any_sync(0xffffffffu, m_new - m_ref > 8.0f)) {
+              // rescale O and l of the rows of this warp (alpha = 1 for rows whose maximum did not move)
+              const float alpha = ex2_approx(m_ref - m_new);
+              m_ref = m_new;
+              l *= alpha;
+              mbar_wait(&p_empty[t * 2 + ((gt - 1) & 1)], ((gt - 1) >> 1) & 1);  // every earlier P V has retired: O is stable
+              tc_fence_after();
 #pragma unroll
-            for (int i = 0; i < 16; ++i) pk[i] = 0u;  // keys beyond N: P must be exactly zero (never NaN garbage)
-          }
-          uint8_t* blk = prow + (c >> 1) * kAtTile;
+              for (int hc = 0; hc < kAtD / 32; ++hc) {
+                uint32_t o[32];
+                tmem_ld_32x32b_x32(o_addr + hc * 32, o);
+                tmem_ld_wait();
 #pragma unroll
-          for (int q = 0; q < 4; ++q) {
-            const int chunk = (c & 1) * 4 + q;  // 16-byte chunk inside the 128-byte row of this K-block
-            *reinterpret_cast<uint4*>(blk + ((chunk ^ rsw) << 4)) = make_uint4(pk[4 * q], pk[4 * q + 1], pk[4 * q + 2], pk[4 * q + 3]);
+                for (int i = 0; i < 32; ++i) o[i] = __float_as_uint(__uint_as_float(o[i]) * alpha);
+                tmem_st_32x32b_x32(o_addr + hc * 32, o);
+              }
+              tmem_st_wait();
+            }
           }
+          if (gt >= 2) mbar_wait(&p_empty[t * 2 + buf], ((gt >> 1) - 1) & 1);  // the P V that read this P buffer two tiles ago has retired
+          // ---- P = exp2(s * c - m_ref) -> bf16 -> shared memory (K-major, 128-byte swizzle), row sum in fp32 ----
+          const float2 sc2 = make_float2(p.scale_log2e, p.scale_log2e), nm2 = make_float2(-m_ref, -m_ref);
+          float2 lsum = make_float2(0.f, 0.f);
+#pragma unroll
+          for (int c = 0; c < 2; ++c) {
+            uint32_t pk[16];
+            if (valid == kAtKV) {  // full tile: no per-element predicates
+#pragma unroll
+              for (int i = 0; i < 32; i += 2) {
+                const float2 x = ffma2(make_float2(__uint_as_float(v[c][i]), __uint_as_float(v[c][i + 1])), sc2, nm2);
+                const float2 e = make_float2(ex2_approx(x.x), ex2_approx(x.y));
+                lsum = fadd2(lsum, e);
+                pk[i >> 1] = pack_bf16x2(e.x, e.y);
+              }
+            } else {  // the sequence's ragged last tile: keys beyond N get P = 0 exactly (never NaN garbage)
+#pragma unroll
+              for (int i = 0; i < 32; i += 2) {
+                const float2 x = ffma2(make_float2(__uint_as_float(v[c][i]), __uint_as_float(v[c][i + 1])), sc2, nm2);
+                const float e0 = c * 32 + i < valid ? ex2_approx(x.x) : 0.f;
+                const float e1 = c * 32 + i + 1 < valid ? ex2_approx(x.y) : 0.f;
+                lsum.x += e0;
+                lsum.y += e1;
+                pk[i >> 1] = pack_bf16x2(e0, e1);
+              }
+            }
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+              const int chunk = c * 4 + q;  // 16-byte chunk inside the 128-byte row
+              *reinterpret_cast<uint4*>(prow + ((chunk ^ rsw) << 4)) = make_uint4(pk[4 * q], pk[4 * q + 1], pk[4 * q + 2], pk[4 * q + 3]);
+            }
+          }
+          l += lsum.x + lsum.y;
         }
         tc_fence_before();
         fence_proxy_async_smem();  // generic-proxy stores of P -> visible to the tensor core's async proxy
         __syncwarp();
-        if (lane == 0) mbar_arrive(&p_full[t]);
+        if (lane == 0) mbar_arrive(&p_full[t * 2 + buf]);
       }
       // ---- epilogue: O / l -> bf16 row ----
-      mbar_wait(&p_empty[t], (gt - 1) & 1);
+      mbar_wait(&p_empty[t * 2 + ((gt - 1) & 1)], ((gt - 1) >> 1) & 1);
       tc_fence_after();
       const float inv = 1.0f / l;
       // tcgen05.ld is .sync.aligned: EVERY lane of the warp executes it (rows beyond N included); only the stores are predicated
@@ -318,7 +348,7 @@ attention_fwd_tc_kernel(const __grid_constant__ CUtensorMap map_qkv, const AttPa
   __syncthreads();
   if (warp == 9) {
     tc_fence_after();
-    tmem_dealloc<512>(tmem_base);
+    tmem_dealloc<kAtTmemCols>(tmem_base);
   }
 }
 
@@ -330,9 +360,11 @@ int launch_attention_tc(const __nv_bfloat16* qkv, int B, int N, int H, __nv_bflo
     VDK_CUDA_OK(cudaFuncSetAttribute(attention_fwd_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kAtSmem));
     attr = true;
   }
-  CUtensorMap map;
+  CUtensorMap map_q, map_kv;  // the same [B][N][3*H*64] view with 128-row (Q) and 64-row (K, V) boxes
   const uint64_t pitch = 3ull * H * kAtD;
-  int rc = make_tma_3d_16bit(&map, qkv, pitch, static_cast<uint64_t>(N), static_cast<uint64_t>(B), pitch, pitch * N, kAtQM);
+  int rc = make_tma_3d_16bit(&map_q, qkv, pitch, static_cast<uint64_t>(N), static_cast<uint64_t>(B), pitch, pitch * N, kAtQM);
+  if (rc != VDK_OK) return rc;
+  rc = make_tma_3d_16bit(&map_kv, qkv, pitch, static_cast<uint64_t>(N), static_cast<uint64_t>(B), pitch, pitch * N, kAtKV);
   if (rc != VDK_OK) return rc;
   AttParams p{};
   p.B = B; p.N = N; p.H = H;
@@ -344,7 +376,7 @@ int launch_attention_tc(const __nv_bfloat16* qkv, int B, int N, int H, __nv_bflo
   const long long n_items = static_cast<long long>((p.n_qtiles + 1) / 2) * H * B;
   VDK_REQUIRE(n_items < (1ll << 31), "attention: too many (image, head, tile pair) items");
   const int grid = static_cast<int>(std::min<long long>(n_items, sm_count()));  // persistent: one CTA per SM
-  attention_fwd_tc_kernel<<<grid, kAtThreads, kAtSmem, s>>>(map, p);
+  attention_fwd_tc_kernel<<<grid, kAtThreads, kAtSmem, s>>>(map_q, map_kv, p);
   VDK_CUDA_OK(cudaGetLastError());
   return VDK_OK;
 }
