@@ -9,7 +9,8 @@
 // items strided over the grid.  320 threads:
 //   warps 0-3   softmax group of query tile 0 (TMEM lane = query row: one thread owns one row, no shuffles)
 //   warps 4-7   softmax group of query tile 1
-//   warp  8     TMA producer: Q tile pair once per item, K/V tiles (64 keys) through a six-deep mbarrier ring, one item ahead
+//   warp  8     TMA producer: Q tile pair once per item (double-buffered: the next item's Q lands during this item), K/V tiles (64 keys) through a
+//               four-deep mbarrier ring
 //   warp  9     tcgen05.mma issuer: S_t = Q_t K_j^T (128x64x64, both operands K-major) into TMEM, O_t += P_t V_j (128x64x64:
 //               P from shared memory, written by the softmax group in the swizzle-128B K-major layout; V as stored =
 //               MN-major operand)
@@ -32,11 +33,11 @@ namespace vdk {
 constexpr int kAtD = 64;          // head dim
 constexpr int kAtQM = 128;        // query rows per tile (TMEM lanes)
 constexpr int kAtKV = 64;         // keys per tile
-constexpr int kAtStages = 6;      // K/V ring (16 KB per stage)
+constexpr int kAtStages = 4;      // K/V ring (16 KB per stage)
 constexpr int kAtThreads = 320;
 constexpr int kAtQTile = kAtQM * kAtD * 2;   // 16 KB: a 128 x 64 bf16 tile (Q, P)
 constexpr int kAtKTile = kAtKV * kAtD * 2;   // 8 KB: a 64 x 64 bf16 tile (K, V)
-constexpr int kAtSmem = 2 * kAtQTile + kAtStages * 2 * kAtKTile + 2 * 2 * kAtQTile + 32 * 8 + 16 + 1024;
+constexpr int kAtSmem = 2 * 2 * kAtQTile + kAtStages * 2 * kAtKTile + 2 * 2 * kAtQTile + 32 * 8 + 16 + 1024;  // Q double-buffered
 static_assert(kAtSmem <= 227 * 1024, "attention shared memory budget");
 constexpr uint32_t kAtTmemCols = 256;  // S_0, S_1 (64 fp32 columns each), O_0, O_1 (64 each)
 
@@ -73,12 +74,12 @@ __global__ void __launch_bounds__(kAtThreads, 1)
 attention_fwd_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ CUtensorMap map_kv, const AttParams p) {
   extern __shared__ uint8_t att_smem_raw[];
   uint8_t* smem = att_smem_raw + ((1024u - (smem_u32(att_smem_raw) & 1023u)) & 1023u);
-  uint8_t* smem_q = smem;                                     // [2 tiles][16 KB]
-  uint8_t* smem_kv = smem + 2 * kAtQTile;                     // [stages][K 8 KB | V 8 KB]
+  uint8_t* smem_q = smem;                                     // [2 items in flight][2 tiles][16 KB]
+  uint8_t* smem_kv = smem + 2 * 2 * kAtQTile;                 // [stages][K 8 KB | V 8 KB]
   uint8_t* smem_p = smem_kv + kAtStages * 2 * kAtKTile;       // [2 groups][2 buffers][16 KB]
-  uint64_t* q_full = reinterpret_cast<uint64_t*>(smem_p + 2 * 2 * kAtQTile);
-  uint64_t* q_empty = q_full + 1;
-  uint64_t* kv_full = q_empty + 1;           // [stages]
+  uint64_t* q_full = reinterpret_cast<uint64_t*>(smem_p + 2 * 2 * kAtQTile);  // [2]
+  uint64_t* q_empty = q_full + 2;            // [2]
+  uint64_t* kv_full = q_empty + 2;           // [stages]
   uint64_t* kv_empty = kv_full + kAtStages;  // [stages]
   uint64_t* s_full = kv_empty + kAtStages;   // [2]      S_t is in TMEM
   uint64_t* s_free = s_full + 2;             // [2]      the group holds S_t in registers: TMEM may be overwritten
@@ -87,15 +88,17 @@ attention_fwd_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_
   uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(p_empty + 4);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int J = p.n_kvtiles;
+  const int J = p.n_kvtiles, N = p.N;
   const int n_pairs = (p.n_qtiles + 1) / 2;
   const int n_items = n_pairs * p.H * p.B;  // persistent: this CTA takes items blockIdx.x, + gridDim.x, ...
 
   if (threadIdx.x == 0) {
     prefetch_tensormap(&map_q);
     prefetch_tensormap(&map_kv);
-    mbar_init(q_full, 1);
-    mbar_init(q_empty, 1);
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(&q_full[i], 1);
+      mbar_init(&q_empty[i], 1);
+    }
     for (int i = 0; i < kAtStages; ++i) {
       mbar_init(&kv_full[i], 1);
       mbar_init(&kv_empty[i], 1);
@@ -131,9 +134,11 @@ attention_fwd_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_
         int pair, h, b;
         decode(item, pair, h, b);
         const int qt0 = pair * 2, n_t = min(2, p.n_qtiles - qt0);
-        if (qc > 0) mbar_wait_relaxed(q_empty, (qc - 1) & 1);  // every S = Q K^T of the previous item has retired
-        mbar_arrive_expect_tx(q_full, n_t * kAtQTile);
-        for (int t = 0; t < n_t; ++t) tma_load_3d(smem_q + t * kAtQTile, &map_q, q_full, h * kAtD, (qt0 + t) * kAtQM, b);
+        const int qb = qc & 1;  // Q is double-buffered: the next item's tiles land while this item is still in its softmax
+        if (qc >= 2) mbar_wait_relaxed(&q_empty[qb], ((qc >> 1) - 1) & 1);  // every S = Q K^T of the item two back has retired
+        mbar_arrive_expect_tx(&q_full[qb], n_t * kAtQTile);
+        for (int t = 0; t < n_t; ++t)
+          tma_load_3d(smem_q + (qb * 2 + t) * kAtQTile, &map_q, &q_full[qb], h * kAtD, (qt0 + t) * kAtQM, b);
         for (int j = 0; j < J; ++j, ++kvc) {
           const int st = kvc % kAtStages;
           if (kvc >= kAtStages) mbar_wait_relaxed(&kv_empty[st], ((kvc / kAtStages) - 1) & 1);
@@ -152,7 +157,7 @@ attention_fwd_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_
       int sg[2] = {0, 0};  // S tiles issued per group (phases of s_full / s_free)
       int pg[2] = {0, 0};  // P V issued per group (buffer = pg & 1, phase = pg >> 1)
       auto issue_s = [&](int t, int stage) {
-        const uint64_t da = umma_desc_k_sw128(smem_u32(smem_q + t * kAtQTile));
+        const uint64_t da = umma_desc_k_sw128(smem_u32(smem_q + ((qc & 1) * 2 + t) * kAtQTile));
         const uint64_t db = umma_desc_k_sw128(smem_u32(smem_kv + stage * 2 * kAtKTile));
         const uint32_t d = tmem_base + t * kAtKV;
 #pragma unroll
@@ -174,7 +179,7 @@ attention_fwd_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_
         int pair, h, b;
         decode(item, pair, h, b);
         const int n_t = min(2, p.n_qtiles - pair * 2);
-        mbar_wait(q_full, qc & 1);
+        mbar_wait(&q_full[qc & 1], (qc >> 1) & 1);
         mbar_wait(&kv_full[kvc % kAtStages], (kvc / kAtStages) & 1);
         tc_fence_after();
         for (int t = 0; t < n_t; ++t) {
@@ -184,7 +189,7 @@ attention_fwd_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_
           }
           issue_s(t, kvc % kAtStages);
         }
-        if (J == 1) umma_commit(q_empty);
+        if (J == 1) umma_commit(&q_empty[qc & 1]);
         for (int j = 0; j < J; ++j, ++kvc) {
           const int st = kvc % kAtStages;
           if (j + 1 < J) {  // next S of both groups as soon as their registers hold the current one: runs under the softmax
@@ -194,7 +199,7 @@ attention_fwd_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_
               tc_fence_after();
               issue_s(t, (kvc + 1) % kAtStages);
             }
-            if (j + 2 == J) umma_commit(q_empty);  // the item's last S MMAs are in flight: Q is free once they retire
+            if (j + 2 == J) umma_commit(&q_empty[qc & 1]);  // the item's last S MMAs are in flight: its Q buffer is free once they retire
           }
           for (int t = 0; t < n_t; ++t) {
             mbar_wait(&p_full[t * 2 + (pg[t] & 1)], (pg[t] >> 1) & 1);
@@ -220,14 +225,14 @@ attention_fwd_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_
       const int qt0 = pair * 2;
       if (t >= min(2, p.n_qtiles - qt0)) continue;   // odd tile count: the pair's second group idles for this item
       const int row = (qt0 + t) * kAtQM + r;         // token index of this query
-      const bool warp_rows_valid = (qt0 + t) * kAtQM + lane_base < p.N;  // warp-uniform
+      const bool warp_rows_valid = (qt0 + t) * kAtQM + lane_base < N;  // warp-uniform
       float m_ref = -INFINITY, l = 0.f;
       for (int j = 0; j < J; ++j, ++gt) {
         const int buf = gt & 1;
         uint8_t* prow = smem_p + (t * 2 + buf) * kAtQTile + r * 128;
         mbar_wait(&s_full[t], gt & 1);
         tc_fence_after();
-        const int valid = min(kAtKV, p.N - j * kAtKV);  // keys of this tile that exist
+        const int valid = min(kAtKV, N - j * kAtKV);  // keys of this tile that exist
         // ---- the tile row of S: TMEM -> registers, then TMEM is handed back at once (the next S = Q K^T runs under this softmax) ----
         uint32_t v[2][32];
         if (warp_rows_valid) {
