@@ -418,6 +418,14 @@ int vdk_ip_topk(const vdk_topk_plan* plan, const float* q32, const void* qh, con
 int vdk_ip_topk_filter(const vdk_topk_plan* plan, const void* qh, const float* q_norm, const float* q_err, const void* gh,
                        const float* g_norm_max, const float* g_err_max, float* kth_lb_out, int32_t* status, void* workspace,
                        size_t workspace_bytes, void* stream);
+/* The scan stage by stage, for shards that exchange their bounds BETWEEN gallery ranges: runs stages [stage_begin, stage_end) of
+ * the plan (stage_begin == 0 initialises the workspace).  ext_lb (device fp32 [n_query], nullable): the element-wise max over all
+ * shards of the kth_lb values published after the previous stage — it tightens this shard's admission threshold and carry list
+ * (a candidate below ext_lb - eps cannot reach the global top-k), so that after every exchange each shard filters as if it
+ * had scanned the union of all shards' prefixes.  kth_lb_out as in vdk_ip_topk_filter. */
+int vdk_ip_topk_filter_stages(const vdk_topk_plan* plan, const void* qh, const float* q_norm, const float* q_err, const void* gh,
+                              const float* g_norm_max, const float* g_err_max, int stage_begin, int stage_end, const float* ext_lb,
+                              float* kth_lb_out, int32_t* status, void* workspace, size_t workspace_bytes, void* stream);
 int vdk_ip_topk_rerank(const vdk_topk_plan* plan, const float* q32, const float* g32, int64_t id_offset,
                        const float* kth_lb_global, float* out_scores, int64_t* out_ids, void* workspace, size_t workspace_bytes,
                        void* stream);

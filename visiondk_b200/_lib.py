@@ -117,6 +117,7 @@ SIGNATURES = {
     "vdk_topk_workspace_bytes": (_sz, [C.POINTER(TopkPlan)]),
     "vdk_ip_topk": (_i, [C.POINTER(TopkPlan), _p, _p, _p, _p, _p, _p, _p, _p, _i64, _p, _p, _p, _p, _sz, _p]),
     "vdk_ip_topk_filter": (_i, [C.POINTER(TopkPlan), _p, _p, _p, _p, _p, _p, _p, _p, _p, _sz, _p]),
+    "vdk_ip_topk_filter_stages": (_i, [C.POINTER(TopkPlan), _p, _p, _p, _p, _p, _p, _i, _i, _p, _p, _p, _p, _sz, _p]),
     "vdk_ip_topk_rerank": (_i, [C.POINTER(TopkPlan), _p, _p, _i64, _p, _p, _p, _p, _sz, _p]),
     "vdk_topk_row_flags": (_i, [C.POINTER(TopkPlan), _p, _sz, C.POINTER(C.c_void_p)]),
     "vdk_score_range": (_i, [C.POINTER(TopkPlan), _p, _p, _i64, _i64, _i, _p, _sz, _p]),

@@ -351,6 +351,7 @@ struct SelectParams {
   int32_t* row_flag;      // [n_query] set to 1 for rows whose lists overflowed (results incomplete)
   float* kth_lb;          // [n_query] optional: lower bound of the k-th largest canonical score of this shard
   int stage_cap;          // entries of dynamic shared memory available for staging (<= kSelStage)
+  const float* ext_lb;    // [n_query] optional: lower bound of the GLOBAL k-th canonical score known before this range
 };
 
 // Rows whose lists hold at most kSelStage entries in total (every sparse range in practice: ~110 carried + a few hundred
@@ -359,6 +360,7 @@ struct SelectParams {
 // then run out of shared memory.  Longer rows keep sweeping the lists in place.
 constexpr int kSelStage = 4096;
 
+template <bool kAgg>
 __global__ void __launch_bounds__(kSelThreads) select_kernel(const SelectParams p) {
   extern __shared__ uint2 s_stage[];  // [p.stage_cap]
   __shared__ unsigned hist[256];
@@ -433,22 +435,40 @@ __global__ void __launch_bounds__(kSelThreads) select_kernel(const SelectParams 
       __syncthreads();
       // long lists are swept by the whole CTA, short ones (a segment holds tens of entries) by one warp each, so that
       // 30+ nearly empty lists do not cost 30+ CTA-wide loop trips
+      // warp-aggregated histogram: candidate scores share sign and exponent, so the first digit of most keys falls into a
+      // handful of bins — one shared-memory atomic per (warp, distinct bin) instead of one per key (the 4096-entry dense
+      // range serialised ~1000 deep on a single bin: 287 us per select)
       for (int l = 0; l < n_lists; ++l) {
         const unsigned c = s_cnt[l];
         if (c <= kShortList) continue;
         const uint2* e = list_ptr(l);
-        for (unsigned i = tid; i < c; i += kSelThreads) {
-          const uint32_t key = ord_u32(__uint_as_float(e[i].x));
-          if ((key & mask) == prefix) atomicAdd(&hist[(key >> shift) & 255u], 1u);
+        for (unsigned base = 0; base < c; base += kSelThreads) {
+          const unsigned i = base + tid;
+          unsigned bin = 0xffffffffu;
+          if (i < c) {
+            const uint32_t key = ord_u32(__uint_as_float(e[i].x));
+            if ((key & mask) == prefix) bin = (key >> shift) & 255u;
+          }
+          if (kAgg) {
+            const unsigned peers = __match_any_sync(0xffffffffu, bin);
+            if (bin != 0xffffffffu && lane == __ffs(peers) - 1) atomicAdd(&hist[bin], static_cast<unsigned>(__popc(peers)));
+          } else if (bin != 0xffffffffu) {
+            atomicAdd(&hist[bin], 1u);
+          }
         }
       }
       for (int l = warp; l < n_lists; l += kSelThreads / 32) {
         const unsigned c = s_cnt[l];
         if (c > kShortList) continue;
         const uint2* e = list_ptr(l);
-        for (unsigned i = lane; i < c; i += 32) {
-          const uint32_t key = ord_u32(__uint_as_float(e[i].x));
-          if ((key & mask) == prefix) atomicAdd(&hist[(key >> shift) & 255u], 1u);
+        for (unsigned base = 0; base < c; base += 32) {
+          const unsigned i = base + lane;
+          unsigned bin = 0xffffffffu;
+          if (i < c) {
+            const uint32_t key = ord_u32(__uint_as_float(e[i].x));
+            if ((key & mask) == prefix) bin = (key >> shift) & 255u;
+          }
+          if (bin != 0xffffffffu) atomicAdd(&hist[bin], 1u);  // short lists: few keys per warp, nothing to aggregate
         }
       }
       __syncthreads();
@@ -485,31 +505,40 @@ __global__ void __launch_bounds__(kSelThreads) select_kernel(const SelectParams 
     kth_approx = unord_u32(prefix);
     tau_use = kth_approx - 2.0f * p.eps[row];
   }
+  // sharded search: a candidate below (global k-th canonical lower bound) - eps cannot reach the global top-k either
+  if (p.ext_lb) tau_use = fmaxf(tau_use, p.ext_lb[row] - p.eps[row]);
 
   // ---- compaction of the survivors into the other carry buffer ----
   uint2* out = p.carry_out + static_cast<size_t>(row) * p.carry_cap;
+  // survivors take consecutive slots of the carry list: one atomic per warp iteration (ballot + prefix), not one per survivor
+  auto keep = [&](bool in_range, uint2 v) {
+    const bool k_ = in_range && __uint_as_float(v.x) >= tau_use;
+    const unsigned m = __ballot_sync(0xffffffffu, k_);
+    if (m == 0u) return;
+    unsigned base_pos = 0;
+    if (lane == 0) base_pos = atomicAdd(&s_m, static_cast<unsigned>(__popc(m)));
+    base_pos = __shfl_sync(0xffffffffu, base_pos, 0);
+    if (k_) {
+      const unsigned pos = base_pos + __popc(m & ((1u << lane) - 1u));
+      if (pos < static_cast<unsigned>(p.carry_cap)) out[pos] = v;
+    }
+  };
   for (int l = 0; l < n_lists; ++l) {
     const unsigned c = s_cnt[l];
     if (c <= kShortList) continue;
     const uint2* e = list_ptr(l);
-    for (unsigned i = tid; i < c; i += kSelThreads) {
-      const uint2 v = e[i];
-      if (__uint_as_float(v.x) >= tau_use) {
-        const unsigned pos = atomicAdd(&s_m, 1u);
-        if (pos < static_cast<unsigned>(p.carry_cap)) out[pos] = v;
-      }
+    for (unsigned base = 0; base < c; base += kSelThreads) {
+      const unsigned i = base + tid;
+      keep(i < c, i < c ? e[i] : make_uint2(0u, 0u));
     }
   }
   for (int l = warp; l < n_lists; l += kSelThreads / 32) {
     const unsigned c = s_cnt[l];
     if (c > kShortList) continue;
     const uint2* e = list_ptr(l);
-    for (unsigned i = lane; i < c; i += 32) {
-      const uint2 v = e[i];
-      if (__uint_as_float(v.x) >= tau_use) {
-        const unsigned pos = atomicAdd(&s_m, 1u);
-        if (pos < static_cast<unsigned>(p.carry_cap)) out[pos] = v;
-      }
+    for (unsigned base = 0; base < c; base += 32) {
+      const unsigned i = base + lane;
+      keep(i < c, i < c ? e[i] : make_uint2(0u, 0u));
     }
   }
   __syncthreads();
@@ -519,7 +548,7 @@ __global__ void __launch_bounds__(kSelThreads) select_kernel(const SelectParams 
     p.tau[row] = tau_use;
     // a lower bound of this shard's k-th largest CANONICAL score (|approx - canonical| <= eps): what the ranks of a sharded
     // search exchange (max) to skip re-ranking candidates that cannot reach the global top-k
-    if (p.kth_lb) p.kth_lb[row] = kth_approx - p.eps[row];
+    if (p.kth_lb) p.kth_lb[row] = p.ext_lb ? fmaxf(kth_approx - p.eps[row], p.ext_lb[row]) : kth_approx - p.eps[row];
     if (s_over || m > static_cast<unsigned>(p.carry_cap)) {
       if (atomicExch(&p.row_flag[row], 1) == 0) atomicAdd(&p.status[0], 1);  // count each row once
     }
@@ -1029,15 +1058,26 @@ static int check_plan(const vdk_topk_plan* plan) {
 
 // The scan half of vdk_ip_topk: thresholds, gallery ranges, selects.  Leaves every query's surviving candidates in the
 // workspace (carry list) and, if `kth_lb_out` is given, a lower bound of the shard's k-th largest canonical score per query.
+// tau[row] = max(tau[row], ext_lb[row] - eps[row]): a lower bound of the GLOBAL k-th canonical score (max over shards) tightens
+// this shard's admission threshold before its next range
+__global__ void tighten_kernel(float* __restrict__ tau, const float* __restrict__ ext_lb, const float* __restrict__ eps, int n) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) tau[i] = fmaxf(tau[i], ext_lb[i] - eps[i]);
+}
+
+// Stages [stage_begin, stage_end) of the scan: thresholds, gallery ranges, selects.  Leaves every query's surviving candidates
+// in the workspace (carry list) and, per query, a lower bound of the shard's k-th largest canonical score (w.kth_lb).
 static int topk_filter(const vdk_topk_plan* plan, const void* qh, const float* q_norm, const float* q_err, const void* gh,
                        const float* g_norm_max, const float* g_err_max, int32_t* status, void* workspace, size_t workspace_bytes,
-                       cudaStream_t s) {
+                       cudaStream_t s, int stage_begin = 0, int stage_end = 8, const float* ext_lb = nullptr) {
   int rc = check_plan(plan);
   if (rc != VDK_OK) return rc;
   VDK_REQUIRE(status, "vdk_ip_topk: null status");
   const int64_t nq = plan->n_query, ng = plan->n_gallery;
   const int dim = plan->dim, k = plan->k, seg_stride = plan->cand_capacity, carry_cap = plan->carry_capacity;
-  VDK_CUDA_OK(cudaMemsetAsync(status, 0, 4 * sizeof(int32_t), s));
+  if (stage_end > plan->n_stages) stage_end = plan->n_stages;
+  VDK_REQUIRE(stage_begin >= 0 && stage_begin <= stage_end, "vdk_ip_topk: bad stage range [%d, %d)", stage_begin, stage_end);
+  if (stage_begin == 0) VDK_CUDA_OK(cudaMemsetAsync(status, 0, 4 * sizeof(int32_t), s));
   if (nq == 0) return VDK_OK;
   VDK_REQUIRE(qh && q_norm && q_err, "vdk_ip_topk: null query operand");
   VDK_REQUIRE(workspace && workspace_bytes >= vdk_topk_workspace_bytes(plan), "vdk_ip_topk: workspace too small");
@@ -1045,14 +1085,21 @@ static int topk_filter(const vdk_topk_plan* plan, const void* qh, const float* q
   if (ng > 0) VDK_REQUIRE(gh && g_norm_max && g_err_max, "vdk_ip_topk: null gallery operand");
 
   const TopkWorkspace w = carve_workspace(workspace, nq, seg_stride, carry_cap);
-  VDK_CUDA_OK(cudaMemsetAsync(w.row_flag, 0, static_cast<size_t>(nq) * sizeof(int32_t), s));
-  eps_kernel<<<(static_cast<int>(nq) + 255) / 256, 256, 0, s>>>(q_norm, q_err, ng > 0 ? g_norm_max : nullptr,
-                                                                 ng > 0 ? g_err_max : nullptr, static_cast<int>(nq),
-                                                                 w.eps, w.tau, w.carry_cnt, w.kth_lb);
-  VDK_CUDA_OK(cudaGetLastError());
+  if (stage_begin == 0) {
+    VDK_CUDA_OK(cudaMemsetAsync(w.row_flag, 0, static_cast<size_t>(nq) * sizeof(int32_t), s));
+    eps_kernel<<<(static_cast<int>(nq) + 255) / 256, 256, 0, s>>>(q_norm, q_err, ng > 0 ? g_norm_max : nullptr,
+                                                                   ng > 0 ? g_err_max : nullptr, static_cast<int>(nq),
+                                                                   w.eps, w.tau, w.carry_cnt, w.kth_lb);
+    VDK_CUDA_OK(cudaGetLastError());
+  }
+  if (ext_lb) {
+    tighten_kernel<<<(static_cast<int>(nq) + 255) / 256, 256, 0, s>>>(w.tau, ext_lb, w.eps, static_cast<int>(nq));
+    VDK_CUDA_OK(cudaGetLastError());
+  }
   static bool sel_attr = false;
   if (!sel_attr) {
-    VDK_CUDA_OK(cudaFuncSetAttribute(select_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSelStage * sizeof(uint2)));
+    VDK_CUDA_OK(cudaFuncSetAttribute(select_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSelStage * sizeof(uint2)));
+    VDK_CUDA_OK(cudaFuncSetAttribute(select_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSelStage * sizeof(uint2)));
     sel_attr = true;
   }
   int cur = 0;  // carry buffer holding the current survivors
@@ -1063,10 +1110,15 @@ static int topk_filter(const vdk_topk_plan* plan, const void* qh, const float* q
     rc = make_tma_2d_16bit(&mg, gh, static_cast<uint64_t>(ng), dim, dim, kGN, kSBK);
     if (rc != VDK_OK) return rc;
     int64_t lo = 0;
-    for (int st = 0; st < plan->n_stages; ++st) {
+    for (int st = 0; st < stage_end; ++st) {
       const int64_t hi = plan->stage_end[st];
       VDK_REQUIRE(hi > lo || (hi == lo && st > 0), "vdk_ip_topk: stage table must be increasing");
       if (hi == lo) continue;
+      if (st < stage_begin) {  // executed by an earlier call: only the carry parity and the range start move
+        cur ^= 1;
+        lo = hi;
+        continue;
+      }
       const bool dense = (st == 0) || ((plan->dense_mask >> st) & 1);
       RangeLaunch info{};
       rc = launch_score_range(mq, mg, static_cast<int>(nq), dim, lo, hi, dense, w, seg_stride, &info, s);
@@ -1089,9 +1141,19 @@ static int topk_filter(const vdk_topk_plan* plan, const void* qh, const float* q
       sp.status = status;
       sp.row_flag = w.row_flag;
       sp.kth_lb = w.kth_lb;
+      sp.ext_lb = ext_lb;
       // staging area: the dense first range needs room for every score of the range, a sparse range for a few hundred
       sp.stage_cap = dense ? kSelStage : kSelStage / 2;
-      select_kernel<<<static_cast<unsigned>(nq), kSelThreads, sp.stage_cap * sizeof(uint2), s>>>(sp);
+      // warp-aggregated histogram atomics pay on the dense range (thousands of keys whose first digit collides); VDK_SELECT_AGG
+      // = 0 never, 1 dense ranges only (default), 2 always
+      static const int agg_mode = [] {
+        const char* e = getenv("VDK_SELECT_AGG");
+        return e ? atoi(e) : 1;
+      }();
+      if (agg_mode == 2 || (agg_mode == 1 && dense))
+        select_kernel<true><<<static_cast<unsigned>(nq), kSelThreads, sp.stage_cap * sizeof(uint2), s>>>(sp);
+      else
+        select_kernel<false><<<static_cast<unsigned>(nq), kSelThreads, sp.stage_cap * sizeof(uint2), s>>>(sp);
       VDK_CUDA_OK(cudaGetLastError());
       cur ^= 1;
       lo = hi;
@@ -1166,6 +1228,21 @@ extern "C" int vdk_ip_topk_filter(const vdk_topk_plan* plan, const void* qh, con
                                   int32_t* status, void* workspace, size_t workspace_bytes, void* stream) {
   cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
   int rc = topk_filter(plan, qh, q_norm, q_err, gh, g_norm_max, g_err_max, status, workspace, workspace_bytes, s);
+  if (rc != VDK_OK) return rc;
+  if (kth_lb_out && plan->n_query > 0) {
+    const TopkWorkspace w = carve_workspace(workspace, plan->n_query, plan->cand_capacity, plan->carry_capacity);
+    VDK_CUDA_OK(cudaMemcpyAsync(kth_lb_out, w.kth_lb, static_cast<size_t>(plan->n_query) * sizeof(float), cudaMemcpyDeviceToDevice, s));
+  }
+  return VDK_OK;
+}
+
+extern "C" int vdk_ip_topk_filter_stages(const vdk_topk_plan* plan, const void* qh, const float* q_norm, const float* q_err,
+                                         const void* gh, const float* g_norm_max, const float* g_err_max, int stage_begin,
+                                         int stage_end, const float* ext_lb, float* kth_lb_out, int32_t* status, void* workspace,
+                                         size_t workspace_bytes, void* stream) {
+  cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
+  int rc = topk_filter(plan, qh, q_norm, q_err, gh, g_norm_max, g_err_max, status, workspace, workspace_bytes, s, stage_begin,
+                       stage_end, ext_lb);
   if (rc != VDK_OK) return rc;
   if (kth_lb_out && plan->n_query > 0) {
     const TopkWorkspace w = carve_workspace(workspace, plan->n_query, plan->cand_capacity, plan->carry_capacity);

@@ -142,9 +142,15 @@ class FlatIPIndex:
             plan.dense_mask = 0xFF
         elif self.stage_ends is not None:
             ends = [int(e) for e in self.stage_ends if int(e) < ng]
+        elif exchange is not None and exchange.schedule is not None:
+            ends = [min(int(e), ng) for e in exchange.schedule]  # the SAME number of ranges on every shard (clamped to its rows)
+            while ends and ends[-1] >= ng:
+                ends.pop()
+            ends = ends + [ng] * (len(exchange.schedule) - len(ends))  # empty trailing ranges keep the exchange count equal
+            ends = ends[:len(exchange.schedule)]
         if ends is not None and ng > 0:
             ends = ends + [ng]
-            assert len(ends) <= 8
+            assert len(ends) <= 8, "at most 8 gallery ranges"
             plan.n_stages = len(ends)
             for j in range(8):
                 plan.stage_end[j] = ends[min(j, len(ends) - 1)]
@@ -162,12 +168,18 @@ class FlatIPIndex:
                                      status.data_ptr(), self._ws.data_ptr(), self._ws.numel(), _lib.stream_ptr())
                 _lib.check(rc, "vdk_ip_topk")
             else:
-                kth_lb = torch.empty((nq,), dtype=torch.float32, device=self.device)
-                rc = lib.vdk_ip_topk_filter(C.byref(plan), qh.data_ptr(), qn.data_ptr(), qe.data_ptr(), gh_ptr, _lib.ptr(gn),
-                                            _lib.ptr(ge), kth_lb.data_ptr(), status.data_ptr(), self._ws.data_ptr(),
-                                            self._ws.numel(), _lib.stream_ptr())
-                _lib.check(rc, "vdk_ip_topk_filter")
-                exchange(kth_lb)
+                # sharded search: the shards exchange their k-th score bounds after EVERY gallery range, so each of them
+                # filters the next range as if it had scanned the union of all shards' prefixes
+                kth_lb = torch.full((nq,), float("-inf"), dtype=torch.float32, device=self.device)
+                n_ex = plan.n_stages if exchange.schedule is None else len(exchange.schedule) + 1
+                for st in range(n_ex):  # every shard runs the same number of exchanges, whatever its row count
+                    if ng > 0 and st < plan.n_stages:
+                        rc = lib.vdk_ip_topk_filter_stages(C.byref(plan), qh.data_ptr(), qn.data_ptr(), qe.data_ptr(), gh_ptr,
+                                                           _lib.ptr(gn), _lib.ptr(ge), st, st + 1, kth_lb.data_ptr() if st > 0 else 0,
+                                                           kth_lb.data_ptr(), status.data_ptr(), self._ws.data_ptr(), self._ws.numel(),
+                                                           _lib.stream_ptr())
+                        _lib.check(rc, "vdk_ip_topk_filter_stages")
+                    exchange(kth_lb)
                 rc = lib.vdk_ip_topk_rerank(C.byref(plan), q32.data_ptr(), g32_ptr, self.id_offset + g_lo, kth_lb.data_ptr(),
                                             out_s.data_ptr(), out_i.data_ptr(), self._ws.data_ptr(), self._ws.numel(),
                                             _lib.stream_ptr())
@@ -350,11 +362,43 @@ def sharded_flat_search(index: "FlatIPIndex", q_local: torch.Tensor, q_sizes, k:
     call `index.check_status(all_ranks=True)` before trusting the result (it raises if any shard overflowed)."""
     from . import sharding
 
-    def exchange(t: torch.Tensor) -> None:
-        sharding.all_reduce_max_(t)
+    class _Exchange:
+        """In-place element-wise max over the shards + the gallery range schedule every shard follows."""
 
+        def __init__(self, schedule):
+            self.schedule = schedule
+
+        def __call__(self, t: torch.Tensor) -> None:
+            sharding.all_reduce_max_(t)
+
+    world = sharding.world_size()
+    schedule = None
+    if world > 1:
+        # one schedule for all shards, from the LARGEST shard (cached on the index: one tiny all-reduce per index build).  After a
+        # range every shard knows the k-th bound of the union of `world` prefixes, so the next range may grow `world` times
+        # faster at the same expected admissions per query: 2 ranges per shard on 8 GPUs instead of 3
+        index._finalize()
+        if getattr(index, "_shard_rows_max", None) is None or index._shard_rows_max[0] != index.ntotal:
+            t = torch.tensor([float(index.ntotal)], device=index.device)
+            sharding.all_reduce_max_(t)
+            index._shard_rows_max = (index.ntotal, int(t.item()))
+        ng_max = index._shard_rows_max[1]
+        # Measured on 2 GPUs (profiles/r02_retrieval.md): shrinking the dense first range to 8192 / world rows and growing by
+        # 1 + 15 * world costs more in admissions (the epilogue's slow path, ~0.05 us per 1000 admitted candidates) than the
+        # smaller dense write saves: 6.90 ms against 6.21 ms.  So: the single-GPU first range, growth 1 + 7 * world.
+        import os  # tuning switches
+        first = int(os.environ.get("VDK_SHARD_FIRST", min(max(4096, (4 * k + 255) // 256 * 256), 16384)))
+        first = min(first, (max(ng_max, 1) + 255) // 256 * 256)
+        growth = int(os.environ.get("VDK_SHARD_GROWTH", 1 + 7 * world))
+        schedule, e = [], first
+        while e < ng_max and len(schedule) < 7:
+            schedule.append(e)
+            e = (e * growth + 255) // 256 * 256
+            if e >= 0.75 * ng_max:  # no sliver of a last range
+                break
+    ex = _Exchange(schedule)
     return sharding.sharded_search(q_local, list(q_sizes),
-                                   lambda q, kk: index.search_device(q, kk, resolve_overflow=not defer_check, exchange=exchange),
+                                   lambda q, kk: index.search_device(q, kk, resolve_overflow=not defer_check, exchange=ex),
                                    merge_topk, k, pack=pack_topk, merge_packed=merge_topk_packed)
 
 

@@ -24,6 +24,10 @@ def shard_sizes(n: int, world: int) -> List[int]:
     return [shard_bounds(n, world, r)[1] - shard_bounds(n, world, r)[0] for r in range(world)]
 
 
+def world_size() -> int:
+    return dist.get_world_size() if dist.is_available() and dist.is_initialized() else 1
+
+
 def _active() -> bool:
     return dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1
 
