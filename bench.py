@@ -745,9 +745,8 @@ def bench_retrieval(ctx, args):
         ach = flops / (k_ms * 1e-3) / 1e12
         roof = {"bound": "tensor", "kernel": "score_filter_kernel<sparse> over the last gallery range", "achieved": ach,
                 "peak": peak, "unit": "TFLOP/s", "frac": ach / peak,
-                # ncu --set full of this launch (profiles/r01_traffic_retrieval_ncu_raw.csv): 1.130 GB read + 38.5 MB written for
-                # 0.756 GB of fp16 gallery rows (L2 hit 91 %: CTAs drift apart on admissions and re-read tiles a few times)
-                "traffic": 1.168e9 if (nq, ng, ctx.world) == (10000, 1000000, 1) else None, "traffic_unit": "bytes/launch",
+                "traffic": (ncu_traffic(f"retrieval_last_range_nq{nq}_ng{ng}_w{ctx.world}") or {}).get("bytes_per_launch"),
+                "traffic_unit": "bytes/launch (profiles/r02_traffic.json)",
                 "peak_source": src, "launch_ms": k_ms,
                 "algorithmic_flops_per_launch": flops, "share_of_step": k_ms / ms,
                 "whole_step": {"achieved": 2.0 * dim * nq * ngl / (ms * 1e-3) / 1e12,
