@@ -718,12 +718,12 @@ def bench_retrieval(ctx, args):
 
     roof = None
     ngl = hi - lo
-    plan = _lib.TopkPlan()
-    _lib.check(lib.vdk_topk_plan_default(C.byref(plan), nq, ngl, dim, k), "plan")
+    plan = index.last_plan  # the plan of the timed searches (sharded: the common range schedule of all shards)
+    ends = sorted({min(int(plan.stage_end[j]), ngl) for j in range(plan.n_stages)})  # padded (empty) trailing ranges collapse
     if ctx.rank == 0:
         qp = PreparedRows(q_full, True)
-        r_lo = plan.stage_end[plan.n_stages - 2] if plan.n_stages > 1 else 0
-        dense = 1 if plan.n_stages == 1 else 0
+        r_lo = ends[-2] if len(ends) > 1 else 0
+        dense = 1 if len(ends) == 1 else 0
         ws = index._ws  # thresholds of the last search are still in the workspace
 
         def score_only():
@@ -743,7 +743,7 @@ def bench_retrieval(ctx, args):
         flops = 2.0 * dim * nq * (ngl - r_lo)
         peak, src = peak_tflops()
         ach = flops / (k_ms * 1e-3) / 1e12
-        roof = {"bound": "tensor", "kernel": "score_filter_kernel<sparse> over the last gallery range", "achieved": ach,
+        roof = {"bound": "tensor", "kernel": "score_filter_kernel<sparse> over the last gallery range", "rows": [int(r_lo), int(ngl)], "achieved": ach,
                 "peak": peak, "unit": "TFLOP/s", "frac": ach / peak,
                 "traffic": (ncu_traffic(f"retrieval_last_range_nq{nq}_ng{ng}_w{ctx.world}") or {}).get("bytes_per_launch"),
                 "traffic_unit": "bytes/launch (profiles/r02_traffic.json)",
@@ -752,7 +752,8 @@ def bench_retrieval(ctx, args):
                 "whole_step": {"achieved": 2.0 * dim * nq * ngl / (ms * 1e-3) / 1e12,
                                "frac": 2.0 * dim * nq * ngl / (ms * 1e-3) / 1e12 / peak,
                                "note": "2*D FLOP per pair over the whole search (all ranges, select, re-rank)"}}
-    launches = 2 + 2 * plan.n_stages + 1 + (3 if ctx.world > 1 else 0)  # + rows_prepare of gathered queries is in the 2; pack, merge
+    # rows_prepare + eps; per range: score_filter + select (+ tighten, rank sketch, bound when sharded); re-rank (+ pack, merge)
+    launches = 2 + len(ends) * (2 if ctx.world == 1 else 5) + 1 + (2 if ctx.world > 1 else 0)
     return {"value": value, "ms": ms, "e2e_ms": e2e_ms, "roofline": roof, "launches_per_step": launches, "parity_check": parity,
             "h2d": nq * dim * 4, "d2h": nq * k * 12}
 

@@ -119,6 +119,8 @@ SIGNATURES = {
     "vdk_ip_topk_filter": (_i, [C.POINTER(TopkPlan), _p, _p, _p, _p, _p, _p, _p, _p, _p, _sz, _p]),
     "vdk_ip_topk_filter_stages": (_i, [C.POINTER(TopkPlan), _p, _p, _p, _p, _p, _p, _i, _i, _p, _p, _p, _p, _sz, _p]),
     "vdk_ip_topk_rerank": (_i, [C.POINTER(TopkPlan), _p, _p, _i64, _p, _p, _p, _p, _sz, _p]),
+    "vdk_ip_topk_rank_sketch": (_i, [C.POINTER(TopkPlan), _i, C.POINTER(C.c_int32), _i, _p, _p, _sz, _p]),
+    "vdk_topk_bound_from_sketches": (_i, [_p, _i, _i64, C.POINTER(C.c_int32), _i, _i, _p, _p]),
     "vdk_topk_row_flags": (_i, [C.POINTER(TopkPlan), _p, _sz, C.POINTER(C.c_void_p)]),
     "vdk_score_range": (_i, [C.POINTER(TopkPlan), _p, _p, _i64, _i64, _i, _p, _sz, _p]),
     "vdk_reduce_max": (_i, [_p, _i64, _p, _p]),

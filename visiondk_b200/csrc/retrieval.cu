@@ -352,6 +352,7 @@ struct SelectParams {
   float* kth_lb;          // [n_query] optional: lower bound of the k-th largest canonical score of this shard
   int stage_cap;          // entries of dynamic shared memory available for staging (<= kSelStage)
   const float* ext_lb;    // [n_query] optional: lower bound of the GLOBAL k-th canonical score known before this range
+  int prefilter;          // dense ranges: drop what cannot reach the top-k before the radix passes (see select_kernel)
 };
 
 // Rows whose lists hold at most kSelStage entries in total (every sparse range in practice: ~110 carried + a few hundred
@@ -360,13 +361,16 @@ struct SelectParams {
 // then run out of shared memory.  Longer rows keep sweeping the lists in place.
 constexpr int kSelStage = 4096;
 
-template <bool kAgg>
+// kPre: the register prefilter of dense ranges (its own instantiation: the 64 registers of its entry array would otherwise cut
+// the occupancy of every sparse-range launch — measured: 120 -> 225 us per sparse select).
+template <bool kAgg, bool kPre>
 __global__ void __launch_bounds__(kSelThreads) select_kernel(const SelectParams p) {
   extern __shared__ uint2 s_stage[];  // [p.stage_cap]
   __shared__ unsigned hist[256];
   __shared__ unsigned s_cnt[kMaxSeg + 1];
   __shared__ unsigned s_off[kMaxSeg + 2];
-  __shared__ unsigned s_bin, s_krem, s_m, s_over;
+  __shared__ unsigned s_bin, s_krem, s_m, s_over, s_n2;
+  __shared__ float s_floor;
   const int row = blockIdx.x;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
 
@@ -375,6 +379,7 @@ __global__ void __launch_bounds__(kSelThreads) select_kernel(const SelectParams 
   if (tid == 0) {
     s_over = 0;
     s_m = 0;
+    s_n2 = 0;
     s_cnt[0] = min(p.carry_cnt[row], static_cast<unsigned>(p.carry_cap));
   }
   if (tid >= 1 && tid < n_lists) {
@@ -402,7 +407,54 @@ __global__ void __launch_bounds__(kSelThreads) select_kernel(const SelectParams 
     return p.seg + static_cast<size_t>(row) * p.seg_stride + static_cast<size_t>(l - 1) * (p.dense_n > 0 ? 0 : p.seg_cap);
   };
   const bool staged = n <= static_cast<unsigned>(p.stage_cap);
-  if (staged) {
+  // Dense range (thousands of scores per row, all of one sign and exponent: the first radix digits barely discriminate and
+  // their histogram atomics pile up on 2-3 bins — 290-430 us per launch).  Prefilter instead: thread t takes the maximum of
+  // entries t, t + 128, ...; >= k threads hold a maximum >= F (the k-th largest of the 128 maxima), so the
+  // k-th largest score of the row is >= F and only entries >= F - 2 eps can survive the select.  They (a few hundred) are
+  // compacted into shared memory and the radix passes run on them.
+  const bool pre = kPre && p.dense_n > 0 && staged && n >= 1024u && p.k <= kSelThreads;  // CTA-uniform
+  if constexpr (kPre) {
+   if (pre) {
+    // two sweeps over the row's entries (32 KB: the second one hits L2), nothing held in registers in between
+    const uint2* c0 = list_ptr_g(0);
+    const uint2* d0 = list_ptr_g(1);
+    const unsigned cnt0 = s_cnt[0];
+    float mx = -INFINITY;
+#pragma unroll 8
+    for (unsigned i = tid; i < n; i += kSelThreads) mx = fmaxf(mx, __uint_as_float(i < cnt0 ? c0[i].x : d0[i - cnt0].x));
+    float* s_mx = reinterpret_cast<float*>(hist);  // re-zeroed by every radix pass
+    s_mx[tid] = mx;
+    __syncthreads();
+    int gt = 0, ge = 0;
+    for (int j = 0; j < kSelThreads; ++j) {
+      const float y = s_mx[j];
+      gt += y > mx ? 1 : 0;
+      ge += y >= mx ? 1 : 0;
+    }
+    if (gt < p.k && p.k <= ge) s_floor = mx;  // the k-th largest maximum (ties write the same value)
+    __syncthreads();
+    const float keep_from = s_floor - 2.0f * p.eps[row];
+#pragma unroll 4
+    for (unsigned base = 0; base < n; base += kSelThreads) {
+      const unsigned i = base + tid;
+      uint2 v = make_uint2(0u, 0u);
+      if (i < n) v = i < cnt0 ? c0[i] : d0[i - cnt0];
+      const bool k_ = i < n && __uint_as_float(v.x) >= keep_from;
+      const unsigned m = __ballot_sync(0xffffffffu, k_);
+      if (m != 0u) {  // warp-uniform
+        unsigned base_pos = 0;
+        if (lane == 0) base_pos = atomicAdd(&s_n2, static_cast<unsigned>(__popc(m)));
+        base_pos = __shfl_sync(0xffffffffu, base_pos, 0);
+        if (k_) s_stage[base_pos + __popc(m & ((1u << lane) - 1u))] = v;
+      }
+    }
+    __syncthreads();
+    if (tid == 0) s_cnt[0] = s_n2;  // <= n <= stage_cap
+    n_lists = 1;
+    __syncthreads();
+   }
+  }
+  if (!pre && staged) {
     for (int l = warp; l < n_lists; l += kSelThreads / 32) {
       const unsigned c = s_cnt[l];
       if (c > kShortList) continue;
@@ -720,6 +772,53 @@ __global__ void topk_merge_kernel(const float* __restrict__ scores, const int64_
       out_ids[row * k + j] = bid;
     }
     if (lane == bl && bid >= 0) ++head;
+  }
+}
+
+// Packed lists (the sharded search's merge): one query per GROUP of `group` = pow2 >= n_lists lanes (4 queries per warp on 8
+// shards).  Lane l of a group walks list l and holds its head as ONE 64-bit key (order-preserving score bits << 32 | ~id: larger
+// is better — score desc, id asc; 0 = list exhausted) with the next entry already loaded, so a step is log2(group) 64-bit
+// max-shuffles and the winner's register move: no load on the critical path (the general kernel above re-loads 32 heads and
+// runs a five-round three-field tournament per step: 169 us for 8 x 10 000 x 100 against ~15 us here).
+__global__ void __launch_bounds__(256) topk_merge_packed_kernel(const unsigned long long* __restrict__ packed, int n_lists,
+                                                                int group, int64_t n_query, int k,
+                                                                float* __restrict__ out_scores, int64_t* __restrict__ out_ids) {
+  const int lane = threadIdx.x & 31;
+  const int sub = lane & (group - 1);
+  const int64_t warp_id = (static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x) >> 5;
+  const int64_t row = warp_id * (32 / group) + lane / group;
+  const bool row_ok = row < n_query;  // lanes of rows past the end keep shuffling (full-mask warp), they never load or store
+  const bool has_list = row_ok && sub < n_lists;
+  const unsigned long long* src = packed + (has_list ? static_cast<size_t>(sub) * n_query * k + static_cast<size_t>(row) * k : 0);
+  auto key_of = [](unsigned long long w) -> unsigned long long {
+    const uint32_t lo = static_cast<uint32_t>(w);
+    if (lo == 0xffffffffu) return 0ull;  // padding (id -1): the list ends here
+    uint32_t u = static_cast<uint32_t>(w >> 32);
+    if (u == 0x80000000u) u = 0u;  // -0.0 ties with +0.0 under the float comparison of the tie rule
+    return (static_cast<unsigned long long>(ord_u32(__uint_as_float(u))) << 32) | static_cast<unsigned long long>(~lo);
+  };
+  unsigned long long cur_w = has_list ? src[0] : ~0ull, nxt_w = (has_list && k > 1) ? src[1] : ~0ull;  // ~0: padding word
+  unsigned long long cur = key_of(cur_w);
+  int head = 0;
+  for (int j = 0; j < k; ++j) {
+    unsigned long long best = cur;
+    for (int off = group >> 1; off > 0; off >>= 1) {
+      const unsigned long long o = __shfl_xor_sync(0xffffffffu, best, off);
+      best = o > best ? o : best;
+    }
+    if (best == 0ull) {  // every list exhausted
+      if (sub == 0 && row_ok) {
+        out_scores[row * k + j] = -FLT_MAX;
+        out_ids[row * k + j] = -1;
+      }
+    } else if (cur == best) {  // keys are unique (shards hold disjoint ids): exactly one lane wins, emits its entry, advances
+      out_scores[row * k + j] = __uint_as_float(static_cast<uint32_t>(cur_w >> 32));  // the original bits (-0.0 stays -0.0)
+      out_ids[row * k + j] = static_cast<int64_t>(static_cast<uint32_t>(cur_w));
+      ++head;
+      cur_w = nxt_w;
+      cur = key_of(cur_w);
+      nxt_w = head + 1 < k ? src[head + 1] : ~0ull;
+    }
   }
 }
 
@@ -1098,8 +1197,9 @@ static int topk_filter(const vdk_topk_plan* plan, const void* qh, const float* q
   }
   static bool sel_attr = false;
   if (!sel_attr) {
-    VDK_CUDA_OK(cudaFuncSetAttribute(select_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSelStage * sizeof(uint2)));
-    VDK_CUDA_OK(cudaFuncSetAttribute(select_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSelStage * sizeof(uint2)));
+    VDK_CUDA_OK(cudaFuncSetAttribute(select_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSelStage * sizeof(uint2)));
+    VDK_CUDA_OK(cudaFuncSetAttribute(select_kernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSelStage * sizeof(uint2)));
+    VDK_CUDA_OK(cudaFuncSetAttribute(select_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSelStage * sizeof(uint2)));
     sel_attr = true;
   }
   int cur = 0;  // carry buffer holding the current survivors
@@ -1144,16 +1244,24 @@ static int topk_filter(const vdk_topk_plan* plan, const void* qh, const float* q
       sp.ext_lb = ext_lb;
       // staging area: the dense first range needs room for every score of the range, a sparse range for a few hundred
       sp.stage_cap = dense ? kSelStage : kSelStage / 2;
+      static const int prefilter = [] {  // VDK_SELECT_PREFILTER=0: the plain staged select on dense ranges too
+        const char* e = getenv("VDK_SELECT_PREFILTER");
+        return e ? atoi(e) : 1;
+      }();
+      sp.prefilter = prefilter;
+      const bool pre = prefilter && dense && k <= kSelThreads;  // what is left after the prefilter needs no aggregation
       // warp-aggregated histogram atomics pay on the dense range (thousands of keys whose first digit collides); VDK_SELECT_AGG
       // = 0 never, 1 dense ranges only (default), 2 always
       static const int agg_mode = [] {
         const char* e = getenv("VDK_SELECT_AGG");
         return e ? atoi(e) : 1;
       }();
-      if (agg_mode == 2 || (agg_mode == 1 && dense))
-        select_kernel<true><<<static_cast<unsigned>(nq), kSelThreads, sp.stage_cap * sizeof(uint2), s>>>(sp);
+      if (pre)
+        select_kernel<false, true><<<static_cast<unsigned>(nq), kSelThreads, sp.stage_cap * sizeof(uint2), s>>>(sp);
+      else if (agg_mode == 2 || (agg_mode == 1 && dense))
+        select_kernel<true, false><<<static_cast<unsigned>(nq), kSelThreads, sp.stage_cap * sizeof(uint2), s>>>(sp);
       else
-        select_kernel<false><<<static_cast<unsigned>(nq), kSelThreads, sp.stage_cap * sizeof(uint2), s>>>(sp);
+        select_kernel<false, false><<<static_cast<unsigned>(nq), kSelThreads, sp.stage_cap * sizeof(uint2), s>>>(sp);
       VDK_CUDA_OK(cudaGetLastError());
       cur ^= 1;
       lo = hi;
@@ -1162,18 +1270,137 @@ static int topk_filter(const vdk_topk_plan* plan, const void* qh, const float* q
   return VDK_OK;
 }
 
-// carry buffer that holds the survivors after topk_filter ran this plan
-static int final_carry(const vdk_topk_plan* plan) {
+// carry buffer that holds the survivors after the first `stages_done` stages of this plan ran
+static int carry_after(const vdk_topk_plan* plan, int stages_done) {
   int cur = 0;
   int64_t lo = 0;
   if (plan->n_gallery > 0)
-    for (int st = 0; st < plan->n_stages; ++st) {
+    for (int st = 0; st < plan->n_stages && st < stages_done; ++st) {
       const int64_t hi = plan->stage_end[st];
       if (hi == lo) continue;
       cur ^= 1;
       lo = hi;
     }
   return cur;
+}
+static int final_carry(const vdk_topk_plan* plan) { return carry_after(plan, plan->n_stages); }
+
+// ------------------------------------------------------------------------------------------------
+// Sharded search: what the shards tell each other between gallery ranges.
+//
+// The k-th bound of ONE shard says little about the k-th score of the union when every shard holds a share of a query's
+// neighbours (max over W shards of "100th of my 4096 rows" is still the 100th-of-4096 quantile, not the 100th of 32768).  So a
+// shard reports a RANK SKETCH: lower bounds of its canonical scores at ranks k, k/2, k/4, ... (>= r_i of its rows score at least
+// sketch[i]).  Shards hold disjoint rows, so for any threshold t the union holds at least sum_s max{r_i : sketch_s[i] >= t}
+// rows scoring >= t; the largest reported t whose sum reaches k is a lower bound of the GLOBAL k-th canonical score.  With
+// neighbours spread evenly it is the ceil(k/W)-th score of the weakest shard (~ the k-th of the union); with all neighbours in
+// one shard it is that shard's k-th (the old max).
+// ------------------------------------------------------------------------------------------------
+constexpr int kSketchMaxRanks = 8;
+constexpr int kSketchCap = 512;  // survivors per query the rank count handles; longer lists (massive ties) report rank k only
+
+struct SketchParams {
+  int n_query, k, n_ranks;
+  int ranks[kSketchMaxRanks];
+  const uint2* carry;
+  const unsigned* carry_cnt;
+  int carry_cap;
+  const float* eps;
+  const float* kth_lb;
+  float* out;  // [n_query][n_ranks]
+};
+
+__global__ void __launch_bounds__(128) rank_sketch_kernel(const SketchParams p) {
+  __shared__ float s_val[4][kSketchCap];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int row = blockIdx.x * 4 + warp;
+  if (row >= p.n_query) return;  // warps are independent from here on (no CTA-wide barrier below)
+  const unsigned m = min(p.carry_cnt[row], static_cast<unsigned>(p.carry_cap));
+  float res[kSketchMaxRanks];
+#pragma unroll
+  for (int r = 0; r < kSketchMaxRanks; ++r) res[r] = -INFINITY;
+  if (m <= static_cast<unsigned>(kSketchCap)) {
+    const uint2* e = p.carry + static_cast<size_t>(row) * p.carry_cap;
+    float* v = s_val[warp];
+    for (unsigned i = lane; i < m; i += 32) v[i] = __uint_as_float(e[i].x);
+    __syncwarp();
+    // the survivors are every scanned row at or above the admission bound: the r-th largest of them is the r-th largest of
+    // the shard so far.  Rank of a value by counting (m ~ k + a few): v is the r-th largest iff #{x > v} < r <= #{x >= v}
+    // four values per lane share one sweep over the list (one shared-memory read per four rank updates)
+    for (unsigned base = 0; base < m; base += 128) {
+      float x[4];
+      int gt[4] = {0, 0, 0, 0}, ge[4] = {0, 0, 0, 0};
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        const unsigned i = base + q * 32 + lane;
+        x[q] = i < m ? v[i] : INFINITY;  // +inf: never matches a rank (#{y >= inf} = 0)
+      }
+      for (unsigned j = 0; j < m; ++j) {
+        const float y = v[j];
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          gt[q] += y > x[q] ? 1 : 0;
+          ge[q] += y >= x[q] ? 1 : 0;
+        }
+      }
+#pragma unroll
+      for (int q = 0; q < 4; ++q)
+#pragma unroll
+        for (int r = 0; r < kSketchMaxRanks; ++r)
+          if (r < p.n_ranks && gt[q] < p.ranks[r] && p.ranks[r] <= ge[q]) res[r] = x[q];
+    }
+  }
+#pragma unroll
+  for (int r = 0; r < kSketchMaxRanks; ++r) {
+#pragma unroll
+    for (int off = 16; off > 0; off >>= 1) res[r] = fmaxf(res[r], __shfl_xor_sync(0xffffffffu, res[r], off));
+  }
+  if (lane == 0) {
+    const float eps = p.eps[row];
+#pragma unroll
+    for (int r = 0; r < kSketchMaxRanks; ++r)
+      if (r < p.n_ranks)
+        // rank k: the select's own bound (it also carries the global bound this shard already knew, which is as good a claim:
+        // a threshold below a valid global bound is a valid global bound)
+        p.out[static_cast<size_t>(row) * p.n_ranks + r] = p.ranks[r] == p.k ? p.kth_lb[row] : res[r] - eps;
+  }
+}
+
+struct BoundParams {
+  const float* sketches;  // [n_shards][n_query][n_ranks]
+  int n_shards, n_query, n_ranks, k;
+  int ranks[kSketchMaxRanks];
+  float* bound;  // [n_query] in/out: max(bound, best threshold the sketches prove)
+};
+
+__global__ void __launch_bounds__(128) sketch_bound_kernel(const BoundParams p) {
+  extern __shared__ float s_sk[];  // [4][n_shards * n_ranks]
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int row = blockIdx.x * 4 + warp;
+  if (row >= p.n_query) return;
+  const int nc = p.n_shards * p.n_ranks;
+  float* v = s_sk + warp * nc;
+  for (int c = lane; c < nc; c += 32) {
+    const int sh = c / p.n_ranks, i = c - sh * p.n_ranks;
+    v[c] = p.sketches[(static_cast<size_t>(sh) * p.n_query + row) * p.n_ranks + i];
+  }
+  __syncwarp();
+  float best = -INFINITY;
+  for (int c = lane; c < nc; c += 32) {
+    const float t = v[c];
+    if (!(t > -INFINITY)) continue;
+    int cnt = 0;
+    for (int sh = 0; sh < p.n_shards; ++sh) {
+      int cs = 0;
+      for (int i = 0; i < p.n_ranks; ++i)
+        if (v[sh * p.n_ranks + i] >= t) cs = max(cs, p.ranks[i]);
+      cnt += cs;
+    }
+    if (cnt >= p.k) best = fmaxf(best, t);
+  }
+#pragma unroll
+  for (int off = 16; off > 0; off >>= 1) best = fmaxf(best, __shfl_xor_sync(0xffffffffu, best, off));
+  if (lane == 0) p.bound[row] = fmaxf(p.bound[row], best);
 }
 
 static int topk_rerank(const vdk_topk_plan* plan, const float* q32, const float* g32, int64_t id_offset, const float* kth_lb_global,
@@ -1258,6 +1485,57 @@ extern "C" int vdk_ip_topk_rerank(const vdk_topk_plan* plan, const float* q32, c
                      reinterpret_cast<cudaStream_t>(stream));
 }
 
+extern "C" int vdk_ip_topk_rank_sketch(const vdk_topk_plan* plan, int stages_done, const int32_t* ranks, int n_ranks,
+                                       float* sketch_out, void* workspace, size_t workspace_bytes, void* stream) {
+  int rc = check_plan(plan);
+  if (rc != VDK_OK) return rc;
+  VDK_REQUIRE(ranks && sketch_out, "vdk_ip_topk_rank_sketch: null operand");
+  VDK_REQUIRE(n_ranks >= 1 && n_ranks <= kSketchMaxRanks, "vdk_ip_topk_rank_sketch: n_ranks must be in [1,%d]", kSketchMaxRanks);
+  VDK_REQUIRE(stages_done >= 1, "vdk_ip_topk_rank_sketch: no stage has run");
+  const int64_t nq = plan->n_query;
+  if (nq == 0) return VDK_OK;
+  VDK_REQUIRE(workspace && workspace_bytes >= vdk_topk_workspace_bytes(plan), "vdk_ip_topk_rank_sketch: workspace too small");
+  const TopkWorkspace w = carve_workspace(workspace, nq, plan->cand_capacity, plan->carry_capacity);
+  SketchParams sp{};
+  sp.n_query = static_cast<int>(nq);
+  sp.k = plan->k;
+  sp.n_ranks = n_ranks;
+  for (int i = 0; i < n_ranks; ++i) {
+    VDK_REQUIRE(ranks[i] >= 1 && ranks[i] <= plan->k, "vdk_ip_topk_rank_sketch: rank %d outside [1,k]", ranks[i]);
+    sp.ranks[i] = ranks[i];
+  }
+  sp.carry = w.carry[carry_after(plan, stages_done)];
+  sp.carry_cnt = w.carry_cnt;
+  sp.carry_cap = plan->carry_capacity;
+  sp.eps = w.eps;
+  sp.kth_lb = w.kth_lb;
+  sp.out = sketch_out;
+  cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
+  rank_sketch_kernel<<<static_cast<unsigned>((nq + 3) / 4), 128, 0, s>>>(sp);
+  VDK_CUDA_OK(cudaGetLastError());
+  return VDK_OK;
+}
+
+extern "C" int vdk_topk_bound_from_sketches(const float* sketches, int n_shards, int64_t n_query, const int32_t* ranks,
+                                            int n_ranks, int k, float* bound_inout, void* stream) {
+  VDK_REQUIRE(sketches && ranks && bound_inout, "vdk_topk_bound_from_sketches: null operand");
+  VDK_REQUIRE(n_ranks >= 1 && n_ranks <= kSketchMaxRanks, "vdk_topk_bound_from_sketches: n_ranks must be in [1,%d]", kSketchMaxRanks);
+  VDK_REQUIRE(n_shards >= 1 && n_shards <= 256 && k >= 1 && n_query >= 0, "vdk_topk_bound_from_sketches: n_shards must be in [1,256]");
+  if (n_query == 0) return VDK_OK;
+  BoundParams bp{};
+  bp.sketches = sketches;
+  bp.n_shards = n_shards;
+  bp.n_query = static_cast<int>(n_query);
+  bp.n_ranks = n_ranks;
+  bp.k = k;
+  for (int i = 0; i < n_ranks; ++i) bp.ranks[i] = ranks[i];
+  bp.bound = bound_inout;
+  cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
+  sketch_bound_kernel<<<static_cast<unsigned>((n_query + 3) / 4), 128, 4 * n_shards * n_ranks * sizeof(float), s>>>(bp);
+  VDK_CUDA_OK(cudaGetLastError());
+  return VDK_OK;
+}
+
 extern "C" int vdk_topk_merge(const float* scores, const int64_t* ids, int n_lists, int64_t n_query, int k,
                               float* out_scores, int64_t* out_ids, void* stream) {
   VDK_REQUIRE(scores && ids && out_scores && out_ids, "vdk_topk_merge: null operand");
@@ -1284,9 +1562,20 @@ extern "C" int vdk_topk_merge_packed(const void* packed, int n_lists, int64_t n_
   VDK_REQUIRE(packed && out_scores && out_ids, "vdk_topk_merge_packed: null operand");
   VDK_REQUIRE(n_lists >= 1 && n_lists <= 32 && k >= 1 && n_query >= 0, "vdk_topk_merge_packed: n_lists must be in [1,32]");
   if (n_query == 0) return VDK_OK;
-  const int64_t blocks = (n_query + 7) / 8;
-  topk_merge_kernel<true><<<static_cast<unsigned>(blocks), 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
-      nullptr, nullptr, reinterpret_cast<const unsigned long long*>(packed), n_lists, n_query, k, out_scores, out_ids);
+  static const int fast = [] {  // VDK_MERGE_FAST=0: the general tournament kernel
+    const char* e = getenv("VDK_MERGE_FAST");
+    return e ? atoi(e) : 1;
+  }();
+  if (fast) {
+    const int group = pow2_ceil(n_lists);
+    const int64_t warps = (n_query + 32 / group - 1) / (32 / group);
+    topk_merge_packed_kernel<<<static_cast<unsigned>((warps + 7) / 8), 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
+        reinterpret_cast<const unsigned long long*>(packed), n_lists, group, n_query, k, out_scores, out_ids);
+  } else {
+    const int64_t blocks = (n_query + 7) / 8;
+    topk_merge_kernel<true><<<static_cast<unsigned>(blocks), 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
+        nullptr, nullptr, reinterpret_cast<const unsigned long long*>(packed), n_lists, n_query, k, out_scores, out_ids);
+  }
   VDK_CUDA_OK(cudaGetLastError());
   return VDK_OK;
 }

@@ -14,6 +14,7 @@ candidates; every returned score is re-computed from the fp32 rows.
 from __future__ import annotations
 
 import ctypes as C
+import os
 from typing import Optional, Tuple
 
 import numpy as np
@@ -80,6 +81,7 @@ class FlatIPIndex:
         self._gmax = None
         self._ws = None
         self.last_status = None
+        self.last_plan = None
         self.stage_ends = None  # optional override of the gallery range schedule (tuning / tests)
         self.wide_path_rows = 0
         self.exhaustive_rows = 0
@@ -179,7 +181,18 @@ class FlatIPIndex:
                                                            kth_lb.data_ptr(), status.data_ptr(), self._ws.data_ptr(), self._ws.numel(),
                                                            _lib.stream_ptr())
                         _lib.check(rc, "vdk_ip_topk_filter_stages")
-                    exchange(kth_lb)
+                    done = min(st + 1, plan.n_stages)
+
+                    def sketch(ranks, done=done):
+                        sk = torch.full((nq, len(ranks)), float("-inf"), dtype=torch.float32, device=self.device)
+                        if ng > 0:  # an empty shard has nothing to report
+                            arr = (C.c_int32 * len(ranks))(*[int(r) for r in ranks])
+                            _lib.check(lib.vdk_ip_topk_rank_sketch(C.byref(plan), done, arr, len(ranks), sk.data_ptr(),
+                                                                   self._ws.data_ptr(), self._ws.numel(), _lib.stream_ptr()),
+                                       "vdk_ip_topk_rank_sketch")
+                        return sk
+
+                    exchange(kth_lb, sketch)
                 rc = lib.vdk_ip_topk_rerank(C.byref(plan), q32.data_ptr(), g32_ptr, self.id_offset + g_lo, kth_lb.data_ptr(),
                                             out_s.data_ptr(), out_i.data_ptr(), self._ws.data_ptr(), self._ws.numel(),
                                             _lib.stream_ptr())
@@ -189,9 +202,10 @@ class FlatIPIndex:
     def search_device(self, q: torch.Tensor, k: int, resolve_overflow: bool = False, exchange=None):
         """Device tensors in/out.  With resolve_overflow=True the call synchronises, and queries whose candidate
         lists overflowed (massive near-ties, adversarially ordered galleries) are recomputed on the wide path.
-        `exchange` (sharded search only): callable that replaces a device float32 [n] tensor by its element-wise maximum over
-        all shards, in place; the returned lists are then this shard's contribution to the GLOBAL top-k (entries that cannot
-        reach it are dropped before the canonical re-rank) and must be merged with the other shards' lists."""
+        `exchange` (sharded search only, see _Exchange): called after every gallery range as exchange(bound, sketch) — it raises the
+        device float32 [n] `bound` (lower bound of the GLOBAL k-th canonical score) in place from what all shards publish;
+        sketch(ranks) returns this shard's rank sketch.  The returned lists are then this shard's contribution to the GLOBAL
+        top-k (entries that cannot reach it are dropped before the canonical re-rank) and must be merged with the other shards'."""
         _lib.load()
         _lib.require_device()
         self._finalize()
@@ -208,7 +222,7 @@ class FlatIPIndex:
         qp = PreparedRows(q, self.normalize)
         ng = self._rows.n if self._rows is not None else 0
         out_s, out_i, status, plan = self._run_topk(qp, None, 0, ng, k, dense_all=False, exchange=exchange)
-        self.last_status = status
+        self.last_status, self.last_plan = status, plan
         if resolve_overflow and int(status[0].item()) > 0:
             self._wide_path(qp, out_s, out_i, plan, k)
         return out_s, out_i
@@ -350,56 +364,98 @@ def merge_topk_packed(packed: torch.Tensor, k: int):
     return out_s, out_i
 
 
-def sharded_flat_search(index: "FlatIPIndex", q_local: torch.Tensor, q_sizes, k: int, defer_check: bool = False):
+def bound_from_sketches(sketches: torch.Tensor, ranks, k: int, bound: torch.Tensor) -> None:
+    """sketches [n_shards, n_query, n_ranks] (every shard's vdk_ip_topk_rank_sketch) -> bound[n_query] = max(bound, the largest
+    reported score the union provably holds k rows above): a lower bound of the global k-th canonical score, in place."""
+    lib = _lib.load()
+    n_shards, nq, nr = sketches.shape
+    assert nr == len(ranks) and sketches.dtype == torch.float32 and bound.dtype == torch.float32
+    sketches = sketches.contiguous()
+    arr = (C.c_int32 * nr)(*[int(r) for r in ranks])
+    with torch.cuda.device(bound.device):
+        _lib.check(lib.vdk_topk_bound_from_sketches(sketches.data_ptr(), n_shards, nq, arr, nr, int(k), bound.data_ptr(),
+                                                    _lib.stream_ptr()), "vdk_topk_bound_from_sketches")
+
+
+class _Exchange:
+    """What the shards of a sharded search tell each other after every gallery range, and the range schedule they all follow.
+
+    sketch mode (default): every shard publishes lower bounds of its canonical scores at ranks k, k/2, k/4, ... (one all-gather
+    of 4 * n_ranks bytes per query) and each shard derives the best provable lower bound of the GLOBAL k-th score
+    (bound_from_sketches): ~ the k-th score of the union of all prefixes when a query's neighbours are spread over the shards,
+    the best shard's k-th when they sit in one.  VDK_SHARD_SKETCH=0: element-wise max of the shards' k-th bounds only."""
+
+    def __init__(self, schedule, comm, k: int):
+        self.schedule, self.comm, self.k = schedule, comm, int(k)
+        ranks = [self.k]
+        if os.environ.get("VDK_SHARD_SKETCH", "1") != "0":
+            r, w = self.k, 1
+            while w < comm.world and len(ranks) < 8 and r > 1:
+                r, w = -(-r // 2), w * 2
+                ranks.append(r)
+        self.ranks = ranks
+
+    def __call__(self, bound: torch.Tensor, sketch) -> None:
+        """bound [n_query] fp32, in place.  sketch(ranks) -> this shard's [n_query, len(ranks)] rank sketch."""
+        if len(self.ranks) == 1:
+            self.comm.all_reduce_max_(bound)
+            return
+        bound_from_sketches(self.comm.all_gather(sketch(self.ranks)), self.ranks, self.k, bound)
+
+
+def shard_schedule(ng_max: int, world: int, k: int):
+    """Gallery range ends every shard of a `world`-way search follows (computed from the LARGEST shard).  After a range every
+    shard knows (from the rank sketches) about the k-th score of the union of `world` prefixes, so the next range may grow `world`
+    times faster at the same expected admissions per query: 2 ranges per shard on 8 GPUs instead of 3.
+    Measured on 2 GPUs (profiles/r02_retrieval.md): shrinking the dense first range to 8192 / world rows and growing by
+    1 + 15 * world costs more in admissions than the smaller dense write saves (6.90 ms against 6.21 ms): so the single-GPU first
+    range, growth 1 + 7 * world.  VDK_SHARD_FIRST / VDK_SHARD_GROWTH override (tuning)."""
+    first = int(os.environ.get("VDK_SHARD_FIRST", min(max(4096, (4 * k + 255) // 256 * 256), 16384)))
+    first = min(first, (max(ng_max, 1) + 255) // 256 * 256)
+    growth = int(os.environ.get("VDK_SHARD_GROWTH", 1 + 7 * world))
+    schedule, e = [], first
+    while e < ng_max and len(schedule) < 7:
+        schedule.append(e)
+        e = (e * growth + 255) // 256 * 256
+        if e >= 0.75 * ng_max:  # no sliver of a last range
+            break
+    return schedule
+
+
+def sharded_flat_search(index: "FlatIPIndex", q_local: torch.Tensor, q_sizes, k: int, defer_check: bool = False, comm=None):
     """The multi-GPU search call (BASELINE config 4): every rank holds one row shard of the gallery in `index` (built with its
     `id_offset`) and `q_sizes[rank]` query embeddings; returns the GLOBAL top-k of ALL queries on every rank, bit-identical
     to the unsharded search (scores are canonical, the merge uses the same (score desc, id asc) rule).
 
-    Three exchanges: all-gather of the query embeddings, a max all-reduce of one float per query (each shard's lower bound of
-    its k-th canonical score: shards then re-rank only the candidates that can reach the global top-k), and ONE all-gather of
-    the packed per-shard lists.  Overflowed queries are resolved locally before the last exchange, so the merge never sees an
-    incomplete list (one host synchronisation per search); defer_check=True skips that synchronisation — the caller then MUST
-    call `index.check_status(all_ranks=True)` before trusting the result (it raises if any shard overflowed)."""
+    Exchanges: all-gather of the query embeddings; after EVERY gallery range an all-gather of the shards' rank sketches (a few
+    floats per query, see _Exchange) from which each shard derives a lower bound of the global k-th score — it filters the next
+    range, and finally re-ranks, only what can still reach the global top-k; ONE all-gather of the packed per-shard lists.
+    Overflowed queries are resolved locally before the last exchange, so the merge never sees an incomplete list (one host
+    synchronisation per search); defer_check=True skips that synchronisation — the caller then MUST call
+    `index.check_status(all_ranks=True)` before trusting the result (it raises if any shard overflowed).
+
+    comm: the shards' collectives (default sharding.DistComm = torch.distributed / NCCL).  With a sharding.LocalShardGroup comm
+    (W shards on one device, one thread each: the test / measurement harness) q_local must already hold ALL queries."""
     from . import sharding
 
-    class _Exchange:
-        """In-place element-wise max over the shards + the gallery range schedule every shard follows."""
-
-        def __init__(self, schedule):
-            self.schedule = schedule
-
-        def __call__(self, t: torch.Tensor) -> None:
-            sharding.all_reduce_max_(t)
-
-    world = sharding.world_size()
+    dist_comm = comm is None or isinstance(comm, sharding.DistComm)
+    comm = comm or sharding.DistComm()
+    world = comm.world
     schedule = None
     if world > 1:
-        # one schedule for all shards, from the LARGEST shard (cached on the index: one tiny all-reduce per index build).  After a
-        # range every shard knows the k-th bound of the union of `world` prefixes, so the next range may grow `world` times
-        # faster at the same expected admissions per query: 2 ranges per shard on 8 GPUs instead of 3
+        # one schedule for all shards, from the LARGEST shard (cached on the index: one tiny all-reduce per index build)
         index._finalize()
         if getattr(index, "_shard_rows_max", None) is None or index._shard_rows_max[0] != index.ntotal:
             t = torch.tensor([float(index.ntotal)], device=index.device)
-            sharding.all_reduce_max_(t)
+            comm.all_reduce_max_(t)
             index._shard_rows_max = (index.ntotal, int(t.item()))
-        ng_max = index._shard_rows_max[1]
-        # Measured on 2 GPUs (profiles/r02_retrieval.md): shrinking the dense first range to 8192 / world rows and growing by
-        # 1 + 15 * world costs more in admissions (the epilogue's slow path, ~0.05 us per 1000 admitted candidates) than the
-        # smaller dense write saves: 6.90 ms against 6.21 ms.  So: the single-GPU first range, growth 1 + 7 * world.
-        import os  # tuning switches
-        first = int(os.environ.get("VDK_SHARD_FIRST", min(max(4096, (4 * k + 255) // 256 * 256), 16384)))
-        first = min(first, (max(ng_max, 1) + 255) // 256 * 256)
-        growth = int(os.environ.get("VDK_SHARD_GROWTH", 1 + 7 * world))
-        schedule, e = [], first
-        while e < ng_max and len(schedule) < 7:
-            schedule.append(e)
-            e = (e * growth + 255) // 256 * 256
-            if e >= 0.75 * ng_max:  # no sliver of a last range
-                break
-    ex = _Exchange(schedule)
-    return sharding.sharded_search(q_local, list(q_sizes),
-                                   lambda q, kk: index.search_device(q, kk, resolve_overflow=not defer_check, exchange=ex),
-                                   merge_topk, k, pack=pack_topk, merge_packed=merge_topk_packed)
+        schedule = shard_schedule(index._shard_rows_max[1], world, k)
+    ex = _Exchange(schedule, comm, k)
+    q_all = sharding.all_gather_rows(q_local, list(q_sizes)) if dist_comm else q_local
+    s, i = index.search_device(q_all, k, resolve_overflow=not defer_check, exchange=ex)
+    if world == 1:
+        return s, i
+    return merge_topk_packed(comm.all_gather(pack_topk(s, i)), k)
 
 
 def exact_pair_scores(q32: torch.Tensor, g32: torch.Tensor, qi: torch.Tensor, gi: torch.Tensor) -> torch.Tensor:

@@ -5,7 +5,12 @@ tests and in the single-GPU two-rank parity test).  The reference only replicate
 happens here: scoring, packing and merging are the CUDA kernels' job.
 
 Exchange 1: all-gather of the query embeddings every rank extracted.
-Exchange 2: ONE all-gather of the per-shard top-k lists, each entry packed into a 64-bit word (score bits << 32 | id).
+Between gallery ranges (visiondk_b200.retrieval._Exchange): all-gather of each shard's RANK SKETCH (lower bounds of its scores at
+ranks k, k/2, k/4, ...: 4 floats per query on 8 GPUs) from which every shard derives a lower bound of the global k-th score.
+Last exchange: ONE all-gather of the per-shard top-k lists, each entry packed into a 64-bit word (score bits << 32 | id).
+
+The collectives sit behind a small `comm` object: DistComm (torch.distributed; the product path) or LocalShardGroup (W shards on
+one device, one host thread each; the single-GPU harness of the W-shard protocol).
 """
 from __future__ import annotations
 
@@ -55,6 +60,83 @@ def all_reduce_max_(t: torch.Tensor) -> None:
         t.copy_(host)
     else:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
+
+
+class DistComm:
+    """The shards' collectives over torch.distributed (NCCL between GPUs): the product path."""
+
+    @property
+    def world(self) -> int:
+        return world_size()
+
+    @property
+    def rank(self) -> int:
+        return dist.get_rank() if _active() else 0
+
+    def all_gather(self, src: torch.Tensor) -> torch.Tensor:
+        """Equal-shaped `src` of every shard -> [world, *src.shape] on every shard."""
+        if not _active():
+            return src.unsqueeze(0)
+        out = torch.empty((dist.get_world_size(),) + tuple(src.shape), dtype=src.dtype, device=src.device)
+        _all_gather_into(out, src.contiguous())
+        return out
+
+    def all_reduce_max_(self, t: torch.Tensor) -> None:
+        all_reduce_max_(t)
+
+
+class LocalShardGroup:
+    """W shards living on ONE device, one host thread each: the same protocol with the collectives replaced by a barrier and a
+    `torch.stack` (all threads launch on the device's default stream, so stream order = launch order).  Test / measurement
+    harness only: it checks the W-shard protocol (and times a shard's share of the work) where a single GPU is available."""
+
+    def __init__(self, world: int):
+        import threading
+        self.world = world
+        self._slots = [None] * world
+        self._barrier = threading.Barrier(world)
+
+    def comm(self, rank: int) -> "LocalShardGroup._Comm":
+        return LocalShardGroup._Comm(self, rank)
+
+    def run(self, fn: Callable, device=None) -> list:
+        """fn(comm) on one thread per shard; returns the per-shard results in rank order (re-raises the first failure)."""
+        import threading
+        results, errors = [None] * self.world, []
+        self._barrier = threading.Barrier(self.world)  # a failed run leaves the old one broken
+
+        def work(rank: int) -> None:
+            try:
+                if device is not None:
+                    torch.cuda.set_device(device)
+                results[rank] = fn(self.comm(rank))
+            except BaseException as e:  # noqa: BLE001 — reported to the caller below
+                errors.append(e)
+                self._barrier.abort()  # release the shards waiting for this one
+
+        threads = [threading.Thread(target=work, args=(r,)) for r in range(self.world)]
+        for t in threads:
+            t.start()
+        for t in threads:
+            t.join()
+        if errors:
+            first = [e for e in errors if not isinstance(e, threading.BrokenBarrierError)] or errors
+            raise first[0]
+        return results
+
+    class _Comm:
+        def __init__(self, group: "LocalShardGroup", rank: int):
+            self.g, self.rank, self.world = group, rank, group.world
+
+        def all_gather(self, src: torch.Tensor) -> torch.Tensor:
+            self.g._slots[self.rank] = src
+            self.g._barrier.wait()
+            out = torch.stack(list(self.g._slots))
+            self.g._barrier.wait()  # nobody overwrites a slot before every thread has read it
+            return out
+
+        def all_reduce_max_(self, t: torch.Tensor) -> None:
+            t.copy_(self.all_gather(t).amax(dim=0))
 
 
 def all_gather_rows(local: torch.Tensor, sizes: List[int]) -> torch.Tensor:
