@@ -363,7 +363,7 @@ constexpr int kSelStage = 4096;
 
 // kPre: the register prefilter of dense ranges (its own instantiation: the 64 registers of its entry array would otherwise cut
 // the occupancy of every sparse-range launch — measured: 120 -> 225 us per sparse select).
-template <bool kAgg, bool kPre>
+template <bool kAgg, int kPre>
 __global__ void __launch_bounds__(kSelThreads) select_kernel(const SelectParams p) {
   extern __shared__ uint2 s_stage[];  // [p.stage_cap]
   __shared__ unsigned hist[256];
@@ -412,8 +412,52 @@ __global__ void __launch_bounds__(kSelThreads) select_kernel(const SelectParams 
   // entries t, t + 128, ...; >= k threads hold a maximum >= F (the k-th largest of the 128 maxima), so the
   // k-th largest score of the row is >= F and only entries >= F - 2 eps can survive the select.  They (a few hundred) are
   // compacted into shared memory and the radix passes run on them.
-  const bool pre = kPre && p.dense_n > 0 && staged && n >= 1024u && p.k <= kSelThreads;  // CTA-uniform
-  if constexpr (kPre) {
+  const bool pre = kPre != 0 && p.dense_n > 0 && staged && n >= 1024u && p.k <= kSelThreads;  // CTA-uniform
+  if constexpr (kPre == 2) {
+    // register form: every entry is read ONCE and kept (64 registers) between the maximum and the compaction
+    if (pre) {
+      constexpr int kPer = kSelStage / kSelThreads;
+      uint2 ent[kPer];
+      const uint2* c0 = list_ptr_g(0);
+      const uint2* d0 = list_ptr_g(1);
+      const unsigned cnt0 = s_cnt[0];
+      float mx = -INFINITY;
+#pragma unroll
+      for (int j = 0; j < kPer; ++j) {
+        const unsigned i = static_cast<unsigned>(j * kSelThreads + tid);
+        ent[j] = make_uint2(0xff800000u, 0u);  // -inf
+        if (i < n) ent[j] = i < cnt0 ? c0[i] : d0[i - cnt0];
+        mx = fmaxf(mx, __uint_as_float(ent[j].x));
+      }
+      float* s_mx = reinterpret_cast<float*>(hist);  // re-zeroed by every radix pass
+      s_mx[tid] = mx;
+      __syncthreads();
+      int gt = 0, ge = 0;
+      for (int j = 0; j < kSelThreads; ++j) {
+        const float y = s_mx[j];
+        gt += y > mx ? 1 : 0;
+        ge += y >= mx ? 1 : 0;
+      }
+      if (gt < p.k && p.k <= ge) s_floor = mx;
+      __syncthreads();
+      const float keep_from = s_floor - 2.0f * p.eps[row];
+#pragma unroll
+      for (int j = 0; j < kPer; ++j) {
+        const bool k_ = static_cast<unsigned>(j * kSelThreads + tid) < n && __uint_as_float(ent[j].x) >= keep_from;
+        const unsigned m = __ballot_sync(0xffffffffu, k_);
+        if (m != 0u) {  // warp-uniform
+          unsigned base_pos = 0;
+          if (lane == 0) base_pos = atomicAdd(&s_n2, static_cast<unsigned>(__popc(m)));
+          base_pos = __shfl_sync(0xffffffffu, base_pos, 0);
+          if (k_) s_stage[base_pos + __popc(m & ((1u << lane) - 1u))] = ent[j];
+        }
+      }
+      __syncthreads();
+      if (tid == 0) s_cnt[0] = s_n2;  // <= n <= stage_cap
+      n_lists = 1;
+      __syncthreads();
+    }
+  } else if constexpr (kPre == 1) {
    if (pre) {
     // two sweeps over the row's entries (32 KB: the second one hits L2), nothing held in registers in between
     const uint2* c0 = list_ptr_g(0);
@@ -1197,9 +1241,10 @@ static int topk_filter(const vdk_topk_plan* plan, const void* qh, const float* q
   }
   static bool sel_attr = false;
   if (!sel_attr) {
-    VDK_CUDA_OK(cudaFuncSetAttribute(select_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSelStage * sizeof(uint2)));
-    VDK_CUDA_OK(cudaFuncSetAttribute(select_kernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSelStage * sizeof(uint2)));
-    VDK_CUDA_OK(cudaFuncSetAttribute(select_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSelStage * sizeof(uint2)));
+    VDK_CUDA_OK(cudaFuncSetAttribute(select_kernel<true, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSelStage * sizeof(uint2)));
+    VDK_CUDA_OK(cudaFuncSetAttribute(select_kernel<false, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSelStage * sizeof(uint2)));
+    VDK_CUDA_OK(cudaFuncSetAttribute(select_kernel<false, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSelStage * sizeof(uint2)));
+    VDK_CUDA_OK(cudaFuncSetAttribute(select_kernel<false, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSelStage * sizeof(uint2)));
     sel_attr = true;
   }
   int cur = 0;  // carry buffer holding the current survivors
@@ -1244,7 +1289,7 @@ static int topk_filter(const vdk_topk_plan* plan, const void* qh, const float* q
       sp.ext_lb = ext_lb;
       // staging area: the dense first range needs room for every score of the range, a sparse range for a few hundred
       sp.stage_cap = dense ? kSelStage : kSelStage / 2;
-      static const int prefilter = [] {  // VDK_SELECT_PREFILTER=0: the plain staged select on dense ranges too
+      static const int prefilter = [] {  // VDK_SELECT_PREFILTER: 0 plain staged select on dense ranges too, 1 two sweeps, 2 registers
         const char* e = getenv("VDK_SELECT_PREFILTER");
         return e ? atoi(e) : 1;
       }();
@@ -1256,12 +1301,14 @@ static int topk_filter(const vdk_topk_plan* plan, const void* qh, const float* q
         const char* e = getenv("VDK_SELECT_AGG");
         return e ? atoi(e) : 1;
       }();
-      if (pre)
-        select_kernel<false, true><<<static_cast<unsigned>(nq), kSelThreads, sp.stage_cap * sizeof(uint2), s>>>(sp);
+      if (pre && prefilter == 2)
+        select_kernel<false, 2><<<static_cast<unsigned>(nq), kSelThreads, sp.stage_cap * sizeof(uint2), s>>>(sp);
+      else if (pre)
+        select_kernel<false, 1><<<static_cast<unsigned>(nq), kSelThreads, sp.stage_cap * sizeof(uint2), s>>>(sp);
       else if (agg_mode == 2 || (agg_mode == 1 && dense))
-        select_kernel<true, false><<<static_cast<unsigned>(nq), kSelThreads, sp.stage_cap * sizeof(uint2), s>>>(sp);
+        select_kernel<true, 0><<<static_cast<unsigned>(nq), kSelThreads, sp.stage_cap * sizeof(uint2), s>>>(sp);
       else
-        select_kernel<false, false><<<static_cast<unsigned>(nq), kSelThreads, sp.stage_cap * sizeof(uint2), s>>>(sp);
+        select_kernel<false, 0><<<static_cast<unsigned>(nq), kSelThreads, sp.stage_cap * sizeof(uint2), s>>>(sp);
       VDK_CUDA_OK(cudaGetLastError());
       cur ^= 1;
       lo = hi;
