@@ -361,8 +361,9 @@ struct SelectParams {
 // then run out of shared memory.  Longer rows keep sweeping the lists in place.
 constexpr int kSelStage = 4096;
 
-// kPre: the register prefilter of dense ranges (its own instantiation: the 64 registers of its entry array would otherwise cut
-// the occupancy of every sparse-range launch — measured: 120 -> 225 us per sparse select).
+// kPre: the prefilter of dense ranges, 1 = two sweeps over the entries, 2 = entries held in registers (default).  Its own
+// instantiation: the 64 registers of the entry array would otherwise cut the occupancy of every sparse-range launch — measured:
+// 120 -> 225 us per sparse select.
 template <bool kAgg, int kPre>
 __global__ void __launch_bounds__(kSelThreads) select_kernel(const SelectParams p) {
   extern __shared__ uint2 s_stage[];  // [p.stage_cap]
@@ -1291,7 +1292,7 @@ static int topk_filter(const vdk_topk_plan* plan, const void* qh, const float* q
       sp.stage_cap = dense ? kSelStage : kSelStage / 2;
       static const int prefilter = [] {  // VDK_SELECT_PREFILTER: 0 plain staged select on dense ranges too, 1 two sweeps, 2 registers
         const char* e = getenv("VDK_SELECT_PREFILTER");
-        return e ? atoi(e) : 1;
+        return e ? atoi(e) : 2;  // measured on 8 emulated shards, same box: 2.11 ms per shard (registers) / 2.19 ms (two sweeps)
       }();
       sp.prefilter = prefilter;
       const bool pre = prefilter && dense && k <= kSelThreads;  // what is left after the prefilter needs no aggregation
