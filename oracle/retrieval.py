@@ -144,6 +144,48 @@ def merge_topk(scores_list, ids_list, k: int):
     return out_s, out_i
 
 
+def sketch_ranks(k: int, world: int):
+    """Ranks a shard of a `world`-way search reports: k, ceil(k/2), ceil(k/4), ... until `world` shards of the smallest rank
+    cover k (visiondk_b200.retrieval._Exchange; no counterpart in the reference, which replicates the index)."""
+    ranks, r, w = [int(k)], int(k), 1
+    while w < world and len(ranks) < 8 and r > 1:
+        r, w = -(-r // 2), w * 2
+        ranks.append(r)
+    return ranks
+
+
+def rank_sketch(shard_scores: np.ndarray, ranks) -> np.ndarray:
+    """shard_scores [nq, n_rows] (this shard's scores, any order) -> [nq, len(ranks)]: the ranks[i]-th largest score of every
+    query (-inf where the shard holds fewer rows): what `vdk_ip_topk_rank_sketch` lower-bounds (by eps, the fp16 pass' error)."""
+    nq, n = shard_scores.shape
+    desc = -np.sort(-shard_scores.astype(np.float64), axis=1)
+    out = np.full((nq, len(ranks)), -np.inf, np.float32)
+    for j, r in enumerate(ranks):
+        if r <= n:
+            out[:, j] = desc[:, r - 1]
+    return out
+
+
+def bound_from_sketches(sketches: np.ndarray, ranks, k: int, bound: np.ndarray) -> np.ndarray:
+    """sketches [n_shards, nq, n_ranks] of shards holding DISJOINT rows -> max(bound, largest reported score t such that
+    sum over shards of max{ranks[i] : sketch[s, q, i] >= t} >= k): a lower bound of the global k-th score
+    (`vdk_topk_bound_from_sketches`).  Entries need not decrease with the rank index (a rank-k entry may carry an older global
+    bound), hence the max over i."""
+    out = np.array(bound, dtype=np.float32, copy=True)
+    n_shards, nq, nr = sketches.shape
+    for q in range(nq):
+        for t in sketches[:, q, :].ravel():
+            if not np.isfinite(t):
+                continue
+            cnt = 0
+            for s_ in range(n_shards):
+                ok = [ranks[i] for i in range(nr) if sketches[s_, q, i] >= t]
+                cnt += max(ok) if ok else 0
+            if cnt >= k:
+                out[q] = max(out[q], t)
+    return out
+
+
 def synthetic_gallery(n_ids: int, per_id: int, dim: int = 512, seed: int = 2, noise: float = 0.5):
     """SURVEY.md §8(d) synthetic CBIR data: identity centres N(0,I) x members = centre + noise*N(0,I),
     L2-normalised float32; one query per identity built the same way.  Returns (gallery, queries, labels)."""

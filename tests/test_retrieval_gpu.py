@@ -285,22 +285,6 @@ def test_l2_variant_of_the_cosine_index(lib):
 
 
 
-def _np_bound_from_sketches(sk, ranks, k, bound):
-    out = bound.copy()
-    n_shards, nq, nr = sk.shape
-    for q in range(nq):
-        for t in sk[:, q, :].ravel():
-            if not np.isfinite(t):
-                continue
-            cnt = 0
-            for s in range(n_shards):
-                ok = [ranks[i] for i in range(nr) if sk[s, q, i] >= t]
-                cnt += max(ok) if ok else 0
-            if cnt >= k:
-                out[q] = max(out[q], t)
-    return out
-
-
 def test_bound_from_sketches_matches_the_counting_argument(lib):
     from visiondk_b200.retrieval import bound_from_sketches
     rng = np.random.default_rng(3)
@@ -311,7 +295,7 @@ def test_bound_from_sketches_matches_the_counting_argument(lib):
         sk[0, :, 0] = np.maximum(sk[0, :, 0], 0.5)  # a rank-k entry that carries an older global bound (not monotone in the rank)
         bound = rng.standard_normal(nq).astype(np.float32)
         bound[::7] = -np.inf
-        want = _np_bound_from_sketches(sk, ranks, k, bound)
+        want = R.bound_from_sketches(sk, ranks, k, bound)
         got = torch.from_numpy(bound).cuda()
         bound_from_sketches(torch.from_numpy(sk).cuda(), ranks, k, got)
         assert np.array_equal(got.cpu().numpy().view(np.uint32), want.view(np.uint32)), (n_shards, ranks, k)
@@ -371,6 +355,7 @@ def test_sharded_protocol_on_local_shards(lib, monkeypatch, world, clustered, sk
         sh.check_status()
     if sketch == "1":
         ranks = _Exchange(None, group.comm(0), k).ranks
+        assert ranks == R.sketch_ranks(k, world)
         assert len(ranks) > 1 and len(gathered) >= 2  # one exchange per gallery range
         g_dev = torch.from_numpy(g).cuda()
         kth_true = ws[:, k - 1]  # the global k-th canonical score
