@@ -409,8 +409,8 @@ int vdk_ip_topk(const vdk_topk_plan* plan, const float* q32, const void* qh, con
  *   vdk_ip_topk_filter  scans this shard (thresholds, ranges, selects), leaves every query's candidates in `workspace` and
  *                       writes kth_lb_out[n_query]: a lower bound of the shard's k-th largest canonical score (-inf if the
  *                       shard holds fewer than k rows);
- *   -- the ranks take the element-wise MAX of kth_lb over all shards (one tiny all-reduce): a lower bound of the GLOBAL
- *      k-th canonical score --
+ *   -- the ranks turn what they publish into a lower bound T of the GLOBAL k-th canonical score: the element-wise max of
+ *      kth_lb, or better vdk_ip_topk_rank_sketch + vdk_topk_bound_from_sketches below --
  *   vdk_ip_topk_rerank  re-scores canonically only the candidates that can still reach the global top-k
  *                       (approx >= kth_lb_global - eps) and emits this shard's list, padded with (-FLT_MAX, -1).
  * The merged result (vdk_topk_merge*) is bit-identical to the unsharded search.  kth_lb_global == NULL re-ranks everything
@@ -419,10 +419,11 @@ int vdk_ip_topk_filter(const vdk_topk_plan* plan, const void* qh, const float* q
                        const float* g_norm_max, const float* g_err_max, float* kth_lb_out, int32_t* status, void* workspace,
                        size_t workspace_bytes, void* stream);
 /* The scan stage by stage, for shards that exchange their bounds BETWEEN gallery ranges: runs stages [stage_begin, stage_end) of
- * the plan (stage_begin == 0 initialises the workspace).  ext_lb (device fp32 [n_query], nullable): the element-wise max over all
- * shards of the kth_lb values published after the previous stage — it tightens this shard's admission threshold and carry list
- * (a candidate below ext_lb - eps cannot reach the global top-k), so that after every exchange each shard filters as if it
- * had scanned the union of all shards' prefixes.  kth_lb_out as in vdk_ip_topk_filter. */
+ * the plan (stage_begin == 0 initialises the workspace).  ext_lb (device fp32 [n_query], nullable): a lower bound of the GLOBAL
+ * k-th canonical score derived from what all shards published after the previous stage (vdk_topk_bound_from_sketches) — it
+ * tightens this shard's admission threshold and carry list (a candidate below ext_lb - eps cannot reach the global top-k), so
+ * that after every exchange each shard filters as if it had scanned the union of all shards' prefixes.  kth_lb_out as in
+ * vdk_ip_topk_filter, never below ext_lb. */
 int vdk_ip_topk_filter_stages(const vdk_topk_plan* plan, const void* qh, const float* q_norm, const float* q_err, const void* gh,
                               const float* g_norm_max, const float* g_err_max, int stage_begin, int stage_end, const float* ext_lb,
                               float* kth_lb_out, int32_t* status, void* workspace, size_t workspace_bytes, void* stream);

@@ -124,8 +124,9 @@ class FlatIPIndex:
     # ---- device-resident path ----------------------------------------------------------------------
     def _run_topk(self, qp: "PreparedRows", rows, g_lo: int, g_hi: int, k: int, dense_all: bool, exchange=None):
         """One vdk_ip_topk call: queries `rows` of qp (None = all) against gallery rows [g_lo, g_hi).  With `exchange` (the
-        sharded search) the call is split: vdk_ip_topk_filter -> exchange(kth_lb) (element-wise max over the ranks, in place)
-        -> vdk_ip_topk_rerank of the candidates that can still reach the global top-k."""
+        sharded search) the call is split: per gallery range vdk_ip_topk_filter_stages -> exchange(bound, sketch) (raises the
+        lower bound of the global k-th score from what all shards publish, in place), then vdk_ip_topk_rerank of the candidates
+        that can still reach the global top-k."""
         lib = _lib.load()
         g = self._rows
         q32, qh, qn, qe = qp.x32, qp.xh, qp.norm, qp.err
