@@ -4,7 +4,8 @@
 
 The reference package cannot be imported as a whole (timm / faiss / torchmetrics are not installed), so the
 torch-only files are loaded by path: models/faceX/head/{arcface,circleloss}.py, models/losses/loss.py,
-models/ema.py, engine/scheduler.py, engine/optimizer.py, and models/faceX/backbone/timm_wrapper.py (the neck) around a stub `timm`.  The committed .npz files are what the CPU tests
+models/ema.py, engine/scheduler.py, engine/optimizer.py, dataset/transforms.py (the eval-time input pipeline, built from the
+reference's own configs/faceX/cbir.yaml), and models/faceX/backbone/timm_wrapper.py (the neck) around a stub `timm`.  The committed .npz files are what the CPU tests
 hold oracle/ to; the GPU tests then hold the CUDA kernels to oracle/.
 """
 from __future__ import annotations
@@ -229,6 +230,45 @@ def neck():
     np.savez_compressed(os.path.join(OUT, "neck_ref.npz"), **out)
 
 
+def preprocess():
+    """The reference's OWN eval-time input pipeline: dataset/transforms.py is loaded by path and its `create_AugTransforms`
+    builds the val transform list of the reference's OWN configs/faceX/cbir.yaml (`data.val.augment`: resize_and_padding ->
+    to_tensor -> normalize, transforms.py:325-365, 466-477, 530-555) at the config's image size and at two smaller sizes.
+    Stored: the uint8 source images (seeded noise and smooth ramps, landscape / portrait / square / tiny / one-pixel-off
+    shapes) and the float32 tensors the reference pipeline returns for them."""
+    import yaml
+    from PIL import Image
+    ref = load("dataset/transforms.py", "ref_transforms")
+    with open(os.path.join(REF, "configs/faceX/cbir.yaml")) as f:
+        cfg = yaml.safe_load(f)
+    augment = cfg["data"]["val"]["augment"]
+    assert [list(a.keys())[0] for a in augment] == ["resize_and_padding", "to_tensor", "normalize"]
+    cfg_size = int(augment[0]["resize_and_padding"]["size"])
+    out = {"cfg_size": np.int32(cfg_size), "mean": np.array(augment[2]["normalize"]["mean"], np.float64),
+           "std": np.array(augment[2]["normalize"]["std"], np.float64)}
+    shapes = [(320, 240), (100, 300), (96, 96), (500, 37), (50, 60), (133, 200), (7, 5), (97, 96), (31, 97), (1, 1)]
+    rng = np.random.default_rng(2025)
+    n = 0
+    for size, use in ((cfg_size, shapes[:2]), (96, shapes), (64, shapes[3:7])):  # kept small: the fixture is committed
+        aug = [dict(a) for a in augment]
+        aug[0] = {"resize_and_padding": {"size": size, "training": False}}
+        pipeline = ref.create_AugTransforms(aug)
+        for (w, h) in use:
+            if n % 2 == 0:
+                img = rng.integers(0, 256, (h, w, 3), dtype=np.uint8)
+            else:  # smooth content: exercises the fixed-point rounding differently from noise
+                yy, xx = np.mgrid[0:h, 0:w]
+                img = np.stack([(xx * 255 // max(w - 1, 1)), (yy * 255 // max(h - 1, 1)), ((xx + yy) * 7 % 256)], axis=2).astype(np.uint8)
+            t = pipeline(Image.fromarray(img))
+            assert tuple(t.shape) == (3, size, size) and t.dtype == torch.float32
+            out[f"img{n}"] = img
+            out[f"size{n}"] = np.int32(size)
+            out[f"out{n}"] = t.numpy()
+            n += 1
+    out["count"] = np.int32(n)
+    np.savez_compressed(os.path.join(OUT, "preprocess_ref.npz"), **out)
+
+
 def ema_sgd_sched():
     ema_mod = load("models/ema.py", "ref_ema")
     sched = load("engine/scheduler.py", "ref_sched")
@@ -269,4 +309,5 @@ if __name__ == "__main__":
     face_verification()
     ema_sgd_sched()
     neck()
+    preprocess()
     print("golden vectors written to", OUT)

@@ -45,3 +45,17 @@ def test_whole_transform_matches_pil_and_torchvision(w, h, size):
     got = P.resize_pad_normalize(img, size, mean, std)
     assert got.shape == (3, size, size) and got.dtype == np.float32
     assert np.array_equal(got.view(np.uint32), ref.view(np.uint32))
+
+
+def test_oracle_matches_the_reference_pipeline_golden():
+    """tests/golden/preprocess_ref.npz was minted by executing the reference's OWN dataset/transforms.py
+    (`create_AugTransforms` on the val augment list of its configs/faceX/cbir.yaml, oracle/make_golden.py::preprocess):
+    the oracle must reproduce every stored tensor bit for bit."""
+    import os
+    z = np.load(os.path.join(os.path.dirname(__file__), "golden", "preprocess_ref.npz"))
+    mean, std = tuple(float(v) for v in z["mean"]), tuple(float(v) for v in z["std"])
+    assert int(z["cfg_size"]) == 224 and int(z["count"]) >= 12
+    for n in range(int(z["count"])):
+        img, size, ref = z[f"img{n}"], int(z[f"size{n}"]), z[f"out{n}"]
+        got = P.resize_pad_normalize(img, size, mean, std)
+        assert got.shape == ref.shape and np.array_equal(got.view(np.uint32), ref.view(np.uint32)), (n, img.shape, size)
