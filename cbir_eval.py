@@ -13,6 +13,7 @@ any iterable of [B,3,S,S] float tensors (the reference's CBIRDatasets + DataLoad
 from __future__ import annotations
 
 import argparse
+import os
 import time
 
 import torch
@@ -62,6 +63,11 @@ def main(argv=None):
     root = str(data_cfg["root"])
     if is_synthetic(root):  # identity-structured synthetic images: the metrics below mean something
         data = SyntheticFaceData(root, size, bs, device)
+        gallery, queries = data.gallery_batches(opt.gallery), data.query_batches(opt.queries)
+        g_label, q_label = data.gallery_labels(opt.gallery), data.query_labels(opt.queries)
+    elif os.path.isdir(root):  # the reference's CBIRDatasets folder layout: decoded on host threads, transformed on the device
+        from engine.cbir.folder import CBIRFolderData
+        data = CBIRFolderData(root, data_cfg["val"]["augment"], bs, device, nw=data_cfg.get("nw", 8))
         gallery, queries = data.gallery_batches(opt.gallery), data.query_batches(opt.queries)
         g_label, q_label = data.gallery_labels(opt.gallery), data.query_labels(opt.queries)
     else:

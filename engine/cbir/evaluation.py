@@ -37,16 +37,24 @@ def compute_metrics(ids: torch.Tensor, scores: torch.Tensor, query_label: torch.
 
 def valuate(model, data_cfg: dict, device, logger=None, vis: bool = False, image_size: Optional[int] = None,
             gallery_limit: Optional[int] = None, query_limit: Optional[int] = None):
-    """engine/cbir/evaluation.py:226-291.  `data_cfg['root']` must be a synthetic:// URL (engine/synthetic.py) — reading image
-    folders is the dataset layer the hot-path scope leaves out; callers with their own loaders use index / search /
-    compute_metrics directly with their label tensors.  `gallery_limit` / `query_limit` bound the in-training eval."""
+    """engine/cbir/evaluation.py:226-291.  `data_cfg['root']`: a synthetic:// URL (engine/synthetic.py) or a local directory in
+    the reference's CBIRDatasets layout (<root>/query/<identity>/*, <root>/gallery/<identity>/*: engine/cbir/folder.py — images
+    decoded on host threads, the val transform list on the device).  HuggingFace dataset names (basedataset.py:516-573) need the
+    network and are not built.  `gallery_limit` / `query_limit` bound the in-training eval."""
+    import os
     device = torch.device(device)
     root = str(data_cfg["root"])
-    if not is_synthetic(root):
-        raise NotImplementedError("valuate: only synthetic:// data roots are built (dataset IO is outside the B200 hot-path scope); "
-                                  "use index() / search() / compute_metrics() with your own loaders and label tensors")
     size = image_size if image_size is not None else getattr(model, "image_size")
-    data = SyntheticFaceData(root, size, data_cfg["val"]["bs"], device)
+    if is_synthetic(root):
+        data = SyntheticFaceData(root, size, data_cfg["val"]["bs"], device)
+    elif os.path.isdir(root):
+        from engine.cbir.folder import CBIRFolderData
+        data = CBIRFolderData(root, data_cfg["val"]["augment"], data_cfg["val"]["bs"], device, nw=data_cfg.get("nw", 8))
+        if data.size != size:
+            raise ValueError(f"val.augment resizes to {data.size} but the model takes {size} x {size} images")
+    else:
+        raise ValueError(f"Dataset loading error: {root} is neither a synthetic:// URL nor a local directory (HuggingFace "
+                         "dataset names need the network and are not built)")
     extractor = FeatureExtractor(model)
     faiss_index = index(extractor, data.gallery_batches(gallery_limit), device, logger=logger)
     cutoffs = list(data_cfg["val"]["metrics"]["cutoffs"])
@@ -55,7 +63,11 @@ def valuate(model, data_cfg: dict, device, logger=None, vis: bool = False, image
         logger.console("Searching ...")
     scores, ids = faiss_index.search_device(q, cutoffs[-1], resolve_overflow=True)
     q_label, g_label = data.query_labels(query_limit), data.gallery_labels(gallery_limit)
-    if vis:  # (retrieval results, scores, ground truths, queries) like :279
+    if vis:  # (retrieval results, scores, ground truths, queries) like :279 — file lists for a folder root, label tensors otherwise
+        if hasattr(data, "gallery_files"):
+            files = data.gallery_files[:gallery_limit]
+            results = [[files[j] for j in row if j != -1] for row in ids.cpu().tolist()]
+            return results, scores.cpu().numpy(), data.positives(query_limit), data.query_files[:query_limit]
         return ids, scores, g_label, q_label
     out = compute_metrics(ids, scores, q_label, g_label, metrics=data_cfg["val"]["metrics"]["metrics"], cutoffs=cutoffs)
     return {k: float(v) for k, v in out.items()}

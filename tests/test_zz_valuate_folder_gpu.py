@@ -1,0 +1,70 @@
+"""`valuate` on an image FOLDER in the reference's CBIRDatasets layout (engine/cbir/folder.py): files -> host decode -> device
+val transforms -> embed -> index -> search -> metrics, against the same computation assembled by hand from the oracle's
+preprocessing of the same files (bit-exact inputs => identical embeddings => identical metrics), plus the vis=True return."""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from conftest import not_yet_run_on_gpu
+from oracle import preprocess as P
+
+pytestmark = pytest.mark.gpu
+
+SIZE = 64
+AUGMENT = [{"resize_and_padding": {"size": SIZE, "training": False}}, {"to_tensor": "no_params"},
+           {"normalize": {"mean": [0.485, 0.456, 0.406], "std": [0.229, 0.224, 0.225]}}]
+
+
+def make_tree(root, n_ids=6, per_gallery=4, per_query=2):
+    from PIL import Image
+    rng = np.random.default_rng(11)
+    for i in range(n_ids):
+        proto = rng.integers(0, 256, (8, 8, 3), dtype=np.uint8)  # every identity = one low-resolution pattern + noise
+        for split, per in (("gallery", per_gallery), ("query", per_query)):
+            d = os.path.join(root, split, f"id_{i:02d}")
+            os.makedirs(d)
+            for j in range(per):
+                w, h = int(rng.integers(40, 120)), int(rng.integers(40, 120))
+                img = np.asarray(Image.fromarray(proto).resize((w, h), Image.NEAREST)).astype(np.int16)
+                img = np.clip(img + rng.integers(-20, 21, img.shape), 0, 255).astype(np.uint8)
+                Image.fromarray(img).save(os.path.join(d, f"img_{j}.png"))
+
+
+@not_yet_run_on_gpu
+def test_valuate_on_an_image_folder(lib, tmp_path):
+    from engine.cbir.evaluation import compute_metrics, valuate
+    from engine.cbir.folder import CBIRFolderData, read_image
+    from visiondk_b200.backbone import TimmWrapper
+    from visiondk_b200.retrieval import FlatIPIndex
+    make_tree(str(tmp_path))
+    model = TimmWrapper("toy", 32, SIZE, pretrained=False, depths=(1, 1, 1, 1), dims=(64, 64, 128, 128)).cuda().eval()
+    metrics_cfg = {"metrics": ["mrr", "recall", "precision", "auc", "ndcg"], "cutoffs": [1, 3, 5]}
+    data_cfg = {"root": str(tmp_path), "nw": 2, "val": {"bs": 5, "augment": AUGMENT, "metrics": metrics_cfg}}
+    got = valuate(model, data_cfg, "cuda", image_size=SIZE)
+    assert {k.split("@")[0] for k in got} == {"MRR", "Recall", "Precision", "AUC", "nDCG"} and len(got) == 13
+    assert all(0.0 <= v <= 1.0 or np.isnan(v) for v in got.values())
+
+    # the same evaluation assembled by hand: oracle preprocessing on the host, same batch size
+    data = CBIRFolderData(str(tmp_path), AUGMENT, 5, "cuda")
+
+    def embed(files):
+        out = []
+        for a in range(0, len(files), 5):
+            x = np.stack([P.resize_pad_normalize(read_image(f), SIZE, data.mean, data.std) for f in files[a:a + 5]])
+            out.append(model.embed(torch.from_numpy(x).cuda(), l2_normalize=True))
+        return torch.cat(out)
+
+    index = FlatIPIndex(32, "cuda")
+    index.add(embed(data.gallery_files))
+    scores, ids = index.search_device(embed(data.query_files), 5, resolve_overflow=True)
+    want = compute_metrics(ids, scores, data.query_labels(), data.gallery_labels(), metrics=metrics_cfg["metrics"],
+                           cutoffs=metrics_cfg["cutoffs"])
+    np.testing.assert_equal({k: float(v) for k, v in want.items()}, got)
+
+    results, vis_scores, positives, queries = valuate(model, data_cfg, "cuda", vis=True, image_size=SIZE)
+    assert queries == data.query_files and positives == data.positives()
+    assert len(results) == len(queries) and all(len(r) == 5 and all(f in data.gallery_files for f in r) for r in results)
+    assert np.array_equal(vis_scores, scores.cpu().numpy())
+    assert results == [[data.gallery_files[j] for j in row] for row in ids.cpu().tolist()]

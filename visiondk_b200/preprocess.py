@@ -33,6 +33,7 @@ class ImagePreprocessor:
         self._pinned = None
         self._dev = None
         self._ws = None
+        self._copied = None  # event after the last host->device copy out of the pinned buffer
 
     def __call__(self, images: Sequence[np.ndarray]) -> torch.Tensor:
         lib = _lib.load()
@@ -46,6 +47,8 @@ class ImagePreprocessor:
                 raise ValueError(f"image {i}: expected uint8 [h, w, 3] (RGB), got {im.dtype} {im.shape}")
             descs[i].offset, descs[i].width, descs[i].height = off, im.shape[1], im.shape[0]
             off += (im.shape[0] * im.shape[1] * 3 + 255) // 256 * 256
+        if self._copied is not None:  # the previous call's asynchronous copy still reads the pinned buffer refilled below
+            self._copied.synchronize()
         if self._pinned is None or self._pinned.numel() < off:
             self._pinned = torch.empty((off,), dtype=torch.uint8, pin_memory=True)
             self._dev = torch.empty((off,), dtype=torch.uint8, device=self.device)
@@ -55,6 +58,8 @@ class ImagePreprocessor:
             host[o:o + im.size] = np.ascontiguousarray(im).reshape(-1)
         with torch.cuda.device(self.device):
             self._dev[:off].copy_(self._pinned[:off], non_blocking=True)
+            self._copied = torch.cuda.Event()
+            self._copied.record()
             need = lib.vdk_preprocess_workspace_bytes(descs, n, self.size)
             if need == 0:
                 raise RuntimeError("vdk_preprocess_workspace_bytes: " + _lib.last_error())
