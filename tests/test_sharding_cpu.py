@@ -128,3 +128,26 @@ def test_rank_sketch_protocol_in_numpy_on_local_shards(world, clustered):
     assert kept >= nq * k  # nothing needed was dropped ...
     if world == 8 and not clustered:
         assert kept <= 3 * nq * k  # ... and little else survives (each shard alone would keep its own k: 8 x)
+
+
+def test_memmap_store_is_read_shard_by_shard(tmp_path):
+    """visiondk_b200.cbir.memmap_shard: every rank maps only its rows of the reference's raw [N, D] embedding file
+    (engine/cbir/evaluation.py:124-152); the shards tile the file exactly, with the ids the sharded search assigns."""
+    from visiondk_b200.cbir import memmap_shard
+    rng = np.random.default_rng(1)
+    for dtype in (np.float16, np.float32):
+        emb = rng.standard_normal((1001, 24)).astype(dtype)
+        path = str(tmp_path / f"gallery.{np.dtype(dtype).name}")
+        mm = np.memmap(path, shape=emb.shape, mode="w+", dtype=dtype)
+        mm[:] = emb
+        mm.flush()
+        for world in (1, 2, 3, 8):
+            rows = []
+            for r in range(world):
+                view, lo, n = memmap_shard(path, 24, dtype, r, world)
+                assert n == 1001 and (lo, lo + len(view)) == sharding.shard_bounds(1001, world, r)
+                assert np.array_equal(view, emb[lo:lo + len(view)])
+                rows.append(np.asarray(view))
+            assert np.array_equal(np.concatenate(rows), emb)
+    with pytest.raises(ValueError, match="whole number"):
+        memmap_shard(path, 25, np.float32)

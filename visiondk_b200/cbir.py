@@ -10,6 +10,7 @@ face_model.py:140), and the faiss objects are replaced by visiondk_b200.retrieva
 """
 from __future__ import annotations
 
+import os
 from typing import Optional
 
 import numpy as np
@@ -105,16 +106,39 @@ class FeatureExtractor:
         return np.concatenate([h.numpy() for h in host_chunks], axis=0)
 
 
+def memmap_shard(path: str, feat_dim: int, dtype=np.float16, rank: int = 0, world: int = 1):
+    """Rows of the reference's raw embedding store (engine/cbir/evaluation.py:124-152: `[N, feat_dim]`, no header) that belong to
+    `rank` of `world` under the sharded search's contiguous row split -> (np.memmap view [n_local, feat_dim], first_row, N).
+    Only this rank's byte range of the file is ever touched (a 1 M x 512 fp16 store: 128 MB per rank on 8 GPUs instead of 1 GB)."""
+    from .sharding import shard_bounds
+    item = np.dtype(dtype).itemsize
+    size = os.path.getsize(path)
+    if feat_dim <= 0 or size % (item * feat_dim) != 0:
+        raise ValueError(f"{path}: {size} bytes is not a whole number of {feat_dim}-wide {np.dtype(dtype).name} rows")
+    n = size // (item * feat_dim)
+    lo, hi = shard_bounds(n, world, rank)
+    view = np.memmap(path, mode="r", dtype=dtype, offset=lo * feat_dim * item, shape=(hi - lo, feat_dim))
+    return view, lo, n
+
+
 def index(extractor: FeatureExtractor, gallery_dataloader, device, logger=None, index_factory: str = "Flat",
           memmap_feat_dim: Optional[int] = None, memmap_dtype=np.float16, memmap_save_path: Optional[str] = None,
-          memmap_load_embedding: bool = False) -> FlatIPIndex:
+          memmap_load_embedding: bool = False, shard: Optional[tuple] = None) -> FlatIPIndex:
     """engine/cbir/evaluation.py:106-169: encode the gallery, build the flat inner-product index (resident on
-    `device`), optionally save / load the embeddings as a raw np.memmap (:124-152)."""
+    `device`), optionally save / load the embeddings as a raw np.memmap (:124-152).
+    shard=(rank, world) with memmap_load_embedding: this rank loads only ITS rows of the store and the index carries their
+    global ids (`id_offset`) — the per-rank index visiondk_b200.retrieval.sharded_flat_search expects (BASELINE config 4)."""
     if index_factory != "Flat":
         raise ValueError("only the 'Flat' (exact inner product) index of the reference's CBIR path is built")
     device = torch.device(device)
+    id_offset = 0
+    if shard is not None and not memmap_load_embedding:
+        raise ValueError("shard=(rank, world) selects rows of a saved embedding store: it needs memmap_load_embedding=True")
     if memmap_load_embedding:
-        emb = np.memmap(memmap_save_path, mode="r", dtype=memmap_dtype).reshape(-1, memmap_feat_dim)
+        if shard is not None:
+            emb, id_offset, _ = memmap_shard(memmap_save_path, memmap_feat_dim, memmap_dtype, shard[0], shard[1])
+        else:
+            emb = np.memmap(memmap_save_path, mode="r", dtype=memmap_dtype).reshape(-1, memmap_feat_dim)
         emb = torch.from_numpy(np.ascontiguousarray(emb, dtype=np.float32)).to(device)
     else:
         emb = extractor.extract_cbir_device(gallery_dataloader, device)
@@ -125,7 +149,7 @@ def index(extractor: FeatureExtractor, gallery_dataloader, device, logger=None, 
             mm = np.memmap(memmap_save_path, shape=host.shape, mode="w+", dtype=host.dtype)
             mm[:] = host
             mm.flush()
-    faiss_index = FlatIPIndex(emb.shape[-1], device)
+    faiss_index = FlatIPIndex(emb.shape[-1], device, id_offset=id_offset)
     if logger is not None:
         logger.console("Adding embeddings...")
     faiss_index.train(emb)
