@@ -68,3 +68,22 @@ def test_valuate_on_an_image_folder(lib, tmp_path):
     assert len(results) == len(queries) and all(len(r) == 5 and all(f in data.gallery_files for f in r) for r in results)
     assert np.array_equal(vis_scores, scores.cpu().numpy())
     assert results == [[data.gallery_files[j] for j in row] for row in ids.cpu().tolist()]
+
+
+@not_yet_run_on_gpu
+def test_extract_face_names_and_features(lib):
+    """FeatureExtractor.extract_face (models/faceX/face_model.py:93-118): keys "<parent dir>/<file>", values = the rows
+    extract_cbir_device returns for the same tensors."""
+    from visiondk_b200.backbone import TimmWrapper
+    from visiondk_b200.cbir import FeatureExtractor
+    model = TimmWrapper("toy", 32, SIZE, pretrained=False, depths=(1, 1, 1, 1), dims=(64, 64, 128, 128)).cuda().eval()
+    gen = torch.Generator().manual_seed(3)
+    batches = [torch.randn(n, 3, SIZE, SIZE, generator=gen) for n in (4, 3)]
+    paths = [[f"/data/lfw/person_{i}/img_{j}.jpg" for j in range(b.shape[0])] for i, b in enumerate(batches)]
+    ext = FeatureExtractor(model)
+    got = ext.extract_face([(None, b, p) for b, p in zip(batches, paths)], "cuda")
+    assert list(got) == [f"person_{i}/img_{j}.jpg" for i, b in enumerate(batches) for j in range(b.shape[0])]
+    want = ext.extract_cbir_device(batches, "cuda").cpu().numpy()
+    assert np.array_equal(np.stack(list(got.values())), want)
+    assert np.allclose(np.linalg.norm(want, axis=1), 1.0, atol=1e-5)
+    assert ext.extract_face([], "cuda") == {}

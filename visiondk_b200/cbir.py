@@ -1,7 +1,7 @@
 """CBIR eval path on B200: extract -> index -> search (Seams 5 and 6).
 
 Mirrors, by name and argument meaning:
-  FeatureExtractor.extract_cbir   models/faceX/face_model.py:120-144
+  FeatureExtractor.extract_cbir   models/faceX/face_model.py:120-144   (.extract_face :93-118)
   index(...)                      engine/cbir/evaluation.py:106-169   (cbir_eval.py:35-96)
   search(...)                     engine/cbir/evaluation.py:171-200   (cbir_eval.py:98-122)
 with the arithmetic on the sm_100a kernels: the backbone's `embed()` fuses F.normalize into the neck epilogue,
@@ -75,6 +75,26 @@ class FeatureExtractor:
         if not feats:
             return torch.empty((0, model.feat_dim), dtype=torch.float32, device=device)
         return torch.cat(feats, dim=0)
+
+    @torch.no_grad()
+    def extract_face(self, dataloader, device) -> dict:
+        """models/faceX/face_model.py:93-118: `dataloader` yields (images, tensors, file_realpaths) (ImageDatasets.collate_fn,
+        dataset/basedataset.py:455-458); returns {"<parent dir>/<file name>": L2-normalised float32 feature} — the
+        `image_name2feature` dict the face evaluator (engine/faceX/evaluation.py:34-113) looks pairs up in."""
+        device = torch.device(device)
+        if device.type != "cuda":
+            raise RuntimeError("visiondk_b200 extraction runs on CUDA (sm_100a) only; there is no CPU fallback")
+        model = self.model
+        model.eval()
+        model.to(device)
+        names, feats = [], []
+        for _, tensors, file_realpaths in dataloader:
+            feats.append(model.embed(tensors.to(device, non_blocking=True), l2_normalize=True))
+            names += [os.path.join(os.path.basename(os.path.dirname(p)), os.path.basename(p)) for p in file_realpaths]
+        if not feats:
+            return {}
+        host = torch.cat(feats, dim=0).cpu().numpy()  # one device->host copy for the whole set (the reference copies per batch)
+        return {name: host[i] for i, name in enumerate(names)}
 
     @torch.no_grad()
     def extract_cbir(self, dataloader, device) -> np.ndarray:
