@@ -47,6 +47,19 @@ def read_image(path: str) -> np.ndarray:
     return np.asarray(img, dtype=np.uint8)
 
 
+def decode_batches(files: Sequence[str], batch: int, nw: int = 8) -> Iterable[List[np.ndarray]]:
+    """Lists of decoded images, `batch` files at a time, decoded on `nw` host threads one batch ahead of the consumer."""
+    chunks = [files[a:a + batch] for a in range(0, len(files), batch)]
+    if not chunks:
+        return
+    with ThreadPoolExecutor(max(1, int(nw))) as pool:
+        pending = [pool.submit(read_image, f) for f in chunks[0]]
+        for j in range(len(chunks)):
+            nxt = [pool.submit(read_image, f) for f in chunks[j + 1]] if j + 1 < len(chunks) else []
+            yield [p.result() for p in pending]
+            pending = nxt
+
+
 class CBIRFolderData:
     """Query / gallery file lists, identity labels and device batches of a local CBIR root (same surface as SyntheticFaceData)."""
 
@@ -97,16 +110,7 @@ class CBIRFolderData:
 
     # ---- batches ----
     def decoded_batches(self, files: Sequence[str]) -> Iterable[List[np.ndarray]]:
-        """Lists of decoded images, `batch` files at a time, decoded on `nw` host threads one batch ahead of the consumer."""
-        chunks = [files[a:a + self.batch] for a in range(0, len(files), self.batch)]
-        if not chunks:
-            return
-        with ThreadPoolExecutor(self.nw) as pool:
-            pending = [pool.submit(read_image, f) for f in chunks[0]]
-            for j in range(len(chunks)):
-                nxt = [pool.submit(read_image, f) for f in chunks[j + 1]] if j + 1 < len(chunks) else []
-                yield [p.result() for p in pending]
-                pending = nxt
+        return decode_batches(files, self.batch, self.nw)
 
     def _device_batches(self, files: Sequence[str]) -> Iterable[torch.Tensor]:
         from visiondk_b200.preprocess import ImagePreprocessor

@@ -18,6 +18,7 @@ import torch.distributed as dist
 import yaml
 
 from engine.cbir.evaluation import valuate as valuate_cbir
+from engine.faceX.evaluation import valuate as valuate_face
 from engine.synthetic import SyntheticFaceData, is_synthetic
 from visiondk_b200.train import FaceTrainer, FaceTrainingModel
 
@@ -181,13 +182,19 @@ class CenterProcessor:
         return trainer
 
     def save_and_eval(self, trainer: FaceTrainer, epoch: int, steps_per_epoch: int):
-        """engine/procedure/train.py:244-278: evaluate the EMA backbone (valuate_cbir -> {metric: float}), write Epoch_N.pt with
+        """engine/procedure/train.py:244-278: evaluate the EMA backbone (face: pair verification -> Val_mean / Val_std; cbir:
+        valuate_cbir -> {metric: float}), write Epoch_N.pt with
         the reference's key set, plus the entries a faithful resume needs ('head', 'ema_head', momentum buffers)."""
         src = trainer.ema if trainer.ema is not None else self.model
         ema_backbone = src.trainingwrapper["backbone"]
-        metrics = valuate_cbir(ema_backbone, self.data_cfg, self.device, None, image_size=self.model_cfg["image_size"],
-                               gallery_limit=getattr(self.opt, "eval_gallery", None) or 4096,
-                               query_limit=getattr(self.opt, "eval_queries", None) or 256)
+        if self.task == "face":  # train.py:246-253: 10-fold pair verification of the EMA backbone
+            mean, std = valuate_face(ema_backbone, self.data_cfg, self.device, image_size=self.model_cfg["image_size"],
+                                     n_pairs=getattr(self.opt, "eval_pairs", None) or 6000)
+            metrics = {"Val_mean": float(mean), "Val_std": float(std)}
+        else:  # train.py:254-260
+            metrics = valuate_cbir(ema_backbone, self.data_cfg, self.device, None, image_size=self.model_cfg["image_size"],
+                                   gallery_limit=getattr(self.opt, "eval_gallery", None) or 4096,
+                                   query_limit=getattr(self.opt, "eval_queries", None) or 256)
         fitness = {"fitness": metrics, "checkpoint": f"Epoch_{epoch + 1}.pt"}
         out_dir = Path(self.project or "run/exp")
         out_dir.mkdir(parents=True, exist_ok=True)

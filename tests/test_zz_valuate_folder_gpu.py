@@ -87,3 +87,51 @@ def test_extract_face_names_and_features(lib):
     assert np.array_equal(np.stack(list(got.values())), want)
     assert np.allclose(np.linalg.norm(want, axis=1), 1.0, atol=1e-5)
     assert ext.extract_face([], "cuda") == {}
+
+
+@not_yet_run_on_gpu
+def test_face_task_pair_verification(lib, tmp_path):
+    """engine/faceX/evaluation.py::valuate: (a) synthetic:// root -> a (mean, std) in range that beats chance on the
+    identity-structured images; (b) a pair file over <root>/val/ images == the same protocol assembled by hand."""
+    from PIL import Image
+    from engine.faceX.evaluation import valuate as valuate_face
+    from engine.cbir.folder import read_image
+    from visiondk_b200.backbone import TimmWrapper
+    from visiondk_b200.metrics import face_verification_accuracy
+    model = TimmWrapper("toy", 32, SIZE, pretrained=False, depths=(1, 1, 1, 1), dims=(64, 64, 128, 128)).cuda().eval()
+    cfg = {"root": "synthetic://cbir?ids=50&per_id=4&queries=10&noise=0.3", "nw": 2, "val": {"bs": 50, "augment": AUGMENT}}
+    mean, std = valuate_face(model, cfg, "cuda", image_size=SIZE, n_pairs=600)
+    assert 0.5 < mean <= 1.0 and 0.0 <= std < 0.2
+
+    rng = np.random.default_rng(5)
+    rel = []
+    for i in range(8):
+        proto = rng.integers(0, 256, (8, 8, 3), dtype=np.uint8)
+        os.makedirs(tmp_path / "val" / f"p{i}")
+        for j in range(3):
+            w, h = int(rng.integers(40, 100)), int(rng.integers(40, 100))
+            img = np.asarray(Image.fromarray(proto).resize((w, h), Image.NEAREST)).astype(np.int16)
+            Image.fromarray(np.clip(img + rng.integers(-25, 26, img.shape), 0, 255).astype(np.uint8)).save(tmp_path / "val" / f"p{i}" / f"{j}.png")
+            rel.append(f"p{i}/{j}.png")
+    pairs = []
+    for n in range(40):  # 10 folds of 4: two genuine, two impostor
+        i = int(rng.integers(0, 8))
+        if n % 4 < 2:
+            a, b = rng.choice(3, 2, replace=False)
+            pairs.append((f"p{i}/{a}.png", f"p{i}/{b}.png", 1))
+        else:
+            o = int((i + 1 + rng.integers(0, 7)) % 8)
+            pairs.append((f"p{i}/{int(rng.integers(0, 3))}.png", f"p{o}/{int(rng.integers(0, 3))}.png", 0))
+    (tmp_path / "pairs.txt").write_text("\n".join(f"{a} {b} {l}" for a, b, l in pairs) + "\n")
+    cfg = {"root": str(tmp_path), "nw": 2, "val": {"bs": 7, "pair_txt": str(tmp_path / "pairs.txt"), "augment": AUGMENT}}
+    got = valuate_face(model, cfg, "cuda", image_size=SIZE)
+
+    used = sorted({p for a, b, _ in pairs for p in (a, b)})
+    feats = {}
+    for a in range(0, len(used), 7):  # same batches as the loader: distinct images in np.unique order, 7 at a time
+        x = np.stack([P.resize_pad_normalize(read_image(str(tmp_path / "val" / r)), SIZE) for r in used[a:a + 7]])
+        f = model.embed(torch.from_numpy(x).cuda(), l2_normalize=True)
+        feats.update({r: f[i] for i, r in enumerate(used[a:a + 7])})
+    scores = torch.stack([(feats[a] * feats[b]).sum() for a, b, _ in pairs])
+    want = face_verification_accuracy(scores, torch.tensor([l for _, _, l in pairs], device="cuda"))
+    assert got == want
