@@ -51,3 +51,15 @@ def test_reference_yaml_parses_unchanged_and_passes_the_schema(name, task):
                                                                                    "feat_dim": head["feat_dim"]}}
     m = BackboneFactory(cfgs["model"]["backbone"]).get_backbone()
     assert m.model_name == "convnext_base" and m.feat_dim == head["feat_dim"]
+
+
+def test_shipped_face_config_passes_the_schema():
+    """configs/faceX/face_convnext_b200.yaml: the face task (BASELINE config 2) with the reference's val transform list."""
+    from engine.cbir.folder import parse_val_augment
+    here = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    cfgs = yaml_load(os.path.join(here, "configs", "faceX", "face_convnext_b200.yaml"))
+    check("face", cfgs)
+    assert cfgs["model"]["task"] == "face" and "arcface" in cfgs["model"]["head"]
+    assert parse_val_augment(cfgs["data"]["val"]["augment"]) == (224, (0.485, 0.456, 0.406), (0.229, 0.224, 0.225))
+    with pytest.raises(ValueError):
+        check("cbir", cfgs)
