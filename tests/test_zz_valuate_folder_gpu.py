@@ -127,11 +127,13 @@ def test_face_task_pair_verification(lib, tmp_path):
     got = valuate_face(model, cfg, "cuda", image_size=SIZE)
 
     used = sorted({p for a, b, _ in pairs for p in (a, b)})
-    feats = {}
+    chunks = []
     for a in range(0, len(used), 7):  # same batches as the loader: distinct images in np.unique order, 7 at a time
         x = np.stack([P.resize_pad_normalize(read_image(str(tmp_path / "val" / r)), SIZE) for r in used[a:a + 7]])
-        f = model.embed(torch.from_numpy(x).cuda(), l2_normalize=True)
-        feats.update({r: f[i] for i, r in enumerate(used[a:a + 7])})
-    scores = torch.stack([(feats[a] * feats[b]).sum() for a, b, _ in pairs])
+        chunks.append(model.embed(torch.from_numpy(x).cuda(), l2_normalize=True))
+    feats, row = torch.cat(chunks), {r: i for i, r in enumerate(used)}
+    ia = torch.tensor([row[a] for a, _, _ in pairs], device="cuda")
+    ib = torch.tensor([row[b] for _, b, _ in pairs], device="cuda")
+    scores = (feats[ia] * feats[ib]).sum(dim=1)
     want = face_verification_accuracy(scores, torch.tensor([l for _, _, l in pairs], device="cuda"))
     assert got == want
