@@ -451,7 +451,7 @@ def sharded_flat_search(index: "FlatIPIndex", q_local: torch.Tensor, q_sizes, k:
             comm.all_reduce_max_(t)
             index._shard_rows_max = (index.ntotal, int(t.item()))
         schedule = shard_schedule(index._shard_rows_max[1], world, k)
-    ex = _Exchange(schedule, comm, k)
+    ex = _Exchange(schedule, comm, k) if world > 1 else None  # one shard: the plain vdk_ip_topk call, nothing to exchange
     q_all = sharding.all_gather_rows(q_local, list(q_sizes)) if dist_comm else q_local
     s, i = index.search_device(q_all, k, resolve_overflow=not defer_check, exchange=ex)
     if world == 1:
